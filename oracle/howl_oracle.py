@@ -1,0 +1,368 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the howl hot path.
+
+A restatement (not a copy) of the arithmetic of castorini/howl's per-batch hot path.
+Citations are ``file:line`` under ``/root/reference`` (howl @ 4ba5f42); the arithmetic that
+lives in third-party code (torchaudio 0.10 pinned / 2.11 here, torch 1.10.1 pinned / 2.11 here)
+is restated from its published formulae.
+
+Parity pinning: the reference's own tests hold NO golden vectors for this path,
+so this oracle is pinned against outputs of the reference itself, generated in the build
+container by ``oracle/make_golden.py`` (imports /root/reference read-only) and committed under
+``tests/golden/``.  ``tests/test_oracle_golden.py`` checks every function here against them.
+
+Two flavours of the frontend are provided:
+  * ``*_f32``  -- float32 torch-CPU ops in the reference's operation order (the parity oracle);
+  * ``*_f64``  -- an independent float64 numpy restatement (tolerance calibration).
+
+Nothing in ``howl_b200`` may import this module.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------------------------
+# constants of the reference configuration (howl/settings.py:27-35)
+# ----------------------------------------------------------------------------------------------
+SAMPLE_RATE = 16000
+N_FFT = 512
+HOP = 200
+N_FREQS = N_FFT // 2 + 1
+LOG_EPS = 1e-7  # howl/data/transform/transform.py:275
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+RES8_MAPS = 45  # howl/model/cnn.py:110
+RES8_LAYERS = 6
+RES8_POOL = (3, 4)  # howl/model/cnn.py:109
+
+
+# ----------------------------------------------------------------------------------------------
+# frame-index arithmetic (integer; must be bit exact)
+# ----------------------------------------------------------------------------------------------
+def num_frames(num_samples: int, hop: int = HOP) -> int:
+    """Frames produced by ``torch.stft(center=True)``: 1 + floor(T / hop)."""
+    return 1 + num_samples // hop
+
+
+def compute_lengths(lengths: np.ndarray, win: int = N_FFT, hop: int = HOP) -> np.ndarray:
+    """``StandardAudioTransform.compute_lengths`` -- howl/data/transform/transform.py:290-296.
+
+    floor_div(len - win, hop) + 1 as int64 (python floor semantics for negatives).
+    """
+    lengths = np.asarray(lengths, dtype=np.int64)
+    return np.floor_divide(lengths - win, hop) + 1
+
+
+# ----------------------------------------------------------------------------------------------
+# filterbanks
+# ----------------------------------------------------------------------------------------------
+def _triangles(all_freqs: torch.Tensor, f_pts: torch.Tensor) -> torch.Tensor:
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.clamp(torch.minimum(down, up), min=0.0)
+
+
+def mel_filterbank(n_mels: int, sample_rate: int = SAMPLE_RATE, n_freqs: int = N_FREQS) -> torch.Tensor:
+    """HTK mel triangles ``fb[n_freqs, n_mels]`` of ``torchaudio.transforms.MelSpectrogram`` defaults.
+
+    Reference call site howl/data/transform/transform.py:249-254 (f_min=0, f_max=sr/2, norm=None,
+    mel_scale='htk'); formula SURVEY App. A.1 item 4.  float32 torch ops in the published order.
+    """
+    f_max = float(sample_rate // 2)
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + 0.0 / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + f_max / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    return _triangles(all_freqs, f_pts)
+
+
+def vtlp_filterbank(
+    alpha: float, n_mels: int, sample_rate: int = SAMPLE_RATE, n_freqs: int = N_FREQS, f_hi: float = 4800
+) -> torch.Tensor:
+    """VTLP-warped filterbank -- howl/data/transform/transform.py:373-410 with training=True.
+
+    The reference warps ``f_pts`` in place and evaluates the second mask on the already-scaled
+    tensor (``:397-401``); that sequencing is reproduced literally.
+    """
+    s = sample_rate
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_max = 2595.0 * math.log10(1.0 + (float(sample_rate // 2) / 700.0))
+    m_pts = torch.linspace(0.0, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    thr = f_hi * min(alpha, 1) / alpha
+    lo = f_pts <= thr
+    f_pts = torch.where(lo, f_pts * alpha, f_pts)  # step 1 (scales the low band)
+    hi = f_pts > thr  # step 2 mask is taken AFTER step 1
+    warped = s / 2 - ((s / 2 - f_hi * min(alpha, 1)) / (s / 2 - f_hi * min(alpha, 1) / alpha)) * (s / 2 - f_pts)
+    f_pts = torch.where(hi, warped, f_pts)
+    return _triangles(all_freqs, f_pts)
+
+
+def filterbank_ranges(fb: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """First / one-past-last non-zero frequency row of every filterbank column (host helper)."""
+    fb = np.asarray(fb)
+    lo = np.zeros(fb.shape[1], dtype=np.int32)
+    hi = np.zeros(fb.shape[1], dtype=np.int32)
+    for m in range(fb.shape[1]):
+        nz = np.nonzero(fb[:, m])[0]
+        if nz.size:
+            lo[m], hi[m] = nz[0], nz[-1] + 1
+    return lo, hi
+
+
+# ----------------------------------------------------------------------------------------------
+# frontend, float32 (parity oracle)
+# ----------------------------------------------------------------------------------------------
+def power_spectrogram_f32(pcm: torch.Tensor) -> torch.Tensor:
+    """|STFT|^2 ``[B, 257, F]`` -- torchaudio ``spectrogram``.
+
+    center=True reflect pad 256, periodic Hann(512), hop 200, onesided, power 2, no normalisation.
+    """
+    window = torch.hann_window(N_FFT, periodic=True, dtype=torch.float32)
+    spec = torch.stft(
+        pcm.float(), N_FFT, hop_length=HOP, win_length=N_FFT, window=window, center=True,
+        pad_mode="reflect", normalized=False, onesided=True, return_complex=True,
+    )
+    return spec.abs().pow(2.0)
+
+
+def log_mel_f32(pcm: torch.Tensor, fb: torch.Tensor) -> torch.Tensor:
+    """``log(mel + 1e-7)`` ``[B, M, F]`` -- transform.py:275 + torchaudio MelScale (App. A.1 item 5-6)."""
+    power = power_spectrogram_f32(pcm)
+    mel = torch.matmul(power.transpose(-1, -2), fb).transpose(-1, -2)
+    return mel.add(LOG_EPS).log().contiguous()
+
+
+def deltas_f32(x: torch.Tensor) -> torch.Tensor:
+    """``torchaudio.functional.compute_deltas`` (win_length 5, replicate pad) along the last axis.
+
+    d[t] = (-2 x[t-2] - x[t-1] + x[t+1] + 2 x[t+2]) / 10   (SURVEY App. A.1 item 7).
+    """
+    shape = x.shape
+    flat = x.reshape(1, -1, shape[-1])
+    padded = F.pad(flat, (2, 2), mode="replicate")
+    kernel = torch.arange(-2, 3, dtype=x.dtype).repeat(flat.shape[1], 1, 1)
+    out = F.conv1d(padded, kernel, groups=flat.shape[1]) / 10.0
+    return out.reshape(shape)
+
+
+def standard_audio_transform_f32(pcm: torch.Tensor, fb: Optional[torch.Tensor] = None, n_mels: int = 40) -> torch.Tensor:
+    """``StandardAudioTransform.forward`` in eval mode (or train mode given the drawn ``fb``).
+
+    howl/data/transform/transform.py:271-280: stack(log-mel, delta, delta-delta) ``[B, 3, M, F]``.
+    """
+    if fb is None:
+        fb = mel_filterbank(n_mels)
+    lm = log_mel_f32(pcm, fb)
+    d = deltas_f32(lm)
+    dd = deltas_f32(d)
+    return torch.stack((lm, d, dd), 1)
+
+
+def zmuv_std(mean: torch.Tensor, mean2: torch.Tensor) -> torch.Tensor:
+    """howl/data/transform/operator.py:141-143."""
+    return (mean2 - mean ** 2).sqrt()
+
+
+def zmuv_forward(x: torch.Tensor, mean: torch.Tensor, mean2: torch.Tensor) -> torch.Tensor:
+    """howl/data/transform/operator.py:145-146."""
+    return (x - mean) / zmuv_std(mean, mean2)
+
+
+def zmuv_update(total, mean, mean2, data: torch.Tensor):
+    """howl/data/transform/operator.py:126-135 (mask=None branch). Returns new (total, mean, mean2)."""
+    n = data.numel()
+    new_mean = (data.sum() + mean * total) / (total + n)
+    new_mean2 = ((data ** 2).sum() + mean2 * total) / (total + n)
+    return total + n, new_mean, new_mean2
+
+
+def spec_augment_apply(x: torch.Tensor, rects: Sequence[Tuple[int, int, int, int]]) -> torch.Tensor:
+    """Zero the rectangles drawn by ``SpecAugmentTransform`` (transform.py:310-326).
+
+    ``rects[b] = (f0, f_len, t0, t_len)`` -- the host draws (global ``random``) stay on the host;
+    a zero length means "no mask".  In place on ``x[B, C, M, F]``.
+    """
+    for b, (f0, fl, t0, tl) in enumerate(rects):
+        if fl > 0:
+            x[b, :, f0:f0 + fl] = 0
+        if tl > 0:
+            x[b, :, :, t0:t0 + tl] = 0
+    return x
+
+
+# ----------------------------------------------------------------------------------------------
+# frontend, float64 numpy (independent restatement)
+# ----------------------------------------------------------------------------------------------
+def log_mel_f64(pcm: np.ndarray, fb: np.ndarray) -> np.ndarray:
+    """float64 restatement of log-mel: explicit reflect pad, framing, Hann, rFFT, |.|^2, fb, log."""
+    pcm = np.asarray(pcm, dtype=np.float64)
+    fb = np.asarray(fb, dtype=np.float64)
+    b, t = pcm.shape
+    f = num_frames(t)
+    n = np.arange(N_FFT)
+    window = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / N_FFT)
+    idx = (np.arange(f)[:, None] * HOP - N_FFT // 2) + n[None, :]  # index into the unpadded clip
+    idx = np.where(idx < 0, -idx, idx)
+    idx = np.where(idx >= t, 2 * (t - 1) - idx, idx)
+    frames = pcm[:, idx] * window  # [B, F, 512]
+    power = np.abs(np.fft.rfft(frames, axis=-1)) ** 2  # [B, F, 257]
+    mel = power @ fb  # [B, F, M]
+    return np.log(mel + LOG_EPS).transpose(0, 2, 1)
+
+
+def deltas_f64(x: np.ndarray) -> np.ndarray:
+    xp = np.pad(x, [(0, 0)] * (x.ndim - 1) + [(2, 2)], mode="edge")
+    t = x.shape[-1]
+    return (-2 * xp[..., 0:t] - xp[..., 1:t + 1] + xp[..., 3:t + 3] + 2 * xp[..., 4:t + 4]) / 10.0
+
+
+def standard_audio_transform_f64(pcm: np.ndarray, fb: np.ndarray) -> np.ndarray:
+    lm = log_mel_f64(pcm, fb)
+    d = deltas_f64(lm)
+    return np.stack((lm, d, deltas_f64(d)), 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# res8 (howl/model/cnn.py:107-145), functional so that no nn.Module from the reference is needed
+# ----------------------------------------------------------------------------------------------
+def res8_param_shapes(num_labels: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    """state_dict order and shapes of the trainable tensors."""
+    shapes = [("conv0.weight", (RES8_MAPS, 1, 3, 3))]
+    for i in range(1, RES8_LAYERS + 1):
+        shapes.append((f"conv{i}.weight", (RES8_MAPS, RES8_MAPS, 3, 3)))
+    shapes.append(("output.weight", (num_labels, RES8_MAPS)))
+    shapes.append(("output.bias", (num_labels,)))
+    return shapes
+
+
+def res8_init(num_labels: int, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """PyTorch-default init (kaiming_uniform a=sqrt(5) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)))."""
+    g = torch.Generator().manual_seed(seed)
+    params: Dict[str, torch.Tensor] = {}
+    for name, shape in res8_param_shapes(num_labels):
+        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else RES8_MAPS
+        bound = 1.0 / math.sqrt(fan_in)
+        params[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return params
+
+
+def res8_bn_init() -> Dict[str, torch.Tensor]:
+    stats: Dict[str, torch.Tensor] = {}
+    for i in range(1, RES8_LAYERS + 1):
+        stats[f"bn{i}.running_mean"] = torch.zeros(RES8_MAPS)
+        stats[f"bn{i}.running_var"] = torch.ones(RES8_MAPS)
+        stats[f"bn{i}.num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+    return stats
+
+
+def res8_forward(
+    x: torch.Tensor,
+    params: Dict[str, torch.Tensor],
+    bn: Dict[str, torch.Tensor],
+    training: bool,
+    taps: Optional[Dict[str, torch.Tensor]] = None,
+) -> torch.Tensor:
+    """``Res8.forward`` -- howl/model/cnn.py:127-145.  ``x`` is ``[B, C>=1, M, F]`` (frontend layout).
+
+    ``bn`` running stats are updated in place when ``training`` (momentum 0.1, unbiased var),
+    exactly as ``nn.BatchNorm2d(affine=False)`` does.  ``taps`` (optional) receives intermediates.
+    """
+    x = x[:, :1].permute(0, 1, 3, 2).contiguous()  # (time, freq) -- cnn.py:128-129
+    old_x = None
+    for i in range(RES8_LAYERS + 1):
+        y = F.relu(F.conv2d(x, params[f"conv{i}.weight"], None, padding=1))
+        if i == 0:
+            y = F.avg_pool2d(y, RES8_POOL)
+            old_x = y
+        if i > 0 and i % 2 == 0:
+            x = y + old_x
+            old_x = x
+        else:
+            x = y
+        if taps is not None:
+            taps[f"u{i}"] = x
+        if i > 0:
+            if training:
+                bn[f"bn{i}.num_batches_tracked"] += 1
+            x = F.batch_norm(
+                x, bn[f"bn{i}.running_mean"], bn[f"bn{i}.running_var"], None, None,
+                training, BN_MOMENTUM, BN_EPS,
+            )
+    x = x.view(x.size(0), x.size(1), -1).mean(2)
+    if taps is not None:
+        taps["pooled"] = x
+    return F.linear(x, params["output.weight"], params["output.bias"])
+
+
+def adamw_step(
+    params: Dict[str, torch.Tensor], grads: Dict[str, torch.Tensor], m: Dict[str, torch.Tensor],
+    v: Dict[str, torch.Tensor], step: int, lr: float, weight_decay: float,
+    betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+) -> None:
+    """``torch.optim.AdamW`` single-tensor update restated; in place; ``step`` is 1-based."""
+    b1, b2 = betas
+    bc1 = 1.0 - b1 ** step
+    bc2 = 1.0 - b2 ** step
+    for k, p in params.items():
+        g = grads[k]
+        p.mul_(1.0 - lr * weight_decay)
+        m[k].mul_(b1).add_(g, alpha=1.0 - b1)
+        v[k].mul_(b2).addcmul_(g, g, value=1.0 - b2)
+        denom = (v[k].sqrt() / math.sqrt(bc2)).add_(eps)
+        p.addcdiv_(m[k], denom, value=-(lr / bc1))
+
+
+def res8_train_step(
+    feats: torch.Tensor, labels: torch.Tensor, params: Dict[str, torch.Tensor], bn: Dict[str, torch.Tensor],
+    m: Dict[str, torch.Tensor], v: Dict[str, torch.Tensor], step: int, lr: float, weight_decay: float,
+) -> Tuple[torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+    """One iteration of training/run/train.py:292-302 (frame objective): fwd, CE(mean), bwd, AdamW.
+
+    Returns (loss, logits, grads); ``params``/``bn``/``m``/``v`` are updated in place.
+    """
+    leaves = {k: p.detach().clone().requires_grad_(True) for k, p in params.items()}
+    logits = res8_forward(feats, leaves, bn, training=True)
+    loss = F.cross_entropy(logits, labels)
+    loss.backward()
+    grads = {k: leaves[k].grad.detach() for k in leaves}
+    with torch.no_grad():
+        adamw_step(params, grads, m, v, step, lr, weight_decay)
+    return loss.detach(), logits.detach(), grads
+
+
+def flatten(tensors: Dict[str, torch.Tensor], num_labels: int) -> torch.Tensor:
+    """Concatenate trainable tensors in state_dict order -> the flat layout of include/howl_b200.h."""
+    return torch.cat([tensors[name].reshape(-1) for name, _ in res8_param_shapes(num_labels)])
+
+
+def unflatten(flat: torch.Tensor, num_labels: int) -> Dict[str, torch.Tensor]:
+    out, off = {}, 0
+    for name, shape in res8_param_shapes(num_labels):
+        n = int(np.prod(shape))
+        out[name] = flat[off:off + n].reshape(shape).clone()
+        off += n
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# full hot path as the reference runs it (used for the CPU baseline and end-to-end parity)
+# ----------------------------------------------------------------------------------------------
+def hot_path_features(pcm: torch.Tensor, fb: torch.Tensor, zmean: torch.Tensor, zmean2: torch.Tensor) -> torch.Tensor:
+    """``zmuv_transform(audio_transform(batch.audio_data))`` -- training/run/train.py:289."""
+    return zmuv_forward(standard_audio_transform_f32(pcm, fb), zmean, zmean2)
+
+
+def synthetic_batch(batch: int, samples: int, num_labels: int, seed: int = 0):
+    """Synthetic inputs of SURVEY §8(d): speech-like RMS noise clamped to [-1, 1], uniform labels."""
+    g = torch.Generator().manual_seed(seed)
+    pcm = (torch.randn(batch, samples, generator=g) * 0.1).clamp_(-1, 1)
+    labels = torch.randint(0, num_labels, (batch,), generator=g)
+    return pcm, labels

@@ -1,0 +1,159 @@
+"""Pin the CPU oracle against outputs of the real reference (tests/golden, made by oracle/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import howl_oracle as O
+
+from conftest import GOLDEN
+
+RTOL = ATOL = 1e-4  # north_star tolerance (fp32), implemented as allclose per SURVEY §8(c)
+
+
+def test_filterbank_and_window_bit_exact(golden):
+    g = golden("frontend")
+    fb = O.mel_filterbank(40).numpy()
+    assert np.array_equal(fb, g["fb"])
+    assert (fb != 0).sum() == 493
+    w = torch.hann_window(512, periodic=True).numpy()
+    assert np.array_equal(w, g["window"])
+
+
+def test_compute_lengths_bit_exact(golden):
+    g = golden("frontend")
+    assert np.array_equal(O.compute_lengths(g["lengths_in"]), g["lengths_out"])
+    assert O.num_frames(8000) == 41 and O.num_frames(16000) == 81
+    assert O.compute_lengths([8000, 16000]).tolist() == [38, 78]
+
+
+def test_frontend_f32_matches_reference(golden):
+    g = golden("frontend")
+    fb = torch.from_numpy(g["fb"])
+    for tag in ("t8000", "t16000", "t4567", "t1000", "speech", "zeros"):
+        out = O.standard_audio_transform_f32(torch.from_numpy(g[f"{tag}_pcm"]), fb).numpy()
+        assert out.shape == g[f"{tag}_out"].shape
+        np.testing.assert_allclose(out, g[f"{tag}_out"], rtol=RTOL, atol=ATOL)
+        if f"{tag}_mels_only" in g:
+            np.testing.assert_allclose(out[:, 0], g[f"{tag}_mels_only"], rtol=RTOL, atol=ATOL)
+
+
+def test_frontend_f64_restatement_agrees(golden):
+    g = golden("frontend")
+    for tag in ("t8000", "t4567", "speech", "zeros"):
+        out = O.standard_audio_transform_f64(g[f"{tag}_pcm"], g["fb"])
+        np.testing.assert_allclose(out, g[f"{tag}_out"], rtol=RTOL, atol=ATOL)
+
+
+def test_vtlp_filterbanks(golden):
+    g = golden("vtlp")
+    for i, a in enumerate(g["alphas"]):
+        fb = O.vtlp_filterbank(float(a), 40).numpy()
+        np.testing.assert_allclose(fb, g[f"fb_{i}"], rtol=1e-6, atol=1e-6)
+    # train-mode forward of the reference == oracle fed with the replayed host draws
+    fe = golden("frontend")
+    pcm = torch.from_numpy(fe["t8000_pcm"])
+    for k in range(4):
+        a = g["train_alphas"][k]
+        fb = O.vtlp_filterbank(float(a), 40) if a > 0 else O.mel_filterbank(40)
+        out = O.standard_audio_transform_f32(pcm, fb).numpy()
+        np.testing.assert_allclose(out, g["train_outs"][k], rtol=RTOL, atol=ATOL)
+    assert (g["train_alphas"] > 0).sum() >= 1
+
+
+def test_zmuv(golden):
+    g = golden("zmuv")
+    fe = golden("frontend")
+    total, mean, mean2 = torch.zeros(1), torch.zeros(1), torch.zeros(1)
+    for x in [fe["t8000_out"][i:i + 1] for i in range(3)] + [fe["speech_out"]]:
+        total, mean, mean2 = O.zmuv_update(total, mean, mean2, torch.from_numpy(x))
+    np.testing.assert_allclose(total.numpy(), g["total"])
+    np.testing.assert_allclose(mean.numpy(), g["mean"], rtol=1e-6)
+    np.testing.assert_allclose(mean2.numpy(), g["mean2"], rtol=1e-6)
+    out = O.zmuv_forward(torch.from_numpy(g["fwd_in"]), torch.from_numpy(g["mean"]), torch.from_numpy(g["mean2"]))
+    np.testing.assert_allclose(out.numpy(), g["fwd_out"], rtol=1e-6, atol=1e-6)
+
+
+def test_spec_augment(golden):
+    g = golden("specaugment")
+    out = O.spec_augment_apply(torch.from_numpy(g["in"]).clone(), [tuple(r) for r in g["rects"].tolist()])
+    assert np.array_equal(out.numpy(), g["out"])
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def test_res8_eval_real_weights(golden):
+    g = golden("res8_heyfirefox")
+    sd = _sd(g, "sd.")
+    feats = O.hot_path_features(torch.from_numpy(g["pcm"]), O.mel_filterbank(40),
+                                torch.from_numpy(g["zmuv.mean"]), torch.from_numpy(g["zmuv.mean2"]))
+    np.testing.assert_allclose(feats.numpy(), g["feats"], rtol=RTOL, atol=ATOL)
+    logits = O.res8_forward(feats, sd, sd, training=False)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(logits.argmax(1).numpy(), g["logits"].argmax(1))
+
+
+def test_res8_train_steps(golden):
+    g = golden("res8_train")
+    L = 12
+    init = _sd(g, "init.")
+    params = {k: init[k].clone() for k, _ in O.res8_param_shapes(L)}
+    bn = {k: v.clone() for k, v in init.items() if k.startswith("bn")}
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v = {k: torch.zeros_like(p) for k, p in params.items()}
+    pcm, labels = torch.from_numpy(g["pcm"]), torch.from_numpy(g["labels"])
+    feats = O.hot_path_features(pcm, O.mel_filterbank(40), torch.from_numpy(g["zmuv_mean"]),
+                                torch.from_numpy(g["zmuv_mean2"]))
+    for step in (1, 2, 3):
+        loss, logits, grads = O.res8_train_step(feats, labels, params, bn, m, v, step, float(g["lr"]), float(g["wd"]))
+        np.testing.assert_allclose(loss.numpy(), g[f"step{step}.loss"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(logits.numpy(), g[f"step{step}.logits"], rtol=RTOL, atol=ATOL)
+        for k in params:
+            np.testing.assert_allclose(grads[k].numpy(), g[f"step{step}.grad.{k}"], rtol=1e-3, atol=1e-5)
+            # Adam's first steps are sign-like (lr*g/(|g|+eps)): where |g| ~ eps=1e-8 the update is
+            # ill-conditioned in g (worst case a sign flip = 2*lr), so end-to-end parameter parity is
+            # statistical: >= 99.9 % of elements within 5 % of lr, none beyond 2.5*lr.  The AdamW arithmetic
+            # itself is checked tightly with identical grads in test_adamw_restated.  Parameters are then
+            # teacher-forced to the reference's so later steps compare like with like.
+            want = g[f"step{step}.sd.{k}"]
+            diff = np.abs(params[k].numpy() - want)
+            assert (diff > 5e-4).mean() <= 1e-3 and diff.max() <= 2.5 * float(g["lr"])
+            params[k].copy_(torch.from_numpy(want))
+        for k in bn:
+            np.testing.assert_allclose(bn[k].numpy(), g[f"step{step}.sd.{k}"], rtol=1e-4, atol=1e-5)
+
+
+def test_adamw_restated():
+    torch.manual_seed(0)
+    p0 = {"a": torch.randn(1000), "b": torch.randn(7, 5)}
+    ref = {k: torch.nn.Parameter(t.clone()) for k, t in p0.items()}
+    opt = torch.optim.AdamW(ref.values(), lr=0.01, weight_decay=1e-2)
+    mine = {k: t.clone() for k, t in p0.items()}
+    m = {k: torch.zeros_like(t) for k, t in p0.items()}
+    v = {k: torch.zeros_like(t) for k, t in p0.items()}
+    for step in range(1, 6):
+        grads = {k: torch.randn_like(t) * 10 ** (-step) for k, t in p0.items()}
+        for k in ref:
+            ref[k].grad = grads[k].clone()
+        opt.step()
+        O.adamw_step(mine, grads, m, v, step, 0.01, 1e-2)
+        for k in ref:
+            np.testing.assert_allclose(mine[k].numpy(), ref[k].detach().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_flat_layout_roundtrip():
+    p = O.res8_init(12, seed=3)
+    flat = O.flatten(p, 12)
+    assert flat.numel() == 109755 + 45 * 12 + 12
+    back = O.unflatten(flat, 12)
+    assert all(torch.equal(back[k], p[k]) for k in p)
+
+
+def test_known_answer_traces_recorded():
+    meta = json.load(open(os.path.join(GOLDEN, "meta.json")))
+    assert meta["traces"]["hey_fire_fox"]["detected"] is True
+    assert meta["traces"]["hey_fire_fox"]["labels"] == [3, 3, 3, 3, 3, 0, 0, 0, 0, 0, 3, 1, 1, 1, 1, 1, 1, 1, 3, 3, 3, 2]
+    assert meta["traces"]["hello_world"] == {"detected": False, "labels": [3] * 7}
