@@ -1,0 +1,94 @@
+// Context management and host-side integer helpers of libhowl_b200.so.
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+char g_howl_create_error[512] = "";
+
+extern "C" int howl_b200_abi_version(void) { return HOWL_B200_ABI_VERSION; }
+
+#define CREATE_FAIL(code, ...)                                              \
+  do {                                                                      \
+    snprintf(g_howl_create_error, sizeof(g_howl_create_error), __VA_ARGS__); \
+    if (ctx) howl_b200_destroy(ctx);                                        \
+    return (code);                                                          \
+  } while (0)
+
+extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_ctx_t** out_ctx) {
+  howl_ctx_t* ctx = nullptr;
+  if (!cfg || !out_ctx) CREATE_FAIL(HOWL_E_INVALID, "create: null argument");
+  if (cfg->n_fft != HOWL_NFFT) CREATE_FAIL(HOWL_E_UNSUPPORTED, "create: n_fft=%d (only 512 is built)", cfg->n_fft);
+  if (cfg->hop <= 0 || cfg->hop > HOWL_NFFT) CREATE_FAIL(HOWL_E_INVALID, "create: hop=%d out of range", cfg->hop);
+  if (cfg->n_mels < 1 || cfg->n_mels > HOWL_MAX_MELS)
+    CREATE_FAIL(HOWL_E_UNSUPPORTED, "create: n_mels=%d outside 1..%d", cfg->n_mels, HOWL_MAX_MELS);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    CREATE_FAIL(HOWL_E_CUDA, "create: no CUDA device (%s); libhowl_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) CREATE_FAIL(HOWL_E_INVALID, "create: device %d of %d", device, ndev);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) CREATE_FAIL(HOWL_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    CREATE_FAIL(HOWL_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    CREATE_FAIL(HOWL_E_UNSUPPORTED, "create: device is sm_%d%d; this library is built for sm_100a only", prop.major,
+                prop.minor);
+  ctx = (howl_ctx_t*)calloc(1, sizeof(howl_ctx_t));
+  if (!ctx) CREATE_FAIL(HOWL_E_INVALID, "create: out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->fe = *cfg;
+  // tables in double, rounded once
+  float win[HOWL_NFFT];
+  float2 tw256[256], tw512[HOWL_NFREQ];
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int n = 0; n < HOWL_NFFT; ++n) win[n] = (float)(0.5 - 0.5 * cos(two_pi * n / HOWL_NFFT));
+  for (int k = 0; k < 256; ++k) tw256[k] = make_float2((float)cos(two_pi * k / 256), (float)(-sin(two_pi * k / 256)));
+  for (int k = 0; k < HOWL_NFREQ; ++k)
+    tw512[k] = make_float2((float)cos(two_pi * k / 512), (float)(-sin(two_pi * k / 512)));
+#define CK(x)                                                                          \
+  if ((e = (x)) != cudaSuccess) CREATE_FAIL(HOWL_E_CUDA, "%s: %s", #x, cudaGetErrorString(e))
+  CK(cudaMalloc(&ctx->d_window, sizeof(win)));
+  CK(cudaMalloc(&ctx->d_tw256, sizeof(tw256)));
+  CK(cudaMalloc(&ctx->d_tw512, sizeof(tw512)));
+  CK(cudaMemcpy(ctx->d_window, win, sizeof(win), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_tw256, tw256, sizeof(tw256), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_tw512, tw512, sizeof(tw512), cudaMemcpyHostToDevice));
+#undef CK
+  *out_ctx = ctx;
+  return HOWL_OK;
+}
+
+extern "C" void howl_b200_destroy(howl_ctx_t* ctx) {
+  if (!ctx) return;
+  cudaFree(ctx->d_window);
+  cudaFree(ctx->d_tw256);
+  cudaFree(ctx->d_tw512);
+  cudaFree(ctx->fb_lo);
+  cudaFree(ctx->fb_hi);
+  cudaFree(ctx->fb_off);
+  cudaFree(ctx->fbc);
+  free(ctx);
+}
+
+extern "C" const char* howl_b200_last_error(const howl_ctx_t* ctx) { return ctx ? ctx->err : g_howl_create_error; }
+extern "C" int howl_b200_sm_count(const howl_ctx_t* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int64_t howl_b200_launch_count(const howl_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int64_t howl_b200_num_frames(int64_t num_samples, int32_t hop) {
+  if (hop <= 0 || num_samples < 0) return -1;
+  return 1 + num_samples / hop;
+}
+
+static inline int64_t floor_div(int64_t a, int64_t b) {
+  int64_t q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+
+extern "C" int howl_b200_compute_lengths(const int64_t* lengths, int64_t n, int32_t win, int32_t hop, int64_t* out) {
+  if (!lengths || !out || n < 0 || hop <= 0) return HOWL_E_INVALID;
+  for (int64_t i = 0; i < n; ++i) out[i] = floor_div(lengths[i] - win, hop) + 1;
+  return HOWL_OK;
+}

@@ -1,0 +1,74 @@
+// Shared declarations for libhowl_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/howl_b200.h"
+
+#define HOWL_NFFT 512
+#define HOWL_NFREQ 257
+#define HOWL_MAX_MELS 128
+
+struct howl_ctx {
+  int device;
+  int sm_count;
+  howl_frontend_cfg fe;
+  // device tables (built in double on the host, rounded once to f32)
+  float* d_window;   // [512]  periodic Hann
+  float2* d_tw256;   // [256]  exp(-2*pi*i*k/256)
+  float2* d_tw512;   // [257]  exp(-2*pi*i*k/512)
+  // compact filterbank scratch (rebuilt by every frontend call; stream ordered)
+  int* fb_lo;
+  int* fb_hi;
+  int* fb_off;
+  float* fbc;
+  int64_t launches;
+  char err[512];
+};
+
+extern char g_howl_create_error[512];
+
+#define HOWL_SET_ERR(ctx, ...)                                    \
+  do {                                                            \
+    if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+  } while (0)
+
+#define HOWL_REQUIRE(ctx, cond, code, ...) \
+  do {                                     \
+    if (!(cond)) {                         \
+      HOWL_SET_ERR(ctx, __VA_ARGS__);      \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+#define HOWL_CUDA(ctx, expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      HOWL_SET_ERR(ctx, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return HOWL_E_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define HOWL_LAUNCHED(ctx)                \
+  do {                                    \
+    (ctx)->launches++;                    \
+    HOWL_CUDA(ctx, cudaGetLastError());   \
+  } while (0)
+
+static inline int64_t howl_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t howl_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

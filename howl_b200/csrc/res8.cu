@@ -1,0 +1,923 @@
+// Res8 forward / backward for sm_100a -- exact-fp32 (FFMA) path.
+//
+// Reference semantics: howl/model/cnn.py:107-145 (Res8), nn.BatchNorm2d(affine=False) in train / eval mode,
+// nn.CrossEntropyLoss(mean) and autograd's backward of all of it (training/run/train.py:292-301).
+//
+// Data layout in HBM (all fp32, caller-provided workspace):
+//   feats  [B, F, 40]         time-major log-mel (K1 output; == the [B,1,F,40] tensor of cnn.py:128-129)
+//   a0     [B, 45, H, 10]     relu(conv0) average-pooled (3,4);  H = F / 3
+//   u_i    [B, 45, H, 10]     i = 1..6, the tensor fed to bn_i (relu(conv_i) [+ residual]); BatchNorm is never
+//                             materialised: the consumer applies (x - mean) * rstd while staging its tile
+//   g, dc, gu                 gradient ping-pong buffers of the same shape
+// Kernels are persistent (one CTA per SM looping over utterances) so that weights stay in shared memory and
+// per-channel statistics / weight gradients are reduced on chip before touching global atomics.
+#include <math.h>
+
+#include "common.cuh"
+
+#define R8_C 45
+#define R8_W 10          // pooled width (n_mels 40 / 4)
+#define R8_LAYERS 6
+#define R8_MELS 40
+#define R8_WPAD 12       // padded row (1 + 10 + 1)
+#define R8_KW (R8_C * R8_C * 9)   // 18225 weights per 45->45 layer
+#define R8_BN_EPS 1e-5
+#define R8_BN_MOM 0.1
+
+// =============================================================================================
+// workspace carve-up
+// =============================================================================================
+struct R8Ws {
+  double* stats_fwd;   // [6][2][45]  sum(u), sum(u^2)
+  double* stats_bwd;   // [6][2][45]  sum(g), sum(g * xhat)
+  double* loss_acc;    // [1]
+  float* mean_rstd;    // [6][2][45]
+  float* wT;           // [6][18225]  transposed + flipped weights for dgrad
+  float* pooled;       // [B,45]
+  float* dh;           // [B,45]
+  float* dlogits;      // [B,L]
+  float* logits;       // [B,L]  copy of the forward's logits for the backward
+  float* a0;
+  float* u[R8_LAYERS];
+  float* g;
+  float* dc;
+  float* gu[2];
+  size_t bytes;
+};
+
+static R8Ws r8_carve(void* base, int64_t B, int H, int L) {
+  R8Ws w;
+  size_t off = 0;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) {
+    void* r = p ? (void*)(p + off) : nullptr;
+    off += howl_align_up(bytes, 256);
+    return r;
+  };
+  w.stats_fwd = (double*)take(sizeof(double) * R8_LAYERS * 2 * R8_C);
+  w.stats_bwd = (double*)take(sizeof(double) * R8_LAYERS * 2 * R8_C);
+  w.loss_acc = (double*)take(sizeof(double) * 2);
+  w.mean_rstd = (float*)take(sizeof(float) * R8_LAYERS * 2 * R8_C);
+  w.wT = (float*)take(sizeof(float) * R8_LAYERS * R8_KW);
+  w.pooled = (float*)take(sizeof(float) * B * R8_C);
+  w.dh = (float*)take(sizeof(float) * B * R8_C);
+  w.dlogits = (float*)take(sizeof(float) * B * L);
+  w.logits = (float*)take(sizeof(float) * B * L);
+  const size_t n = sizeof(float) * (size_t)B * R8_C * H * R8_W;
+  w.a0 = (float*)take(n);
+  for (int i = 0; i < R8_LAYERS; ++i) w.u[i] = (float*)take(n);
+  w.g = (float*)take(n);
+  w.dc = (float*)take(n);
+  w.gu[0] = (float*)take(n);
+  w.gu[1] = (float*)take(n);
+  w.bytes = off;
+  return w;
+}
+
+// =============================================================================================
+// conv0 (1 -> 45, 3x3, pad 1) + ReLU + AvgPool(3,4), one CTA per utterance
+// =============================================================================================
+#define C0_THREADS 288
+#define C0_STRIDE (R8_MELS + 4)   // padded row of the staged feature tile (col 0 = left halo, 16-byte aligned groups)
+
+__device__ __forceinline__ void c0_stage_tile(float* s_x, const float* __restrict__ feats, int F, int rows, int tid,
+                                              int nthreads) {
+  // s_x[(y + 1) * C0_STRIDE + (x + 1)], y in [-1, rows-2]; zero outside the clip
+  for (int i = tid; i < rows * C0_STRIDE; i += nthreads) s_x[i] = 0.f;
+  __syncthreads();
+  const int nvalid = min(F, rows - 1);
+  for (int i = tid; i < nvalid * (R8_MELS / 4); i += nthreads) {
+    const int y = i / (R8_MELS / 4), x4 = i - y * (R8_MELS / 4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(feats + (size_t)y * R8_MELS) + x4);
+    float* d = s_x + (y + 1) * C0_STRIDE + x4 * 4 + 1;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+}
+
+__global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __restrict__ feats,
+                                                                 const float* __restrict__ w0, float* __restrict__ a0,
+                                                                 int F, int H) {
+  extern __shared__ __align__(16) float smem[];
+  const int rows = 3 * H + 2;
+  float* s_x = smem;
+  float* s_w = smem + rows * C0_STRIDE;
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  for (int i = tid; i < R8_C * 9; i += C0_THREADS) s_w[i] = __ldg(w0 + i);
+  c0_stage_tile(s_x, feats + b * (int64_t)F * R8_MELS, F, rows, tid, C0_THREADS);
+  __syncthreads();
+  const int HW = H * R8_W;
+  for (int pp = tid; pp < HW; pp += C0_THREADS) {
+    const int h = pp / R8_W, w = pp - h * R8_W;
+    float patch[5][6];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) patch[r][c] = s_x[(3 * h + r) * C0_STRIDE + 4 * w + c];
+    float* dst = a0 + (b * R8_C) * (int64_t)HW + pp;
+    for (int oc = 0; oc < R8_C; ++oc) {
+      float wk[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) wk[k] = s_w[oc * 9 + k];
+      float sum = 0.f;
+#pragma unroll
+      for (int py = 0; py < 3; ++py)
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          float pre = 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) pre = fmaf(wk[ky * 3 + kx], patch[py + ky][px + kx], pre);
+          sum += fmaxf(pre, 0.f);
+        }
+      dst[(int64_t)oc * HW] = __fdiv_rn(sum, 12.f);
+    }
+  }
+}
+
+// backward of conv0: dW0[oc][k] = sum relu'(pre) * G[oc][h][w] / 12 * patch; pre is recomputed with the same
+// FMA order as the forward.  Persistent; G = ga (+ gb).
+__global__ void __launch_bounds__(C0_THREADS) conv0_bwd_kernel(const float* __restrict__ feats,
+                                                                const float* __restrict__ w0,
+                                                                const float* __restrict__ ga,
+                                                                const float* __restrict__ gb, float* __restrict__ dw0,
+                                                                int64_t B, int F, int H) {
+  extern __shared__ __align__(16) float smem[];
+  const int rows = 3 * H + 2;
+  float* s_x = smem;
+  float* s_w = smem + rows * C0_STRIDE;
+  float* s_acc = s_w + R8_C * 9;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < R8_C * 9; i += C0_THREADS) {
+    s_w[i] = __ldg(w0 + i);
+    s_acc[i] = 0.f;
+  }
+  const int HW = H * R8_W;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    c0_stage_tile(s_x, feats + b * (int64_t)F * R8_MELS, F, rows, tid, C0_THREADS);
+    __syncthreads();
+    for (int pp0 = 0; pp0 < HW; pp0 += C0_THREADS) {
+      const int pp = pp0 + tid;
+      const bool active = pp < HW;
+      const int h = active ? pp / R8_W : 0, w = active ? pp - (pp / R8_W) * R8_W : 0;
+      float patch[5][6];
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) patch[r][c] = s_x[(3 * h + r) * C0_STRIDE + 4 * w + c];
+      for (int oc = 0; oc < R8_C; ++oc) {
+        float wk[9], acc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          wk[k] = s_w[oc * 9 + k];
+          acc[k] = 0.f;
+        }
+        float gv = 0.f;
+        if (active) {
+          const int64_t idx = (b * R8_C + oc) * (int64_t)HW + pp;
+          gv = ga[idx];
+          if (gb) gv += gb[idx];
+          gv = __fdiv_rn(gv, 12.f);
+        }
+#pragma unroll
+        for (int py = 0; py < 3; ++py)
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            float pre = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) pre = fmaf(wk[ky * 3 + kx], patch[py + ky][px + kx], pre);
+            const float gm = pre > 0.f ? gv : 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(gm, patch[py + ky][px + kx], acc[ky * 3 + kx]);
+          }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float v = warp_sum(acc[k]);
+          if (lane == 0) atomicAdd(&s_acc[oc * 9 + k], v);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < R8_C * 9; i += C0_THREADS) atomicAdd(&dw0[i], s_acc[i]);
+}
+
+// =============================================================================================
+// generic 45 -> 45 3x3 convolution (forward and data-gradient), persistent over utterances
+// =============================================================================================
+#define CV_THREADS 256
+#define CV_OCG 9                  // output-channel groups of 5
+#define CV_WSTRIDE 16             // floats per (c, dy, ocg) weight packet: [dx 3][o 5] + 1 pad
+
+struct ConvParams {
+  const float* in;        // [B,45,H,10]
+  const float* in_mean;   // [45] or null (identity)
+  const float* in_rstd;
+  const float* w;         // [45 out][45 in][3][3]
+  const float* res;       // residual added after ReLU, or null
+  float* out;
+  double* stats;          // [2][45] or null
+  const float* aux;       // STATS == 2: tensor whose normalised value multiplies the output in the 2nd statistic
+  const float* aux_mean;
+  const float* aux_rstd;
+  int64_t B;
+  int H;
+};
+
+static size_t conv_smem_bytes(int H) {
+  size_t f = (size_t)R8_C * 3 * CV_OCG * CV_WSTRIDE + (size_t)R8_C * (H + 2) * R8_WPAD + (size_t)H * CV_OCG * 10 +
+             4 * 48;
+  return f * sizeof(float);
+}
+
+template <bool RELU, int STATS>
+__global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const ConvParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, HP = H + 2, HW = H * R8_W;
+  float* s_w = smem;                                         // [45][3][9][16]
+  float* s_in = s_w + R8_C * 3 * CV_OCG * CV_WSTRIDE;        // [45][H+2][12]
+  float* s_part = s_in + R8_C * HP * R8_WPAD;                // [H*9][10]
+  float* s_mean = s_part + H * CV_OCG * 10;                  // [48] x 4
+  float* s_rstd = s_mean + 48;
+  float* s_amean = s_rstd + 48;
+  float* s_arstd = s_amean + 48;
+  const int tid = threadIdx.x;
+
+  // weights -> [c][dy][ocg][dx*5 + o]
+  for (int i = tid; i < R8_KW; i += CV_THREADS) {
+    const int oc = i / (R8_C * 9), rem = i - oc * (R8_C * 9);
+    const int c = rem / 9, k = rem - c * 9, dy = k / 3, dx = k - dy * 3;
+    s_w[((c * 3 + dy) * CV_OCG + oc / 5) * CV_WSTRIDE + dx * 5 + (oc % 5)] = __ldg(p.w + i);
+  }
+  for (int i = tid; i < R8_C * 3 * CV_OCG; i += CV_THREADS) s_w[i * CV_WSTRIDE + 15] = 0.f;
+  for (int i = tid; i < R8_C * HP * R8_WPAD; i += CV_THREADS) s_in[i] = 0.f;   // halo stays zero for good
+  if (tid < R8_C) {
+    s_mean[tid] = p.in_mean ? p.in_mean[tid] : 0.f;
+    s_rstd[tid] = p.in_rstd ? p.in_rstd[tid] : 1.f;
+    if (STATS == 2) {
+      s_amean[tid] = p.aux_mean[tid];
+      s_arstd[tid] = p.aux_rstd[tid];
+    }
+  }
+  const int items = H * CV_OCG;
+  double stat_acc = 0.0;   // threads < 90: running per-channel statistic over this CTA's utterances
+
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    __syncthreads();
+    // ---- stage the (normalised) input tile
+    const float* src = p.in + b * (int64_t)R8_C * HW;
+    for (int e = tid; e < R8_C * H * 5; e += CV_THREADS) {
+      const int c = e / (H * 5), rem = e - c * (H * 5), r = rem / 5, x2 = rem - r * 5;
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src) + e);
+      const float mu = s_mean[c], rs = s_rstd[c];
+      float* d = s_in + (c * HP + r + 1) * R8_WPAD + 1 + 2 * x2;
+      d[0] = (v.x - mu) * rs;
+      d[1] = (v.y - mu) * rs;
+    }
+    __syncthreads();
+    for (int it0 = 0; it0 < items; it0 += CV_THREADS) {
+      const int id = it0 + tid;
+      const bool active = id < items;
+      const int ocg = active ? id / H : 0, row = active ? id - (id / H) * H : 0;
+      float acc[5][10];
+#pragma unroll
+      for (int o = 0; o < 5; ++o)
+#pragma unroll
+        for (int x = 0; x < 10; ++x) acc[o][x] = 0.f;
+      const float* wp = s_w + ocg * CV_WSTRIDE;
+      const float* ip = s_in + row * R8_WPAD;
+      for (int c = 0; c < R8_C; ++c) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          float xin[12], wv[16];
+          const float4* i4 = reinterpret_cast<const float4*>(ip + (c * HP + dy) * R8_WPAD);
+          const float4* w4 = reinterpret_cast<const float4*>(wp + (c * 3 + dy) * CV_OCG * CV_WSTRIDE);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float4 t = i4[q];
+            xin[4 * q] = t.x; xin[4 * q + 1] = t.y; xin[4 * q + 2] = t.z; xin[4 * q + 3] = t.w;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t = w4[q];
+            wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
+          }
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int o = 0; o < 5; ++o)
+#pragma unroll
+              for (int x = 0; x < 10; ++x) acc[o][x] = fmaf(wv[dx * 5 + o], xin[x + dx], acc[o][x]);
+        }
+      }
+      // ---- epilogue
+      if (active) {
+#pragma unroll
+        for (int o = 0; o < 5; ++o) {
+          const int oc = ocg * 5 + o;
+          const int64_t base = ((b * R8_C + oc) * (int64_t)H + row) * R8_W;
+          float s1 = 0.f, s2 = 0.f;
+          float am = 0.f, ar = 0.f;
+          if (STATS == 2) {
+            am = s_amean[oc];
+            ar = s_arstd[oc];
+          }
+#pragma unroll
+          for (int x2 = 0; x2 < 5; ++x2) {
+            float v0 = acc[o][2 * x2], v1 = acc[o][2 * x2 + 1];
+            if (RELU) {
+              v0 = fmaxf(v0, 0.f);
+              v1 = fmaxf(v1, 0.f);
+            }
+            if (p.res) {
+              const float2 r = __ldg(reinterpret_cast<const float2*>(p.res + base) + x2);
+              v0 += r.x;
+              v1 += r.y;
+            }
+            reinterpret_cast<float2*>(p.out + base)[x2] = make_float2(v0, v1);
+            if (STATS == 1) {
+              s1 += v0 + v1;
+              s2 = fmaf(v0, v0, fmaf(v1, v1, s2));
+            } else if (STATS == 2) {
+              const float2 a = __ldg(reinterpret_cast<const float2*>(p.aux + base) + x2);
+              s1 += v0 + v1;
+              s2 = fmaf(v0, (a.x - am) * ar, fmaf(v1, (a.y - am) * ar, s2));
+            }
+          }
+          if (STATS) {
+            s_part[id * 10 + o * 2] = s1;
+            s_part[id * 10 + o * 2 + 1] = s2;
+          }
+        }
+      }
+    }
+    if (STATS) {
+      __syncthreads();
+      if (tid < 2 * R8_C) {
+        const int which = tid / R8_C, ch = tid - which * R8_C, ocg = ch / 5, o = ch - ocg * 5;
+        float s = 0.f;
+        for (int r = 0; r < H; ++r) s += s_part[(ocg * H + r) * 10 + o * 2 + which];
+        stat_acc += (double)s;
+      }
+    }
+  }
+  if (STATS) {
+    if (tid < 2 * R8_C) atomicAdd(&p.stats[tid], stat_acc);
+  }
+}
+
+// =============================================================================================
+// weight gradient of a 45 -> 45 3x3 convolution, persistent; thread tile 3 (out) x 3 (in) x 9 taps
+// =============================================================================================
+#define WG_THREADS 256
+
+struct WgradParams {
+  const float* dc;       // [B,45,H,10]  gradient at the conv output (ReLU mask applied)
+  const float* x;        // [B,45,H,10]  conv input before normalisation
+  const float* x_mean;   // or null
+  const float* x_rstd;
+  float* dw;             // [45][45][3][3], accumulated with atomics
+  int64_t B;
+  int H;
+};
+
+static size_t wgrad_smem_bytes(int H) {
+  return sizeof(float) * ((size_t)R8_C * H * R8_WPAD + (size_t)R8_C * (H + 2) * R8_WPAD + 2 * 48);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_kernel(const WgradParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, HP = H + 2, HW = H * R8_W;
+  float* s_dc = smem;                              // [45][H][12]   (cols 0..9 used)
+  float* s_x = s_dc + R8_C * H * R8_WPAD;          // [45][H+2][12] (halo zero)
+  float* s_mean = s_x + R8_C * HP * R8_WPAD;
+  float* s_rstd = s_mean + 48;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < R8_C * HP * R8_WPAD; i += WG_THREADS) s_x[i] = 0.f;
+  for (int i = tid; i < R8_C * H * R8_WPAD; i += WG_THREADS) s_dc[i] = 0.f;
+  if (tid < R8_C) {
+    s_mean[tid] = p.x_mean ? p.x_mean[tid] : 0.f;
+    s_rstd[tid] = p.x_rstd ? p.x_rstd[tid] : 1.f;
+  }
+  const bool active = tid < 225;
+  const int og = active ? tid / 15 : 0, cg = active ? tid - (tid / 15) * 15 : 0;
+  float acc[3][3][9];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[a][c][k] = 0.f;
+
+  for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    __syncthreads();
+    const float* sdc = p.dc + b * (int64_t)R8_C * HW;
+    const float* sx = p.x + b * (int64_t)R8_C * HW;
+    for (int e = tid; e < R8_C * H * 5; e += WG_THREADS) {
+      const int c = e / (H * 5), rem = e - c * (H * 5), r = rem / 5, x2 = rem - r * 5;
+      const float2 d = __ldg(reinterpret_cast<const float2*>(sdc) + e);
+      const float2 v = __ldg(reinterpret_cast<const float2*>(sx) + e);
+      reinterpret_cast<float2*>(s_dc + (c * H + r) * R8_WPAD)[x2] = d;
+      const float mu = s_mean[c], rs = s_rstd[c];
+      float* q = s_x + (c * HP + r + 1) * R8_WPAD + 1 + 2 * x2;
+      q[0] = (v.x - mu) * rs;
+      q[1] = (v.y - mu) * rs;
+    }
+    __syncthreads();
+    if (active) {
+      for (int r = 0; r < H; ++r) {
+        float dv[3][12];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float4* d4 = reinterpret_cast<const float4*>(s_dc + ((og * 3 + a) * H + r) * R8_WPAD);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float4 t = d4[q];
+            dv[a][4 * q] = t.x; dv[a][4 * q + 1] = t.y; dv[a][4 * q + 2] = t.z; dv[a][4 * q + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          float xv[3][12];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float4* x4 = reinterpret_cast<const float4*>(s_x + ((cg * 3 + c) * HP + r + dy) * R8_WPAD);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const float4 t = x4[q];
+              xv[c][4 * q] = t.x; xv[c][4 * q + 1] = t.y; xv[c][4 * q + 2] = t.z; xv[c][4 * q + 3] = t.w;
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int x = 0; x < 10; ++x)
+                  acc[a][c][dy * 3 + dx] = fmaf(dv[a][x], xv[c][x + dx], acc[a][c][dy * 3 + dx]);
+        }
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) atomicAdd(&p.dw[((og * 3 + a) * R8_C + cg * 3 + c) * 9 + k], acc[a][c][k]);
+  }
+}
+
+// =============================================================================================
+// small kernels
+// =============================================================================================
+// BatchNorm statistics -> mean / rstd (+ running-stat update with momentum 0.1 and unbiased variance)
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, float* __restrict__ mean_rstd,
+                                   float* __restrict__ running, int64_t* __restrict__ nbt) {
+  const int c = threadIdx.x;
+  if (c < R8_C) {
+    const double mean = stats[c] / count;
+    double var = stats[R8_C + c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[c] = (float)mean;
+    mean_rstd[R8_C + c] = (float)(1.0 / sqrt(var + R8_BN_EPS));
+    if (running) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running[c] = (float)((1.0 - R8_BN_MOM) * running[c] + R8_BN_MOM * mean);
+      running[R8_C + c] = (float)((1.0 - R8_BN_MOM) * running[R8_C + c] + R8_BN_MOM * unbiased);
+    }
+  }
+  if (c == 0 && nbt) *nbt += 1;
+}
+
+// eval mode: running statistics -> mean / rstd for all six layers
+__global__ void bn_eval_prepare_kernel(const float* __restrict__ running, float* __restrict__ mean_rstd) {
+  const int i = blockIdx.x, c = threadIdx.x;
+  if (c < R8_C) {
+    mean_rstd[i * 2 * R8_C + c] = running[i * 2 * R8_C + c];
+    mean_rstd[i * 2 * R8_C + R8_C + c] = 1.f / sqrtf(running[i * 2 * R8_C + R8_C + c] + (float)R8_BN_EPS);
+  }
+}
+
+// bn6 -> spatial mean -> Linear(45 -> L); one CTA (128 threads) per utterance
+__global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__ u6, const float* __restrict__ mean_rstd,
+                                                       const float* __restrict__ wout, const float* __restrict__ bout,
+                                                       float* __restrict__ pooled, float* __restrict__ logits,
+                                                       float* __restrict__ logits_ws, int HW, int L) {
+  __shared__ float s_pool[48];
+  const int64_t b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < R8_C; c += 4) {
+    const float* src = u6 + (b * R8_C + c) * (int64_t)HW;
+    float s = 0.f;
+    for (int i = lane; i < HW; i += 32) s += src[i];
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float v = (s / (float)HW - mean_rstd[c]) * mean_rstd[R8_C + c];
+      s_pool[c] = v;
+      pooled[b * R8_C + c] = v;
+    }
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    float acc = bout[l];
+    for (int c = 0; c < R8_C; ++c) acc = fmaf(wout[l * R8_C + c], s_pool[c], acc);
+    logits[b * L + l] = acc;
+    logits_ws[b * L + l] = acc;
+  }
+}
+
+// softmax cross-entropy backward at the head: one thread per utterance
+__global__ void head_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                const float* __restrict__ wout, float* __restrict__ dlogits, float* __restrict__ dh,
+                                double* __restrict__ loss_acc, int64_t B, int L, float inv_batch) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double nll = 0.0;
+  if (b < B) {
+    const float* z = logits + b * L;
+    float mx = z[0];
+    for (int l = 1; l < L; ++l) mx = fmaxf(mx, z[l]);
+    float se = 0.f;
+    for (int l = 0; l < L; ++l) se += expf(z[l] - mx);
+    const float lse = mx + logf(se);
+    const int64_t y = labels[b];
+    float acc[R8_C];
+#pragma unroll
+    for (int c = 0; c < R8_C; ++c) acc[c] = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float pl = expf(z[l] - lse);
+      const float d = (pl - (l == y ? 1.f : 0.f)) * inv_batch;
+      dlogits[b * L + l] = d;
+#pragma unroll
+      for (int c = 0; c < R8_C; ++c) acc[c] = fmaf(d, __ldg(wout + l * R8_C + c), acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < R8_C; ++c) dh[b * R8_C + c] = acc[c];
+    if (y >= 0 && y < L) nll = (double)(lse - z[y]);
+  }
+  nll = warp_sum(nll);
+  if ((threadIdx.x & 31) == 0 && nll != 0.0) atomicAdd(loss_acc, nll * (double)inv_batch);
+}
+
+// head parameter gradients + the two BatchNorm-backward statistics of layer 6 (g6 = dh / HW broadcast over pixels)
+//   blocks 0..L-1 : d output.weight[l][:] ; block L : d output.bias ; block L+1 : stats_bwd[5]
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ dlogits,
+                                                          const float* __restrict__ pooled,
+                                                          const float* __restrict__ dh, float* __restrict__ dwout,
+                                                          float* __restrict__ dbout, double* __restrict__ stats6,
+                                                          const double* __restrict__ loss_acc, float* __restrict__ loss,
+                                                          int64_t B, int L) {
+  __shared__ double sh[8][96];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int blk = blockIdx.x;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;   // up to three columns per lane
+  if (blk < L) {
+    for (int64_t b = warp; b < B; b += 8) {
+      const double d = dlogits[b * L + blk];
+      a0 += d * pooled[b * R8_C + lane];
+      if (lane + 32 < R8_C) a1 += d * pooled[b * R8_C + lane + 32];
+    }
+  } else if (blk == L) {
+    for (int64_t b = warp; b < B; b += 8) {
+      if (lane < L) a0 += dlogits[b * L + lane];
+      if (lane + 32 < L) a1 += dlogits[b * L + lane + 32];
+      if (lane + 64 < L) a2 += dlogits[b * L + lane + 64];
+    }
+  } else {
+    for (int64_t b = warp; b < B; b += 8) {
+      const float d0 = dh[b * R8_C + lane];
+      a0 += d0;
+      a1 += (double)d0 * pooled[b * R8_C + lane];   // lanes 0..31
+    }
+    // channels 32..44 in a second sweep
+    double c0 = 0.0, c1 = 0.0;
+    if (lane + 32 < R8_C)
+      for (int64_t b = warp; b < B; b += 8) {
+        const float d0 = dh[b * R8_C + lane + 32];
+        c0 += d0;
+        c1 += (double)d0 * pooled[b * R8_C + lane + 32];
+      }
+    sh[warp][lane] = a0;
+    sh[warp][32 + lane] = a1;
+    __syncthreads();
+    double t0 = 0.0, t1 = 0.0;
+    if (warp == 0) {
+      for (int w = 0; w < 8; ++w) {
+        t0 += sh[w][lane];
+        t1 += sh[w][32 + lane];
+      }
+    }
+    __syncthreads();
+    sh[warp][lane] = c0;
+    sh[warp][32 + lane] = c1;
+    __syncthreads();
+    if (warp == 0) {
+      stats6[lane] = t0;
+      stats6[R8_C + lane] = t1;
+      if (lane + 32 < R8_C) {
+        double u0 = 0.0, u1 = 0.0;
+        for (int w = 0; w < 8; ++w) {
+          u0 += sh[w][lane];
+          u1 += sh[w][32 + lane];
+        }
+        stats6[32 + lane] = u0;
+        stats6[R8_C + 32 + lane] = u1;
+      }
+      if (lane == 0) *loss = (float)(*loss_acc);
+    }
+    return;
+  }
+  sh[warp][lane] = a0;
+  sh[warp][32 + lane] = a1;
+  sh[warp][64 + lane] = a2;
+  __syncthreads();
+  if (warp == 0) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      t0 += sh[w][lane];
+      t1 += sh[w][32 + lane];
+      t2 += sh[w][64 + lane];
+    }
+    if (blk < L) {
+      dwout[blk * R8_C + lane] = (float)t0;
+      if (lane + 32 < R8_C) dwout[blk * R8_C + lane + 32] = (float)t1;
+    } else {
+      if (lane < L) dbout[lane] = (float)t0;
+      if (lane + 32 < L) dbout[lane + 32] = (float)t1;
+      if (lane + 64 < L) dbout[lane + 64] = (float)t2;
+    }
+  }
+}
+
+// BatchNorm backward + residual fan-in + ReLU mask:
+//   G  = rstd * (g - m1 - xhat * m2) [+ gu_in];   gu_out = G (even layers);   dc = mask ? G : 0
+//   mask = (u > mask_prev) for residual layers (relu output y = u - prev), (u > 0) otherwise
+struct ApplyParams {
+  const float* g;          // full tensor, or null when g_bcast is used
+  const float* g_bcast;    // [B,45]: g = g_bcast / HW (layer 6)
+  const float* u;
+  const float* mean_rstd;  // [2][45] of this layer
+  const double* stats;     // [2][45] sum(g), sum(g xhat)
+  const float* gu_in;
+  const float* mask_prev;
+  float* gu_out;
+  float* dc;
+  int64_t n2;              // number of float2 elements
+  int HW;
+  double count;
+};
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const ApplyParams p) {
+  const int hw2 = p.HW / 2;
+  const float inv_hw = 1.f / (float)p.HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t plane = i / hw2;            // b * 45 + c
+    const int c = (int)(plane % R8_C);
+    const float mu = __ldg(p.mean_rstd + c), rs = __ldg(p.mean_rstd + R8_C + c);
+    const float m1 = (float)(p.stats[c] / p.count), m2 = (float)(p.stats[R8_C + c] / p.count);
+    float2 g;
+    if (p.g) {
+      g = reinterpret_cast<const float2*>(p.g)[i];
+    } else {
+      const float v = __ldg(p.g_bcast + plane) * inv_hw;
+      g = make_float2(v, v);
+    }
+    const float2 u = reinterpret_cast<const float2*>(p.u)[i];
+    float2 G;
+    G.x = rs * (g.x - m1 - (u.x - mu) * rs * m2);
+    G.y = rs * (g.y - m1 - (u.y - mu) * rs * m2);
+    if (p.gu_in) {
+      const float2 t = reinterpret_cast<const float2*>(p.gu_in)[i];
+      G.x += t.x;
+      G.y += t.y;
+    }
+    if (p.gu_out) reinterpret_cast<float2*>(p.gu_out)[i] = G;
+    float2 prev = make_float2(0.f, 0.f);
+    if (p.mask_prev) prev = reinterpret_cast<const float2*>(p.mask_prev)[i];
+    float2 d;
+    d.x = (u.x > prev.x) ? G.x : 0.f;
+    d.y = (u.y > prev.y) ? G.y : 0.f;
+    reinterpret_cast<float2*>(p.dc)[i] = d;
+  }
+}
+
+// Wt[l][c][o][2-dy][2-dx] = W[l][o][c][dy][dx]
+__global__ void transpose_weights_kernel(const float* __restrict__ w, float* __restrict__ wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R8_LAYERS * R8_KW) return;
+  const int l = i / R8_KW, rem = i - l * R8_KW;
+  const int o = rem / (R8_C * 9), r2 = rem - o * (R8_C * 9), c = r2 / 9, k = r2 - c * 9;
+  wt[l * R8_KW + (c * R8_C + o) * 9 + (8 - k)] = w[i];
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+extern "C" int64_t howl_b200_res8_param_count(int32_t num_labels) {
+  if (num_labels < 1) return -1;
+  return (int64_t)R8_C * 9 + (int64_t)R8_LAYERS * R8_KW + (int64_t)num_labels * R8_C + num_labels;
+}
+
+extern "C" int64_t howl_b200_res8_workspace_bytes(int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels,
+                                                  int train) {
+  (void)train;
+  if (B < 0 || frames < 3 || n_mels != R8_MELS || num_labels < 1) return -1;
+  return (int64_t)r8_carve(nullptr, B, frames / 3, num_labels).bytes;
+}
+
+static int r8_check(howl_ctx_t* ctx, int64_t B, int frames, int n_mels, int L, const void* ws, size_t ws_bytes,
+                    R8Ws* out) {
+  HOWL_REQUIRE(ctx, n_mels == R8_MELS, HOWL_E_UNSUPPORTED, "res8: n_mels=%d (kernels are built for 40)", n_mels);
+  HOWL_REQUIRE(ctx, frames >= 3, HOWL_E_INVALID, "res8: %d frames is fewer than one pooling window", frames);
+  HOWL_REQUIRE(ctx, L >= 1 && L <= 96, HOWL_E_UNSUPPORTED, "res8: num_labels=%d outside 1..96", L);
+  HOWL_REQUIRE(ctx, B >= 1, HOWL_E_INVALID, "res8: empty batch");
+  const int H = frames / 3;
+  HOWL_REQUIRE(ctx, conv_smem_bytes(H) <= 227 * 1024 && wgrad_smem_bytes(H) <= 227 * 1024, HOWL_E_UNSUPPORTED,
+               "res8: %d frames exceeds the shared-memory tile of the conv kernels", frames);
+  HOWL_REQUIRE(ctx, ws != nullptr, HOWL_E_WORKSPACE, "res8: null workspace");
+  *out = r8_carve(const_cast<void*>(ws), B, H, L);
+  HOWL_REQUIRE(ctx, out->bytes <= ws_bytes, HOWL_E_WORKSPACE, "res8: workspace %zu < required %zu", ws_bytes,
+               out->bytes);
+  return HOWL_OK;
+}
+
+static int r8_grid(howl_ctx_t* ctx, int64_t B) { return (int)(B < ctx->sm_count ? B : ctx->sm_count); }
+
+extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* feats, int64_t B, int32_t frames,
+                                  int32_t n_mels, int32_t num_labels, const float* params, float* bn_running,
+                                  int64_t* num_batches_tracked, int train, float* logits, void* workspace,
+                                  size_t workspace_bytes) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, feats && params && bn_running && logits, HOWL_E_INVALID, "res8_fwd: null pointer");
+  R8Ws ws;
+  int rc = r8_check(ctx, B, frames, n_mels, num_labels, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = frames / 3, HW = H * R8_W, L = num_labels;
+  const float* w0 = params;
+  const float* wl = params + R8_C * 9;
+  const float* wout = wl + (size_t)R8_LAYERS * R8_KW;
+  const float* bout = wout + (size_t)L * R8_C;
+
+  {
+    const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + R8_C * 9);
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, ws.a0, frames, H);
+    HOWL_LAUNCHED(ctx);
+  }
+  if (train) {
+    HOWL_CUDA(ctx, cudaMemsetAsync(ws.stats_fwd, 0, sizeof(double) * R8_LAYERS * 2 * R8_C, st));
+  } else {
+    bn_eval_prepare_kernel<<<R8_LAYERS, 64, 0, st>>>(bn_running, ws.mean_rstd);
+    HOWL_LAUNCHED(ctx);
+  }
+  const size_t csm = conv_smem_bytes(H);
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+  const int grid = r8_grid(ctx, B);
+  const double count = (double)B * HW;
+  for (int i = 1; i <= R8_LAYERS; ++i) {
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = (i == 1) ? ws.a0 : ws.u[i - 2];
+    if (i > 1) {
+      p.in_mean = ws.mean_rstd + (i - 2) * 2 * R8_C;
+      p.in_rstd = p.in_mean + R8_C;
+    }
+    p.w = wl + (size_t)(i - 1) * R8_KW;
+    p.res = (i % 2 == 0) ? ((i == 2) ? ws.a0 : ws.u[i - 3]) : nullptr;
+    p.out = ws.u[i - 1];
+    p.B = B;
+    p.H = H;
+    if (train) {
+      p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
+      conv3x3_kernel<true, 1><<<grid, CV_THREADS, csm, st>>>(p);
+      HOWL_LAUNCHED(ctx);
+      bn_finalize_kernel<<<1, 64, 0, st>>>(p.stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C,
+                                           bn_running + (i - 1) * 2 * R8_C,
+                                           num_batches_tracked ? num_batches_tracked + (i - 1) : nullptr);
+      HOWL_LAUNCHED(ctx);
+    } else {
+      conv3x3_kernel<true, 0><<<grid, CV_THREADS, csm, st>>>(p);
+      HOWL_LAUNCHED(ctx);
+    }
+  }
+  head_fwd_kernel<<<(unsigned)B, 128, 0, st>>>(ws.u[5], ws.mean_rstd + 5 * 2 * R8_C, wout, bout, ws.pooled, logits,
+                                               ws.logits, HW, L);
+  HOWL_LAUNCHED(ctx);
+  return HOWL_OK;
+}
+
+extern "C" int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* labels, int64_t B,
+                                  int32_t frames, int32_t n_mels, int32_t num_labels, int64_t loss_scale_batch,
+                                  const float* params, float* grads, float* loss, void* workspace,
+                                  size_t workspace_bytes) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, feats && labels && params && grads && loss, HOWL_E_INVALID, "res8_bwd: null pointer");
+  HOWL_REQUIRE(ctx, loss_scale_batch >= 1, HOWL_E_INVALID, "res8_bwd: loss_scale_batch must be >= 1");
+  R8Ws ws;
+  int rc = r8_check(ctx, B, frames, n_mels, num_labels, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = frames / 3, HW = H * R8_W, L = num_labels;
+  const float* w0 = params;
+  const float* wl = params + R8_C * 9;
+  const float* wout = wl + (size_t)R8_LAYERS * R8_KW;
+  float* g_w0 = grads;
+  float* g_wl = grads + R8_C * 9;
+  float* g_wout = g_wl + (size_t)R8_LAYERS * R8_KW;
+  float* g_bout = g_wout + (size_t)L * R8_C;
+  const int64_t nparam = howl_b200_res8_param_count(L);
+  HOWL_CUDA(ctx, cudaMemsetAsync(grads, 0, sizeof(float) * nparam, st));
+  HOWL_CUDA(ctx, cudaMemsetAsync(ws.stats_bwd, 0, sizeof(double) * R8_LAYERS * 2 * R8_C, st));
+  HOWL_CUDA(ctx, cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * 2, st));
+
+  transpose_weights_kernel<<<(R8_LAYERS * R8_KW + 255) / 256, 256, 0, st>>>(wl, ws.wT);
+  HOWL_LAUNCHED(ctx);
+  head_bwd_kernel<<<(unsigned)howl_ceil_div(B, 128), 128, 0, st>>>(ws.logits, labels, wout, ws.dlogits, ws.dh,
+                                                                   ws.loss_acc, B, L, 1.f / (float)loss_scale_batch);
+  HOWL_LAUNCHED(ctx);
+  head_wgrad_kernel<<<L + 2, 256, 0, st>>>(ws.dlogits, ws.pooled, ws.dh, g_wout, g_bout,
+                                           ws.stats_bwd + 5 * 2 * R8_C, ws.loss_acc, loss, B, L);
+  HOWL_LAUNCHED(ctx);
+
+  const size_t csm = conv_smem_bytes(H), wsm = wgrad_smem_bytes(H);
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+  const int grid = r8_grid(ctx, B);
+  const double count = (double)B * HW;
+  const int64_t n2 = (int64_t)B * R8_C * HW / 2;
+  int64_t ablocks = howl_ceil_div(n2, 256);
+  if (ablocks > (int64_t)ctx->sm_count * 16) ablocks = (int64_t)ctx->sm_count * 16;
+
+  for (int i = R8_LAYERS; i >= 1; --i) {
+    const bool even = (i % 2 == 0);
+    ApplyParams a;
+    memset(&a, 0, sizeof(a));
+    if (i == R8_LAYERS) a.g_bcast = ws.dh; else a.g = ws.g;
+    a.u = ws.u[i - 1];
+    a.mean_rstd = ws.mean_rstd + (i - 1) * 2 * R8_C;
+    a.stats = ws.stats_bwd + (i - 1) * 2 * R8_C;
+    if (even) {
+      a.gu_in = (i < R8_LAYERS) ? ws.gu[((i + 2) / 2) & 1] : nullptr;
+      a.gu_out = ws.gu[(i / 2) & 1];
+      a.mask_prev = (i == 2) ? ws.a0 : ws.u[i - 3];
+    }
+    a.dc = ws.dc;
+    a.n2 = n2;
+    a.HW = HW;
+    a.count = count;
+    bn_bwd_apply_kernel<<<(unsigned)ablocks, 256, 0, st>>>(a);
+    HOWL_LAUNCHED(ctx);
+
+    WgradParams wg;
+    memset(&wg, 0, sizeof(wg));
+    wg.dc = ws.dc;
+    wg.x = (i == 1) ? ws.a0 : ws.u[i - 2];
+    if (i > 1) {
+      wg.x_mean = ws.mean_rstd + (i - 2) * 2 * R8_C;
+      wg.x_rstd = wg.x_mean + R8_C;
+    }
+    wg.dw = g_wl + (size_t)(i - 1) * R8_KW;
+    wg.B = B;
+    wg.H = H;
+    conv3x3_wgrad_kernel<<<grid, WG_THREADS, wsm, st>>>(wg);
+    HOWL_LAUNCHED(ctx);
+
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = ws.dc;
+    p.w = ws.wT + (size_t)(i - 1) * R8_KW;
+    p.out = ws.g;
+    p.B = B;
+    p.H = H;
+    if (i > 1) {
+      p.stats = ws.stats_bwd + (i - 2) * 2 * R8_C;
+      p.aux = ws.u[i - 2];
+      p.aux_mean = ws.mean_rstd + (i - 2) * 2 * R8_C;
+      p.aux_rstd = p.aux_mean + R8_C;
+      conv3x3_kernel<false, 2><<<grid, CV_THREADS, csm, st>>>(p);
+    } else {
+      conv3x3_kernel<false, 0><<<grid, CV_THREADS, csm, st>>>(p);
+    }
+    HOWL_LAUNCHED(ctx);
+  }
+  {
+    const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + 2 * R8_C * 9);
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int g0 = (int)(B < 2LL * ctx->sm_count ? B : 2LL * ctx->sm_count);
+    conv0_bwd_kernel<<<g0, C0_THREADS, sm, st>>>(feats, w0, ws.g, ws.gu[1], g_w0, B, frames, H);
+    HOWL_LAUNCHED(ctx);
+  }
+  return HOWL_OK;
+}

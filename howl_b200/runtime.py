@@ -1,0 +1,162 @@
+"""Thin torch-tensor wrapper over the C ABI: owns a howl_ctx_t and hands device pointers to the library.
+
+PyTorch is plumbing here (device memory, streams); every computation is done by libhowl_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import FE_MELS_ONLY, FE_STACKED, FE_TIME_MAJOR, FE_ZMUV, HowlB200Error
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _check(t: torch.Tensor, dtype, device, name: str):
+    if t.dtype != dtype or t.device != device or not t.is_contiguous():
+        raise HowlB200Error(f"{name}: need contiguous {dtype} tensor on {device}, got {t.dtype} {t.device} "
+                            f"contiguous={t.is_contiguous()}")
+
+
+class Context:
+    """One per (device, thread).  Mirrors howl_ctx_t."""
+
+    def __init__(self, device="cuda:0", n_mels: int = 40, sample_rate: int = 16000, n_fft: int = 512, hop: int = 200):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise HowlB200Error("howl_b200 runs on CUDA devices only (no CPU fallback)")
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        self.n_mels, self.hop, self.n_fft, self.sample_rate = n_mels, hop, n_fft, sample_rate
+        cfg = _lib.FrontendCfg(sample_rate, n_fft, hop, n_mels)
+        handle = C.c_void_p()
+        rc = self.lib.howl_b200_create(index, C.byref(cfg), C.byref(handle))
+        if rc != 0:
+            raise HowlB200Error(f"howl_b200_create failed ({rc}): {self.lib.howl_b200_last_error(None).decode()}")
+        self.handle = handle
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.howl_b200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _rc(self, rc: int, what: str):
+        if rc != 0:
+            raise HowlB200Error(f"{what} failed ({rc}): {self.lib.howl_b200_last_error(self.handle).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.howl_b200_launch_count(self.handle))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.howl_b200_sm_count(self.handle))
+
+    def num_frames(self, samples: int) -> int:
+        return int(self.lib.howl_b200_num_frames(samples, self.hop))
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ frontend
+    def frontend(self, pcm: torch.Tensor, fb: torch.Tensor, layout: str = "stacked", zmuv=None,
+                 rects: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """layout: 'stacked' [B,3,M,F] | 'mels' [B,M,F] | 'time_major' [B,F,M]; zmuv = (mean, std) or None."""
+        _check(pcm, torch.float32, self.device, "pcm")
+        _check(fb, torch.float32, self.device, "fb")
+        if pcm.dim() != 2 or tuple(fb.shape) != (self.n_fft // 2 + 1, self.n_mels):
+            raise HowlB200Error(f"frontend: pcm must be [B,T] and fb [{self.n_fft // 2 + 1},{self.n_mels}]")
+        b, t = pcm.shape
+        f = self.num_frames(t)
+        flag = {"stacked": FE_STACKED, "mels": FE_MELS_ONLY, "time_major": FE_TIME_MAJOR}[layout]
+        shape = {"stacked": (b, 3, self.n_mels, f), "mels": (b, self.n_mels, f), "time_major": (b, f, self.n_mels)}[layout]
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        _check(out, torch.float32, self.device, "out")
+        mean, std = 0.0, 1.0
+        if zmuv is not None:
+            mean, std = float(zmuv[0]), float(zmuv[1])
+            flag |= FE_ZMUV
+        if rects is not None:
+            _check(rects, torch.int32, self.device, "rects")
+        self._rc(self.lib.howl_b200_frontend_fwd(self.handle, self._stream(), _ptr(pcm), b, t, _ptr(fb), mean, std,
+                                                 _ptr(rects), flag, _ptr(out)), "frontend_fwd")
+        return out
+
+    def sum_sumsq(self, x: torch.Tensor, sums: torch.Tensor) -> None:
+        _check(x, torch.float32, self.device, "x")
+        _check(sums, torch.float64, self.device, "sums")
+        self._rc(self.lib.howl_b200_sum_sumsq(self.handle, self._stream(), _ptr(x), x.numel(), _ptr(sums)), "sum_sumsq")
+
+    # ------------------------------------------------------------------ res8
+    def res8_param_count(self, num_labels: int) -> int:
+        return int(self.lib.howl_b200_res8_param_count(num_labels))
+
+    def res8_workspace_bytes(self, batch: int, frames: int, num_labels: int, train: bool = True) -> int:
+        n = int(self.lib.howl_b200_res8_workspace_bytes(batch, frames, self.n_mels, num_labels, int(train)))
+        if n < 0:
+            raise HowlB200Error(f"res8: unsupported shape B={batch} frames={frames} mels={self.n_mels} L={num_labels}")
+        return n
+
+    def res8_fwd(self, feats, params, bn_running, nbt, train: bool, ws: torch.Tensor, logits=None):
+        b, f, m = feats.shape
+        num_labels = self._labels_from_params(params)
+        if logits is None:
+            logits = torch.empty(b, num_labels, dtype=torch.float32, device=self.device)
+        self._rc(self.lib.howl_b200_res8_fwd(self.handle, self._stream(), _ptr(feats), b, f, m, num_labels, _ptr(params),
+                                             _ptr(bn_running), _ptr(nbt), int(train), _ptr(logits), _ptr(ws),
+                                             ws.numel()), "res8_fwd")
+        return logits
+
+    def res8_bwd(self, feats, labels, params, grads, loss, ws, loss_scale_batch: Optional[int] = None):
+        b, f, m = feats.shape
+        num_labels = self._labels_from_params(params)
+        _check(labels, torch.int64, self.device, "labels")
+        self._rc(self.lib.howl_b200_res8_bwd(self.handle, self._stream(), _ptr(feats), _ptr(labels), b, f, m, num_labels,
+                                             loss_scale_batch or b, _ptr(params), _ptr(grads), _ptr(loss), _ptr(ws),
+                                             ws.numel()), "res8_bwd")
+
+    def adamw(self, params, grads, m, v, step: int, lr: float, weight_decay: float, betas=(0.9, 0.999), eps=1e-8):
+        self._rc(self.lib.howl_b200_adamw(self.handle, self._stream(), _ptr(params), _ptr(grads), _ptr(m), _ptr(v),
+                                          params.numel(), step, lr, betas[0], betas[1], eps, weight_decay), "adamw")
+
+    def res8_train_step(self, pcm, labels, fb, zmuv, params, bn_running, nbt, grads, m, v, step, lr, weight_decay,
+                        loss, logits, ws, rects=None):
+        b, t = pcm.shape
+        num_labels = self._labels_from_params(params)
+        self._rc(self.lib.howl_b200_res8_train_step(
+            self.handle, self._stream(), _ptr(pcm), _ptr(labels), b, t, _ptr(fb), float(zmuv[0]), float(zmuv[1]),
+            _ptr(rects), num_labels, _ptr(params), _ptr(bn_running), _ptr(nbt), _ptr(grads), _ptr(m), _ptr(v), step,
+            lr, weight_decay, _ptr(loss), _ptr(logits), _ptr(ws), ws.numel()), "res8_train_step")
+
+    def train_step_workspace_bytes(self, batch: int, samples: int, num_labels: int) -> int:
+        f = self.num_frames(samples)
+        feat = (batch * f * self.n_mels * 4 + 255) // 256 * 256
+        return feat + self.res8_workspace_bytes(batch, f, num_labels, True)
+
+    @staticmethod
+    def _labels_from_params(params: torch.Tensor) -> int:
+        n = params.numel() - 45 * 9 - 6 * 45 * 45 * 9
+        if n <= 0 or n % 46:
+            raise HowlB200Error(f"res8: flat parameter buffer of {params.numel()} floats is not a res8 layout")
+        return n // 46

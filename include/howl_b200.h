@@ -1,0 +1,135 @@
+/*
+ * howl_b200.h -- C ABI of libhowl_b200.so: the B200 (sm_100a) implementation of castorini/howl's
+ * data-parallel hot path (audio frontend -> res8 forward/backward -> AdamW).
+ *
+ * The reference (howl @ 4ba5f42) is pure Python and has no FFI of its own; each entry
+ * point below therefore cites the reference *call site* it replaces.  Conventions:
+ *   - extern "C", plain pointers and sizes, no torch / C++ types;
+ *   - every tensor argument is a caller-owned, contiguous DEVICE pointer unless marked "host";
+ *   - calls are asynchronous on the cudaStream_t passed as `void* stream`; no hidden synchronisation;
+ *   - return 0 (HOWL_OK) or a negative HOWL_E_* code; howl_b200_last_error() gives the message;
+ *   - a context is bound to one device and is not thread-safe.
+ * INTEGRATION.md shows the ctypes binding a howl maintainer would add.
+ */
+#ifndef HOWL_B200_H_
+#define HOWL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOWL_B200_ABI_VERSION 1
+
+enum {
+  HOWL_OK = 0,
+  HOWL_E_INVALID = -1,     /* bad argument (null pointer, size out of range, T <= n_fft/2, ...) */
+  HOWL_E_CUDA = -2,        /* a CUDA runtime call or kernel launch failed */
+  HOWL_E_UNSUPPORTED = -3, /* configuration outside what the kernels are built for */
+  HOWL_E_WORKSPACE = -4    /* caller-supplied workspace too small */
+};
+
+/* frontend output layouts / options (flags argument of howl_b200_frontend_fwd) */
+enum {
+  HOWL_FE_TIME_MAJOR = 0x1, /* out = [B, F, M] log-mel only: the [B,1,F,M] tensor Res8.forward builds at cnn.py:128-129 */
+  HOWL_FE_MELS_ONLY = 0x2,  /* out = [B, M, F]   (StandardAudioTransform(..., mels_only=True), transform.py:276-277) */
+  HOWL_FE_STACKED = 0x4,    /* out = [B, 3, M, F] log-mel, delta, delta-delta (transform.py:278-280) */
+  HOWL_FE_ZMUV = 0x10       /* apply (x - mean) / std afterwards (ZmuvTransform.forward, operator.py:145-146) */
+};
+
+typedef struct howl_ctx howl_ctx_t;
+
+typedef struct {
+  int32_t sample_rate; /* 16000 (SETTINGS.audio_transform.sample_rate, settings.py:33) */
+  int32_t n_fft;       /* 512 only (settings.py:31) */
+  int32_t hop;         /* 200 (settings.py:34) */
+  int32_t n_mels;      /* 1..128 (NUM_MELS; settings.py:32) */
+} howl_frontend_cfg;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int howl_b200_abi_version(void);
+/* Replaces: StandardAudioTransform.__init__ (howl/data/transform/transform.py:237-264). */
+int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_ctx_t** out_ctx);
+void howl_b200_destroy(howl_ctx_t* ctx);
+const char* howl_b200_last_error(const howl_ctx_t* ctx); /* ctx may be NULL: last create() error */
+int howl_b200_sm_count(const howl_ctx_t* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t howl_b200_launch_count(const howl_ctx_t* ctx);
+
+/* ---- integer frame arithmetic (host; bit exact) ------------------------------------------------ */
+/* torch.stft(center=True): 1 + floor(T / hop).  Replaces the implicit frame count of transform.py:249-254. */
+int64_t howl_b200_num_frames(int64_t num_samples, int32_t hop);
+/* StandardAudioTransform.compute_lengths (transform.py:290-296): floor((len - win) / hop) + 1, host arrays. */
+int howl_b200_compute_lengths(const int64_t* lengths, int64_t n, int32_t win, int32_t hop, int64_t* out);
+
+/* ---- K1: fused audio frontend --------------------------------------------------------------- */
+/*
+ * Replaces: `zmuv_transform(audio_transform(batch.audio_data))` (training/run/train.py:289), i.e.
+ * StandardAudioTransform._execute_op (transform.py:271-280) + ZmuvTransform.forward (operator.py:145-146)
+ * + SpecAugmentTransform.fmask/tmask (transform.py:310-326).
+ *   pcm    [B, T] f32
+ *   fb     [n_fft/2+1, n_mels] f32: the mel filterbank (standard or the VTLP matrix drawn for this call)
+ *   rects  [B, 4] i32 (f0, f_len, t0, t_len) SpecAugment rectangles drawn on the host, or NULL
+ *   out    layout per `flags`
+ * T must exceed n_fft/2 (reflect padding, as torch.stft requires).
+ */
+int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float* pcm, int64_t B, int64_t T, const float* fb,
+                           float zmuv_mean, float zmuv_std, const int32_t* rects, uint32_t flags, float* out);
+
+/* Sum and sum of squares of n floats into sums[2] (f64, ACCUMULATED onto the existing contents).
+ * Replaces the two reductions of ZmuvTransform.update (operator.py:126-135). */
+int howl_b200_sum_sumsq(howl_ctx_t* ctx, void* stream, const float* x, int64_t n, double* sums);
+
+/* ---- res8 ----------------------------------------------------------------------------------- */
+/* Flat parameter layout (state_dict order):
+ *   conv0.weight[45,1,3,3] | conv1..6.weight[45,45,3,3] | output.weight[L,45] | output.bias[L]
+ * BN running statistics: bn_running[6][2][45] f32 (mean, var per layer), num_batches_tracked[6] i64. */
+int64_t howl_b200_res8_param_count(int32_t num_labels);
+/* Bytes of workspace for a batch of B clips of `frames` x `n_mels` features (train != 0: keeps activations). */
+int64_t howl_b200_res8_workspace_bytes(int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels, int train);
+
+/*
+ * Res8.forward (howl/model/cnn.py:127-145) on time-major features [B, F, M] (HOWL_FE_TIME_MAJOR output).
+ * train != 0: batch statistics + running-stat update (nn.BatchNorm2d(affine=False) semantics) and the
+ * activations are kept in `workspace` for howl_b200_res8_bwd.  Writes logits [B, L].
+ */
+int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* feats, int64_t B, int32_t frames, int32_t n_mels,
+                       int32_t num_labels, const float* params, float* bn_running, int64_t* num_batches_tracked,
+                       int train, float* logits, void* workspace, size_t workspace_bytes);
+
+/*
+ * CrossEntropyLoss(mean) + loss.backward() (training/run/train.py:293,299-301) for the forward kept in
+ * `workspace`.  labels [B] i64.  `loss_scale_batch` is the batch size the mean is taken over (B, or the
+ * global batch under data parallelism so that an allreduce(SUM) of `grads` yields the global-mean gradient).
+ * grads (flat layout) is OVERWRITTEN; loss[1] f32 receives sum_b nll_b / loss_scale_batch.
+ */
+int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* labels, int64_t B,
+                       int32_t frames, int32_t n_mels, int32_t num_labels, int64_t loss_scale_batch,
+                       const float* params, float* grads, float* loss, void* workspace, size_t workspace_bytes);
+
+/* ---- K4: fused AdamW over a flat buffer ------------------------------------------------------- */
+/* torch.optim.AdamW.step (training/run/train.py:256,302): decoupled weight decay, bias correction,
+ * eps outside the sqrt; `step` is 1-based. */
+int howl_b200_adamw(howl_ctx_t* ctx, void* stream, float* params, const float* grads, float* exp_avg,
+                    float* exp_avg_sq, int64_t n, int64_t step, float lr, float beta1, float beta2, float eps,
+                    float weight_decay);
+
+/* ---- whole train step (single device, no collective) ---------------------------------------------- */
+/*
+ * One iteration of the loop body training/run/train.py:287-302 for res8 / frame objective:
+ * frontend -> Res8 -> CE -> backward -> AdamW, PCM in, updated parameters out.
+ * Under data parallelism call frontend_fwd + res8_fwd + res8_bwd, allreduce `grads`, then adamw.
+ */
+int howl_b200_res8_train_step(howl_ctx_t* ctx, void* stream, const float* pcm, const int64_t* labels, int64_t B,
+                              int64_t T, const float* fb, float zmuv_mean, float zmuv_std, const int32_t* rects,
+                              int32_t num_labels, float* params, float* bn_running, int64_t* num_batches_tracked,
+                              float* grads, float* exp_avg, float* exp_avg_sq, int64_t step, float lr,
+                              float weight_decay, float* loss, float* logits, void* workspace,
+                              size_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOWL_B200_H_ */

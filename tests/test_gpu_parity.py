@@ -1,0 +1,253 @@
+"""GPU parity: libhowl_b200.so (through the C ABI) against the CPU oracle and the committed golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import howl_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = ATOL = 1e-4  # north_star: 1e-4 relative fp32, implemented as allclose(rtol, atol)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import howl_b200
+
+    c = howl_b200.Context("cuda:0", n_mels=40)
+    yield c
+    c.close()
+
+
+DEV = torch.device("cuda:0")
+
+
+def _bn_dev(bn):
+    return torch.stack([torch.stack([bn[f"bn{i}.running_mean"], bn[f"bn{i}.running_var"]]) for i in range(1, 7)]).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------ frontend
+@pytest.mark.parametrize("tag", ["t8000", "t16000", "t4567", "t1000", "speech", "zeros"])
+def test_frontend_stacked_matches_golden(ctx, golden, tag):
+    g = golden("frontend")
+    fb = torch.from_numpy(g["fb"]).to(DEV)
+    out = ctx.frontend(torch.from_numpy(g[f"{tag}_pcm"]).to(DEV), fb, "stacked").cpu().numpy()
+    assert out.shape == g[f"{tag}_out"].shape
+    np.testing.assert_allclose(out, g[f"{tag}_out"], rtol=RTOL, atol=ATOL)
+
+
+def test_frontend_layouts_agree(ctx, golden):
+    g = golden("frontend")
+    fb = torch.from_numpy(g["fb"]).to(DEV)
+    pcm = torch.from_numpy(g["t16000_pcm"]).to(DEV)
+    stacked = ctx.frontend(pcm, fb, "stacked")
+    mels = ctx.frontend(pcm, fb, "mels")
+    tm = ctx.frontend(pcm, fb, "time_major")
+    assert torch.equal(stacked[:, 0], mels)
+    assert torch.equal(mels.transpose(1, 2).contiguous(), tm)
+    np.testing.assert_allclose(mels.cpu().numpy(), g["t16000_mels_only"], rtol=RTOL, atol=ATOL)
+
+
+def test_frontend_zmuv_and_specaugment(ctx, golden):
+    g, sa, z = golden("frontend"), golden("specaugment"), golden("zmuv")
+    fb = torch.from_numpy(g["fb"]).to(DEV)
+    pcm = torch.from_numpy(g["t8000_pcm"]).to(DEV)
+    mean, std = float(z["mean"][0]), float(z["std"][0])
+    out = ctx.frontend(pcm, fb, "stacked", zmuv=(mean, std)).cpu().numpy()
+    np.testing.assert_allclose(out, z["fwd_out"], rtol=RTOL, atol=ATOL)
+    rects = torch.from_numpy(sa["rects"].astype(np.int32)).to(DEV)
+    masked = ctx.frontend(pcm, fb, "stacked", rects=rects).cpu().numpy()
+    np.testing.assert_allclose(masked, sa["out"], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(masked == 0, sa["out"] == 0)  # mask rectangles are index-exact
+    tm = ctx.frontend(pcm, fb, "time_major", rects=rects).cpu().numpy()
+    np.testing.assert_allclose(tm, sa["out"][:, 0].transpose(0, 2, 1), rtol=RTOL, atol=ATOL)
+
+
+def test_frontend_vtlp_filterbanks(ctx, golden):
+    g, v = golden("frontend"), golden("vtlp")
+    pcm = torch.from_numpy(g["t8000_pcm"]).to(DEV)
+    for k in range(4):
+        a = v["train_alphas"][k]
+        fb = O.vtlp_filterbank(float(a), 40) if a > 0 else O.mel_filterbank(40)
+        out = ctx.frontend(pcm, fb.to(DEV), "stacked").cpu().numpy()
+        np.testing.assert_allclose(out, v["train_outs"][k], rtol=RTOL, atol=ATOL)
+    fb = O.vtlp_filterbank(1.0999, 40)  # degenerate triangles: 744 non-zeros, weights up to 17.9
+    out = ctx.frontend(pcm, fb.to(DEV), "mels").cpu().numpy()
+    np.testing.assert_allclose(out, O.log_mel_f32(pcm.cpu(), fb).numpy(), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("shape", [(5, 257), (3, 300), (2, 5400), (1, 5403), (7, 16000), (1, 35774)])
+def test_frontend_ragged_shapes_vs_oracle(ctx, shape):
+    pcm, _ = O.synthetic_batch(shape[0], shape[1], 4, seed=shape[1])
+    fb = O.mel_filterbank(40)
+    out = ctx.frontend(pcm.to(DEV), fb.to(DEV), "stacked").cpu().numpy()
+    want = O.standard_audio_transform_f32(pcm, fb).numpy()
+    assert out.shape == want.shape and out.shape[-1] == O.num_frames(shape[1])
+    np.testing.assert_allclose(out, want, rtol=RTOL, atol=ATOL)
+
+
+def test_frontend_rejects_short_clip(ctx):
+    import howl_b200
+
+    with pytest.raises(howl_b200.HowlB200Error):
+        ctx.frontend(torch.zeros(1, 256, device=DEV), O.mel_filterbank(40).to(DEV), "mels")
+
+
+def test_frontend_80_mels(golden):
+    import howl_b200
+
+    c = howl_b200.Context("cuda:0", n_mels=80)
+    pcm, _ = O.synthetic_batch(2, 8000, 4, seed=3)
+    fb = O.mel_filterbank(80)
+    out = c.frontend(pcm.to(DEV), fb.to(DEV), "stacked").cpu().numpy()
+    np.testing.assert_allclose(out, O.standard_audio_transform_f32(pcm, fb).numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_sum_sumsq(ctx):
+    x = torch.randn(1_000_003, device=DEV)
+    sums = torch.zeros(2, dtype=torch.float64, device=DEV)
+    ctx.sum_sumsq(x, sums)
+    ctx.sum_sumsq(x[:1000].contiguous(), sums)
+    xd = x.double()
+    want = torch.stack([xd.sum() + xd[:1000].sum(), (xd * xd).sum() + (xd[:1000] ** 2).sum()])
+    np.testing.assert_allclose(sums.cpu().numpy(), want.cpu().numpy(), rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ res8
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def test_res8_eval_real_weights(ctx, golden):
+    g = golden("res8_heyfirefox")
+    sd = _sd(g, "sd.")
+    L = 4
+    flat = O.flatten(sd, L).to(DEV)
+    bn = _bn_dev(sd)
+    nbt = torch.zeros(6, dtype=torch.int64, device=DEV)
+    pcm = torch.from_numpy(g["pcm"]).to(DEV)
+    mean = float(g["zmuv.mean"][0])
+    std = float(np.sqrt(g["zmuv.mean2"][0] - g["zmuv.mean"][0] ** 2))
+    feats = ctx.frontend(pcm, O.mel_filterbank(40).to(DEV), "time_major", zmuv=(mean, std))
+    np.testing.assert_allclose(feats.cpu().numpy(), g["feats"][:, 0].transpose(0, 2, 1), rtol=RTOL, atol=ATOL)
+    ws = ctx.workspace(ctx.res8_workspace_bytes(pcm.shape[0], feats.shape[1], L, False))
+    bn_before = bn.clone()
+    logits = ctx.res8_fwd(feats, flat, bn, nbt, False, ws).cpu().numpy()
+    np.testing.assert_allclose(logits, g["logits"], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(logits.argmax(1), g["logits"].argmax(1))
+    assert torch.equal(bn, bn_before) and int(nbt.sum()) == 0  # eval leaves running stats alone
+
+
+def test_res8_train_steps_match_reference(ctx, golden):
+    g = golden("res8_train")
+    L = 12
+    init = _sd(g, "init.")
+    flat = O.flatten(init, L).to(DEV)
+    bn = _bn_dev(init)
+    nbt = torch.zeros(6, dtype=torch.int64, device=DEV)
+    grads, m, v = torch.zeros_like(flat), torch.zeros_like(flat), torch.zeros_like(flat)
+    loss = torch.zeros(1, device=DEV)
+    pcm, labels = torch.from_numpy(g["pcm"]).to(DEV), torch.from_numpy(g["labels"]).to(DEV)
+    B, T = pcm.shape
+    logits = torch.zeros(B, L, device=DEV)
+    mean = float(g["zmuv_mean"][0])
+    std = float(np.sqrt(g["zmuv_mean2"][0] - g["zmuv_mean"][0] ** 2))
+    fb = O.mel_filterbank(40).to(DEV)
+    ws = ctx.workspace(ctx.train_step_workspace_bytes(B, T, L))
+    lr, wd = float(g["lr"]), float(g["wd"])
+    for step in (1, 2, 3):
+        ctx.res8_train_step(pcm, labels, fb, (mean, std), flat, bn, nbt, grads, m, v, step, lr, wd, loss, logits, ws)
+        np.testing.assert_allclose(loss.item(), g[f"step{step}.loss"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(logits.cpu().numpy(), g[f"step{step}.logits"], rtol=RTOL, atol=ATOL)
+        got_g = O.unflatten(grads.cpu(), L)
+        got_p = O.unflatten(flat.cpu(), L)
+        for k in got_g:
+            np.testing.assert_allclose(got_g[k].numpy(), g[f"step{step}.grad.{k}"], rtol=1e-3, atol=1e-5)
+            want = g[f"step{step}.sd.{k}"]
+            diff = np.abs(got_p[k].numpy() - want)
+            # AdamW's first steps are sign-like in g: statistical bound, then teacher-force (see test_oracle_golden)
+            assert (diff > 5e-4).mean() <= 1e-3 and diff.max() <= 2.5 * lr
+        for i in range(1, 7):
+            np.testing.assert_allclose(bn[i - 1, 0].cpu().numpy(), g[f"step{step}.sd.bn{i}.running_mean"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(bn[i - 1, 1].cpu().numpy(), g[f"step{step}.sd.bn{i}.running_var"], rtol=1e-4, atol=1e-5)
+        assert nbt.tolist() == [step] * 6
+        want_sd = {k: torch.from_numpy(g[f"step{step}.sd.{k}"]) for k, _ in O.res8_param_shapes(L)}
+        flat.copy_(O.flatten(want_sd, L).to(DEV))
+
+
+@pytest.mark.parametrize("B,T,L", [(1, 8000, 4), (3, 8000, 5), (5, 16000, 30), (2, 12345, 12), (200, 8000, 4)])
+def test_res8_train_step_vs_oracle(ctx, B, T, L):
+    pcm, labels = O.synthetic_batch(B, T, L, seed=B * 7 + L)
+    params, bn = O.res8_init(L, seed=B), O.res8_bn_init()
+    fb = O.mel_filterbank(40)
+    zmean, zstd = -1.78896, 3.93389
+    flat = O.flatten(params, L).to(DEV)
+    bnd = _bn_dev(bn)
+    nbt = torch.zeros(6, dtype=torch.int64, device=DEV)
+    grads, m, v = torch.zeros_like(flat), torch.zeros_like(flat), torch.zeros_like(flat)
+    loss, logits = torch.zeros(1, device=DEV), torch.zeros(B, L, device=DEV)
+    ws = ctx.workspace(ctx.train_step_workspace_bytes(B, T, L))
+    ctx.res8_train_step(pcm.to(DEV), labels.to(DEV), fb.to(DEV), (zmean, zstd), flat, bnd, nbt, grads, m, v, 1, 0.01, 1e-5,
+                        loss, logits, ws)
+    feats = O.hot_path_features(pcm, fb, torch.tensor([zmean]), torch.tensor([zmean ** 2 + zstd ** 2]))
+    om = {k: torch.zeros_like(p) for k, p in params.items()}
+    ov = {k: torch.zeros_like(p) for k, p in params.items()}
+    if B == 1:
+        # BatchNorm over a single clip is still fine (270 / 130 pixels per channel)
+        pass
+    oloss, ologits, ograds = O.res8_train_step(feats, labels, params, bn, om, ov, 1, 0.01, 1e-5)
+    np.testing.assert_allclose(logits.cpu().numpy(), ologits.numpy(), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(loss.item(), oloss.item(), rtol=RTOL, atol=ATOL)
+    og = O.flatten(ograds, L).numpy()
+    gg = grads.cpu().numpy()
+    scale = np.abs(og).max()
+    np.testing.assert_allclose(gg, og, rtol=1e-3, atol=1e-4 * scale)
+    for i in range(1, 7):
+        np.testing.assert_allclose(bnd[i - 1, 0].cpu().numpy(), bn[f"bn{i}.running_mean"].numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(bnd[i - 1, 1].cpu().numpy(), bn[f"bn{i}.running_var"].numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_adamw_matches_torch(ctx):
+    torch.manual_seed(0)
+    n = 109939
+    p = torch.randn(n, device=DEV)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=0.01, weight_decay=1e-2)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn(n, device=DEV) * 10.0 ** (-step)
+        ref.grad = g.clone()
+        opt.step()
+        ctx.adamw(p, g, m, v, step, 0.01, 1e-2)
+        np.testing.assert_allclose(p.cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_data_parallel_grad_identity(ctx):
+    """Sharded batches with loss_scale_batch = global batch sum to the full-batch gradient when BN stats are per shard
+    identical -- here checked in the degenerate way the DP path relies on: two half batches, each scaled by 1/B_global,
+    equal the oracle run on each half scaled accordingly (per-rank BN statistics, DDP semantics)."""
+    L, T, B = 4, 8000, 6
+    pcm, labels = O.synthetic_batch(B, T, L, seed=42)
+    params = O.res8_init(L, seed=1)
+    fb = O.mel_filterbank(40)
+    zmean, zstd = -1.78896, 3.93389
+    flat = O.flatten(params, L).to(DEV)
+    total = torch.zeros_like(flat)
+    want = torch.zeros(flat.numel())
+    for half in range(2):
+        sl = slice(half * 3, half * 3 + 3)
+        bn = O.res8_bn_init()
+        bnd = _bn_dev(bn)
+        nbt = torch.zeros(6, dtype=torch.int64, device=DEV)
+        feats = ctx.frontend(pcm[sl].to(DEV), fb.to(DEV), "time_major", zmuv=(zmean, zstd))
+        ws = ctx.workspace(ctx.res8_workspace_bytes(3, feats.shape[1], L))
+        ctx.res8_fwd(feats, flat, bnd, nbt, True, ws)
+        grads, loss = torch.zeros_like(flat), torch.zeros(1, device=DEV)
+        ctx.res8_bwd(feats, labels[sl].to(DEV), flat, grads, loss, ws, loss_scale_batch=B)
+        total += grads
+        f = O.hot_path_features(pcm[sl], fb, torch.tensor([zmean]), torch.tensor([zmean ** 2 + zstd ** 2]))
+        leaves = {k: p.clone().requires_grad_(True) for k, p in params.items()}
+        lg = O.res8_forward(f, leaves, bn, True)
+        (torch.nn.functional.cross_entropy(lg, labels[sl], reduction="sum") / B).backward()
+        want += O.flatten({k: leaves[k].grad for k in leaves}, L)
+    scale = want.abs().max().item()
+    np.testing.assert_allclose(total.cpu().numpy(), want.numpy(), rtol=1e-3, atol=1e-4 * scale)
