@@ -35,6 +35,8 @@ SIGNATURES: Dict[str, tuple] = {
     "howl_b200_last_error": (C.c_char_p, [_vp]),
     "howl_b200_sm_count": (C.c_int, [_vp]),
     "howl_b200_launch_count": (_i64, [_vp]),
+    "howl_b200_profile_begin": (C.c_int, [_vp, _vp]),
+    "howl_b200_profile_end": (C.c_int, [_vp, _vp, _sz, _vp, _i32]),
     "howl_b200_num_frames": (_i64, [_i64, _i32]),
     "howl_b200_compute_lengths": (C.c_int, [_vp, _i64, _i32, _i32, _vp]),
     "howl_b200_frontend_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _vp, _u32, _vp]),

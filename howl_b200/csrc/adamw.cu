@@ -38,7 +38,7 @@ extern "C" int howl_b200_adamw(howl_ctx_t* ctx, void* stream, float* params, con
   if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
   adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, decay, beta1,
                                                                    beta2, eps, step_size, inv_sqrt_bc2);
-  HOWL_LAUNCHED(ctx);
+  HOWL_LAUNCHED(ctx, "adamw");
   return HOWL_OK;
 }
 

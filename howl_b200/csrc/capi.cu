@@ -60,8 +60,39 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
   return HOWL_OK;
 }
 
+extern "C" int howl_b200_profile_begin(howl_ctx_t* ctx, void* stream) {
+  if (!ctx) return HOWL_E_INVALID;
+  if (!ctx->prof_ev[0]) {
+    for (int i = 0; i <= HOWL_PROF_CAP; ++i) HOWL_CUDA(ctx, cudaEventCreate(&ctx->prof_ev[i]));
+  }
+  ctx->prof_stream = (cudaStream_t)stream;
+  ctx->prof_n = 0;
+  ctx->prof_on = 1;
+  HOWL_CUDA(ctx, cudaEventRecord(ctx->prof_ev[0], ctx->prof_stream));
+  return HOWL_OK;
+}
+
+extern "C" int howl_b200_profile_end(howl_ctx_t* ctx, char* names, size_t names_bytes, float* ms, int32_t cap) {
+  if (!ctx || !ms || !names) return HOWL_E_INVALID;
+  ctx->prof_on = 0;
+  if (ctx->prof_n == 0) return 0;
+  HOWL_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[ctx->prof_n]));
+  size_t off = 0;
+  int n = ctx->prof_n < cap ? ctx->prof_n : cap;
+  for (int i = 0; i < n; ++i) {
+    HOWL_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+    const size_t len = strlen(ctx->prof_name[i]) + 1;
+    if (off + len > names_bytes) { n = i; break; }
+    memcpy(names + off, ctx->prof_name[i], len);
+    off += len;
+  }
+  return n;
+}
+
 extern "C" void howl_b200_destroy(howl_ctx_t* ctx) {
   if (!ctx) return;
+  if (ctx->prof_ev[0])
+    for (int i = 0; i <= HOWL_PROF_CAP; ++i) cudaEventDestroy(ctx->prof_ev[i]);
   cudaFree(ctx->d_window);
   cudaFree(ctx->d_tw256);
   cudaFree(ctx->d_tw512);

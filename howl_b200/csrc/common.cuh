@@ -10,6 +10,7 @@
 #define HOWL_NFFT 512
 #define HOWL_NFREQ 257
 #define HOWL_MAX_MELS 128
+#define HOWL_PROF_CAP 1024
 
 struct howl_ctx {
   int device;
@@ -25,6 +26,12 @@ struct howl_ctx {
   int* fb_off;
   float* fbc;
   int64_t launches;
+  // optional per-launch timing
+  int prof_on;
+  int prof_n;
+  cudaStream_t prof_stream;
+  cudaEvent_t prof_ev[HOWL_PROF_CAP + 1];
+  const char* prof_name[HOWL_PROF_CAP];
   char err[512];
 };
 
@@ -53,10 +60,15 @@ extern char g_howl_create_error[512];
   } while (0)
 
 // after a kernel launch: count it and surface launch-configuration errors
-#define HOWL_LAUNCHED(ctx)                \
-  do {                                    \
-    (ctx)->launches++;                    \
-    HOWL_CUDA(ctx, cudaGetLastError());   \
+#define HOWL_LAUNCHED(ctx, name)                                                       \
+  do {                                                                                 \
+    (ctx)->launches++;                                                                 \
+    HOWL_CUDA(ctx, cudaGetLastError());                                                \
+    if ((ctx)->prof_on && (ctx)->prof_n < HOWL_PROF_CAP) {                             \
+      (ctx)->prof_name[(ctx)->prof_n] = (name);                                        \
+      (ctx)->prof_n++;                                                                 \
+      HOWL_CUDA(ctx, cudaEventRecord((ctx)->prof_ev[(ctx)->prof_n], (ctx)->prof_stream)); \
+    }                                                                                  \
   } while (0)
 
 static inline int64_t howl_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

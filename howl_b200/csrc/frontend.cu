@@ -429,7 +429,7 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
   int rc = fe_scratch(ctx);
   if (rc) return rc;
   fb_compact_kernel<<<1, HOWL_MAX_MELS, 0, st>>>(fb, M, ctx->fb_lo, ctx->fb_hi, ctx->fb_off, ctx->fbc);
-  HOWL_LAUNCHED(ctx);
+  HOWL_LAUNCHED(ctx, "fb_compact");
 
   FeParams p;
   p.pcm = pcm; p.fb = fb; p.fbc = ctx->fbc; p.fb_lo = ctx->fb_lo; p.fb_hi = ctx->fb_hi; p.fb_off = ctx->fb_off;
@@ -451,7 +451,7 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
     q.use_tma = p.use_tma && ((reinterpret_cast<uintptr_t>(q.pcm) & 15) == 0);
     grid.y = (unsigned)nb;
     frontend_kernel<<<grid, FE_THREADS, smem, st>>>(q);
-    HOWL_LAUNCHED(ctx);
+    HOWL_LAUNCHED(ctx, "frontend");
   }
   if (flags & HOWL_FE_STACKED) {
     const int64_t rows = B * M;
@@ -464,7 +464,7 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
     if (blocks > cap) blocks = cap;
     deltas_kernel<<<(unsigned)blocks, warps * 32, sm, st>>>(out, rows, M, F, zmuv_mean, zmuv_std,
                                                             (flags & HOWL_FE_ZMUV) ? 1 : 0, rects);
-    HOWL_LAUNCHED(ctx);
+    HOWL_LAUNCHED(ctx, "deltas");
   }
   return HOWL_OK;
 }
@@ -477,6 +477,6 @@ extern "C" int howl_b200_sum_sumsq(howl_ctx_t* ctx, void* stream, const float* x
   const int64_t cap = (int64_t)ctx->sm_count * 8;
   if (blocks > cap) blocks = cap;
   sum_sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, sums);
-  HOWL_LAUNCHED(ctx);
+  HOWL_LAUNCHED(ctx, "sum_sumsq");
   return HOWL_OK;
 }

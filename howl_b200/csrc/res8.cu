@@ -772,13 +772,13 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + R8_C * 9);
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, ws.a0, frames, H);
-    HOWL_LAUNCHED(ctx);
+    HOWL_LAUNCHED(ctx, "conv0_pool");
   }
   if (train) {
     HOWL_CUDA(ctx, cudaMemsetAsync(ws.stats_fwd, 0, sizeof(double) * R8_LAYERS * 2 * R8_C, st));
   } else {
     bn_eval_prepare_kernel<<<R8_LAYERS, 64, 0, st>>>(bn_running, ws.mean_rstd);
-    HOWL_LAUNCHED(ctx);
+    HOWL_LAUNCHED(ctx, "bn_eval_prepare");
   }
   const size_t csm = conv_smem_bytes(H);
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
@@ -801,19 +801,19 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     if (train) {
       p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
       conv3x3_kernel<true, 1><<<grid, CV_THREADS, csm, st>>>(p);
-      HOWL_LAUNCHED(ctx);
+      HOWL_LAUNCHED(ctx, "conv3x3_fwd");
       bn_finalize_kernel<<<1, 64, 0, st>>>(p.stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C,
                                            bn_running + (i - 1) * 2 * R8_C,
                                            num_batches_tracked ? num_batches_tracked + (i - 1) : nullptr);
-      HOWL_LAUNCHED(ctx);
+      HOWL_LAUNCHED(ctx, "bn_finalize");
     } else {
       conv3x3_kernel<true, 0><<<grid, CV_THREADS, csm, st>>>(p);
-      HOWL_LAUNCHED(ctx);
+      HOWL_LAUNCHED(ctx, "conv3x3_fwd");
     }
   }
   head_fwd_kernel<<<(unsigned)B, 128, 0, st>>>(ws.u[5], ws.mean_rstd + 5 * 2 * R8_C, wout, bout, ws.pooled, logits,
                                                ws.logits, HW, L);
-  HOWL_LAUNCHED(ctx);
+  HOWL_LAUNCHED(ctx, "head_fwd");
   return HOWL_OK;
 }
 
@@ -842,13 +842,13 @@ extern "C" int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* fe
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * 2, st));
 
   transpose_weights_kernel<<<(R8_LAYERS * R8_KW + 255) / 256, 256, 0, st>>>(wl, ws.wT);
-  HOWL_LAUNCHED(ctx);
+  HOWL_LAUNCHED(ctx, "transpose_weights");
   head_bwd_kernel<<<(unsigned)howl_ceil_div(B, 128), 128, 0, st>>>(ws.logits, labels, wout, ws.dlogits, ws.dh,
                                                                    ws.loss_acc, B, L, 1.f / (float)loss_scale_batch);
-  HOWL_LAUNCHED(ctx);
+  HOWL_LAUNCHED(ctx, "head_bwd");
   head_wgrad_kernel<<<L + 2, 256, 0, st>>>(ws.dlogits, ws.pooled, ws.dh, g_wout, g_bout,
                                            ws.stats_bwd + 5 * 2 * R8_C, ws.loss_acc, loss, B, L);
-  HOWL_LAUNCHED(ctx);
+  HOWL_LAUNCHED(ctx, "head_wgrad");
 
   const size_t csm = conv_smem_bytes(H), wsm = wgrad_smem_bytes(H);
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
@@ -878,7 +878,7 @@ extern "C" int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* fe
     a.HW = HW;
     a.count = count;
     bn_bwd_apply_kernel<<<(unsigned)ablocks, 256, 0, st>>>(a);
-    HOWL_LAUNCHED(ctx);
+    HOWL_LAUNCHED(ctx, "bn_bwd_apply");
 
     WgradParams wg;
     memset(&wg, 0, sizeof(wg));
@@ -892,7 +892,7 @@ extern "C" int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* fe
     wg.B = B;
     wg.H = H;
     conv3x3_wgrad_kernel<<<grid, WG_THREADS, wsm, st>>>(wg);
-    HOWL_LAUNCHED(ctx);
+    HOWL_LAUNCHED(ctx, "conv3x3_wgrad");
 
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -910,14 +910,14 @@ extern "C" int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* fe
     } else {
       conv3x3_kernel<false, 0><<<grid, CV_THREADS, csm, st>>>(p);
     }
-    HOWL_LAUNCHED(ctx);
+    HOWL_LAUNCHED(ctx, "conv3x3_dgrad");
   }
   {
     const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + 2 * R8_C * 9);
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const int g0 = (int)(B < 2LL * ctx->sm_count ? B : 2LL * ctx->sm_count);
     conv0_bwd_kernel<<<g0, C0_THREADS, sm, st>>>(feats, w0, ws.g, ws.gu[1], g_w0, B, frames, H);
-    HOWL_LAUNCHED(ctx);
+    HOWL_LAUNCHED(ctx, "conv0_bwd");
   }
   return HOWL_OK;
 }

@@ -69,6 +69,20 @@ class Context:
     def sm_count(self) -> int:
         return int(self.lib.howl_b200_sm_count(self.handle))
 
+    def profile_begin(self):
+        self._rc(self.lib.howl_b200_profile_begin(self.handle, self._stream()), "profile_begin")
+
+    def profile_end(self):
+        """-> list of (kernel label, device ms) for every launch since profile_begin()."""
+        cap = 1024
+        names = C.create_string_buffer(cap * 32)
+        ms = (C.c_float * cap)()
+        n = self.lib.howl_b200_profile_end(self.handle, names, len(names), ms, cap)
+        if n < 0:
+            self._rc(n, "profile_end")
+        labels = names.raw.split(b"\0")[:n]
+        return [(labels[i].decode(), float(ms[i])) for i in range(n)]
+
     def num_frames(self, samples: int) -> int:
         return int(self.lib.howl_b200_num_frames(samples, self.hop))
 

@@ -1,0 +1,151 @@
+"""Res8TrainStep -- the fused train step of training/run/train.py:287-302 behind one object.
+
+Owns the flat parameter / optimizer buffers and the activation workspace; every computation is a call into
+libhowl_b200.so.  Data parallelism: each rank runs its shard, one NCCL all-reduce of the flat fp32
+gradient (res8: 110,307 floats at L=12) sits between the backward and the fused AdamW; BatchNorm statistics stay
+per rank (DDP semantics).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from .runtime import Context
+
+
+def res8_param_shapes(num_labels: int):
+    """state_dict order of Res8's trainable tensors (howl/model/cnn.py:114-125)."""
+    shapes = [("conv0.weight", (45, 1, 3, 3))]
+    shapes += [(f"conv{i}.weight", (45, 45, 3, 3)) for i in range(1, 7)]
+    shapes += [("output.weight", (num_labels, 45)), ("output.bias", (num_labels,))]
+    return shapes
+
+
+def init_res8_flat(num_labels: int, seed: int, device) -> torch.Tensor:
+    """PyTorch-default initialisation (kaiming_uniform(a=sqrt 5) == U(+-1/sqrt(fan_in))) into the flat layout."""
+    g = torch.Generator().manual_seed(seed)
+    parts = []
+    for _, shape in res8_param_shapes(num_labels):
+        fan_in = math.prod(shape[1:]) if len(shape) > 1 else 45
+        parts.append(((torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)).reshape(-1))
+    return torch.cat(parts).to(device)
+
+
+def mel_filterbank(n_mels: int, sample_rate: int = 16000, n_freqs: int = 257) -> torch.Tensor:
+    """HTK mel triangles [n_freqs, n_mels] with the torch op sequence of torchaudio's melscale_fbanks (host side;
+    the reference builds the same matrix in MelSpectrogram.__init__, transform.py:249-254)."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_max = 2595.0 * math.log10(1.0 + (float(sample_rate // 2) / 700.0))
+    m_pts = torch.linspace(0.0, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.clamp(torch.minimum(down, up), min=0.0)
+
+
+class Res8TrainStep:
+    def __init__(self, device, num_labels: int, batch: int, samples: int, n_mels: int = 40, lr: float = 0.01,
+                 weight_decay: float = 1e-5, zmuv: Tuple[float, float] = (0.0, 1.0), seed: int = 0, world_size: int = 1):
+        self.ctx = Context(device, n_mels=n_mels)
+        dev = self.ctx.device
+        self.device, self.num_labels, self.batch, self.samples = dev, num_labels, batch, samples
+        self.lr, self.weight_decay, self.zmuv, self.world = lr, weight_decay, zmuv, world_size
+        self.params = init_res8_flat(num_labels, seed, dev)
+        n = self.params.numel()
+        assert n == self.ctx.res8_param_count(num_labels)
+        self.grads, self.m, self.v = (torch.zeros(n, device=dev) for _ in range(3))
+        self.bn_running = torch.stack([torch.zeros(6, 45), torch.ones(6, 45)], 1).contiguous().to(dev)  # [6][2][45]
+        self.nbt = torch.zeros(6, dtype=torch.int64, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        self.logits = torch.zeros(batch, num_labels, device=dev)
+        self.fb = mel_filterbank(n_mels).to(dev)
+        self.frames = self.ctx.num_frames(samples)
+        self.feat_bytes = (batch * self.frames * n_mels * 4 + 255) // 256 * 256
+        self.ws = torch.empty(self.ctx.train_step_workspace_bytes(batch, samples, num_labels), dtype=torch.uint8, device=dev)
+        self.step_count = 0
+        # host-input pipeline (step_host)
+        self._copy_stream = torch.cuda.Stream(dev)
+        self._slots = None
+        self._slot_free = None
+        self._slot_ready = None
+        self._host_loss = torch.zeros(1).pin_memory()
+        self._host_i = 0
+
+    # ------------------------------------------------------------------ device-resident step
+    def step(self, pcm: torch.Tensor, labels: torch.Tensor, rects: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One train step on device tensors; returns the (device) loss tensor of this step."""
+        self.step_count += 1
+        c = self.ctx
+        if self.world == 1:
+            c.res8_train_step(pcm, labels, self.fb, self.zmuv, self.params, self.bn_running, self.nbt, self.grads, self.m,
+                              self.v, self.step_count, self.lr, self.weight_decay, self.loss, self.logits, self.ws, rects)
+        else:
+            import torch.distributed as dist
+
+            feats = self.ws[: self.batch * self.frames * c.n_mels * 4].view(torch.float32).view(self.batch, self.frames, c.n_mels)
+            ws = self.ws[self.feat_bytes:]
+            c.frontend(pcm, self.fb, "time_major", zmuv=self.zmuv, rects=rects, out=feats)
+            c.res8_fwd(feats, self.params, self.bn_running, self.nbt, True, ws, logits=self.logits)
+            c.res8_bwd(feats, labels, self.params, self.grads, self.loss, ws, loss_scale_batch=self.batch * self.world)
+            dist.all_reduce(self.grads)          # one NCCL all-reduce(SUM) of the flat gradient over NVLink
+            c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
+        return self.loss
+
+    # ------------------------------------------------------------------ host-input step (end-to-end path)
+    def step_host(self, pcm_host: torch.Tensor, labels_host: torch.Tensor) -> None:
+        """Same step fed from (pinned) host tensors: the H2D copies ride a copy stream, double buffered against
+        compute; the loss of every step is read back (D2H) asynchronously."""
+        dev = self.device
+        if self._slots is None:
+            self._slots = [(torch.empty(self.batch, self.samples, device=dev), torch.empty(self.batch, dtype=torch.int64, device=dev))
+                           for _ in range(2)]
+            self._slot_free = [torch.cuda.Event() for _ in range(2)]
+            self._slot_ready = [torch.cuda.Event() for _ in range(2)]
+            for e in self._slot_free:
+                e.record(torch.cuda.current_stream(dev))
+        k = self._host_i % 2
+        self._host_i += 1
+        pcm_d, lab_d = self._slots[k]
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._slot_free[k])
+            pcm_d.copy_(pcm_host, non_blocking=True)
+            lab_d.copy_(labels_host, non_blocking=True)
+            self._slot_ready[k].record(self._copy_stream)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(self._slot_ready[k])
+        self.step(pcm_d, lab_d)
+        self._slot_free[k].record(cur)
+        self._host_loss.copy_(self.loss, non_blocking=True)
+
+    def flush_host(self) -> float:
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(self._host_loss.item())
+
+    # ------------------------------------------------------------------ per-kernel timing
+    def profile_groups(self, pcm, labels, reps: int = 3):
+        """Device time of every kernel label over `reps` steps (CUDA events on the launching stream)."""
+        acc, cnt = {}, {}
+        for _ in range(reps):
+            self.ctx.profile_begin()
+            self.step(pcm, labels)
+            for name, ms in self.ctx.profile_end():
+                acc[name] = acc.get(name, 0.0) + ms
+                cnt[name] = cnt.get(name, 0) + 1
+        return [{"name": k, "ms": acc[k] / reps, "launches_per_step": cnt[k] // reps} for k in acc]
+
+    # ------------------------------------------------------------------ state_dict interop
+    def state_dict(self):
+        out, off = {}, 0
+        for name, shape in res8_param_shapes(self.num_labels):
+            n = math.prod(shape)
+            out[name] = self.params[off:off + n].view(shape).clone()
+            off += n
+        for i in range(6):
+            out[f"bn{i + 1}.running_mean"] = self.bn_running[i, 0].clone()
+            out[f"bn{i + 1}.running_var"] = self.bn_running[i, 1].clone()
+            out[f"bn{i + 1}.num_batches_tracked"] = self.nbt[i].clone()
+        return out

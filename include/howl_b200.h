@@ -58,6 +58,13 @@ int howl_b200_sm_count(const howl_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t howl_b200_launch_count(const howl_ctx_t* ctx);
 
+/* ---- per-launch device timing (CUDA events on the launching stream; used by bench.py's roofline) --------- */
+/* After profile_begin every kernel launch of this context is bracketed by an event on `stream`. */
+int howl_b200_profile_begin(howl_ctx_t* ctx, void* stream);
+/* Synchronises, fills ms[i] with the device time of launch i and names (NUL-separated) with the kernel labels;
+ * returns the number of launches recorded (or a negative error) and switches profiling off. */
+int howl_b200_profile_end(howl_ctx_t* ctx, char* names, size_t names_bytes, float* ms, int32_t cap);
+
 /* ---- integer frame arithmetic (host; bit exact) ------------------------------------------------ */
 /* torch.stft(center=True): 1 + floor(T / hop).  Replaces the implicit frame count of transform.py:249-254. */
 int64_t howl_b200_num_frames(int64_t num_samples, int32_t hop);
