@@ -538,11 +538,25 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__
 
 // softmax cross-entropy backward at the head: one thread per utterance
 __global__ void head_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
-                                const float* __restrict__ wout, float* __restrict__ dlogits, float* __restrict__ dh,
-                                double* __restrict__ loss_acc, int64_t B, int L, float inv_batch) {
+                                const float* __restrict__ dlogits_in, const float* __restrict__ wout,
+                                float* __restrict__ dlogits, float* __restrict__ dh, double* __restrict__ loss_acc,
+                                int64_t B, int L, float inv_batch) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double nll = 0.0;
-  if (b < B) {
+  if (b < B && !labels) {
+    // upstream gradient supplied by the caller (autograd path): only dh = dlogits . W_out is needed
+    float acc[R8_C];
+#pragma unroll
+    for (int c = 0; c < R8_C; ++c) acc[c] = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float d = dlogits_in[b * L + l];
+      dlogits[b * L + l] = d;
+#pragma unroll
+      for (int c = 0; c < R8_C; ++c) acc[c] = fmaf(d, __ldg(wout + l * R8_C + c), acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < R8_C; ++c) dh[b * R8_C + c] = acc[c];
+  } else if (b < B) {
     const float* z = logits + b * L;
     float mx = z[0];
     for (int l = 1; l < L; ++l) mx = fmaxf(mx, z[l]);
@@ -817,13 +831,10 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   return HOWL_OK;
 }
 
-extern "C" int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* labels, int64_t B,
-                                  int32_t frames, int32_t n_mels, int32_t num_labels, int64_t loss_scale_batch,
-                                  const float* params, float* grads, float* loss, void* workspace,
-                                  size_t workspace_bytes) {
-  if (!ctx) return HOWL_E_INVALID;
-  HOWL_REQUIRE(ctx, feats && labels && params && grads && loss, HOWL_E_INVALID, "res8_bwd: null pointer");
-  HOWL_REQUIRE(ctx, loss_scale_batch >= 1, HOWL_E_INVALID, "res8_bwd: loss_scale_batch must be >= 1");
+static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* labels,
+                       const float* dlogits_in, int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels,
+                       int64_t loss_scale_batch, const float* params, float* grads, float* loss, void* workspace,
+                       size_t workspace_bytes) {
   R8Ws ws;
   int rc = r8_check(ctx, B, frames, n_mels, num_labels, workspace, workspace_bytes, &ws);
   if (rc) return rc;
@@ -843,11 +854,13 @@ extern "C" int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* fe
 
   transpose_weights_kernel<<<(R8_LAYERS * R8_KW + 255) / 256, 256, 0, st>>>(wl, ws.wT);
   HOWL_LAUNCHED(ctx, "transpose_weights");
-  head_bwd_kernel<<<(unsigned)howl_ceil_div(B, 128), 128, 0, st>>>(ws.logits, labels, wout, ws.dlogits, ws.dh,
-                                                                   ws.loss_acc, B, L, 1.f / (float)loss_scale_batch);
+  head_bwd_kernel<<<(unsigned)howl_ceil_div(B, 128), 128, 0, st>>>(ws.logits, labels, dlogits_in, wout, ws.dlogits,
+                                                                   ws.dh, ws.loss_acc, B, L,
+                                                                   1.f / (float)loss_scale_batch);
   HOWL_LAUNCHED(ctx, "head_bwd");
   head_wgrad_kernel<<<L + 2, 256, 0, st>>>(ws.dlogits, ws.pooled, ws.dh, g_wout, g_bout,
-                                           ws.stats_bwd + 5 * 2 * R8_C, ws.loss_acc, loss, B, L);
+                                           ws.stats_bwd + 5 * 2 * R8_C, ws.loss_acc, loss ? loss : (float*)ws.loss_acc + 2,
+                                           B, L);
   HOWL_LAUNCHED(ctx, "head_wgrad");
 
   const size_t csm = conv_smem_bytes(H), wsm = wgrad_smem_bytes(H);
@@ -920,4 +933,25 @@ extern "C" int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* fe
     HOWL_LAUNCHED(ctx, "conv0_bwd");
   }
   return HOWL_OK;
+}
+
+
+extern "C" int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* labels, int64_t B,
+                                  int32_t frames, int32_t n_mels, int32_t num_labels, int64_t loss_scale_batch,
+                                  const float* params, float* grads, float* loss, void* workspace,
+                                  size_t workspace_bytes) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, feats && labels && params && grads && loss, HOWL_E_INVALID, "res8_bwd: null pointer");
+  HOWL_REQUIRE(ctx, loss_scale_batch >= 1, HOWL_E_INVALID, "res8_bwd: loss_scale_batch must be >= 1");
+  return r8_bwd_impl(ctx, stream, feats, labels, nullptr, B, frames, n_mels, num_labels, loss_scale_batch, params, grads,
+                     loss, workspace, workspace_bytes);
+}
+
+extern "C" int howl_b200_res8_bwd_dlogits(howl_ctx_t* ctx, void* stream, const float* feats, const float* dlogits,
+                                          int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels,
+                                          const float* params, float* grads, void* workspace, size_t workspace_bytes) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, feats && dlogits && params && grads, HOWL_E_INVALID, "res8_bwd_dlogits: null pointer");
+  return r8_bwd_impl(ctx, stream, feats, nullptr, dlogits, B, frames, n_mels, num_labels, 1, params, grads, nullptr,
+                     workspace, workspace_bytes);
 }

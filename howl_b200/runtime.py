@@ -122,6 +122,26 @@ class Context:
         _check(sums, torch.float64, self.device, "sums")
         self._rc(self.lib.howl_b200_sum_sumsq(self.handle, self._stream(), _ptr(x), x.numel(), _ptr(sums)), "sum_sumsq")
 
+    def zmuv(self, x: torch.Tensor, mean: float, std: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _check(x, torch.float32, self.device, "x")
+        out = torch.empty_like(x) if out is None else out
+        self._rc(self.lib.howl_b200_zmuv_fwd(self.handle, self._stream(), _ptr(x), x.numel(), mean, std, _ptr(out)), "zmuv_fwd")
+        return out
+
+    def spec_mask(self, x: torch.Tensor, rects: torch.Tensor) -> torch.Tensor:
+        _check(x, torch.float32, self.device, "x")
+        _check(rects, torch.int32, self.device, "rects")
+        b, c, m, f = x.shape
+        self._rc(self.lib.howl_b200_spec_mask(self.handle, self._stream(), _ptr(x), b, c, m, f, _ptr(rects)), "spec_mask")
+        return x
+
+    def to_time_major(self, x: torch.Tensor) -> torch.Tensor:
+        _check(x, torch.float32, self.device, "x")
+        b, c, m, f = x.shape
+        out = torch.empty(b, f, m, dtype=torch.float32, device=self.device)
+        self._rc(self.lib.howl_b200_to_time_major(self.handle, self._stream(), _ptr(x), b, c, m, f, _ptr(out)), "to_time_major")
+        return out
+
     # ------------------------------------------------------------------ res8
     def res8_param_count(self, num_labels: int) -> int:
         return int(self.lib.howl_b200_res8_param_count(num_labels))
@@ -149,6 +169,14 @@ class Context:
         self._rc(self.lib.howl_b200_res8_bwd(self.handle, self._stream(), _ptr(feats), _ptr(labels), b, f, m, num_labels,
                                              loss_scale_batch or b, _ptr(params), _ptr(grads), _ptr(loss), _ptr(ws),
                                              ws.numel()), "res8_bwd")
+
+    def res8_bwd_from_dlogits(self, feats, dlogits, params, grads, ws):
+        b, f, m = feats.shape
+        num_labels = self._labels_from_params(params)
+        _check(dlogits, torch.float32, self.device, "dlogits")
+        self._rc(self.lib.howl_b200_res8_bwd_dlogits(self.handle, self._stream(), _ptr(feats), _ptr(dlogits), b, f, m,
+                                                     num_labels, _ptr(params), _ptr(grads), _ptr(ws), ws.numel()),
+                 "res8_bwd_dlogits")
 
     def adamw(self, params, grads, m, v, step: int, lr: float, weight_decay: float, betas=(0.9, 0.999), eps=1e-8):
         self._rc(self.lib.howl_b200_adamw(self.handle, self._stream(), _ptr(params), _ptr(grads), _ptr(m), _ptr(v),

@@ -84,14 +84,14 @@ class Res8TrainStep:
             c.res8_train_step(pcm, labels, self.fb, self.zmuv, self.params, self.bn_running, self.nbt, self.grads, self.m,
                               self.v, self.step_count, self.lr, self.weight_decay, self.loss, self.logits, self.ws, rects)
         else:
-            import torch.distributed as dist
+            from .parallel import allreduce_flat_grads
 
             feats = self.ws[: self.batch * self.frames * c.n_mels * 4].view(torch.float32).view(self.batch, self.frames, c.n_mels)
             ws = self.ws[self.feat_bytes:]
             c.frontend(pcm, self.fb, "time_major", zmuv=self.zmuv, rects=rects, out=feats)
             c.res8_fwd(feats, self.params, self.bn_running, self.nbt, True, ws, logits=self.logits)
             c.res8_bwd(feats, labels, self.params, self.grads, self.loss, ws, loss_scale_batch=self.batch * self.world)
-            dist.all_reduce(self.grads)          # one NCCL all-reduce(SUM) of the flat gradient over NVLink
+            allreduce_flat_grads(self.grads)     # one NCCL all-reduce(SUM) of the flat gradient over NVLink
             c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
         return self.loss
 

@@ -89,6 +89,15 @@ int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float* pcm, int6
  * Replaces the two reductions of ZmuvTransform.update (operator.py:126-135). */
 int howl_b200_sum_sumsq(howl_ctx_t* ctx, void* stream, const float* x, int64_t n, double* sums);
 
+/* ZmuvTransform.forward on any tensor of n floats (operator.py:145-146): out = (x - mean) / std; in place allowed. */
+int howl_b200_zmuv_fwd(howl_ctx_t* ctx, void* stream, const float* x, int64_t n, float mean, float std, float* out);
+/* SpecAugmentTransform.fmask/tmask (transform.py:310-326) in place on x [B,C,M,F] with host-drawn rects [B,4] i32. */
+int howl_b200_spec_mask(howl_ctx_t* ctx, void* stream, float* x, int64_t B, int32_t C, int32_t M, int32_t F,
+                        const int32_t* rects);
+/* x[:, :1].permute(0,1,3,2).contiguous() of Res8.forward (cnn.py:128-129): x [B,C,M,F] -> out [B,F,M]. */
+int howl_b200_to_time_major(howl_ctx_t* ctx, void* stream, const float* x, int64_t B, int32_t C, int32_t M, int32_t F,
+                            float* out);
+
 /* ---- res8 ----------------------------------------------------------------------------------- */
 /* Flat parameter layout (state_dict order):
  *   conv0.weight[45,1,3,3] | conv1..6.weight[45,45,3,3] | output.weight[L,45] | output.bias[L]
@@ -115,6 +124,12 @@ int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* feats, int64_
 int howl_b200_res8_bwd(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* labels, int64_t B,
                        int32_t frames, int32_t n_mels, int32_t num_labels, int64_t loss_scale_batch,
                        const float* params, float* grads, float* loss, void* workspace, size_t workspace_bytes);
+
+/* Same backward for an arbitrary upstream gradient dlogits [B, L] (autograd of Res8.forward when the loss is
+ * computed by the caller, e.g. nn.CrossEntropyLoss / a custom criterion at training/run/train.py:250-253). */
+int howl_b200_res8_bwd_dlogits(howl_ctx_t* ctx, void* stream, const float* feats, const float* dlogits, int64_t B,
+                               int32_t frames, int32_t n_mels, int32_t num_labels, const float* params, float* grads,
+                               void* workspace, size_t workspace_bytes);
 
 /* ---- K4: fused AdamW over a flat buffer ------------------------------------------------------- */
 /* torch.optim.AdamW.step (training/run/train.py:256,302): decoupled weight decay, bias correction,

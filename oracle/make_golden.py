@@ -218,11 +218,33 @@ def main():
             ts[f"step{step}.sd.{k}"] = v.detach().numpy().copy()
     np.savez_compressed(os.path.join(OUT, "res8_train.npz"), **ts)
 
+    # ------------------------------------------------------------------ label-sequence FSM (host logic) cases
+    from howl.model.inference import InferenceEngine
+
+    rng = random.Random(2024)
+    fsm = []
+    dummy = types.SimpleNamespace(streaming_state=None)
+    for case in range(300):
+        eng = InferenceEngine(dummy, zmuv, ctx)
+        eng.sequence = [[0, 1, 2], [0], [2, 1], [0, 0, 1]][case % 4]
+        eng.tolerance_window_ms = rng.choice([100, 500, 900])
+        eng.inference_window_ms = rng.choice([1000, 2000])
+        t, hist = 0.0, []
+        for _ in range(rng.randrange(1, 40)):
+            t += rng.choice([63, 63, 63, 200, 700])
+            hist.append((t, rng.choice([0, 1, 2, 3, 3])))
+        eng.label_history = list(hist)
+        now = t + rng.choice([0, 63, 1500])
+        fsm.append({"sequence": eng.sequence, "tolerance": eng.tolerance_window_ms, "window": eng.inference_window_ms,
+                    "history": hist, "now": now, "present": bool(eng.sequence_present(now)),
+                    "kept": len(eng.label_history)})
+    meta["fsm_cases"] = fsm
+
     with open(os.path.join(OUT, "meta.json"), "w") as fh:
         json.dump(meta, fh, indent=1, sort_keys=True)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
-    print(json.dumps(traces))
+    print(json.dumps(traces), sum(c["present"] for c in fsm), "of", len(fsm), "fsm cases present")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,148 @@
+"""GPU: the howl-shaped Python surface (transforms, ZMUV, registry/Res8 module, inference engines) on top of the C ABI."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import howl_oracle as O
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+RTOL = ATOL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def _env(monkeypatch):
+    from howl_b200.settings import SETTINGS
+
+    monkeypatch.setenv("NUM_MELS", "40")
+    monkeypatch.setenv("INFERENCE_SEQUENCE", "[0,1,2]")
+    monkeypatch.setenv("INFERENCE_THRESHOLD", "0")
+    SETTINGS.reset()
+    yield
+    SETTINGS.reset()
+
+
+def test_standard_audio_transform_eval_and_train_draw_order(golden):
+    from howl_b200.transform import StandardAudioTransform
+
+    g, v = golden("frontend"), golden("vtlp")
+    pcm = torch.from_numpy(g["t8000_pcm"]).to(DEV)
+    std = StandardAudioTransform().to(DEV).eval()
+    np.testing.assert_allclose(std(pcm).cpu().numpy(), g["t8000_out"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(std(pcm, mels_only=True).cpu().numpy(), g["t8000_mels_only"], rtol=RTOL, atol=ATOL)
+    lens = torch.from_numpy(g["lengths_in"])
+    assert np.array_equal(std.compute_lengths(lens).numpy(), g["lengths_out"])
+    # train mode: the same global-`random` seed must reproduce the reference's coin flips and alphas
+    std.train()
+    random.seed(7)
+    for k in range(4):
+        np.testing.assert_allclose(std(pcm).cpu().numpy(), v["train_outs"][k], rtol=RTOL, atol=ATOL)
+
+
+def test_zmuv_transform_update_and_state_dict(golden):
+    from howl_b200.transform import ZmuvTransform
+
+    z, g = golden("zmuv"), golden("frontend")
+    zm = ZmuvTransform().to(DEV)
+    for x in [g["t8000_out"][i:i + 1] for i in range(3)] + [g["speech_out"]]:
+        zm.update(torch.from_numpy(x).to(DEV))
+    np.testing.assert_allclose(zm.total.cpu().numpy(), z["total"])
+    np.testing.assert_allclose(zm.mean.cpu().numpy(), z["mean"], rtol=1e-5)
+    np.testing.assert_allclose(zm.mean2.cpu().numpy(), z["mean2"], rtol=1e-5)
+    assert set(zm.state_dict()) == {"total", "mean", "mean2"}
+    out = zm(torch.from_numpy(z["fwd_in"]).to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(out, z["fwd_out"], rtol=1e-5, atol=1e-5)
+
+
+def test_spec_augment_replays_reference_draws(golden):
+    from howl_b200.transform import SpecAugmentTransform
+
+    sa = golden("specaugment")
+    spec = SpecAugmentTransform().train()
+    random.seed(11)
+    out = spec(torch.from_numpy(sa["in"]).to(DEV)).cpu().numpy()
+    assert np.array_equal(out, sa["out"])
+    random.seed(11)
+    rects = spec.draw_rects(sa["in"].shape[0], 40, sa["in"].shape[3])
+    assert np.array_equal(rects.numpy(), sa["rects"])
+
+
+def test_registry_and_res8_state_dict_keys(golden):
+    from howl_b200.model import RegisteredModel
+
+    assert "res8" in RegisteredModel.registered_names()
+    model = RegisteredModel.find_registered_class("res8")(4)
+    g = golden("res8_heyfirefox")
+    want = sorted(k[3:] for k in g if k.startswith("sd."))
+    assert sorted(model.state_dict().keys()) == want
+    assert sum(p.numel() for p in model.parameters()) == 109939
+    assert model.streaming() is model and model.static() is model and model.compute_length(5) == 5
+
+
+def test_res8_module_trains_like_the_reference_loop(golden):
+    """The loop body of training/run/train.py:288-302 with torch's CrossEntropyLoss and torch.optim.AdamW over
+    model.parameters(), checked against the golden reference run."""
+    from howl_b200.model import RegisteredModel
+    from howl_b200.transform import StandardAudioTransform, ZmuvTransform
+
+    g = golden("res8_train")
+    L = 12
+    model = RegisteredModel.find_registered_class("res8")(L)
+    model.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("init.")})
+    model = model.to(DEV).streaming()
+    std = StandardAudioTransform().to(DEV).eval()
+    zmuv = ZmuvTransform().to(DEV)
+    zmuv.mean, zmuv.mean2 = torch.from_numpy(g["zmuv_mean"]).to(DEV), torch.from_numpy(g["zmuv_mean2"]).to(DEV)
+    opt = torch.optim.AdamW(model.parameters(), float(g["lr"]), weight_decay=float(g["wd"]))
+    crit = torch.nn.CrossEntropyLoss()
+    pcm, labels = torch.from_numpy(g["pcm"]).to(DEV), torch.from_numpy(g["labels"]).to(DEV)
+    model.train()
+    for step in (1, 2):
+        lengths = std.compute_lengths(torch.full((pcm.size(0),), pcm.size(1)))
+        scores = model(zmuv(std(pcm)), lengths)
+        loss = crit(scores, labels)
+        opt.zero_grad()
+        model.zero_grad()
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), g[f"step{step}.loss"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(scores.detach().cpu().numpy(), g[f"step{step}.logits"], rtol=RTOL, atol=ATOL)
+        for k, p in model.named_parameters():
+            np.testing.assert_allclose(p.grad.cpu().numpy(), g[f"step{step}.grad.{k}"], rtol=1e-3, atol=1e-5)
+        opt.step()
+        sd = model.state_dict()
+        for i in range(1, 7):
+            np.testing.assert_allclose(sd[f"bn{i}.running_var"].cpu().numpy(), g[f"step{step}.sd.bn{i}.running_var"], rtol=1e-4, atol=1e-5)
+            assert int(sd[f"bn{i}.num_batches_tracked"]) == step
+        # teacher-force the parameters (AdamW's first steps are ill-conditioned in g; see test_oracle_golden)
+        model.load_state_dict({k: torch.from_numpy(g[f"step{step}.sd.{k}"]) for k in sd})
+
+
+@pytest.mark.parametrize("batched", [False, True])
+def test_frame_inference_engine_known_answers(golden, batched):
+    """the shipped hey-fire-fox res8 + zmuv through FrameInferenceEngine(500, 63)."""
+    from howl_b200.inference import FrameInferenceEngine, SimpleContext
+    from howl_b200.model import RegisteredModel
+    from howl_b200.transform import ZmuvTransform
+
+    g = golden("res8_heyfirefox")
+    meta = json.load(open(os.path.join(GOLDEN, "meta.json")))["traces"]
+    model = RegisteredModel.find_registered_class("res8")(4)
+    model.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")})
+    model = model.to(DEV).eval()
+    zmuv = ZmuvTransform()
+    zmuv.load_state_dict({k: torch.from_numpy(g[f"zmuv.{k}"]) for k in ("total", "mean", "mean2")})
+    zmuv = zmuv.to(DEV)
+    ctx = SimpleContext.for_vocab(["hey", "fire", "fox"])
+    assert (ctx.num_labels, ctx.negative_label, ctx.blank_label) == (4, 3, -1)
+    for name in ("hey_fire_fox", "hello_world"):
+        engine = FrameInferenceEngine(500, 63, model, zmuv, ctx)
+        audio = torch.from_numpy(g[f"trace_{name}_pcm"]).to(DEV)
+        detected = engine.infer_batched(audio) if batched else engine.infer(audio)
+        assert detected == meta[name]["detected"]
+        assert [int(l) for _, l in engine.label_history] == meta[name]["labels"]

@@ -174,7 +174,7 @@ def test_res8_train_steps_match_reference(ctx, golden):
         flat.copy_(O.flatten(want_sd, L).to(DEV))
 
 
-@pytest.mark.parametrize("B,T,L", [(1, 8000, 4), (3, 8000, 5), (5, 16000, 30), (2, 12345, 12), (200, 8000, 4)])
+@pytest.mark.parametrize("B,T,L", [(1, 8000, 4), (3, 8000, 5), (5, 16000, 30), (2, 12345, 12), (200, 8000, 4), (300, 16000, 12)])
 def test_res8_train_step_vs_oracle(ctx, B, T, L):
     pcm, labels = O.synthetic_batch(B, T, L, seed=B * 7 + L)
     params, bn = O.res8_init(L, seed=B), O.res8_bn_init()
@@ -191,16 +191,29 @@ def test_res8_train_step_vs_oracle(ctx, B, T, L):
     feats = O.hot_path_features(pcm, fb, torch.tensor([zmean]), torch.tensor([zmean ** 2 + zstd ** 2]))
     om = {k: torch.zeros_like(p) for k, p in params.items()}
     ov = {k: torch.zeros_like(p) for k, p in params.items()}
-    if B == 1:
-        # BatchNorm over a single clip is still fine (270 / 130 pixels per channel)
-        pass
+    # ground truth for the gradients: the same graph in float64.  torch's fp32 CPU backward accumulates the
+    # BatchNorm-backward reductions in fp32 and drifts from fp64 by up to ~3 % of a layer's gradient scale at B=200
+    # (measured: DESIGN.md "parity notes"); the CUDA path accumulates those sums in fp64, so it is held to the
+    # tight bound against fp64 and, separately, must be no further from the fp32 oracle than that oracle is from fp64.
+    leaves = {k: p.double().requires_grad_(True) for k, p in params.items()}
+    bn64 = {k: (t.double() if t.is_floating_point() else t.clone()) for k, t in O.res8_bn_init().items()}
+    torch.nn.functional.cross_entropy(O.res8_forward(feats.double(), leaves, bn64, True), labels).backward()
+    g64 = O.flatten({k: leaves[k].grad for k in leaves}, L).numpy()
     oloss, ologits, ograds = O.res8_train_step(feats, labels, params, bn, om, ov, 1, 0.01, 1e-5)
     np.testing.assert_allclose(logits.cpu().numpy(), ologits.numpy(), rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(loss.item(), oloss.item(), rtol=RTOL, atol=ATOL)
     og = O.flatten(ograds, L).numpy()
-    gg = grads.cpu().numpy()
-    scale = np.abs(og).max()
-    np.testing.assert_allclose(gg, og, rtol=1e-3, atol=1e-4 * scale)
+    gg = grads.cpu().numpy().astype(np.float64)
+    off = 0
+    for name, shape in O.res8_param_shapes(L):
+        n = int(np.prod(shape))
+        sl = slice(off, off + n)
+        off += n
+        scale = np.abs(g64[sl]).max()
+        err_gpu = np.abs(gg[sl] - g64[sl]).max() / scale
+        err_cpu32 = np.abs(og[sl] - g64[sl]).max() / scale
+        assert err_gpu <= 1e-4, (name, err_gpu)
+        assert np.abs(gg[sl] - og[sl]).max() / scale <= max(2e-4, 2.5 * err_cpu32), (name, err_cpu32)
     for i in range(1, 7):
         np.testing.assert_allclose(bnd[i - 1, 0].cpu().numpy(), bn[f"bn{i}.running_mean"].numpy(), rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(bnd[i - 1, 1].cpu().numpy(), bn[f"bn{i}.running_var"].numpy(), rtol=1e-4, atol=1e-6)

@@ -1,0 +1,130 @@
+"""CPU: host-side logic of the howl-shaped surface (settings, stride, label-sequence FSM, sharding) and the
+world_size-2 gloo path of the data-parallel step."""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def test_settings_follow_reference_env_names(monkeypatch):
+    from howl_b200.settings import SETTINGS
+
+    monkeypatch.setenv("NUM_MELS", "40")
+    monkeypatch.setenv("INFERENCE_SEQUENCE", "[0,1,2]")
+    monkeypatch.setenv("INFERENCE_WEIGHTS", "[1.0, 2.0]")
+    SETTINGS.reset()
+    assert SETTINGS.audio_transform.num_mels == 40 and SETTINGS.audio_transform.num_fft == 512
+    assert SETTINGS.audio_transform.hop_length == 200 and SETTINGS.audio.sample_rate == 16000
+    assert SETTINGS.inference_engine.inference_sequence == [0, 1, 2]
+    assert SETTINGS.inference_engine.inference_weights == [1.0, 2.0]
+    monkeypatch.delenv("NUM_MELS")
+    SETTINGS.reset()
+    assert SETTINGS.audio_transform.num_mels == 80  # reference default (howl/settings.py:32)
+    SETTINGS.reset()
+
+
+def test_stride_known_answer():
+    """howl/utils/audio_utils_test.py:23-35: 112,128 samples, 500 ms window, 250 ms stride -> 29 / 27 windows."""
+    from howl_b200.inference import stride
+
+    audio = torch.zeros(112128)
+    assert len(list(stride(audio, 500, 250, 16000, drop_incomplete=False))) == 29
+    assert len(list(stride(audio, 500, 250, 16000, drop_incomplete=True))) == 27
+    w = list(stride(torch.arange(35774.0), 500, 63, 16000))
+    assert all(x.numel() == 8000 for x in w) and w[1][0].item() == 1008.0
+
+
+def test_sequence_fsm_matches_reference_cases(monkeypatch):
+    from howl_b200.inference import InferenceEngine, SimpleContext
+    from howl_b200.settings import SETTINGS
+
+    monkeypatch.setenv("NUM_MELS", "40")
+    SETTINGS.reset()
+    cases = json.load(open(os.path.join(GOLDEN, "meta.json")))["fsm_cases"]
+    assert len(cases) == 300
+    model = types.SimpleNamespace(streaming_state=None)
+    eng = InferenceEngine(model, None, SimpleContext.for_vocab(["hey", "fire", "fox"]))
+    for c in cases:
+        eng.sequence, eng.tolerance_window_ms, eng.inference_window_ms = c["sequence"], c["tolerance"], c["window"]
+        eng.label_history = [tuple(h) for h in c["history"]]
+        assert eng.sequence_present(c["now"]) == c["present"]
+        assert len(eng.label_history) == c["kept"]
+    SETTINGS.reset()
+
+
+def test_prediction_smoothing_and_threshold(monkeypatch):
+    from howl_b200.inference import InferenceEngine, SimpleContext
+    from howl_b200.settings import SETTINGS
+
+    monkeypatch.setenv("NUM_MELS", "40")
+    monkeypatch.setenv("INFERENCE_THRESHOLD", "0.6")
+    SETTINGS.reset()
+    eng = InferenceEngine(types.SimpleNamespace(streaming_state=None), None, SimpleContext.for_vocab(["a", "b"]))
+    assert eng._append_probability_frame(np.array([0.7, 0.2, 0.1]), 0.0) == 0
+    assert eng._append_probability_frame(np.array([0.1, 0.5, 0.4]), 30.0) == 0      # max over the 50 ms window
+    assert eng._append_probability_frame(np.array([0.1, 0.5, 0.4]), 100.0) == 2     # below threshold -> negative label
+    SETTINGS.reset()
+
+
+def test_shard_range_covers_batch():
+    from howl_b200.parallel import shard_range
+
+    for B, W in [(32768, 8), (4096, 1), (10, 4), (7, 8)]:
+        spans = [shard_range(B, r, W) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+    assert shard_range(32768, 3, 8) == (12288, 16384)
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from oracle import howl_oracle as O            # compute stand-in on CPU; the product path is CUDA-only
+from howl_b200.parallel import shard_range, allreduce_flat_grads
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+L, B, T = 4, 6, 8000
+pcm, labels = O.synthetic_batch(B, T, L, seed=3)
+lo, hi = shard_range(B, rank, world)
+params = O.res8_init(L, seed=1)
+fb = O.mel_filterbank(40)
+feats = O.hot_path_features(pcm[lo:hi], fb, torch.tensor([-1.8]), torch.tensor([-1.8 ** 2 + 3.9 ** 2]))
+leaves = {k: p.clone().requires_grad_(True) for k, p in params.items()}
+logits = O.res8_forward(feats, leaves, O.res8_bn_init(), True)
+(torch.nn.functional.cross_entropy(logits, labels[lo:hi], reduction="sum") / B).backward()   # loss_scale_batch = global B
+flat = O.flatten({k: leaves[k].grad for k in leaves}, L)
+local = flat.clone()
+allreduce_flat_grads(flat)
+gathered = [torch.zeros_like(local) for _ in range(world)]
+dist.all_gather(gathered, local)
+assert torch.allclose(flat, sum(gathered), rtol=1e-6, atol=1e-8)
+m = {k: torch.zeros_like(p) for k, p in params.items()}; v = {k: torch.zeros_like(p) for k, p in params.items()}
+O.adamw_step(params, O.unflatten(flat, L), m, v, 1, 0.01, 1e-5)
+after = O.flatten(params, L)
+peers = [torch.zeros_like(after) for _ in range(world)]
+dist.all_gather(peers, after)
+assert all(torch.equal(peers[0], p) for p in peers)          # replicas stay bit-identical after the step
+if rank == 0:
+    print("DP_OK", float(flat.abs().sum()))
+dist.destroy_process_group()
+"""
+
+
+def test_data_parallel_step_gloo_world2(tmp_path):
+    import subprocess
+
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, env=env,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "DP_OK" in out.stdout
