@@ -39,6 +39,7 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->fe = *cfg;
+  ctx->conv_engine = 1;
   // tables in double, rounded once
   float win[HOWL_NFFT];
   float2 tw256[256], tw512[HOWL_NFREQ];
@@ -58,6 +59,17 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
 #undef CK
   *out_ctx = ctx;
   return HOWL_OK;
+}
+
+extern "C" int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return HOWL_E_INVALID;
+  if (strcmp(name, "conv_engine") == 0) {
+    HOWL_REQUIRE(ctx, value == 0 || value == 1, HOWL_E_INVALID, "set_option: conv_engine must be 0 (fp32) or 1 (tcgen05)");
+    ctx->conv_engine = (int)value;
+    return HOWL_OK;
+  }
+  HOWL_SET_ERR(ctx, "set_option: unknown option '%s'", name);
+  return HOWL_E_INVALID;
 }
 
 extern "C" int howl_b200_profile_begin(howl_ctx_t* ctx, void* stream) {

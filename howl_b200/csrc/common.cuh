@@ -26,6 +26,7 @@ struct howl_ctx {
   int* fb_off;
   float* fbc;
   int64_t launches;
+  int conv_engine;   // 0 = fp32 FFMA kernels, 1 = tcgen05 bf16x3 kernels (default)
   // optional per-launch timing
   int prof_on;
   int prof_n;

@@ -15,14 +15,7 @@
 
 #include "common.cuh"
 
-#define R8_C 45
-#define R8_W 10          // pooled width (n_mels 40 / 4)
-#define R8_LAYERS 6
-#define R8_MELS 40
-#define R8_WPAD 12       // padded row (1 + 10 + 1)
-#define R8_KW (R8_C * R8_C * 9)   // 18225 weights per 45->45 layer
-#define R8_BN_EPS 1e-5
-#define R8_BN_MOM 0.1
+#include "res8_common.cuh"
 
 // =============================================================================================
 // workspace carve-up
@@ -33,6 +26,7 @@ struct R8Ws {
   double* loss_acc;    // [1]
   float* mean_rstd;    // [6][2][45]
   float* wT;           // [6][18225]  transposed + flipped weights for dgrad
+  __nv_bfloat16* wprep; // tensor-core weight operands (R8TC_WELEMS)
   float* pooled;       // [B,45]
   float* dh;           // [B,45]
   float* dlogits;      // [B,L]
@@ -59,6 +53,7 @@ static R8Ws r8_carve(void* base, int64_t B, int H, int L) {
   w.loss_acc = (double*)take(sizeof(double) * 2);
   w.mean_rstd = (float*)take(sizeof(float) * R8_LAYERS * 2 * R8_C);
   w.wT = (float*)take(sizeof(float) * R8_LAYERS * R8_KW);
+  w.wprep = (__nv_bfloat16*)take(sizeof(__nv_bfloat16) * R8TC_WELEMS);
   w.pooled = (float*)take(sizeof(float) * B * R8_C);
   w.dh = (float*)take(sizeof(float) * B * R8_C);
   w.dlogits = (float*)take(sizeof(float) * B * L);
@@ -215,20 +210,6 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_bwd_kernel(const float* __re
 #define CV_OCG 9                  // output-channel groups of 5
 #define CV_WSTRIDE 16             // floats per (c, dy, ocg) weight packet: [dx 3][o 5] + 1 pad
 
-struct ConvParams {
-  const float* in;        // [B,45,H,10]
-  const float* in_mean;   // [45] or null (identity)
-  const float* in_rstd;
-  const float* w;         // [45 out][45 in][3][3]
-  const float* res;       // residual added after ReLU, or null
-  float* out;
-  double* stats;          // [2][45] or null
-  const float* aux;       // STATS == 2: tensor whose normalised value multiplies the output in the 2nd statistic
-  const float* aux_mean;
-  const float* aux_rstd;
-  int64_t B;
-  int H;
-};
 
 static size_t conv_smem_bytes(int H) {
   size_t f = (size_t)R8_C * 3 * CV_OCG * CV_WSTRIDE + (size_t)R8_C * (H + 2) * R8_WPAD + (size_t)H * CV_OCG * 10 +
@@ -377,15 +358,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_kernel(const ConvParams
 // =============================================================================================
 #define WG_THREADS 256
 
-struct WgradParams {
-  const float* dc;       // [B,45,H,10]  gradient at the conv output (ReLU mask applied)
-  const float* x;        // [B,45,H,10]  conv input before normalisation
-  const float* x_mean;   // or null
-  const float* x_rstd;
-  float* dw;             // [45][45][3][3], accumulated with atomics
-  int64_t B;
-  int H;
-};
 
 static size_t wgrad_smem_bytes(int H) {
   return sizeof(float) * ((size_t)R8_C * H * R8_WPAD + (size_t)R8_C * (H + 2) * R8_WPAD + 2 * 48);
@@ -799,6 +771,11 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
   const int grid = r8_grid(ctx, B);
   const double count = (double)B * HW;
+  const bool use_tc = ctx->conv_engine == 1 && r8tc_supported(H);
+  if (use_tc) {
+    rc = r8tc_weight_prep(ctx, st, wl, ws.wprep, 0);
+    if (rc) return rc;
+  }
   for (int i = 1; i <= R8_LAYERS; ++i) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -812,14 +789,23 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     p.out = ws.u[i - 1];
     p.B = B;
     p.H = H;
+    const __nv_bfloat16* whi = ws.wprep + ((size_t)((i - 1) * 2 + 0) * 2) * R8TC_WBLOCK;
     if (train) {
       p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
-      conv3x3_kernel<true, 1><<<grid, CV_THREADS, csm, st>>>(p);
-      HOWL_LAUNCHED(ctx, "conv3x3_fwd");
+      if (use_tc) {
+        rc = r8tc_conv(ctx, st, p, whi, whi + R8TC_WBLOCK, true, 1);
+        if (rc) return rc;
+      } else {
+        conv3x3_kernel<true, 1><<<grid, CV_THREADS, csm, st>>>(p);
+        HOWL_LAUNCHED(ctx, "conv3x3_fwd");
+      }
       bn_finalize_kernel<<<1, 64, 0, st>>>(p.stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C,
                                            bn_running + (i - 1) * 2 * R8_C,
                                            num_batches_tracked ? num_batches_tracked + (i - 1) : nullptr);
       HOWL_LAUNCHED(ctx, "bn_finalize");
+    } else if (use_tc) {
+      rc = r8tc_conv(ctx, st, p, whi, whi + R8TC_WBLOCK, true, 0);
+      if (rc) return rc;
     } else {
       conv3x3_kernel<true, 0><<<grid, CV_THREADS, csm, st>>>(p);
       HOWL_LAUNCHED(ctx, "conv3x3_fwd");
@@ -852,8 +838,14 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.stats_bwd, 0, sizeof(double) * R8_LAYERS * 2 * R8_C, st));
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * 2, st));
 
-  transpose_weights_kernel<<<(R8_LAYERS * R8_KW + 255) / 256, 256, 0, st>>>(wl, ws.wT);
-  HOWL_LAUNCHED(ctx, "transpose_weights");
+  const bool use_tc = ctx->conv_engine == 1 && r8tc_supported(frames / 3);
+  if (use_tc) {
+    rc = r8tc_weight_prep(ctx, st, wl, ws.wprep, 1);
+    if (rc) return rc;
+  } else {
+    transpose_weights_kernel<<<(R8_LAYERS * R8_KW + 255) / 256, 256, 0, st>>>(wl, ws.wT);
+    HOWL_LAUNCHED(ctx, "transpose_weights");
+  }
   head_bwd_kernel<<<(unsigned)howl_ceil_div(B, 128), 128, 0, st>>>(ws.logits, labels, dlogits_in, wout, ws.dlogits,
                                                                    ws.dh, ws.loss_acc, B, L,
                                                                    1.f / (float)loss_scale_batch);
@@ -904,8 +896,13 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     wg.dw = g_wl + (size_t)(i - 1) * R8_KW;
     wg.B = B;
     wg.H = H;
-    conv3x3_wgrad_kernel<<<grid, WG_THREADS, wsm, st>>>(wg);
-    HOWL_LAUNCHED(ctx, "conv3x3_wgrad");
+    if (use_tc) {
+      rc = r8tc_wgrad(ctx, st, wg);
+      if (rc) return rc;
+    } else {
+      conv3x3_wgrad_kernel<<<grid, WG_THREADS, wsm, st>>>(wg);
+      HOWL_LAUNCHED(ctx, "conv3x3_wgrad");
+    }
 
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -919,11 +916,16 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
       p.aux = ws.u[i - 2];
       p.aux_mean = ws.mean_rstd + (i - 2) * 2 * R8_C;
       p.aux_rstd = p.aux_mean + R8_C;
-      conv3x3_kernel<false, 2><<<grid, CV_THREADS, csm, st>>>(p);
-    } else {
-      conv3x3_kernel<false, 0><<<grid, CV_THREADS, csm, st>>>(p);
     }
-    HOWL_LAUNCHED(ctx, "conv3x3_dgrad");
+    if (use_tc) {
+      const __nv_bfloat16* whi = ws.wprep + ((size_t)((i - 1) * 2 + 1) * 2) * R8TC_WBLOCK;
+      rc = r8tc_conv(ctx, st, p, whi, whi + R8TC_WBLOCK, false, i > 1 ? 2 : 0);
+      if (rc) return rc;
+    } else {
+      if (i > 1) conv3x3_kernel<false, 2><<<grid, CV_THREADS, csm, st>>>(p);
+      else conv3x3_kernel<false, 0><<<grid, CV_THREADS, csm, st>>>(p);
+      HOWL_LAUNCHED(ctx, "conv3x3_dgrad");
+    }
   }
   {
     const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + 2 * R8_C * 9);

@@ -1,0 +1,51 @@
+// Declarations shared by the fp32 (res8.cu) and tensor-core (res8_tc.cu) Res8 kernels.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+#define R8_C 45
+#define R8_W 10          // pooled width (n_mels 40 / 4)
+#define R8_LAYERS 6
+#define R8_MELS 40
+#define R8_WPAD 12       // padded row (1 + 10 + 1)
+#define R8_KW (R8_C * R8_C * 9)   // 18225 weights per 45->45 layer
+#define R8_BN_EPS 1e-5
+#define R8_BN_MOM 0.1
+
+
+struct ConvParams {
+  const float* in;        // [B,45,H,10]
+  const float* in_mean;   // [45] or null (identity)
+  const float* in_rstd;
+  const float* w;         // [45 out][45 in][3][3]
+  const float* res;       // residual added after ReLU, or null
+  float* out;
+  double* stats;          // [2][45] or null
+  const float* aux;       // STATS == 2: tensor whose normalised value multiplies the output in the 2nd statistic
+  const float* aux_mean;
+  const float* aux_rstd;
+  int64_t B;
+  int H;
+};
+
+struct WgradParams {
+  const float* dc;       // [B,45,H,10]  gradient at the conv output (ReLU mask applied)
+  const float* x;        // [B,45,H,10]  conv input before normalisation
+  const float* x_mean;   // or null
+  const float* x_rstd;
+  float* dw;             // [45][45][3][3], accumulated with atomics
+  int64_t B;
+  int H;
+};
+
+// tensor-core weight operands: per layer and direction (0 = forward, 1 = data gradient) a (hi, lo) pair of
+// [9 taps][6 chunks][48 out][8 in] bf16 blocks
+#define R8TC_WBLOCK (54 * 48 * 8)
+#define R8TC_WELEMS ((size_t)R8_LAYERS * 2 * 2 * R8TC_WBLOCK)
+
+int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __nv_bfloat16* wprep, int dir);
+int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* whi, const __nv_bfloat16* wlo,
+              bool relu, int stats);
+int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const WgradParams& p);
+bool r8tc_supported(int H);

@@ -69,6 +69,15 @@ class Context:
     def sm_count(self) -> int:
         return int(self.lib.howl_b200_sm_count(self.handle))
 
+    def set_option(self, name: str, value: int):
+        self._rc(self.lib.howl_b200_set_option(self.handle, name.encode(), int(value)), "set_option")
+
+    def selftest_umma(self, a: torch.Tensor, b: torch.Tensor, mn_major: bool, variant: int = 0) -> torch.Tensor:
+        d = torch.empty(128, 48, dtype=torch.float32, device=self.device)
+        self._rc(self.lib.howl_b200_selftest_umma(self.handle, self._stream(), _ptr(a), _ptr(b), _ptr(d), int(mn_major),
+                                                  variant), "selftest_umma")
+        return d
+
     def profile_begin(self):
         self._rc(self.lib.howl_b200_profile_begin(self.handle, self._stream()), "profile_begin")
 

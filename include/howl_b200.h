@@ -58,6 +58,14 @@ int howl_b200_sm_count(const howl_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t howl_b200_launch_count(const howl_ctx_t* ctx);
 
+/* Options: "conv_engine" = 1 (default) 45->45 convolutions on tcgen05 tensor cores with bf16x3-split operands and
+ * fp32 accumulation; 0 = exact-fp32 FFMA kernels. */
+int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value);
+/* Debug aid: one 128x48x32 GEMM through the library's UMMA descriptor helpers (A, B fp32 device arrays, bf16-rounded
+ * inside; mn_major selects the operand layout of the weight-gradient GEMM); D fp32 [128][48]. */
+int howl_b200_selftest_umma(howl_ctx_t* ctx, void* stream, const float* A, const float* B, float* D, int32_t mn_major,
+                            int32_t variant);
+
 /* ---- per-launch device timing (CUDA events on the launching stream; used by bench.py's roofline) --------- */
 /* After profile_begin every kernel launch of this context is bracketed by an event on `stream`. */
 int howl_b200_profile_begin(howl_ctx_t* ctx, void* stream);
