@@ -8,8 +8,10 @@ from oracle import howl_oracle as O
 dev = torch.device("cuda:0")
 ctx = howl_b200.Context(dev)
 torch.manual_seed(0)
-for mn in (0, 1):
-    for variant in (0, 1):
+sel = sys.argv[1] if len(sys.argv) > 1 else "all"
+cases = {"k0": [(0, 0)], "mn0": [(1, 0)], "mn1": [(1, 1)], "all": [(0, 0), (1, 0)], "conv": []}[sel]
+for mn, variant in cases:
+    if True:
         if mn == 0:
             A = torch.randn(128, 32, device=dev); Bm = torch.randn(48, 32, device=dev)
             ref = A.bfloat16().float() @ Bm.bfloat16().float().t()
@@ -35,7 +37,7 @@ def run(engine, B, T, L):
     torch.cuda.synchronize()
     return logits.cpu(), grads.cpu(), loss.item(), bnd.cpu()
 
-for (B, T, L) in [(4, 16000, 12), (7, 8000, 4), (300, 16000, 12)]:
+for (B, T, L) in ([(4, 16000, 12), (7, 8000, 4), (300, 16000, 12)] if sel in ("all", "conv") else []):
     l0, g0, s0, b0 = run(0, B, T, L)
     l1, g1, s1, b1 = run(1, B, T, L)
     print(f"B={B} T={T}: logits tc-vs-fp32 max {(l1 - l0).abs().max().item():.3e} (scale {l0.abs().max().item():.3f}) loss {s0:.6f} {s1:.6f} "
