@@ -13,31 +13,43 @@
 #include "res8_common.cuh"
 #include "tc_common.cuh"
 
-#define TC_THREADS 256
+#define TC_THREADS 288            // warps 0-7: staging transform + epilogue, warp 8: TMA + MMA issue
+#define TC_WORKERS 256
 #define TC_PITCH 11
 #define TC_Q0 12                  // raster index of pixel (0, 0)
 #define TC_N 48                   // channels padded to 48
 #define TC_WBYTES (R8TC_WBLOCK * 2)
+#define TC_SMEM_LIMIT (227 * 1024 - 512)
 
 struct TcGeom {
   int H, U, Pu, tiles, R;        // R = operand rows kept in shared memory
+  size_t smem;
 };
 
+// staging slot of one utterance's raw planes: TMA needs 16-byte aligned source and size, an utterance block starts at a
+// multiple of 8 bytes only, so the copy starts at the aligned-down address and the slot carries up to 16 bytes of slack
+__host__ __device__ static inline size_t tc_slot_bytes(int H) { return ((size_t)R8_C * H * R8_W * 4 + 16 + 15) & ~(size_t)15; }
+
+static size_t tc_conv_smem(int U, int R, int H) {
+  return 2 * (size_t)TC_WBYTES + 12 * (size_t)R * 16 + (size_t)U * tc_slot_bytes(H) + (192 + 8 * 2 * 48) * 4;
+}
+
 static TcGeom tc_geom(int H) {
-  TcGeom best{H, 0, (H + 2) * TC_PITCH, 0, 0};
+  TcGeom best{H, 0, (H + 2) * TC_PITCH, 0, 0, 0};
   double best_eff = 0.0;
   for (int U = 1; U <= 4; ++U) {
     const int n_out = (U - 1) * best.Pu + TC_PITCH * H - 1;
     const int tiles = (n_out + 127) / 128;
     const int R = (TC_Q0 + tiles * 128 + 12 + 7) & ~7;
-    const size_t smem = 2 * (size_t)TC_WBYTES + 2 * (size_t)R * 96 + 4096;
-    if (tiles > 5 || smem > 227 * 1024) continue;
+    const size_t smem = tc_conv_smem(U, R, H);
+    if (tiles > 5 || smem > TC_SMEM_LIMIT) continue;
     const double eff = (double)U * H * R8_W / (tiles * 128.0);
     if (eff > best_eff + 1e-9) {
       best_eff = eff;
       best.U = U;
       best.tiles = tiles;
       best.R = R;
+      best.smem = smem;
     }
   }
   return best;
@@ -49,13 +61,13 @@ static size_t tc_wgrad_smem(int H, int* Kp_out, int* Rx_out) {
   const int Rx = (12 + Kp + 12 + 7) & ~7;
   if (Kp_out) *Kp_out = Kp;
   if (Rx_out) *Rx_out = Rx;
-  // the A operand addresses 16 groups of 8 output channels (M = 128): keep the 10 padding groups inside the buffer
+  // the A operand addresses 16 groups of 8 rows (M = 128 = dC_hi | dC_lo | padding): groups 12..15 must stay inside
   const size_t operand = (12 * (size_t)Kp + 12 * (size_t)Rx) * 16;
-  const size_t need_a = ((size_t)(6 + 16) * Kp) * 16;
-  return (operand > need_a ? operand : need_a) + 200 * 4;
+  const size_t need_a = ((size_t)16 * Kp) * 16;
+  return (operand > need_a ? operand : need_a) + 2 * tc_slot_bytes(H) + 128 * 4;
 }
 
-bool r8tc_supported(int H) { return tc_geom(H).U > 0 && tc_wgrad_smem(H, nullptr, nullptr) <= 227 * 1024; }
+bool r8tc_supported(int H) { return tc_geom(H).U > 0 && tc_wgrad_smem(H, nullptr, nullptr) <= TC_SMEM_LIMIT; }
 
 // =============================================================================================
 // weight operands: W fp32 [6][45 o][45 c][3][3] -> bf16 (hi, lo) [tap][chunk][48 n][8 k]
@@ -87,6 +99,30 @@ int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __
   return HOWL_OK;
 }
 
+// raw fp32 planes [45][H][10] (shared-memory staging, landed by TMA) -> (hi, lo) bf16 raster rows; BN on the fly.
+// 256 worker threads; one item = 8 channels of one pixel = one 16-byte operand row.
+__device__ __forceinline__ void tc_transform(const float* __restrict__ stage, bool present, int H, int row_base, int R,
+                                             const float* s_mean, const float* s_rstd, uint4* a_hi, uint4* a_lo, int tid) {
+  const int HW = H * R8_W;
+  for (int it = tid; it < 6 * HW; it += TC_WORKERS) {
+    const int chunk = it / HW, pp = it - chunk * HW;
+    const int y = pp / R8_W, x = pp - y * R8_W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = chunk * 8 + j;
+      const int cc = c < R8_C ? c : R8_C - 1;                      // clamp: no divergent guards around the loads
+      const float raw = stage[cc * HW + pp];
+      v[j] = (present && c < R8_C) ? (raw - s_mean[cc]) * s_rstd[cc] : 0.f;
+    }
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    const int row = row_base + (y + 1) * TC_PITCH + (x + 1);
+    a_hi[chunk * R + row] = hi;
+    a_lo[chunk * R + row] = lo;
+  }
+}
+
 // =============================================================================================
 // forward / data-gradient kernel
 // =============================================================================================
@@ -97,52 +133,37 @@ struct TcConvArgs {
   TcGeom g;
 };
 
-// stage one [45][H][10] fp32 plane set as (hi, lo) bf16 rows of the raster; BN applied on the fly
-__device__ __forceinline__ void tc_stage_planes(const float* __restrict__ src, bool present, int H, int row_base,
-                                                int R, const float* s_mean, const float* s_rstd, uint4* a_hi,
-                                                uint4* a_lo, int tid) {
-  const int HW = H * R8_W;
-  for (int it = tid; it < 6 * HW; it += TC_THREADS) {
-    const int chunk = it / HW, pp = it - chunk * HW;
-    const int y = pp / R8_W, x = pp - y * R8_W;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = chunk * 8 + j;
-      v[j] = (present && c < R8_C) ? (__ldg(src + (size_t)c * HW + pp) - s_mean[c]) * s_rstd[c] : 0.f;
-    }
-    uint4 hi, lo;
-    tc::split8(v, hi, lo);
-    const int row = row_base + (y + 1) * TC_PITCH + (x + 1);
-    a_hi[chunk * R + row] = hi;
-    a_lo[chunk * R + row] = lo;
-  }
-}
-
 template <bool RELU, int STATS>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const ConvParams& p = a.p;
   const int H = p.H, U = a.g.U, Pu = a.g.Pu, tiles = a.g.tiles, R = a.g.R, HW = H * R8_W;
+  const uint32_t plane_bytes = (uint32_t)(R8_C * HW * 4);
   uint4* w_hi = reinterpret_cast<uint4*>(smem);
   uint4* w_lo = reinterpret_cast<uint4*>(smem + TC_WBYTES);
   uint4* a_hi = reinterpret_cast<uint4*>(smem + 2 * TC_WBYTES);
   uint4* a_lo = a_hi + 6 * R;
-  float* s_f = reinterpret_cast<float*>(a_lo + 6 * R);
+  unsigned char* stage = reinterpret_cast<unsigned char*>(a_lo + 6 * R);   // [U] slots of raw fp32 planes [45][HW]
+  const size_t slot = tc_slot_bytes(H);
+  float* s_f = reinterpret_cast<float*>(stage + (size_t)U * slot);
   float* s_mean = s_f;            // [48]
   float* s_rstd = s_f + 48;
   float* s_amean = s_f + 96;
   float* s_arstd = s_f + 144;
   float* s_red = s_f + 192;       // [8 warps][2][48]
-  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ __align__(8) uint64_t bar_w, bar_stage, bar_tile[5];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t groups = (p.B + U - 1) / U;
 
-  if (warp == 0) tc::tmem_alloc<256>(&s_tmem);
-  if (tid == 32) {
-    tc::mbar_init(&bar_w, 1);
-    tc::mbar_init(&bar_mma, 1);
-    tc::fence_barrier_init();
+  if (warp == 8) {
+    tc::tmem_alloc<256>(&s_tmem);
+    if (lane == 0) {
+      tc::mbar_init(&bar_w, 1);
+      tc::mbar_init(&bar_stage, 1);
+      for (int t = 0; t < 5; ++t) tc::mbar_init(&bar_tile[t], 1);
+      tc::fence_barrier_init();
+    }
   }
   for (int i = tid; i < 12 * R; i += TC_THREADS) a_hi[i] = make_uint4(0, 0, 0, 0);   // a_hi and a_lo are contiguous
   if (tid < 48) {
@@ -155,103 +176,146 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvA
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  if (tid == 32) {
+  const uint32_t tmem = s_tmem;
+
+  // TMA producer for one group of U utterances (each utterance's 45 planes are one contiguous block in HBM)
+  auto issue_stage = [&](int64_t g) {
+    uint32_t bytes = 0;
+    for (int u = 0; u < U; ++u) {
+      const int64_t b = g * U + u;
+      if (b < p.B) {
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.in + b * (int64_t)R8_C * HW) & 15);
+        bytes += (mis + plane_bytes + 15u) & ~15u;
+      }
+    }
+    tc::mbar_expect_tx(&bar_stage, bytes);
+    for (int u = 0; u < U; ++u) {
+      const int64_t b = g * U + u;
+      if (b < p.B) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.in + b * (int64_t)R8_C * HW);
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+        tc::tma_bulk_g2s(stage + (size_t)u * slot, src - mis, (mis + plane_bytes + 15u) & ~15u, &bar_stage);
+      }
+    }
+  };
+  if (tid == 256) {
     tc::mbar_expect_tx(&bar_w, 2 * TC_WBYTES);
     tc::tma_bulk_g2s(w_hi, a.whi, TC_WBYTES, &bar_w);
     tc::tma_bulk_g2s(w_lo, a.wlo, TC_WBYTES, &bar_w);
+    if ((int64_t)blockIdx.x < groups) issue_stage(blockIdx.x);
   }
-  const uint32_t tmem = s_tmem;
   const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 0, 0);
   const uint32_t a_hi_s = tc::smem_u32(a_hi), a_lo_s = tc::smem_u32(a_lo);
   const uint32_t w_hi_s = tc::smem_u32(w_hi), w_lo_s = tc::smem_u32(w_lo);
-  tc::mbar_wait(&bar_w, 0);
 
   float st1[R8_C], st2[R8_C];
 #pragma unroll
   for (int c = 0; c < R8_C; ++c) st1[c] = st2[c] = 0.f;
 
-  const int64_t groups = (p.B + U - 1) / U;
   uint32_t phase = 0;
   for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
-    // ---- stage U utterances (generic proxy writes), then hand the tile to the async proxy
-    for (int u = 0; u < U; ++u) {
-      const int64_t b = g * U + u;
-      tc_stage_planes(p.in + b * (int64_t)R8_C * HW, b < p.B, H, u * Pu, R, s_mean, s_rstd, a_hi, a_lo, tid);
+    // ---- raw planes have landed: transform to bf16 (hi, lo) operand rows
+    if (warp < 8) {
+      tc::mbar_wait(&bar_stage, phase);
+      for (int u = 0; u < U; ++u) {
+        const int64_t b = g * U + u;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.in + b * (int64_t)R8_C * HW) & 15);
+        tc_transform(reinterpret_cast<const float*>(stage + (size_t)u * slot + mis), b < p.B, H, u * Pu, R, s_mean, s_rstd,
+                     a_hi, a_lo, tid);
+      }
+      tc::fence_proxy_async();
     }
-    tc::fence_proxy_async();
-    __syncthreads();
-    // ---- one thread issues every MMA of this group: tiles x 9 taps x 3 k-steps x 3 split terms
-    if (tid == 0) {
-      tc::fence_after_sync();
-      for (int t = 0; t < tiles; ++t) {
-        const uint32_t d = tmem + (uint32_t)(t * TC_N);
-        uint32_t acc = 0;
+    __syncthreads();            // operands complete, staging buffer free
+    if (warp == 8) {
+      if (lane == 0) {
+        if (g + gridDim.x < groups) issue_stage(g + gridDim.x);   // prefetch the next group during the MMAs
+        if (g == (int64_t)blockIdx.x) tc::mbar_wait(&bar_w, 0);
+        tc::fence_after_sync();
+        for (int t = 0; t < tiles; ++t) {
+          const uint32_t d = tmem + (uint32_t)(t * TC_N);
+          uint32_t acc = 0;
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
-          const uint32_t row0 = (uint32_t)(TC_Q0 + 128 * t + shift);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
+            const uint32_t row0 = (uint32_t)(TC_Q0 + 128 * t + shift);
 #pragma unroll
-          for (int ks = 0; ks < 3; ++ks) {
-            const uint32_t aoff = ((uint32_t)(2 * ks) * R + row0) * 16u;
-            const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N) * 16u;
-            const uint64_t ah = tc::smem_desc(a_hi_s + aoff, (uint32_t)R * 16u, 128u);
-            const uint64_t al = tc::smem_desc(a_lo_s + aoff, (uint32_t)R * 16u, 128u);
-            const uint64_t bh = tc::smem_desc(w_hi_s + boff, TC_N * 16u, 128u);
-            const uint64_t bl = tc::smem_desc(w_lo_s + boff, TC_N * 16u, 128u);
-            tc::umma_bf16(d, al, bh, idesc, acc);
-            tc::umma_bf16(d, ah, bl, idesc, 1u);
-            tc::umma_bf16(d, ah, bh, idesc, 1u);
-            acc = 1u;
+            for (int ks = 0; ks < 3; ++ks) {
+              const uint32_t aoff = ((uint32_t)(2 * ks) * R + row0) * 16u;
+              const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N) * 16u;
+              const uint64_t ah = tc::smem_desc(a_hi_s + aoff, (uint32_t)R * 16u, 128u);
+              const uint64_t al = tc::smem_desc(a_lo_s + aoff, (uint32_t)R * 16u, 128u);
+              const uint64_t bh = tc::smem_desc(w_hi_s + boff, TC_N * 16u, 128u);
+              const uint64_t bl = tc::smem_desc(w_lo_s + boff, TC_N * 16u, 128u);
+              tc::umma_bf16(d, al, bh, idesc, acc);
+              tc::umma_bf16(d, ah, bl, idesc, 1u);
+              tc::umma_bf16(d, ah, bh, idesc, 1u);
+              acc = 1u;
+            }
+          }
+          tc::umma_commit(&bar_tile[t]);      // tile t can be drained while later tiles are still in the tensor pipe
+        }
+      }
+    } else {
+      // ---- epilogue out of TMEM: warps 0-3 take even tiles, warps 4-7 odd tiles; thread = one raster row
+      for (int t = warp >> 2; t < tiles; t += 2) {
+        const int q = TC_Q0 + 128 * t + 32 * (warp & 3) + lane;
+        const int u = q / Pu, rem = q - u * Pu;
+        const int y = rem / TC_PITCH - 1, x = rem % TC_PITCH - 1;
+        const int64_t b = g * U + u;
+        const bool valid = (u < U) && (b < p.B) && (y >= 0) && (y < H) && (x >= 0) && (x < R8_W);
+        const int64_t base = valid ? b * (int64_t)R8_C * HW + y * R8_W + x : 0;
+        const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(t * TC_N);
+        tc::mbar_wait(&bar_tile[t], phase);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          float rr[16], aa[16], v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = cb * 16 + j;
+            rr[j] = aa[j] = 0.f;
+            if (c < R8_C && valid) {
+              if (p.res) rr[j] = __ldg(p.res + base + (int64_t)c * HW);
+              if (STATS == 2) aa[j] = __ldg(p.aux + base + (int64_t)c * HW);
+            }
+          }
+          tc::tmem_ld16(taddr + 16 * cb, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = cb * 16 + j;
+              if (c < R8_C) {
+                float o = v[j];
+                if (RELU) o = fmaxf(o, 0.f);
+                o += rr[j];
+                p.out[base + (int64_t)c * HW] = o;
+                if (STATS == 1) {
+                  st1[c] += o;
+                  st2[c] = fmaf(o, o, st2[c]);
+                } else if (STATS == 2) {
+                  st1[c] += o;
+                  st2[c] = fmaf(o, (aa[j] - s_amean[c]) * s_arstd[c], st2[c]);
+                }
+              }
+            }
           }
         }
       }
-      tc::umma_commit(&bar_mma);
+      tc::fence_before_sync();
     }
-    tc::mbar_wait(&bar_mma, phase);
     phase ^= 1u;
-    tc::fence_after_sync();
-    // ---- epilogue out of TMEM: warps 0-3 take even tiles, warps 4-7 odd tiles; thread = one raster row
-    for (int t = warp >> 2; t < tiles; t += 2) {
-      const int q = TC_Q0 + 128 * t + 32 * (warp & 3) + lane;
-      const int u = q / Pu, rem = q - u * Pu;
-      const int y = rem / TC_PITCH - 1, x = rem % TC_PITCH - 1;
-      const int64_t b = g * U + u;
-      const bool valid = (u < U) && (b < p.B) && (y >= 0) && (y < H) && (x >= 0) && (x < R8_W);
-      const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(t * TC_N);
-      float v[48];
-      tc::tmem_ld16(taddr, v);
-      tc::tmem_ld16(taddr + 16, v + 16);
-      tc::tmem_ld16(taddr + 32, v + 32);
-      if (valid) {
-        const int64_t base = b * (int64_t)R8_C * HW + y * R8_W + x;
-#pragma unroll
-        for (int c = 0; c < R8_C; ++c) {
-          float o = v[c];
-          if (RELU) o = fmaxf(o, 0.f);
-          const int64_t idx = base + (int64_t)c * HW;
-          if (p.res) o += __ldg(p.res + idx);
-          p.out[idx] = o;
-          if (STATS == 1) {
-            st1[c] += o;
-            st2[c] = fmaf(o, o, st2[c]);
-          } else if (STATS == 2) {
-            st1[c] += o;
-            st2[c] = fmaf(o, (__ldg(p.aux + idx) - s_amean[c]) * s_arstd[c], st2[c]);
-          }
-        }
-      }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
+    __syncthreads();            // TMEM drained, operand rows reusable
   }
   // ---- per-channel statistics: lanes -> warps -> one fp64 atomic per channel and CTA
   if (STATS) {
+    if (warp < 8) {
 #pragma unroll
-    for (int c = 0; c < R8_C; ++c) {
-      const float a1 = warp_sum(st1[c]), a2 = warp_sum(st2[c]);
-      if (lane == 0) {
-        s_red[(warp * 2 + 0) * 48 + c] = a1;
-        s_red[(warp * 2 + 1) * 48 + c] = a2;
+      for (int c = 0; c < R8_C; ++c) {
+        const float a1 = warp_sum(st1[c]), a2 = warp_sum(st2[c]);
+        if (lane == 0) {
+          s_red[(warp * 2 + 0) * 48 + c] = a1;
+          s_red[(warp * 2 + 1) * 48 + c] = a2;
+        }
       }
     }
     __syncthreads();
@@ -263,10 +327,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvA
     }
   }
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<256>(tmem);
+  if (warp == 8) tc::tmem_dealloc<256>(tmem);
 }
-
-static size_t tc_conv_smem(const TcGeom& g) { return 2 * (size_t)TC_WBYTES + 12 * (size_t)g.R * 16 + (192 + 8 * 2 * 48) * 4; }
 
 int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* whi, const __nv_bfloat16* wlo,
               bool relu, int stats) {
@@ -276,7 +338,7 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
   a.wlo = wlo;
   a.g = tc_geom(p.H);
   HOWL_REQUIRE(ctx, a.g.U > 0, HOWL_E_UNSUPPORTED, "tensor-core conv: H=%d does not fit", p.H);
-  const size_t smem = tc_conv_smem(a.g);
+  const size_t smem = a.g.smem;
   const int64_t groups = (p.B + a.g.U - 1) / a.g.U;
   const int grid = (int)(groups < ctx->sm_count ? groups : ctx->sm_count);
 #define TC_LAUNCH(RELU_, STATS_)                                                                                  \
@@ -296,7 +358,10 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
 }
 
 // =============================================================================================
-// weight-gradient kernel: dW_tap[o][c] = sum_q dC[q][o] * X[q + shift][c], all 9 taps resident in TMEM
+// weight-gradient kernel: dW_tap[o][c] = sum_q dC[q][o] * X[q + shift][c], all 9 taps resident in TMEM.
+// The M = 128 rows of the A operand are [dC_hi (48) | dC_lo (48) | padding (32)] -- dC_lo sits exactly six 8-channel
+// groups behind dC_hi in shared memory -- so two MMAs per k-step (x X_hi, x X_lo) produce hi*hi, lo*hi, hi*lo and
+// lo*lo; the epilogue adds TMEM rows o and 48 + o.
 // =============================================================================================
 struct TcWgradArgs {
   WgradParams p;
@@ -308,20 +373,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   extern __shared__ __align__(128) unsigned char smem[];
   const WgradParams& p = a.p;
   const int H = p.H, HW = H * R8_W, Kp = a.Kp, Rx = a.Rx;
+  const uint32_t plane_bytes = (uint32_t)(R8_C * HW * 4);
   uint4* d_hi = reinterpret_cast<uint4*>(smem);     // [6][Kp]   dC, rows = raster position q
   uint4* d_lo = d_hi + 6 * Kp;
   uint4* x_hi = d_lo + 6 * Kp;                      // [6][Rx]   X,  rows = q + 12
   uint4* x_lo = x_hi + 6 * Rx;
-  float* s_mean = reinterpret_cast<float*>(x_lo + 6 * Rx);
+  const size_t operand = (12 * (size_t)Kp + 12 * (size_t)Rx) * 16, need_a = (size_t)16 * Kp * 16;
+  const size_t slot = tc_slot_bytes(H);
+  unsigned char* stage_d = smem + (operand > need_a ? operand : need_a);
+  unsigned char* stage_x = stage_d + slot;
+  float* s_mean = reinterpret_cast<float*>(stage_x + slot);
   float* s_rstd = s_mean + 48;
-  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ __align__(8) uint64_t bar_stage, bar_mma;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (warp == 0) tc::tmem_alloc<512>(&s_tmem);
-  if (tid == 32) {
-    tc::mbar_init(&bar_mma, 1);
-    tc::fence_barrier_init();
+  if (warp == 8) {
+    tc::tmem_alloc<512>(&s_tmem);
+    if (lane == 0) {
+      tc::mbar_init(&bar_stage, 1);
+      tc::mbar_init(&bar_mma, 1);
+      tc::fence_barrier_init();
+    }
   }
   for (int i = tid; i < 12 * Kp + 12 * Rx; i += TC_THREADS) d_hi[i] = make_uint4(0, 0, 0, 0);
   if (tid < 48) {
@@ -333,34 +406,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
+  auto issue_stage = [&](int64_t b) {
+    const unsigned char* sd = reinterpret_cast<const unsigned char*>(p.dc + b * (int64_t)R8_C * HW);
+    const unsigned char* sx = reinterpret_cast<const unsigned char*>(p.x + b * (int64_t)R8_C * HW);
+    const uint32_t md = (uint32_t)(reinterpret_cast<uintptr_t>(sd) & 15), mx = (uint32_t)(reinterpret_cast<uintptr_t>(sx) & 15);
+    const uint32_t bd = (md + plane_bytes + 15u) & ~15u, bx = (mx + plane_bytes + 15u) & ~15u;
+    tc::mbar_expect_tx(&bar_stage, bd + bx);
+    tc::tma_bulk_g2s(stage_d, sd - md, bd, &bar_stage);
+    tc::tma_bulk_g2s(stage_x, sx - mx, bx, &bar_stage);
+  };
+  if (tid == 256 && (int64_t)blockIdx.x < p.B) issue_stage(blockIdx.x);
   const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 1, 1);   // both operands MN-major (K = raster positions)
-  const uint32_t d_hi_s = tc::smem_u32(d_hi), d_lo_s = tc::smem_u32(d_lo);
+  const uint32_t d_hi_s = tc::smem_u32(d_hi);
   const uint32_t x_hi_s = tc::smem_u32(x_hi), x_lo_s = tc::smem_u32(x_lo);
+  // identity "BN" for the dC planes
+  __shared__ float s_id[96];
+  if (tid < 48) {
+    s_id[tid] = 0.f;
+    s_id[48 + tid] = 1.f;
+  }
+  __syncthreads();
   uint32_t phase = 0, first = 1;
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
-    // dC: no normalisation, rows q;  X: BN on the fly, rows q + 12
-    {
-      const float* src = p.dc + b * (int64_t)R8_C * HW;
-      for (int it = tid; it < 6 * HW; it += TC_THREADS) {
-        const int chunk = it / HW, pp = it - chunk * HW;
-        const int y = pp / R8_W, x = pp - y * R8_W;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = chunk * 8 + j;
-          v[j] = (c < R8_C) ? __ldg(src + (size_t)c * HW + pp) : 0.f;
-        }
-        uint4 hi, lo;
-        tc::split8(v, hi, lo);
-        const int row = (y + 1) * TC_PITCH + (x + 1);
-        d_hi[chunk * Kp + row] = hi;
-        d_lo[chunk * Kp + row] = lo;
-      }
+    if (warp < 8) {
+      tc::mbar_wait(&bar_stage, phase);
+      const uint32_t md = (uint32_t)(reinterpret_cast<uintptr_t>(p.dc + b * (int64_t)R8_C * HW) & 15);
+      const uint32_t mx = (uint32_t)(reinterpret_cast<uintptr_t>(p.x + b * (int64_t)R8_C * HW) & 15);
+      tc_transform(reinterpret_cast<const float*>(stage_d + md), true, H, 0, Kp, s_id, s_id + 48, d_hi, d_lo, tid);   // dC: rows q
+      tc_transform(reinterpret_cast<const float*>(stage_x + mx), true, H, 12, Rx, s_mean, s_rstd, x_hi, x_lo, tid);  // X: rows q + 12
+      tc::fence_proxy_async();
     }
-    tc_stage_planes(p.x + b * (int64_t)R8_C * HW, true, H, 12, Rx, s_mean, s_rstd, x_hi, x_lo, tid);
-    tc::fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 256) {
+      if (b + gridDim.x < p.B) issue_stage(b + gridDim.x);
       tc::fence_after_sync();
 #pragma unroll 1
       for (int tap = 0; tap < 9; ++tap) {
@@ -371,13 +449,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
           const uint32_t aoff = (uint32_t)k0 * 16u;
           const uint32_t boff = (uint32_t)(12 + shift + k0) * 16u;
           // MN-major: lbo = stride between 8-position K groups (128 B), sbo = stride between 8-channel groups
-          const uint64_t ah = tc::smem_desc(d_hi_s + aoff, 128u, (uint32_t)Kp * 16u);
-          const uint64_t al = tc::smem_desc(d_lo_s + aoff, 128u, (uint32_t)Kp * 16u);
+          const uint64_t ad = tc::smem_desc(d_hi_s + aoff, 128u, (uint32_t)Kp * 16u);
           const uint64_t bh = tc::smem_desc(x_hi_s + boff, 128u, (uint32_t)Rx * 16u);
           const uint64_t bl = tc::smem_desc(x_lo_s + boff, 128u, (uint32_t)Rx * 16u);
-          tc::umma_bf16(d, al, bh, idesc, acc);
-          tc::umma_bf16(d, ah, bl, idesc, 1u);
-          tc::umma_bf16(d, ah, bh, idesc, 1u);
+          tc::umma_bf16(d, ad, bl, idesc, acc);
+          tc::umma_bf16(d, ad, bh, idesc, 1u);
           acc = 1u;
         }
       }
@@ -388,32 +464,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
     phase ^= 1u;
     tc::fence_after_sync();
   }
-  // ---- epilogue: TMEM lane = output channel o (rows 45..127 are padding), column = tap * 48 + c
-  if (first == 0) {
-    const int o = 32 * (warp & 3) + lane;
+  // ---- epilogue: TMEM lane r: r < 48 -> dC_hi row of channel r, 48 <= r < 96 -> dC_lo row of channel r - 48
+  if (first == 0 && warp < 8) {
+    const int r = 32 * (warp & 3) + lane;
+    const int o = r < 48 ? r : r - 48;
+    const bool ok = r < 96 && o < R8_C;
     const int half = warp >> 2;                    // warps 0-3: taps 0..4, warps 4-7: taps 5..8
     for (int tap = half ? 5 : 0; tap < (half ? 9 : 5); ++tap) {
       const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(tap * TC_N);
-      float v[48];
-      tc::tmem_ld16(taddr, v);
-      tc::tmem_ld16(taddr + 16, v + 16);
-      tc::tmem_ld16(taddr + 32, v + 32);
-      if (o < R8_C) {
 #pragma unroll
-        for (int c = 0; c < R8_C; ++c) atomicAdd(&p.dw[(o * R8_C + c) * 9 + tap], v[c]);
+      for (int cb = 0; cb < 3; ++cb) {
+        float v[16];
+        tc::tmem_ld16(taddr + 16 * cb, v);
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = cb * 16 + j;
+            if (c < R8_C) atomicAdd(&p.dw[(o * R8_C + c) * 9 + tap], v[j]);
+          }
+        }
       }
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+  if (warp == 8) tc::tmem_dealloc<512>(tmem);
 }
 
 int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const WgradParams& p) {
   TcWgradArgs a;
   a.p = p;
   const size_t smem = tc_wgrad_smem(p.H, &a.Kp, &a.Rx);
-  HOWL_REQUIRE(ctx, smem <= 227 * 1024, HOWL_E_UNSUPPORTED, "tensor-core wgrad: H=%d does not fit", p.H);
+  HOWL_REQUIRE(ctx, smem <= TC_SMEM_LIMIT, HOWL_E_UNSUPPORTED, "tensor-core wgrad: H=%d does not fit", p.H);
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(p.B < ctx->sm_count ? p.B : ctx->sm_count);
   conv3x3_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
