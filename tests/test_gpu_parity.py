@@ -29,12 +29,17 @@ def _assert_grads(got, refs, L, tight):
     conv-weight gradient by ~1e-3 of its scale; torch-CPU fp32, float64 and both engines differ pairwise by that noise
     (parity notes).  The head gradients see no mask downstream and stay tight."""
     off = 0
+    norm_all = np.linalg.norm(refs[0])
     for name, shape in O.res8_param_shapes(L):
         n = int(np.prod(shape))
         sl = slice(off, off + n)
         off += n
         ref = refs[0][sl]
         scale = np.abs(ref).max()
+        if not tight and np.linalg.norm(ref) < 1e-3 * norm_all:
+            # a tensor whose gradient is (numerically) nil next to the rest, e.g. under single-clip BatchNorm
+            assert np.linalg.norm(got[sl] - ref) <= 1e-3 * norm_all, name
+            continue
         if tight:
             np.testing.assert_allclose(got[sl], ref, rtol=1e-3, atol=1e-5, err_msg=name)
             continue
