@@ -104,22 +104,29 @@ int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __
 __device__ __forceinline__ void tc_transform(const float* __restrict__ stage, bool present, int H, int row_base, int R,
                                              const float* s_mean, const float* s_rstd, uint4* a_hi, uint4* a_lo, int tid) {
   const int HW = H * R8_W;
-  for (int it = tid; it < 6 * HW; it += TC_WORKERS) {
-    const int chunk = it / HW, pp = it - chunk * HW;
-    const int y = pp / R8_W, x = pp - y * R8_W;
-    float v[8];
+#pragma unroll 1
+  for (int chunk = 0; chunk < 6; ++chunk) {
+    float mu[8], rs[8];
+    int coff[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = chunk * 8 + j;
-      const int cc = c < R8_C ? c : R8_C - 1;                      // clamp: no divergent guards around the loads
-      const float raw = stage[cc * HW + pp];
-      v[j] = (present && c < R8_C) ? (raw - s_mean[cc]) * s_rstd[cc] : 0.f;
+      const int cc = c < R8_C ? c : R8_C - 1;                 // clamped address, zero scale: no guards around loads
+      mu[j] = s_mean[cc];
+      rs[j] = (present && c < R8_C) ? s_rstd[cc] : 0.f;
+      coff[j] = cc * HW;
     }
-    uint4 hi, lo;
-    tc::split8(v, hi, lo);
-    const int row = row_base + (y + 1) * TC_PITCH + (x + 1);
-    a_hi[chunk * R + row] = hi;
-    a_lo[chunk * R + row] = lo;
+    for (int pp = tid; pp < HW; pp += TC_WORKERS) {
+      const int y = pp / R8_W, x = pp - y * R8_W;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (stage[coff[j] + pp] - mu[j]) * rs[j];
+      uint4 hi, lo;
+      tc::split8(v, hi, lo);
+      const int row = row_base + (y + 1) * TC_PITCH + (x + 1);
+      a_hi[chunk * R + row] = hi;
+      a_lo[chunk * R + row] = lo;
+    }
   }
 }
 
@@ -208,9 +215,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvA
   const uint32_t a_hi_s = tc::smem_u32(a_hi), a_lo_s = tc::smem_u32(a_lo);
   const uint32_t w_hi_s = tc::smem_u32(w_hi), w_lo_s = tc::smem_u32(w_lo);
 
-  float st1[R8_C], st2[R8_C];
+  float st1[24], st2[24];        // statistics of this thread's 24 channels (warp quad) over all its rows
 #pragma unroll
-  for (int c = 0; c < R8_C; ++c) st1[c] = st2[c] = 0.f;
+  for (int c = 0; c < 24; ++c) st1[c] = st2[c] = 0.f;
 
   uint32_t phase = 0;
   for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
@@ -231,70 +238,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvA
         if (g + gridDim.x < groups) issue_stage(g + gridDim.x);   // prefetch the next group during the MMAs
         if (g == (int64_t)blockIdx.x) tc::mbar_wait(&bar_w, 0);
         tc::fence_after_sync();
+        const uint32_t ah_lo = tc::desc_lo(a_hi_s, (uint32_t)R * 16u), al_lo = tc::desc_lo(a_lo_s, (uint32_t)R * 16u);
+        const uint32_t bh_lo = tc::desc_lo(w_hi_s, TC_N * 16u), bl_lo = tc::desc_lo(w_lo_s, TC_N * 16u);
+        const uint32_t d_hi128 = tc::desc_hi(128u);
         for (int t = 0; t < tiles; ++t) {
           const uint32_t d = tmem + (uint32_t)(t * TC_N);
-          uint32_t acc = 0;
-#pragma unroll 1
+          const uint32_t rowb = (uint32_t)(TC_Q0 + 128 * t);
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
-            const uint32_t row0 = (uint32_t)(TC_Q0 + 128 * t + shift);
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks) {
-              const uint32_t aoff = ((uint32_t)(2 * ks) * R + row0) * 16u;
-              const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N) * 16u;
-              const uint64_t ah = tc::smem_desc(a_hi_s + aoff, (uint32_t)R * 16u, 128u);
-              const uint64_t al = tc::smem_desc(a_lo_s + aoff, (uint32_t)R * 16u, 128u);
-              const uint64_t bh = tc::smem_desc(w_hi_s + boff, TC_N * 16u, 128u);
-              const uint64_t bl = tc::smem_desc(w_lo_s + boff, TC_N * 16u, 128u);
-              tc::umma_bf16(d, al, bh, idesc, acc);
+              const uint32_t aoff = (uint32_t)(2 * ks) * (uint32_t)R + rowb + (uint32_t)shift;   // 16-byte units
+              const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N);
+              const uint64_t ah = tc::desc_make(ah_lo + aoff, d_hi128), al = tc::desc_make(al_lo + aoff, d_hi128);
+              const uint64_t bh = tc::desc_make(bh_lo + boff, d_hi128), bl = tc::desc_make(bl_lo + boff, d_hi128);
+              tc::umma_bf16(d, al, bh, idesc, (tap | ks) ? 1u : 0u);
               tc::umma_bf16(d, ah, bl, idesc, 1u);
               tc::umma_bf16(d, ah, bh, idesc, 1u);
-              acc = 1u;
             }
           }
           tc::umma_commit(&bar_tile[t]);      // tile t can be drained while later tiles are still in the tensor pipe
         }
       }
     } else {
-      // ---- epilogue out of TMEM: warps 0-3 take even tiles, warps 4-7 odd tiles; thread = one raster row
-      for (int t = warp >> 2; t < tiles; t += 2) {
+      // ---- epilogue out of TMEM: thread = one raster row; warp quad h (warps 4h..4h+3) owns channels 24h..24h+23 of
+      //      every tile, so both quads start on tile 0 as soon as it commits and the work is balanced
+      const int half = warp >> 2;
+      for (int t = 0; t < tiles; ++t) {
         const int q = TC_Q0 + 128 * t + 32 * (warp & 3) + lane;
         const int u = q / Pu, rem = q - u * Pu;
         const int y = rem / TC_PITCH - 1, x = rem % TC_PITCH - 1;
         const int64_t b = g * U + u;
         const bool valid = (u < U) && (b < p.B) && (y >= 0) && (y < H) && (x >= 0) && (x < R8_W);
         const int64_t base = valid ? b * (int64_t)R8_C * HW + y * R8_W + x : 0;
-        const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(t * TC_N);
+        const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(t * TC_N + 24 * half);
+        float rr[24], aa[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {       // residual / aux operands are fetched while the tile is still in flight
+          const int c = 24 * half + j;
+          rr[j] = aa[j] = 0.f;
+          if (c < R8_C && valid) {
+            if (p.res) rr[j] = __ldg(p.res + base + (int64_t)c * HW);
+            if (STATS == 2) aa[j] = __ldg(p.aux + base + (int64_t)c * HW);
+          }
+        }
         tc::mbar_wait(&bar_tile[t], phase);
         tc::fence_after_sync();
 #pragma unroll
         for (int cb = 0; cb < 3; ++cb) {
-          float rr[16], aa[16], v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = cb * 16 + j;
-            rr[j] = aa[j] = 0.f;
-            if (c < R8_C && valid) {
-              if (p.res) rr[j] = __ldg(p.res + base + (int64_t)c * HW);
-              if (STATS == 2) aa[j] = __ldg(p.aux + base + (int64_t)c * HW);
-            }
-          }
-          tc::tmem_ld16(taddr + 16 * cb, v);
+          float v[8];
+          tc::tmem_ld8(taddr + 8 * cb, v);
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = cb * 16 + j;
+            for (int j = 0; j < 8; ++j) {
+              const int jj = cb * 8 + j, c = 24 * half + jj;
               if (c < R8_C) {
                 float o = v[j];
                 if (RELU) o = fmaxf(o, 0.f);
-                o += rr[j];
+                o += rr[jj];
                 p.out[base + (int64_t)c * HW] = o;
                 if (STATS == 1) {
-                  st1[c] += o;
-                  st2[c] = fmaf(o, o, st2[c]);
+                  st1[jj] += o;
+                  st2[jj] = fmaf(o, o, st2[jj]);
                 } else if (STATS == 2) {
-                  st1[c] += o;
-                  st2[c] = fmaf(o, (aa[j] - s_amean[c]) * s_arstd[c], st2[c]);
+                  st1[jj] += o;
+                  st2[jj] = fmaf(o, (aa[jj] - s_amean[c]) * s_arstd[c], st2[jj]);
                 }
               }
             }
@@ -310,19 +319,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvA
   if (STATS) {
     if (warp < 8) {
 #pragma unroll
-      for (int c = 0; c < R8_C; ++c) {
-        const float a1 = warp_sum(st1[c]), a2 = warp_sum(st2[c]);
+      for (int j = 0; j < 24; ++j) {
+        const float a1 = warp_sum(st1[j]), a2 = warp_sum(st2[j]);
         if (lane == 0) {
-          s_red[(warp * 2 + 0) * 48 + c] = a1;
-          s_red[(warp * 2 + 1) * 48 + c] = a2;
+          s_red[(warp * 2 + 0) * 24 + j] = a1;
+          s_red[(warp * 2 + 1) * 24 + j] = a2;
         }
       }
     }
     __syncthreads();
     if (tid < 2 * R8_C) {
-      const int which = tid / R8_C, c = tid - which * R8_C;
+      const int which = tid / R8_C, c = tid - which * R8_C, half = c / 24, j = c - 24 * half;
       double s = 0.0;
-      for (int w = 0; w < 8; ++w) s += (double)s_red[(w * 2 + which) * 48 + c];
+      for (int w = 4 * half; w < 4 * half + 4; ++w) s += (double)s_red[(w * 2 + which) * 24 + j];
       atomicAdd(&p.stats[tid], s);
     }
   }
@@ -440,20 +449,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
     if (tid == 256) {
       if (b + gridDim.x < p.B) issue_stage(b + gridDim.x);
       tc::fence_after_sync();
-#pragma unroll 1
+      // MN-major: lbo = stride between 8-position K groups (128 B), sbo = stride between 8-channel groups
+      const uint32_t ad_lo = tc::desc_lo(d_hi_s, 128u), ad_hi = tc::desc_hi((uint32_t)Kp * 16u);
+      const uint32_t bh_lo = tc::desc_lo(x_hi_s, 128u), bl_lo = tc::desc_lo(x_lo_s, 128u), b_hi = tc::desc_hi((uint32_t)Rx * 16u);
+#pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
         const uint32_t d = tmem + (uint32_t)(tap * TC_N);
         uint32_t acc = first ? 0u : 1u;
+#pragma unroll 4
         for (int k0 = 0; k0 < Kp; k0 += 16) {
-          const uint32_t aoff = (uint32_t)k0 * 16u;
-          const uint32_t boff = (uint32_t)(12 + shift + k0) * 16u;
-          // MN-major: lbo = stride between 8-position K groups (128 B), sbo = stride between 8-channel groups
-          const uint64_t ad = tc::smem_desc(d_hi_s + aoff, 128u, (uint32_t)Kp * 16u);
-          const uint64_t bh = tc::smem_desc(x_hi_s + boff, 128u, (uint32_t)Rx * 16u);
-          const uint64_t bl = tc::smem_desc(x_lo_s + boff, 128u, (uint32_t)Rx * 16u);
-          tc::umma_bf16(d, ad, bl, idesc, acc);
-          tc::umma_bf16(d, ad, bh, idesc, 1u);
+          const uint64_t ad = tc::desc_make(ad_lo + (uint32_t)k0, ad_hi);
+          const uint32_t boff = (uint32_t)(12 + shift + k0);
+          tc::umma_bf16(d, ad, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
+          tc::umma_bf16(d, ad, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
           acc = 1u;
         }
       }

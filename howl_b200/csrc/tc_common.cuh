@@ -72,6 +72,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- UMMA descriptors -------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_NONE.  lbo / sbo in bytes (multiples of 16).
 //   K-major : sbo = stride between 8-row groups (M/N), lbo = stride between the two 16-byte K chunks of one MMA
@@ -84,6 +96,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
   return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
+// The same descriptor as (lo, hi) words: only the start-address field (lo bits 0..13, in 16-byte units) changes between
+// MMAs of one operand, so the issuing thread keeps `hi` and a base `lo` and adds row offsets.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFF) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc_make(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 // instruction descriptor for kind::f16, bf16 x bf16 -> f32, M x N, operand majorness (0 = K, 1 = MN)
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
@@ -109,11 +127,10 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);          // one packed F2FP
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - __low2float(hh), v[2 * i + 1] - __high2float(hh));
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
