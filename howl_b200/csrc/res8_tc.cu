@@ -141,7 +141,7 @@ struct TcConvArgs {
 };
 
 template <bool RELU, int STATS>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvArgs a) {
+__global__ void __maxnreg__(224) conv3x3_tc_kernel(const TcConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const ConvParams& p = a.p;
   const int H = p.H, U = a.g.U, Pu = a.g.Pu, tiles = a.g.tiles, R = a.g.R, HW = H * R8_W;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvA
         for (int t = 0; t < tiles; ++t) {
           const uint32_t d = tmem + (uint32_t)(t * TC_N);
           const uint32_t rowb = (uint32_t)(TC_Q0 + 128 * t);
-#pragma unroll
+#pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
 #pragma unroll
@@ -273,15 +273,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvA
         const bool valid = (u < U) && (b < p.B) && (y >= 0) && (y < H) && (x >= 0) && (x < R8_W);
         const int64_t base = valid ? b * (int64_t)R8_C * HW + y * R8_W + x : 0;
         const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(t * TC_N + 24 * half);
-        float rr[24], aa[24];
+        // the one extra operand of this mode (residual in the forward, aux in the data gradient) is fetched while the
+        // tile is still in the tensor pipe
+        const float* extra = (STATS == 2) ? p.aux : p.res;
+        float pre[24];
 #pragma unroll
-        for (int j = 0; j < 24; ++j) {       // residual / aux operands are fetched while the tile is still in flight
+        for (int j = 0; j < 24; ++j) {
           const int c = 24 * half + j;
-          rr[j] = aa[j] = 0.f;
-          if (c < R8_C && valid) {
-            if (p.res) rr[j] = __ldg(p.res + base + (int64_t)c * HW);
-            if (STATS == 2) aa[j] = __ldg(p.aux + base + (int64_t)c * HW);
-          }
+          pre[j] = (extra && c < R8_C && valid) ? __ldg(extra + base + (int64_t)c * HW) : 0.f;
         }
         tc::mbar_wait(&bar_tile[t], phase);
         tc::fence_after_sync();
@@ -296,14 +295,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(const TcConvA
               if (c < R8_C) {
                 float o = v[j];
                 if (RELU) o = fmaxf(o, 0.f);
-                o += rr[jj];
+                if (STATS != 2) o += pre[jj];
+                else if (p.res) o += __ldg(p.res + base + (int64_t)c * HW);
                 p.out[base + (int64_t)c * HW] = o;
                 if (STATS == 1) {
                   st1[jj] += o;
                   st2[jj] = fmaf(o, o, st2[jj]);
                 } else if (STATS == 2) {
                   st1[jj] += o;
-                  st2[jj] = fmaf(o, (aa[jj] - s_amean[c]) * s_arstd[c], st2[jj]);
+                  st2[jj] = fmaf(o, (pre[jj] - s_amean[c]) * s_arstd[c], st2[jj]);
                 }
               }
             }
