@@ -13,7 +13,8 @@
 #include "res8_common.cuh"
 #include "tc_common.cuh"
 
-#define TC_THREADS 288            // warps 0-7: staging transform + epilogue, warp 8: TMA + MMA issue
+#define TC_THREADS 288            // weight-gradient kernel: warps 0-7 staging transform + epilogue, warp 8 TMA + MMA issue
+#define TC_CONV_THREADS 256       // forward / data-gradient kernel: 8 worker warps, lane 0 of warp 0 also issues TMA + MMAs
 #define TC_WORKERS 256
 #define TC_PITCH 11
 #define TC_Q0 12                  // raster index of pixel (0, 0)
@@ -141,7 +142,7 @@ struct TcConvArgs {
 };
 
 template <bool RELU, int STATS>
-__global__ void __maxnreg__(224) conv3x3_tc_kernel(const TcConvArgs a) {
+__global__ void __launch_bounds__(TC_CONV_THREADS, 1) conv3x3_tc_kernel(const TcConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const ConvParams& p = a.p;
   const int H = p.H, U = a.g.U, Pu = a.g.Pu, tiles = a.g.tiles, R = a.g.R, HW = H * R8_W;
@@ -163,16 +164,14 @@ __global__ void __maxnreg__(224) conv3x3_tc_kernel(const TcConvArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t groups = (p.B + U - 1) / U;
 
-  if (warp == 8) {
-    tc::tmem_alloc<256>(&s_tmem);
-    if (lane == 0) {
-      tc::mbar_init(&bar_w, 1);
-      tc::mbar_init(&bar_stage, 1);
-      for (int t = 0; t < 5; ++t) tc::mbar_init(&bar_tile[t], 1);
-      tc::fence_barrier_init();
-    }
+  if (warp == 0) tc::tmem_alloc<256>(&s_tmem);
+  if (tid == 32) {
+    tc::mbar_init(&bar_w, 1);
+    tc::mbar_init(&bar_stage, 1);
+    for (int t = 0; t < 5; ++t) tc::mbar_init(&bar_tile[t], 1);
+    tc::fence_barrier_init();
   }
-  for (int i = tid; i < 12 * R; i += TC_THREADS) a_hi[i] = make_uint4(0, 0, 0, 0);   // a_hi and a_lo are contiguous
+  for (int i = tid; i < 12 * R; i += TC_CONV_THREADS) a_hi[i] = make_uint4(0, 0, 0, 0);   // a_hi and a_lo are contiguous
   if (tid < 48) {
     const bool c_ok = tid < R8_C;
     s_mean[tid] = (c_ok && p.in_mean) ? p.in_mean[tid] : 0.f;
@@ -205,7 +204,7 @@ __global__ void __maxnreg__(224) conv3x3_tc_kernel(const TcConvArgs a) {
       }
     }
   };
-  if (tid == 256) {
+  if (tid == 0) {
     tc::mbar_expect_tx(&bar_w, 2 * TC_WBYTES);
     tc::tma_bulk_g2s(w_hi, a.whi, TC_WBYTES, &bar_w);
     tc::tma_bulk_g2s(w_lo, a.wlo, TC_WBYTES, &bar_w);
@@ -222,19 +221,17 @@ __global__ void __maxnreg__(224) conv3x3_tc_kernel(const TcConvArgs a) {
   uint32_t phase = 0;
   for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
     // ---- raw planes have landed: transform to bf16 (hi, lo) operand rows
-    if (warp < 8) {
-      tc::mbar_wait(&bar_stage, phase);
-      for (int u = 0; u < U; ++u) {
-        const int64_t b = g * U + u;
-        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.in + b * (int64_t)R8_C * HW) & 15);
-        tc_transform(reinterpret_cast<const float*>(stage + (size_t)u * slot + mis), b < p.B, H, u * Pu, R, s_mean, s_rstd,
-                     a_hi, a_lo, tid);
-      }
-      tc::fence_proxy_async();
+    tc::mbar_wait(&bar_stage, phase);
+    for (int u = 0; u < U; ++u) {
+      const int64_t b = g * U + u;
+      const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p.in + b * (int64_t)R8_C * HW) & 15);
+      tc_transform(reinterpret_cast<const float*>(stage + (size_t)u * slot + mis), b < p.B, H, u * Pu, R, s_mean, s_rstd,
+                   a_hi, a_lo, tid);
     }
+    tc::fence_proxy_async();
     __syncthreads();            // operands complete, staging buffer free
-    if (warp == 8) {
-      if (lane == 0) {
+    {
+      if (tid == 0) {   // one thread feeds the tensor pipe (short loop: two integer adds per MMA), then joins its warp
         if (g + gridDim.x < groups) issue_stage(g + gridDim.x);   // prefetch the next group during the MMAs
         if (g == (int64_t)blockIdx.x) tc::mbar_wait(&bar_w, 0);
         tc::fence_after_sync();
@@ -261,7 +258,9 @@ __global__ void __maxnreg__(224) conv3x3_tc_kernel(const TcConvArgs a) {
           tc::umma_commit(&bar_tile[t]);      // tile t can be drained while later tiles are still in the tensor pipe
         }
       }
-    } else {
+      __syncwarp();
+    }
+    {
       // ---- epilogue out of TMEM: thread = one raster row; warp quad h (warps 4h..4h+3) owns channels 24h..24h+23 of
       //      every tile, so both quads start on tile 0 as soon as it commits and the work is balanced
       const int half = warp >> 2;
@@ -317,7 +316,7 @@ __global__ void __maxnreg__(224) conv3x3_tc_kernel(const TcConvArgs a) {
   }
   // ---- per-channel statistics: lanes -> warps -> one fp64 atomic per channel and CTA
   if (STATS) {
-    if (warp < 8) {
+    {
 #pragma unroll
       for (int j = 0; j < 24; ++j) {
         const float a1 = warp_sum(st1[j]), a2 = warp_sum(st2[j]);
@@ -336,7 +335,7 @@ __global__ void __maxnreg__(224) conv3x3_tc_kernel(const TcConvArgs a) {
     }
   }
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc<256>(tmem);
+  if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
 int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* whi, const __nv_bfloat16* wlo,
@@ -354,7 +353,7 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
   do {                                                                                                            \
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<RELU_, STATS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                         (int)smem));                                                              \
-    conv3x3_tc_kernel<RELU_, STATS_><<<grid, TC_THREADS, smem, st>>>(a);                                          \
+    conv3x3_tc_kernel<RELU_, STATS_><<<grid, TC_CONV_THREADS, smem, st>>>(a);                                         \
   } while (0)
   if (relu && stats == 1) TC_LAUNCH(true, 1);
   else if (relu && stats == 0) TC_LAUNCH(true, 0);
