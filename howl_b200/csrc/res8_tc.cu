@@ -231,8 +231,9 @@ __global__ void __launch_bounds__(TC_CONV_THREADS, 1) conv3x3_tc_kernel(const Tc
     tc::fence_proxy_async();
     __syncthreads();            // operands complete, staging buffer free
     {
-      if (tid == 0) {   // one thread feeds the tensor pipe (short loop: two integer adds per MMA), then joins its warp
-        if (g + gridDim.x < groups) issue_stage(g + gridDim.x);   // prefetch the next group during the MMAs
+      if (tid == 0 && g + gridDim.x < groups) issue_stage(g + gridDim.x);   // prefetch the next group during the MMAs
+      __syncwarp();
+      if (warp == 0) {   // warp 0 feeds the tensor pipe (converged; one lane elected per MMA), then joins the epilogue
         if (g == (int64_t)blockIdx.x) tc::mbar_wait(&bar_w, 0);
         tc::fence_after_sync();
         const uint32_t ah_lo = tc::desc_lo(a_hi_s, (uint32_t)R * 16u), al_lo = tc::desc_lo(a_lo_s, (uint32_t)R * 16u);
@@ -250,12 +251,12 @@ __global__ void __launch_bounds__(TC_CONV_THREADS, 1) conv3x3_tc_kernel(const Tc
               const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N);
               const uint64_t ah = tc::desc_make(ah_lo + aoff, d_hi128), al = tc::desc_make(al_lo + aoff, d_hi128);
               const uint64_t bh = tc::desc_make(bh_lo + boff, d_hi128), bl = tc::desc_make(bl_lo + boff, d_hi128);
-              tc::umma_bf16(d, al, bh, idesc, (tap | ks) ? 1u : 0u);
-              tc::umma_bf16(d, ah, bl, idesc, 1u);
-              tc::umma_bf16(d, ah, bh, idesc, 1u);
+              tc::umma_bf16_warp(d, al, bh, idesc, (tap | ks) ? 1u : 0u);
+              tc::umma_bf16_warp(d, ah, bl, idesc, 1u);
+              tc::umma_bf16_warp(d, ah, bh, idesc, 1u);
             }
           }
-          tc::umma_commit(&bar_tile[t]);      // tile t can be drained while later tiles are still in the tensor pipe
+          tc::umma_commit_warp(&bar_tile[t]);   // tile t can be drained while later tiles are still in the tensor pipe
         }
       }
       __syncwarp();
@@ -445,8 +446,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
       tc::fence_proxy_async();
     }
     __syncthreads();
-    if (tid == 256) {
-      if (b + gridDim.x < p.B) issue_stage(b + gridDim.x);
+    if (tid == 256 && b + gridDim.x < p.B) issue_stage(b + gridDim.x);
+    __syncwarp();
+    if (warp == 8) {
       tc::fence_after_sync();
       // MN-major: lbo = stride between 8-position K groups (128 B), sbo = stride between 8-channel groups
       const uint32_t ad_lo = tc::desc_lo(d_hi_s, 128u), ad_hi = tc::desc_hi((uint32_t)Kp * 16u);
@@ -460,12 +462,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
         for (int k0 = 0; k0 < Kp; k0 += 16) {
           const uint64_t ad = tc::desc_make(ad_lo + (uint32_t)k0, ad_hi);
           const uint32_t boff = (uint32_t)(12 + shift + k0);
-          tc::umma_bf16(d, ad, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
-          tc::umma_bf16(d, ad, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
+          tc::umma_bf16_warp(d, ad, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
+          tc::umma_bf16_warp(d, ad, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
           acc = 1u;
         }
       }
-      tc::umma_commit(&bar_mma);
+      tc::umma_commit_warp(&bar_mma);
     }
     first = 0;
     tc::mbar_wait(&bar_mma, phase);   // operands may be overwritten once the MMAs have drained
