@@ -255,10 +255,17 @@ def main_ours(args):
         conv_launches = 18   # 6 fwd + 6 dgrad + 6 wgrad launches of the 45->45 3x3 kernels per step
         conv_ms = sum(g["ms"] for g in groups if g["name"].startswith("conv3x3"))
         achieved_tf = B * CONV_LAYER_FLOP_PER_UTT * conv_launches / (conv_ms / 1e3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):   # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu capture
+            tj = json.load(open(tpath))
+            key = "conv3x3_wgrad_tc_kernel" if "wgrad" in dom["name"] else ("conv3x3_tc_kernel<false,2>" if "_tc" in dom["name"] else "conv3x3_kernel<true,1>")
+            traffic = tj.get(key)
+        engine = "tcgen05 bf16x3-split MMA, fp32 TMEM accumulate" if any("_tc" in g["name"] for g in groups) else "fp32 FFMA"
         roofline = {
-            "bound": "tensor", "kernel": "conv3x3 45->45 (fwd/dgrad/wgrad, fp32 FFMA path)", "achieved": achieved_tf,
+            "bound": "tensor", "kernel": f"conv3x3 45->45, 18 launches/step (6 fwd + 6 dgrad + 6 wgrad), {engine}", "achieved": achieved_tf,
             "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved_tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": None,
+            "frac": achieved_tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": traffic,
             "peak_source": peaks["source"] + " (dense bf16 cuBLAS, sustained)",
             "fp32_ffma_peak_tflops": FP32_PEAK_TFLOPS, "frac_of_fp32_ffma_peak": achieved_tf / FP32_PEAK_TFLOPS,
             "conv_ms_per_step": conv_ms, "dominant_launch": dom["name"], "dominant_launch_ms": dom["ms"],
