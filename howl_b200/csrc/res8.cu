@@ -131,50 +131,55 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
   }
 }
 
-// backward of conv0: dW0[oc][k] = sum relu'(pre) * G[oc][h][w] / 12 * patch; pre is recomputed with the same
-// FMA order as the forward.  Persistent; G = ga (+ gb).
-__global__ void __launch_bounds__(C0_THREADS) conv0_bwd_kernel(const float* __restrict__ feats,
-                                                                const float* __restrict__ w0,
-                                                                const float* __restrict__ ga,
-                                                                const float* __restrict__ gb, float* __restrict__ dw0,
-                                                                int64_t B, int F, int H) {
+// backward of conv0: dW0[oc][k] = sum_{b,pos} relu'(pre[oc,pos]) * G[oc, pos/pool] / 12 * x[pos + k]; pre is recomputed
+// with the same FMA order as the forward.  Persistent CTAs; thread = (pixel group pg, output channel oc): the nine
+// tap accumulators of its channel stay in registers across all pixels and utterances (no per-channel reductions in the
+// loop), the 5x6 input patch of a pooled pixel is a shared-memory broadcast, G = ga (+ gb) is staged per utterance.
+#define C0B_GROUPS 6
+#define C0B_THREADS (C0B_GROUPS * 48)
+__global__ void __launch_bounds__(C0B_THREADS) conv0_bwd_kernel(const float* __restrict__ feats,
+                                                                 const float* __restrict__ w0,
+                                                                 const float* __restrict__ ga,
+                                                                 const float* __restrict__ gb, float* __restrict__ dw0,
+                                                                 int64_t B, int F, int H) {
   extern __shared__ __align__(16) float smem[];
-  const int rows = 3 * H + 2;
-  float* s_x = smem;
-  float* s_w = smem + rows * C0_STRIDE;
-  float* s_acc = s_w + R8_C * 9;
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i < R8_C * 9; i += C0_THREADS) {
-    s_w[i] = __ldg(w0 + i);
-    s_acc[i] = 0.f;
+  const int rows = 3 * H + 2, HW = H * R8_W;
+  float* s_x = smem;                          // [(3H+2)][44]  feature tile with halo
+  float* s_g = s_x + rows * C0_STRIDE;        // [45][HW + 1]  G / 12 for this utterance (padded row: bank spread)
+  float* s_acc = s_g + R8_C * (HW + 1);       // [45][9]
+  const int tid = threadIdx.x;
+  const int pg = tid / 48, oc = tid - pg * 48;
+  const bool active = oc < R8_C;
+  float wk[9], acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    wk[k] = active ? __ldg(w0 + oc * 9 + k) : 0.f;
+    acc[k] = 0.f;
   }
-  const int HW = H * R8_W;
+  for (int i = tid; i < R8_C * 9; i += C0B_THREADS) s_acc[i] = 0.f;
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    c0_stage_tile(s_x, feats + b * (int64_t)F * R8_MELS, F, rows, tid, C0_THREADS);
+    c0_stage_tile(s_x, feats + b * (int64_t)F * R8_MELS, F, rows, tid, C0B_THREADS);
+    for (int i = tid; i < R8_C * HW; i += C0B_THREADS) {
+      const int64_t idx = b * (int64_t)R8_C * HW + i;
+      float gv = ga[idx];
+      if (gb) gv += gb[idx];
+      const int c = i / HW;
+      s_g[c * (HW + 1) + (i - c * HW)] = __fdiv_rn(gv, 12.f);
+    }
     __syncthreads();
-    for (int pp0 = 0; pp0 < HW; pp0 += C0_THREADS) {
-      const int pp = pp0 + tid;
-      const bool active = pp < HW;
-      const int h = active ? pp / R8_W : 0, w = active ? pp - (pp / R8_W) * R8_W : 0;
-      float patch[5][6];
+    if (active) {
+      for (int pp = pg; pp < HW; pp += C0B_GROUPS) {
+        const int h = pp / R8_W, w = pp - h * R8_W;
+        const float gv = s_g[oc * (HW + 1) + pp];
+        float patch[5][6];
 #pragma unroll
-      for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) patch[r][c] = s_x[(3 * h + r) * C0_STRIDE + 4 * w + c];
-      for (int oc = 0; oc < R8_C; ++oc) {
-        float wk[9], acc[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          wk[k] = s_w[oc * 9 + k];
-          acc[k] = 0.f;
-        }
-        float gv = 0.f;
-        if (active) {
-          const int64_t idx = (b * R8_C + oc) * (int64_t)HW + pp;
-          gv = ga[idx];
-          if (gb) gv += gb[idx];
-          gv = __fdiv_rn(gv, 12.f);
+        for (int r = 0; r < 5; ++r) {
+          const float* rowp = s_x + (3 * h + r) * C0_STRIDE + 4 * w;       // 16-byte aligned
+          const float4 a = *reinterpret_cast<const float4*>(rowp);
+          const float2 c2 = *reinterpret_cast<const float2*>(rowp + 4);
+          patch[r][0] = a.x; patch[r][1] = a.y; patch[r][2] = a.z; patch[r][3] = a.w;
+          patch[r][4] = c2.x; patch[r][5] = c2.y;
         }
 #pragma unroll
         for (int py = 0; py < 3; ++py)
@@ -191,16 +196,16 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_bwd_kernel(const float* __re
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(gm, patch[py + ky][px + kx], acc[ky * 3 + kx]);
           }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const float v = warp_sum(acc[k]);
-          if (lane == 0) atomicAdd(&s_acc[oc * 9 + k], v);
-        }
       }
     }
   }
   __syncthreads();
-  for (int i = tid; i < R8_C * 9; i += C0_THREADS) atomicAdd(&dw0[i], s_acc[i]);
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) atomicAdd(&s_acc[oc * 9 + k], acc[k]);
+  }
+  __syncthreads();
+  for (int i = tid; i < R8_C * 9; i += C0B_THREADS) atomicAdd(&dw0[i], s_acc[i]);
 }
 
 // =============================================================================================
@@ -928,10 +933,11 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     }
   }
   {
-    const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + 2 * R8_C * 9);
+    const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + R8_C * (HW + 1) + R8_C * 9);
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const int g0 = (int)(B < 2LL * ctx->sm_count ? B : 2LL * ctx->sm_count);
-    conv0_bwd_kernel<<<g0, C0_THREADS, sm, st>>>(feats, w0, ws.g, ws.gu[1], g_w0, B, frames, H);
+    const int per_sm = sm <= 72 * 1024 ? 3 : (sm <= 110 * 1024 ? 2 : 1);
+    const int g0 = (int)(B < (int64_t)per_sm * ctx->sm_count ? B : (int64_t)per_sm * ctx->sm_count);
+    conv0_bwd_kernel<<<g0, C0B_THREADS, sm, st>>>(feats, w0, ws.g, ws.gu[1], g_w0, B, frames, H);
     HOWL_LAUNCHED(ctx, "conv0_bwd");
   }
   return HOWL_OK;
