@@ -62,7 +62,10 @@ static R8Ws r8_carve(void* base, int64_t B, int H, int L) {
   w.a0 = (float*)take(n);
   for (int i = 0; i < R8_LAYERS; ++i) w.u[i] = (float*)take(n);
   w.g = (float*)take(n);
-  w.dc = (float*)take(n);
+  {   // dc doubles as the operand-format gradient of the tensor-core engine (r8tc_dcop_bytes per utterance)
+    const size_t nop = (size_t)B * r8tc_dcop_bytes(H);
+    w.dc = (float*)take(n > nop ? n : nop);
+  }
   w.gu[0] = (float*)take(n);
   w.gu[1] = (float*)take(n);
   w.bytes = off;
@@ -847,6 +850,8 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   if (use_tc) {
     rc = r8tc_weight_prep(ctx, st, wl, ws.wprep, 1);
     if (rc) return rc;
+    // halo rows of the operand-format gradient stay zero for all six layers
+    HOWL_CUDA(ctx, cudaMemsetAsync(ws.dc, 0, (size_t)B * r8tc_dcop_bytes(frames / 3), st));
   } else {
     transpose_weights_kernel<<<(R8_LAYERS * R8_KW + 255) / 256, 256, 0, st>>>(wl, ws.wT);
     HOWL_LAUNCHED(ctx, "transpose_weights");
@@ -887,12 +892,23 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     a.n2 = n2;
     a.HW = HW;
     a.count = count;
-    bn_bwd_apply_kernel<<<(unsigned)ablocks, 256, 0, st>>>(a);
-    HOWL_LAUNCHED(ctx, "bn_bwd_apply");
+    if (use_tc) {
+      ApplyOpParams ao;
+      ao.g = a.g; ao.g_bcast = a.g_bcast; ao.u = a.u; ao.mean_rstd = a.mean_rstd; ao.stats = a.stats;
+      ao.gu_in = a.gu_in; ao.mask_prev = a.mask_prev; ao.gu_out = a.gu_out;
+      ao.dc_op = reinterpret_cast<__nv_bfloat16*>(ws.dc);
+      ao.B = B; ao.H = H; ao.count = count;
+      rc = r8tc_apply(ctx, st, ao);
+      if (rc) return rc;
+    } else {
+      bn_bwd_apply_kernel<<<(unsigned)ablocks, 256, 0, st>>>(a);
+      HOWL_LAUNCHED(ctx, "bn_bwd_apply");
+    }
 
     WgradParams wg;
     memset(&wg, 0, sizeof(wg));
     wg.dc = ws.dc;
+    wg.dc_op = reinterpret_cast<const __nv_bfloat16*>(ws.dc);
     wg.x = (i == 1) ? ws.a0 : ws.u[i - 2];
     if (i > 1) {
       wg.x_mean = ws.mean_rstd + (i - 2) * 2 * R8_C;
@@ -924,7 +940,7 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     }
     if (use_tc) {
       const __nv_bfloat16* whi = ws.wprep + ((size_t)((i - 1) * 2 + 1) * 2) * R8TC_WBLOCK;
-      rc = r8tc_conv(ctx, st, p, whi, whi + R8TC_WBLOCK, false, i > 1 ? 2 : 0);
+      rc = r8tc_dgrad(ctx, st, p, reinterpret_cast<const __nv_bfloat16*>(ws.dc), whi, whi + R8TC_WBLOCK, i > 1 ? 2 : 0);
       if (rc) return rc;
     } else {
       if (i > 1) conv3x3_kernel<false, 2><<<grid, CV_THREADS, csm, st>>>(p);

@@ -30,7 +30,8 @@ struct ConvParams {
 };
 
 struct WgradParams {
-  const float* dc;       // [B,45,H,10]  gradient at the conv output (ReLU mask applied)
+  const float* dc;       // [B,45,H,10]  gradient at the conv output (ReLU mask applied); fp32 engine
+  const __nv_bfloat16* dc_op;   // tensor-core engine: the same gradient in operand format (see r8tc_dcop_bytes)
   const float* x;        // [B,45,H,10]  conv input before normalisation
   const float* x_mean;   // or null
   const float* x_rstd;
@@ -49,3 +50,28 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
               bool relu, int stats);
 int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const WgradParams& p);
 bool r8tc_supported(int H);
+
+// Operand-format conv-output gradient ("dc_op"), written by the BatchNorm-backward kernel for the tensor-core engine and
+// consumed by TMA straight into the UMMA operand tiles of the data-gradient and weight-gradient kernels:
+//   per utterance [part: hi, lo][chunk of 8 channels: 6][raster row q: Kp][8 x bf16],  q = (y + 1) * 11 + (x + 1),
+//   Kp = round_up((H + 2) * 11, 16); halo rows are zero.
+size_t r8tc_dcop_bytes(int H);          // bytes per utterance
+int r8tc_dcop_rows(int H);              // Kp
+
+struct ApplyOpParams {
+  const float* g;          // dgrad output [B,45,HW], or null when g_bcast is used
+  const float* g_bcast;    // [B,45]: g = g_bcast / HW (layer 6)
+  const float* u;
+  const float* mean_rstd;  // [2][45] of this layer
+  const double* stats;     // [2][45] sum(g), sum(g xhat)
+  const float* gu_in;
+  const float* mask_prev;
+  float* gu_out;
+  __nv_bfloat16* dc_op;
+  int64_t B;
+  int H;
+  double count;
+};
+int r8tc_apply(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p);
+int r8tc_dgrad(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* dc_op, const __nv_bfloat16* whi,
+               const __nv_bfloat16* wlo, int stats);

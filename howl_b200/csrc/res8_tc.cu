@@ -65,7 +65,7 @@ static size_t tc_wgrad_smem(int H, int* Kp_out, int* Rx_out) {
   // the A operand addresses 16 groups of 8 rows (M = 128 = dC_hi | dC_lo | padding): groups 12..15 must stay inside
   const size_t operand = (12 * (size_t)Kp + 12 * (size_t)Rx) * 16;
   const size_t need_a = ((size_t)16 * Kp) * 16;
-  return (operand > need_a ? operand : need_a) + 2 * tc_slot_bytes(H) + 128 * 4;
+  return (operand > need_a ? operand : need_a) + tc_slot_bytes(H) + 128 * 4;
 }
 
 bool r8tc_supported(int H) { return tc_geom(H).U > 0 && tc_wgrad_smem(H, nullptr, nullptr) <= TC_SMEM_LIMIT; }
@@ -388,19 +388,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   uint4* x_hi = d_lo + 6 * Kp;                      // [6][Rx]   X,  rows = q + 12
   uint4* x_lo = x_hi + 6 * Rx;
   const size_t operand = (12 * (size_t)Kp + 12 * (size_t)Rx) * 16, need_a = (size_t)16 * Kp * 16;
-  const size_t slot = tc_slot_bytes(H);
-  unsigned char* stage_d = smem + (operand > need_a ? operand : need_a);
-  unsigned char* stage_x = stage_d + slot;
-  float* s_mean = reinterpret_cast<float*>(stage_x + slot);
+  unsigned char* stage_x = smem + (operand > need_a ? operand : need_a);
+  float* s_mean = reinterpret_cast<float*>(stage_x + tc_slot_bytes(H));
   float* s_rstd = s_mean + 48;
-  __shared__ __align__(8) uint64_t bar_stage, bar_mma;
+  __shared__ __align__(8) uint64_t bar_stage, bar_d, bar_mma;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t dop_bytes = (uint32_t)(12 * Kp * 16);
 
   if (warp == 8) {
     tc::tmem_alloc<512>(&s_tmem);
     if (lane == 0) {
       tc::mbar_init(&bar_stage, 1);
+      tc::mbar_init(&bar_d, 1);
       tc::mbar_init(&bar_mma, 1);
       tc::fence_barrier_init();
     }
@@ -411,37 +411,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
     s_mean[tid] = (c_ok && p.x_mean) ? p.x_mean[tid] : 0.f;
     s_rstd[tid] = (c_ok && p.x_rstd) ? p.x_rstd[tid] : 1.f;
   }
+  tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
+  // X: raw fp32 planes -> staging slot (prefetched one utterance ahead); dC: operand-format image straight into d_hi|d_lo
   auto issue_stage = [&](int64_t b) {
-    const unsigned char* sd = reinterpret_cast<const unsigned char*>(p.dc + b * (int64_t)R8_C * HW);
     const unsigned char* sx = reinterpret_cast<const unsigned char*>(p.x + b * (int64_t)R8_C * HW);
-    const uint32_t md = (uint32_t)(reinterpret_cast<uintptr_t>(sd) & 15), mx = (uint32_t)(reinterpret_cast<uintptr_t>(sx) & 15);
-    const uint32_t bd = (md + plane_bytes + 15u) & ~15u, bx = (mx + plane_bytes + 15u) & ~15u;
-    tc::mbar_expect_tx(&bar_stage, bd + bx);
-    tc::tma_bulk_g2s(stage_d, sd - md, bd, &bar_stage);
+    const uint32_t mx = (uint32_t)(reinterpret_cast<uintptr_t>(sx) & 15);
+    const uint32_t bx = (mx + plane_bytes + 15u) & ~15u;
+    tc::mbar_expect_tx(&bar_stage, bx);
     tc::tma_bulk_g2s(stage_x, sx - mx, bx, &bar_stage);
   };
-  if (tid == 256 && (int64_t)blockIdx.x < p.B) issue_stage(blockIdx.x);
+  auto issue_d = [&](int64_t b) {
+    tc::mbar_expect_tx(&bar_d, dop_bytes);
+    tc::tma_bulk_g2s(d_hi, reinterpret_cast<const unsigned char*>(p.dc_op) + (size_t)b * dop_bytes, dop_bytes, &bar_d);
+  };
+  if (tid == 256 && (int64_t)blockIdx.x < p.B) {
+    issue_stage(blockIdx.x);
+    issue_d(blockIdx.x);
+  }
   const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 1, 1);   // both operands MN-major (K = raster positions)
   const uint32_t d_hi_s = tc::smem_u32(d_hi);
   const uint32_t x_hi_s = tc::smem_u32(x_hi), x_lo_s = tc::smem_u32(x_lo);
-  // identity "BN" for the dC planes
-  __shared__ float s_id[96];
-  if (tid < 48) {
-    s_id[tid] = 0.f;
-    s_id[48 + tid] = 1.f;
-  }
-  __syncthreads();
   uint32_t phase = 0, first = 1;
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     if (warp < 8) {
       tc::mbar_wait(&bar_stage, phase);
-      const uint32_t md = (uint32_t)(reinterpret_cast<uintptr_t>(p.dc + b * (int64_t)R8_C * HW) & 15);
       const uint32_t mx = (uint32_t)(reinterpret_cast<uintptr_t>(p.x + b * (int64_t)R8_C * HW) & 15);
-      tc_transform(reinterpret_cast<const float*>(stage_d + md), true, H, 0, Kp, s_id, s_id + 48, d_hi, d_lo, tid);   // dC: rows q
       tc_transform(reinterpret_cast<const float*>(stage_x + mx), true, H, 12, Rx, s_mean, s_rstd, x_hi, x_lo, tid);  // X: rows q + 12
       tc::fence_proxy_async();
     }
@@ -449,6 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
     if (tid == 256 && b + gridDim.x < p.B) issue_stage(b + gridDim.x);
     __syncwarp();
     if (warp == 8) {
+      tc::mbar_wait(&bar_d, phase);       // dC operand image of this utterance has landed
       tc::fence_after_sync();
       // MN-major: lbo = stride between 8-position K groups (128 B), sbo = stride between 8-channel groups
       const uint32_t ad_lo = tc::desc_lo(d_hi_s, 128u), ad_hi = tc::desc_hi((uint32_t)Kp * 16u);
@@ -473,6 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
     tc::mbar_wait(&bar_mma, phase);   // operands may be overwritten once the MMAs have drained
     phase ^= 1u;
     tc::fence_after_sync();
+    if (tid == 256 && b + gridDim.x < p.B) issue_d(b + gridDim.x);
   }
   // ---- epilogue: TMEM lane r: r < 48 -> dC_hi row of channel r, 48 <= r < 96 -> dC_lo row of channel r - 48
   if (first == 0 && warp < 8) {
@@ -618,5 +618,274 @@ extern "C" int howl_b200_selftest_umma(howl_ctx_t* ctx, void* stream, const floa
   HOWL_CUDA(ctx, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, mn_major, variant);
   HOWL_LAUNCHED(ctx, "umma_selftest");
+  return HOWL_OK;
+}
+
+// =============================================================================================
+// Tensor-core backward, second generation: the conv-output gradient lives in HBM in OPERAND FORMAT (dc_op), so the
+// data-gradient kernel has no transform phase: TMA lands the next utterance's operand tile in the second shared-memory
+// buffer while the tensor pipe works on the current one, accumulators are double-buffered in TMEM, and the eight worker
+// warps do nothing but drain TMEM (store g, reduce the BatchNorm-backward statistics).
+// =============================================================================================
+__host__ __device__ static inline int r8tc_dcop_rows_dev(int H) { return ((H + 2) * TC_PITCH + 15) & ~15; }
+int r8tc_dcop_rows(int H) { return r8tc_dcop_rows_dev(H); }
+size_t r8tc_dcop_bytes(int H) { return (size_t)12 * r8tc_dcop_rows(H) * 16; }
+
+// BatchNorm backward + residual fan-in + ReLU mask (same arithmetic as bn_bwd_apply_kernel in res8.cu), one thread =
+// 8 channels of one pixel; emits the (hi, lo) bf16 operand rows directly.  grid.y = channel chunk.
+__global__ void __launch_bounds__(256) bn_bwd_apply_op_kernel(const ApplyOpParams p) {
+  const int HW = p.H * R8_W, Kp = r8tc_dcop_rows_dev(p.H), chunk = blockIdx.y;
+  float mu[8], rs[8], m1[8], m2[8];
+  bool ok[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = chunk * 8 + j;
+    ok[j] = c < R8_C;
+    const int cc = ok[j] ? c : 0;
+    mu[j] = __ldg(p.mean_rstd + cc);
+    rs[j] = __ldg(p.mean_rstd + R8_C + cc);
+    m1[j] = (float)(p.stats[cc] / p.count);
+    m2[j] = (float)(p.stats[R8_C + cc] / p.count);
+  }
+  const float inv_hw = 1.f / (float)HW;
+  const int64_t items = p.B * HW;
+  uint4* out = reinterpret_cast<uint4*>(p.dc_op);
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = it / HW;
+    const int pp = (int)(it - b * HW);
+    const int y = pp / R8_W, x = pp - y * R8_W;
+    float d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = chunk * 8 + j;
+      d[j] = 0.f;
+      if (ok[j]) {
+        const int64_t idx = (b * R8_C + c) * (int64_t)HW + pp;
+        const float g = p.g ? p.g[idx] : __ldg(p.g_bcast + b * R8_C + c) * inv_hw;
+        const float u = p.u[idx];
+        float G = rs[j] * (g - m1[j] - (u - mu[j]) * rs[j] * m2[j]);
+        if (p.gu_in) G += p.gu_in[idx];
+        if (p.gu_out) p.gu_out[idx] = G;
+        const float prev = p.mask_prev ? p.mask_prev[idx] : 0.f;
+        d[j] = (u > prev) ? G : 0.f;
+      }
+    }
+    uint4 hi, lo;
+    tc::split8(d, hi, lo);
+    const int64_t base = b * 12 * (int64_t)Kp + (int64_t)chunk * Kp + (y + 1) * TC_PITCH + (x + 1);
+    out[base] = hi;
+    out[base + 6 * (int64_t)Kp] = lo;
+  }
+}
+
+int r8tc_apply(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p) {
+  const int64_t items = p.B * p.H * R8_W;
+  int64_t bx = howl_ceil_div(items, 256);
+  const int64_t cap = (int64_t)ctx->sm_count * 4;
+  if (bx > cap) bx = cap;
+  bn_bwd_apply_op_kernel<<<dim3((unsigned)bx, 6, 1), 256, 0, st>>>(p);
+  HOWL_LAUNCHED(ctx, "bn_bwd_apply_op");
+  return HOWL_OK;
+}
+
+#define TCD_THREADS 288          // warps 0-7: epilogue workers, warp 8: TMA + MMA issue
+struct TcDgradArgs {
+  ConvParams p;                  // p.in unused (operands come from dc_op); out / stats / aux as in the fp32 kernel
+  const __nv_bfloat16* dc_op;
+  const __nv_bfloat16* whi;
+  const __nv_bfloat16* wlo;
+  int Kp, tiles;
+};
+
+template <int STATS>
+__global__ void __launch_bounds__(TCD_THREADS, 1) conv3x3_dgrad_tc_kernel(const TcDgradArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const ConvParams& p = a.p;
+  const int H = p.H, HW = H * R8_W, Kp = a.Kp, tiles = a.tiles;
+  const uint32_t op_bytes = (uint32_t)(12 * Kp * 16);
+  uint4* w_hi = reinterpret_cast<uint4*>(smem);
+  uint4* w_lo = reinterpret_cast<uint4*>(smem + TC_WBYTES);
+  unsigned char* a_buf = smem + 2 * TC_WBYTES;                          // 2 x [hi 6][lo 6][Kp] + tail pad
+  float* s_f = reinterpret_cast<float*>(a_buf + 2 * (size_t)op_bytes + 128 * 16);
+  float* s_amean = s_f;
+  float* s_arstd = s_f + 48;
+  float* s_red = s_f + 96;       // [8 warps][2][24]
+  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_tile[2][3], bar_free[2];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (warp == 8) {
+    tc::tmem_alloc<512>(&s_tmem);
+    if (lane == 0) {
+      tc::mbar_init(&bar_w, 1);
+      for (int i = 0; i < 2; ++i) {
+        tc::mbar_init(&bar_a[i], 1);
+        tc::mbar_init(&bar_free[i], 8);
+        for (int t = 0; t < 3; ++t) tc::mbar_init(&bar_tile[i][t], 1);
+      }
+      tc::fence_barrier_init();
+    }
+  }
+  // tail pad (rows a tile may read past the second buffer) must be finite
+  for (int i = tid; i < 128; i += TCD_THREADS) reinterpret_cast<uint4*>(a_buf + 2 * (size_t)op_bytes)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 48) {
+    const bool c_ok = tid < R8_C;
+    s_amean[tid] = (c_ok && STATS == 2) ? p.aux_mean[tid] : 0.f;
+    s_arstd[tid] = (c_ok && STATS == 2) ? p.aux_rstd[tid] : 0.f;
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  const int64_t n_local = (p.B - blockIdx.x + gridDim.x - 1) / gridDim.x;   // utterances this CTA owns
+
+  if (warp == 8) {
+    // ================= producer / issuer warp (converged; one lane elected per instruction) =================
+    const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.dc_op);
+    auto load_op = [&](int64_t k) {     // utterance k of this CTA -> buffer k & 1
+      if (lane == 0) {
+        const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
+        tc::mbar_expect_tx(&bar_a[k & 1], op_bytes);
+        tc::tma_bulk_g2s(a_buf + (size_t)(k & 1) * op_bytes, src0 + (size_t)b * op_bytes, op_bytes, &bar_a[k & 1]);
+      }
+    };
+    if (lane == 0) {
+      tc::mbar_expect_tx(&bar_w, 2 * TC_WBYTES);
+      tc::tma_bulk_g2s(w_hi, a.whi, TC_WBYTES, &bar_w);
+      tc::tma_bulk_g2s(w_lo, a.wlo, TC_WBYTES, &bar_w);
+    }
+    if (n_local > 0) load_op(0);
+    if (n_local > 1) load_op(1);
+    __syncwarp();
+    tc::mbar_wait(&bar_w, 0);
+    const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 0, 0);
+    const uint32_t w_hi_s = tc::smem_u32(w_hi), w_lo_s = tc::smem_u32(w_lo);
+    const uint32_t bh_lo = tc::desc_lo(w_hi_s, TC_N * 16u), bl_lo = tc::desc_lo(w_lo_s, TC_N * 16u);
+    const uint32_t d_hi128 = tc::desc_hi(128u);
+    for (int64_t k = 0; k < n_local; ++k) {
+      const int buf = (int)(k & 1);
+      const uint32_t par = (uint32_t)((k >> 1) & 1);
+      tc::mbar_wait(&bar_a[buf], par);                       // operand tile landed
+      if (k >= 2) tc::mbar_wait(&bar_free[buf], par ^ 1u);   // epilogue of utterance k-2 has drained this TMEM half
+      tc::fence_after_sync();
+      const uint32_t a_hi_s = tc::smem_u32(a_buf + (size_t)buf * op_bytes), a_lo_s = a_hi_s + (uint32_t)(6 * Kp * 16);
+      const uint32_t ah_lo = tc::desc_lo(a_hi_s, (uint32_t)Kp * 16u), al_lo = tc::desc_lo(a_lo_s, (uint32_t)Kp * 16u);
+      for (int t = 0; t < tiles; ++t) {
+        const uint32_t d = tmem + (uint32_t)(buf * 256 + t * TC_N);
+        const uint32_t rowb = (uint32_t)(TC_Q0 + 128 * t);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks) {
+            const uint32_t aoff = (uint32_t)(2 * ks) * (uint32_t)Kp + rowb + (uint32_t)shift;
+            const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N);
+            const uint64_t ah = tc::desc_make(ah_lo + aoff, d_hi128), al = tc::desc_make(al_lo + aoff, d_hi128);
+            const uint64_t bh = tc::desc_make(bh_lo + boff, d_hi128), bl = tc::desc_make(bl_lo + boff, d_hi128);
+            tc::umma_bf16_warp(d, al, bh, idesc, (tap | ks) ? 1u : 0u);
+            tc::umma_bf16_warp(d, ah, bl, idesc, 1u);
+            tc::umma_bf16_warp(d, ah, bh, idesc, 1u);
+          }
+        }
+        tc::umma_commit_warp(&bar_tile[buf][t]);
+      }
+      // refill the other buffer with utterance k + 1 once the MMAs of utterance k - 1 have released it
+      if (k >= 1 && k + 1 < n_local) {
+        tc::mbar_wait(&bar_tile[buf ^ 1][tiles - 1], (uint32_t)(((k - 1) >> 1) & 1));
+        load_op(k + 1);
+      }
+    }
+  } else {
+    // ================= epilogue workers: thread = one raster row, warp quad = 24 channels =================
+    const int half = warp >> 2;
+    float st1[24], st2[24];
+#pragma unroll
+    for (int c = 0; c < 24; ++c) st1[c] = st2[c] = 0.f;
+    for (int64_t k = 0; k < n_local; ++k) {
+      const int buf = (int)(k & 1);
+      const uint32_t par = (uint32_t)((k >> 1) & 1);
+      const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
+      for (int t = 0; t < tiles; ++t) {
+        const int q = TC_Q0 + 128 * t + 32 * (warp & 3) + lane;
+        const int y = q / TC_PITCH - 1, x = q % TC_PITCH - 1;
+        const bool valid = (y >= 0) && (y < H) && (x >= 0) && (x < R8_W);
+        const int64_t base = valid ? b * (int64_t)R8_C * HW + y * R8_W + x : 0;
+        const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * 256 + t * TC_N + 24 * half);
+        float pre[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+          const int c = 24 * half + j;
+          pre[j] = (STATS == 2 && c < R8_C && valid) ? __ldg(p.aux + base + (int64_t)c * HW) : 0.f;
+        }
+        tc::mbar_wait(&bar_tile[buf][t], par);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          float v[8];
+          tc::tmem_ld8(taddr + 8 * cb, v);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int jj = cb * 8 + j, c = 24 * half + jj;
+              if (c < R8_C) {
+                const float o = v[j];
+                p.out[base + (int64_t)c * HW] = o;
+                if (STATS == 2) {
+                  st1[jj] += o;
+                  st2[jj] = fmaf(o, (pre[jj] - s_amean[c]) * s_arstd[c], st2[jj]);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_free[buf]);
+    }
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < 24; ++j) {
+        const float a1 = warp_sum(st1[j]), a2 = warp_sum(st2[j]);
+        if (lane == 0) {
+          s_red[(warp * 2 + 0) * 24 + j] = a1;
+          s_red[(warp * 2 + 1) * 24 + j] = a2;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (STATS && tid < 2 * R8_C) {
+    const int which = tid / R8_C, c = tid - which * R8_C, half = c / 24, j = c - 24 * half;
+    double s = 0.0;
+    for (int w = 4 * half; w < 4 * half + 4; ++w) s += (double)s_red[(w * 2 + which) * 24 + j];
+    atomicAdd(&p.stats[tid], s);
+  }
+  if (warp == 8) tc::tmem_dealloc<512>(tmem);
+}
+
+int r8tc_dgrad(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* dc_op, const __nv_bfloat16* whi,
+               const __nv_bfloat16* wlo, int stats) {
+  TcDgradArgs a;
+  a.p = p;
+  a.dc_op = dc_op;
+  a.whi = whi;
+  a.wlo = wlo;
+  a.Kp = r8tc_dcop_rows(p.H);
+  a.tiles = (TC_PITCH * p.H - 1 + 127) / 128;
+  HOWL_REQUIRE(ctx, a.tiles <= 3, HOWL_E_UNSUPPORTED, "tensor-core dgrad: H=%d needs more than 3 tiles", p.H);
+  const size_t smem = 2 * (size_t)TC_WBYTES + 2 * r8tc_dcop_bytes(p.H) + 128 * 16 + (96 + 8 * 2 * 24) * 4;
+  HOWL_REQUIRE(ctx, smem <= TC_SMEM_LIMIT, HOWL_E_UNSUPPORTED, "tensor-core dgrad: H=%d does not fit", p.H);
+  const int grid = (int)(p.B < ctx->sm_count ? p.B : ctx->sm_count);
+  if (stats == 2) {
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_dgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_dgrad_tc_kernel<2><<<grid, TCD_THREADS, smem, st>>>(a);
+  } else {
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_dgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_dgrad_tc_kernel<0><<<grid, TCD_THREADS, smem, st>>>(a);
+  }
+  HOWL_LAUNCHED(ctx, "conv3x3_dgrad_tc");
   return HOWL_OK;
 }

@@ -18,7 +18,8 @@ def carve(B, H, L):
     n = 4 * B * 45 * H * 10
     take("a0", n)
     for i in range(1, 7): take(f"u{i}", n)
-    take("g", n); take("dc", n); take("gu0", n); take("gu1", n)
+    Kp = ((H + 2) * 11 + 15) // 16 * 16
+    take("g", n); take("dc", max(n, B * 12 * Kp * 16)); take("gu0", n); take("gu1", n)
     return out, off
 
 def main():
