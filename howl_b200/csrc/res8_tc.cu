@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(TC_CONV_THREADS, 1) conv3x3_tc_kernel(const Tc
     {
       if (tid == 0 && g + gridDim.x < groups) issue_stage(g + gridDim.x);   // prefetch the next group during the MMAs
       __syncwarp();
-      if (warp == 0) {   // warp 0 feeds the tensor pipe (converged; one lane elected per MMA), then joins the epilogue
+      if (warp == 0 && tc::elect_one()) {   // one elected lane of warp 0 feeds the tensor pipe, then the warp joins the epilogue
         if (g == (int64_t)blockIdx.x) tc::mbar_wait(&bar_w, 0);
         tc::fence_after_sync();
         const uint32_t ah_lo = tc::desc_lo(a_hi_s, (uint32_t)R * 16u), al_lo = tc::desc_lo(a_lo_s, (uint32_t)R * 16u);
@@ -251,12 +251,12 @@ __global__ void __launch_bounds__(TC_CONV_THREADS, 1) conv3x3_tc_kernel(const Tc
               const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N);
               const uint64_t ah = tc::desc_make(ah_lo + aoff, d_hi128), al = tc::desc_make(al_lo + aoff, d_hi128);
               const uint64_t bh = tc::desc_make(bh_lo + boff, d_hi128), bl = tc::desc_make(bl_lo + boff, d_hi128);
-              tc::umma_bf16_warp(d, al, bh, idesc, (tap | ks) ? 1u : 0u);
-              tc::umma_bf16_warp(d, ah, bl, idesc, 1u);
-              tc::umma_bf16_warp(d, ah, bh, idesc, 1u);
+              tc::umma_bf16(d, al, bh, idesc, (tap | ks) ? 1u : 0u);
+              tc::umma_bf16(d, ah, bl, idesc, 1u);
+              tc::umma_bf16(d, ah, bh, idesc, 1u);
             }
           }
-          tc::umma_commit_warp(&bar_tile[t]);   // tile t can be drained while later tiles are still in the tensor pipe
+          tc::umma_commit(&bar_tile[t]);   // tile t can be drained while later tiles are still in the tensor pipe
         }
       }
       __syncwarp();
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
     __syncthreads();
     if (tid == 256 && b + gridDim.x < p.B) issue_stage(b + gridDim.x);
     __syncwarp();
-    if (warp == 8) {
+    if (warp == 8 && tc::elect_one()) {
       tc::mbar_wait(&bar_d, phase);       // dC operand image of this utterance has landed
       tc::fence_after_sync();
       // MN-major: lbo = stride between 8-position K groups (128 B), sbo = stride between 8-channel groups
@@ -461,12 +461,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
         for (int k0 = 0; k0 < Kp; k0 += 16) {
           const uint64_t ad = tc::desc_make(ad_lo + (uint32_t)k0, ad_hi);
           const uint32_t boff = (uint32_t)(12 + shift + k0);
-          tc::umma_bf16_warp(d, ad, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
-          tc::umma_bf16_warp(d, ad, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
+          tc::umma_bf16(d, ad, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
+          tc::umma_bf16(d, ad, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
           acc = 1u;
         }
       }
-      tc::umma_commit_warp(&bar_mma);
+      tc::umma_commit(&bar_mma);
     }
     first = 0;
     tc::mbar_wait(&bar_mma, phase);   // operands may be overwritten once the MMAs have drained
@@ -633,19 +633,21 @@ size_t r8tc_dcop_bytes(int H) { return (size_t)12 * r8tc_dcop_rows(H) * 16; }
 
 // BatchNorm backward + residual fan-in + ReLU mask (same arithmetic as bn_bwd_apply_kernel in res8.cu), one thread =
 // 8 channels of one pixel; emits the (hi, lo) bf16 operand rows directly.  grid.y = channel chunk.
+template <bool EVEN, bool GU_IN, bool BCAST>
 __global__ void __launch_bounds__(256) bn_bwd_apply_op_kernel(const ApplyOpParams p) {
   const int HW = p.H * R8_W, Kp = r8tc_dcop_rows_dev(p.H), chunk = blockIdx.y;
-  float mu[8], rs[8], m1[8], m2[8];
-  bool ok[8];
+  float mu[8], rs[8], m1[8], m2[8], live[8];
+  int coff[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
-    ok[j] = c < R8_C;
-    const int cc = ok[j] ? c : 0;
+    const int cc = c < R8_C ? c : R8_C - 1;          // clamped address + zero weight: no guards around the loads
+    live[j] = c < R8_C ? 1.f : 0.f;
     mu[j] = __ldg(p.mean_rstd + cc);
     rs[j] = __ldg(p.mean_rstd + R8_C + cc);
     m1[j] = (float)(p.stats[cc] / p.count);
     m2[j] = (float)(p.stats[R8_C + cc] / p.count);
+    coff[j] = cc * HW;
   }
   const float inv_hw = 1.f / (float)HW;
   const int64_t items = p.B * HW;
@@ -654,21 +656,22 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_op_kernel(const ApplyOpParam
     const int64_t b = it / HW;
     const int pp = (int)(it - b * HW);
     const int y = pp / R8_W, x = pp - y * R8_W;
+    const int64_t ub = b * (int64_t)R8_C * HW + pp;
+    float g[8], u[8], gi[8], pv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {       // every load of the item is issued before any is consumed
+      const int64_t idx = ub + coff[j];
+      u[j] = p.u[idx];
+      g[j] = BCAST ? __ldg(p.g_bcast + b * R8_C + (coff[j] / HW)) * inv_hw : p.g[idx];
+      gi[j] = GU_IN ? p.gu_in[idx] : 0.f;
+      pv[j] = EVEN ? p.mask_prev[idx] : 0.f;
+    }
     float d[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = chunk * 8 + j;
-      d[j] = 0.f;
-      if (ok[j]) {
-        const int64_t idx = (b * R8_C + c) * (int64_t)HW + pp;
-        const float g = p.g ? p.g[idx] : __ldg(p.g_bcast + b * R8_C + c) * inv_hw;
-        const float u = p.u[idx];
-        float G = rs[j] * (g - m1[j] - (u - mu[j]) * rs[j] * m2[j]);
-        if (p.gu_in) G += p.gu_in[idx];
-        if (p.gu_out) p.gu_out[idx] = G;
-        const float prev = p.mask_prev ? p.mask_prev[idx] : 0.f;
-        d[j] = (u > prev) ? G : 0.f;
-      }
+      const float G = rs[j] * (g[j] - m1[j] - (u[j] - mu[j]) * rs[j] * m2[j]) + gi[j];
+      if (EVEN && live[j] != 0.f) p.gu_out[ub + coff[j]] = G;
+      d[j] = (u[j] > pv[j]) ? G * live[j] : 0.f;
     }
     uint4 hi, lo;
     tc::split8(d, hi, lo);
@@ -683,7 +686,20 @@ int r8tc_apply(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p) {
   int64_t bx = howl_ceil_div(items, 256);
   const int64_t cap = (int64_t)ctx->sm_count * 4;
   if (bx > cap) bx = cap;
-  bn_bwd_apply_op_kernel<<<dim3((unsigned)bx, 6, 1), 256, 0, st>>>(p);
+  const dim3 grid((unsigned)bx, 6, 1);
+  const bool even = p.gu_out != nullptr;
+  HOWL_REQUIRE(ctx, even == (p.mask_prev != nullptr) && (!p.gu_in || even) && ((p.g != nullptr) != (p.g_bcast != nullptr)),
+               HOWL_E_INVALID, "apply: inconsistent arguments");
+  if (p.g_bcast) {
+    HOWL_REQUIRE(ctx, even && !p.gu_in, HOWL_E_INVALID, "apply: broadcast gradient is the last (even) layer");
+    bn_bwd_apply_op_kernel<true, false, true><<<grid, 256, 0, st>>>(p);
+  } else if (even && p.gu_in) {
+    bn_bwd_apply_op_kernel<true, true, false><<<grid, 256, 0, st>>>(p);
+  } else if (even) {
+    bn_bwd_apply_op_kernel<true, false, false><<<grid, 256, 0, st>>>(p);
+  } else {
+    bn_bwd_apply_op_kernel<false, false, false><<<grid, 256, 0, st>>>(p);
+  }
   HOWL_LAUNCHED(ctx, "bn_bwd_apply_op");
   return HOWL_OK;
 }
@@ -758,44 +774,50 @@ __global__ void __launch_bounds__(TCD_THREADS, 1) conv3x3_dgrad_tc_kernel(const 
     if (n_local > 0) load_op(0);
     if (n_local > 1) load_op(1);
     __syncwarp();
-    tc::mbar_wait(&bar_w, 0);
-    const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 0, 0);
-    const uint32_t w_hi_s = tc::smem_u32(w_hi), w_lo_s = tc::smem_u32(w_lo);
-    const uint32_t bh_lo = tc::desc_lo(w_hi_s, TC_N * 16u), bl_lo = tc::desc_lo(w_lo_s, TC_N * 16u);
-    const uint32_t d_hi128 = tc::desc_hi(128u);
-    for (int64_t k = 0; k < n_local; ++k) {
-      const int buf = (int)(k & 1);
-      const uint32_t par = (uint32_t)((k >> 1) & 1);
-      tc::mbar_wait(&bar_a[buf], par);                       // operand tile landed
-      if (k >= 2) tc::mbar_wait(&bar_free[buf], par ^ 1u);   // epilogue of utterance k-2 has drained this TMEM half
-      tc::fence_after_sync();
-      const uint32_t a_hi_s = tc::smem_u32(a_buf + (size_t)buf * op_bytes), a_lo_s = a_hi_s + (uint32_t)(6 * Kp * 16);
-      const uint32_t ah_lo = tc::desc_lo(a_hi_s, (uint32_t)Kp * 16u), al_lo = tc::desc_lo(a_lo_s, (uint32_t)Kp * 16u);
-      for (int t = 0; t < tiles; ++t) {
-        const uint32_t d = tmem + (uint32_t)(buf * 256 + t * TC_N);
-        const uint32_t rowb = (uint32_t)(TC_Q0 + 128 * t);
+    if (tc::elect_one()) {
+      tc::mbar_wait(&bar_w, 0);
+      const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 0, 0);
+      const uint32_t w_hi_s = tc::smem_u32(w_hi), w_lo_s = tc::smem_u32(w_lo);
+      const uint32_t bh_lo = tc::desc_lo(w_hi_s, TC_N * 16u), bl_lo = tc::desc_lo(w_lo_s, TC_N * 16u);
+      const uint32_t d_hi128 = tc::desc_hi(128u);
+      const uint32_t a_base = tc::smem_u32(a_buf);
+      for (int64_t k = 0; k < n_local; ++k) {
+        const int buf = (int)(k & 1);
+        const uint32_t par = (uint32_t)((k >> 1) & 1);
+        tc::mbar_wait(&bar_a[buf], par);                       // operand tile landed
+        if (k >= 2) tc::mbar_wait(&bar_free[buf], par ^ 1u);   // epilogue of utterance k-2 has drained this TMEM half
+        tc::fence_after_sync();
+        const uint32_t a_hi_s = a_base + (uint32_t)buf * op_bytes, a_lo_s = a_hi_s + (uint32_t)(6 * Kp * 16);
+        const uint32_t ah_lo = tc::desc_lo(a_hi_s, (uint32_t)Kp * 16u), al_lo = tc::desc_lo(a_lo_s, (uint32_t)Kp * 16u);
+        for (int t = 0; t < tiles; ++t) {
+          const uint32_t d = tmem + (uint32_t)(buf * 256 + t * TC_N);
+          const uint32_t rowb = (uint32_t)(TC_Q0 + 128 * t);
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
 #pragma unroll
-          for (int ks = 0; ks < 3; ++ks) {
-            const uint32_t aoff = (uint32_t)(2 * ks) * (uint32_t)Kp + rowb + (uint32_t)shift;
-            const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N);
-            const uint64_t ah = tc::desc_make(ah_lo + aoff, d_hi128), al = tc::desc_make(al_lo + aoff, d_hi128);
-            const uint64_t bh = tc::desc_make(bh_lo + boff, d_hi128), bl = tc::desc_make(bl_lo + boff, d_hi128);
-            tc::umma_bf16_warp(d, al, bh, idesc, (tap | ks) ? 1u : 0u);
-            tc::umma_bf16_warp(d, ah, bl, idesc, 1u);
-            tc::umma_bf16_warp(d, ah, bh, idesc, 1u);
+            for (int ks = 0; ks < 3; ++ks) {
+              const uint32_t aoff = (uint32_t)(2 * ks) * (uint32_t)Kp + rowb + (uint32_t)shift;
+              const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N);
+              const uint64_t ah = tc::desc_make(ah_lo + aoff, d_hi128), al = tc::desc_make(al_lo + aoff, d_hi128);
+              const uint64_t bh = tc::desc_make(bh_lo + boff, d_hi128), bl = tc::desc_make(bl_lo + boff, d_hi128);
+              tc::umma_bf16(d, al, bh, idesc, (tap | ks) ? 1u : 0u);
+              tc::umma_bf16(d, ah, bl, idesc, 1u);
+              tc::umma_bf16(d, ah, bh, idesc, 1u);
+            }
           }
+          tc::umma_commit(&bar_tile[buf][t]);
         }
-        tc::umma_commit_warp(&bar_tile[buf][t]);
-      }
-      // refill the other buffer with utterance k + 1 once the MMAs of utterance k - 1 have released it
-      if (k >= 1 && k + 1 < n_local) {
-        tc::mbar_wait(&bar_tile[buf ^ 1][tiles - 1], (uint32_t)(((k - 1) >> 1) & 1));
-        load_op(k + 1);
+        // refill the other buffer with utterance k + 1 once the MMAs of utterance k - 1 have released it
+        if (k >= 1 && k + 1 < n_local) {
+          tc::mbar_wait(&bar_tile[buf ^ 1][tiles - 1], (uint32_t)(((k - 1) >> 1) & 1));
+          const int64_t b = blockIdx.x + (k + 1) * (int64_t)gridDim.x;
+          tc::mbar_expect_tx(&bar_a[(k + 1) & 1], op_bytes);
+          tc::tma_bulk_g2s(a_buf + (size_t)((k + 1) & 1) * op_bytes, src0 + (size_t)b * op_bytes, op_bytes, &bar_a[(k + 1) & 1]);
+        }
       }
     }
+    __syncwarp();
   } else {
     // ================= epilogue workers: thread = one raster row, warp quad = 24 channels =================
     const int half = warp >> 2;

@@ -119,6 +119,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// elect.sync: true in exactly one lane of the (converged) warp.  Branching on it lets ptxas treat the region as
+// single-threaded: descriptor arithmetic stays in the uniform datapath and UTCHMMA needs no per-instruction election.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred)
+      :
+      : "memory");
+  return pred != 0;
+}
 // Same MMA, to be executed by ALL lanes of a converged warp with warp-uniform operands: one lane is elected inside the
 // PTX, so the compiler keeps descriptors in uniform registers and emits ELECT + predicated UTCHMMA (no per-lane loop).
 __device__ __forceinline__ void umma_bf16_warp(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
