@@ -82,6 +82,31 @@ class _BatchNormStats(nn.Module):
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
 
 
+def _flatten_into(owner, params, attr: str, device):
+    """Make `params` (nn.Parameters, state_dict order) contiguous views of ONE flat fp32 buffer stored at owner.<attr>.
+    Re-done whenever something (`.to()`, `load_state_dict` with assign, ...) broke the aliasing; the Parameter objects
+    keep their identity, so optimizers built earlier stay valid."""
+    flat = getattr(owner, attr)
+    n = sum(p.numel() for p in params)
+    ok = flat is not None and flat.device == device and flat.numel() == n
+    if ok:
+        off = 0
+        for p in params:
+            if p.data_ptr() != flat.data_ptr() + 4 * off or not p.is_contiguous():
+                ok = False
+                break
+            off += p.numel()
+    if not ok:
+        flat = torch.empty(n, dtype=torch.float32, device=device)
+        off = 0
+        for p in params:
+            flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        setattr(owner, attr, flat)
+    return flat
+
+
 class _Res8Function(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, feats, labels_hint, *params):
@@ -119,24 +144,7 @@ class Res8(RegisteredModel, name="res8"):
         return ps
 
     def _ensure_flat(self, device):
-        ps = self._param_list()
-        n = sum(p.numel() for p in ps)
-        ok = self._flat is not None and self._flat.device == device and self._flat.numel() == n
-        if ok:
-            off = 0
-            for p in ps:
-                if p.data_ptr() != self._flat.data_ptr() + 4 * off or not p.is_contiguous():
-                    ok = False
-                    break
-                off += p.numel()
-        if not ok:
-            flat = torch.empty(n, dtype=torch.float32, device=device)
-            off = 0
-            for p in ps:
-                flat[off:off + p.numel()].copy_(p.data.reshape(-1))
-                p.data = flat[off:off + p.numel()].view(p.shape)
-                off += p.numel()
-            self._flat = flat
+        _flatten_into(self, self._param_list(), "_flat", device)
         bns = [getattr(self, f"bn{i}") for i in range(1, 7)]
         okb = self._bn_flat is not None and self._bn_flat.device == device
         if okb:
@@ -186,3 +194,118 @@ class Res8(RegisteredModel, name="res8"):
         if self.training and torch.is_grad_enabled():
             return _Res8Function.apply(self, feats, None, *self._param_list())
         return self._run_forward(feats, train=self.training)
+
+
+# =====================================================================================================================
+# lstm / seq-lstm (howl/model/rnn.py:41-91)
+# =====================================================================================================================
+class _LstmCell(nn.Module):
+    """Parameter holder with torch.nn.LSTM's names and default init (U(+-1/sqrt(hidden)))."""
+
+    def __init__(self, n_mels: int, hidden: int):
+        super().__init__()
+        bound = 1.0 / math.sqrt(hidden)
+        for name, shape in (("weight_ih_l0", (4 * hidden, n_mels)), ("weight_hh_l0", (4 * hidden, hidden)),
+                            ("bias_ih_l0", (4 * hidden,)), ("bias_hh_l0", (4 * hidden,))):
+            setattr(self, name, nn.Parameter((torch.rand(shape) * 2 - 1) * bound))
+
+
+class _LstmFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, feats, lengths, max_steps, *params):
+        ctx.model, ctx.shape, ctx.lengths, ctx.max_steps = model, tuple(feats.shape), lengths, max_steps
+        return model._run(feats, lengths, max_steps, train=True)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        m = ctx.model
+        c = get_context(m._flat.device, ctx.shape[2])
+        grads = torch.empty_like(m._flat)
+        c.lstm_bwd(ctx.shape, ctx.lengths, ctx.max_steps, None, m._flat, grads, None, m._ws, dlogits=dlogits.contiguous())
+        out, off = [], 0
+        for p in m._param_list():
+            out.append(grads[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        return (None, None, None, None, *out)
+
+
+class _LstmBase(RegisteredModel):
+    HIDDEN = 128
+
+    def __init__(self, num_labels: int, config=None):
+        super().__init__(num_labels)
+        n_mels = getattr(config, "num_mels", 40) if config is not None else 40
+        self.n_mels = n_mels
+        self.lstm = _LstmCell(n_mels, self.HIDDEN)
+        self.dnn = nn.Sequential(_Weight((2 * self.HIDDEN, self.HIDDEN), (2 * self.HIDDEN,)), nn.Identity(),
+                                 _Weight((num_labels, 2 * self.HIDDEN), (num_labels,)))
+        self._flat = self._ws = None
+
+    def _param_list(self):
+        return [self.lstm.weight_ih_l0, self.lstm.weight_hh_l0, self.lstm.bias_ih_l0, self.lstm.bias_hh_l0,
+                self.dnn[0].weight, self.dnn[0].bias, self.dnn[2].weight, self.dnn[2].bias]
+
+    def _prepare(self, x, lengths):
+        if x.device.type != "cuda":
+            raise RuntimeError("howl_b200 lstm models need CUDA tensors (no CPU fallback)")
+        ctx = get_context(x.device, x.shape[2])
+        feats = ctx.to_time_major(x.contiguous().float())      # x[:, 0].permute(2, 0, 1) of rnn.py:61-65,86-88, kept [B, F, M]
+        if lengths is None:
+            lengths = torch.full((x.shape[0],), feats.shape[1], dtype=torch.int64)
+        max_steps = int(lengths.max())
+        lengths = lengths.to(device=x.device, dtype=torch.int64).contiguous()
+        _flatten_into(self, self._param_list(), "_flat", x.device)
+        return ctx, feats, lengths, max_steps
+
+    def _workspace(self, ctx, batch, max_steps, train, sequential):
+        need = ctx.lstm_workspace_bytes(batch, max_steps, self.num_labels, train, sequential)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != ctx.device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=ctx.device)
+        return self._ws
+
+
+class SimpleLstm(_LstmBase, name="lstm"):
+    """dnn(h_n) -> [B, L]; the reference never carries state for this model (its streaming_state setter is a no-op)."""
+
+    def _run(self, feats, lengths, max_steps, train):
+        ctx = get_context(feats.device, feats.shape[2])
+        ws = self._workspace(ctx, feats.shape[0], max_steps, train, False)
+        return ctx.lstm_fwd(feats, lengths, max_steps, self._flat, ws, sequential=False, train=train)
+
+    def forward(self, x, lengths):
+        ctx, feats, lengths, max_steps = self._prepare(x, lengths)
+        if self.training and torch.is_grad_enabled():
+            return _LstmFunction.apply(self, feats, lengths, max_steps, *self._param_list())
+        return self._run(feats, lengths, max_steps, train=False)
+
+
+class SequentialLstm(_LstmBase, name="seq-lstm"):
+    """dnn(h_t) for every frame -> [T', B, L]; carries (h, c) between calls when streaming (rnn.py:60-71)."""
+
+    def __init__(self, num_labels: int, config=None):
+        super().__init__(num_labels, config)
+        self.hc = None
+
+    @property
+    def streaming_state(self) -> Any:
+        return self.hc
+
+    @streaming_state.setter
+    def streaming_state(self, x: Any):
+        self.hc = x
+
+    def forward(self, x, lengths):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list()) and self.training:
+            raise NotImplementedError("training seq-lstm (CTC objective) is not built yet; use torch.no_grad() / .eval()")
+        ctx, feats, lengths, max_steps = self._prepare(x, lengths)
+        b = feats.shape[0]
+        ws = self._workspace(ctx, b, max_steps, False, True)
+        state_in = None
+        if self.is_streaming and self.hc is not None:
+            state_in = torch.stack([self.hc[0].reshape(b, self.HIDDEN), self.hc[1].reshape(b, self.HIDDEN)]).contiguous().float()
+        state_out = torch.empty(2, b, self.HIDDEN, dtype=torch.float32, device=feats.device) if self.is_streaming else None
+        out = ctx.lstm_fwd(feats, lengths, max_steps, self._flat, ws, sequential=True, train=False, state_in=state_in,
+                           state_out=state_out)
+        if self.is_streaming:
+            self.hc = (state_out[0].unsqueeze(0).clone(), state_out[1].unsqueeze(0).clone())
+        return out

@@ -187,6 +187,62 @@ class Context:
                                                      num_labels, _ptr(params), _ptr(grads), _ptr(ws), ws.numel()),
                  "res8_bwd_dlogits")
 
+    # ------------------------------------------------------------------ lstm / seq-lstm
+    def lstm_param_count(self, num_labels: int) -> int:
+        return int(self.lib.howl_b200_lstm_param_count(num_labels, self.n_mels))
+
+    def lstm_workspace_bytes(self, batch: int, max_steps: int, num_labels: int, train: bool = True, sequential: bool = False) -> int:
+        n = int(self.lib.howl_b200_lstm_workspace_bytes(batch, max_steps, self.n_mels, num_labels, int(train), int(sequential)))
+        if n < 0:
+            raise HowlB200Error(f"lstm: unsupported shape B={batch} steps={max_steps} L={num_labels}")
+        return n
+
+    def lstm_labels_from_params(self, params: torch.Tensor) -> int:
+        n = params.numel() - (512 * self.n_mels + 512 * 128 + 1024 + 256 * 128 + 256)
+        if n <= 0 or n % 257:
+            raise HowlB200Error(f"lstm: flat parameter buffer of {params.numel()} floats is not an lstm layout")
+        return n // 257
+
+    def lstm_fwd(self, feats, lengths, max_steps: int, params, ws, sequential=False, train=False, state_in=None,
+                 state_out=None, out=None):
+        b, f, m = feats.shape
+        num_labels = self.lstm_labels_from_params(params)
+        _check(lengths, torch.int64, self.device, "lengths")
+        if out is None:
+            shape = (max_steps, b, num_labels) if sequential else (b, num_labels)
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        self._rc(self.lib.howl_b200_lstm_fwd(self.handle, self._stream(), _ptr(feats), _ptr(lengths), b, f, m, num_labels,
+                                             max_steps, _ptr(params), _ptr(state_in), _ptr(state_out), int(sequential),
+                                             int(train), _ptr(out), _ptr(ws), ws.numel()), "lstm_fwd")
+        return out
+
+    def lstm_bwd(self, feats_shape, lengths, max_steps: int, labels, params, grads, loss, ws, loss_scale_batch=None, dlogits=None):
+        b, f, m = feats_shape
+        num_labels = self.lstm_labels_from_params(params)
+        if dlogits is not None:
+            self._rc(self.lib.howl_b200_lstm_bwd_dlogits(self.handle, self._stream(), _ptr(lengths), _ptr(dlogits), b, f, m,
+                                                         num_labels, max_steps, _ptr(params), _ptr(grads), _ptr(ws),
+                                                         ws.numel()), "lstm_bwd_dlogits")
+        else:
+            _check(labels, torch.int64, self.device, "labels")
+            self._rc(self.lib.howl_b200_lstm_bwd(self.handle, self._stream(), _ptr(lengths), _ptr(labels), b, f, m, num_labels,
+                                                 max_steps, loss_scale_batch or b, _ptr(params), _ptr(grads), _ptr(loss),
+                                                 _ptr(ws), ws.numel()), "lstm_bwd")
+
+    def lstm_train_step(self, pcm, labels, lengths, max_steps, fb, zmuv, params, grads, m, v, step, lr, weight_decay, loss,
+                        logits, ws):
+        b, t = pcm.shape
+        num_labels = self.lstm_labels_from_params(params)
+        self._rc(self.lib.howl_b200_lstm_train_step(
+            self.handle, self._stream(), _ptr(pcm), _ptr(labels), _ptr(lengths), b, t, _ptr(fb), float(zmuv[0]),
+            float(zmuv[1]), num_labels, max_steps, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), step, lr, weight_decay,
+            _ptr(loss), _ptr(logits), _ptr(ws), ws.numel()), "lstm_train_step")
+
+    def lstm_train_step_workspace_bytes(self, batch: int, samples: int, max_steps: int, num_labels: int) -> int:
+        f = self.num_frames(samples)
+        feat = (batch * f * self.n_mels * 4 + 255) // 256 * 256
+        return feat + self.lstm_workspace_bytes(batch, max_steps, num_labels, True, False)
+
     def adamw(self, params, grads, m, v, step: int, lr: float, weight_decay: float, betas=(0.9, 0.999), eps=1e-8):
         self._rc(self.lib.howl_b200_adamw(self.handle, self._stream(), _ptr(params), _ptr(grads), _ptr(m), _ptr(v),
                                           params.numel(), step, lr, betas[0], betas[1], eps, weight_decay), "adamw")

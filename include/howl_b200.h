@@ -139,6 +139,38 @@ int howl_b200_res8_bwd_dlogits(howl_ctx_t* ctx, void* stream, const float* feats
                                int32_t frames, int32_t n_mels, int32_t num_labels, const float* params, float* grads,
                                void* workspace, size_t workspace_bytes);
 
+/* ---- K5: lstm / seq-lstm ------------------------------------------------------------------------- */
+/* Flat parameter layout (state_dict order): lstm.weight_ih_l0[512,M] | lstm.weight_hh_l0[512,128] |
+ * lstm.bias_ih_l0[512] | lstm.bias_hh_l0[512] | dnn.0.weight[256,128] | dnn.0.bias[256] | dnn.2.weight[L,256] | dnn.2.bias[L]. */
+int64_t howl_b200_lstm_param_count(int32_t num_labels, int32_t n_mels);
+int64_t howl_b200_lstm_workspace_bytes(int64_t B, int32_t max_steps, int32_t n_mels, int32_t num_labels, int train,
+                                       int sequential);
+/*
+ * SimpleLstm.forward (howl/model/rnn.py:85-91; sequential == 0, out [B, L] = dnn(h_n)) and SequentialLstm.forward
+ * (rnn.py:60-71; sequential != 0, out [max_steps, B, L], zero rows beyond each length) on time-major features [B, F, M].
+ * lengths [B] i64 (device) = frames each sequence advances (pack_padded_sequence semantics, any order);
+ * max_steps = max(lengths) (host).  state_in / state_out: [2][B][128] (h, c) streaming state or NULL (rnn.py:62-68).
+ * train != 0 keeps the activations in `workspace` for howl_b200_lstm_bwd (frame objective only).
+ */
+int howl_b200_lstm_fwd(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* lengths, int64_t B,
+                       int32_t frames, int32_t n_mels, int32_t num_labels, int32_t max_steps, const float* params,
+                       const float* state_in, float* state_out, int sequential, int train, float* out, void* workspace,
+                       size_t workspace_bytes);
+/* CrossEntropyLoss(mean) + backward through the MLP head and the recurrence (BPTT) for the forward kept in `workspace`
+ * (training/run/train.py:293,299-301 with --model lstm).  grads (flat layout) is OVERWRITTEN. */
+int howl_b200_lstm_bwd(howl_ctx_t* ctx, void* stream, const int64_t* lengths, const int64_t* labels, int64_t B,
+                       int32_t frames, int32_t n_mels, int32_t num_labels, int32_t max_steps, int64_t loss_scale_batch,
+                       const float* params, float* grads, float* loss, void* workspace, size_t workspace_bytes);
+int howl_b200_lstm_bwd_dlogits(howl_ctx_t* ctx, void* stream, const int64_t* lengths, const float* dlogits, int64_t B,
+                               int32_t frames, int32_t n_mels, int32_t num_labels, int32_t max_steps, const float* params,
+                               float* grads, void* workspace, size_t workspace_bytes);
+/* frontend -> lstm -> CE -> backward -> AdamW in one call (single device). */
+int howl_b200_lstm_train_step(howl_ctx_t* ctx, void* stream, const float* pcm, const int64_t* labels,
+                              const int64_t* lengths, int64_t B, int64_t T, const float* fb, float zmuv_mean,
+                              float zmuv_std, int32_t num_labels, int32_t max_steps, float* params, float* grads,
+                              float* exp_avg, float* exp_avg_sq, int64_t step, float lr, float weight_decay, float* loss,
+                              float* logits, void* workspace, size_t workspace_bytes);
+
 /* ---- K4: fused AdamW over a flat buffer ------------------------------------------------------- */
 /* torch.optim.AdamW.step (training/run/train.py:256,302): decoupled weight decay, bias correction,
  * eps outside the sqrt; `step` is 1-based. */

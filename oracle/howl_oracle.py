@@ -366,3 +366,92 @@ def synthetic_batch(batch: int, samples: int, num_labels: int, seed: int = 0):
     pcm = (torch.randn(batch, samples, generator=g) * 0.1).clamp_(-1, 1)
     labels = torch.randint(0, num_labels, (batch,), generator=g)
     return pcm, labels
+
+
+# ----------------------------------------------------------------------------------------------
+# lstm / seq-lstm (howl/model/rnn.py:41-91): nn.LSTM(40 -> 128) over the first `length` frames, MLP(128 -> 256 -> L)
+# ----------------------------------------------------------------------------------------------
+LSTM_HIDDEN = 128
+LSTM_MLP = 256
+
+
+def lstm_param_shapes(num_labels: int, n_mels: int = 40) -> List[Tuple[str, Tuple[int, ...]]]:
+    """state_dict order."""
+    h = LSTM_HIDDEN
+    return [("lstm.weight_ih_l0", (4 * h, n_mels)), ("lstm.weight_hh_l0", (4 * h, h)), ("lstm.bias_ih_l0", (4 * h,)),
+            ("lstm.bias_hh_l0", (4 * h,)), ("dnn.0.weight", (LSTM_MLP, h)), ("dnn.0.bias", (LSTM_MLP,)),
+            ("dnn.2.weight", (num_labels, LSTM_MLP)), ("dnn.2.bias", (num_labels,))]
+
+
+def lstm_init(num_labels: int, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """PyTorch defaults: nn.LSTM U(+-1/sqrt(hidden)); nn.Linear U(+-1/sqrt(fan_in))."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, shape in lstm_param_shapes(num_labels):
+        if name.startswith("lstm."):
+            bound = 1.0 / math.sqrt(LSTM_HIDDEN)
+        else:
+            bound = 1.0 / math.sqrt(shape[1] if len(shape) > 1 else {"dnn.0.bias": LSTM_HIDDEN, "dnn.2.bias": LSTM_MLP}[name])
+        out[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return out
+
+
+def lstm_recurrence(feats: torch.Tensor, params: Dict[str, torch.Tensor], lengths: torch.Tensor,
+                    state: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """The cell of torch.nn.LSTM restated: gates = W_ih x + b_ih + W_hh h + b_hh, rows ordered (i, f, g, o);
+    c' = f c + i g; h' = o tanh(c').  `feats` is the frontend layout [B, C>=1, M, F]; as in
+    pack_padded_sequence(x.permute(2,0,1), lengths) (rnn.py:65,88) sequence b only advances for t < lengths[b].
+    Returns (h_seq [Tmax, B, H] zero beyond each length -- pad_packed_sequence semantics --, (h_n, c_n))."""
+    x = feats[:, 0].permute(2, 0, 1)  # [F, B, M]
+    b = x.shape[1]
+    hdim = LSTM_HIDDEN
+    h = state[0].reshape(b, hdim) if state is not None else x.new_zeros(b, hdim)
+    c = state[1].reshape(b, hdim) if state is not None else x.new_zeros(b, hdim)
+    tmax = int(lengths.max())
+    outs = []
+    for t in range(tmax):
+        gates = F.linear(x[t], params["lstm.weight_ih_l0"], params["lstm.bias_ih_l0"]) + \
+            F.linear(h, params["lstm.weight_hh_l0"], params["lstm.bias_hh_l0"])
+        i, f, g, o = gates.chunk(4, 1)
+        c_new = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h_new = torch.sigmoid(o) * torch.tanh(c_new)
+        live = (lengths > t).to(x.dtype).unsqueeze(1)
+        c = live * c_new + (1 - live) * c
+        h = live * h_new + (1 - live) * h
+        outs.append(live * h_new)
+    return torch.stack(outs), (h, c)
+
+
+def lstm_forward(feats, params, lengths, sequential: bool = False, state=None):
+    """SimpleLstm.forward (rnn.py:85-91): dnn(h_n) -> [B, L];  SequentialLstm.forward (rnn.py:60-71): dnn(h_seq) ->
+    [Tmax, B, L] plus the carried state."""
+    h_seq, (h, c) = lstm_recurrence(feats, params, lengths, state)
+    top = h_seq if sequential else h
+    z = F.relu(F.linear(top, params["dnn.0.weight"], params["dnn.0.bias"]))
+    out = F.linear(z, params["dnn.2.weight"], params["dnn.2.bias"])
+    return (out, (h, c)) if sequential else out
+
+
+def lstm_flatten(tensors: Dict[str, torch.Tensor], num_labels: int) -> torch.Tensor:
+    return torch.cat([tensors[name].reshape(-1) for name, _ in lstm_param_shapes(num_labels)])
+
+
+def lstm_unflatten(flat: torch.Tensor, num_labels: int) -> Dict[str, torch.Tensor]:
+    out, off = {}, 0
+    for name, shape in lstm_param_shapes(num_labels):
+        n = int(np.prod(shape))
+        out[name] = flat[off:off + n].reshape(shape).clone()
+        off += n
+    return out
+
+
+def lstm_train_step(feats, labels, lengths, params, m, v, step, lr, weight_decay):
+    """Frame-objective iteration with the `lstm` model (training/run/train.py:292-302, pretrain_gsc.py:126-133)."""
+    leaves = {k: p.detach().clone().requires_grad_(True) for k, p in params.items()}
+    logits = lstm_forward(feats, leaves, lengths)
+    loss = F.cross_entropy(logits, labels)
+    loss.backward()
+    grads = {k: leaves[k].grad.detach() for k in leaves}
+    with torch.no_grad():
+        adamw_step(params, grads, m, v, step, lr, weight_decay)
+    return loss.detach(), logits.detach(), grads

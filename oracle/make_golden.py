@@ -218,6 +218,58 @@ def main():
             ts[f"step{step}.sd.{k}"] = v.detach().numpy().copy()
     np.savez_compressed(os.path.join(OUT, "res8_train.npz"), **ts)
 
+    # ------------------------------------------------------------------ lstm / seq-lstm (rnn.py:41-91)
+    ls = {}
+    gsc = f"{REF}/howl-models/howl/experiments/commands_recognition/lstm/0"
+    lsd = torch.load(f"{gsc}/model-best.pt.bin", map_location="cpu")
+    lz = torch.load(f"{gsc}/zmuv.pt.bin", map_location="cpu")
+    lstm = RegisteredModel.find_registered_class("lstm")(30).eval()
+    lstm.load_state_dict(lsd)
+    ls.update({f"sd.{k}": v.numpy() for k, v in lsd.items()})
+    ls.update({"zmuv.mean": lz["mean"].numpy(), "zmuv.mean2": lz["mean2"].numpy()})
+    wins16 = torch.stack([torch.from_numpy(speech[s:s + 16000]) for s in (0, 4000, 9000, 15000, 19000)])
+    zl = ZmuvTransform()
+    zl.load_state_dict(lz)
+    with torch.no_grad():
+        f16 = zl(std(wins16))
+        len16 = std.compute_lengths(torch.full((wins16.size(0),), 16000))
+        ls["pcm"], ls["lengths"] = wins16.numpy(), len16.numpy()
+        ls["logits"] = lstm(f16, len16).numpy()
+        # ragged lengths (descending, as pack_padded_sequence demands)
+        ragged = torch.tensor([78, 70, 41, 12, 1])
+        ls["ragged_lengths"] = ragged.numpy()
+        ls["ragged_logits"] = lstm(f16, ragged).numpy()
+        # seq-lstm with the same weights: per-frame logits and the carried streaming state over two calls
+        seq = RegisteredModel.find_registered_class("seq-lstm")(30).eval().streaming()
+        seq.load_state_dict(lsd)
+        out1 = seq(f16, len16)
+        h1, c1 = seq.streaming_state
+        out2 = seq(f16, len16)
+        ls["seq_out1"], ls["seq_out2"] = out1.numpy(), out2.numpy()
+        ls["seq_h1"], ls["seq_c1"] = h1.numpy(), c1.numpy()
+    # two reference train steps (frame objective, torch AdamW), seeded init
+    torch.manual_seed(21)
+    lm = RegisteredModel.find_registered_class("lstm")(12).train()
+    ls.update({f"init.{k}": v.detach().numpy().copy() for k, v in lm.state_dict().items()})
+    g2 = torch.Generator().manual_seed(5)
+    lp = (torch.randn(6, 8000, generator=g2) * 0.1).clamp_(-1, 1)
+    ly = torch.randint(0, 12, (6,), generator=g2)
+    ll = std.compute_lengths(torch.full((6,), 8000))
+    ls["t_pcm"], ls["t_labels"], ls["t_lengths"] = lp.numpy(), ly.numpy(), ll.numpy()
+    lopt = torch.optim.AdamW(lm.parameters(), 0.01, weight_decay=1e-5)
+    for stp in (1, 2):
+        sc = lm(zl(std(lp)), ll)
+        lo = torch.nn.functional.cross_entropy(sc, ly)
+        lopt.zero_grad()
+        lo.backward()
+        ls[f"step{stp}.loss"], ls[f"step{stp}.logits"] = lo.detach().numpy(), sc.detach().numpy()
+        for k, prm in lm.named_parameters():
+            ls[f"step{stp}.grad.{k}"] = prm.grad.numpy().copy()
+        lopt.step()
+        for k, v in lm.state_dict().items():
+            ls[f"step{stp}.sd.{k}"] = v.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "lstm.npz"), **ls)
+
     # ------------------------------------------------------------------ label-sequence FSM (host logic) cases
     from howl.model.inference import InferenceEngine
 

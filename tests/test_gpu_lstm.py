@@ -1,0 +1,129 @@
+"""GPU: lstm / seq-lstm (howl/model/rnn.py:41-91) through the C ABI and the nn.Module mirrors, against the committed
+reference outputs (real GSC checkpoint, ragged lengths, streaming state, two reference train steps) and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import howl_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+RTOL = ATOL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def _env(monkeypatch):
+    from howl_b200.settings import SETTINGS
+
+    monkeypatch.setenv("NUM_MELS", "40")
+    SETTINGS.reset()
+    yield
+    SETTINGS.reset()
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def _feats(g, key="pcm"):
+    return O.hot_path_features(torch.from_numpy(g[key]), O.mel_filterbank(40), torch.from_numpy(g["zmuv.mean"]),
+                               torch.from_numpy(g["zmuv.mean2"]))
+
+
+def test_registry_and_state_dict_keys(golden):
+    from howl_b200.model import RegisteredModel
+
+    g = golden("lstm")
+    for name in ("lstm", "seq-lstm"):
+        m = RegisteredModel.find_registered_class(name)(30)
+        assert list(m.state_dict().keys()) == [k[3:] for k in g if k.startswith("sd.")]
+        assert sum(p.numel() for p in m.parameters()) == 127774      # lstm @30 labels
+
+
+def test_lstm_real_weights_ragged_and_streaming(golden):
+    from howl_b200.model import RegisteredModel
+
+    g = golden("lstm")
+    sd = _sd(g, "sd.")
+    feats = _feats(g).to(DEV)
+    lstm = RegisteredModel.find_registered_class("lstm")(30)
+    lstm.load_state_dict(sd)
+    lstm = lstm.to(DEV).eval()
+    with torch.no_grad():
+        out = lstm(feats, torch.from_numpy(g["lengths"]))
+        np.testing.assert_allclose(out.cpu().numpy(), g["logits"], rtol=RTOL, atol=ATOL)
+        assert np.array_equal(out.argmax(1).cpu().numpy(), g["logits"].argmax(1))
+        out = lstm(feats, torch.from_numpy(g["ragged_lengths"]))
+        np.testing.assert_allclose(out.cpu().numpy(), g["ragged_logits"], rtol=RTOL, atol=ATOL)
+        seq = RegisteredModel.find_registered_class("seq-lstm")(30)
+        seq.load_state_dict(sd)
+        seq = seq.to(DEV).eval().streaming()
+        o1 = seq(feats, torch.from_numpy(g["lengths"]))
+        np.testing.assert_allclose(o1.cpu().numpy(), g["seq_out1"], rtol=RTOL, atol=ATOL)
+        h, c = seq.streaming_state
+        np.testing.assert_allclose(h.cpu().numpy(), g["seq_h1"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(c.cpu().numpy(), g["seq_c1"], rtol=RTOL, atol=ATOL)
+        o2 = seq(feats, torch.from_numpy(g["lengths"]))
+        np.testing.assert_allclose(o2.cpu().numpy(), g["seq_out2"], rtol=RTOL, atol=ATOL)
+
+
+def test_lstm_module_reference_train_steps(golden):
+    """training/run/train.py:292-302 with --model lstm: torch CrossEntropyLoss + torch AdamW over model.parameters()."""
+    from howl_b200.model import RegisteredModel
+
+    g = golden("lstm")
+    L = 12
+    model = RegisteredModel.find_registered_class("lstm")(L)
+    model.load_state_dict(_sd(g, "init."))
+    model = model.to(DEV).train()
+    opt = torch.optim.AdamW(model.parameters(), 0.01, weight_decay=1e-5)
+    feats = _feats(g, "t_pcm").to(DEV)
+    labels, lengths = torch.from_numpy(g["t_labels"]).to(DEV), torch.from_numpy(g["t_lengths"])
+    for step in (1, 2):
+        scores = model(feats, lengths)
+        loss = torch.nn.functional.cross_entropy(scores, labels)
+        opt.zero_grad()
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), g[f"step{step}.loss"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(scores.detach().cpu().numpy(), g[f"step{step}.logits"], rtol=RTOL, atol=ATOL)
+        for k, p in model.named_parameters():
+            want = g[f"step{step}.grad.{k}"]
+            np.testing.assert_allclose(p.grad.cpu().numpy(), want, rtol=2e-3, atol=1e-4 * np.abs(want).max(), err_msg=k)
+        opt.step()
+        model.load_state_dict({k: torch.from_numpy(g[f"step{step}.sd.{k}"]) for k in model.state_dict()})
+
+
+@pytest.mark.parametrize("B,T", [(1, 8000), (33, 8000), (70, 16000)])
+def test_lstm_fused_train_step_vs_oracle(B, T):
+    import howl_b200
+
+    L = 5
+    ctx = howl_b200.Context(DEV, n_mels=40)
+    pcm, labels = O.synthetic_batch(B, T, L, seed=B)
+    fb = O.mel_filterbank(40)
+    zmean, zstd = -1.78896, 3.93389
+    F = O.num_frames(T)
+    full = int(O.compute_lengths([T])[0])
+    rng = np.random.default_rng(B)
+    lengths = torch.from_numpy(np.sort(rng.integers(1, full + 1, size=B))[::-1].copy()) if B > 1 else torch.tensor([full])
+    lengths[0] = full
+    params = O.lstm_init(L, seed=3)
+    flat = O.lstm_flatten(params, L).to(DEV)
+    assert flat.numel() == ctx.lstm_param_count(L)
+    grads, m, v = torch.zeros_like(flat), torch.zeros_like(flat), torch.zeros_like(flat)
+    loss, logits = torch.zeros(1, device=DEV), torch.zeros(B, L, device=DEV)
+    ws = torch.empty(ctx.lstm_train_step_workspace_bytes(B, T, full, L), dtype=torch.uint8, device=DEV)
+    ctx.lstm_train_step(pcm.to(DEV), labels.to(DEV), lengths.to(DEV), full, fb.to(DEV), (zmean, zstd), flat, grads, m, v, 1,
+                        0.01, 1e-5, loss, logits, ws)
+    feats = O.hot_path_features(pcm, fb, torch.tensor([zmean]), torch.tensor([zmean ** 2 + zstd ** 2]))
+    om = {k: torch.zeros_like(p) for k, p in params.items()}
+    ov = {k: torch.zeros_like(p) for k, p in params.items()}
+    oloss, ologits, ograds = O.lstm_train_step(feats, labels, lengths, params, om, ov, 1, 0.01, 1e-5)
+    np.testing.assert_allclose(logits.cpu().numpy(), ologits.numpy(), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(loss.item(), oloss.item(), rtol=RTOL, atol=ATOL)
+    got = O.lstm_unflatten(grads.cpu(), L)
+    for k in got:
+        want = ograds[k].numpy()
+        np.testing.assert_allclose(got[k].numpy(), want, rtol=2e-3, atol=2e-4 * np.abs(want).max(), err_msg=k)
+    np.testing.assert_allclose(flat.cpu().numpy(), O.lstm_flatten(params, L).numpy(), rtol=1e-3, atol=5e-4)
+    ctx.close()

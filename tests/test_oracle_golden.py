@@ -157,3 +157,59 @@ def test_known_answer_traces_recorded():
     assert meta["traces"]["hey_fire_fox"]["detected"] is True
     assert meta["traces"]["hey_fire_fox"]["labels"] == [3, 3, 3, 3, 3, 0, 0, 0, 0, 0, 3, 1, 1, 1, 1, 1, 1, 1, 3, 3, 3, 2]
     assert meta["traces"]["hello_world"] == {"detected": False, "labels": [3] * 7}
+
+
+# ------------------------------------------------------------------------------------------ lstm / seq-lstm
+def test_lstm_restatement_equals_torch_nn_lstm():
+    torch.manual_seed(0)
+    p = O.lstm_init(7, seed=4)
+    ref = torch.nn.LSTM(40, 128)
+    ref.load_state_dict({k[5:]: v for k, v in p.items() if k.startswith("lstm.")})
+    feats = torch.randn(5, 3, 40, 23)
+    lengths = torch.tensor([23, 23, 17, 9, 1])
+    h_seq, (h, c) = O.lstm_recurrence(feats, p, lengths)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(feats[:, 0].permute(2, 0, 1).contiguous(), lengths)
+    out, (hn, cn) = ref(packed)
+    out, _ = torch.nn.utils.rnn.pad_packed_sequence(out)
+    np.testing.assert_allclose(h_seq.detach().numpy(), out.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(h.detach().numpy(), hn[0].detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(c.detach().numpy(), cn[0].detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_lstm_real_weights_and_streaming_state(golden):
+    g = golden("lstm")
+    sd = _sd(g, "sd.")
+    assert [k for k, _ in O.lstm_param_shapes(30)] == list(sd.keys())
+    feats = O.hot_path_features(torch.from_numpy(g["pcm"]), O.mel_filterbank(40), torch.from_numpy(g["zmuv.mean"]),
+                                torch.from_numpy(g["zmuv.mean2"]))
+    lengths = torch.from_numpy(g["lengths"])
+    assert lengths.tolist() == [78] * 5
+    np.testing.assert_allclose(O.lstm_forward(feats, sd, lengths).numpy(), g["logits"], rtol=RTOL, atol=ATOL)
+    ragged = torch.from_numpy(g["ragged_lengths"])
+    np.testing.assert_allclose(O.lstm_forward(feats, sd, ragged).numpy(), g["ragged_logits"], rtol=RTOL, atol=ATOL)
+    out1, st = O.lstm_forward(feats, sd, lengths, sequential=True)
+    np.testing.assert_allclose(out1.numpy(), g["seq_out1"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(st[0].numpy(), g["seq_h1"][0], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(st[1].numpy(), g["seq_c1"][0], rtol=RTOL, atol=ATOL)
+    out2, _ = O.lstm_forward(feats, sd, lengths, sequential=True, state=st)
+    np.testing.assert_allclose(out2.numpy(), g["seq_out2"], rtol=RTOL, atol=ATOL)
+
+
+def test_lstm_train_steps(golden):
+    g = golden("lstm")
+    L = 12
+    init = _sd(g, "init.")
+    params = {k: init[k].clone() for k, _ in O.lstm_param_shapes(L)}
+    assert O.lstm_flatten(params, L).numel() == 121092 + 8 * 257
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v = {k: torch.zeros_like(p) for k, p in params.items()}
+    feats = O.hot_path_features(torch.from_numpy(g["t_pcm"]), O.mel_filterbank(40), torch.from_numpy(g["zmuv.mean"]),
+                                torch.from_numpy(g["zmuv.mean2"]))
+    labels, lengths = torch.from_numpy(g["t_labels"]), torch.from_numpy(g["t_lengths"])
+    for step in (1, 2):
+        loss, logits, grads = O.lstm_train_step(feats, labels, lengths, params, m, v, step, 0.01, 1e-5)
+        np.testing.assert_allclose(loss.numpy(), g[f"step{step}.loss"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(logits.numpy(), g[f"step{step}.logits"], rtol=RTOL, atol=ATOL)
+        for k in params:
+            np.testing.assert_allclose(grads[k].numpy(), g[f"step{step}.grad.{k}"], rtol=1e-3, atol=1e-6)
+            params[k].copy_(torch.from_numpy(g[f"step{step}.sd.{k}"]))   # teacher-force (AdamW's first steps are sign-like)
