@@ -149,3 +149,69 @@ class Res8TrainStep:
             out[f"bn{i + 1}.running_var"] = self.bn_running[i, 1].clone()
             out[f"bn{i + 1}.num_batches_tracked"] = self.nbt[i].clone()
         return out
+
+
+def lstm_param_shapes(num_labels: int, n_mels: int = 40):
+    """state_dict order of SimpleLstm / SequentialLstm (howl/model/rnn.py:41-91)."""
+    return [("lstm.weight_ih_l0", (512, n_mels)), ("lstm.weight_hh_l0", (512, 128)), ("lstm.bias_ih_l0", (512,)),
+            ("lstm.bias_hh_l0", (512,)), ("dnn.0.weight", (256, 128)), ("dnn.0.bias", (256,)),
+            ("dnn.2.weight", (num_labels, 256)), ("dnn.2.bias", (num_labels,))]
+
+
+class LstmTrainStep:
+    """Fused train step of the `lstm` model (frame objective): frontend -> LSTM -> MLP -> CE -> BPTT -> AdamW."""
+
+    def __init__(self, device, num_labels: int, batch: int, samples: int, n_mels: int = 40, lr: float = 0.01,
+                 weight_decay: float = 1e-5, zmuv: Tuple[float, float] = (0.0, 1.0), seed: int = 0, world_size: int = 1):
+        self.ctx = Context(device, n_mels=n_mels)
+        dev = self.ctx.device
+        self.device, self.num_labels, self.batch, self.samples = dev, num_labels, batch, samples
+        self.lr, self.weight_decay, self.zmuv, self.world = lr, weight_decay, zmuv, world_size
+        g = torch.Generator().manual_seed(seed)
+        parts = []
+        for name, shape in lstm_param_shapes(num_labels, n_mels):
+            fan = 128 if name.startswith("lstm.") else (shape[1] if len(shape) > 1 else {"dnn.0.bias": 128, "dnn.2.bias": 256}[name])
+            parts.append(((torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan)).reshape(-1))
+        self.params = torch.cat(parts).to(dev)
+        n = self.params.numel()
+        assert n == self.ctx.lstm_param_count(num_labels)
+        self.grads, self.m, self.v = (torch.zeros(n, device=dev) for _ in range(3))
+        self.loss = torch.zeros(1, device=dev)
+        self.logits = torch.zeros(batch, num_labels, device=dev)
+        self.fb = mel_filterbank(n_mels).to(dev)
+        self.frames = self.ctx.num_frames(samples)
+        self.steps = (samples - self.ctx.n_fft) // self.ctx.hop + 1          # compute_lengths of a full clip
+        self.lengths = torch.full((batch,), self.steps, dtype=torch.int64, device=dev)
+        self.feat_bytes = (batch * self.frames * n_mels * 4 + 255) // 256 * 256
+        self.ws = torch.empty(self.ctx.lstm_train_step_workspace_bytes(batch, samples, self.steps, num_labels), dtype=torch.uint8,
+                              device=dev)
+        self.step_count = 0
+
+    def step(self, pcm: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        self.step_count += 1
+        c = self.ctx
+        if self.world == 1:
+            c.lstm_train_step(pcm, labels, self.lengths, self.steps, self.fb, self.zmuv, self.params, self.grads, self.m, self.v,
+                              self.step_count, self.lr, self.weight_decay, self.loss, self.logits, self.ws)
+        else:
+            from .parallel import allreduce_flat_grads
+
+            feats = self.ws[: self.batch * self.frames * c.n_mels * 4].view(torch.float32).view(self.batch, self.frames, c.n_mels)
+            ws = self.ws[self.feat_bytes:]
+            c.frontend(pcm, self.fb, "time_major", zmuv=self.zmuv, out=feats)
+            c.lstm_fwd(feats, self.lengths, self.steps, self.params, ws, train=True, out=self.logits)
+            c.lstm_bwd(tuple(feats.shape), self.lengths, self.steps, labels, self.params, self.grads, self.loss, ws,
+                       loss_scale_batch=self.batch * self.world)
+            allreduce_flat_grads(self.grads)
+            c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
+        return self.loss
+
+    def profile_groups(self, pcm, labels, reps: int = 3):
+        acc, cnt = {}, {}
+        for _ in range(reps):
+            self.ctx.profile_begin()
+            self.step(pcm, labels)
+            for name, ms in self.ctx.profile_end():
+                acc[name] = acc.get(name, 0.0) + ms
+                cnt[name] = cnt.get(name, 0) + 1
+        return [{"name": k, "ms": acc[k] / reps, "launches_per_step": cnt[k] // reps} for k in acc]
