@@ -55,7 +55,11 @@ SIGNATURES: Dict[str, tuple] = {
     "howl_b200_lstm_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, C.c_int, C.c_int]),
     "howl_b200_lstm_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _sz]),
     "howl_b200_lstm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _sz]),
-    "howl_b200_lstm_bwd_dlogits": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz]),
+    "howl_b200_lstm_bwd_dlogits": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz]),
+    "howl_b200_lstm_ctc_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp,
+                                         _vp, _sz]),
+    "howl_b200_seq_lstm_ctc_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _i64, _vp, _f32, _f32, _i32,
+                                                    _i32, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _sz]),
     "howl_b200_lstm_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _i32, _i32, _vp, _vp, _vp,
                                             _vp, _i64, _f32, _f32, _vp, _vp, _vp, _sz]),
     "howl_b200_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32]),

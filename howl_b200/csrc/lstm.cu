@@ -18,6 +18,8 @@
 #define LS_MLP 256
 #define LS_NB 16            // sequences per CTA
 #define LS_THREADS 512
+#define CTC_UMAX 32         // longest target sequence supported by the CTC kernel
+#define CTC_SMAX (2 * CTC_UMAX + 1 + 3)
 
 struct LstmWs {
   float* wt;        // [M + 128][512]  transposed [W_ih | W_hh]
@@ -34,8 +36,9 @@ struct LstmWs {
   float* z1;        // [R][256]
   float* logits;    // [B][L]
   float* dlogits;
-  float* dz1;       // [B][256]
-  float* dh;        // [B][128]
+  float* dz1;       // [R][256]
+  float* dh;        // [R][128]  gradient at h_n (R = B) or at every h_t (R = T*B, sequential)
+  float* alpha;     // [B][T][CTC_SMAX]  CTC forward variables (sequential + train)
   double* loss_acc;
   size_t bytes;
 };
@@ -61,11 +64,12 @@ static LstmWs lstm_carve(void* base, int64_t B, int T, int M, int L, int train, 
   w.loss_acc = (double*)take(sizeof(double) * 2);
   const int64_t rows = sequential ? (int64_t)T * B : B;
   w.z1 = (float*)take(sizeof(float) * rows * LS_MLP);
-  w.logits = (float*)take(sizeof(float) * B * L);
-  w.dlogits = (float*)take(sizeof(float) * B * L);
-  w.dz1 = (float*)take(sizeof(float) * B * LS_MLP);
-  w.dh = (float*)take(sizeof(float) * B * LS_H);
+  w.logits = (float*)take(sizeof(float) * rows * L);
+  w.dlogits = (float*)take(sizeof(float) * rows * L);
+  w.dz1 = (float*)take(sizeof(float) * rows * LS_MLP);
+  w.dh = (float*)take(sizeof(float) * rows * LS_H);
   if (sequential) w.hseq = (float*)take(sizeof(float) * (size_t)T * B * LS_H);
+  if (sequential && train) w.alpha = (float*)take(sizeof(float) * (size_t)B * T * CTC_SMAX);
   if (train) {
     w.gates = (float*)take(sizeof(float) * (size_t)T * B * LS_G);
     w.cs = (float*)take(sizeof(float) * (size_t)T * B * LS_H);
@@ -351,7 +355,8 @@ struct LstmBwdArgs {
   const float* c0;
   float* gates;           // in: activated gates, out: d(pre-activation)
   const float* cs;
-  const float* dh_head;   // [B][128] gradient at h_n
+  const float* dh_head;   // [B][128] gradient at h_n (frame objective), or null
+  const float* dh_seq;    // [T][B][128] gradient at every h_t (sequential objective), or null
   int64_t B;
   int T;
 };
@@ -375,7 +380,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_kernel(const LstmBwdAr
       const bool inb = b0 + b < a.B;
       const bool live = t < s_len[b];
       float dht = s_dh[p];
-      if (inb && t == s_len[b] - 1) dht += a.dh_head[(b0 + b) * LS_H + u];
+      if (inb && a.dh_head && t == s_len[b] - 1) dht += a.dh_head[(b0 + b) * LS_H + u];
+      if (inb && a.dh_seq && live) dht += a.dh_seq[((size_t)t * a.B + b0 + b) * LS_H + u];
       float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f;
       if (inb && live) {
         const size_t row = (size_t)t * a.B + b0 + b;
@@ -425,6 +431,121 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_kernel(const LstmBwdAr
     for (int p = tid; p < LS_NB * LS_H; p += LS_THREADS)
       s_dh[p] += s_part[p] + s_part[LS_NB * LS_H + p] + s_part[2 * LS_NB * LS_H + p] + s_part[3 * LS_NB * LS_H + p];
     __syncthreads();
+  }
+}
+
+
+// =============================================================================================
+// CTC (nn.CTCLoss(blank), reduction 'mean', on log_softmax(scores); training/run/train.py:253,296-298).
+// One warp per sequence: log-space forward variables (kept in the workspace), backward variables on the fly, and the
+// gradient with respect to the SCORES (log_softmax folded in):
+//   d(-ln P)/d z_t(k) = softmax_t(k) - sum_{s: l'_s = k} exp(alpha_t(s) + beta_t(s) - logp_t(k) - ln P)
+// scaled by 1 / (max(U, 1) * batch).  Frames beyond the input length get zero gradient.
+// =============================================================================================
+__device__ __forceinline__ float log_add(float a, float b) {
+  if (a == -INFINITY) return b;
+  if (b == -INFINITY) return a;
+  const float m = fmaxf(a, b);
+  return m + log1pf(expf(-fabsf(a - b)));
+}
+
+__global__ void __launch_bounds__(128) ctc_kernel(const float* __restrict__ scores, const int64_t* __restrict__ targets,
+                                                  const int64_t* __restrict__ tgt_len, const int64_t* __restrict__ in_len,
+                                                  int blank, int T, int64_t B, int L, int Lmax, float* __restrict__ alpha_ws,
+                                                  float* __restrict__ dscores, double* __restrict__ loss_acc,
+                                                  float inv_batch) {
+  __shared__ float s_a[4][2][CTC_SMAX];
+  __shared__ float s_logp[4][96];
+  __shared__ float s_acc[4][96];
+  __shared__ int s_lab[4][CTC_SMAX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * 4 + w;
+  if (b >= B) return;
+  int U = (int)tgt_len[b];
+  if (U > CTC_UMAX) U = CTC_UMAX;
+  const int S = 2 * U + 1;
+  int Tb = (int)in_len[b];
+  if (Tb > T) Tb = T;
+  for (int s = lane; s < CTC_SMAX; s += 32) s_lab[w][s] = (s < S && (s & 1)) ? (int)targets[b * Lmax + (s >> 1)] : blank;
+  __syncwarp();
+  float* my_alpha = alpha_ws + (size_t)b * T * CTC_SMAX;
+  auto frame_logp = [&](int t) {   // log_softmax of frame t into s_logp
+    const float* z = scores + ((size_t)t * B + b) * L;
+    float mx = -INFINITY;
+    for (int k = lane; k < L; k += 32) mx = fmaxf(mx, z[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int k = lane; k < L; k += 32) se += expf(z[k] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    __syncwarp();
+    for (int k = lane; k < L; k += 32) s_logp[w][k] = z[k] - lse;
+    __syncwarp();
+  };
+  // ---- forward
+  float logP = -INFINITY;
+  if (Tb > 0) {
+    frame_logp(0);
+    for (int s = lane; s < S; s += 32) {
+      const float v = (s < 2) ? s_logp[w][s_lab[w][s]] : -INFINITY;
+      s_a[w][0][s] = v;
+      my_alpha[s] = v;
+    }
+    __syncwarp();
+    for (int t = 1; t < Tb; ++t) {
+      frame_logp(t);
+      const float* prev = s_a[w][(t - 1) & 1];
+      float* cur = s_a[w][t & 1];
+      for (int s = lane; s < S; s += 32) {
+        float v = prev[s];
+        if (s >= 1) v = log_add(v, prev[s - 1]);
+        if (s >= 2 && (s & 1) && s_lab[w][s] != s_lab[w][s - 2]) v = log_add(v, prev[s - 2]);
+        v += s_logp[w][s_lab[w][s]];
+        cur[s] = v;
+        my_alpha[(size_t)t * CTC_SMAX + s] = v;
+      }
+      __syncwarp();
+    }
+    const float* last = s_a[w][(Tb - 1) & 1];
+    logP = last[S - 1];
+    if (S >= 2) logP = log_add(logP, last[S - 2]);
+  }
+  const float scale = inv_batch / (float)(U > 0 ? U : 1);
+  if (lane == 0) atomicAdd(loss_acc, (double)(-logP) * (double)scale);
+  // ---- frames beyond the input length: zero gradient
+  for (int t = Tb; t < T; ++t)
+    for (int k = lane; k < L; k += 32) dscores[((size_t)t * B + b) * L + k] = 0.f;
+  // ---- backward + gradient
+  float* bcur = s_a[w][0];
+  float* bnext = s_a[w][1];
+  for (int t = Tb - 1; t >= 0; --t) {
+    frame_logp(t);
+    for (int s = lane; s < S; s += 32) {
+      float v;
+      if (t == Tb - 1) {
+        v = (s >= S - 2) ? 0.f : -INFINITY;
+      } else {
+        v = bnext[s];
+        if (s + 1 < S) v = log_add(v, bnext[s + 1]);
+        if (s + 2 < S && (s & 1) && s_lab[w][s + 2] != s_lab[w][s]) v = log_add(v, bnext[s + 2]);
+      }
+      bcur[s] = v + s_logp[w][s_lab[w][s]];
+    }
+    for (int k = lane; k < L; k += 32) s_acc[w][k] = 0.f;
+    __syncwarp();
+    for (int s = lane; s < S; s += 32) {
+      const int k = s_lab[w][s];
+      const float e = my_alpha[(size_t)t * CTC_SMAX + s] + bcur[s] - s_logp[w][k] - logP;
+      if (e > -80.f) atomicAdd(&s_acc[w][k], expf(e));
+    }
+    __syncwarp();
+    for (int k = lane; k < L; k += 32)
+      dscores[((size_t)t * B + b) * L + k] = (expf(s_logp[w][k]) - s_acc[w][k]) * scale;
+    __syncwarp();
+    float* tmp = bcur;
+    bcur = bnext;
+    bnext = tmp;
   }
 }
 
@@ -534,7 +655,6 @@ extern "C" int howl_b200_lstm_fwd(howl_ctx_t* ctx, void* stream, const float* fe
                                   int train, float* out, void* workspace, size_t workspace_bytes) {
   if (!ctx) return HOWL_E_INVALID;
   HOWL_REQUIRE(ctx, feats && lengths && params && out, HOWL_E_INVALID, "lstm_fwd: null pointer");
-  HOWL_REQUIRE(ctx, !(sequential && train), HOWL_E_UNSUPPORTED, "lstm_fwd: training the sequential (CTC) objective is not built");
   int rc = lstm_check(ctx, B, frames, n_mels, num_labels, max_steps, workspace);
   if (rc) return rc;
   const int M = n_mels, L = num_labels, T = max_steps, K = M + LS_H;
@@ -568,24 +688,26 @@ extern "C" int howl_b200_lstm_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   const int64_t rows = sequential ? (int64_t)T * B : B;
   lstm_head_fwd_kernel<<<(unsigned)howl_ceil_div(rows, 16), 256, 0, st>>>(sequential ? ws.hseq : ws.hfin, rows, ws.w1t, v.b1,
                                                                           v.w2, v.b2, train ? ws.z1 : nullptr, out,
-                                                                          sequential ? nullptr : ws.logits, L);
+                                                                          (sequential && !train) ? nullptr : ws.logits, L);
   HOWL_LAUNCHED(ctx, "lstm_head_fwd");
   return HOWL_OK;
 }
 
 static int lstm_bwd_impl(howl_ctx_t* ctx, void* stream, const int64_t* lengths, const int64_t* labels,
-                         const float* dlogits_in, int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels,
+                         const float* dlogits_in, int sequential, const int64_t* targets, const int64_t* tgt_len,
+                         int max_target_len, int blank, int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels,
                          int32_t max_steps, int64_t loss_scale_batch, const float* params, float* grads, float* loss,
                          void* workspace, size_t workspace_bytes) {
   int rc = lstm_check(ctx, B, frames, n_mels, num_labels, max_steps, workspace);
   if (rc) return rc;
   const int M = n_mels, L = num_labels, T = max_steps, K = M + LS_H;
-  LstmWs ws = lstm_carve(workspace, B, T, M, L, 1, 0);
+  LstmWs ws = lstm_carve(workspace, B, T, M, L, 1, sequential);
   HOWL_REQUIRE(ctx, ws.bytes <= workspace_bytes, HOWL_E_WORKSPACE, "lstm_bwd: workspace %zu < required %zu", workspace_bytes,
                ws.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const LstmParams v = lstm_views(params, M, L);
   const int64_t nparam = howl_b200_lstm_param_count(L, M);
+  const int64_t rows = sequential ? (int64_t)T * B : B;
   float* g_w_ih = grads;
   float* g_w_hh = g_w_ih + (size_t)LS_G * M;
   float* g_b_ih = g_w_hh + (size_t)LS_G * LS_H;
@@ -596,22 +718,33 @@ static int lstm_bwd_impl(howl_ctx_t* ctx, void* stream, const int64_t* lengths, 
   float* g_b2 = g_w2 + (size_t)L * LS_MLP;
   HOWL_CUDA(ctx, cudaMemsetAsync(grads, 0, sizeof(float) * nparam, st));
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * 2, st));
-  lstm_head_bwd_kernel<<<(unsigned)howl_ceil_div(B, 16), 256, 0, st>>>(ws.logits, labels, dlogits_in, ws.z1, v.w1, v.w2,
-                                                                       ws.dlogits, ws.dz1, ws.dh, ws.loss_acc, B, L,
-                                                                       1.f / (float)loss_scale_batch);
+  const float inv_batch = 1.f / (float)loss_scale_batch;
+  if (sequential && targets) {
+    HOWL_REQUIRE(ctx, max_target_len >= 1 && max_target_len <= CTC_UMAX, HOWL_E_UNSUPPORTED,
+                 "ctc: max target length %d outside 1..%d", max_target_len, CTC_UMAX);
+    HOWL_REQUIRE(ctx, blank >= 0 && blank < L, HOWL_E_INVALID, "ctc: blank %d outside the %d labels", blank, L);
+    ctc_kernel<<<(unsigned)howl_ceil_div(B, 4), 128, 0, st>>>(ws.logits, targets, tgt_len, lengths, blank, T, B, L,
+                                                               max_target_len, ws.alpha, ws.dlogits, ws.loss_acc, inv_batch);
+    HOWL_LAUNCHED(ctx, "ctc");
+    dlogits_in = ws.dlogits;
+  }
+  lstm_head_bwd_kernel<<<(unsigned)howl_ceil_div(rows, 16), 256, 0, st>>>(ws.logits, labels, dlogits_in, ws.z1, v.w1, v.w2,
+                                                                          ws.dlogits, ws.dz1, ws.dh, ws.loss_acc, rows, L,
+                                                                          inv_batch);
   HOWL_LAUNCHED(ctx, "lstm_head_bwd");
   if (loss) {
     lstm_loss_kernel<<<1, 1, 0, st>>>(ws.loss_acc, loss);
     HOWL_LAUNCHED(ctx, "lstm_loss");
   }
   // head parameter gradients
-  if ((rc = lstm_atb(ctx, st, ws.dlogits, L, ws.z1, LS_MLP, g_w2, LS_MLP, L, LS_MLP, B))) return rc;
-  if ((rc = lstm_colsum(ctx, st, ws.dlogits, L, L, B, g_b2, nullptr))) return rc;
-  if ((rc = lstm_atb(ctx, st, ws.dz1, LS_MLP, ws.hfin, LS_H, g_w1, LS_H, LS_MLP, LS_H, B))) return rc;
-  if ((rc = lstm_colsum(ctx, st, ws.dz1, LS_MLP, LS_MLP, B, g_b1, nullptr))) return rc;
+  if ((rc = lstm_atb(ctx, st, ws.dlogits, L, ws.z1, LS_MLP, g_w2, LS_MLP, L, LS_MLP, rows))) return rc;
+  if ((rc = lstm_colsum(ctx, st, ws.dlogits, L, L, rows, g_b2, nullptr))) return rc;
+  if ((rc = lstm_atb(ctx, st, ws.dz1, LS_MLP, sequential ? ws.hseq : ws.hfin, LS_H, g_w1, LS_H, LS_MLP, LS_H, rows))) return rc;
+  if ((rc = lstm_colsum(ctx, st, ws.dz1, LS_MLP, LS_MLP, rows, g_b1, nullptr))) return rc;
   // BPTT
   LstmBwdArgs a;
-  a.lengths = lengths; a.w_hh = v.w_hh; a.c0 = ws.c0; a.gates = ws.gates; a.cs = ws.cs; a.dh_head = ws.dh; a.B = B; a.T = T;
+  a.lengths = lengths; a.w_hh = v.w_hh; a.c0 = ws.c0; a.gates = ws.gates; a.cs = ws.cs;
+  a.dh_head = sequential ? nullptr : ws.dh; a.dh_seq = sequential ? ws.dh : nullptr; a.B = B; a.T = T;
   const size_t smem = sizeof(float) * ((size_t)LS_G * LS_NB + 2 * LS_NB * LS_H + 4 * LS_NB * LS_H);
   HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   lstm_bwd_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
@@ -631,18 +764,61 @@ extern "C" int howl_b200_lstm_bwd(howl_ctx_t* ctx, void* stream, const int64_t* 
   if (!ctx) return HOWL_E_INVALID;
   HOWL_REQUIRE(ctx, lengths && labels && params && grads && loss, HOWL_E_INVALID, "lstm_bwd: null pointer");
   HOWL_REQUIRE(ctx, loss_scale_batch >= 1, HOWL_E_INVALID, "lstm_bwd: loss_scale_batch must be >= 1");
-  return lstm_bwd_impl(ctx, stream, lengths, labels, nullptr, B, frames, n_mels, num_labels, max_steps, loss_scale_batch,
-                       params, grads, loss, workspace, workspace_bytes);
+  return lstm_bwd_impl(ctx, stream, lengths, labels, nullptr, 0, nullptr, nullptr, 0, 0, B, frames, n_mels, num_labels,
+                       max_steps, loss_scale_batch, params, grads, loss, workspace, workspace_bytes);
 }
 
 extern "C" int howl_b200_lstm_bwd_dlogits(howl_ctx_t* ctx, void* stream, const int64_t* lengths, const float* dlogits,
-                                          int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels,
+                                          int sequential, int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels,
                                           int32_t max_steps, const float* params, float* grads, void* workspace,
                                           size_t workspace_bytes) {
   if (!ctx) return HOWL_E_INVALID;
   HOWL_REQUIRE(ctx, lengths && dlogits && params && grads, HOWL_E_INVALID, "lstm_bwd_dlogits: null pointer");
-  return lstm_bwd_impl(ctx, stream, lengths, nullptr, dlogits, B, frames, n_mels, num_labels, max_steps, 1, params, grads,
-                       nullptr, workspace, workspace_bytes);
+  return lstm_bwd_impl(ctx, stream, lengths, nullptr, dlogits, sequential, nullptr, nullptr, 0, 0, B, frames, n_mels,
+                       num_labels, max_steps, 1, params, grads, nullptr, workspace, workspace_bytes);
+}
+
+extern "C" int howl_b200_lstm_ctc_bwd(howl_ctx_t* ctx, void* stream, const int64_t* lengths, const int64_t* targets,
+                                      const int64_t* target_lengths, int32_t max_target_len, int32_t blank, int64_t B,
+                                      int32_t frames, int32_t n_mels, int32_t num_labels, int32_t max_steps,
+                                      int64_t loss_scale_batch, const float* params, float* grads, float* loss,
+                                      void* workspace, size_t workspace_bytes) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, lengths && targets && target_lengths && params && grads && loss, HOWL_E_INVALID, "lstm_ctc_bwd: null pointer");
+  HOWL_REQUIRE(ctx, loss_scale_batch >= 1, HOWL_E_INVALID, "lstm_ctc_bwd: loss_scale_batch must be >= 1");
+  return lstm_bwd_impl(ctx, stream, lengths, nullptr, nullptr, 1, targets, target_lengths, max_target_len, blank, B, frames,
+                       n_mels, num_labels, max_steps, loss_scale_batch, params, grads, loss, workspace, workspace_bytes);
+}
+
+extern "C" int howl_b200_seq_lstm_ctc_train_step(howl_ctx_t* ctx, void* stream, const float* pcm, const int64_t* targets,
+                                                 const int64_t* target_lengths, int32_t max_target_len, int32_t blank,
+                                                 const int64_t* lengths, int64_t B, int64_t T, const float* fb,
+                                                 float zmuv_mean, float zmuv_std, int32_t num_labels, int32_t max_steps,
+                                                 float* params, float* state, float* grads, float* exp_avg,
+                                                 float* exp_avg_sq, int64_t step, float lr, float weight_decay,
+                                                 float* loss, float* scores, void* workspace, size_t workspace_bytes) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, workspace, HOWL_E_WORKSPACE, "seq_lstm_ctc_train_step: null workspace");
+  const int M = ctx->fe.n_mels;
+  const int64_t F = howl_b200_num_frames(T, ctx->fe.hop);
+  HOWL_REQUIRE(ctx, F > 0 && F < (1 << 20), HOWL_E_INVALID, "seq_lstm_ctc_train_step: bad clip length %lld", (long long)T);
+  const size_t feat_bytes = howl_align_up(sizeof(float) * (size_t)B * F * M, 256);
+  HOWL_REQUIRE(ctx, workspace_bytes > feat_bytes, HOWL_E_WORKSPACE, "seq_lstm_ctc_train_step: workspace too small");
+  float* feats = (float*)workspace;
+  void* ws = (char*)workspace + feat_bytes;
+  const size_t ws_bytes = workspace_bytes - feat_bytes;
+  int rc = howl_b200_frontend_fwd(ctx, stream, pcm, B, T, fb, zmuv_mean, zmuv_std, nullptr, HOWL_FE_TIME_MAJOR | HOWL_FE_ZMUV,
+                                  feats);
+  if (rc) return rc;
+  // streaming: the (detached) state of the previous call is the initial state and is replaced (rnn.py:62-68)
+  rc = howl_b200_lstm_fwd(ctx, stream, feats, lengths, B, (int)F, M, num_labels, max_steps, params, state, state, 1, 1, scores,
+                          ws, ws_bytes);
+  if (rc) return rc;
+  rc = howl_b200_lstm_ctc_bwd(ctx, stream, lengths, targets, target_lengths, max_target_len, blank, B, (int)F, M, num_labels,
+                              max_steps, B, params, grads, loss, ws, ws_bytes);
+  if (rc) return rc;
+  return howl_b200_adamw(ctx, stream, params, grads, exp_avg, exp_avg_sq, howl_b200_lstm_param_count(num_labels, M), step, lr,
+                         0.9f, 0.999f, 1e-8f, weight_decay);
 }
 
 extern "C" int howl_b200_lstm_train_step(howl_ctx_t* ctx, void* stream, const float* pcm, const int64_t* labels,

@@ -221,7 +221,8 @@ class _LstmFunction(torch.autograd.Function):
         m = ctx.model
         c = get_context(m._flat.device, ctx.shape[2])
         grads = torch.empty_like(m._flat)
-        c.lstm_bwd(ctx.shape, ctx.lengths, ctx.max_steps, None, m._flat, grads, None, m._ws, dlogits=dlogits.contiguous())
+        c.lstm_bwd(ctx.shape, ctx.lengths, ctx.max_steps, None, m._flat, grads, None, m._ws, dlogits=dlogits.contiguous(),
+                   sequential=dlogits.dim() == 3)
         out, off = [], 0
         for p in m._param_list():
             out.append(grads[off:off + p.numel()].view(p.shape))
@@ -294,18 +295,22 @@ class SequentialLstm(_LstmBase, name="seq-lstm"):
     def streaming_state(self, x: Any):
         self.hc = x
 
-    def forward(self, x, lengths):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list()) and self.training:
-            raise NotImplementedError("training seq-lstm (CTC objective) is not built yet; use torch.no_grad() / .eval()")
-        ctx, feats, lengths, max_steps = self._prepare(x, lengths)
+    def _run(self, feats, lengths, max_steps, train):
+        ctx = get_context(feats.device, feats.shape[2])
         b = feats.shape[0]
-        ws = self._workspace(ctx, b, max_steps, False, True)
+        ws = self._workspace(ctx, b, max_steps, train, True)
         state_in = None
         if self.is_streaming and self.hc is not None:
             state_in = torch.stack([self.hc[0].reshape(b, self.HIDDEN), self.hc[1].reshape(b, self.HIDDEN)]).contiguous().float()
         state_out = torch.empty(2, b, self.HIDDEN, dtype=torch.float32, device=feats.device) if self.is_streaming else None
-        out = ctx.lstm_fwd(feats, lengths, max_steps, self._flat, ws, sequential=True, train=False, state_in=state_in,
+        out = ctx.lstm_fwd(feats, lengths, max_steps, self._flat, ws, sequential=True, train=train, state_in=state_in,
                            state_out=state_out)
-        if self.is_streaming:
+        if self.is_streaming:      # detached by construction (rnn.py:66-68)
             self.hc = (state_out[0].unsqueeze(0).clone(), state_out[1].unsqueeze(0).clone())
         return out
+
+    def forward(self, x, lengths):
+        ctx, feats, lengths, max_steps = self._prepare(x, lengths)
+        if self.training and torch.is_grad_enabled():
+            return _LstmFunction.apply(self, feats, lengths, max_steps, *self._param_list())
+        return self._run(feats, lengths, max_steps, train=False)

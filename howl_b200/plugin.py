@@ -32,7 +32,7 @@ def install(strict: bool = True):
     # the reference registry keeps name -> class; re-point "res8" and keep every other registered name
     base.RegisteredModel.registered_map["res8"] = model.Res8
     base.RegisteredModel.registered_map["lstm"] = model.SimpleLstm
-    base.RegisteredModel.registered_map["seq-lstm"] = model.SequentialLstm   # inference only so far
+    base.RegisteredModel.registered_map["seq-lstm"] = model.SequentialLstm
     cnn.Res8 = model.Res8
     inf.StandardAudioTransform = transform.StandardAudioTransform
     inf.InferenceEngine = inference.InferenceEngine

@@ -216,13 +216,15 @@ class Context:
                                              int(train), _ptr(out), _ptr(ws), ws.numel()), "lstm_fwd")
         return out
 
-    def lstm_bwd(self, feats_shape, lengths, max_steps: int, labels, params, grads, loss, ws, loss_scale_batch=None, dlogits=None):
+    def lstm_bwd(self, feats_shape, lengths, max_steps: int, labels, params, grads, loss, ws, loss_scale_batch=None, dlogits=None,
+                 sequential=False):
         b, f, m = feats_shape
         num_labels = self.lstm_labels_from_params(params)
         if dlogits is not None:
-            self._rc(self.lib.howl_b200_lstm_bwd_dlogits(self.handle, self._stream(), _ptr(lengths), _ptr(dlogits), b, f, m,
-                                                         num_labels, max_steps, _ptr(params), _ptr(grads), _ptr(ws),
-                                                         ws.numel()), "lstm_bwd_dlogits")
+            _check(dlogits, torch.float32, self.device, "dlogits")
+            self._rc(self.lib.howl_b200_lstm_bwd_dlogits(self.handle, self._stream(), _ptr(lengths), _ptr(dlogits),
+                                                         int(sequential), b, f, m, num_labels, max_steps, _ptr(params),
+                                                         _ptr(grads), _ptr(ws), ws.numel()), "lstm_bwd_dlogits")
         else:
             _check(labels, torch.int64, self.device, "labels")
             self._rc(self.lib.howl_b200_lstm_bwd(self.handle, self._stream(), _ptr(lengths), _ptr(labels), b, f, m, num_labels,
@@ -237,6 +239,30 @@ class Context:
             self.handle, self._stream(), _ptr(pcm), _ptr(labels), _ptr(lengths), b, t, _ptr(fb), float(zmuv[0]),
             float(zmuv[1]), num_labels, max_steps, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), step, lr, weight_decay,
             _ptr(loss), _ptr(logits), _ptr(ws), ws.numel()), "lstm_train_step")
+
+    def lstm_ctc_bwd(self, feats_shape, lengths, max_steps, targets, target_lengths, blank, params, grads, loss, ws,
+                     loss_scale_batch=None):
+        b, f, m = feats_shape
+        num_labels = self.lstm_labels_from_params(params)
+        _check(targets, torch.int64, self.device, "targets")
+        _check(target_lengths, torch.int64, self.device, "target_lengths")
+        self._rc(self.lib.howl_b200_lstm_ctc_bwd(self.handle, self._stream(), _ptr(lengths), _ptr(targets), _ptr(target_lengths),
+                                                 targets.shape[1], blank, b, f, m, num_labels, max_steps, loss_scale_batch or b,
+                                                 _ptr(params), _ptr(grads), _ptr(loss), _ptr(ws), ws.numel()), "lstm_ctc_bwd")
+
+    def seq_lstm_ctc_train_step(self, pcm, targets, target_lengths, blank, lengths, max_steps, fb, zmuv, params, state, grads, m,
+                                v, step, lr, weight_decay, loss, scores, ws):
+        b, t = pcm.shape
+        num_labels = self.lstm_labels_from_params(params)
+        self._rc(self.lib.howl_b200_seq_lstm_ctc_train_step(
+            self.handle, self._stream(), _ptr(pcm), _ptr(targets), _ptr(target_lengths), targets.shape[1], blank, _ptr(lengths),
+            b, t, _ptr(fb), float(zmuv[0]), float(zmuv[1]), num_labels, max_steps, _ptr(params), _ptr(state), _ptr(grads),
+            _ptr(m), _ptr(v), step, lr, weight_decay, _ptr(loss), _ptr(scores), _ptr(ws), ws.numel()), "seq_lstm_ctc_train_step")
+
+    def seq_lstm_train_step_workspace_bytes(self, batch: int, samples: int, max_steps: int, num_labels: int) -> int:
+        f = self.num_frames(samples)
+        feat = (batch * f * self.n_mels * 4 + 255) // 256 * 256
+        return feat + self.lstm_workspace_bytes(batch, max_steps, num_labels, True, True)
 
     def lstm_train_step_workspace_bytes(self, batch: int, samples: int, max_steps: int, num_labels: int) -> int:
         f = self.num_frames(samples)

@@ -161,9 +161,26 @@ int howl_b200_lstm_fwd(howl_ctx_t* ctx, void* stream, const float* feats, const 
 int howl_b200_lstm_bwd(howl_ctx_t* ctx, void* stream, const int64_t* lengths, const int64_t* labels, int64_t B,
                        int32_t frames, int32_t n_mels, int32_t num_labels, int32_t max_steps, int64_t loss_scale_batch,
                        const float* params, float* grads, float* loss, void* workspace, size_t workspace_bytes);
-int howl_b200_lstm_bwd_dlogits(howl_ctx_t* ctx, void* stream, const int64_t* lengths, const float* dlogits, int64_t B,
-                               int32_t frames, int32_t n_mels, int32_t num_labels, int32_t max_steps, const float* params,
-                               float* grads, void* workspace, size_t workspace_bytes);
+/* Backward for an arbitrary upstream gradient: dlogits [B, L] (sequential == 0) or [max_steps, B, L] (sequential != 0,
+ * e.g. from torch's F.log_softmax + nn.CTCLoss at training/run/train.py:296-298). */
+int howl_b200_lstm_bwd_dlogits(howl_ctx_t* ctx, void* stream, const int64_t* lengths, const float* dlogits, int sequential,
+                               int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels, int32_t max_steps,
+                               const float* params, float* grads, void* workspace, size_t workspace_bytes);
+/* F.log_softmax + nn.CTCLoss(blank) (reduction 'mean') + backward for a sequential forward kept in `workspace`
+ * (training/run/train.py:253,294-301 with --model seq-lstm).  targets [B, max_target_len] i64 (padded), target_lengths [B]
+ * i64, lengths [B] i64 = frames per sequence (all device).  loss[1] = mean_b(-ln p_b / max(U_b, 1)). */
+int howl_b200_lstm_ctc_bwd(howl_ctx_t* ctx, void* stream, const int64_t* lengths, const int64_t* targets,
+                           const int64_t* target_lengths, int32_t max_target_len, int32_t blank, int64_t B, int32_t frames,
+                           int32_t n_mels, int32_t num_labels, int32_t max_steps, int64_t loss_scale_batch,
+                           const float* params, float* grads, float* loss, void* workspace, size_t workspace_bytes);
+/* frontend -> seq-lstm (streaming state [2][B][128] read and replaced, or NULL) -> CTC -> BPTT -> AdamW (single device). */
+int howl_b200_seq_lstm_ctc_train_step(howl_ctx_t* ctx, void* stream, const float* pcm, const int64_t* targets,
+                                      const int64_t* target_lengths, int32_t max_target_len, int32_t blank,
+                                      const int64_t* lengths, int64_t B, int64_t T, const float* fb, float zmuv_mean,
+                                      float zmuv_std, int32_t num_labels, int32_t max_steps, float* params, float* state,
+                                      float* grads, float* exp_avg, float* exp_avg_sq, int64_t step, float lr,
+                                      float weight_decay, float* loss, float* scores, void* workspace,
+                                      size_t workspace_bytes);
 /* frontend -> lstm -> CE -> backward -> AdamW in one call (single device). */
 int howl_b200_lstm_train_step(howl_ctx_t* ctx, void* stream, const float* pcm, const int64_t* labels,
                               const int64_t* lengths, int64_t B, int64_t T, const float* fb, float zmuv_mean,

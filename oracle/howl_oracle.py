@@ -455,3 +455,19 @@ def lstm_train_step(feats, labels, lengths, params, m, v, step, lr, weight_decay
     with torch.no_grad():
         adamw_step(params, grads, m, v, step, lr, weight_decay)
     return loss.detach(), logits.detach(), grads
+
+
+def seq_lstm_ctc_step(feats, targets, target_lengths, lengths, params, state, blank, m, v, step, lr, weight_decay):
+    """One iteration of the CTC branch of training/run/train.py:294-302 with the streaming `seq-lstm`:
+    scores = model(x, lengths); log_softmax; nn.CTCLoss(blank) (reduction 'mean'); backward; AdamW.
+    `state` is the detached (h, c) carried from the previous call (rnn.py:62-68) or None.
+    Returns (loss, scores, grads, new_state)."""
+    leaves = {k: p.detach().clone().requires_grad_(True) for k, p in params.items()}
+    scores, new_state = lstm_forward(feats, leaves, lengths, sequential=True, state=state)
+    logp = F.log_softmax(scores, -1)
+    loss = F.ctc_loss(logp, targets, lengths, target_lengths, blank=blank, reduction="mean")
+    loss.backward()
+    grads = {k: leaves[k].grad.detach() for k in leaves}
+    with torch.no_grad():
+        adamw_step(params, grads, m, v, step, lr, weight_decay)
+    return loss.detach(), scores.detach(), grads, (new_state[0].detach(), new_state[1].detach())

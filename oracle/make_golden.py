@@ -268,6 +268,27 @@ def main():
         lopt.step()
         for k, v in lm.state_dict().items():
             ls[f"step{stp}.sd.{k}"] = v.detach().numpy().copy()
+    # two reference CTC steps with the STREAMING seq-lstm (train.py:246,253,294-302): state carried between the steps
+    torch.manual_seed(33)
+    sm = RegisteredModel.find_registered_class("seq-lstm")(5).train().streaming()
+    ls.update({f"ctc.init.{k}": v.detach().numpy().copy() for k, v in sm.state_dict().items()})
+    ctc = torch.nn.CTCLoss(4)
+    tg = torch.tensor([[0, 1, 2], [1, 1, 3], [2, 3, 3], [0, 3, 3], [3, 2, 1], [0, 0, 0]])     # padded with the negative label 3
+    tl = torch.tensor([3, 2, 1, 1, 3, 3])
+    ls["ctc.targets"], ls["ctc.target_lengths"] = tg.numpy(), tl.numpy()
+    sopt = torch.optim.AdamW(sm.parameters(), 0.01, weight_decay=1e-5)
+    for stp in (1, 2):
+        sc = sm(zl(std(lp)), ll)
+        lo = ctc(torch.nn.functional.log_softmax(sc, -1), tg, ll, tl)
+        sopt.zero_grad()
+        lo.backward()
+        ls[f"ctc.step{stp}.loss"], ls[f"ctc.step{stp}.scores"] = lo.detach().numpy(), sc.detach().numpy()
+        ls[f"ctc.step{stp}.h"], ls[f"ctc.step{stp}.c"] = sm.streaming_state[0].numpy(), sm.streaming_state[1].numpy()
+        for k, prm in sm.named_parameters():
+            ls[f"ctc.step{stp}.grad.{k}"] = prm.grad.numpy().copy()
+        sopt.step()
+        for k, v in sm.state_dict().items():
+            ls[f"ctc.step{stp}.sd.{k}"] = v.detach().numpy().copy()
     np.savez_compressed(os.path.join(OUT, "lstm.npz"), **ls)
 
     # ------------------------------------------------------------------ label-sequence FSM (host logic) cases

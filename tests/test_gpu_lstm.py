@@ -127,3 +127,97 @@ def test_lstm_fused_train_step_vs_oracle(B, T):
         np.testing.assert_allclose(got[k].numpy(), want, rtol=2e-3, atol=2e-4 * np.abs(want).max(), err_msg=k)
     np.testing.assert_allclose(flat.cpu().numpy(), O.lstm_flatten(params, L).numpy(), rtol=1e-3, atol=5e-4)
     ctx.close()
+
+
+def test_seq_lstm_ctc_reference_steps_module_and_fused(golden):
+    """The CTC branch of training/run/train.py:294-302 with the streaming seq-lstm, (a) through the nn.Module mirror with
+    torch's log_softmax + nn.CTCLoss + AdamW, (b) through the fused C-ABI step with the library's own CTC kernel."""
+    import howl_b200
+    from howl_b200.model import RegisteredModel
+
+    g = golden("lstm")
+    L, blank = 5, 4
+    feats_cpu = _feats(g, "t_pcm")
+    lengths = torch.from_numpy(g["t_lengths"])
+    tg, tl = torch.from_numpy(g["ctc.targets"]), torch.from_numpy(g["ctc.target_lengths"])
+    # ---- (a) module
+    model = RegisteredModel.find_registered_class("seq-lstm")(L)
+    model.load_state_dict(_sd(g, "ctc.init."))
+    model = model.to(DEV).train().streaming()
+    opt = torch.optim.AdamW(model.parameters(), 0.01, weight_decay=1e-5)
+    ctc = torch.nn.CTCLoss(blank)
+    for step in (1, 2):
+        scores = model(feats_cpu.to(DEV), lengths)
+        loss = ctc(torch.nn.functional.log_softmax(scores, -1), tg.to(DEV), lengths.to(DEV), tl.to(DEV))
+        opt.zero_grad()
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), g[f"ctc.step{step}.loss"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(scores.detach().cpu().numpy(), g[f"ctc.step{step}.scores"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(model.streaming_state[0].cpu().numpy(), g[f"ctc.step{step}.h"], rtol=RTOL, atol=ATOL)
+        for k, p in model.named_parameters():
+            want = g[f"ctc.step{step}.grad.{k}"]
+            np.testing.assert_allclose(p.grad.cpu().numpy(), want, rtol=2e-3, atol=2e-4 * np.abs(want).max(), err_msg=k)
+        opt.step()
+        model.load_state_dict({k: torch.from_numpy(g[f"ctc.step{step}.sd.{k}"]) for k in model.state_dict()})
+    # ---- (b) fused step, own CTC kernel
+    ctx = howl_b200.Context(DEV, n_mels=40)
+    pcm = torch.from_numpy(g["t_pcm"]).to(DEV)
+    B, T = pcm.shape
+    steps = int(lengths.max())
+    init = _sd(g, "ctc.init.")
+    flat = O.lstm_flatten({k: init[k] for k, _ in O.lstm_param_shapes(L)}, L).to(DEV)
+    grads, m, v = torch.zeros_like(flat), torch.zeros_like(flat), torch.zeros_like(flat)
+    state = torch.zeros(2, B, 128, device=DEV)
+    loss, scores = torch.zeros(1, device=DEV), torch.zeros(steps, B, L, device=DEV)
+    ws = torch.empty(ctx.seq_lstm_train_step_workspace_bytes(B, T, steps, L), dtype=torch.uint8, device=DEV)
+    mean = float(g["zmuv.mean"][0])
+    std = float(np.sqrt(g["zmuv.mean2"][0] - g["zmuv.mean"][0] ** 2))
+    for step in (1, 2):
+        ctx.seq_lstm_ctc_train_step(pcm, tg.to(DEV), tl.to(DEV), blank, lengths.to(DEV), steps, O.mel_filterbank(40).to(DEV),
+                                    (mean, std), flat, state, grads, m, v, step, 0.01, 1e-5, loss, scores, ws)
+        np.testing.assert_allclose(loss.item(), g[f"ctc.step{step}.loss"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(scores.cpu().numpy(), g[f"ctc.step{step}.scores"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(state[0].cpu().numpy(), g[f"ctc.step{step}.h"][0], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(state[1].cpu().numpy(), g[f"ctc.step{step}.c"][0], rtol=RTOL, atol=ATOL)
+        got = O.lstm_unflatten(grads.cpu(), L)
+        for k in got:
+            want = g[f"ctc.step{step}.grad.{k}"]
+            np.testing.assert_allclose(got[k].numpy(), want, rtol=2e-3, atol=2e-4 * np.abs(want).max(), err_msg=k)
+        flat.copy_(O.lstm_flatten({k: torch.from_numpy(g[f"ctc.step{step}.sd.{k}"]) for k, _ in O.lstm_param_shapes(L)}, L).to(DEV))
+    ctx.close()
+
+
+@pytest.mark.parametrize("B,T", [(3, 8000), (40, 16000)])
+def test_ctc_kernel_vs_torch_ragged(B, T):
+    """Own CTC kernel against torch's F.ctc_loss on ragged input / target lengths (incl. repeated labels, length-1 targets)."""
+    import howl_b200
+
+    L, blank = 6, 5
+    ctx = howl_b200.Context(DEV, n_mels=40)
+    pcm, _ = O.synthetic_batch(B, T, L, seed=B + 1)
+    fb = O.mel_filterbank(40)
+    zmean, zstd = -1.78896, 3.93389
+    full = int(O.compute_lengths([T])[0])
+    rng = np.random.default_rng(B)
+    lengths = torch.from_numpy(np.sort(rng.integers(max(8, full // 2), full + 1, size=B))[::-1].copy())
+    lengths[0] = full
+    tl = torch.from_numpy(rng.integers(1, 7, size=B))
+    tg = torch.from_numpy(rng.integers(0, blank, size=(B, 6)))
+    params = O.lstm_init(L, seed=9)
+    flat = O.lstm_flatten(params, L).to(DEV)
+    feats_cpu = O.hot_path_features(pcm, fb, torch.tensor([zmean]), torch.tensor([zmean ** 2 + zstd ** 2]))
+    feats = ctx.frontend(pcm.to(DEV), fb.to(DEV), "time_major", zmuv=(zmean, zstd))
+    ws = torch.empty(ctx.lstm_workspace_bytes(B, full, L, True, True), dtype=torch.uint8, device=DEV)
+    scores = ctx.lstm_fwd(feats, lengths.to(DEV), full, flat, ws, sequential=True, train=True)
+    grads, loss = torch.zeros_like(flat), torch.zeros(1, device=DEV)
+    ctx.lstm_ctc_bwd(tuple(feats.shape), lengths.to(DEV), full, tg.to(DEV), tl.to(DEV), blank, flat, grads, loss, ws)
+    m = {k: torch.zeros_like(p) for k, p in params.items()}
+    v = {k: torch.zeros_like(p) for k, p in params.items()}
+    oloss, oscores, ograds, _ = O.seq_lstm_ctc_step(feats_cpu, tg, tl, lengths, params, None, blank, m, v, 1, 0.01, 0.0)
+    np.testing.assert_allclose(scores.cpu().numpy(), oscores.numpy(), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(loss.item(), oloss.item(), rtol=RTOL, atol=ATOL)
+    got = O.lstm_unflatten(grads.cpu(), L)
+    for k in got:
+        want = ograds[k].numpy()
+        np.testing.assert_allclose(got[k].numpy(), want, rtol=2e-3, atol=2e-4 * np.abs(want).max(), err_msg=k)
+    ctx.close()

@@ -213,3 +213,26 @@ def test_lstm_train_steps(golden):
         for k in params:
             np.testing.assert_allclose(grads[k].numpy(), g[f"step{step}.grad.{k}"], rtol=1e-3, atol=1e-6)
             params[k].copy_(torch.from_numpy(g[f"step{step}.sd.{k}"]))   # teacher-force (AdamW's first steps are sign-like)
+
+
+def test_seq_lstm_ctc_steps(golden):
+    g = golden("lstm")
+    L = 5
+    init = _sd(g, "ctc.init.")
+    params = {k: init[k].clone() for k, _ in O.lstm_param_shapes(L)}
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v = {k: torch.zeros_like(p) for k, p in params.items()}
+    feats = O.hot_path_features(torch.from_numpy(g["t_pcm"]), O.mel_filterbank(40), torch.from_numpy(g["zmuv.mean"]),
+                                torch.from_numpy(g["zmuv.mean2"]))
+    lengths = torch.from_numpy(g["t_lengths"])
+    tg, tl = torch.from_numpy(g["ctc.targets"]), torch.from_numpy(g["ctc.target_lengths"])
+    state = None
+    for step in (1, 2):
+        loss, scores, grads, state = O.seq_lstm_ctc_step(feats, tg, tl, lengths, params, state, 4, m, v, step, 0.01, 1e-5)
+        np.testing.assert_allclose(loss.numpy(), g[f"ctc.step{step}.loss"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(scores.numpy(), g[f"ctc.step{step}.scores"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(state[0].numpy(), g[f"ctc.step{step}.h"][0], rtol=RTOL, atol=ATOL)
+        for k in params:
+            want = g[f"ctc.step{step}.grad.{k}"]
+            np.testing.assert_allclose(grads[k].numpy(), want, rtol=1e-3, atol=1e-5 * max(1.0, np.abs(want).max()))
+            params[k].copy_(torch.from_numpy(g[f"ctc.step{step}.sd.{k}"]))
