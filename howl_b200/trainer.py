@@ -215,3 +215,48 @@ class LstmTrainStep:
                 acc[name] = acc.get(name, 0.0) + ms
                 cnt[name] = cnt.get(name, 0) + 1
         return [{"name": k, "ms": acc[k] / reps, "launches_per_step": cnt[k] // reps} for k in acc]
+
+
+class SeqLstmCtcTrainStep(LstmTrainStep):
+    """Fused train step of the streaming `seq-lstm` with the CTC objective (training/run/train.py:294-302,
+    envs/seq-lstm.env): frontend -> LSTM (state carried, detached) -> MLP per frame -> log_softmax + CTC -> BPTT -> AdamW."""
+
+    def __init__(self, device, num_labels: int, batch: int, samples: int, blank: int, max_target_len: int = 3, **kw):
+        super().__init__(device, num_labels, batch, samples, **kw)
+        dev = self.device
+        self.blank = blank
+        self.state = torch.zeros(2, batch, 128, device=dev)
+        self.scores = torch.zeros(self.steps, batch, num_labels, device=dev)
+        self.ws = torch.empty(self.ctx.seq_lstm_train_step_workspace_bytes(batch, samples, self.steps, num_labels),
+                              dtype=torch.uint8, device=dev)
+
+    def step(self, pcm: torch.Tensor, targets: torch.Tensor, target_lengths: torch.Tensor) -> torch.Tensor:
+        self.step_count += 1
+        c = self.ctx
+        if self.world == 1:
+            c.seq_lstm_ctc_train_step(pcm, targets, target_lengths, self.blank, self.lengths, self.steps, self.fb, self.zmuv,
+                                      self.params, self.state, self.grads, self.m, self.v, self.step_count, self.lr,
+                                      self.weight_decay, self.loss, self.scores, self.ws)
+        else:
+            from .parallel import allreduce_flat_grads
+
+            feats = self.ws[: self.batch * self.frames * c.n_mels * 4].view(torch.float32).view(self.batch, self.frames, c.n_mels)
+            ws = self.ws[self.feat_bytes:]
+            c.frontend(pcm, self.fb, "time_major", zmuv=self.zmuv, out=feats)
+            c.lstm_fwd(feats, self.lengths, self.steps, self.params, ws, sequential=True, train=True, state_in=self.state,
+                       state_out=self.state, out=self.scores)
+            c.lstm_ctc_bwd(tuple(feats.shape), self.lengths, self.steps, targets, target_lengths, self.blank, self.params,
+                           self.grads, self.loss, ws, loss_scale_batch=self.batch * self.world)
+            allreduce_flat_grads(self.grads)
+            c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
+        return self.loss
+
+    def profile_groups(self, pcm, targets, target_lengths, reps: int = 3):
+        acc, cnt = {}, {}
+        for _ in range(reps):
+            self.ctx.profile_begin()
+            self.step(pcm, targets, target_lengths)
+            for name, ms in self.ctx.profile_end():
+                acc[name] = acc.get(name, 0.0) + ms
+                cnt[name] = cnt.get(name, 0) + 1
+        return [{"name": k, "ms": acc[k] / reps, "launches_per_step": cnt[k] // reps} for k in acc]

@@ -3,7 +3,7 @@
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from howl_b200.trainer import LstmTrainStep
+from howl_b200.trainer import LstmTrainStep, SeqLstmCtcTrainStep
 
 B, T, L = int(os.environ.get("B", 2048)), 8000, 5
 dev = torch.device("cuda:0")
@@ -21,3 +21,17 @@ ms = e0.elapsed_time(e1) / 10
 groups = tr.profile_groups(pcm, lab)
 print(json.dumps({"model": "lstm (frame objective)", "batch": B, "ms_per_step": ms, "utt_per_s": B / ms * 1e3,
                   "groups_ms": {x["name"]: round(x["ms"], 4) for x in groups}}))
+
+# ---- BASELINE.json configs[3]: seq-lstm, streaming state, CTC (blank = 4, L = 5), B = 2048, 0.5 s clips
+tr = SeqLstmCtcTrainStep(dev, 5, B, T, blank=4, zmuv=(-1.78896, 3.93389), lr=1e-4)
+tg = torch.randint(0, 4, (B, 3), generator=g).to(dev)
+tl = torch.randint(1, 4, (B,), generator=g).to(dev)
+for _ in range(3): tr.step(pcm, tg, tl)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10): tr.step(pcm, tg, tl)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+groups = tr.profile_groups(pcm, tg, tl)
+print(json.dumps({"model": "seq-lstm (streaming, CTC)", "batch": B, "ms_per_step": ms, "utt_per_s": B / ms * 1e3,
+                  "loss": tr.loss.item(), "groups_ms": {x["name"]: round(x["ms"], 4) for x in groups}}))
