@@ -112,6 +112,7 @@ extern "C" void howl_b200_destroy(howl_ctx_t* ctx) {
   cudaFree(ctx->fb_hi);
   cudaFree(ctx->fb_off);
   cudaFree(ctx->fbc);
+  cudaFree(ctx->mel_plan);
   free(ctx);
 }
 

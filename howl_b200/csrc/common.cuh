@@ -25,6 +25,7 @@ struct howl_ctx {
   int* fb_hi;
   int* fb_off;
   float* fbc;
+  int* mel_plan;     // FePlan (frontend.cu)
   int64_t launches;
   int conv_engine;   // 0 = fp32 FFMA kernels, 1 = tcgen05 bf16x3 kernels (default)
   // optional per-launch timing

@@ -16,7 +16,9 @@
 #define FE_TILE 27          // frames per CTA (81 = 3 tiles for 1 s clips, 41 = 27 + 14 for 0.5 s)
 #define FE_WARPS 8
 #define FE_THREADS (FE_WARPS * 32)
-#define FE_FBC_CAP 3072     // compact filterbank entries kept in shared memory (standard 40-mel bank: 493)
+#define FE_FBC_CAP 1024     // compact filterbank entries kept in shared memory (standard 40-mel bank: 493, VTLP worst ~750)
+#define FE_MAXU 128         // work units of the mel contraction: a filter span, or half of a span longer than 16 bins
+#define FE_LANE_UNITS 8     // units one lane may own
 #define FE_LOG_EPS 1e-7f
 
 struct FeParams {
@@ -26,6 +28,7 @@ struct FeParams {
   const int* fb_lo;       // [M]
   const int* fb_hi;       // [M]
   const int* fb_off;      // [M + 1]
+  const int* mel_plan;    // balanced work plan built by fb_compact_kernel (layout: FePlan)
   const float* window;
   const float2* tw256;
   const float2* tw512;
@@ -38,11 +41,22 @@ struct FeParams {
   int use_tma;
 };
 
+// Balanced plan of the sparse mel contraction.  A unit = bins [lo, hi) of one filter (spans longer than 16 bins are cut
+// in two); units are dealt to the 32 lanes longest-first onto the least loaded lane, so a frame costs ~nnz/32 + a few
+// iterations per lane instead of the longest span plus the tail round.
+struct FePlan {
+  int n_units;
+  int u_lo[FE_MAXU], u_hi[FE_MAXU], u_off[FE_MAXU];     // bin range and offset of the unit's first weight in fbc
+  int mel_unit[HOWL_MAX_MELS][2];                       // units of every filter (-1 = none)
+  int lane_n[32];
+  int lane_unit[32][FE_LANE_UNITS];
+};
+
 // ---------------------------------------------------------------------------------------------
 // compact filterbank: [lo, hi) non-zero span per column + prefix offsets.  One block, M threads.
 // ---------------------------------------------------------------------------------------------
 __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __restrict__ lo, int* __restrict__ hi,
-                                  int* __restrict__ off, float* __restrict__ fbc) {
+                                  int* __restrict__ off, float* __restrict__ fbc, FePlan* __restrict__ plan) {
   __shared__ int s_len[HOWL_MAX_MELS];
   __shared__ int s_off[HOWL_MAX_MELS + 1];
   const int m = threadIdx.x;
@@ -75,6 +89,40 @@ __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __re
     for (int j = l; j < h; ++j) fbc[s_off[m] + (j - l)] = fb[j * M + m];
   }
   if (m == 0) off[M] = s_off[M];
+  __syncthreads();
+  if (m == 0) {   // tiny serial planner (<= 256 units, 32 lanes)
+    int n = 0;
+    for (int i = 0; i < M; ++i) {
+      const int l = lo[i], h = hi[i], len = h - l;
+      plan->mel_unit[i][0] = plan->mel_unit[i][1] = -1;
+      if (len <= 0) continue;
+      const int cut = (len > 16 && n + 2 <= FE_MAXU) ? l + len / 2 : h;
+      plan->u_lo[n] = l; plan->u_hi[n] = cut; plan->u_off[n] = s_off[i];
+      plan->mel_unit[i][0] = n++;
+      if (cut < h) {
+        plan->u_lo[n] = cut; plan->u_hi[n] = h; plan->u_off[n] = s_off[i] + (cut - l);
+        plan->mel_unit[i][1] = n++;
+      }
+    }
+    plan->n_units = n;
+    int load[32];
+    bool used[FE_MAXU];
+    for (int i = 0; i < 32; ++i) { load[i] = 0; plan->lane_n[i] = 0; }
+    for (int i = 0; i < n; ++i) used[i] = false;
+    for (int it = 0; it < n; ++it) {
+      int best = -1, blen = -1;
+      for (int i = 0; i < n; ++i) {
+        const int len = plan->u_hi[i] - plan->u_lo[i];
+        if (!used[i] && len > blen) { blen = len; best = i; }
+      }
+      used[best] = true;
+      int lane = 0;
+      for (int i = 1; i < 32; ++i)
+        if (plan->lane_n[i] < FE_LANE_UNITS && (plan->lane_n[lane] >= FE_LANE_UNITS || load[i] < load[lane])) lane = i;
+      plan->lane_unit[lane][plan->lane_n[lane]++] = best;
+      load[lane] += blen + 2;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -154,7 +202,9 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FeParams p) 
   int* s_lo = reinterpret_cast<int*>(s_res + FE_TILE * p.M);
   int* s_hi = s_lo + HOWL_MAX_MELS;
   int* s_off = s_hi + HOWL_MAX_MELS;
+  float* s_upart = reinterpret_cast<float*>(s_off + HOWL_MAX_MELS + 4);     // [FE_WARPS][FE_MAXU] unit partial sums
   __shared__ __align__(8) uint64_t s_bar;
+  const FePlan* plan = reinterpret_cast<const FePlan*>(p.mel_plan);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = blockIdx.y;
@@ -214,6 +264,9 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FeParams p) 
   for (int fi = warp; fi < nfr; fi += FE_WARPS) {
     const int f = f0 + fi;
     const int64_t start = (int64_t)f * p.hop - HOWL_NFFT / 2;  // first sample of the frame (may be < 0)
+    const bool interior = (start >= 0) && (start + HOWL_NFFT <= T);   // no reflection: plain 64-bit vector loads
+    const float2* fr2 = reinterpret_cast<const float2*>(s_pcm + (interior ? (int)(start - lo) : 0));
+    const float2* win2 = reinterpret_cast<const float2*>(s_win);
     // ---- pass 0 (NS = 1, no twiddles) straight from the staged PCM: z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1]
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -222,12 +275,17 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FeParams p) 
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int n = j + 64 * r;
-        int64_t sa = start + 2 * n, sb = sa + 1;
-        if (sa < 0) sa = -sa;
-        if (sb < 0) sb = -sb;
-        if (sa >= T) sa = 2 * (T - 1) - sa;
-        if (sb >= T) sb = 2 * (T - 1) - sb;
-        v[r] = make_float2(s_pcm[sa - lo] * s_win[2 * n], s_pcm[sb - lo] * s_win[2 * n + 1]);
+        if (interior) {
+          const float2 x = fr2[n], w = win2[n];
+          v[r] = make_float2(x.x * w.x, x.y * w.y);
+        } else {
+          int64_t sa = start + 2 * n, sb = sa + 1;
+          if (sa < 0) sa = -sa;
+          if (sb < 0) sb = -sb;
+          if (sa >= T) sa = 2 * (T - 1) - sa;
+          if (sb >= T) sb = 2 * (T - 1) - sb;
+          v[r] = make_float2(s_pcm[sa - lo] * s_win[2 * n], s_pcm[sb - lo] * s_win[2 * n + 1]);
+        }
       }
       const float2 t0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
       const float2 t1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
@@ -260,15 +318,26 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FeParams p) 
       }
     }
     __syncwarp();
-    // ---- sparse mel contraction + log + zmuv + mask
-    for (int m = lane; m < p.M; m += 32) {
-      const int jl = s_lo[m], jh = s_hi[m], off = s_off[m];
-      float acc = 0.f;
-      for (int j = jl; j < jh; ++j) {
-        const int e = off + (j - jl);
-        const float w = (e < FE_FBC_CAP) ? s_fbc[e] : __ldg(p.fbc + e);
-        acc = fmaf(pw[j], w, acc);
+    // ---- sparse mel contraction (balanced units) + log + zmuv + mask
+    float* up = s_upart + warp * FE_MAXU;
+    {
+      const int nu = plan->lane_n[lane];
+      for (int q = 0; q < nu; ++q) {
+        const int u = plan->lane_unit[lane][q];
+        const int jl = plan->u_lo[u], jh = plan->u_hi[u], off = plan->u_off[u];
+        float acc = 0.f;
+        for (int j = jl; j < jh; ++j) {
+          const int e = off + (j - jl);
+          const float w = (e < FE_FBC_CAP) ? s_fbc[e] : __ldg(p.fbc + e);
+          acc = fmaf(pw[j], w, acc);
+        }
+        up[u] = acc;
       }
+    }
+    __syncwarp();
+    for (int m = lane; m < p.M; m += 32) {
+      const int u0 = plan->mel_unit[m][0], u1 = plan->mel_unit[m][1];
+      float acc = (u0 >= 0 ? up[u0] : 0.f) + (u1 >= 0 ? up[u1] : 0.f);
       float v = logf(acc + FE_LOG_EPS);
       if (do_zmuv) v = __fdiv_rn(v - p.zmean, p.zstd);
       if (masked && ((m >= rf0 && m < rf0 + rfl) || (f >= rt0 && f < rt0 + rtl))) v = 0.f;
@@ -391,6 +460,7 @@ static int fe_scratch(howl_ctx_t* ctx) {
     HOWL_CUDA(ctx, cudaMalloc(&ctx->fb_hi, sizeof(int) * HOWL_MAX_MELS));
     HOWL_CUDA(ctx, cudaMalloc(&ctx->fb_off, sizeof(int) * (HOWL_MAX_MELS + 1)));
     HOWL_CUDA(ctx, cudaMalloc(&ctx->fbc, sizeof(float) * HOWL_NFREQ * HOWL_MAX_MELS));
+    HOWL_CUDA(ctx, cudaMalloc(&ctx->mel_plan, sizeof(FePlan)));
   }
   return HOWL_OK;
 }
@@ -405,6 +475,7 @@ size_t howl_fe_smem_bytes(int hop, int M) {
   b += sizeof(float2) * FE_WARPS * 512;
   b += sizeof(float) * FE_TILE * M;
   b += sizeof(int) * (3 * HOWL_MAX_MELS + 4);
+  b += sizeof(float) * FE_WARPS * FE_MAXU;
   return howl_align_up(b, 16);
 }
 
@@ -428,11 +499,12 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
   const int F = (int)F64;
   int rc = fe_scratch(ctx);
   if (rc) return rc;
-  fb_compact_kernel<<<1, HOWL_MAX_MELS, 0, st>>>(fb, M, ctx->fb_lo, ctx->fb_hi, ctx->fb_off, ctx->fbc);
+  fb_compact_kernel<<<1, HOWL_MAX_MELS, 0, st>>>(fb, M, ctx->fb_lo, ctx->fb_hi, ctx->fb_off, ctx->fbc,
+                                                 reinterpret_cast<FePlan*>(ctx->mel_plan));
   HOWL_LAUNCHED(ctx, "fb_compact");
 
   FeParams p;
-  p.pcm = pcm; p.fb = fb; p.fbc = ctx->fbc; p.fb_lo = ctx->fb_lo; p.fb_hi = ctx->fb_hi; p.fb_off = ctx->fb_off;
+  p.pcm = pcm; p.fb = fb; p.fbc = ctx->fbc; p.fb_lo = ctx->fb_lo; p.fb_hi = ctx->fb_hi; p.fb_off = ctx->fb_off; p.mel_plan = ctx->mel_plan;
   p.window = ctx->d_window; p.tw256 = ctx->d_tw256; p.tw512 = ctx->d_tw512;
   p.rects = rects; p.out = out; p.B = B; p.T = T; p.F = F; p.M = M; p.hop = hop;
   p.zmean = zmuv_mean; p.zstd = zmuv_std; p.flags = flags;

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
 // loop), the 5x6 input patch of a pooled pixel is a shared-memory broadcast, G = ga (+ gb) is staged per utterance.
 #define C0B_GROUPS 6
 #define C0B_THREADS (C0B_GROUPS * 48)
-__global__ void __launch_bounds__(C0B_THREADS) conv0_bwd_kernel(const float* __restrict__ feats,
+__global__ void __launch_bounds__(C0B_THREADS, 3) conv0_bwd_kernel(const float* __restrict__ feats,
                                                                  const float* __restrict__ w0,
                                                                  const float* __restrict__ ga,
                                                                  const float* __restrict__ gb, float* __restrict__ dw0,
