@@ -105,17 +105,25 @@ __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __re
       }
     }
     plan->n_units = n;
+    // longest-first order by a counting sort on the span length (<= 257), then greedy onto the least loaded lane
     int load[32];
-    bool used[FE_MAXU];
-    for (int i = 0; i < 32; ++i) { load[i] = 0; plan->lane_n[i] = 0; }
-    for (int i = 0; i < n; ++i) used[i] = false;
-    for (int it = 0; it < n; ++it) {
-      int best = -1, blen = -1;
-      for (int i = 0; i < n; ++i) {
-        const int len = plan->u_hi[i] - plan->u_lo[i];
-        if (!used[i] && len > blen) { blen = len; best = i; }
+    short order[FE_MAXU];
+    short cnt[HOWL_NFREQ + 2];
+    for (int i = 0; i < HOWL_NFREQ + 2; ++i) cnt[i] = 0;
+    for (int i = 0; i < n; ++i) cnt[plan->u_hi[i] - plan->u_lo[i]]++;
+    {
+      int pos = 0;
+      for (int len = HOWL_NFREQ + 1; len >= 0; --len) {
+        const int c = cnt[len];
+        cnt[len] = (short)pos;
+        pos += c;
       }
-      used[best] = true;
+    }
+    for (int i = 0; i < n; ++i) order[cnt[plan->u_hi[i] - plan->u_lo[i]]++] = (short)i;
+    for (int i = 0; i < 32; ++i) { load[i] = 0; plan->lane_n[i] = 0; }
+    for (int it = 0; it < n; ++it) {
+      const int best = order[it];
+      const int blen = plan->u_hi[best] - plan->u_lo[best];
       int lane = 0;
       for (int i = 1; i < 32; ++i)
         if (plan->lane_n[i] < FE_LANE_UNITS && (plan->lane_n[lane] >= FE_LANE_UNITS || load[i] < load[lane])) lane = i;
