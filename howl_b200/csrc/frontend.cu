@@ -58,6 +58,7 @@ struct FePlan {
 __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __restrict__ lo, int* __restrict__ hi,
                                   int* __restrict__ off, float* __restrict__ fbc, FePlan* __restrict__ plan) {
   __shared__ int s_len[HOWL_MAX_MELS];
+  __shared__ int s_lo2[HOWL_MAX_MELS];
   __shared__ int s_off[HOWL_MAX_MELS + 1];
   const int m = threadIdx.x;
   int l = 0, h = 0;
@@ -73,6 +74,7 @@ __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __re
     lo[m] = l;
     hi[m] = h;
     s_len[m] = h - l;
+    s_lo2[m] = l;
   }
   __syncthreads();
   if (m == 0) {
@@ -90,10 +92,12 @@ __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __re
   }
   if (m == 0) off[M] = s_off[M];
   __syncthreads();
-  if (m == 0) {   // tiny serial planner (<= 256 units, 32 lanes)
+  __shared__ FePlan s_plan;      // planned in shared memory (one thread, no global-latency chain), copied out by all
+  if (m == 0) {   // tiny serial planner (<= 128 units, 32 lanes)
+    FePlan* plan = &s_plan;
     int n = 0;
     for (int i = 0; i < M; ++i) {
-      const int l = lo[i], h = hi[i], len = h - l;
+      const int l = s_lo2[i], h = s_lo2[i] + s_len[i], len = s_len[i];
       plan->mel_unit[i][0] = plan->mel_unit[i][1] = -1;
       if (len <= 0) continue;
       const int cut = (len > 16 && n + 2 <= FE_MAXU) ? l + len / 2 : h;
@@ -130,6 +134,12 @@ __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __re
       plan->lane_unit[lane][plan->lane_n[lane]++] = best;
       load[lane] += blen + 2;
     }
+  }
+  __syncthreads();
+  {
+    const int* src = reinterpret_cast<const int*>(&s_plan);
+    int* dst = reinterpret_cast<int*>(plan);
+    for (int i = threadIdx.x; i < (int)(sizeof(FePlan) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
   }
 }
 
