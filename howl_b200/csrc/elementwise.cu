@@ -76,3 +76,37 @@ extern "C" int howl_b200_to_time_major(howl_ctx_t* ctx, void* stream, const floa
   HOWL_LAUNCHED(ctx, "to_time_major");
   return HOWL_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// batch gather: the data movement of WakeWordFrameBatchifier.__call__ + tensorize_audio_data
+// (howl/data/transform/batchifier.py:56-118, operator.py:89-109) once the host has drawn the plan: row r of the batch is
+// counts[r] samples starting at clips[starts[r]], placed at column dst_off[r] of a zero row of max_length samples.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) batch_gather_kernel(const float* __restrict__ clips, const int64_t* __restrict__ starts,
+                                                           const int64_t* __restrict__ counts,
+                                                           const int64_t* __restrict__ dst_off, int64_t max_length,
+                                                           float* __restrict__ out) {
+  const int64_t r = blockIdx.y;
+  const int64_t n = counts[r], d0 = dst_off[r];
+  const float* src = clips + starts[r];
+  float* dst = out + r * max_length;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < max_length; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i - d0;
+    dst[i] = (j >= 0 && j < n) ? __ldg(src + j) : 0.f;
+  }
+}
+
+extern "C" int howl_b200_batch_gather(howl_ctx_t* ctx, void* stream, const float* clips, const int64_t* starts,
+                                      const int64_t* counts, const int64_t* dst_off, int64_t B, int64_t max_length,
+                                      float* out) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, clips && starts && counts && dst_off && out, HOWL_E_INVALID, "batch_gather: null pointer");
+  HOWL_REQUIRE(ctx, B >= 0 && B <= 65535 && max_length >= 0, HOWL_E_INVALID, "batch_gather: bad shape");
+  if (B == 0 || max_length == 0) return HOWL_OK;
+  int64_t bx = howl_ceil_div(max_length, 256 * 4);
+  if (bx > 64) bx = 64;
+  batch_gather_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(clips, starts, counts, dst_off,
+                                                                                        max_length, out);
+  HOWL_LAUNCHED(ctx, "batch_gather");
+  return HOWL_OK;
+}

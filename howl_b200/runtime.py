@@ -151,6 +151,16 @@ class Context:
         self._rc(self.lib.howl_b200_to_time_major(self.handle, self._stream(), _ptr(x), b, c, m, f, _ptr(out)), "to_time_major")
         return out
 
+    def batch_gather(self, clips: torch.Tensor, starts: torch.Tensor, counts: torch.Tensor, dst_off: torch.Tensor,
+                     max_length: int) -> torch.Tensor:
+        _check(clips, torch.float32, self.device, "clips")
+        for name, t in (("starts", starts), ("counts", counts), ("dst_off", dst_off)):
+            _check(t, torch.int64, self.device, name)
+        out = torch.empty(starts.numel(), max_length, dtype=torch.float32, device=self.device)
+        self._rc(self.lib.howl_b200_batch_gather(self.handle, self._stream(), _ptr(clips), _ptr(starts), _ptr(counts),
+                                                 _ptr(dst_off), starts.numel(), max_length, _ptr(out)), "batch_gather")
+        return out
+
     # ------------------------------------------------------------------ res8
     def res8_param_count(self, num_labels: int) -> int:
         return int(self.lib.howl_b200_res8_param_count(num_labels))

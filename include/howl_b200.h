@@ -106,6 +106,12 @@ int howl_b200_spec_mask(howl_ctx_t* ctx, void* stream, float* x, int64_t B, int3
 int howl_b200_to_time_major(howl_ctx_t* ctx, void* stream, const float* x, int64_t B, int32_t C, int32_t M, int32_t F,
                             float* out);
 
+/* Data movement of WakeWordFrameBatchifier / tensorize_audio_data (howl/data/transform/batchifier.py:56-118,
+ * operator.py:89-109) for a plan drawn on the host: out[r] (max_length samples, zero filled) receives counts[r] samples of
+ * `clips` starting at absolute offset starts[r], at column dst_off[r].  All index arrays [B] i64 on the device. */
+int howl_b200_batch_gather(howl_ctx_t* ctx, void* stream, const float* clips, const int64_t* starts, const int64_t* counts,
+                           const int64_t* dst_off, int64_t B, int64_t max_length, float* out);
+
 /* ---- res8 ----------------------------------------------------------------------------------- */
 /* Flat parameter layout (state_dict order):
  *   conv0.weight[45,1,3,3] | conv1..6.weight[45,45,3,3] | output.weight[L,45] | output.bias[L]

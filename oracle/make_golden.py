@@ -291,6 +291,32 @@ def main():
             ls[f"ctc.step{stp}.sd.{k}"] = v.detach().numpy().copy()
     np.savez_compressed(os.path.join(OUT, "lstm.npz"), **ls)
 
+    # ------------------------------------------------------------------ WakeWordFrameBatchifier (batchifier.py:37-118)
+    from howl.data.common.example import WakeWordClipExample
+    from howl.data.common.label import FrameLabelData
+    from howl.data.common.metadata import AudioClipMetadata
+    from howl.data.transform.batchifier import WakeWordFrameBatchifier
+
+    bt = {}
+    rngb = np.random.default_rng(17)
+    maps = [{}, {300.0: 0, 650.0: 1}, {420.5: 2}, {}, {100.0: 0, 480.0: 1, 900.0: 2}, {250.0: 1}, {}, {700.0: 0, 1500.0: 2}]
+    lens = [16000, 16000, 9000, 3000, 20000, 5000, 8000, 30000]
+    clips_np = [rngb.standard_normal(n).astype(np.float32) * 0.1 for n in lens]
+    exs = [WakeWordClipExample(FrameLabelData(m, [], []), AudioClipMetadata(path=".", phone_strings=None, words=None,
+                                                                            phone_end_timestamps=None, end_timestamps=None,
+                                                                            transcription=""),
+                               torch.from_numpy(c), 16000) for m, c in zip(maps, clips_np)]
+    bt["clips"] = np.concatenate(clips_np)
+    bt["lengths"] = np.array(lens)
+    meta["batchifier_maps"] = [[[k, v] for k, v in m.items()] for m in maps]   # insertion order matters (random.choice)
+    for trial in range(6):
+        random.seed(100 + trial)
+        fb_ = WakeWordFrameBatchifier(3, positive_sample_prob=[0.5, 0.9, 0.1][trial % 3])
+        out = fb_(exs * 2)
+        bt[f"t{trial}.audio"], bt[f"t{trial}.labels"] = out.audio_data.numpy(), out.labels.numpy()
+        bt[f"t{trial}.lengths"] = out.lengths.numpy()
+    np.savez_compressed(os.path.join(OUT, "batchifier.npz"), **bt)
+
     # ------------------------------------------------------------------ label-sequence FSM (host logic) cases
     from howl.model.inference import InferenceEngine
 

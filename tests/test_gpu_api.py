@@ -149,3 +149,22 @@ def test_frame_inference_engine_known_answers(golden, batched):
         detected = engine.infer_batched(audio) if batched else engine.infer(audio)
         assert detected == meta[name]["detected"]
         assert [int(l) for _, l in engine.label_history] == meta[name]["labels"]
+
+
+def test_device_batchifier_matches_reference_batches():
+    """clips resident in HBM, plan drawn on the host with the reference's draws, one gather kernel."""
+    import howl_b200
+    from howl_b200.batchifier import DeviceFrameBatchifier
+    from test_host_logic import _batchifier_inputs
+
+    g, clips = _batchifier_inputs()
+    ctx = howl_b200.Context(DEV, n_mels=40)
+    dev_clips = torch.from_numpy(g["clips"]).to(DEV)
+    for trial in range(6):
+        random.seed(100 + trial)
+        b = DeviceFrameBatchifier(3, positive_sample_prob=[0.5, 0.9, 0.1][trial % 3])
+        audio, labels, lengths = b(ctx, dev_clips, clips * 2)
+        assert np.array_equal(audio.cpu().numpy(), g[f"t{trial}.audio"])
+        assert np.array_equal(labels.cpu().numpy(), g[f"t{trial}.labels"])
+        assert np.array_equal(lengths.cpu().numpy(), g[f"t{trial}.lengths"])
+    ctx.close()

@@ -128,3 +128,36 @@ def test_data_parallel_step_gloo_world2(tmp_path):
                          timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "DP_OK" in out.stdout
+
+
+def _batchifier_inputs():
+    import json as _json
+
+    from howl_b200.batchifier import ClipRef
+
+    g = dict(np.load(os.path.join(GOLDEN, "batchifier.npz")))
+    maps = _json.load(open(os.path.join(GOLDEN, "meta.json")))["batchifier_maps"]
+    offs = np.concatenate([[0], np.cumsum(g["lengths"])])
+    clips = [ClipRef(int(offs[i]), int(g["lengths"][i]), {float(k): v for k, v in maps[i]}) for i in range(len(maps))]
+    return g, clips
+
+
+def test_frame_batchifier_plan_is_bit_exact_with_reference():
+    """WakeWordFrameBatchifier on seeded global `random`: window indices, labels, pad side and row order must reproduce the
+    reference batch exactly (integer index math; the gather is emulated with numpy here, the CUDA kernel in the GPU suite)."""
+    import random
+
+    from howl_b200.batchifier import DeviceFrameBatchifier
+
+    g, clips = _batchifier_inputs()
+    for trial in range(6):
+        random.seed(100 + trial)
+        b = DeviceFrameBatchifier(3, positive_sample_prob=[0.5, 0.9, 0.1][trial % 3])
+        starts, counts, dst, labels, max_length = b.plan(clips * 2)
+        assert max_length == 8000
+        out = np.zeros((len(starts), max_length), np.float32)
+        for r in range(len(starts)):
+            out[r, dst[r]:dst[r] + counts[r]] = g["clips"][starts[r]:starts[r] + counts[r]]
+        assert np.array_equal(labels, g[f"t{trial}.labels"])
+        assert np.array_equal(counts, g[f"t{trial}.lengths"])
+        assert np.array_equal(out, g[f"t{trial}.audio"])
