@@ -57,15 +57,18 @@ struct FePlan {
 // ---------------------------------------------------------------------------------------------
 __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __restrict__ lo, int* __restrict__ hi,
                                   int* __restrict__ off, float* __restrict__ fbc, FePlan* __restrict__ plan) {
+  extern __shared__ float s_fb[];              // the whole [257][M] bank, staged once with coalesced loads
   __shared__ int s_len[HOWL_MAX_MELS];
   __shared__ int s_lo2[HOWL_MAX_MELS];
+  for (int i = threadIdx.x; i < HOWL_NFREQ * M; i += blockDim.x) s_fb[i] = fb[i];
+  __syncthreads();
   __shared__ int s_off[HOWL_MAX_MELS + 1];
   const int m = threadIdx.x;
   int l = 0, h = 0;
   if (m < M) {
     l = HOWL_NFREQ;
     for (int j = 0; j < HOWL_NFREQ; ++j) {
-      if (fb[j * M + m] != 0.f) {
+      if (s_fb[j * M + m] != 0.f) {
         if (j < l) l = j;
         h = j + 1;
       }
@@ -88,7 +91,7 @@ __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __re
   __syncthreads();
   if (m < M) {
     off[m] = s_off[m];
-    for (int j = l; j < h; ++j) fbc[s_off[m] + (j - l)] = fb[j * M + m];
+    for (int j = l; j < h; ++j) fbc[s_off[m] + (j - l)] = s_fb[j * M + m];
   }
   if (m == 0) off[M] = s_off[M];
   __syncthreads();
@@ -517,7 +520,9 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
   const int F = (int)F64;
   int rc = fe_scratch(ctx);
   if (rc) return rc;
-  fb_compact_kernel<<<1, HOWL_MAX_MELS, 0, st>>>(fb, M, ctx->fb_lo, ctx->fb_hi, ctx->fb_off, ctx->fbc,
+  const size_t fbsm = sizeof(float) * HOWL_NFREQ * M;
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(fb_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fbsm));
+  fb_compact_kernel<<<1, HOWL_MAX_MELS, fbsm, st>>>(fb, M, ctx->fb_lo, ctx->fb_hi, ctx->fb_off, ctx->fbc,
                                                  reinterpret_cast<FePlan*>(ctx->mel_plan));
   HOWL_LAUNCHED(ctx, "fb_compact");
 
