@@ -16,6 +16,7 @@
 #include "common.cuh"
 
 #include "res8_common.cuh"
+#include "tc_common.cuh"
 
 // =============================================================================================
 // workspace carve-up
@@ -36,6 +37,9 @@ struct R8Ws {
   float* g;
   float* dc;
   float* gu[2];
+  __nv_bfloat16* uop[R8_LAYERS];   // a0, u1..u5 in operand format (tensor-core engine; null when H is unsupported)
+  float* fold_bias;    // [6][48]
+  void* fold_halo;     // [6][12] x 16 B
   size_t bytes;
 };
 
@@ -68,6 +72,10 @@ static R8Ws r8_carve(void* base, int64_t B, int H, int L) {
   }
   w.gu[0] = (float*)take(n);
   w.gu[1] = (float*)take(n);
+  w.fold_bias = (float*)take(sizeof(float) * R8_LAYERS * 48);
+  w.fold_halo = take((size_t)R8_LAYERS * 12 * 16);
+  for (int i = 0; i < R8_LAYERS; ++i)
+    w.uop[i] = r8tc_supported(H) ? (__nv_bfloat16*)take((size_t)B * r8tc_uop_bytes(H)) : nullptr;
   w.bytes = off;
   return w;
 }
@@ -94,13 +102,22 @@ __device__ __forceinline__ void c0_stage_tile(float* s_x, const float* __restric
 
 __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __restrict__ feats,
                                                                  const float* __restrict__ w0, float* __restrict__ a0,
-                                                                 int F, int H) {
+                                                                 uint4* __restrict__ a0_op, int Rx, int F, int H) {
   extern __shared__ __align__(16) float smem[];
   const int rows = 3 * H + 2;
   float* s_x = smem;
   float* s_w = smem + rows * C0_STRIDE;
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
+  uint4* op = a0_op ? a0_op + (size_t)b * 12 * Rx : nullptr;   // operand-format copy: raster row q at row q + 12
+  if (op) {
+    for (int r = tid; r < Rx; r += C0_THREADS) {                // guard and halo rows are zero
+      const int q = r - 12, y = q / 11 - 1, x = q % 11 - 1;
+      if (q >= 0 && y >= 0 && y < H && x >= 0 && x < R8_W) continue;
+#pragma unroll
+      for (int g = 0; g < 12; ++g) op[g * Rx + r] = make_uint4(0, 0, 0, 0);
+    }
+  }
   for (int i = tid; i < R8_C * 9; i += C0_THREADS) s_w[i] = __ldg(w0 + i);
   c0_stage_tile(s_x, feats + b * (int64_t)F * R8_MELS, F, rows, tid, C0_THREADS);
   __syncthreads();
@@ -113,7 +130,20 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
 #pragma unroll
       for (int c = 0; c < 6; ++c) patch[r][c] = s_x[(3 * h + r) * C0_STRIDE + 4 * w + c];
     float* dst = a0 + (b * R8_C) * (int64_t)HW + pp;
-    for (int oc = 0; oc < R8_C; ++oc) {
+    float ov[8];
+#pragma unroll 1
+    for (int oc = 0; oc < 48; ++oc) {
+      if (oc >= R8_C) {
+        ov[oc & 7] = (oc == R8_C) ? 1.f : 0.f;   // channel 45 = ones (weight-gradient BatchNorm fold), 46 / 47 padding
+        if (oc == 47 && op) {
+          uint4 hi, lo;
+          tc::split8(ov, hi, lo);
+          const int r = 12 + (h + 1) * 11 + (w + 1);
+          op[5 * Rx + r] = hi;
+          op[11 * Rx + r] = lo;
+        }
+        continue;
+      }
       float wk[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) wk[k] = s_w[oc * 9 + k];
@@ -129,7 +159,16 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
             for (int kx = 0; kx < 3; ++kx) pre = fmaf(wk[ky * 3 + kx], patch[py + ky][px + kx], pre);
           sum += fmaxf(pre, 0.f);
         }
-      dst[(int64_t)oc * HW] = __fdiv_rn(sum, 12.f);
+      const float o = __fdiv_rn(sum, 12.f);
+      dst[(int64_t)oc * HW] = o;
+      ov[oc & 7] = o;
+      if ((oc & 7) == 7 && op) {
+        uint4 hi, lo;
+        tc::split8(ov, hi, lo);
+        const int r = 12 + (h + 1) * 11 + (w + 1);
+        op[(oc >> 3) * Rx + r] = hi;
+        op[(6 + (oc >> 3)) * Rx + r] = lo;
+      }
     }
   }
 }
@@ -765,7 +804,9 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   {
     const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + R8_C * 9);
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, ws.a0, frames, H);
+    const bool op = ctx->conv_engine == 1 && r8tc_supported(H);
+    conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, ws.a0, op ? reinterpret_cast<uint4*>(ws.uop[0]) : nullptr,
+                                                          r8tc_uop_rows(H), frames, H);
     HOWL_LAUNCHED(ctx, "conv0_pool");
   }
   if (train) {
@@ -779,8 +820,9 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
   const int grid = r8_grid(ctx, B);
   const double count = (double)B * HW;
-  const bool use_tc = ctx->conv_engine == 1 && r8tc_supported(H);
-  if (use_tc) {
+  const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(H);
+  const bool gen2 = use_tc && ctx->conv_engine == 1;     // operand-format activations + BatchNorm folded into the weights
+  if (use_tc && !gen2) {
     rc = r8tc_weight_prep(ctx, st, wl, ws.wprep, 0);
     if (rc) return rc;
   }
@@ -797,8 +839,23 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     p.out = ws.u[i - 1];
     p.B = B;
     p.H = H;
-    const __nv_bfloat16* whi = ws.wprep + ((size_t)((i - 1) * 2 + 0) * 2) * R8TC_WBLOCK;
-    if (train) {
+    __nv_bfloat16* whi = ws.wprep + ((size_t)((i - 1) * 2 + 0) * 2) * R8TC_WBLOCK;
+    if (gen2) {
+      if (train) p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
+      float* bias = ws.fold_bias + (i - 1) * 48;
+      void* halo = (char*)ws.fold_halo + (size_t)(i - 1) * 12 * 16;
+      rc = r8tc_fold(ctx, st, p.w, i > 1 ? p.in_mean : nullptr, whi, whi + R8TC_WBLOCK, bias, halo);
+      if (rc) return rc;
+      rc = r8tc_fwd_op(ctx, st, p, ws.uop[i - 1], i < R8_LAYERS ? ws.uop[i] : nullptr, whi, whi + R8TC_WBLOCK, bias, halo,
+                       train ? 1 : 0);
+      if (rc) return rc;
+      if (train) {
+        bn_finalize_kernel<<<1, 64, 0, st>>>(p.stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C,
+                                             bn_running + (i - 1) * 2 * R8_C,
+                                             num_batches_tracked ? num_batches_tracked + (i - 1) : nullptr);
+        HOWL_LAUNCHED(ctx, "bn_finalize");
+      }
+    } else if (train) {
       p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
       if (use_tc) {
         rc = r8tc_conv(ctx, st, p, whi, whi + R8TC_WBLOCK, true, 1);
@@ -846,7 +903,8 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.stats_bwd, 0, sizeof(double) * R8_LAYERS * 2 * R8_C, st));
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * 2, st));
 
-  const bool use_tc = ctx->conv_engine == 1 && r8tc_supported(frames / 3);
+  const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(frames / 3);
+  const bool gen2 = use_tc && ctx->conv_engine == 1;
   if (use_tc) {
     rc = r8tc_weight_prep(ctx, st, wl, ws.wprep, 1);
     if (rc) return rc;
@@ -917,7 +975,10 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     wg.dw = g_wl + (size_t)(i - 1) * R8_KW;
     wg.B = B;
     wg.H = H;
-    if (use_tc) {
+    if (gen2) {
+      rc = r8tc_wgrad_op(ctx, st, wg.dc_op, ws.uop[i - 1], wg.x_mean, wg.x_rstd, wg.dw, B, H);
+      if (rc) return rc;
+    } else if (use_tc) {
       rc = r8tc_wgrad(ctx, st, wg);
       if (rc) return rc;
     } else {

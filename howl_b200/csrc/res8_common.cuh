@@ -73,5 +73,14 @@ struct ApplyOpParams {
   double count;
 };
 int r8tc_apply(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p);
+// operand-format activations ("u_op"): dc_op layout with 12 guard rows before and after (row stride Kp + 24)
+size_t r8tc_uop_bytes(int H);
+int r8tc_uop_rows(int H);
+int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* whi,
+              __nv_bfloat16* wlo, float* bias, void* halo);
+int r8tc_wgrad_op(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, const __nv_bfloat16* x_op, const float* x_mean,
+                  const float* x_rstd, float* dw, int64_t B, int H);
+int r8tc_fwd_op(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* in_op, __nv_bfloat16* out_op,
+                const __nv_bfloat16* whi, const __nv_bfloat16* wlo, const float* bias, const void* halo, int stats);
 int r8tc_dgrad(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* dc_op, const __nv_bfloat16* whi,
                const __nv_bfloat16* wlo, int stats);

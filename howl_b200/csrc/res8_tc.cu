@@ -68,7 +68,14 @@ static size_t tc_wgrad_smem(int H, int* Kp_out, int* Rx_out) {
   return (operand > need_a ? operand : need_a) + tc_slot_bytes(H) + 128 * 4;
 }
 
-bool r8tc_supported(int H) { return tc_geom(H).U > 0 && tc_wgrad_smem(H, nullptr, nullptr) <= TC_SMEM_LIMIT; }
+static size_t tc_fwd_op_smem(int H) {
+  const int Kp = ((H + 2) * TC_PITCH + 15) & ~15;
+  return 2 * (size_t)TC_WBYTES + 2 * (size_t)12 * (Kp + 24) * 16 + 128 * 16 + (48 + 8 * 2 * 24) * 4 + 12 * 16;
+}
+bool r8tc_supported(int H) {
+  return tc_geom(H).U > 0 && tc_wgrad_smem(H, nullptr, nullptr) <= TC_SMEM_LIMIT && tc_fwd_op_smem(H) <= TC_SMEM_LIMIT &&
+         TC_PITCH * H - 1 <= 3 * 128;
+}
 
 // =============================================================================================
 // weight operands: W fp32 [6][45 o][45 c][3][3] -> bf16 (hi, lo) [tap][chunk][48 n][8 k]
@@ -909,5 +916,455 @@ int r8tc_dgrad(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv
     conv3x3_dgrad_tc_kernel<0><<<grid, TCD_THREADS, smem, st>>>(a);
   }
   HOWL_LAUNCHED(ctx, "conv3x3_dgrad_tc");
+  return HOWL_OK;
+}
+
+// =============================================================================================
+// Forward, second generation: activations are ALSO kept in operand format ("u_op": per utterance
+// [hi,lo][6 chunks][Rx = Kp + 24 rows][8 bf16], raster row q at row q + 12, channel 45 = 1 at valid pixels, halo rows 0),
+// written by the producer's epilogue.  BatchNorm of the producer is folded into the consumer:
+//     conv_W( (u - mean) * rstd, zero padded ) = conv_{W'}( u with halo := mean ) + bias,
+//     W'[o][c] = W[o][c] * rstd[c],   bias[o] = - sum_{c,tap} W'[o][c][tap] * mean[c]
+// so the forward needs no transform either: TMA lands the raw operand tile, the workers only overwrite the ~50 halo rows
+// with split(mean), and the rest is the double-buffered pipeline of the data-gradient kernel.
+// =============================================================================================
+int r8tc_uop_rows(int H) { return r8tc_dcop_rows(H) + 24; }
+size_t r8tc_uop_bytes(int H) { return (size_t)12 * r8tc_uop_rows(H) * 16; }
+
+// per layer: folded (hi, lo) weights in the operand layout, bias[48], halo rows (split mean) [2][6] x 16 B
+__global__ void tc_fold_kernel(const float* __restrict__ w, const float* __restrict__ mean_rstd,
+                               __nv_bfloat16* __restrict__ whi, __nv_bfloat16* __restrict__ wlo, float* __restrict__ bias,
+                               uint4* __restrict__ halo) {
+  __shared__ float s_mu[48], s_rs[48];
+  const int tid = threadIdx.x;
+  if (tid < 48) {
+    const bool ok = tid < R8_C && mean_rstd != nullptr;
+    s_mu[tid] = ok ? mean_rstd[tid] : 0.f;
+    s_rs[tid] = (tid < R8_C) ? (mean_rstd ? mean_rstd[R8_C + tid] : 1.f) : 0.f;
+  }
+  __syncthreads();
+  for (int r = tid; r < R8TC_WBLOCK; r += blockDim.x) {
+    const int j = r & 7, n = (r >> 3) % TC_N, chunk = ((r >> 3) / TC_N) % 6, tap = (r >> 3) / (TC_N * 6);
+    const int c = chunk * 8 + j;
+    float v = 0.f;
+    if (n < R8_C && c < R8_C) v = w[(n * R8_C + c) * 9 + tap] * s_rs[c];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    whi[r] = hi;
+    wlo[r] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+  if (tid < 48) {
+    double b = 0.0;
+    if (tid < R8_C)
+      for (int c = 0; c < R8_C; ++c) {
+        double s = 0.0;
+        for (int tap = 0; tap < 9; ++tap) s += (double)w[(tid * R8_C + c) * 9 + tap];
+        b -= s * (double)s_rs[c] * (double)s_mu[c];
+      }
+    bias[tid] = (float)b;
+  }
+  if (tid < 6) {
+    float v[8];
+    for (int j = 0; j < 8; ++j) v[j] = s_mu[tid * 8 + j];     // channels 45..47 (incl. the ones channel) have mean 0
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    halo[tid] = hi;
+    halo[6 + tid] = lo;
+  }
+}
+
+struct TcFwdArgs {
+  ConvParams p;                  // out (planar fp32), res, stats; p.in unused
+  const __nv_bfloat16* in_op;    // u_{i-1} in operand format
+  __nv_bfloat16* out_op;         // u_i in operand format, or null (eval)
+  const __nv_bfloat16* whi;      // folded weights of this layer
+  const __nv_bfloat16* wlo;
+  const float* bias;             // [48]
+  const uint4* halo;             // [2][6]
+  int Kp, Rx, tiles;
+};
+
+template <int STATS>
+__global__ void __launch_bounds__(TCD_THREADS, 1) conv3x3_fwd_op_tc_kernel(const TcFwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const ConvParams& p = a.p;
+  const int H = p.H, HW = H * R8_W, Kp = a.Kp, Rx = a.Rx, tiles = a.tiles;
+  const uint32_t op_bytes = (uint32_t)(12 * Rx * 16);
+  uint4* w_hi = reinterpret_cast<uint4*>(smem);
+  uint4* w_lo = reinterpret_cast<uint4*>(smem + TC_WBYTES);
+  unsigned char* a_buf = smem + 2 * TC_WBYTES;                          // 2 x [hi 6][lo 6][Rx] + tail pad
+  float* s_f = reinterpret_cast<float*>(a_buf + 2 * (size_t)op_bytes + 128 * 16);
+  float* s_bias = s_f;           // [48]
+  float* s_red = s_f + 48;       // [8 warps][2][24]
+  uint4* s_halo = reinterpret_cast<uint4*>(s_f + 48 + 8 * 2 * 24);      // [2][6]
+  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_halo[2], bar_tile[2][3], bar_free[2];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (warp == 8) {
+    tc::tmem_alloc<512>(&s_tmem);
+    if (lane == 0) {
+      tc::mbar_init(&bar_w, 1);
+      for (int i = 0; i < 2; ++i) {
+        tc::mbar_init(&bar_a[i], 1);
+        tc::mbar_init(&bar_halo[i], 8);
+        tc::mbar_init(&bar_free[i], 8);
+        for (int t = 0; t < 3; ++t) tc::mbar_init(&bar_tile[i][t], 1);
+      }
+      tc::fence_barrier_init();
+    }
+  }
+  for (int i = tid; i < 128; i += TCD_THREADS) reinterpret_cast<uint4*>(a_buf + 2 * (size_t)op_bytes)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 48) s_bias[tid] = a.bias[tid];
+  if (tid < 12) s_halo[tid] = a.halo[tid];
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  const int64_t n_local = (p.B - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp == 8) {
+    // ================= producer / issuer warp =================
+    const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.in_op);
+    if (tc::elect_one()) {
+      auto load_op = [&](int64_t k) {
+        const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
+        tc::mbar_expect_tx(&bar_a[k & 1], op_bytes);
+        tc::tma_bulk_g2s(a_buf + (size_t)(k & 1) * op_bytes, src0 + (size_t)b * op_bytes, op_bytes, &bar_a[k & 1]);
+      };
+      tc::mbar_expect_tx(&bar_w, 2 * TC_WBYTES);
+      tc::tma_bulk_g2s(w_hi, a.whi, TC_WBYTES, &bar_w);
+      tc::tma_bulk_g2s(w_lo, a.wlo, TC_WBYTES, &bar_w);
+      if (n_local > 0) load_op(0);
+      if (n_local > 1) load_op(1);
+      tc::mbar_wait(&bar_w, 0);
+      const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 0, 0);
+      const uint32_t w_hi_s = tc::smem_u32(w_hi), w_lo_s = tc::smem_u32(w_lo);
+      const uint32_t bh_lo = tc::desc_lo(w_hi_s, TC_N * 16u), bl_lo = tc::desc_lo(w_lo_s, TC_N * 16u);
+      const uint32_t d_hi128 = tc::desc_hi(128u);
+      const uint32_t a_base = tc::smem_u32(a_buf);
+      for (int64_t k = 0; k < n_local; ++k) {
+        const int buf = (int)(k & 1);
+        const uint32_t par = (uint32_t)((k >> 1) & 1);
+        tc::mbar_wait(&bar_halo[buf], par);                    // operand tile landed AND halo rows rewritten by the workers
+        if (k >= 2) tc::mbar_wait(&bar_free[buf], par ^ 1u);   // epilogue of utterance k-2 has drained this TMEM half
+        tc::fence_after_sync();
+        const uint32_t a_hi_s = a_base + (uint32_t)buf * op_bytes, a_lo_s = a_hi_s + (uint32_t)(6 * Rx * 16);
+        const uint32_t ah_lo = tc::desc_lo(a_hi_s, (uint32_t)Rx * 16u), al_lo = tc::desc_lo(a_lo_s, (uint32_t)Rx * 16u);
+        for (int t = 0; t < tiles; ++t) {
+          const uint32_t d = tmem + (uint32_t)(buf * 256 + t * TC_N);
+          const uint32_t rowb = (uint32_t)(12 + TC_Q0 + 128 * t);      // raster row q lives at operand row q + 12
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+              const uint32_t aoff = (uint32_t)(2 * ks) * (uint32_t)Rx + rowb + (uint32_t)shift;
+              const uint32_t boff = (uint32_t)((tap * 6 + 2 * ks) * TC_N);
+              const uint64_t ah = tc::desc_make(ah_lo + aoff, d_hi128), al = tc::desc_make(al_lo + aoff, d_hi128);
+              const uint64_t bh = tc::desc_make(bh_lo + boff, d_hi128), bl = tc::desc_make(bl_lo + boff, d_hi128);
+              tc::umma_bf16(d, al, bh, idesc, (tap | ks) ? 1u : 0u);
+              tc::umma_bf16(d, ah, bl, idesc, 1u);
+              tc::umma_bf16(d, ah, bh, idesc, 1u);
+            }
+          }
+          tc::umma_commit(&bar_tile[buf][t]);
+        }
+        if (k >= 1 && k + 1 < n_local) {
+          tc::mbar_wait(&bar_tile[buf ^ 1][tiles - 1], (uint32_t)(((k - 1) >> 1) & 1));
+          load_op(k + 1);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= workers: halo rows of the NEXT operand tile, then the epilogue of the current one =================
+    const int half = warp >> 2;
+    float st1[24], st2[24];
+#pragma unroll
+    for (int c = 0; c < 24; ++c) st1[c] = st2[c] = 0.f;
+    auto fill_halo = [&](int64_t k) {     // utterance k of this CTA: wait for its TMA, overwrite the invalid raster rows with mean
+      const int buf = (int)(k & 1);
+      tc::mbar_wait(&bar_a[buf], (uint32_t)((k >> 1) & 1));
+      uint4* hi = reinterpret_cast<uint4*>(a_buf + (size_t)buf * op_bytes);
+      uint4* lo = hi + 6 * Rx;
+      for (int q = tid; q < Kp; q += TC_WORKERS) {
+        const int y = q / TC_PITCH - 1, x = q % TC_PITCH - 1;
+        if (y >= 0 && y < H && x >= 0 && x < R8_W) continue;
+#pragma unroll
+        for (int ch = 0; ch < 6; ++ch) {
+          hi[ch * Rx + 12 + q] = s_halo[ch];
+          lo[ch * Rx + 12 + q] = s_halo[6 + ch];
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_halo[buf]);
+    };
+    if (n_local > 0) fill_halo(0);
+    for (int64_t k = 0; k < n_local; ++k) {
+      const int buf = (int)(k & 1);
+      const uint32_t par = (uint32_t)((k >> 1) & 1);
+      const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
+      if (k + 1 < n_local) fill_halo(k + 1);
+      uint4* o_hi = a.out_op ? reinterpret_cast<uint4*>(a.out_op) + (size_t)b * 12 * Rx : nullptr;
+      if (o_hi) {   // guard rows the tile threads never reach
+        for (int i = tid; i < 24 * 12; i += TC_WORKERS) o_hi[(i / 24) * Rx + (i % 24)] = make_uint4(0, 0, 0, 0);
+      }
+      for (int t = 0; t < tiles; ++t) {
+        const int q = TC_Q0 + 128 * t + 32 * (warp & 3) + lane;
+        const int y = q / TC_PITCH - 1, x = q % TC_PITCH - 1;
+        const bool valid = (y >= 0) && (y < H) && (x >= 0) && (x < R8_W);
+        const int64_t base = valid ? b * (int64_t)R8_C * HW + y * R8_W + x : 0;
+        const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * 256 + t * TC_N + 24 * half);
+        float pre[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+          const int c = 24 * half + j;
+          pre[j] = (p.res && c < R8_C && valid) ? __ldg(p.res + base + (int64_t)c * HW) : 0.f;
+        }
+        tc::mbar_wait(&bar_tile[buf][t], par);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          float v[8], ov[8];
+          tc::tmem_ld8(taddr + 8 * cb, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int jj = cb * 8 + j, c = 24 * half + jj;
+            float o = 0.f;
+            if (valid && c < R8_C) {
+              o = fmaxf(v[j] + s_bias[c], 0.f) + pre[jj];
+              p.out[base + (int64_t)c * HW] = o;
+              if (STATS == 1) {
+                st1[jj] += o;
+                st2[jj] = fmaf(o, o, st2[jj]);
+              }
+            } else if (valid && c == R8_C) {
+              o = 1.f;                      // the "ones" channel: lets the weight gradient fold BatchNorm (sum of dC per tap)
+            }
+            ov[j] = o;
+          }
+          if (o_hi && q + 12 < Rx) {
+            uint4 hi, lo;
+            tc::split8(ov, hi, lo);
+            const int ch = 3 * half + cb;
+            o_hi[ch * Rx + 12 + q] = hi;
+            o_hi[(6 + ch) * Rx + 12 + q] = lo;
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_free[buf]);
+    }
+    if (STATS) {
+#pragma unroll
+      for (int j = 0; j < 24; ++j) {
+        const float a1 = warp_sum(st1[j]), a2 = warp_sum(st2[j]);
+        if (lane == 0) {
+          s_red[(warp * 2 + 0) * 24 + j] = a1;
+          s_red[(warp * 2 + 1) * 24 + j] = a2;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (STATS && tid < 2 * R8_C) {
+    const int which = tid / R8_C, c = tid - which * R8_C, half = c / 24, j = c - 24 * half;
+    double s = 0.0;
+    for (int w = 4 * half; w < 4 * half + 4; ++w) s += (double)s_red[(w * 2 + which) * 24 + j];
+    atomicAdd(&p.stats[tid], s);
+  }
+  if (warp == 8) tc::tmem_dealloc<512>(tmem);
+}
+
+int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* whi,
+              __nv_bfloat16* wlo, float* bias, void* halo) {
+  tc_fold_kernel<<<1, 512, 0, st>>>(w_layer, mean_rstd, whi, wlo, bias, reinterpret_cast<uint4*>(halo));
+  HOWL_LAUNCHED(ctx, "tc_fold");
+  return HOWL_OK;
+}
+
+int r8tc_fwd_op(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* in_op, __nv_bfloat16* out_op,
+                const __nv_bfloat16* whi, const __nv_bfloat16* wlo, const float* bias, const void* halo, int stats) {
+  TcFwdArgs a;
+  a.p = p;
+  a.in_op = in_op; a.out_op = out_op; a.whi = whi; a.wlo = wlo; a.bias = bias; a.halo = reinterpret_cast<const uint4*>(halo);
+  a.Kp = r8tc_dcop_rows(p.H);
+  a.Rx = r8tc_uop_rows(p.H);
+  a.tiles = (TC_PITCH * p.H - 1 + 127) / 128;
+  HOWL_REQUIRE(ctx, a.tiles <= 3, HOWL_E_UNSUPPORTED, "tensor-core forward: H=%d needs more than 3 tiles", p.H);
+  const size_t smem = 2 * (size_t)TC_WBYTES + 2 * r8tc_uop_bytes(p.H) + 128 * 16 + (48 + 8 * 2 * 24) * 4 + 12 * 16;
+  HOWL_REQUIRE(ctx, smem <= TC_SMEM_LIMIT, HOWL_E_UNSUPPORTED, "tensor-core forward: H=%d does not fit", p.H);
+  const int grid = (int)(p.B < ctx->sm_count ? p.B : ctx->sm_count);
+  if (stats) {
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_fwd_op_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_fwd_op_tc_kernel<1><<<grid, TCD_THREADS, smem, st>>>(a);
+  } else {
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_fwd_op_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_fwd_op_tc_kernel<0><<<grid, TCD_THREADS, smem, st>>>(a);
+  }
+  HOWL_LAUNCHED(ctx, "conv3x3_fwd_tc");
+  return HOWL_OK;
+}
+
+// =============================================================================================
+// Weight gradient, second generation: BOTH operands arrive by TMA in operand format (dC from the BatchNorm-backward
+// kernel, X = u_op from the forward), so there is no staging or transform and the eight epilogue warps sleep until the
+// accumulators are final.  X is double buffered; dC is single buffered but split in two K halves that are issued
+// half-outer, so the next utterance's first half lands while the second half of this one is being multiplied.
+// BatchNorm of X is folded into the epilogue through the "ones" channel (column 45 of every tap):
+//     dW[o][c] = rstd[c] * ( sum_q dC[q][o] X[q+s][c]  -  mean[c] * sum_q dC[q][o] 1[q+s] )
+// =============================================================================================
+struct TcWgrad2Args {
+  const __nv_bfloat16* dc_op;
+  const __nv_bfloat16* x_op;
+  const float* x_mean;   // or null (layer 1: X = a0, no normalisation)
+  const float* x_rstd;
+  float* dw;
+  int64_t B;
+  int Kp, Rx, Kh;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_op_tc_kernel(const TcWgrad2Args a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int Kp = a.Kp, Rx = a.Rx, Kh = a.Kh;
+  const uint32_t x_bytes = (uint32_t)(12 * Rx * 16);
+  unsigned char* d_buf = smem;                                   // [hi 6 | lo 6][Kp] x 16 B; M groups 12..15 run into x_buf
+  unsigned char* x_buf = smem + (size_t)12 * Kp * 16;            // 2 x [hi 6 | lo 6][Rx] x 16 B
+  __shared__ __align__(8) uint64_t bar_x[2], bar_d[2], bar_h[2];
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (warp == 8) {
+    tc::tmem_alloc<512>(&s_tmem);
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        tc::mbar_init(&bar_x[i], 1);
+        tc::mbar_init(&bar_d[i], 1);
+        tc::mbar_init(&bar_h[i], 1);
+      }
+      tc::fence_barrier_init();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  const int64_t n_local = (a.B - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp == 8) {
+    if (tc::elect_one() && n_local > 0) {
+      const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(a.x_op);
+      const unsigned char* dsrc = reinterpret_cast<const unsigned char*>(a.dc_op);
+      const uint32_t d_bytes = (uint32_t)(12 * Kp * 16);
+      auto load_x = [&](int64_t k) {
+        const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
+        tc::mbar_expect_tx(&bar_x[k & 1], x_bytes);
+        tc::tma_bulk_g2s(x_buf + (size_t)(k & 1) * x_bytes, xsrc + (size_t)b * x_bytes, x_bytes, &bar_x[k & 1]);
+      };
+      auto load_d = [&](int64_t k, int hf) {     // K rows [hf * Kh, hf ? Kp : Kh) of all twelve 8-channel groups
+        const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
+        const uint32_t r0 = hf ? (uint32_t)Kh : 0u, nr = hf ? (uint32_t)(Kp - Kh) : (uint32_t)Kh;
+        tc::mbar_expect_tx(&bar_d[hf], 12u * nr * 16u);
+        for (uint32_t g = 0; g < 12; ++g)
+          tc::tma_bulk_g2s(d_buf + ((size_t)g * Kp + r0) * 16, dsrc + (size_t)b * d_bytes + ((size_t)g * Kp + r0) * 16, nr * 16u,
+                           &bar_d[hf]);
+      };
+      load_x(0);
+      load_d(0, 0);
+      load_d(0, 1);
+      if (n_local > 1) load_x(1);
+      const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 1, 1);   // both operands MN-major (K = raster positions)
+      const uint32_t d_s = tc::smem_u32(d_buf), x_s = tc::smem_u32(x_buf);
+      const uint32_t ad_lo = tc::desc_lo(d_s, 128u), ad_hi = tc::desc_hi((uint32_t)Kp * 16u);
+      const uint32_t b_hi = tc::desc_hi((uint32_t)Rx * 16u);
+      for (int64_t k = 0; k < n_local; ++k) {
+        const uint32_t par = (uint32_t)(k & 1);
+        const uint32_t xh_s = x_s + (uint32_t)(k & 1) * x_bytes;
+        const uint32_t bh_lo = tc::desc_lo(xh_s, 128u), bl_lo = tc::desc_lo(xh_s + (uint32_t)(6 * Rx * 16), 128u);
+        tc::mbar_wait(&bar_x[k & 1], (uint32_t)((k >> 1) & 1));
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          if (hf == 1 && k > 0) {
+            // utterance k-1 is completely multiplied (its MMAs precede this one's first half in the pipe): its second dC half
+            // and its X buffer are free.  Both loads land while the first half of utterance k is being multiplied.
+            tc::mbar_wait(&bar_h[1], par ^ 1u);
+            load_d(k, 1);
+            if (k + 1 < n_local) load_x(k + 1);
+          }
+          tc::mbar_wait(&bar_d[hf], par);
+          tc::fence_after_sync();
+          const int kb = hf ? Kh : 0, ke = hf ? Kp : Kh;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
+            const uint32_t d = tmem + (uint32_t)(tap * TC_N);
+            uint32_t acc = (k == 0 && hf == 0) ? 0u : 1u;
+#pragma unroll 2
+            for (int k0 = kb; k0 < ke; k0 += 16) {
+              const uint64_t ad = tc::desc_make(ad_lo + (uint32_t)k0, ad_hi);
+              const uint32_t boff = (uint32_t)(12 + shift + k0);
+              tc::umma_bf16(d, ad, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
+              tc::umma_bf16(d, ad, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
+              acc = 1u;
+            }
+          }
+          tc::umma_commit(&bar_h[hf]);
+        }
+        // first half done -> its dC rows take utterance k+1's first half while the second half still multiplies
+        if (k + 1 < n_local) {
+          tc::mbar_wait(&bar_h[0], par);
+          load_d(k + 1, 0);
+        }
+      }
+      tc::mbar_wait(&bar_h[1], (uint32_t)((n_local - 1) & 1));
+    }
+    __syncwarp();
+  }
+  tc::fence_before_sync();
+  __syncthreads();          // the issuer arrives only after the last commit: every accumulator is final
+  tc::fence_after_sync();
+  if (n_local > 0 && warp < 8) {
+    const int r = 32 * (warp & 3) + lane;
+    const int o = r < 48 ? r : r - 48;
+    const bool ok = r < 96 && o < R8_C;
+    const int half = warp >> 2;                    // warps 0-3: taps 0..4, warps 4-7: taps 5..8
+    for (int tap = half ? 5 : 0; tap < (half ? 9 : 5); ++tap) {
+      const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(tap * TC_N);
+      float v[48];
+      tc::tmem_ld16(taddr, v);
+      tc::tmem_ld16(taddr + 16, v + 16);
+      tc::tmem_ld16(taddr + 32, v + 32);
+      if (ok) {
+        const float ones = v[R8_C];
+#pragma unroll
+        for (int c = 0; c < R8_C; ++c) {
+          const float mu = a.x_mean ? __ldg(a.x_mean + c) : 0.f, rs = a.x_rstd ? __ldg(a.x_rstd + c) : 1.f;
+          atomicAdd(&a.dw[(o * R8_C + c) * 9 + tap], rs * (v[c] - mu * ones));
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc<512>(tmem);
+}
+
+int r8tc_wgrad_op(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, const __nv_bfloat16* x_op, const float* x_mean,
+                  const float* x_rstd, float* dw, int64_t B, int H) {
+  TcWgrad2Args a;
+  a.dc_op = dc_op; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.B = B;
+  a.Kp = r8tc_dcop_rows(H);
+  a.Rx = r8tc_uop_rows(H);
+  a.Kh = (a.Kp / 32) * 16;
+  const size_t smem = (size_t)12 * a.Kp * 16 + 2 * r8tc_uop_bytes(H);
+  HOWL_REQUIRE(ctx, smem <= TC_SMEM_LIMIT && a.Kh >= 16, HOWL_E_UNSUPPORTED, "tensor-core wgrad: H=%d does not fit", H);
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_op_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)(B < ctx->sm_count ? B : ctx->sm_count);
+  conv3x3_wgrad_op_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+  HOWL_LAUNCHED(ctx, "conv3x3_wgrad_tc");
   return HOWL_OK;
 }
