@@ -192,6 +192,9 @@ def main_ours(args):
 
     step_obj = Res8TrainStep(dev, num_labels=NUM_LABELS, batch=B, samples=SAMPLES, n_mels=N_MELS, lr=LR, weight_decay=WD,
                              zmuv=(ZMEAN, ZSTD), seed=0, world_size=world)
+    for opt in ("conv_engine",):   # tuning experiments only
+        if os.environ.get("HOWL_" + opt.upper()):
+            step_obj.ctx.set_option(opt, int(os.environ["HOWL_" + opt.upper()]))
     ctx = step_obj.ctx
 
     def barrier():

@@ -40,6 +40,8 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
   ctx->sm_count = prop.multiProcessorCount;
   ctx->fe = *cfg;
   ctx->conv_engine = 1;
+  ctx->tc_prof = nullptr;
+  ctx->tc_prof_kind = 0;
   // tables in double, rounded once
   float win[HOWL_NFFT];
   float2 tw256[256], tw512[HOWL_NFREQ];
@@ -64,7 +66,7 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
 extern "C" int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return HOWL_E_INVALID;
   if (strcmp(name, "conv_engine") == 0) {
-    HOWL_REQUIRE(ctx, value >= 0 && value <= 2, HOWL_E_INVALID, "set_option: conv_engine must be 0 (fp32), 1 (tcgen05) or 2 (tcgen05, first generation)");
+    HOWL_REQUIRE(ctx, value == 0 || value == 1, HOWL_E_INVALID, "set_option: conv_engine must be 0 (fp32) or 1 (tcgen05)");
     ctx->conv_engine = (int)value;
     return HOWL_OK;
   }
@@ -134,5 +136,14 @@ static inline int64_t floor_div(int64_t a, int64_t b) {
 extern "C" int howl_b200_compute_lengths(const int64_t* lengths, int64_t n, int32_t win, int32_t hop, int64_t* out) {
   if (!lengths || !out || n < 0 || hop <= 0) return HOWL_E_INVALID;
   for (int64_t i = 0; i < n; ++i) out[i] = floor_div(lengths[i] - win, hop) + 1;
+  return HOWL_OK;
+}
+
+// Tuning aid, not part of the drop-in surface: the stream convolution kernels of the given kind (1 forward, 2 data gradient)
+// write their per-CTA pipeline-wait cycle counters to buf[sm_count][16] (device memory); null switches it off.
+extern "C" int howl_b200_debug_stream_profile(howl_ctx_t* ctx, void* buf, int32_t kind) {
+  if (!ctx) return HOWL_E_INVALID;
+  ctx->tc_prof = (unsigned long long*)buf;
+  ctx->tc_prof_kind = kind;
   return HOWL_OK;
 }

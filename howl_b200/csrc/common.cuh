@@ -27,7 +27,9 @@ struct howl_ctx {
   float* fbc;
   int* mel_plan;     // FePlan (frontend.cu)
   int64_t launches;
-  int conv_engine;   // 0 = fp32 FFMA kernels, 1 = tcgen05 bf16x3 kernels (default)
+  int conv_engine;
+  unsigned long long* tc_prof;   // tuning aid (howl_b200_debug_stream_profile): device buffer [sm_count][16] or null
+  int tc_prof_kind;              // 1 = forward, 2 = data gradient
   // optional per-launch timing
   int prof_on;
   int prof_n;

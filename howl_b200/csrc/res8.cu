@@ -38,8 +38,6 @@ struct R8Ws {
   float* dc;
   float* gu[2];
   __nv_bfloat16* uop[R8_LAYERS];   // a0, u1..u5 in operand format (tensor-core engine; null when H is unsupported)
-  float* fold_bias;    // [6][48]
-  void* fold_halo;     // [6][12] x 16 B
   size_t bytes;
 };
 
@@ -72,10 +70,8 @@ static R8Ws r8_carve(void* base, int64_t B, int H, int L) {
   }
   w.gu[0] = (float*)take(n);
   w.gu[1] = (float*)take(n);
-  w.fold_bias = (float*)take(sizeof(float) * R8_LAYERS * 48);
-  w.fold_halo = take((size_t)R8_LAYERS * 12 * 16);
   for (int i = 0; i < R8_LAYERS; ++i)
-    w.uop[i] = r8tc_supported(H) ? (__nv_bfloat16*)take((size_t)B * r8tc_uop_bytes(H)) : nullptr;
+    w.uop[i] = r8tc_supported(H) ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
   w.bytes = off;
   return w;
 }
@@ -109,11 +105,11 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
   float* s_w = smem + rows * C0_STRIDE;
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
-  uint4* op = a0_op ? a0_op + (size_t)b * 12 * Rx : nullptr;   // operand-format copy: raster row q at row q + 12
+  uint4* op = a0_op ? a0_op + (size_t)b * 12 * Rx : nullptr;   // operand-format copy (res8_common.cuh), Rx rows
   if (op) {
-    for (int r = tid; r < Rx; r += C0_THREADS) {                // guard and halo rows are zero
-      const int q = r - 12, y = q / 11 - 1, x = q % 11 - 1;
-      if (q >= 0 && y >= 0 && y < H && x >= 0 && x < R8_W) continue;
+    for (int r = tid; r < Rx; r += C0_THREADS) {                // rows outside the image are zero
+      const int y = r / 11 - 1, x = r % 11 - 1;
+      if (y >= 0 && y < H && x >= 0 && x < R8_W) continue;
 #pragma unroll
       for (int g = 0; g < 12; ++g) op[g * Rx + r] = make_uint4(0, 0, 0, 0);
     }
@@ -138,7 +134,7 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
         if (oc == 47 && op) {
           uint4 hi, lo;
           tc::split8(ov, hi, lo);
-          const int r = 12 + (h + 1) * 11 + (w + 1);
+          const int r = (h + 1) * 11 + (w + 1);
           op[5 * Rx + r] = hi;
           op[11 * Rx + r] = lo;
         }
@@ -165,7 +161,7 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
       if ((oc & 7) == 7 && op) {
         uint4 hi, lo;
         tc::split8(ov, hi, lo);
-        const int r = 12 + (h + 1) * 11 + (w + 1);
+        const int r = (h + 1) * 11 + (w + 1);
         op[(oc >> 3) * Rx + r] = hi;
         op[(6 + (oc >> 3)) * Rx + r] = lo;
       }
@@ -806,7 +802,7 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const bool op = ctx->conv_engine == 1 && r8tc_supported(H);
     conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, ws.a0, op ? reinterpret_cast<uint4*>(ws.uop[0]) : nullptr,
-                                                          r8tc_uop_rows(H), frames, H);
+                                                          r8tc_dcop_rows(H), frames, H);
     HOWL_LAUNCHED(ctx, "conv0_pool");
   }
   if (train) {
@@ -820,12 +816,7 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
   const int grid = r8_grid(ctx, B);
   const double count = (double)B * HW;
-  const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(H);
-  const bool gen2 = use_tc && ctx->conv_engine == 1;     // operand-format activations + BatchNorm folded into the weights
-  if (use_tc && !gen2) {
-    rc = r8tc_weight_prep(ctx, st, wl, ws.wprep, 0);
-    if (rc) return rc;
-  }
+  const bool use_tc = ctx->conv_engine == 1 && r8tc_supported(H);
   for (int i = 1; i <= R8_LAYERS; ++i) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -839,41 +830,24 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     p.out = ws.u[i - 1];
     p.B = B;
     p.H = H;
-    __nv_bfloat16* whi = ws.wprep + ((size_t)((i - 1) * 2 + 0) * 2) * R8TC_WBLOCK;
-    if (gen2) {
+    if (use_tc) {
+      // operand-format activations; BatchNorm of layer i-1 folded into this layer's weights (res8_tc.cu)
+      __nv_bfloat16* wblk = ws.wprep + ((size_t)((i - 1) * 2 + 0) * 2) * R8TC_WBLOCK;
       if (train) p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
-      float* bias = ws.fold_bias + (i - 1) * 48;
-      void* halo = (char*)ws.fold_halo + (size_t)(i - 1) * 12 * 16;
-      rc = r8tc_fold(ctx, st, p.w, i > 1 ? p.in_mean : nullptr, whi, whi + R8TC_WBLOCK, bias, halo);
+      rc = r8tc_fold(ctx, st, p.w, i > 1 ? p.in_mean : nullptr, wblk);
       if (rc) return rc;
-      rc = r8tc_fwd_op(ctx, st, p, ws.uop[i - 1], i < R8_LAYERS ? ws.uop[i] : nullptr, whi, whi + R8TC_WBLOCK, bias, halo,
-                       train ? 1 : 0);
-      if (rc) return rc;
-      if (train) {
-        bn_finalize_kernel<<<1, 64, 0, st>>>(p.stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C,
-                                             bn_running + (i - 1) * 2 * R8_C,
-                                             num_batches_tracked ? num_batches_tracked + (i - 1) : nullptr);
-        HOWL_LAUNCHED(ctx, "bn_finalize");
-      }
-    } else if (train) {
-      p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
-      if (use_tc) {
-        rc = r8tc_conv(ctx, st, p, whi, whi + R8TC_WBLOCK, true, 1);
-        if (rc) return rc;
-      } else {
-        conv3x3_kernel<true, 1><<<grid, CV_THREADS, csm, st>>>(p);
-        HOWL_LAUNCHED(ctx, "conv3x3_fwd");
-      }
-      bn_finalize_kernel<<<1, 64, 0, st>>>(p.stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C,
-                                           bn_running + (i - 1) * 2 * R8_C,
-                                           num_batches_tracked ? num_batches_tracked + (i - 1) : nullptr);
-      HOWL_LAUNCHED(ctx, "bn_finalize");
-    } else if (use_tc) {
-      rc = r8tc_conv(ctx, st, p, whi, whi + R8TC_WBLOCK, true, 0);
+      rc = r8tc_conv(ctx, st, p, ws.uop[i - 1], i < R8_LAYERS ? ws.uop[i] : nullptr, wblk, true, train ? 1 : 0);
       if (rc) return rc;
     } else {
-      conv3x3_kernel<true, 0><<<grid, CV_THREADS, csm, st>>>(p);
+      if (train) p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
+      if (train) conv3x3_kernel<true, 1><<<grid, CV_THREADS, csm, st>>>(p);
+      else conv3x3_kernel<true, 0><<<grid, CV_THREADS, csm, st>>>(p);
       HOWL_LAUNCHED(ctx, "conv3x3_fwd");
+    }
+    if (train) {
+      bn_finalize_kernel<<<1, 64, 0, st>>>(p.stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C, bn_running + (i - 1) * 2 * R8_C,
+                                           num_batches_tracked ? num_batches_tracked + (i - 1) : nullptr);
+      HOWL_LAUNCHED(ctx, "bn_finalize");
     }
   }
   head_fwd_kernel<<<(unsigned)B, 128, 0, st>>>(ws.u[5], ws.mean_rstd + 5 * 2 * R8_C, wout, bout, ws.pooled, logits,
@@ -903,10 +877,9 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.stats_bwd, 0, sizeof(double) * R8_LAYERS * 2 * R8_C, st));
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * 2, st));
 
-  const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(frames / 3);
-  const bool gen2 = use_tc && ctx->conv_engine == 1;
+  const bool use_tc = ctx->conv_engine == 1 && r8tc_supported(frames / 3);
   if (use_tc) {
-    rc = r8tc_weight_prep(ctx, st, wl, ws.wprep, 1);
+    rc = r8tc_weight_prep(ctx, st, wl, ws.wprep);
     if (rc) return rc;
     // halo rows of the operand-format gradient stay zero for all six layers
     HOWL_CUDA(ctx, cudaMemsetAsync(ws.dc, 0, (size_t)B * r8tc_dcop_bytes(frames / 3), st));
@@ -975,11 +948,8 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     wg.dw = g_wl + (size_t)(i - 1) * R8_KW;
     wg.B = B;
     wg.H = H;
-    if (gen2) {
-      rc = r8tc_wgrad_op(ctx, st, wg.dc_op, ws.uop[i - 1], wg.x_mean, wg.x_rstd, wg.dw, B, H);
-      if (rc) return rc;
-    } else if (use_tc) {
-      rc = r8tc_wgrad(ctx, st, wg);
+    if (use_tc) {
+      rc = r8tc_wgrad(ctx, st, wg.dc_op, ws.uop[i - 1], wg.x_mean, wg.x_rstd, wg.dw, B, H);
       if (rc) return rc;
     } else {
       conv3x3_wgrad_kernel<<<grid, WG_THREADS, wsm, st>>>(wg);
@@ -1000,8 +970,9 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
       p.aux_rstd = p.aux_mean + R8_C;
     }
     if (use_tc) {
-      const __nv_bfloat16* whi = ws.wprep + ((size_t)((i - 1) * 2 + 1) * 2) * R8TC_WBLOCK;
-      rc = r8tc_dgrad(ctx, st, p, reinterpret_cast<const __nv_bfloat16*>(ws.dc), whi, whi + R8TC_WBLOCK, i > 1 ? 2 : 0);
+      const __nv_bfloat16* wblk = ws.wprep + ((size_t)((i - 1) * 2 + 1) * 2) * R8TC_WBLOCK;
+      rc = r8tc_conv(ctx, st, p, reinterpret_cast<const __nv_bfloat16*>(ws.dc), nullptr, wblk, false,
+                     i > 1 ? 2 : 0);
       if (rc) return rc;
     } else {
       if (i > 1) conv3x3_kernel<false, 2><<<grid, CV_THREADS, csm, st>>>(p);

@@ -40,23 +40,19 @@ struct WgradParams {
   int H;
 };
 
-// tensor-core weight operands: per layer and direction (0 = forward, 1 = data gradient) a (hi, lo) pair of
-// [9 taps][6 chunks][48 out][8 in] bf16 blocks
+// tensor-core weight operands: per layer and direction (0 = forward with the producer's BatchNorm folded in, 1 = data
+// gradient) one bf16 block [9 taps][6 chunks][96 n: 48 hi | 48 lo][8 k]
 #define R8TC_WBLOCK (54 * 48 * 8)
 #define R8TC_WELEMS ((size_t)R8_LAYERS * 2 * 2 * R8TC_WBLOCK)
 
-int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __nv_bfloat16* wprep, int dir);
-int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* whi, const __nv_bfloat16* wlo,
-              bool relu, int stats);
-int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const WgradParams& p);
 bool r8tc_supported(int H);
 
-// Operand-format conv-output gradient ("dc_op"), written by the BatchNorm-backward kernel for the tensor-core engine and
-// consumed by TMA straight into the UMMA operand tiles of the data-gradient and weight-gradient kernels:
-//   per utterance [part: hi, lo][chunk of 8 channels: 6][raster row q: Kp][8 x bf16],  q = (y + 1) * 11 + (x + 1),
-//   Kp = round_up((H + 2) * 11, 16); halo rows are zero.
+// Operand format of every tensor the tensor-core convolutions read (activations "u_op", conv-output gradients "dc_op"),
+// landed by TMA straight into the UMMA operand tiles:
+//   per utterance [part: hi, lo][chunk of 8 channels: 6][raster row q: R][8 x bf16],  q = (y + 1) * 11 + (x + 1),
+//   R = round_up((H + 2) * 11, 64); rows outside the image are zero.  Channel 45 of u_op is 1 at the image pixels.
 size_t r8tc_dcop_bytes(int H);          // bytes per utterance
-int r8tc_dcop_rows(int H);              // Kp
+int r8tc_dcop_rows(int H);              // R
 
 struct ApplyOpParams {
   const float* g;          // dgrad output [B,45,HW], or null when g_bcast is used
@@ -73,14 +69,13 @@ struct ApplyOpParams {
   double count;
 };
 int r8tc_apply(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p);
-// operand-format activations ("u_op"): dc_op layout with 12 guard rows before and after (row stride Kp + 24)
-size_t r8tc_uop_bytes(int H);
-int r8tc_uop_rows(int H);
-int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* whi,
-              __nv_bfloat16* wlo, float* bias, void* halo);
-int r8tc_wgrad_op(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, const __nv_bfloat16* x_op, const float* x_mean,
-                  const float* x_rstd, float* dw, int64_t B, int H);
-int r8tc_fwd_op(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* in_op, __nv_bfloat16* out_op,
-                const __nv_bfloat16* whi, const __nv_bfloat16* wlo, const float* bias, const void* halo, int stats);
-int r8tc_dgrad(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* dc_op, const __nv_bfloat16* whi,
-               const __nv_bfloat16* wlo, int stats);
+// data-gradient weight operands of all six layers (direction 1 blocks of wprep)
+int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __nv_bfloat16* wprep);
+// forward weight operand of one layer with BatchNorm(mean_rstd, or identity when null) folded in (the border-dependent bias
+// rides on the ones channel)
+int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* blk);
+// forward (fwd, stats 0 / 1) or data gradient (!fwd, stats 0 / 2) of one layer; p.in is unused
+int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* in_op, __nv_bfloat16* out_op,
+              const __nv_bfloat16* w, bool fwd, int stats);
+int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, const __nv_bfloat16* x_op, const float* x_mean,
+               const float* x_rstd, float* dw, int64_t B, int H);

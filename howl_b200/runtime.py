@@ -78,6 +78,11 @@ class Context:
                                                   variant), "selftest_umma")
         return d
 
+    def debug_stream_profile(self, buf, kind: int):
+        """Tuning aid: per-CTA wait-cycle counters of the tensor-core conv kernels (kind 1 fwd, 2 dgrad) -> buf[sm][16] int64."""
+        self._rc(self.lib.howl_b200_debug_stream_profile(self.handle, _ptr(buf) if buf is not None else None, kind),
+                 "debug_stream_profile")
+
     def profile_begin(self):
         self._rc(self.lib.howl_b200_profile_begin(self.handle, self._stream()), "profile_begin")
 
@@ -285,6 +290,12 @@ class Context:
 
     def res8_train_step(self, pcm, labels, fb, zmuv, params, bn_running, nbt, grads, m, v, step, lr, weight_decay,
                         loss, logits, ws, rects=None):
+        _check(pcm, torch.float32, self.device, "pcm")
+        _check(labels, torch.int64, self.device, "labels")
+        for name, t_ in (("fb", fb), ("params", params), ("bn_running", bn_running), ("grads", grads), ("m", m), ("v", v)):
+            _check(t_, torch.float32, self.device, name)
+        if pcm.dim() != 2 or labels.numel() != pcm.shape[0]:
+            raise HowlB200Error("res8_train_step: pcm must be [B,T] and labels [B]")
         b, t = pcm.shape
         num_labels = self._labels_from_params(params)
         self._rc(self.lib.howl_b200_res8_train_step(

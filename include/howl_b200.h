@@ -66,6 +66,10 @@ int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value);
 int howl_b200_selftest_umma(howl_ctx_t* ctx, void* stream, const float* A, const float* B, float* D, int32_t mn_major,
                             int32_t variant);
 
+/* Tuning aid: the tensor-core forward (kind 1) or data-gradient (kind 2) kernels write per-CTA cycle counters of their
+ * pipeline waits to buf[sm_count][16] (uint64, device memory); buf = NULL switches it off.  See tests/profile_stream.py. */
+int howl_b200_debug_stream_profile(howl_ctx_t* ctx, void* buf, int32_t kind);
+
 /* ---- per-launch device timing (CUDA events on the launching stream; used by bench.py's roofline) --------- */
 /* After profile_begin every kernel launch of this context is bracketed by an event on `stream`. */
 int howl_b200_profile_begin(howl_ctx_t* ctx, void* stream);
