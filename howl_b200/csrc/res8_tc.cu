@@ -21,7 +21,7 @@
 #include "res8_common.cuh"
 #include "tc_common.cuh"
 
-#define TC_THREADS 288            // weight-gradient kernel: warps 0-7 epilogue, warp 8 TMA + MMA issue
+#define TC_THREADS 320            // weight-gradient kernel: warps 0-7 epilogue, warp 8 MMA issue, warp 9 TMA loader
 #define TS_THREADS 448            // stream kernel: warps 0-11 epilogue, warp 12 MMA issue, warp 13 TMA loader
 #define TS_EPI_WARPS 12
 #define TC_WORKERS 256
@@ -456,7 +456,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   const uint32_t tmem = s_tmem;
   const int64_t n_local = (a.B - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
-  if (warp == 8) {
+  if (warp == 9) {
+    // ================= TMA loader =================
     if (tc::elect_one() && n_local > 0) {
       const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(a.x_op);
       const unsigned char* dsrc = reinterpret_cast<const unsigned char*>(a.dc_op);
@@ -480,6 +481,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
       load_d(0, 0);
       load_d(0, 1);
       if (n_local > 1) load_x(1);
+      for (int64_t k = 0; k + 1 < n_local; ++k) {
+        const uint32_t par = (uint32_t)(k & 1);
+        tc::mbar_wait(&bar_h[0], par);          // first K half of utterance k multiplied: its dC rows take utterance k+1's
+        load_d(k + 1, 0);
+        tc::mbar_wait(&bar_h[1], par);          // utterance k completely multiplied: second dC half and its X buffer are free
+        load_d(k + 1, 1);
+        if (k + 2 < n_local) load_x(k + 2);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ================= MMA issuer =================
+    if (tc::elect_one() && n_local > 0) {
       const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 1, 1);   // both operands MN-major (K = raster positions)
       const uint32_t d_s = tc::smem_u32(d_buf), x_s = tc::smem_u32(x_buf);
       const uint32_t ad_lo = tc::desc_lo(d_s, 128u), ad_hi = tc::desc_hi((uint32_t)R * 16u);
@@ -491,13 +505,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
         tc::mbar_wait(&bar_x[k & 1], (uint32_t)((k >> 1) & 1));
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
-          if (hf == 1 && k > 0) {
-            // utterance k-1 is completely multiplied (its MMAs precede this one's first half in the pipe): its second dC half
-            // and its X buffer are free.  Both loads land while the first half of utterance k is being multiplied.
-            tc::mbar_wait(&bar_h[1], par ^ 1u);
-            load_d(k, 1);
-            if (k + 1 < n_local) load_x(k + 1);
-          }
           tc::mbar_wait(&bar_d[hf], par);
           tc::fence_after_sync();
           const int kb = hf ? Kh : 0, ke = hf ? R : Kh;
@@ -516,11 +523,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
             }
           }
           tc::umma_commit(&bar_h[hf]);
-        }
-        // first half done -> its dC rows take utterance k+1's first half while the second half still multiplies
-        if (k + 1 < n_local) {
-          tc::mbar_wait(&bar_h[0], par);
-          load_d(k + 1, 0);
         }
       }
       tc::mbar_wait(&bar_h[1], (uint32_t)((n_local - 1) & 1));
@@ -596,7 +598,20 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
              ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * i + 1])) << 16);
     return make_uint4(h[0], h[1], h[2], h[3]);
   };
-  if (!mn_major) {
+  if (mn_major == 2) {   // test 2: A K-major (copied to tensor memory with tcgen05.cp), B MN-major
+    for (int i = tid; i < 4 * 128; i += 128) {
+      const int chunk = i / 128, row = i % 128;
+      float v[8];
+      for (int j = 0; j < 8; ++j) v[j] = A[row * 32 + chunk * 8 + j];
+      sa[chunk * 128 + row] = pack(v);
+    }
+    for (int i = tid; i < 6 * 32; i += 128) {
+      const int chunk = i / 32, k = i % 32;
+      float v[8];
+      for (int j = 0; j < 8; ++j) v[j] = B[k * 48 + chunk * 8 + j];
+      sb[chunk * 32 + k] = pack(v);
+    }
+  } else if (!mn_major) {
     for (int i = tid; i < 4 * 128; i += 128) {
       const int chunk = i / 128, row = i % 128;
       float v[8];
@@ -633,6 +648,13 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     for (int ks = 0; ks < 2; ++ks) {
       uint64_t ad, bd;
       uint32_t idesc;
+      if (mn_major == 2) {
+        const uint32_t a_tmem = tmem + 48u + 8u * (uint32_t)ks;
+        tc::tmem_cp_128x256b(a_tmem, tc::smem_desc(sa_s + (2 * ks) * 128 * 16, 128 * 16, 128));
+        bd = tc::smem_desc(sb_s + ks * 16 * 16, 128, 32 * 16);
+        tc::umma_bf16_ts(tmem, a_tmem, bd, tc::instr_desc_bf16(128, 48, 0, 1), ks ? 1u : 0u);
+        continue;
+      }
       if (!mn_major) {
         uint32_t lbo_a = 128 * 16, sbo_a = 128, lbo_b = 48 * 16, sbo_b = 128;
         if (variant & 1) { uint32_t t = lbo_a; lbo_a = sbo_a; sbo_a = t; t = lbo_b; lbo_b = sbo_b; sbo_b = t; }

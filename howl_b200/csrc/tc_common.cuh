@@ -134,6 +134,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       : "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same MMA with the A operand (M x 16 bf16, row m in TMEM lane m, 8 x 32-bit columns) read from tensor memory instead of
+// shared memory; only K-major A exists in this form.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared memory -> tensor memory: 128 lanes x 256 bit (one M = 128, K = 16 bf16 A tile) from a K-major operand described like an
+// MMA operand (8-row x 16-byte core matrices; lbo = stride between the two 16-byte K chunks, sbo = stride between 8-row groups).
+// Ordered with the MMAs of the issuing thread (same pipe, issue order).
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t d_tmem, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(d_tmem), "l"(sdesc) : "memory");
+}
 // elect.sync: true in exactly one lane of the (converged) warp.  Branching on it lets ptxas treat the region as
 // single-threaded: descriptor arithmetic stays in the uniform datapath and UTCHMMA needs no per-instruction election.
 __device__ __forceinline__ bool elect_one() {

@@ -9,16 +9,19 @@ dev = torch.device("cuda:0")
 ctx = howl_b200.Context(dev)
 torch.manual_seed(0)
 sel = sys.argv[1] if len(sys.argv) > 1 else "all"
-cases = {"k0": [(0, 0)], "mn0": [(1, 0)], "mn1": [(1, 1)], "all": [(0, 0), (1, 0)], "conv": []}[sel]
+cases = {"k0": [(0, 0)], "mn0": [(1, 0)], "mn1": [(1, 1)], "ts": [(2, 0)], "all": [(0, 0), (1, 0)], "conv": []}[sel]
 for mn, variant in cases:
     if True:
-        if mn == 0:
+        if mn == 2:     # A [128][32] via tcgen05.cp into tensor memory, B [32][48] MN-major from shared memory
+            A = torch.randn(128, 32, device=dev); Bm = torch.randn(32, 48, device=dev)
+            ref = A.bfloat16().float() @ Bm.bfloat16().float()
+        elif mn == 0:
             A = torch.randn(128, 32, device=dev); Bm = torch.randn(48, 32, device=dev)
             ref = A.bfloat16().float() @ Bm.bfloat16().float().t()
         else:
             A = torch.randn(32, 128, device=dev); Bm = torch.randn(32, 48, device=dev)
             ref = A.bfloat16().float().t() @ Bm.bfloat16().float()
-        D = ctx.selftest_umma(A.contiguous(), Bm.contiguous(), bool(mn), variant)
+        D = ctx.selftest_umma(A.contiguous(), Bm.contiguous(), int(mn), variant)
         torch.cuda.synchronize()
         print(f"selftest mn_major={mn} variant={variant}: max err {(D - ref).abs().max().item():.3e} (ref scale {ref.abs().max().item():.2f})", flush=True)
 
