@@ -38,6 +38,7 @@ SIGNATURES: Dict[str, tuple] = {
     "howl_b200_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "howl_b200_selftest_umma": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32]),
     "howl_b200_debug_stream_profile": (C.c_int, [_vp, _vp, _i32]),
+    "howl_b200_debug_umma_bench": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "howl_b200_profile_begin": (C.c_int, [_vp, _vp]),
     "howl_b200_profile_end": (C.c_int, [_vp, _vp, _sz, _vp, _i32]),
     "howl_b200_num_frames": (_i64, [_i64, _i32]),

@@ -37,6 +37,7 @@ struct R8Ws {
   float* g;
   float* dc;
   float* gu[2];
+  __nv_bfloat16* dcT;              // conv-output gradient, rows = channels (weight-gradient operand of the tensor-core engine)
   __nv_bfloat16* uop[R8_LAYERS];   // a0, u1..u5 in operand format (tensor-core engine; null when H is unsupported)
   size_t bytes;
 };
@@ -70,6 +71,7 @@ static R8Ws r8_carve(void* base, int64_t B, int H, int L) {
   }
   w.gu[0] = (float*)take(n);
   w.gu[1] = (float*)take(n);
+  w.dcT = r8tc_supported(H) ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
   for (int i = 0; i < R8_LAYERS; ++i)
     w.uop[i] = r8tc_supported(H) ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
   w.bytes = off;
@@ -881,8 +883,6 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   if (use_tc) {
     rc = r8tc_weight_prep(ctx, st, wl, ws.wprep);
     if (rc) return rc;
-    // halo rows of the operand-format gradient stay zero for all six layers
-    HOWL_CUDA(ctx, cudaMemsetAsync(ws.dc, 0, (size_t)B * r8tc_dcop_bytes(frames / 3), st));
   } else {
     transpose_weights_kernel<<<(R8_LAYERS * R8_KW + 255) / 256, 256, 0, st>>>(wl, ws.wT);
     HOWL_LAUNCHED(ctx, "transpose_weights");
@@ -928,6 +928,7 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
       ao.g = a.g; ao.g_bcast = a.g_bcast; ao.u = a.u; ao.mean_rstd = a.mean_rstd; ao.stats = a.stats;
       ao.gu_in = a.gu_in; ao.mask_prev = a.mask_prev; ao.gu_out = a.gu_out;
       ao.dc_op = reinterpret_cast<__nv_bfloat16*>(ws.dc);
+      ao.dc_opT = ws.dcT;
       ao.B = B; ao.H = H; ao.count = count;
       rc = r8tc_apply(ctx, st, ao);
       if (rc) return rc;
@@ -949,7 +950,7 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     wg.B = B;
     wg.H = H;
     if (use_tc) {
-      rc = r8tc_wgrad(ctx, st, wg.dc_op, ws.uop[i - 1], wg.x_mean, wg.x_rstd, wg.dw, B, H);
+      rc = r8tc_wgrad(ctx, st, ws.dcT, ws.uop[i - 1], wg.x_mean, wg.x_rstd, wg.dw, B, H);
       if (rc) return rc;
     } else {
       conv3x3_wgrad_kernel<<<grid, WG_THREADS, wsm, st>>>(wg);

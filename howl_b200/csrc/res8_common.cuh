@@ -64,6 +64,7 @@ struct ApplyOpParams {
   const float* mask_prev;
   float* gu_out;
   __nv_bfloat16* dc_op;
+  __nv_bfloat16* dc_opT;   // the same gradient with rows = channels (weight-gradient A operand), r8tc_dcop_bytes per utterance
   int64_t B;
   int H;
   double count;
@@ -77,5 +78,5 @@ int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const floa
 // forward (fwd, stats 0 / 1) or data gradient (!fwd, stats 0 / 2) of one layer; p.in is unused
 int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* in_op, __nv_bfloat16* out_op,
               const __nv_bfloat16* w, bool fwd, int stats);
-int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, const __nv_bfloat16* x_op, const float* x_mean,
+int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_opT, const __nv_bfloat16* x_op, const float* x_mean,
                const float* x_rstd, float* dw, int64_t B, int H);

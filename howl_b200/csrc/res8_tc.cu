@@ -408,31 +408,36 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
 }
 
 // =============================================================================================
-// Weight gradient: both operands arrive by TMA in operand format (dC from the BatchNorm-backward kernel, X from the
-// forward), the eight epilogue warps sleep until the accumulators are final.  The M = 128 rows of the A operand are
-// [dC_hi (48) | dC_lo (48) | padding (32)] -- dC_lo sits exactly six 8-channel groups behind dC_hi -- so two MMAs per k-step
-// (x X_hi, x X_lo) produce all four partial products; the epilogue adds TMEM rows o and 48 + o.
-// X is double buffered; dC is single buffered but split in two K halves that are issued half-outer, so the next
-// utterance's first half lands while the second half of this one is being multiplied.
+// Weight gradient:  dW_tap[o][c] = sum_q dC[q][o] * X[q + shift_tap][c],  9 taps x 48 accumulator columns resident in TMEM
+// across all utterances of a CTA.  The kernel is bound by operand reads, and the A tile (dC, 128 x 16) is the same for all
+// nine taps and both halves of X -- so it is copied ONCE per 16-row K step from shared memory into tensor memory
+// (tcgen05.cp) and the 18 MMAs of the step read A from there; only the 48 x 16 X tiles stream out of shared memory.
+//   A rows (TMEM lanes): [dC_hi (48) | dC_lo (48) | 32 don't-care]  from dc_opT (rows = channels, K-major), one 128 x 256 bit copy
+//   B: X_lo then X_hi, MN-major straight from the operand-format activations (rows = raster positions, 12 guard rows)
+// so the four partial products land in rows o and 48 + o, which the epilogue adds.  Both operands arrive by TMA (a loader
+// warp refills the buffers the moment their last MMA has retired): X is double buffered; dC is single buffered but split in two
+// K halves, so the next utterance's first half lands while the second half of this one is being multiplied.
 // BatchNorm of X is folded into the epilogue through the "ones" channel (column 45 of every tap):
 //     dW[o][c] = rstd[c] * ( sum_q dC[q][o] X[q+s][c]  -  mean[c] * sum_q dC[q][o] 1[q+s] )
 // =============================================================================================
 struct TcWgradArgs {
-  const __nv_bfloat16* dc_op;
+  const __nv_bfloat16* dc_opT;
   const __nv_bfloat16* x_op;
   const float* x_mean;   // or null (layer 1: X = a0, no normalisation)
   const float* x_rstd;
   float* dw;
   int64_t B;
-  int R, Kh;
+  int R;
 };
+#define TW_ASLOTS 8          // ring of A tiles in tensor memory behind the 9 x 48 accumulator columns
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const TcWgradArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int R = a.R, Rx = R + 2 * TC_PAD, Kh = a.Kh;
-  const uint32_t x_bytes = (uint32_t)(12 * Rx * 16);
-  unsigned char* d_buf = smem;                                   // [hi 6 | lo 6][R] x 16 B; M groups 12..15 run into x_buf
-  unsigned char* x_buf = smem + (size_t)12 * R * 16;             // 2 x [hi 6 | lo 6][Rx] x 16 B, raster row q at row q + 12
+  const int R = a.R, Rx = R + 2 * TC_PAD, Kh = R / 2;
+  const uint32_t x_bytes = (uint32_t)(12 * Rx * 16), d_bytes = (uint32_t)(12 * R * 16);
+  unsigned char* d_buf = smem;                                   // [R / 8 row groups][96 channels][8 rows] bf16; the 128-row copy
+                                                                 // of the last group runs 512 B into x_buf (don't-care lanes)
+  unsigned char* x_buf = smem + d_bytes;                         // 2 x [hi 6 | lo 6][Rx] x 16 B, raster row q at row q + 12
   __shared__ __align__(8) uint64_t bar_x[2], bar_d[2], bar_h[2];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -460,22 +465,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
     // ================= TMA loader =================
     if (tc::elect_one() && n_local > 0) {
       const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(a.x_op);
-      const unsigned char* dsrc = reinterpret_cast<const unsigned char*>(a.dc_op);
-      const size_t utt_bytes = (size_t)12 * R * 16;
+      const unsigned char* dsrc = reinterpret_cast<const unsigned char*>(a.dc_opT);
       auto load_x = [&](int64_t k) {
         const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
-        tc::mbar_expect_tx(&bar_x[k & 1], (uint32_t)utt_bytes);
+        tc::mbar_expect_tx(&bar_x[k & 1], d_bytes);
         for (uint32_t g = 0; g < 12; ++g)
           tc::tma_bulk_g2s(x_buf + (size_t)(k & 1) * x_bytes + ((size_t)g * Rx + TC_PAD) * 16,
-                           xsrc + (size_t)b * utt_bytes + (size_t)g * R * 16, (uint32_t)(R * 16), &bar_x[k & 1]);
+                           xsrc + (size_t)b * d_bytes + (size_t)g * R * 16, (uint32_t)(R * 16), &bar_x[k & 1]);
       };
-      auto load_d = [&](int64_t k, int hf) {     // K rows [hf * Kh, hf ? R : Kh) of all twelve 8-channel groups
+      auto load_d = [&](int64_t k, int hf) {     // K rows [hf * Kh, (hf + 1) * Kh): contiguous in the transposed format
         const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
-        const uint32_t r0 = hf ? (uint32_t)Kh : 0u, nr = hf ? (uint32_t)(R - Kh) : (uint32_t)Kh;
-        tc::mbar_expect_tx(&bar_d[hf], 12u * nr * 16u);
-        for (uint32_t g = 0; g < 12; ++g)
-          tc::tma_bulk_g2s(d_buf + ((size_t)g * R + r0) * 16, dsrc + (size_t)b * utt_bytes + ((size_t)g * R + r0) * 16, nr * 16u,
-                           &bar_d[hf]);
+        tc::mbar_expect_tx(&bar_d[hf], d_bytes / 2);
+        tc::tma_bulk_g2s(d_buf + (size_t)hf * (d_bytes / 2), dsrc + (size_t)b * d_bytes + (size_t)hf * (d_bytes / 2), d_bytes / 2,
+                         &bar_d[hf]);
       };
       load_x(0);
       load_d(0, 0);
@@ -494,10 +496,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   } else if (warp == 8) {
     // ================= MMA issuer =================
     if (tc::elect_one() && n_local > 0) {
-      const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 1, 1);   // both operands MN-major (K = raster positions)
+      const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 0, 1);   // A K-major from tensor memory, B MN-major (K = raster rows)
       const uint32_t d_s = tc::smem_u32(d_buf), x_s = tc::smem_u32(x_buf);
-      const uint32_t ad_lo = tc::desc_lo(d_s, 128u), ad_hi = tc::desc_hi((uint32_t)R * 16u);
+      const uint32_t cp_lo = tc::desc_lo(d_s, 96u * 16u), cp_hi = tc::desc_hi(128u);   // two 8-row groups 1536 B apart, channel rows dense
       const uint32_t b_hi = tc::desc_hi((uint32_t)Rx * 16u);
+      const uint32_t a_tmem0 = tmem + 9u * TC_N;
+      uint32_t step = 0;
       for (int64_t k = 0; k < n_local; ++k) {
         const uint32_t par = (uint32_t)(k & 1);
         const uint32_t xh_s = x_s + (uint32_t)(k & 1) * x_bytes;
@@ -507,19 +511,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
         for (int hf = 0; hf < 2; ++hf) {
           tc::mbar_wait(&bar_d[hf], par);
           tc::fence_after_sync();
-          const int kb = hf ? Kh : 0, ke = hf ? R : Kh;
+          // the copy of K step i + 1 is issued ahead of the MMAs of step i (tcgen05 ops retire in issue order; the ring of A
+          // tiles keeps a copy from overwriting a tile whose MMAs are still queued)
+          tc::tmem_cp_128x256b(a_tmem0 + 8u * (step % TW_ASLOTS), tc::desc_make(cp_lo + (uint32_t)((hf * Kh) >> 3) * 96u, cp_hi));
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
-            const uint32_t d = tmem + (uint32_t)(tap * TC_N);
-            uint32_t acc = (k == 0 && hf == 0) ? 0u : 1u;
-#pragma unroll 2
-            for (int k0 = kb; k0 < ke; k0 += 16) {
-              const uint64_t ad = tc::desc_make(ad_lo + (uint32_t)k0, ad_hi);
+          for (int k0 = hf * Kh; k0 < (hf + 1) * Kh; k0 += 16, ++step) {
+            const uint32_t a_t = a_tmem0 + 8u * (step % TW_ASLOTS);
+            if (k0 + 16 < (hf + 1) * Kh)
+              tc::tmem_cp_128x256b(a_tmem0 + 8u * ((step + 1) % TW_ASLOTS), tc::desc_make(cp_lo + (uint32_t)((k0 + 16) >> 3) * 96u, cp_hi));
+            const uint32_t acc = step ? 1u : 0u;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
+              const uint32_t d = tmem + (uint32_t)(tap * TC_N);
               const uint32_t boff = (uint32_t)(TC_PAD + shift + k0);
-              tc::umma_bf16(d, ad, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
-              tc::umma_bf16(d, ad, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
-              acc = 1u;
+              tc::umma_bf16_ts(d, a_t, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
+              tc::umma_bf16_ts(d, a_t, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
             }
           }
           tc::umma_commit(&bar_h[hf]);
@@ -558,12 +565,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   if (warp == 8) tc::tmem_dealloc<512>(tmem);
 }
 
-int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, const __nv_bfloat16* x_op, const float* x_mean,
+int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_opT, const __nv_bfloat16* x_op, const float* x_mean,
                const float* x_rstd, float* dw, int64_t B, int H) {
   TcWgradArgs a;
-  a.dc_op = dc_op; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.B = B;
+  a.dc_opT = dc_opT; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.B = B;
   a.R = r8tc_dcop_rows(H);
-  a.Kh = a.R / 2;
   HOWL_REQUIRE(ctx, r8tc_supported(H), HOWL_E_UNSUPPORTED, "tensor-core wgrad: H=%d does not fit", H);
   const size_t smem = tc_wgrad_smem(a.R);
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -572,6 +578,60 @@ int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, con
   HOWL_LAUNCHED(ctx, "conv3x3_wgrad_tc");
   return HOWL_OK;
 }
+
+// =============================================================================================
+// tuning aid: issue-to-retire cost of one tcgen05.mma shape on an otherwise idle SM.  One CTA issues `iters` M = 128, K = 16
+// bf16 MMAs into one accumulator (operands are whatever shared memory holds -- only the timing matters) and reports the
+// cycles from first issue to the commit's arrival.  mode bit 0: A from tensor memory (TS) instead of shared memory (SS);
+// bit 1: B MN-major instead of K-major; bit 2: M = 64.
+// =============================================================================================
+__global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int N, int iters, long long* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tc::tmem_alloc<512>(&s_tmem);
+  if (tid == 32) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < (128 * 2 + 256 * 2) * 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  if (warp == 0 && tc::elect_one()) {
+    const int M = (mode & 4) ? 64 : 128;
+    const uint32_t sa = tc::smem_u32(smem), sb = sa + 128 * 32;
+    const uint64_t ad = tc::smem_desc(sa, 128 * 16, 128);
+    const uint64_t bd = (mode & 2) ? tc::smem_desc(sb, 128, 16 * 16) : tc::smem_desc(sb, (uint32_t)N * 16, 128);
+    const uint32_t idesc = tc::instr_desc_bf16(M, N, 0, (mode & 2) ? 1 : 0);
+    const uint32_t a_t = tmem + 256u;
+    if (mode & 1) tc::tmem_cp_128x256b(a_t, ad);
+    const long long t0 = clock64();
+    if (mode & 1)
+      for (int i = 0; i < iters; ++i) tc::umma_bf16_ts(tmem, a_t, bd, idesc, i ? 1u : 0u);
+    else
+      for (int i = 0; i < iters; ++i) tc::umma_bf16(tmem, ad, bd, idesc, i ? 1u : 0u);
+    tc::umma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    out[0] = clock64() - t0;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+extern "C" int howl_b200_debug_umma_bench(howl_ctx_t* ctx, void* stream, int32_t mode, int32_t N, int32_t iters, long long* cycles) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, cycles && iters > 0 && N >= 16 && N <= 256 && N % 16 == 0, HOWL_E_INVALID, "umma_bench: bad arguments");
+  const size_t smem = (128 * 2 + 256 * 2) * 16;
+  umma_bench_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, N, iters, cycles);
+  HOWL_LAUNCHED(ctx, "umma_bench");
+  return HOWL_OK;
+}
+
 // =============================================================================================
 // descriptor self-test: two small GEMMs through exactly the helpers above
 //   test 0 (K-major):  D[128][48] = A[128][32] * B[48][32]^T       rows at 16 B, chunk stride = rows * 16
@@ -700,11 +760,16 @@ extern "C" int howl_b200_selftest_umma(howl_ctx_t* ctx, void* stream, const floa
   return HOWL_OK;
 }
 
-// BatchNorm backward + residual fan-in + ReLU mask (same arithmetic as bn_bwd_apply_kernel in res8.cu), one thread =
-// 8 channels of one pixel; emits the (hi, lo) bf16 operand rows directly.  grid.y = channel chunk.
+// BatchNorm backward + residual fan-in + ReLU mask (same arithmetic as bn_bwd_apply_kernel in res8.cu).  One thread = 8 channels
+// of one RASTER position (halo positions compute zeros), so a warp covers four aligned groups of 8 raster rows.  Emits the
+// conv-output gradient twice, both as (hi, lo) bf16:
+//   dc_op  [hi, lo][6 chunks][R rows][8 channels]       rows = pixels : A operand of the data gradient (K = channels)
+//   dc_opT [R / 8 row groups][hi 48 | lo 48 channels][8 rows]  rows = channels: K-major A operand of the weight gradient, which copies
+//          it to tensor memory (K = pixels); produced by an 8 x 8 transpose among the 8 lanes of a row group.
+// grid.y = channel chunk.
 template <bool EVEN, bool GU_IN, bool BCAST>
 __global__ void __launch_bounds__(256) bn_bwd_apply_op_kernel(const ApplyOpParams p) {
-  const int HW = p.H * R8_W, Kp = r8tc_dcop_rows_dev(p.H), chunk = blockIdx.y;
+  const int HW = p.H * R8_W, R = r8tc_dcop_rows_dev(p.H), chunk = blockIdx.y;
   float mu[8], rs[8], m1[8], m2[8], live[8];
   int coff[8];
 #pragma unroll
@@ -719,39 +784,64 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_op_kernel(const ApplyOpParam
     coff[j] = cc * HW;
   }
   const float inv_hw = 1.f / (float)HW;
-  const int64_t items = p.B * HW;
+  const int64_t items = p.B * R;                     // multiple of 64: whole warps, aligned 8-lane row groups
   uint4* out = reinterpret_cast<uint4*>(p.dc_op);
+  uint4* outT = reinterpret_cast<uint4*>(p.dc_opT);
+  const int lane = threadIdx.x & 31, sub = lane & 7;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = it / HW;
-    const int pp = (int)(it - b * HW);
-    const int y = pp / R8_W, x = pp - y * R8_W;
-    const int64_t ub = b * (int64_t)R8_C * HW + pp;
-    float g[8], u[8], gi[8], pv[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {       // every load of the item is issued before any is consumed
-      const int64_t idx = ub + coff[j];
-      u[j] = p.u[idx];
-      g[j] = BCAST ? __ldg(p.g_bcast + b * R8_C + (coff[j] / HW)) * inv_hw : p.g[idx];
-      gi[j] = GU_IN ? p.gu_in[idx] : 0.f;
-      pv[j] = EVEN ? p.mask_prev[idx] : 0.f;
-    }
+    const int64_t b = it / R;
+    const int q = (int)(it - b * R);
+    const int y = q / TC_PITCH - 1, x = q % TC_PITCH - 1;
+    const bool valid = (y >= 0) && (y < p.H) && (x >= 0) && (x < R8_W);
     float d[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float G = rs[j] * (g[j] - m1[j] - (u[j] - mu[j]) * rs[j] * m2[j]) + gi[j];
-      if (EVEN && live[j] != 0.f) p.gu_out[ub + coff[j]] = G;
-      d[j] = (u[j] > pv[j]) ? G * live[j] : 0.f;
+    for (int j = 0; j < 8; ++j) d[j] = 0.f;
+    if (valid) {
+      const int64_t ub = b * (int64_t)R8_C * HW + y * R8_W + x;
+      float g[8], u[8], gi[8], pv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {       // every load of the item is issued before any is consumed
+        const int64_t idx = ub + coff[j];
+        u[j] = p.u[idx];
+        g[j] = BCAST ? __ldg(p.g_bcast + b * R8_C + (coff[j] / HW)) * inv_hw : p.g[idx];
+        gi[j] = GU_IN ? p.gu_in[idx] : 0.f;
+        pv[j] = EVEN ? p.mask_prev[idx] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float G = rs[j] * (g[j] - m1[j] - (u[j] - mu[j]) * rs[j] * m2[j]) + gi[j];
+        if (EVEN && live[j] != 0.f) p.gu_out[ub + coff[j]] = G;
+        d[j] = (u[j] > pv[j]) ? G * live[j] : 0.f;
+      }
     }
     uint4 hi, lo;
     tc::split8(d, hi, lo);
-    const int64_t base = b * 12 * (int64_t)Kp + (int64_t)chunk * Kp + (y + 1) * TC_PITCH + (x + 1);
-    out[base] = hi;
-    out[base + 6 * (int64_t)Kp] = lo;
+    const int64_t base = b * 12 * (int64_t)R + (int64_t)chunk * R + q;
+    out[base] = hi;                                   // halo rows are written too (zeros): no memset of dc_op needed
+    out[base + 6 * (int64_t)R] = lo;
+    // 8 x 8 transpose inside the row group: afterwards lane `sub` holds channel chunk * 8 + sub at the group's 8 rows
+#pragma unroll
+    for (int s = 1; s < 8; s <<= 1) {
+      const bool up = (sub & s) != 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if ((j & s) == 0) {
+          // lanes with bit s clear keep d[j] and receive the partner's d[j] into d[j + s]; lanes with it set do the mirror image
+          const float send = up ? d[j] : d[j + s];
+          const float got = __shfl_xor_sync(0xffffffffu, send, s);
+          if (up) d[j] = got; else d[j + s] = got;
+        }
+      }
+    }
+    tc::split8(d, hi, lo);
+    const int64_t baseT = (b * (int64_t)(R / 8) + (q >> 3)) * 96 + chunk * 8 + sub;
+    outT[baseT] = hi;
+    outT[baseT + 48] = lo;
   }
 }
 
 int r8tc_apply(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p) {
-  const int64_t items = p.B * p.H * R8_W;
+  const int64_t items = p.B * r8tc_dcop_rows(p.H);
   int64_t bx = howl_ceil_div(items, 256);
   const int64_t cap = (int64_t)ctx->sm_count * 4;
   if (bx > cap) bx = cap;

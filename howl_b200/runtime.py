@@ -78,6 +78,12 @@ class Context:
                                                   variant), "selftest_umma")
         return d
 
+    def debug_umma_bench(self, mode: int, n: int, iters: int = 4096) -> float:
+        """Tuning aid: cycles per M=128 x n x 16 bf16 tcgen05.mma (mode bit 0: A from TMEM, 1: B MN-major, 2: M=64)."""
+        out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._rc(self.lib.howl_b200_debug_umma_bench(self.handle, self._stream(), mode, n, iters, _ptr(out)), "debug_umma_bench")
+        return float(out.item()) / iters
+
     def debug_stream_profile(self, buf, kind: int):
         """Tuning aid: per-CTA wait-cycle counters of the tensor-core conv kernels (kind 1 fwd, 2 dgrad) -> buf[sm][16] int64."""
         self._rc(self.lib.howl_b200_debug_stream_profile(self.handle, _ptr(buf) if buf is not None else None, kind),

@@ -70,6 +70,10 @@ int howl_b200_selftest_umma(howl_ctx_t* ctx, void* stream, const float* A, const
  * pipeline waits to buf[sm_count][16] (uint64, device memory); buf = NULL switches it off.  See tests/profile_stream.py. */
 int howl_b200_debug_stream_profile(howl_ctx_t* ctx, void* buf, int32_t kind);
 
+/* Tuning aid: cycles (device int64) that `iters` back-to-back M=128 (mode bit 2: 64) x N x 16 bf16 tcgen05.mma take on one SM.
+ * mode bit 0: A operand from tensor memory, bit 1: B operand MN-major. */
+int howl_b200_debug_umma_bench(howl_ctx_t* ctx, void* stream, int32_t mode, int32_t N, int32_t iters, long long* cycles);
+
 /* ---- per-launch device timing (CUDA events on the launching stream; used by bench.py's roofline) --------- */
 /* After profile_begin every kernel launch of this context is bracketed by an event on `stream`. */
 int howl_b200_profile_begin(howl_ctx_t* ctx, void* stream);
