@@ -95,7 +95,9 @@ __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __re
   }
   if (m == 0) off[M] = s_off[M];
   __syncthreads();
-  __shared__ FePlan s_plan;      // planned in shared memory (one thread, no global-latency chain), copied out by all
+  __shared__ FePlan s_plan;      // planned in shared memory (no global-latency chain), copied out by all
+  __shared__ short s_order[FE_MAXU];
+  __shared__ short s_cnt[HOWL_NFREQ + 2];
   if (m == 0) {   // tiny serial planner (<= 128 units, 32 lanes)
     FePlan* plan = &s_plan;
     int n = 0;
@@ -112,31 +114,36 @@ __global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __re
       }
     }
     plan->n_units = n;
-    // longest-first order by a counting sort on the span length (<= 257), then greedy onto the least loaded lane
-    int load[32];
-    short order[FE_MAXU];
-    short cnt[HOWL_NFREQ + 2];
-    for (int i = 0; i < HOWL_NFREQ + 2; ++i) cnt[i] = 0;
-    for (int i = 0; i < n; ++i) cnt[plan->u_hi[i] - plan->u_lo[i]]++;
+    // longest-first order by a counting sort on the span length (<= 257)
+    for (int i = 0; i < HOWL_NFREQ + 2; ++i) s_cnt[i] = 0;
+    for (int i = 0; i < n; ++i) s_cnt[plan->u_hi[i] - plan->u_lo[i]]++;
     {
       int pos = 0;
       for (int len = HOWL_NFREQ + 1; len >= 0; --len) {
-        const int c = cnt[len];
-        cnt[len] = (short)pos;
+        const int c = s_cnt[len];
+        s_cnt[len] = (short)pos;
         pos += c;
       }
     }
-    for (int i = 0; i < n; ++i) order[cnt[plan->u_hi[i] - plan->u_lo[i]]++] = (short)i;
-    for (int i = 0; i < 32; ++i) { load[i] = 0; plan->lane_n[i] = 0; }
+    for (int i = 0; i < n; ++i) s_order[s_cnt[plan->u_hi[i] - plan->u_lo[i]]++] = (short)i;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // greedy onto the least loaded lane (ties: lowest lane; lanes holding FE_LANE_UNITS units are closed): warp 0, lane i
+    // keeps the load of plan lane i in a register, one warp-min per unit
+    const int lane = threadIdx.x, n = s_plan.n_units;
+    int my_load = 0, my_n = 0;
     for (int it = 0; it < n; ++it) {
-      const int best = order[it];
-      const int blen = plan->u_hi[best] - plan->u_lo[best];
-      int lane = 0;
-      for (int i = 1; i < 32; ++i)
-        if (plan->lane_n[i] < FE_LANE_UNITS && (plan->lane_n[lane] >= FE_LANE_UNITS || load[i] < load[lane])) lane = i;
-      plan->lane_unit[lane][plan->lane_n[lane]++] = best;
-      load[lane] += blen + 2;
+      const int best = s_order[it];
+      const int blen = s_plan.u_hi[best] - s_plan.u_lo[best];
+      const unsigned key = (my_n < FE_LANE_UNITS) ? (unsigned)my_load * 32u + (unsigned)lane : 0xFFFFFFFFu;
+      const unsigned sel = __reduce_min_sync(0xffffffffu, key) & 31u;
+      if ((unsigned)lane == sel) {
+        s_plan.lane_unit[lane][my_n++] = best;
+        my_load += blen + 2;
+      }
     }
+    s_plan.lane_n[lane] = my_n;
   }
   __syncthreads();
   {
@@ -522,7 +529,7 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
   if (rc) return rc;
   const size_t fbsm = sizeof(float) * HOWL_NFREQ * M;
   HOWL_CUDA(ctx, cudaFuncSetAttribute(fb_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fbsm));
-  fb_compact_kernel<<<1, HOWL_MAX_MELS, fbsm, st>>>(fb, M, ctx->fb_lo, ctx->fb_hi, ctx->fb_off, ctx->fbc,
+  fb_compact_kernel<<<1, 512, fbsm, st>>>(fb, M, ctx->fb_lo, ctx->fb_hi, ctx->fb_off, ctx->fbc,
                                                  reinterpret_cast<FePlan*>(ctx->mel_plan));
   HOWL_LAUNCHED(ctx, "fb_compact");
 

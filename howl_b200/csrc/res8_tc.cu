@@ -36,7 +36,7 @@ int r8tc_dcop_rows(int H) { return r8tc_dcop_rows_dev(H); }
 size_t r8tc_dcop_bytes(int H) { return (size_t)12 * r8tc_dcop_rows(H) * 16; }
 
 static size_t tc_stream_smem(int R) { return (size_t)TC_WBYTES + (size_t)12 * (2 * R + 2 * TC_PAD) * 16 + (48 * 2 + TS_EPI_WARPS * 2 * 16) * 4; }
-static size_t tc_wgrad_smem(int R) { return (size_t)12 * R * 16 + 2 * (size_t)12 * (R + 2 * TC_PAD) * 16; }
+static size_t tc_wgrad_smem(int R) { return (size_t)6 * (12 * R * 16 / 4) + 2 * (size_t)12 * (R + 2 * TC_PAD) * 16; }   // TW_DSLOTS quarters + 2 X
 bool r8tc_supported(int H) {
   const int R = r8tc_dcop_rows(H);
   return H >= 1 && 2 * R / 128 * 96 <= 512 && tc_stream_smem(R) <= TC_SMEM_LIMIT && tc_wgrad_smem(R) <= TC_SMEM_LIMIT;
@@ -415,8 +415,9 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
 //   A rows (TMEM lanes): [dC_hi (48) | dC_lo (48) | 32 don't-care]  from dc_opT (rows = channels, K-major), one 128 x 256 bit copy
 //   B: X_lo then X_hi, MN-major straight from the operand-format activations (rows = raster positions, 12 guard rows)
 // so the four partial products land in rows o and 48 + o, which the epilogue adds.  Both operands arrive by TMA (a loader
-// warp refills the buffers the moment their last MMA has retired): X is double buffered; dC is single buffered but split in two
-// K halves, so the next utterance's first half lands while the second half of this one is being multiplied.
+// warp refills the buffers the moment their last MMA has retired): X is double buffered per utterance, dC streams through a ring
+// of six quarter-utterance slots -- with the A tile out of the way an utterance is multiplied in ~9k cycles, about one TMA
+// round trip under load, so the operands have to be in flight well over an utterance ahead.
 // BatchNorm of X is folded into the epilogue through the "ones" channel (column 45 of every tap):
 //     dW[o][c] = rstd[c] * ( sum_q dC[q][o] X[q+s][c]  -  mean[c] * sum_q dC[q][o] 1[q+s] )
 // =============================================================================================
@@ -430,25 +431,26 @@ struct TcWgradArgs {
   int R;
 };
 #define TW_ASLOTS 8          // ring of A tiles in tensor memory behind the 9 x 48 accumulator columns
+#define TW_DSLOTS 6          // shared-memory ring of dC quarter-utterances
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const TcWgradArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int R = a.R, Rx = R + 2 * TC_PAD, Kh = R / 2;
-  const uint32_t x_bytes = (uint32_t)(12 * Rx * 16), d_bytes = (uint32_t)(12 * R * 16);
-  unsigned char* d_buf = smem;                                   // [R / 8 row groups][96 channels][8 rows] bf16; the 128-row copy
-                                                                 // of the last group runs 512 B into x_buf (don't-care lanes)
-  unsigned char* x_buf = smem + d_bytes;                         // 2 x [hi 6 | lo 6][Rx] x 16 B, raster row q at row q + 12
-  __shared__ __align__(8) uint64_t bar_x[2], bar_d[2], bar_h[2];
+  const int R = a.R, Rx = R + 2 * TC_PAD, Rq = R / 4;            // a quarter utterance = Rq raster rows = Rq / 16 K steps
+  const uint32_t x_bytes = (uint32_t)(12 * Rx * 16), u_bytes = (uint32_t)(12 * R * 16), q_bytes = u_bytes / 4;
+  unsigned char* d_ring = smem;                                  // TW_DSLOTS x [Rq / 8 row groups][96 channels][8 rows] bf16; the
+                                                                 // 128-row copy of a slot's last group runs 512 B past it (don't-care lanes)
+  unsigned char* x_buf = smem + (size_t)TW_DSLOTS * q_bytes;     // 2 x [hi 6 | lo 6][Rx] x 16 B, raster row q at row q + 12
+  __shared__ __align__(8) uint64_t bar_x[2], bar_d[TW_DSLOTS], bar_free[TW_DSLOTS];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (warp == 8) {
     tc::tmem_alloc<512>(&s_tmem);
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) {
-        tc::mbar_init(&bar_x[i], 1);
+      for (int i = 0; i < 2; ++i) tc::mbar_init(&bar_x[i], 1);
+      for (int i = 0; i < TW_DSLOTS; ++i) {
         tc::mbar_init(&bar_d[i], 1);
-        tc::mbar_init(&bar_h[i], 1);
+        tc::mbar_init(&bar_free[i], 1);
       }
       tc::fence_barrier_init();
     }
@@ -460,36 +462,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   tc::fence_after_sync();
   const uint32_t tmem = s_tmem;
   const int64_t n_local = (a.B - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t n_quarters = 4 * n_local;
 
   if (warp == 9) {
-    // ================= TMA loader =================
+    // ================= TMA loader: dC quarters through a ring of TW_DSLOTS, X double buffered per utterance =================
     if (tc::elect_one() && n_local > 0) {
       const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(a.x_op);
       const unsigned char* dsrc = reinterpret_cast<const unsigned char*>(a.dc_opT);
       auto load_x = [&](int64_t k) {
         const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
-        tc::mbar_expect_tx(&bar_x[k & 1], d_bytes);
+        tc::mbar_expect_tx(&bar_x[k & 1], u_bytes);
         for (uint32_t g = 0; g < 12; ++g)
           tc::tma_bulk_g2s(x_buf + (size_t)(k & 1) * x_bytes + ((size_t)g * Rx + TC_PAD) * 16,
-                           xsrc + (size_t)b * d_bytes + (size_t)g * R * 16, (uint32_t)(R * 16), &bar_x[k & 1]);
+                           xsrc + (size_t)b * u_bytes + (size_t)g * R * 16, (uint32_t)(R * 16), &bar_x[k & 1]);
       };
-      auto load_d = [&](int64_t k, int hf) {     // K rows [hf * Kh, (hf + 1) * Kh): contiguous in the transposed format
-        const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
-        tc::mbar_expect_tx(&bar_d[hf], d_bytes / 2);
-        tc::tma_bulk_g2s(d_buf + (size_t)hf * (d_bytes / 2), dsrc + (size_t)b * d_bytes + (size_t)hf * (d_bytes / 2), d_bytes / 2,
-                         &bar_d[hf]);
+      auto load_q = [&](int64_t g) {            // quarter g & 3 of utterance g / 4: contiguous in the transposed format
+        const int64_t b = blockIdx.x + (g >> 2) * (int64_t)gridDim.x;
+        const int slot = (int)(g % TW_DSLOTS);
+        tc::mbar_expect_tx(&bar_d[slot], q_bytes);
+        tc::tma_bulk_g2s(d_ring + (size_t)slot * q_bytes, dsrc + (size_t)b * u_bytes + (size_t)(g & 3) * q_bytes, q_bytes, &bar_d[slot]);
       };
       load_x(0);
-      load_d(0, 0);
-      load_d(0, 1);
+      for (int64_t g = 0; g < TW_DSLOTS && g < n_quarters; ++g) load_q(g);
       if (n_local > 1) load_x(1);
-      for (int64_t k = 0; k + 1 < n_local; ++k) {
-        const uint32_t par = (uint32_t)(k & 1);
-        tc::mbar_wait(&bar_h[0], par);          // first K half of utterance k multiplied: its dC rows take utterance k+1's
-        load_d(k + 1, 0);
-        tc::mbar_wait(&bar_h[1], par);          // utterance k completely multiplied: second dC half and its X buffer are free
-        load_d(k + 1, 1);
-        if (k + 2 < n_local) load_x(k + 2);
+      for (int64_t g = 0; g < n_quarters; ++g) {
+        const bool more_d = g + TW_DSLOTS < n_quarters, more_x = (g & 3) == 3 && (g >> 2) + 2 < n_local;
+        if (!more_d && !more_x) continue;
+        tc::mbar_wait(&bar_free[g % TW_DSLOTS], (uint32_t)((g / TW_DSLOTS) & 1));   // MMAs of quarter g have retired
+        if (more_d) load_q(g + TW_DSLOTS);
+        if (more_x) load_x((g >> 2) + 2);       // the utterance's last quarter also releases its X buffer
       }
     }
     __syncwarp();
@@ -497,42 +498,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
     // ================= MMA issuer =================
     if (tc::elect_one() && n_local > 0) {
       const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 0, 1);   // A K-major from tensor memory, B MN-major (K = raster rows)
-      const uint32_t d_s = tc::smem_u32(d_buf), x_s = tc::smem_u32(x_buf);
-      const uint32_t cp_lo = tc::desc_lo(d_s, 96u * 16u), cp_hi = tc::desc_hi(128u);   // two 8-row groups 1536 B apart, channel rows dense
+      const uint32_t d_s = tc::smem_u32(d_ring), x_s = tc::smem_u32(x_buf);
+      const uint32_t cp_hi = tc::desc_hi(128u);                       // channel rows dense; the two 8-row K groups 1536 B apart
       const uint32_t b_hi = tc::desc_hi((uint32_t)Rx * 16u);
       const uint32_t a_tmem0 = tmem + 9u * TC_N;
       uint32_t step = 0;
-      for (int64_t k = 0; k < n_local; ++k) {
-        const uint32_t par = (uint32_t)(k & 1);
+      for (int64_t g = 0; g < n_quarters; ++g) {
+        const int64_t k = g >> 2;
+        const int qi = (int)(g & 3), slot = (int)(g % TW_DSLOTS);
         const uint32_t xh_s = x_s + (uint32_t)(k & 1) * x_bytes;
         const uint32_t bh_lo = tc::desc_lo(xh_s, 128u), bl_lo = tc::desc_lo(xh_s + (uint32_t)(6 * Rx * 16), 128u);
-        tc::mbar_wait(&bar_x[k & 1], (uint32_t)((k >> 1) & 1));
+        const uint32_t cp_lo = tc::desc_lo(d_s + (uint32_t)slot * q_bytes, 96u * 16u);
+        if (qi == 0) tc::mbar_wait(&bar_x[k & 1], (uint32_t)((k >> 1) & 1));
+        tc::mbar_wait(&bar_d[slot], (uint32_t)((g / TW_DSLOTS) & 1));
+        tc::fence_after_sync();
+        // the copy of K step i + 1 is issued ahead of the MMAs of step i (tcgen05 ops retire in issue order; the ring of A
+        // tiles keeps a copy from overwriting a tile whose MMAs are still queued)
+        tc::tmem_cp_128x256b(a_tmem0 + 8u * (step % TW_ASLOTS), tc::desc_make(cp_lo, cp_hi));
 #pragma unroll 1
-        for (int hf = 0; hf < 2; ++hf) {
-          tc::mbar_wait(&bar_d[hf], par);
-          tc::fence_after_sync();
-          // the copy of K step i + 1 is issued ahead of the MMAs of step i (tcgen05 ops retire in issue order; the ring of A
-          // tiles keeps a copy from overwriting a tile whose MMAs are still queued)
-          tc::tmem_cp_128x256b(a_tmem0 + 8u * (step % TW_ASLOTS), tc::desc_make(cp_lo + (uint32_t)((hf * Kh) >> 3) * 96u, cp_hi));
-#pragma unroll 1
-          for (int k0 = hf * Kh; k0 < (hf + 1) * Kh; k0 += 16, ++step) {
-            const uint32_t a_t = a_tmem0 + 8u * (step % TW_ASLOTS);
-            if (k0 + 16 < (hf + 1) * Kh)
-              tc::tmem_cp_128x256b(a_tmem0 + 8u * ((step + 1) % TW_ASLOTS), tc::desc_make(cp_lo + (uint32_t)((k0 + 16) >> 3) * 96u, cp_hi));
-            const uint32_t acc = step ? 1u : 0u;
+        for (int kq = 0; kq < Rq; kq += 16, ++step) {
+          const uint32_t a_t = a_tmem0 + 8u * (step % TW_ASLOTS);
+          if (kq + 16 < Rq)
+            tc::tmem_cp_128x256b(a_tmem0 + 8u * ((step + 1) % TW_ASLOTS), tc::desc_make(cp_lo + (uint32_t)((kq + 16) >> 3) * 96u, cp_hi));
+          const uint32_t acc = step ? 1u : 0u;
+          const int k0 = qi * Rq + kq;
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
-              const uint32_t d = tmem + (uint32_t)(tap * TC_N);
-              const uint32_t boff = (uint32_t)(TC_PAD + shift + k0);
-              tc::umma_bf16_ts(d, a_t, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
-              tc::umma_bf16_ts(d, a_t, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
-            }
+          for (int tap = 0; tap < 9; ++tap) {
+            const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
+            const uint32_t d = tmem + (uint32_t)(tap * TC_N);
+            const uint32_t boff = (uint32_t)(TC_PAD + shift + k0);
+            tc::umma_bf16_ts(d, a_t, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
+            tc::umma_bf16_ts(d, a_t, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
           }
-          tc::umma_commit(&bar_h[hf]);
         }
+        tc::umma_commit(&bar_free[slot]);
       }
-      tc::mbar_wait(&bar_h[1], (uint32_t)((n_local - 1) & 1));
+      tc::mbar_wait(&bar_free[(n_quarters - 1) % TW_DSLOTS], (uint32_t)(((n_quarters - 1) / TW_DSLOTS) & 1));
     }
     __syncwarp();
   }
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int N, int
     tc::mbar_init(&bar, 1);
     tc::fence_barrier_init();
   }
-  for (int i = tid; i < (128 * 2 + 256 * 2) * 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  for (int i = tid; i < (128 * 2 + 256 * 2 + 64) * 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
@@ -608,12 +609,23 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int N, int
     const uint64_t bd = (mode & 2) ? tc::smem_desc(sb, 128, 16 * 16) : tc::smem_desc(sb, (uint32_t)N * 16, 128);
     const uint32_t idesc = tc::instr_desc_bf16(M, N, 0, (mode & 2) ? 1 : 0);
     const uint32_t a_t = tmem + 256u;
-    if (mode & 1) tc::tmem_cp_128x256b(a_t, ad);
+    if (mode & 1) {
+      tc::tmem_cp_128x256b(a_t, ad);
+      if (mode & 32) tc::tmem_cp_128x256b(tmem + 432u, ad);
+    }
+    // bit 3: rotate over 9 accumulators (48 columns apart, two MMAs each); bit 4: operands start one 16-byte row off the
+    // 128-byte core-matrix alignment (what a 3x3 tap shift does); bit 5: a tcgen05.cp of a fresh A tile every 18 MMAs
+    const uint32_t mis = (mode & 16) ? 1u : 0u;
+    const uint64_t ad2 = ad + mis, bd2 = bd + mis;
     const long long t0 = clock64();
-    if (mode & 1)
-      for (int i = 0; i < iters; ++i) tc::umma_bf16_ts(tmem, a_t, bd, idesc, i ? 1u : 0u);
-    else
-      for (int i = 0; i < iters; ++i) tc::umma_bf16(tmem, ad, bd, idesc, i ? 1u : 0u);
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t d = (mode & 8) ? tmem + 48u * (uint32_t)((i >> 1) % 9) : tmem;
+      const uint32_t acc = (mode & 8) ? (i >= 18 ? 1u : (uint32_t)(i & 1)) : (i ? 1u : 0u);
+      const uint32_t at = (mode & 32) ? 432u + 8u * (uint32_t)((i / 18) & 7) : 256u;
+      if ((mode & 32) && i % 18 == 0) tc::tmem_cp_128x256b(tmem + 432u + 8u * (uint32_t)(((i / 18) + 1) & 7), ad);
+      if (mode & 1) tc::umma_bf16_ts(d, tmem + at, bd2, idesc, acc);
+      else tc::umma_bf16(d, ad2, bd2, idesc, acc);
+    }
     tc::umma_commit(&bar);
     tc::mbar_wait(&bar, 0);
     out[0] = clock64() - t0;
@@ -626,7 +638,7 @@ __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int N, int
 extern "C" int howl_b200_debug_umma_bench(howl_ctx_t* ctx, void* stream, int32_t mode, int32_t N, int32_t iters, long long* cycles) {
   if (!ctx) return HOWL_E_INVALID;
   HOWL_REQUIRE(ctx, cycles && iters > 0 && N >= 16 && N <= 256 && N % 16 == 0, HOWL_E_INVALID, "umma_bench: bad arguments");
-  const size_t smem = (128 * 2 + 256 * 2) * 16;
+  const size_t smem = (128 * 2 + 256 * 2 + 64) * 16;   // + slack for the misaligned variants
   umma_bench_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, N, iters, cycles);
   HOWL_LAUNCHED(ctx, "umma_bench");
   return HOWL_OK;

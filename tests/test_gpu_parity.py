@@ -207,7 +207,7 @@ def test_res8_train_steps_match_reference(ctx, golden):
         flat.copy_(O.flatten(want_sd, L).to(DEV))
 
 
-@pytest.mark.parametrize("B,T,L", [(1, 8000, 4), (3, 8000, 5), (5, 16000, 30), (2, 12345, 12), (200, 8000, 4), (300, 16000, 12)])
+@pytest.mark.parametrize("B,T,L", [(1, 8000, 4), (3, 8000, 5), (5, 16000, 30), (2, 12345, 12), (4, 20000, 6), (200, 8000, 4), (300, 16000, 12)])
 def test_res8_train_step_vs_oracle(ctx, B, T, L):
     pcm, labels = O.synthetic_batch(B, T, L, seed=B * 7 + L)
     params, bn = O.res8_init(L, seed=B), O.res8_bn_init()
