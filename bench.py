@@ -255,29 +255,52 @@ def main_ours(args):
 
     if rank == 0:
         peaks = load_peaks()
-        dom = max((g for g in groups if g["name"].startswith("conv")), key=lambda g: g["ms"])
+        by = {g["name"]: g for g in groups}
         conv_launches = 18   # 6 fwd + 6 dgrad + 6 wgrad launches of the 45->45 3x3 kernels per step
         conv_ms = sum(g["ms"] for g in groups if g["name"].startswith("conv3x3"))
-        achieved_tf = B * CONV_LAYER_FLOP_PER_UTT * conv_launches / (conv_ms / 1e3) / 1e12
-        traffic = None
+        conv_tf = B * CONV_LAYER_FLOP_PER_UTT * conv_launches / (conv_ms / 1e3) / 1e12
+        tensor_peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        tj = {}
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):   # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu capture
+        if os.path.exists(tpath):   # dram__bytes_read + write per launch, from the committed `ncu --set full` capture
             tj = json.load(open(tpath))
-            key = "conv3x3_wgrad_tc_kernel" if "wgrad" in dom["name"] else ("conv3x3_tc_kernel<false,2>" if "_tc" in dom["name"] else "conv3x3_kernel<true,1>")
-            traffic = tj.get(key)
         engine = "tcgen05 bf16x3-split MMA, fp32 TMEM accumulate" if any("_tc" in g["name"] for g in groups) else "fp32 FFMA"
-        roofline = {
-            "bound": "tensor", "kernel": f"conv3x3 45->45, 18 launches/step (6 fwd + 6 dgrad + 6 wgrad), {engine}", "achieved": achieved_tf,
-            "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved_tf / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": traffic,
-            "peak_source": peaks["source"] + " (dense bf16 cuBLAS, sustained)",
-            "fp32_ffma_peak_tflops": FP32_PEAK_TFLOPS, "frac_of_fp32_ffma_peak": achieved_tf / FP32_PEAK_TFLOPS,
-            "conv_ms_per_step": conv_ms, "dominant_launch": dom["name"], "dominant_launch_ms": dom["ms"],
+        # the dominant kernel group of the step decides the headline bound; the other groups are listed beside it
+        dom = max((g for g in groups if g["name"].startswith(("conv3x3", "bn_bwd_apply"))), key=lambda g: g["ms"])
+        HW_ = 27 * 10
+        plane, opb = 45 * HW_ * 4, 12 * 320 * 16          # fp32 activation plane set / operand-format block, bytes per utterance
+        # BatchNorm-backward kernel, algorithmic bytes per utterance summed over its six launches:
+        #   layer 6: u + mask in, gu + dc_op + dc_opT out; layers 4, 2: g + u + mask + gu in, same out; layers 5, 3, 1: g + u in, 2 operands out
+        apply_bytes = (2 * plane + plane + 2 * opb) + 2 * (4 * plane + plane + 2 * opb) + 3 * (2 * plane + 2 * opb)
+        if dom["name"].startswith("bn_bwd_apply"):
+            launches_dom = max(1, dom.get("launches_per_step", 6))
+            ach = B * apply_bytes / (dom["ms"] / 1e3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "bn_bwd_apply_op (BatchNorm backward + residual fan-in + ReLU mask -> both gradient "
+                                                  "operand formats), 6 launches/step",
+                        "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                        "traffic": tj.get("bn_bwd_apply_op"), "algorithmic_bytes_per_launch": B * apply_bytes / launches_dom,
+                        "peak_source": peaks["source"] + " (copy bandwidth)"}
+        else:
+            per_launch_ms = dom["ms"] / 6
+            ach = B * CONV_LAYER_FLOP_PER_UTT / (per_launch_ms / 1e3) / 1e12
+            roofline = {"bound": "tensor", "kernel": f"{dom['name']} (conv3x3 45->45, 6 launches/step), {engine}", "achieved": ach,
+                        "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": tj.get(dom["name"]),
+                        "peak_source": peaks["source"] + " (dense bf16 cuBLAS, sustained)"}
+        roofline.update({
+            "dominant_launch": dom["name"], "dominant_launch_ms": dom["ms"],
+            "conv": {"kernel": f"conv3x3 45->45, 18 launches/step (6 fwd + 6 dgrad + 6 wgrad), {engine}", "tflops": conv_tf,
+                     "frac_of_bf16_peak": conv_tf / tensor_peak, "fp32_ffma_peak_tflops": FP32_PEAK_TFLOPS,
+                     "frac_of_fp32_ffma_peak": conv_tf / FP32_PEAK_TFLOPS, "ms_per_step": conv_ms,
+                     "note": "issued bf16 MMA flops are 3x the fp32-equivalent figure (hi*hi + hi*lo + lo*hi); the N=48 MMAs are bound "
+                             "by shared-memory operand reads, see DESIGN.md"},
+            "apply": ({"hbm_gbs": B * apply_bytes / (by["bn_bwd_apply_op"]["ms"] / 1e3) / 1e9,
+                       "hbm_frac": B * apply_bytes / (by["bn_bwd_apply_op"]["ms"] / 1e3) / 1e9 / peaks["hbm_gbs"]}
+                      if "bn_bwd_apply_op" in by else None),
             "step_hbm_gbs_algorithmic": B * STEP_BYTES_PER_UTT / (ms_step / 1e3) / 1e9,
             "step_hbm_frac": B * STEP_BYTES_PER_UTT / (ms_step / 1e3) / 1e9 / peaks["hbm_gbs"],
             "step_tflops_algorithmic": B * STEP_FLOP_PER_UTT / (ms_step / 1e3) / 1e12,
             "frontend": next((g for g in groups if g["name"] == "frontend"), None),
-        }
+        })
         fe = roofline["frontend"]
         if fe:
             fe["hbm_gbs"] = B * 76960 / (fe["ms"] / 1e3) / 1e9

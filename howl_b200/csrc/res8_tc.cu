@@ -414,10 +414,10 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
 // (tcgen05.cp) and the 18 MMAs of the step read A from there; only the 48 x 16 X tiles stream out of shared memory.
 //   A rows (TMEM lanes): [dC_hi (48) | dC_lo (48) | 32 don't-care]  from dc_opT (rows = channels, K-major), one 128 x 256 bit copy
 //   B: X_lo then X_hi, MN-major straight from the operand-format activations (rows = raster positions, 12 guard rows)
-// so the four partial products land in rows o and 48 + o, which the epilogue adds.  Both operands arrive by TMA (a loader
-// warp refills the buffers the moment their last MMA has retired): X is double buffered per utterance, dC streams through a ring
-// of six quarter-utterance slots -- with the A tile out of the way an utterance is multiplied in ~9k cycles, about one TMA
-// round trip under load, so the operands have to be in flight well over an utterance ahead.
+// so the four partial products land in rows o and 48 + o, which the epilogue adds.  With the A tile out of the way an utterance is
+// multiplied in ~9k cycles, about one TMA round trip under load, and consumes more bytes than one SM's TMA queue delivers: dC
+// streams by TMA through a ring of six quarter-utterance slots (a loader warp refills a slot the moment its MMAs retire), X is
+// double buffered per utterance and copied by the eight otherwise idle epilogue warps with plain vector loads.
 // BatchNorm of X is folded into the epilogue through the "ones" channel (column 45 of every tap):
 //     dW[o][c] = rstd[c] * ( sum_q dC[q][o] X[q+s][c]  -  mean[c] * sum_q dC[q][o] 1[q+s] )
 // =============================================================================================
@@ -440,14 +440,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   unsigned char* d_ring = smem;                                  // TW_DSLOTS x [Rq / 8 row groups][96 channels][8 rows] bf16; the
                                                                  // 128-row copy of a slot's last group runs 512 B past it (don't-care lanes)
   unsigned char* x_buf = smem + (size_t)TW_DSLOTS * q_bytes;     // 2 x [hi 6 | lo 6][Rx] x 16 B, raster row q at row q + 12
-  __shared__ __align__(8) uint64_t bar_x[2], bar_d[TW_DSLOTS], bar_free[TW_DSLOTS];
+  __shared__ __align__(8) uint64_t bar_x[2], bar_xfree[2], bar_d[TW_DSLOTS], bar_free[TW_DSLOTS];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (warp == 8) {
     tc::tmem_alloc<512>(&s_tmem);
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) tc::mbar_init(&bar_x[i], 1);
+      for (int i = 0; i < 2; ++i) {
+        tc::mbar_init(&bar_x[i], 8);        // one arrival per copying warp
+        tc::mbar_init(&bar_xfree[i], 1);
+      }
       for (int i = 0; i < TW_DSLOTS; ++i) {
         tc::mbar_init(&bar_d[i], 1);
         tc::mbar_init(&bar_free[i], 1);
@@ -465,32 +468,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   const int64_t n_quarters = 4 * n_local;
 
   if (warp == 9) {
-    // ================= TMA loader: dC quarters through a ring of TW_DSLOTS, X double buffered per utterance =================
+    // ================= TMA loader: dC quarters through a ring of TW_DSLOTS =================
     if (tc::elect_one() && n_local > 0) {
-      const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(a.x_op);
       const unsigned char* dsrc = reinterpret_cast<const unsigned char*>(a.dc_opT);
-      auto load_x = [&](int64_t k) {
-        const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
-        tc::mbar_expect_tx(&bar_x[k & 1], u_bytes);
-        for (uint32_t g = 0; g < 12; ++g)
-          tc::tma_bulk_g2s(x_buf + (size_t)(k & 1) * x_bytes + ((size_t)g * Rx + TC_PAD) * 16,
-                           xsrc + (size_t)b * u_bytes + (size_t)g * R * 16, (uint32_t)(R * 16), &bar_x[k & 1]);
-      };
       auto load_q = [&](int64_t g) {            // quarter g & 3 of utterance g / 4: contiguous in the transposed format
         const int64_t b = blockIdx.x + (g >> 2) * (int64_t)gridDim.x;
         const int slot = (int)(g % TW_DSLOTS);
         tc::mbar_expect_tx(&bar_d[slot], q_bytes);
         tc::tma_bulk_g2s(d_ring + (size_t)slot * q_bytes, dsrc + (size_t)b * u_bytes + (size_t)(g & 3) * q_bytes, q_bytes, &bar_d[slot]);
       };
-      load_x(0);
       for (int64_t g = 0; g < TW_DSLOTS && g < n_quarters; ++g) load_q(g);
-      if (n_local > 1) load_x(1);
-      for (int64_t g = 0; g < n_quarters; ++g) {
-        const bool more_d = g + TW_DSLOTS < n_quarters, more_x = (g & 3) == 3 && (g >> 2) + 2 < n_local;
-        if (!more_d && !more_x) continue;
+      for (int64_t g = 0; g + TW_DSLOTS < n_quarters; ++g) {
         tc::mbar_wait(&bar_free[g % TW_DSLOTS], (uint32_t)((g / TW_DSLOTS) & 1));   // MMAs of quarter g have retired
-        if (more_d) load_q(g + TW_DSLOTS);
-        if (more_x) load_x((g >> 2) + 2);       // the utterance's last quarter also releases its X buffer
+        load_q(g + TW_DSLOTS);
       }
     }
     __syncwarp();
@@ -532,10 +522,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
           }
         }
         tc::umma_commit(&bar_free[slot]);
+        if (qi == 3) tc::umma_commit(&bar_xfree[k & 1]);     // the utterance's X buffer may be overwritten
       }
       tc::mbar_wait(&bar_free[(n_quarters - 1) % TW_DSLOTS], (uint32_t)(((n_quarters - 1) / TW_DSLOTS) & 1));
     }
     __syncwarp();
+  } else if (n_local > 0) {
+    // ================= warps 0-7: X operand of utterance k -> buffer k & 1 with plain 16-byte loads.  One SM's TMA queue
+    // sustains ~8 B/clk here, half of what the MMAs consume; the epilogue warps are idle until the end, so they carry X and
+    // the TMA carries dC. =================
+    const uint4* xsrc = reinterpret_cast<const uint4*>(a.x_op);
+    const int n16 = 12 * R;
+    for (int64_t k = 0; k < n_local; ++k) {
+      if (k >= 2) tc::mbar_wait(&bar_xfree[k & 1], (uint32_t)(((k - 2) >> 1) & 1));
+      const uint4* src = xsrc + (size_t)(blockIdx.x + k * (int64_t)gridDim.x) * n16;
+      uint4* dst = reinterpret_cast<uint4*>(x_buf + (size_t)(k & 1) * x_bytes);
+#pragma unroll 1
+      for (int i0 = tid; i0 < n16; i0 += 4 * TC_WORKERS) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * TC_WORKERS;
+          v[u] = i < n16 ? __ldcs(src + i) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * TC_WORKERS;
+          if (i < n16) dst[(i / R) * Rx + TC_PAD + (i % R)] = v[u];
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_x[k & 1]);
+    }
   }
   tc::fence_before_sync();
   __syncthreads();          // the issuer arrives only after the last commit: every accumulator is final
