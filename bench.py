@@ -316,7 +316,7 @@ def main_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"res8 NUM_MELS=40 batch={B}/GPU fused STFT->mel->conv train step, synthetic GSC-shaped 1 s clips, "
                                    f"L={NUM_LABELS}", "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2_policy": "inputs (262 MB PCM + 2.4 GB activations per step) exceed the 126 MB L2; two alternating batches"},
+                       "l2_policy": "inputs (262 MB PCM + 4.5 GB activations and operands per step) exceed the 126 MB L2; two alternating batches"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "groups_ms": {g["name"]: round(g["ms"], 4) for g in groups},
         }

@@ -161,3 +161,18 @@ def test_frame_batchifier_plan_is_bit_exact_with_reference():
         assert np.array_equal(labels, g[f"t{trial}.labels"])
         assert np.array_equal(counts, g[f"t{trial}.lengths"])
         assert np.array_equal(out, g[f"t{trial}.audio"])
+
+
+def test_honkling_export_matches_reference_script():
+    """§8f row 4: byte-identical to training/run/export_honkling.py on the shipped hey-fire-fox checkpoint (golden: SHA-256)."""
+    import hashlib
+    from collections import OrderedDict
+
+    from howl_b200.export import export_honkling
+
+    g = np.load(os.path.join(GOLDEN, "res8_heyfirefox.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "meta.json")))["honkling"]
+    sd = OrderedDict((k[3:], torch.from_numpy(g[k])) for k in g.files if k.startswith("sd."))
+    text = export_honkling(sd, meta["name"]).encode()
+    assert len(text) == meta["bytes"] and text[:96].decode() == meta["head"] and text[-48:].decode() == meta["tail"]
+    assert hashlib.sha256(text).hexdigest() == meta["sha256"]
