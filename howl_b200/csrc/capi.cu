@@ -66,7 +66,7 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
 extern "C" int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return HOWL_E_INVALID;
   if (strcmp(name, "conv_engine") == 0) {
-    HOWL_REQUIRE(ctx, value == 0 || value == 1, HOWL_E_INVALID, "set_option: conv_engine must be 0 (fp32) or 1 (tcgen05)");
+    HOWL_REQUIRE(ctx, value >= 0 && value <= 2, HOWL_E_INVALID, "set_option: conv_engine must be 0 (fp32), 1 (tcgen05, split bf16) or 2 (tcgen05, single bf16)");
     ctx->conv_engine = (int)value;
     return HOWL_OK;
   }

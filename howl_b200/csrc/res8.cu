@@ -802,7 +802,7 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   {
     const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + R8_C * 9);
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const bool op = ctx->conv_engine == 1 && r8tc_supported(H);
+    const bool op = ctx->conv_engine >= 1 && r8tc_supported(H);
     conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, ws.a0, op ? reinterpret_cast<uint4*>(ws.uop[0]) : nullptr,
                                                           r8tc_dcop_rows(H), frames, H);
     HOWL_LAUNCHED(ctx, "conv0_pool");
@@ -818,7 +818,7 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
   const int grid = r8_grid(ctx, B);
   const double count = (double)B * HW;
-  const bool use_tc = ctx->conv_engine == 1 && r8tc_supported(H);
+  const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(H);
   for (int i = 1; i <= R8_LAYERS; ++i) {
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -879,7 +879,7 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.stats_bwd, 0, sizeof(double) * R8_LAYERS * 2 * R8_C, st));
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * 2, st));
 
-  const bool use_tc = ctx->conv_engine == 1 && r8tc_supported(frames / 3);
+  const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(frames / 3);
   if (use_tc) {
     rc = r8tc_weight_prep(ctx, st, wl, ws.wprep);
     if (rc) return rc;

@@ -120,6 +120,7 @@ struct TcStreamArgs {
   __nv_bfloat16* out_op;         // FWD: the output in operand format as well, or null
   const __nv_bfloat16* w;        // [9][6][96][8]
   int R;
+  int single;                    // fast mode: bf16 x bf16 only (the two lo-term MMAs are skipped)
   unsigned long long* prof;      // tuning aid: per-CTA cycle counters of the pipeline waits, or null
 };
 
@@ -254,8 +255,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
             for (int ks = 0; ks < 3; ++ks) {
               const uint32_t aoff = (uint32_t)(2 * ks) * (uint32_t)RS + rowb + (uint32_t)shift;
               const uint64_t bd = tc::desc_make(b_lo + (uint32_t)((tap * 6 + 2 * ks) * 96), d_hi128);
-              tc::umma_bf16(d, tc::desc_make(ah_lo + aoff, d_hi128), bd, idesc96, (tap | ks) ? 1u : 0u);   // hi x (hi | lo)
-              tc::umma_bf16(d, tc::desc_make(al_lo + aoff, d_hi128), bd, idesc48, 1u);                     // lo x hi
+              if (a.single) {
+                tc::umma_bf16(d, tc::desc_make(ah_lo + aoff, d_hi128), bd, idesc48, (tap | ks) ? 1u : 0u);   // hi x hi only
+              } else {
+                tc::umma_bf16(d, tc::desc_make(ah_lo + aoff, d_hi128), bd, idesc96, (tap | ks) ? 1u : 0u);   // hi x (hi | lo)
+                tc::umma_bf16(d, tc::desc_make(al_lo + aoff, d_hi128), bd, idesc48, 1u);                     // lo x hi
+              }
             }
           }
           tc::umma_commit(&bar_tile[j]);
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             if (jj < 13 || full) {
-              float o = __uint_as_float(v[jj]) + __uint_as_float(v2[jj]);
+              float o = __uint_as_float(v[jj]) + (a.single ? 0.f : __uint_as_float(v2[jj]));
               if (FWD) o = fmaxf(o, 0.f) + pre[jj];
               p.out[off0 + (uint32_t)jj * (uint32_t)HW] = o;
               if (STATS == 1) {
@@ -383,6 +388,7 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
               const __nv_bfloat16* w, bool fwd, int stats) {
   TcStreamArgs a;
   a.p = p;
+  a.single = ctx->conv_engine == 2;
   a.in_op = in_op; a.out_op = out_op; a.w = w;
   HOWL_REQUIRE(ctx, p.B * (int64_t)R8_C * p.H * R8_W < ((int64_t)1 << 31), HOWL_E_UNSUPPORTED,
                "tensor-core conv: batch of %lld utterances exceeds the 32-bit element offsets", (long long)p.B);
@@ -429,6 +435,7 @@ struct TcWgradArgs {
   float* dw;
   int64_t B;
   int R;
+  int single;            // fast mode: the X_lo MMA is skipped
 };
 #define TW_ASLOTS 8          // ring of A tiles in tensor memory behind the 9 x 48 accumulator columns
 #define TW_DSLOTS 6          // shared-memory ring of dC quarter-utterances
@@ -517,8 +524,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
             const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
             const uint32_t d = tmem + (uint32_t)(tap * TC_N);
             const uint32_t boff = (uint32_t)(TC_PAD + shift + k0);
-            tc::umma_bf16_ts(d, a_t, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
-            tc::umma_bf16_ts(d, a_t, tc::desc_make(bh_lo + boff, b_hi), idesc, 1u);
+            if (!a.single) tc::umma_bf16_ts(d, a_t, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
+            tc::umma_bf16_ts(d, a_t, tc::desc_make(bh_lo + boff, b_hi), idesc, a.single ? acc : 1u);
           }
         }
         tc::umma_commit(&bar_free[slot]);
@@ -590,6 +597,7 @@ int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_opT, co
   TcWgradArgs a;
   a.dc_opT = dc_opT; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.B = B;
   a.R = r8tc_dcop_rows(H);
+  a.single = ctx->conv_engine == 2;
   HOWL_REQUIRE(ctx, r8tc_supported(H), HOWL_E_UNSUPPORTED, "tensor-core wgrad: H=%d does not fit", H);
   const size_t smem = tc_wgrad_smem(a.R);
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -58,8 +58,9 @@ int howl_b200_sm_count(const howl_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t howl_b200_launch_count(const howl_ctx_t* ctx);
 
-/* Options: "conv_engine" = 1 (default) 45->45 convolutions on tcgen05 tensor cores with bf16x3-split operands and
- * fp32 accumulation; 0 = exact-fp32 FFMA kernels. */
+/* Options: "conv_engine" = 1 (default, PARITY mode) 45->45 convolutions on tcgen05 tensor cores with bf16x3-split operands
+ * and fp32 accumulation (logits within 1e-5 of fp32); 0 = exact-fp32 FFMA kernels; 2 = FAST mode, the same kernels with the
+ * low-order bf16 terms skipped (single bf16 x bf16 products, ~3e-3 relative: outside the 1e-4 parity bar, never the default). */
 int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value);
 /* Debug aid: one 128x48x32 GEMM through the library's UMMA descriptor helpers (A, B fp32 device arrays, bf16-rounded
  * inside; mn_major selects the operand layout of the weight-gradient GEMM); D fp32 [128][48]. */

@@ -207,7 +207,8 @@ def test_res8_train_steps_match_reference(ctx, golden):
         flat.copy_(O.flatten(want_sd, L).to(DEV))
 
 
-@pytest.mark.parametrize("B,T,L", [(1, 8000, 4), (3, 8000, 5), (5, 16000, 30), (2, 12345, 12), (4, 20000, 6), (200, 8000, 4), (300, 16000, 12)])
+@pytest.mark.parametrize("B,T,L", [(1, 8000, 4), (3, 8000, 5), (5, 16000, 30), (2, 12345, 12), (4, 20000, 6), (3, 1000, 4), (2, 5400, 4), (200, 8000, 4),
+                                   (300, 16000, 12)])
 def test_res8_train_step_vs_oracle(ctx, B, T, L):
     pcm, labels = O.synthetic_batch(B, T, L, seed=B * 7 + L)
     params, bn = O.res8_init(L, seed=B), O.res8_bn_init()
@@ -288,3 +289,32 @@ def test_data_parallel_grad_identity(ctx):
         (torch.nn.functional.cross_entropy(lg, labels[sl], reduction="sum") / B).backward()
         want += O.flatten({k: leaves[k].grad for k in leaves}, L)
     _assert_grads(total.cpu().numpy().astype(np.float64), [want.numpy().astype(np.float64)], L, tight=False)
+
+
+def test_res8_fast_mode_is_close_but_not_the_default():
+    """conv_engine=2 (single bf16 x bf16 products) is a separately reported fast mode: it must track the parity engine to
+    bf16 accuracy, and the default engine must stay the split-precision one."""
+    import howl_b200
+
+    c = howl_b200.Context("cuda:0", n_mels=40)
+    B, T, L = 64, 16000, 12
+    pcm, labels = O.synthetic_batch(B, T, L, seed=3)
+    params, bn = O.res8_init(L, seed=4), O.res8_bn_init()
+    feats = c.frontend(pcm.to(DEV), O.mel_filterbank(40).to(DEV), "time_major", zmuv=(-1.78896, 3.93389))
+    out = {}
+    for engine in (None, 1, 2):
+        if engine is not None:
+            c.set_option("conv_engine", engine)
+        flat = O.flatten(params, L).to(DEV)
+        bnd, nbt = _bn_dev(bn), torch.zeros(6, dtype=torch.int64, device=DEV)
+        ws = c.workspace(c.res8_workspace_bytes(B, feats.shape[1], L))
+        logits = c.res8_fwd(feats, flat, bnd, nbt, True, ws)
+        grads, loss = torch.zeros_like(flat), torch.zeros(1, device=DEV)
+        c.res8_bwd(feats, labels.to(DEV), flat, grads, loss, ws)
+        out[engine] = (logits.cpu().numpy().astype(np.float64), grads.cpu().numpy().astype(np.float64))
+    c.close()
+    np.testing.assert_allclose(out[None][0], out[1][0], rtol=0, atol=1e-6)   # the default IS the parity engine (fp64 atomics reorder)
+    scale = np.abs(out[1][0]).max()
+    err = np.abs(out[2][0] - out[1][0]).max() / scale
+    assert 1e-6 < err < 3e-2, err                                      # bf16-level agreement, and really a different arithmetic
+    assert np.linalg.norm(out[2][1] - out[1][1]) / np.linalg.norm(out[1][1]) < 0.2
