@@ -120,12 +120,12 @@ struct TcStreamArgs {
   __nv_bfloat16* out_op;         // FWD: the output in operand format as well, or null
   const __nv_bfloat16* w;        // [9][6][96][8]
   int R;
-  int single;                    // fast mode: bf16 x bf16 only (the two lo-term MMAs are skipped)
   unsigned long long* prof;      // tuning aid: per-CTA cycle counters of the pipeline waits, or null
 };
 
 // STATS: 0 none, 1 forward BatchNorm statistics (sum, sum of squares), 2 BatchNorm-backward (sum g, sum g * xhat(aux))
-template <bool FWD, int STATS>
+// SINGLE: fast mode, bf16 x bf16 only (the two low-order MMAs per product are skipped; conv_engine = 2)
+template <bool FWD, int STATS, bool SINGLE>
 __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const TcStreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const ConvParams& p = a.p;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
             for (int ks = 0; ks < 3; ++ks) {
               const uint32_t aoff = (uint32_t)(2 * ks) * (uint32_t)RS + rowb + (uint32_t)shift;
               const uint64_t bd = tc::desc_make(b_lo + (uint32_t)((tap * 6 + 2 * ks) * 96), d_hi128);
-              if (a.single) {
+              if (SINGLE) {
                 tc::umma_bf16(d, tc::desc_make(ah_lo + aoff, d_hi128), bd, idesc48, (tap | ks) ? 1u : 0u);   // hi x hi only
               } else {
                 tc::umma_bf16(d, tc::desc_make(ah_lo + aoff, d_hi128), bd, idesc96, (tap | ks) ? 1u : 0u);   // hi x (hi | lo)
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             if (jj < 13 || full) {
-              float o = __uint_as_float(v[jj]) + (a.single ? 0.f : __uint_as_float(v2[jj]));
+              float o = __uint_as_float(v[jj]) + (SINGLE ? 0.f : __uint_as_float(v2[jj]));
               if (FWD) o = fmaxf(o, 0.f) + pre[jj];
               p.out[off0 + (uint32_t)jj * (uint32_t)HW] = o;
               if (STATS == 1) {
@@ -388,7 +388,6 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
               const __nv_bfloat16* w, bool fwd, int stats) {
   TcStreamArgs a;
   a.p = p;
-  a.single = ctx->conv_engine == 2;
   a.in_op = in_op; a.out_op = out_op; a.w = w;
   HOWL_REQUIRE(ctx, p.B * (int64_t)R8_C * p.H * R8_W < ((int64_t)1 << 31), HOWL_E_UNSUPPORTED,
                "tensor-core conv: batch of %lld utterances exceeds the 32-bit element offsets", (long long)p.B);
@@ -397,11 +396,17 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
   HOWL_REQUIRE(ctx, r8tc_supported(p.H), HOWL_E_UNSUPPORTED, "tensor-core conv: H=%d does not fit", p.H);
   const size_t smem = tc_stream_smem(a.R);
   const int grid = (int)(p.B < ctx->sm_count ? p.B : ctx->sm_count);
-#define TS_LAUNCH(FWD_, STATS_)                                                                                          \
+  const bool single = ctx->conv_engine == 2;
+#define TS_LAUNCH1(FWD_, STATS_, SINGLE_)                                                                                \
   do {                                                                                                                   \
-    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_stream_tc_kernel<FWD_, STATS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        (int)smem));                                                                     \
-    conv3x3_stream_tc_kernel<FWD_, STATS_><<<grid, TS_THREADS, smem, st>>>(a);                                           \
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_stream_tc_kernel<FWD_, STATS_, SINGLE_>,                                 \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+    conv3x3_stream_tc_kernel<FWD_, STATS_, SINGLE_><<<grid, TS_THREADS, smem, st>>>(a);                                  \
+  } while (0)
+#define TS_LAUNCH(FWD_, STATS_)                  \
+  do {                                           \
+    if (single) TS_LAUNCH1(FWD_, STATS_, true);  \
+    else TS_LAUNCH1(FWD_, STATS_, false);        \
   } while (0)
   if (fwd && stats == 1) TS_LAUNCH(true, 1);
   else if (fwd && stats == 0) TS_LAUNCH(true, 0);
@@ -409,6 +414,7 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
   else if (!fwd && stats == 0) TS_LAUNCH(false, 0);
   else HOWL_REQUIRE(ctx, false, HOWL_E_INVALID, "tensor-core conv: unsupported mode");
 #undef TS_LAUNCH
+#undef TS_LAUNCH1
   HOWL_LAUNCHED(ctx, fwd ? "conv3x3_fwd_tc" : "conv3x3_dgrad_tc");
   return HOWL_OK;
 }
@@ -420,10 +426,10 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_
 // (tcgen05.cp) and the 18 MMAs of the step read A from there; only the 48 x 16 X tiles stream out of shared memory.
 //   A rows (TMEM lanes): [dC_hi (48) | dC_lo (48) | 32 don't-care]  from dc_opT (rows = channels, K-major), one 128 x 256 bit copy
 //   B: X_lo then X_hi, MN-major straight from the operand-format activations (rows = raster positions, 12 guard rows)
-// so the four partial products land in rows o and 48 + o, which the epilogue adds.  With the A tile out of the way an utterance is
-// multiplied in ~9k cycles, about one TMA round trip under load, and consumes more bytes than one SM's TMA queue delivers: dC
-// streams by TMA through a ring of six quarter-utterance slots (a loader warp refills a slot the moment its MMAs retire), X is
-// double buffered per utterance and copied by the eight otherwise idle epilogue warps with plain vector loads.
+// so the four partial products land in rows o and 48 + o, which the epilogue adds.  Both operands arrive by TMA (a loader
+// warp refills the buffers the moment their last MMA has retired): X is double buffered per utterance, dC streams through a ring
+// of six quarter-utterance slots -- with the A tile out of the way an utterance is multiplied in ~9k cycles, about one TMA
+// round trip under load, so the operands have to be in flight well over an utterance ahead.
 // BatchNorm of X is folded into the epilogue through the "ones" channel (column 45 of every tap):
 //     dW[o][c] = rstd[c] * ( sum_q dC[q][o] X[q+s][c]  -  mean[c] * sum_q dC[q][o] 1[q+s] )
 // =============================================================================================
@@ -435,11 +441,11 @@ struct TcWgradArgs {
   float* dw;
   int64_t B;
   int R;
-  int single;            // fast mode: the X_lo MMA is skipped
 };
 #define TW_ASLOTS 8          // ring of A tiles in tensor memory behind the 9 x 48 accumulator columns
 #define TW_DSLOTS 6          // shared-memory ring of dC quarter-utterances
 
+template <bool SINGLE>   // SINGLE: fast mode, the X_lo MMA is skipped
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const TcWgradArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.R, Rx = R + 2 * TC_PAD, Rq = R / 4;            // a quarter utterance = Rq raster rows = Rq / 16 K steps
@@ -447,17 +453,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   unsigned char* d_ring = smem;                                  // TW_DSLOTS x [Rq / 8 row groups][96 channels][8 rows] bf16; the
                                                                  // 128-row copy of a slot's last group runs 512 B past it (don't-care lanes)
   unsigned char* x_buf = smem + (size_t)TW_DSLOTS * q_bytes;     // 2 x [hi 6 | lo 6][Rx] x 16 B, raster row q at row q + 12
-  __shared__ __align__(8) uint64_t bar_x[2], bar_xfree[2], bar_d[TW_DSLOTS], bar_free[TW_DSLOTS];
+  __shared__ __align__(8) uint64_t bar_x[2], bar_d[TW_DSLOTS], bar_free[TW_DSLOTS];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (warp == 8) {
     tc::tmem_alloc<512>(&s_tmem);
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) {
-        tc::mbar_init(&bar_x[i], 8);        // one arrival per copying warp
-        tc::mbar_init(&bar_xfree[i], 1);
-      }
+      for (int i = 0; i < 2; ++i) tc::mbar_init(&bar_x[i], 1);
       for (int i = 0; i < TW_DSLOTS; ++i) {
         tc::mbar_init(&bar_d[i], 1);
         tc::mbar_init(&bar_free[i], 1);
@@ -475,19 +478,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   const int64_t n_quarters = 4 * n_local;
 
   if (warp == 9) {
-    // ================= TMA loader: dC quarters through a ring of TW_DSLOTS =================
+    // ================= TMA loader: dC quarters through a ring of TW_DSLOTS, X double buffered per utterance =================
     if (tc::elect_one() && n_local > 0) {
+      const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(a.x_op);
       const unsigned char* dsrc = reinterpret_cast<const unsigned char*>(a.dc_opT);
+      auto load_x = [&](int64_t k) {
+        const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
+        tc::mbar_expect_tx(&bar_x[k & 1], u_bytes);
+        for (uint32_t g = 0; g < 12; ++g)
+          tc::tma_bulk_g2s(x_buf + (size_t)(k & 1) * x_bytes + ((size_t)g * Rx + TC_PAD) * 16,
+                           xsrc + (size_t)b * u_bytes + (size_t)g * R * 16, (uint32_t)(R * 16), &bar_x[k & 1]);
+      };
       auto load_q = [&](int64_t g) {            // quarter g & 3 of utterance g / 4: contiguous in the transposed format
         const int64_t b = blockIdx.x + (g >> 2) * (int64_t)gridDim.x;
         const int slot = (int)(g % TW_DSLOTS);
         tc::mbar_expect_tx(&bar_d[slot], q_bytes);
         tc::tma_bulk_g2s(d_ring + (size_t)slot * q_bytes, dsrc + (size_t)b * u_bytes + (size_t)(g & 3) * q_bytes, q_bytes, &bar_d[slot]);
       };
+      load_x(0);
       for (int64_t g = 0; g < TW_DSLOTS && g < n_quarters; ++g) load_q(g);
-      for (int64_t g = 0; g + TW_DSLOTS < n_quarters; ++g) {
+      if (n_local > 1) load_x(1);
+      for (int64_t g = 0; g < n_quarters; ++g) {
+        const bool more_d = g + TW_DSLOTS < n_quarters, more_x = (g & 3) == 3 && (g >> 2) + 2 < n_local;
+        if (!more_d && !more_x) continue;
         tc::mbar_wait(&bar_free[g % TW_DSLOTS], (uint32_t)((g / TW_DSLOTS) & 1));   // MMAs of quarter g have retired
-        load_q(g + TW_DSLOTS);
+        if (more_d) load_q(g + TW_DSLOTS);
+        if (more_x) load_x((g >> 2) + 2);       // the utterance's last quarter also releases its X buffer
       }
     }
     __syncwarp();
@@ -524,44 +540,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
             const int shift = (tap / 3 - 1) * TC_PITCH + (tap % 3 - 1);
             const uint32_t d = tmem + (uint32_t)(tap * TC_N);
             const uint32_t boff = (uint32_t)(TC_PAD + shift + k0);
-            if (!a.single) tc::umma_bf16_ts(d, a_t, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
-            tc::umma_bf16_ts(d, a_t, tc::desc_make(bh_lo + boff, b_hi), idesc, a.single ? acc : 1u);
+            if (!SINGLE) tc::umma_bf16_ts(d, a_t, tc::desc_make(bl_lo + boff, b_hi), idesc, acc);
+            tc::umma_bf16_ts(d, a_t, tc::desc_make(bh_lo + boff, b_hi), idesc, SINGLE ? acc : 1u);
           }
         }
         tc::umma_commit(&bar_free[slot]);
-        if (qi == 3) tc::umma_commit(&bar_xfree[k & 1]);     // the utterance's X buffer may be overwritten
       }
       tc::mbar_wait(&bar_free[(n_quarters - 1) % TW_DSLOTS], (uint32_t)(((n_quarters - 1) / TW_DSLOTS) & 1));
     }
     __syncwarp();
-  } else if (n_local > 0) {
-    // ================= warps 0-7: X operand of utterance k -> buffer k & 1 with plain 16-byte loads.  One SM's TMA queue
-    // sustains ~8 B/clk here, half of what the MMAs consume; the epilogue warps are idle until the end, so they carry X and
-    // the TMA carries dC. =================
-    const uint4* xsrc = reinterpret_cast<const uint4*>(a.x_op);
-    const int n16 = 12 * R;
-    for (int64_t k = 0; k < n_local; ++k) {
-      if (k >= 2) tc::mbar_wait(&bar_xfree[k & 1], (uint32_t)(((k - 2) >> 1) & 1));
-      const uint4* src = xsrc + (size_t)(blockIdx.x + k * (int64_t)gridDim.x) * n16;
-      uint4* dst = reinterpret_cast<uint4*>(x_buf + (size_t)(k & 1) * x_bytes);
-#pragma unroll 1
-      for (int i0 = tid; i0 < n16; i0 += 4 * TC_WORKERS) {
-        uint4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * TC_WORKERS;
-          v[u] = i < n16 ? __ldcs(src + i) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * TC_WORKERS;
-          if (i < n16) dst[(i / R) * Rx + TC_PAD + (i % R)] = v[u];
-        }
-      }
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bar_x[k & 1]);
-    }
   }
   tc::fence_before_sync();
   __syncthreads();          // the issuer arrives only after the last commit: every accumulator is final
@@ -597,12 +584,16 @@ int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_opT, co
   TcWgradArgs a;
   a.dc_opT = dc_opT; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.B = B;
   a.R = r8tc_dcop_rows(H);
-  a.single = ctx->conv_engine == 2;
   HOWL_REQUIRE(ctx, r8tc_supported(H), HOWL_E_UNSUPPORTED, "tensor-core wgrad: H=%d does not fit", H);
   const size_t smem = tc_wgrad_smem(a.R);
-  HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(B < ctx->sm_count ? B : ctx->sm_count);
-  conv3x3_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+  if (ctx->conv_engine == 2) {
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_wgrad_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
+  } else {
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_wgrad_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
+  }
   HOWL_LAUNCHED(ctx, "conv3x3_wgrad_tc");
   return HOWL_OK;
 }
