@@ -260,3 +260,61 @@ class SeqLstmCtcTrainStep(LstmTrainStep):
                 acc[name] = acc.get(name, 0.0) + ms
                 cnt[name] = cnt.get(name, 0) + 1
         return [{"name": k, "ms": acc[k] / reps, "launches_per_step": cnt[k] // reps} for k in acc]
+
+
+class Trainer:
+    """``howl.trainer.Trainer`` (``howl/trainer.py:11-31``): constructible from a ``TrainingConfig`` exactly like the reference's
+    (which is a stub without a training loop); ``train`` is the addition the reference leaves open -- the epoch loop of
+    ``training/run/train.py:280-307`` over the fused CUDA step.
+
+    Construction touches neither CUDA nor the datasets (the reference's does not either); the fused step is built on the first
+    ``train`` call, for the clip length and batch size of the first batch.
+    """
+
+    def __init__(self, training_cfg, logger=None, device="cuda:0"):
+        import logging
+
+        from .inference import SimpleContext
+
+        self.training_cfg = training_cfg
+        self.context_cfg = training_cfg.context_config
+        if self.context_cfg.token_type != "word":
+            raise NotImplementedError("Trainer: only word-level contexts (token_type='word') are supported")
+        vocab = list(self.context_cfg.vocab or [])
+        self.context = SimpleContext.for_vocab(vocab)           # labels: vocab..., then the negative label (context.py:86-97)
+        sequence = self.context_cfg.sequence if self.context_cfg.sequence is not None else range(len(vocab))
+        self.wake_word = " ".join(vocab[i] for i in sequence)        # Vocab.wakeword (howl/data/common/vocab.py:96-98): no stripping
+        self.logger = logger or logging.getLogger(self.__class__.__name__)
+        self.device = device
+        self.step_obj = None
+        self.epoch = 0
+        if training_cfg.model_config.architecture != "res8":
+            raise NotImplementedError(f"Trainer: fused training step exists for res8, not {training_cfg.model_config.architecture!r}")
+
+    def _ensure_step(self, pcm: torch.Tensor, zmuv):
+        if self.step_obj is None:
+            cfg = self.training_cfg
+            self.step_obj = Res8TrainStep(self.device, num_labels=self.context.num_labels, batch=pcm.shape[0], samples=pcm.shape[1],
+                                          lr=cfg.learning_rate, weight_decay=cfg.weight_decay, zmuv=zmuv, seed=self.context_cfg.seed)
+        return self.step_obj
+
+    def train_epoch(self, batches, zmuv=(0.0, 1.0)) -> float:
+        """One pass over ``batches`` (iterable of (pcm [B,T] float32, labels [B] int64), host or device tensors); returns the mean
+        loss.  The learning rate decays by ``lr_decay`` after the epoch (``train.py:306-307``)."""
+        total, n = 0.0, 0
+        for pcm, labels in batches:
+            step = self._ensure_step(pcm, zmuv)
+            loss = step.step(pcm.to(step.device, torch.float32), labels.to(step.device, torch.int64))
+            total, n = total + float(loss.item()), n + 1
+        if self.step_obj is not None:
+            self.step_obj.lr *= self.training_cfg.lr_decay
+        self.epoch += 1
+        return total / max(n, 1)
+
+    def train(self, make_batches, zmuv=(0.0, 1.0)):
+        """``num_epochs`` epochs; ``make_batches(epoch)`` returns that epoch's batch iterable.  Returns the per-epoch mean losses."""
+        losses = []
+        for epoch in range(self.training_cfg.num_epochs):
+            losses.append(self.train_epoch(make_batches(epoch), zmuv))
+            self.logger.info("epoch %d: mean loss %.5f, lr %.6f", epoch, losses[-1], self.step_obj.lr if self.step_obj else float("nan"))
+        return losses

@@ -176,3 +176,22 @@ def test_honkling_export_matches_reference_script():
     text = export_honkling(sd, meta["name"]).encode()
     assert len(text) == meta["bytes"] and text[:96].decode() == meta["head"] and text[-48:].decode() == meta["tail"]
     assert hashlib.sha256(text).hexdigest() == meta["sha256"]
+
+
+def test_trainer_instantiates_from_the_reference_config(tmp_path):
+    """howl/trainer_test.py:11-15: TrainingConfig.parse_file(test_training_config.json) -> Trainer(cfg), no CUDA needed."""
+    from howl_b200.config import TrainingConfig
+    from howl_b200.trainer import Trainer
+
+    cfg_path = tmp_path / "test_training_config.json"
+    cfg_path.write_text(json.dumps({      # the reference's test/test_data/test_training_config.json
+        "context_config": {"vocab": [" hey", "fire", "fox"]}, "batch_size": 16, "learning_rate": 0.01, "num_epochs": 10,
+        "lr_decay": 0.955, "weight_decay": 0.00001, "use_noise_dataset": False, "noise_datasets": [{"path": "/data/MS-SNSD"}],
+        "train_datasets": [{"path": "/data/speaker-id-split-medium"}], "val_datasets": [{"path": "/data/speaker-id-split-medium"}],
+        "test_datasets": [{"path": "/data/speaker-id-split-medium"}]}))
+    cfg = TrainingConfig.parse_file(cfg_path)
+    assert cfg.model_config.architecture == "res8" and cfg.train_datasets[0].audio_transform_config.num_mels == 40
+    assert cfg.inference_engine_config.inference_window_ms == 2000 and cfg.cache_config.cache_size == 128144
+    tr = Trainer(cfg)
+    assert tr.context.num_labels == 4 and tr.context.negative_label == 3 and tr.wake_word == " hey fire fox"
+    assert tr.step_obj is None                       # nothing touched CUDA
