@@ -195,3 +195,30 @@ def test_trainer_instantiates_from_the_reference_config(tmp_path):
     tr = Trainer(cfg)
     assert tr.context.num_labels == 4 and tr.context.negative_label == 3 and tr.wake_word == " hey fire fox"
     assert tr.step_obj is None                       # nothing touched CUDA
+
+
+def test_trainer_epoch_loop_decays_lr(monkeypatch):
+    """train.py:280-307 control flow (no CUDA: the fused step is replaced by a recorder)."""
+    import howl_b200.trainer as T
+    from howl_b200.config import ContextConfig, TrainingConfig
+
+    calls = []
+
+    class FakeStep:
+        def __init__(self, device, num_labels, batch, samples, lr, weight_decay, zmuv, seed):
+            self.device, self.lr = torch.device("cpu"), lr
+            calls.append(("init", num_labels, batch, samples, lr, weight_decay, zmuv, seed))
+
+        def step(self, pcm, labels):
+            assert pcm.dtype == torch.float32 and labels.dtype == torch.int64
+            calls.append(("step", self.lr))
+            return torch.tensor(2.0)
+
+    monkeypatch.setattr(T, "Res8TrainStep", FakeStep)
+    cfg = TrainingConfig(num_epochs=3, learning_rate=0.01, lr_decay=0.5, context_config=ContextConfig(vocab=["hey", "fire", "fox"], seed=7))
+    tr = T.Trainer(cfg)
+    batches = lambda epoch: [(torch.zeros(4, 800, dtype=torch.float64), torch.zeros(4, dtype=torch.int32))] * 2
+    losses = tr.train(batches, zmuv=(-1.0, 2.0))
+    assert losses == [2.0, 2.0, 2.0] and tr.epoch == 3
+    assert calls[0] == ("init", 4, 4, 800, 0.01, 1e-05, (-1.0, 2.0), 7)
+    assert [c[1] for c in calls[1:]] == [0.01, 0.01, 0.005, 0.005, 0.0025, 0.0025]
