@@ -471,3 +471,57 @@ def seq_lstm_ctc_step(feats, targets, target_lengths, lengths, params, state, bl
     with torch.no_grad():
         adamw_step(params, grads, m, v, step, lr, weight_decay)
     return loss.detach(), scores.detach(), grads, (new_state[0].detach(), new_state[1].detach())
+
+
+# =====================================================================================================
+# MobileNetClassifier (howl/model/cnn.py:15-29 on torchvision's MobileNetV2, width 1.0) -- forward restatement for the next
+# §8 row (a10).  Functional over a state dict with the reference's key names: `downsample.{0,1}.*` (Conv2d(1,3,3,pad=(1,3)) +
+# BatchNorm2d(3) + ReLU + MaxPool2d((1,2))), `model.features.N...` and `model.classifier.1.{weight,bias}`.
+# =====================================================================================================
+MOBILENET_V2_SETTING = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1))
+
+
+def _bn(x, sd, key, train, eps=1e-5):
+    """BatchNorm2d with affine parameters; train: biased batch statistics (running stats are not updated here)."""
+    if train:
+        mean = x.mean((0, 2, 3))
+        var = x.var((0, 2, 3), unbiased=False)
+    else:
+        mean, var = sd[key + ".running_mean"], sd[key + ".running_var"]
+    y = (x - mean[None, :, None, None]) / torch.sqrt(var[None, :, None, None] + eps)
+    return y * sd[key + ".weight"][None, :, None, None] + sd[key + ".bias"][None, :, None, None]
+
+
+def mobilenet_plan():
+    """[(features index, inp, oup, stride, expand)] of the 17 inverted-residual blocks (torchvision mobilenetv2.py)."""
+    plan, inp, idx = [], 32, 1
+    for t, c, n, s in MOBILENET_V2_SETTING:
+        for i in range(n):
+            plan.append((idx, inp, c, s if i == 0 else 1, t))
+            inp, idx = c, idx + 1
+    return plan
+
+
+def mobilenet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], train: bool = False) -> torch.Tensor:
+    """x: [B, C>=1, 40, F] stacked features (only the log-mel channel is used, cnn.py:27); returns logits [B, L].
+    Dropout of the classifier is the identity (eval) -- the training-mode restatement is deterministic up to dropout."""
+    import torch.nn.functional as F
+
+    relu6 = lambda t: torch.clamp(t, 0.0, 6.0)
+    x = x[:, :1]
+    x = F.conv2d(x, sd["downsample.0.weight"], sd["downsample.0.bias"], padding=(1, 3))
+    x = F.max_pool2d(torch.relu(_bn(x, sd, "downsample.1", train)), (1, 2))
+    f = "model.features."
+    x = relu6(_bn(F.conv2d(x, sd[f + "0.0.weight"], None, stride=2, padding=1), sd, f + "0.1", train))
+    for idx, inp, oup, stride, t in mobilenet_plan():
+        p, h, j = f"{f}{idx}.conv.", x, 0
+        if t != 1:      # pointwise expansion
+            h = relu6(_bn(F.conv2d(h, sd[f"{p}0.0.weight"]), sd, f"{p}0.1", train))
+            j = 1
+        hidden = h.shape[1]
+        h = relu6(_bn(F.conv2d(h, sd[f"{p}{j}.0.weight"], None, stride=stride, padding=1, groups=hidden), sd, f"{p}{j}.1", train))   # depthwise
+        h = _bn(F.conv2d(h, sd[f"{p}{j + 1}.weight"]), sd, f"{p}{j + 2}", train)                                                  # linear projection
+        x = x + h if (stride == 1 and inp == oup) else h
+    x = relu6(_bn(F.conv2d(x, sd[f + "18.0.weight"]), sd, f + "18.1", train))
+    x = x.mean((2, 3))                                                  # adaptive_avg_pool2d(1) + flatten
+    return x @ sd["model.classifier.1.weight"].t() + sd["model.classifier.1.bias"]

@@ -3,6 +3,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import howl_oracle as O
@@ -236,3 +237,30 @@ def test_seq_lstm_ctc_steps(golden):
             want = g[f"ctc.step{step}.grad.{k}"]
             np.testing.assert_allclose(grads[k].numpy(), want, rtol=1e-3, atol=1e-5 * max(1.0, np.abs(want).max()))
             params[k].copy_(torch.from_numpy(g[f"ctc.step{step}.sd.{k}"]))
+
+
+def test_mobilenet_restatement_matches_reference(golden):
+    """§8 row a10 groundwork: the functional MobileNetClassifier restatement against the reference module with the shipped GSC
+    checkpoint.  The fixture holds inputs + logits; the 9 MB of weights are read from the mounted reference (build container) --
+    skipped where it is absent (the GPU box has neither the mount nor, yet, a CUDA path for this model)."""
+    import hashlib
+    import os
+
+    ckpt = "/root/reference/howl-models/howl/experiments/commands_recognition/mobilenet/0/model-best.pt.bin"
+    if not os.path.exists(ckpt):
+        pytest.skip("reference checkpoint not mounted")
+    g = golden("mobilenet")
+    sd = torch.load(ckpt, map_location="cpu")
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k].numpy()).tobytes())
+    assert h.hexdigest() == bytes(g["digest"]).decode()
+    feats = torch.from_numpy(g["feats"])
+    assert len(O.mobilenet_plan()) == 17
+    with torch.no_grad():
+        np.testing.assert_allclose(O.mobilenet_forward(feats, sd, train=False).numpy(), g["logits_eval"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(O.mobilenet_forward(feats, sd, train=True).numpy(), g["logits_train"], rtol=1e-4, atol=1e-4)
+    # and the frontend of that workspace (zmuv.pt.bin of the run) reproduces the stored features
+    f2 = O.zmuv_forward(O.standard_audio_transform_f32(torch.from_numpy(g["pcm"])), torch.from_numpy(g["zmuv_mean"]), torch.from_numpy(g["zmuv_mean2"]))
+    np.testing.assert_allclose(f2.numpy(), g["feats"], rtol=1e-4, atol=1e-4)
