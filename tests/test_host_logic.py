@@ -222,3 +222,32 @@ def test_trainer_epoch_loop_decays_lr(monkeypatch):
     assert losses == [2.0, 2.0, 2.0] and tr.epoch == 3
     assert calls[0] == ("init", 4, 4, 800, 0.01, 1e-05, (-1.0, 2.0), 7)
     assert [c[1] for c in calls[1:]] == [0.01, 0.01, 0.005, 0.005, 0.0025, 0.0025]
+
+
+def test_plugin_installs_into_the_reference_package():
+    """install() re-points the hot-path classes inside an importable castorini/howl checkout (CPU: import
+    level only).  Runs in a subprocess so the patched reference modules do not leak into other tests; skipped where the
+    reference is not mounted."""
+    import subprocess
+
+    if not os.path.isdir("/root/reference/howl"):
+        pytest.skip("reference checkout not mounted")
+    code = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%r, "oracle")); sys.path.insert(0, %r)
+os.environ.update({"NUM_MELS": "40", "MAX_WINDOW_SIZE_SECONDS": "1", "VOCAB": '["hey","fire","fox"]', "INFERENCE_SEQUENCE": "[0,1,2]"})
+from make_golden import _install_shims
+_install_shims()
+import howl_b200.plugin as P
+assert P.install() is True
+from howl.model import RegisteredModel
+import howl.data.transform.transform as t, howl.data.transform.operator as op, howl.model.inference as inf
+names = {n: RegisteredModel.find_registered_class(n).__module__ for n in ("res8", "lstm", "seq-lstm")}
+assert set(names.values()) == {"howl_b200.model"}, names
+assert "mobilenet" in RegisteredModel.registered_names() and "las" in RegisteredModel.registered_names()   # others untouched
+assert t.StandardAudioTransform.__module__ == t.SpecAugmentTransform.__module__ == op.ZmuvTransform.__module__ == "howl_b200.transform"
+assert inf.FrameInferenceEngine.__module__ == "howl_b200.inference"
+print("ok")
+''' % (ROOT, ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
