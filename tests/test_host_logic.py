@@ -251,3 +251,58 @@ print("ok")
 ''' % (ROOT, ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_batchnorm_fold_identities_used_by_the_tensor_core_kernels():
+    """The algebra behind res8_tc.cu, in float64 on the CPU: (1) forward -- BatchNorm of the producer folded into the consumer's
+    weights, the border-dependent mean term carried per tap by a "ones" input channel that is 1 inside the image and 0 in the
+    zero padding; (2) weight gradient -- dW = rstd * (D - mean * D_ones) from the un-normalised activations and that channel."""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(0)
+    B, C, H, W = 3, 5, 6, 7
+    u = torch.randn(B, C, H, W, generator=g, dtype=torch.float64) * 2 + 1.5
+    w = torch.randn(4, C, 3, 3, generator=g, dtype=torch.float64)
+    mean, var = u.mean((0, 2, 3)), u.var((0, 2, 3), unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + 1e-5)
+    xn = (u - mean[None, :, None, None]) * rstd[None, :, None, None]
+    want = F.conv2d(xn, w, padding=1)                                   # the reference: conv of the normalised, ZERO padded tensor
+    # (1) folded weights + ones channel, raw activations with zero padding
+    w_f = w * rstd[None, :, None, None]
+    w_ones = -(w_f * mean[None, :, None, None]).sum(1, keepdim=True)     # per output channel and per tap
+    u1 = torch.cat([u, torch.ones(B, 1, H, W, dtype=torch.float64)], 1)
+    got = F.conv2d(u1, torch.cat([w_f, w_ones], 1), padding=1)
+    assert torch.allclose(got, want, rtol=1e-12, atol=1e-12)
+    # a constant bias instead of the per-tap ones weights is wrong exactly at the border pixels
+    bias_only = F.conv2d(u, w_f, padding=1) + w_ones.sum((1, 2, 3))[None, :, None, None]
+    assert torch.allclose(bias_only[:, :, 1:-1, 1:-1], want[:, :, 1:-1, 1:-1]) and not torch.allclose(bias_only, want)
+    # (2) weight gradient of that convolution w.r.t. w, from raw activations and the ones channel
+    dc = torch.randn(B, 4, H, W, generator=g, dtype=torch.float64)
+    w_req = w.clone().requires_grad_(True)
+    F.conv2d(xn, w_req, padding=1).backward(dc)
+    d_raw = torch.autograd.grad(F.conv2d(u1, (wz := torch.zeros(4, C + 1, 3, 3, dtype=torch.float64, requires_grad=True)), padding=1), wz, dc)[0]
+    folded = rstd[None, :, None, None] * (d_raw[:, :C] - mean[None, :, None, None] * d_raw[:, C:])
+    assert torch.allclose(folded, w_req.grad, rtol=1e-12, atol=1e-12)
+
+
+def test_operand_format_row_group_transpose():
+    """bn_bwd_apply_op_kernel: the 8 x 8 transpose among the 8 lanes of a raster-row group (three xor-butterfly stages) that turns
+    "lane = row, register = channel" into "lane = channel, register = row" for the weight gradient's K-major operand."""
+    d = np.arange(64).reshape(8, 8)          # d[lane][reg]
+    for s in (1, 2, 4):
+        new = d.copy()
+        for lane in range(8):
+            up = bool(lane & s)
+            for j in range(8):
+                if j & s:
+                    continue
+                send = d[lane][j] if up else d[lane][j + s]
+                partner = lane ^ s
+                got = d[partner][j] if bool(partner & s) else d[partner][j + s]
+                assert send == (d[lane][j] if up else d[lane][j + s])
+                if up:
+                    new[lane][j] = got
+                else:
+                    new[lane][j + s] = got
+        d = new
+    assert (d == np.arange(64).reshape(8, 8).T).all()
