@@ -126,7 +126,8 @@ int howl_b200_batch_gather(howl_ctx_t* ctx, void* stream, const float* clips, co
  *   conv0.weight[45,1,3,3] | conv1..6.weight[45,45,3,3] | output.weight[L,45] | output.bias[L]
  * BN running statistics: bn_running[6][2][45] f32 (mean, var per layer), num_batches_tracked[6] i64. */
 int64_t howl_b200_res8_param_count(int32_t num_labels);
-/* Bytes of workspace for a batch of B clips of `frames` x `n_mels` features (train != 0: keeps activations). */
+/* Bytes of workspace for a batch of B clips of `frames` x `n_mels` features (train != 0: keeps activations).  About 1.1 MB per
+ * 1 s utterance: 10 planar fp32 activation / gradient tensors plus 8 operand-format (bf16 hi, lo) tensors of the tcgen05 engine. */
 int64_t howl_b200_res8_workspace_bytes(int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels, int train);
 
 /*
