@@ -525,3 +525,72 @@ def mobilenet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], train: bool 
     x = relu6(_bn(F.conv2d(x, sd[f + "18.0.weight"]), sd, f + "18.1", train))
     x = x.mean((2, 3))                                                  # adaptive_avg_pool2d(1) + flatten
     return x @ sd["model.classifier.1.weight"].t() + sd["model.classifier.1.bias"]
+
+
+# =====================================================================================================
+# LASClassifier (howl/model/rnn.py:133-215) -- forward restatement, groundwork for §8 row a12.  State-dict keys as the reference's:
+# encoder.conv1/conv2, encoder.conv_encoder.{1,5} (BatchNorm2d), encoder.lstm_encoder.* (bidirectional, 1 layer), attn.*, fc.{0,3}.
+# =====================================================================================================
+def _lstm_direction(x: torch.Tensor, w_ih, w_hh, b_ih, b_hh, lengths: torch.Tensor, reverse: bool):
+    """One direction of torch.nn.LSTM over a packed batch.  x [T, B, I]; sequence b has lengths[b] valid steps; the reverse
+    direction starts at each sequence's own last step.  Returns (outputs [T, B, H] zero beyond the lengths, h_n [B, H])."""
+    tmax, b = int(lengths.max()), x.shape[1]
+    hdim = w_hh.shape[1]
+    h, c = x.new_zeros(b, hdim), x.new_zeros(b, hdim)
+    outs = [None] * tmax
+    for t in (range(tmax - 1, -1, -1) if reverse else range(tmax)):
+        gates = F.linear(x[t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+        i, f, g, o = gates.chunk(4, 1)
+        c_new = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h_new = torch.sigmoid(o) * torch.tanh(c_new)
+        live = (lengths > t).to(x.dtype).unsqueeze(1)
+        c = live * c_new + (1 - live) * c
+        h = live * h_new + (1 - live) * h
+        outs[t] = live * h_new
+    return torch.stack(outs), h
+
+
+def las_lengths(lengths: torch.Tensor, use_maxpool: bool = True) -> torch.Tensor:
+    """LASEncoder.forward's length arithmetic (rnn.py:163-168): two 3-wide convolutions with padding 2 (+2 frames each), each
+    followed by MaxPool2d((1, 2)); float floor at every step as the reference does."""
+    l = ((lengths.float() - 3 + 4) / 1 + 1).floor()
+    if use_maxpool:
+        l = (l / 2).floor()
+    l = ((l.float() - 3 + 4) / 1 + 1).floor()
+    if use_maxpool:
+        l = (l / 2).floor()
+    return l.long()
+
+
+def las_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], lengths: Optional[torch.Tensor] = None, train: bool = False,
+                num_heads: int = 4) -> torch.Tensor:
+    """x: [B, 3, 40, F] stacked features, lengths: frames per clip, sorted descending (pack_padded_sequence, rnn.py:169).
+    Dropout is the identity.  Returns logits [B, L]."""
+    if lengths is None:
+        lengths = torch.full((x.shape[0],), x.shape[-1], dtype=torch.long)
+    e = "encoder."
+    h = F.conv2d(x, sd[e + "conv1.weight"], sd[e + "conv1.bias"], padding=2)
+    h = F.max_pool2d(torch.relu(_bn(h, sd, e + "conv_encoder.1", train)), (1, 2))
+    h = F.conv2d(h, sd[e + "conv2.weight"], sd[e + "conv2.bias"], padding=2)
+    h = F.max_pool2d(torch.relu(_bn(h, sd, e + "conv_encoder.5", train)), (1, 2))
+    h = h.permute(3, 0, 1, 2).contiguous()
+    h = h.view(-1, h.size(1), h.size(2) * h.size(3))                       # [F', B, 8 * 44]
+    ll = las_lengths(lengths)
+    p = e + "lstm_encoder."
+    fwd, _ = _lstm_direction(h, sd[p + "weight_ih_l0"], sd[p + "weight_hh_l0"], sd[p + "bias_ih_l0"], sd[p + "bias_hh_l0"], ll, False)
+    bwd, _ = _lstm_direction(h, sd[p + "weight_ih_l0_reverse"], sd[p + "weight_hh_l0_reverse"], sd[p + "bias_ih_l0_reverse"],
+                             sd[p + "bias_hh_l0_reverse"], ll, True)
+    rnn_seq = torch.cat([fwd, bwd], 2)                                      # [Tmax, B, 192] = pad_packed_sequence output
+    mask = (torch.arange(rnn_seq.shape[0])[:, None] < ll[None, :]).to(rnn_seq.dtype)
+    # FixedAttentionModule.forward (rnn.py:181-191)
+    values = F.linear(rnn_seq, sd["attn.v_proj.weight"], sd["attn.v_proj.bias"])
+    keys = F.linear(rnn_seq, sd["attn.k_proj.weight"], sd["attn.k_proj.bias"])
+    t, b, d = values.shape
+    v4 = values.view(t, b, num_heads, d // num_heads)
+    k4 = keys.view(t, b, num_heads, d // num_heads)
+    cvec = sd["attn.context_vec"].view(-1, num_heads).unsqueeze(-1).expand(-1, -1, t)
+    logits = torch.einsum("ijkl,lki->ijk", v4, cvec) + ((1 - mask) * -100).unsqueeze(-1)
+    scores = torch.softmax(logits, 0)
+    context = torch.einsum("ijk,ijkl->jkl", scores, k4).reshape(b, -1)
+    hid = torch.relu(F.linear(context, sd["fc.0.weight"], sd["fc.0.bias"]))
+    return F.linear(hid, sd["fc.3.weight"], sd["fc.3.bias"])

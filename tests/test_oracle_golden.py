@@ -264,3 +264,26 @@ def test_mobilenet_restatement_matches_reference(golden):
     # and the frontend of that workspace (zmuv.pt.bin of the run) reproduces the stored features
     f2 = O.zmuv_forward(O.standard_audio_transform_f32(torch.from_numpy(g["pcm"])), torch.from_numpy(g["zmuv_mean"]), torch.from_numpy(g["zmuv_mean2"]))
     np.testing.assert_allclose(f2.numpy(), g["feats"], rtol=1e-4, atol=1e-4)
+
+
+def test_las_restatement_matches_reference(golden):
+    """§8 row a12 groundwork: LASClassifier forward (convs + packed BiLSTM + 4-head fixed attention + MLP) against the reference
+    module with the shipped GSC checkpoint, equal-length and ragged (length-sorted) batches; weights from the mounted reference."""
+    import hashlib
+    import os
+
+    ckpt = "/root/reference/howl-models/howl/experiments/commands_recognition/las/0/model-best.pt.bin"
+    if not os.path.exists(ckpt):
+        pytest.skip("reference checkpoint not mounted")
+    g = golden("las")
+    sd = torch.load(ckpt, map_location="cpu")
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k].numpy()).tobytes())
+    assert h.hexdigest() == bytes(g["digest"]).decode()
+    feats = torch.from_numpy(g["feats"])
+    assert O.las_lengths(torch.tensor([78, 58, 18])).tolist() == [21, 16, 6]      # (n + 2) // 2, twice
+    with torch.no_grad():
+        np.testing.assert_allclose(O.las_forward(feats, sd).numpy(), g["logits_full"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(O.las_forward(feats, sd, torch.from_numpy(g["lengths"])).numpy(), g["logits_ragged"], rtol=1e-4, atol=1e-4)
