@@ -1,6 +1,6 @@
 // Res8 45->45 3x3 convolutions on the 5th-generation tensor cores (tcgen05.mma + TMEM), sm_100a.
 //
-// Every tensor a convolution reads lives in HBM in OPERAND FORMAT: per utterance
+// Every tensor a convolution reads lives in HBM in OPERAND FORMAT (res8_common.cuh): per utterance
 //     [hi, lo][6 chunks of 8 channels][R raster rows][8 x bf16]          R = round_up((H + 2) * 11, 64)
 // in the padded "pitch 11" raster  q(y, x) = (y + 1) * 11 + (x + 1)  (one shared halo column between image rows), so
 // that a 3x3 tap is a shift of the operand start address by (dy - 1) * 11 + (dx - 1) rows and no kernel stages or
@@ -12,12 +12,15 @@
 //    rows of the raster are wasted M rows.  Per tile, tap and 16-channel K step: one N = 96 MMA  A_hi x [W_hi | W_lo]  and
 //    one N = 48 MMA  A_lo x W_hi  -- the kernels are bound by the shared-memory operand reads of these skinny MMAs, and
 //    this ordering reads the 4 KB A tile twice instead of three times.  Five 96-column accumulators rotate through TMEM;
-//    eight epilogue warps drain them (bias, ReLU, residual, BatchNorm statistics, operand-format output).
-//  * BatchNorm of the producer is folded into the consumer's weights (forward) or epilogue (weight gradient); the halo
-//    rows of the forward operand are overwritten with the channel mean so that zero padding of the NORMALISED tensor is
-//    reproduced exactly.
-//  * weight gradient: 9 GEMMs  dW_tap[out, in] += sum_q dC[q, out] * X[q + shift, in],  both operands MN-major from the
-//    same layout, 9 x 48 accumulator columns resident in TMEM across all utterances of a CTA.
+//    twelve epilogue warps drain them (ReLU, residual, BatchNorm statistics, planar and operand-format output), one warp
+//    issues the MMAs, one warp issues the TMA copies the moment a ring slot is released.
+//  * BatchNorm of the producer is folded into the consumer: into its weights for the forward (W' = W * rstd; the mean term
+//    rides per tap on the "ones" channel 45, which reproduces zero padding of the NORMALISED tensor exactly, tc_fold_kernel)
+//    and into the epilogue for the weight gradient.  Halo rows stay zero everywhere.
+//  * weight gradient: 9 GEMMs  dW_tap[out, in] += sum_q dC[q, out] * X[q + shift, in]  with the 9 x 48 accumulator columns
+//    resident in TMEM across all utterances of a CTA.  The dC tile of a K step is copied once from shared memory into tensor
+//    memory (tcgen05.cp, from the channel-major copy dc_opT of the gradient) and feeds all 18 MMAs of the step as the A operand;
+//    only the X tiles (MN-major, straight from the operand format) are read from shared memory per MMA.
 #include "res8_common.cuh"
 #include "tc_common.cuh"
 
@@ -175,6 +178,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
 
   if (warp == TS_EPI_WARPS + 1) {
     // ================= TMA loader: refills a ring slot the moment its last reader tile has been multiplied =================
+    // "Last reader" counts the tiles that own rows of the slot.  A neighbouring tile also reaches up to TC_PAD rows across the slot
+    // boundary (tap shifts), i.e. into the first / last 12 raster rows of the other utterance -- halo rows, zero in every
+    // utterance (and in the zero-initialised ring), so such a read may overlap the refill: it sees zeros before and after.
     if (tc::elect_one()) {
       const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.in_op);
       const size_t utt_bytes = (size_t)12 * R * 16;
