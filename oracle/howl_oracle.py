@@ -594,3 +594,35 @@ def las_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], lengths: Optional[
     context = torch.einsum("ijk,ijkl->jkl", scores, k4).reshape(b, -1)
     hid = torch.relu(F.linear(context, sd["fc.0.weight"], sd["fc.0.bias"]))
     return F.linear(hid, sd["fc.3.weight"], sd["fc.3.bias"])
+
+
+# =====================================================================================================
+# SimpleGru (howl/model/rnn.py:94-130) -- forward restatement.  Keys: conv_encoder.{0,1,4,6}, lstm_encoder.* (a GRU), dnn.{0,3}.
+# =====================================================================================================
+def gru_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], lengths: Optional[torch.Tensor] = None, train: bool = False) -> torch.Tensor:
+    """x: [B, C>=1, 40, F]; lengths: frames per clip, sorted descending (the reference adds 4 to them IN PLACE -- conv1 pads the
+    time axis by 3 on each side -- and halves them for the max-pool, rnn.py:121-124).  torch.nn.GRU cell: r, z, n gate rows;
+    n = tanh(W_in x + b_in + r * (W_hn h + b_hn)); h' = (1 - z) * n + z * h.  Returns logits [B, L] from the last valid state."""
+    if lengths is None:
+        lengths = torch.full((x.shape[0],), x.shape[-1], dtype=torch.long)
+    c = "conv_encoder."
+    h = F.conv2d(x[:, :1], sd[c + "0.weight"], sd[c + "0.bias"], padding=(1, 3))
+    h = F.max_pool2d(torch.relu(_bn(h, sd, c + "1", train)), (1, 2))
+    h = torch.relu(F.conv2d(h, sd[c + "4.weight"], sd[c + "4.bias"], padding=1))
+    h = _bn(h, sd, c + "6", train).squeeze(1)                             # [B, 40, F']
+    ll = ((lengths + 4).float() / 2).floor().long()
+    seq = h.permute(2, 0, 1).contiguous()                                   # [F', B, 40]
+    p = "lstm_encoder."
+    w_ih, w_hh, b_ih, b_hh = sd[p + "weight_ih_l0"], sd[p + "weight_hh_l0"], sd[p + "bias_ih_l0"], sd[p + "bias_hh_l0"]
+    state = seq.new_zeros(seq.shape[1], w_hh.shape[1])
+    for t in range(int(ll.max())):
+        gi, gh = F.linear(seq[t], w_ih, b_ih), F.linear(state, w_hh, b_hh)
+        i_r, i_z, i_n = gi.chunk(3, 1)
+        h_r, h_z, h_n = gh.chunk(3, 1)
+        r, z = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
+        n = torch.tanh(i_n + r * h_n)
+        new = (1 - z) * n + z * state
+        live = (ll > t).to(seq.dtype).unsqueeze(1)
+        state = live * new + (1 - live) * state
+    hid = torch.relu(F.linear(state, sd["dnn.0.weight"], sd["dnn.0.bias"]))
+    return F.linear(hid, sd["dnn.3.weight"], sd["dnn.3.bias"])

@@ -287,3 +287,15 @@ def test_las_restatement_matches_reference(golden):
     with torch.no_grad():
         np.testing.assert_allclose(O.las_forward(feats, sd).numpy(), g["logits_full"], rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(O.las_forward(feats, sd, torch.from_numpy(g["lengths"])).numpy(), g["logits_ragged"], rtol=1e-4, atol=1e-4)
+
+
+def test_gru_restatement_matches_reference(golden):
+    """SimpleGru forward (conv encoder + packed GRU + MLP) against the reference module, seeded weights stored in the fixture."""
+    g = golden("gru")
+    sd = {k[3:]: torch.from_numpy(np.asarray(g[k])) for k in g if k.startswith("sd.")}
+    feats, lengths = torch.from_numpy(g["feats"]), torch.from_numpy(g["lengths"])
+    with torch.no_grad():
+        np.testing.assert_allclose(O.gru_forward(feats, sd).numpy(), g["logits_eval_full"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(O.gru_forward(feats, sd, lengths).numpy(), g["logits_eval_ragged"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(O.gru_forward(feats, sd, lengths, train=True).numpy(), g["logits_train_ragged"], rtol=1e-4, atol=1e-5)
+    assert lengths.tolist() == [78, 68, 43, 23]       # the restatement must not modify its argument (the reference does: `lengths += 4`)
