@@ -8,7 +8,7 @@ LIB := howl_b200/lib/libhowl_b200.so
 
 all: $(LIB)
 
-build/%.o: howl_b200/csrc/%.cu $(wildcard howl_b200/csrc/*.cuh) include/howl_b200.h
+build/%.o: howl_b200/csrc/%.cu $(wildcard howl_b200/csrc/*.cuh) include/howl_b200.h include/howl_b200_debug.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -12,6 +12,7 @@ from typing import Dict, List
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhowl_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "howl_b200.h")
+DEBUG_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "howl_b200_debug.h")   # tuning aids / test hooks
 
 HOWL_OK = 0
 FE_TIME_MAJOR, FE_MELS_ONLY, FE_STACKED, FE_ZMUV = 0x1, 0x2, 0x4, 0x10
@@ -39,6 +40,7 @@ SIGNATURES: Dict[str, tuple] = {
     "howl_b200_selftest_umma": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32]),
     "howl_b200_debug_stream_profile": (C.c_int, [_vp, _vp, _i32]),
     "howl_b200_debug_umma_bench": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "howl_b200_res8_debug_masks": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
     "howl_b200_profile_begin": (C.c_int, [_vp, _vp]),
     "howl_b200_profile_end": (C.c_int, [_vp, _vp, _sz, _vp, _i32]),
     "howl_b200_num_frames": (_i64, [_i64, _i32]),
@@ -73,11 +75,13 @@ SIGNATURES: Dict[str, tuple] = {
 _lib = None
 
 
-def header_symbols() -> List[str]:
-    """Every function name declared in include/howl_b200.h."""
-    text = open(HEADER_PATH).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(howl_b200_[a-z0-9_]+)\s*\(", text)))
+def header_symbols(debug: bool = True) -> List[str]:
+    """Every function name declared in include/howl_b200.h (+ include/howl_b200_debug.h when `debug`)."""
+    names = set()
+    for path in [HEADER_PATH] + ([DEBUG_HEADER_PATH] if debug else []):
+        text = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+        names |= set(re.findall(r"\b(howl_b200_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def load():

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "../../include/howl_b200_debug.h"
 
 char g_howl_create_error[512] = "";
 

@@ -17,6 +17,7 @@
 
 #include "res8_common.cuh"
 #include "tc_common.cuh"
+#include "../../include/howl_b200_debug.h"
 
 // =============================================================================================
 // workspace carve-up
@@ -1011,4 +1012,64 @@ extern "C" int howl_b200_res8_bwd_dlogits(howl_ctx_t* ctx, void* stream, const f
   HOWL_REQUIRE(ctx, feats && dlogits && params && grads, HOWL_E_INVALID, "res8_bwd_dlogits: null pointer");
   return r8_bwd_impl(ctx, stream, feats, nullptr, dlogits, B, frames, n_mels, num_labels, 1, params, grads, nullptr,
                      workspace, workspace_bytes);
+}
+
+// =============================================================================================
+// test hook (include/howl_b200_debug.h): the ReLU decisions of the backward, for the mask-forced gradient oracle
+// =============================================================================================
+// conv0: the same FMA order as conv0_pool_kernel / conv0_bwd_kernel (ky outer, kx inner, from 0)
+__global__ void debug_mask0_kernel(const float* __restrict__ feats, const float* __restrict__ w0, uint8_t* __restrict__ mask0,
+                                   int64_t B, int F, int H) {
+  const int rows = 3 * H;
+  const int64_t n = B * rows * R8_MELS;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % R8_MELS), y = (int)((i / R8_MELS) % rows);
+    const int64_t b = i / ((int64_t)R8_MELS * rows);
+    float patch[3][3];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        patch[ky][kx] = (yy >= 0 && yy < F && xx >= 0 && xx < R8_MELS) ? feats[(b * F + yy) * R8_MELS + xx] : 0.f;
+      }
+    for (int oc = 0; oc < R8_C; ++oc) {
+      float pre = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) pre = fmaf(__ldg(w0 + oc * 9 + ky * 3 + kx), patch[ky][kx], pre);
+      mask0[((b * R8_C + oc) * rows + y) * R8_MELS + x] = pre > 0.f ? 1 : 0;
+    }
+  }
+}
+
+__global__ void debug_mask_kernel(const float* __restrict__ u, const float* __restrict__ prev, uint8_t* __restrict__ mask, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = u[i] > (prev ? prev[i] : 0.f) ? 1 : 0;
+}
+
+extern "C" int howl_b200_res8_debug_masks(howl_ctx_t* ctx, void* stream, const float* feats, const float* params, int64_t B,
+                                          int32_t frames, int32_t n_mels, int32_t num_labels, const void* workspace,
+                                          size_t workspace_bytes, uint8_t* mask0, uint8_t* masks16) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, feats && params, HOWL_E_INVALID, "res8_debug_masks: null pointer");
+  R8Ws ws;
+  int rc = r8_check(ctx, B, frames, n_mels, num_labels, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = frames / 3;
+  const int64_t n = B * R8_C * H * R8_W;
+  if (mask0) {
+    debug_mask0_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(feats, params, mask0, B, frames, H);
+    HOWL_LAUNCHED(ctx, "debug_mask0");
+  }
+  if (masks16) {
+    for (int i = 1; i <= R8_LAYERS; ++i) {
+      const float* prev = (i % 2 == 0) ? ((i == 2) ? ws.a0 : ws.u[i - 3]) : nullptr;
+      debug_mask_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ws.u[i - 1], prev, masks16 + (size_t)(i - 1) * n, n);
+      HOWL_LAUNCHED(ctx, "debug_mask");
+    }
+  }
+  return HOWL_OK;
 }

@@ -208,6 +208,18 @@ class Context:
                                                      num_labels, _ptr(params), _ptr(grads), _ptr(ws), ws.numel()),
                  "res8_bwd_dlogits")
 
+    def res8_debug_masks(self, feats, params, ws, conv0: bool = True):
+        """Test hook (include/howl_b200_debug.h): the ReLU decisions of the backward for the forward kept in `ws`.
+        -> (mask0 [B,45,3H,M] uint8 or None, masks [6,B,45,H,10] uint8)."""
+        b, f, m = feats.shape
+        h = f // 3
+        num_labels = self._labels_from_params(params)
+        mask0 = torch.empty(b, 45, 3 * h, m, dtype=torch.uint8, device=self.device) if conv0 else None
+        masks = torch.empty(6, b, 45, h, 10, dtype=torch.uint8, device=self.device)
+        self._rc(self.lib.howl_b200_res8_debug_masks(self.handle, self._stream(), _ptr(feats), _ptr(params), b, f, m, num_labels,
+                                                     _ptr(ws), ws.numel(), _ptr(mask0), _ptr(masks)), "res8_debug_masks")
+        return mask0, masks
+
     # ------------------------------------------------------------------ lstm / seq-lstm
     def lstm_param_count(self, num_labels: int) -> int:
         return int(self.lib.howl_b200_lstm_param_count(num_labels, self.n_mels))

@@ -47,7 +47,59 @@ def mel_filterbank(n_mels: int, sample_rate: int = 16000, n_freqs: int = 257) ->
     return torch.clamp(torch.minimum(down, up), min=0.0)
 
 
-class Res8TrainStep:
+class _HostPipeline:
+    """Host-input front of a fused step (SURVEY §8 row a1 = ``ClassificationBatch.to``, howl/data/common/batch.py:27-32):
+    ``step_host(*pinned_host_tensors)`` copies the step's inputs H2D on a copy stream into one of ``HOST_SLOTS`` device slots
+    (so the copy of step k+1.. overlaps the compute of step k), runs ``self.step`` on the slot and reads the loss back (D2H)
+    asynchronously; ``flush_host()`` drains and returns the last loss."""
+
+    HOST_SLOTS = 3
+
+    def _init_host_pipeline(self):
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._slots = None
+        self._host_loss = torch.zeros(1).pin_memory()
+        self._host_i = 0
+
+    def step_host(self, *host_tensors: torch.Tensor) -> None:
+        dev = self.device
+        if self._slots is None or any(tuple(d.shape) != tuple(h.shape) or d.dtype != h.dtype for d, h in zip(self._slots[0], host_tensors)):
+            self._slots = [tuple(torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host_tensors) for _ in range(self.HOST_SLOTS)]
+            self._slot_free = [torch.cuda.Event() for _ in range(self.HOST_SLOTS)]
+            self._slot_ready = [torch.cuda.Event() for _ in range(self.HOST_SLOTS)]
+            for e in self._slot_free:
+                e.record(torch.cuda.current_stream(dev))
+        k = self._host_i % self.HOST_SLOTS
+        self._host_i += 1
+        slot = self._slots[k]
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._slot_free[k])
+            for d, h in zip(slot, host_tensors):
+                d.copy_(h, non_blocking=True)
+            self._slot_ready[k].record(self._copy_stream)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(self._slot_ready[k])
+        self.step(*slot)
+        self._slot_free[k].record(cur)
+        self._host_loss.copy_(self.loss, non_blocking=True)
+
+    def flush_host(self) -> float:
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(self._host_loss.item())
+
+    def profile_groups(self, *inputs, reps: int = 3):
+        """Device time of every kernel label over `reps` steps (CUDA events on the launching stream)."""
+        acc, cnt = {}, {}
+        for _ in range(reps):
+            self.ctx.profile_begin()
+            self.step(*inputs)
+            for name, ms in self.ctx.profile_end():
+                acc[name] = acc.get(name, 0.0) + ms
+                cnt[name] = cnt.get(name, 0) + 1
+        return [{"name": k, "ms": acc[k] / reps, "launches_per_step": cnt[k] // reps} for k in acc]
+
+
+class Res8TrainStep(_HostPipeline):
     def __init__(self, device, num_labels: int, batch: int, samples: int, n_mels: int = 40, lr: float = 0.01,
                  weight_decay: float = 1e-5, zmuv: Tuple[float, float] = (0.0, 1.0), seed: int = 0, world_size: int = 1):
         self.ctx = Context(device, n_mels=n_mels)
@@ -67,13 +119,7 @@ class Res8TrainStep:
         self.feat_bytes = (batch * self.frames * n_mels * 4 + 255) // 256 * 256
         self.ws = torch.empty(self.ctx.train_step_workspace_bytes(batch, samples, num_labels), dtype=torch.uint8, device=dev)
         self.step_count = 0
-        # host-input pipeline (step_host)
-        self._copy_stream = torch.cuda.Stream(dev)
-        self._slots = None
-        self._slot_free = None
-        self._slot_ready = None
-        self._host_loss = torch.zeros(1).pin_memory()
-        self._host_i = 0
+        self._init_host_pipeline()
 
     # ------------------------------------------------------------------ device-resident step
     def step(self, pcm: torch.Tensor, labels: torch.Tensor, rects: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -94,48 +140,6 @@ class Res8TrainStep:
             allreduce_flat_grads(self.grads)     # one NCCL all-reduce(SUM) of the flat gradient over NVLink
             c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
         return self.loss
-
-    # ------------------------------------------------------------------ host-input step (end-to-end path)
-    def step_host(self, pcm_host: torch.Tensor, labels_host: torch.Tensor) -> None:
-        """Same step fed from (pinned) host tensors: the H2D copies ride a copy stream, double buffered against
-        compute; the loss of every step is read back (D2H) asynchronously."""
-        dev = self.device
-        if self._slots is None:
-            self._slots = [(torch.empty(self.batch, self.samples, device=dev), torch.empty(self.batch, dtype=torch.int64, device=dev))
-                           for _ in range(2)]
-            self._slot_free = [torch.cuda.Event() for _ in range(2)]
-            self._slot_ready = [torch.cuda.Event() for _ in range(2)]
-            for e in self._slot_free:
-                e.record(torch.cuda.current_stream(dev))
-        k = self._host_i % 2
-        self._host_i += 1
-        pcm_d, lab_d = self._slots[k]
-        with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(self._slot_free[k])
-            pcm_d.copy_(pcm_host, non_blocking=True)
-            lab_d.copy_(labels_host, non_blocking=True)
-            self._slot_ready[k].record(self._copy_stream)
-        cur = torch.cuda.current_stream(dev)
-        cur.wait_event(self._slot_ready[k])
-        self.step(pcm_d, lab_d)
-        self._slot_free[k].record(cur)
-        self._host_loss.copy_(self.loss, non_blocking=True)
-
-    def flush_host(self) -> float:
-        torch.cuda.current_stream(self.device).synchronize()
-        return float(self._host_loss.item())
-
-    # ------------------------------------------------------------------ per-kernel timing
-    def profile_groups(self, pcm, labels, reps: int = 3):
-        """Device time of every kernel label over `reps` steps (CUDA events on the launching stream)."""
-        acc, cnt = {}, {}
-        for _ in range(reps):
-            self.ctx.profile_begin()
-            self.step(pcm, labels)
-            for name, ms in self.ctx.profile_end():
-                acc[name] = acc.get(name, 0.0) + ms
-                cnt[name] = cnt.get(name, 0) + 1
-        return [{"name": k, "ms": acc[k] / reps, "launches_per_step": cnt[k] // reps} for k in acc]
 
     # ------------------------------------------------------------------ state_dict interop (SURVEY App. B.2)
     def state_dict(self):
@@ -158,7 +162,7 @@ def lstm_param_shapes(num_labels: int, n_mels: int = 40):
             ("dnn.2.weight", (num_labels, 256)), ("dnn.2.bias", (num_labels,))]
 
 
-class LstmTrainStep:
+class LstmTrainStep(_HostPipeline):
     """Fused train step of the `lstm` model (frame objective): frontend -> LSTM -> MLP -> CE -> BPTT -> AdamW."""
 
     def __init__(self, device, num_labels: int, batch: int, samples: int, n_mels: int = 40, lr: float = 0.01,
@@ -186,6 +190,7 @@ class LstmTrainStep:
         self.ws = torch.empty(self.ctx.lstm_train_step_workspace_bytes(batch, samples, self.steps, num_labels), dtype=torch.uint8,
                               device=dev)
         self.step_count = 0
+        self._init_host_pipeline()
 
     def step(self, pcm: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         self.step_count += 1
@@ -205,16 +210,6 @@ class LstmTrainStep:
             allreduce_flat_grads(self.grads)
             c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
         return self.loss
-
-    def profile_groups(self, pcm, labels, reps: int = 3):
-        acc, cnt = {}, {}
-        for _ in range(reps):
-            self.ctx.profile_begin()
-            self.step(pcm, labels)
-            for name, ms in self.ctx.profile_end():
-                acc[name] = acc.get(name, 0.0) + ms
-                cnt[name] = cnt.get(name, 0) + 1
-        return [{"name": k, "ms": acc[k] / reps, "launches_per_step": cnt[k] // reps} for k in acc]
 
 
 class SeqLstmCtcTrainStep(LstmTrainStep):
@@ -250,16 +245,6 @@ class SeqLstmCtcTrainStep(LstmTrainStep):
             allreduce_flat_grads(self.grads)
             c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
         return self.loss
-
-    def profile_groups(self, pcm, targets, target_lengths, reps: int = 3):
-        acc, cnt = {}, {}
-        for _ in range(reps):
-            self.ctx.profile_begin()
-            self.step(pcm, targets, target_lengths)
-            for name, ms in self.ctx.profile_end():
-                acc[name] = acc.get(name, 0.0) + ms
-                cnt[name] = cnt.get(name, 0) + 1
-        return [{"name": k, "ms": acc[k] / reps, "launches_per_step": cnt[k] // reps} for k in acc]
 
 
 class Trainer:

@@ -62,19 +62,6 @@ int64_t howl_b200_launch_count(const howl_ctx_t* ctx);
  * and fp32 accumulation (logits within 1e-5 of fp32); 0 = exact-fp32 FFMA kernels; 2 = FAST mode, the same kernels with the
  * low-order bf16 terms skipped (single bf16 x bf16 products, ~3e-3 relative: outside the 1e-4 parity bar, never the default). */
 int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value);
-/* Debug aid: one 128x48x32 GEMM through the library's UMMA descriptor helpers (A, B fp32 device arrays, bf16-rounded
- * inside; mn_major selects the operand layout of the weight-gradient GEMM); D fp32 [128][48]. */
-int howl_b200_selftest_umma(howl_ctx_t* ctx, void* stream, const float* A, const float* B, float* D, int32_t mn_major,
-                            int32_t variant);
-
-/* Tuning aid: the tensor-core forward (kind 1) or data-gradient (kind 2) kernels write per-CTA cycle counters of their
- * pipeline waits to buf[sm_count][16] (uint64, device memory); buf = NULL switches it off.  See tests/profile_stream.py. */
-int howl_b200_debug_stream_profile(howl_ctx_t* ctx, void* buf, int32_t kind);
-
-/* Tuning aid: cycles (device int64) that `iters` back-to-back M=128 (mode bit 2: 64) x N x 16 bf16 tcgen05.mma take on one SM.
- * mode bit 0: A operand from tensor memory, bit 1: B operand MN-major. */
-int howl_b200_debug_umma_bench(howl_ctx_t* ctx, void* stream, int32_t mode, int32_t N, int32_t iters, long long* cycles);
-
 /* ---- per-launch device timing (CUDA events on the launching stream; used by bench.py's roofline) --------- */
 /* After profile_begin every kernel launch of this context is bracketed by an event on `stream`. */
 int howl_b200_profile_begin(howl_ctx_t* ctx, void* stream);

@@ -1,0 +1,42 @@
+/*
+ * howl_b200_debug.h -- tuning aids and test hooks of libhowl_b200.so.  NOT part of the drop-in boundary
+ * (include/howl_b200.h): nothing a howl maintainer binds lives here.  Used by tools/ (micro-benchmarks) and by
+ * tests/ (the mask-forced gradient oracle).
+ */
+#ifndef HOWL_B200_DEBUG_H_
+#define HOWL_B200_DEBUG_H_
+
+#include "howl_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One 128x48x32 GEMM through the library's UMMA descriptor helpers (A, B fp32 device arrays, bf16-rounded inside;
+ * mn_major selects the operand layout of the weight-gradient GEMM); D fp32 [128][48]. */
+int howl_b200_selftest_umma(howl_ctx_t* ctx, void* stream, const float* A, const float* B, float* D, int32_t mn_major,
+                            int32_t variant);
+
+/* The tensor-core forward (kind 1) or data-gradient (kind 2) kernels write per-CTA cycle counters of their pipeline
+ * waits to buf[sm_count][16] (uint64, device memory); buf = NULL switches it off.  See tools/profile_stream.py. */
+int howl_b200_debug_stream_profile(howl_ctx_t* ctx, void* buf, int32_t kind);
+
+/* Cycles (device int64) that `iters` back-to-back M=128 (mode bit 2: 64) x N x 16 bf16 tcgen05.mma take on one SM.
+ * mode bit 0: A operand from tensor memory, bit 1: B operand MN-major. */
+int howl_b200_debug_umma_bench(howl_ctx_t* ctx, void* stream, int32_t mode, int32_t N, int32_t iters, long long* cycles);
+
+/*
+ * Test hook for the mask-forced gradient oracle (tests/test_gpu_parity.py): the ReLU decisions the backward of the
+ * forward kept in `workspace` takes, as bytes (1 = gradient passes).
+ *   mask0   [B, 45, 3*H, n_mels]  conv0 pre-activation > 0 at the pixels the (3,4) average pooling keeps (H = frames / 3)
+ *   masks16 [6, B, 45, H, 10]     layers 1..6: relu(conv_i) > 0, i.e. u_i > 0 (odd layers) or u_i > residual (even layers)
+ * Either pointer may be NULL.  feats / params as given to howl_b200_res8_fwd.
+ */
+int howl_b200_res8_debug_masks(howl_ctx_t* ctx, void* stream, const float* feats, const float* params, int64_t B,
+                               int32_t frames, int32_t n_mels, int32_t num_labels, const void* workspace,
+                               size_t workspace_bytes, uint8_t* mask0, uint8_t* masks16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOWL_B200_DEBUG_H_ */

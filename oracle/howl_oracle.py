@@ -125,7 +125,7 @@ def power_spectrogram_f32(pcm: torch.Tensor) -> torch.Tensor:
 
     center=True reflect pad 256, periodic Hann(512), hop 200, onesided, power 2, no normalisation.
     """
-    window = torch.hann_window(N_FFT, periodic=True, dtype=torch.float32)
+    window = torch.hann_window(N_FFT, periodic=True, dtype=torch.float32, device=pcm.device)
     spec = torch.stft(
         pcm.float(), N_FFT, hop_length=HOP, win_length=N_FFT, window=window, center=True,
         pad_mode="reflect", normalized=False, onesided=True, return_complex=True,
@@ -148,7 +148,7 @@ def deltas_f32(x: torch.Tensor) -> torch.Tensor:
     shape = x.shape
     flat = x.reshape(1, -1, shape[-1])
     padded = F.pad(flat, (2, 2), mode="replicate")
-    kernel = torch.arange(-2, 3, dtype=x.dtype).repeat(flat.shape[1], 1, 1)
+    kernel = torch.arange(-2, 3, dtype=x.dtype, device=x.device).repeat(flat.shape[1], 1, 1)
     out = F.conv1d(padded, kernel, groups=flat.shape[1]) / 10.0
     return out.reshape(shape)
 
@@ -299,6 +299,36 @@ def res8_forward(
     x = x.view(x.size(0), x.size(1), -1).mean(2)
     if taps is not None:
         taps["pooled"] = x
+    return F.linear(x, params["output.weight"], params["output.bias"])
+
+
+def res8_forward_masked(
+    x: torch.Tensor,
+    params: Dict[str, torch.Tensor],
+    mask0: torch.Tensor,
+    masks: torch.Tensor,
+) -> torch.Tensor:
+    """``Res8.forward`` (howl/model/cnn.py:127-145, train-mode BatchNorm) with every ReLU replaced by a GIVEN 0/1 mask:
+    ``relu(z) -> z * mask``.  With the masks the implementation under test actually took, d(loss)/d(weights) of this graph is
+    the gradient that implementation must produce -- free of the "flip noise" of pre-activations that sit within rounding of
+    zero (parity notes), so it can be held to a tight tolerance.
+
+    ``mask0`` [B,45,3H,M]: conv0 pre-activation > 0 on the rows the (3,4) pooling keeps; ``masks`` [6,B,45,H,10]: layers 1..6.
+    Any float dtype (use float64).  Running statistics are not touched.
+    """
+    x = x[:, :1].permute(0, 1, 3, 2).contiguous()
+    h3 = mask0.shape[2]
+    y = F.conv2d(x, params["conv0.weight"], None, padding=1)[:, :, :h3] * mask0.to(x.dtype)
+    x = old_x = F.avg_pool2d(y, RES8_POOL)
+    for i in range(1, RES8_LAYERS + 1):
+        y = F.conv2d(x, params[f"conv{i}.weight"], None, padding=1) * masks[i - 1].to(x.dtype)
+        if i % 2 == 0:
+            x = y + old_x
+            old_x = x
+        else:
+            x = y
+        x = F.batch_norm(x, None, None, None, None, True, BN_MOMENTUM, BN_EPS)
+    x = x.view(x.size(0), x.size(1), -1).mean(2)
     return F.linear(x, params["output.weight"], params["output.bias"])
 
 

@@ -24,6 +24,9 @@ def test_every_header_symbol_is_exported_and_bound(lib):
         assert hasattr(lib, n), n
         assert n in _lib.SIGNATURES, f"{n} declared in the header but not bound in howl_b200/_lib.py"
     assert set(_lib.SIGNATURES) == set(names)
+    # the drop-in boundary (howl_b200.h) carries no tuning aids / test hooks: those live in howl_b200_debug.h
+    product = _lib.header_symbols(debug=False)
+    assert not [n for n in product if "debug" in n or "selftest" in n]
 
 
 def test_abi_version(lib):

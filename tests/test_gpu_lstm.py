@@ -93,7 +93,7 @@ def test_lstm_module_reference_train_steps(golden):
         model.load_state_dict({k: torch.from_numpy(g[f"step{step}.sd.{k}"]) for k in model.state_dict()})
 
 
-@pytest.mark.parametrize("B,T", [(1, 8000), (33, 8000), (70, 16000)])
+@pytest.mark.parametrize("B,T", [(1, 8000), (33, 8000), (70, 16000), (2048, 8000)])   # last: BASELINE config 4's batch
 def test_lstm_fused_train_step_vs_oracle(B, T):
     import howl_b200
 
@@ -187,7 +187,7 @@ def test_seq_lstm_ctc_reference_steps_module_and_fused(golden):
     ctx.close()
 
 
-@pytest.mark.parametrize("B,T", [(3, 8000), (40, 16000)])
+@pytest.mark.parametrize("B,T", [(3, 8000), (40, 16000), (2048, 8000)])   # last: BASELINE config 4 (seq-lstm + CTC, batch 2048)
 def test_ctc_kernel_vs_torch_ragged(B, T):
     """Own CTC kernel against torch's F.ctc_loss on ragged input / target lengths (incl. repeated labels, length-1 targets)."""
     import howl_b200
