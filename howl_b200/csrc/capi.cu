@@ -21,6 +21,7 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
   if (!cfg || !out_ctx) CREATE_FAIL(HOWL_E_INVALID, "create: null argument");
   if (cfg->n_fft != HOWL_NFFT) CREATE_FAIL(HOWL_E_UNSUPPORTED, "create: n_fft=%d (only 512 is built)", cfg->n_fft);
   if (cfg->hop <= 0 || cfg->hop > HOWL_NFFT) CREATE_FAIL(HOWL_E_INVALID, "create: hop=%d out of range", cfg->hop);
+  if (cfg->hop & 1) CREATE_FAIL(HOWL_E_UNSUPPORTED, "create: odd hop=%d (the frontend reads frames with 64-bit vector loads)", cfg->hop);
   if (cfg->n_mels < 1 || cfg->n_mels > HOWL_MAX_MELS)
     CREATE_FAIL(HOWL_E_UNSUPPORTED, "create: n_mels=%d outside 1..%d", cfg->n_mels, HOWL_MAX_MELS);
   int ndev = 0;

@@ -107,17 +107,33 @@ def _flatten_into(owner, params, attr: str, device):
     return flat
 
 
+def _check_unchanged(ctx, flat):
+    if flat.data_ptr() != ctx.flat_ptr or flat._version != ctx.flat_version:
+        raise RuntimeError("howl_b200: the model's parameters were modified (or moved) between forward and backward; "
+                           "gradients would be computed against the wrong weights")
+
+
 class _Res8Function(torch.autograd.Function):
+    """Everything backward needs travels on the autograd ctx: the activation workspace of THIS forward (a fresh allocation per
+    training forward -- a later forward, an eval pass or a larger batch cannot overwrite it) and the identity / version of the
+    flat parameter buffer (checked in backward, as torch does for saved tensors)."""
+
     @staticmethod
     def forward(ctx, model, feats, labels_hint, *params):
-        logits = model._run_forward(feats, train=True)
-        ctx.model, ctx.feats = model, feats
+        c = get_context(feats.device, feats.shape[2])
+        ws = torch.empty(c.res8_workspace_bytes(feats.shape[0], feats.shape[1], model.num_labels, True), dtype=torch.uint8,
+                         device=feats.device)
+        logits = model._run_forward(feats, train=True, ws=ws)
+        ctx.model, ctx.feats, ctx.ws = model, feats, ws
+        ctx.flat_ptr, ctx.flat_version = model._flat.data_ptr(), model._flat._version
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         model = ctx.model
-        grads = model._run_backward(ctx.feats, dlogits.contiguous())
+        _check_unchanged(ctx, model._flat)
+        grads = model._run_backward(ctx.feats, dlogits.contiguous(), ctx.ws)
+        ctx.ws = None
         out, off = [], 0
         for _, shape in res8_param_shapes(model.num_labels):
             n = math.prod(shape)
@@ -171,18 +187,18 @@ class Res8(RegisteredModel, name="res8"):
             self._ws = torch.empty(need, dtype=torch.uint8, device=ctx.device)
         return self._ws
 
-    def _run_forward(self, feats, train: bool):
+    def _run_forward(self, feats, train: bool, ws=None):
         ctx = get_context(feats.device, feats.shape[2])
-        self._ensure_flat(feats.device)
-        ws = self._workspace(ctx, feats.shape[0], feats.shape[1])
+        if ws is None:      # inference / no-grad passes share one scratch workspace; training forwards bring their own
+            ws = self._workspace(ctx, feats.shape[0], feats.shape[1])
         return ctx.res8_fwd(feats, self._flat, self._bn_flat, self._nbt, train, ws)
 
-    def _run_backward(self, feats, dlogits):
+    def _run_backward(self, feats, dlogits, ws):
         # generic upstream gradient: the library's backward starts from CrossEntropy; for an arbitrary dlogits the
         # head backward is re-expressed through a label-free entry point
         ctx = get_context(feats.device, feats.shape[2])
         grads = torch.empty_like(self._flat)
-        ctx.res8_bwd_from_dlogits(feats, dlogits, self._flat, grads, self._ws)
+        ctx.res8_bwd_from_dlogits(feats, dlogits, self._flat, grads, ws)
         return grads
 
     # ---- nn.Module API ----------------------------------------------------------------------------------
@@ -191,6 +207,7 @@ class Res8(RegisteredModel, name="res8"):
             raise RuntimeError("howl_b200.Res8 needs CUDA tensors (no CPU fallback)")
         ctx = get_context(x.device, x.shape[2])
         feats = ctx.to_time_major(x.contiguous().float())      # x[:, :1].permute(0,1,3,2).contiguous()  (cnn.py:128-129)
+        self._ensure_flat(feats.device)
         if self.training and torch.is_grad_enabled():
             return _Res8Function.apply(self, feats, None, *self._param_list())
         return self._run_forward(feats, train=self.training)
@@ -213,16 +230,22 @@ class _LstmCell(nn.Module):
 class _LstmFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, feats, lengths, max_steps, *params):
-        ctx.model, ctx.shape, ctx.lengths, ctx.max_steps = model, tuple(feats.shape), lengths, max_steps
-        return model._run(feats, lengths, max_steps, train=True)
+        c = get_context(feats.device, feats.shape[2])
+        ws = torch.empty(c.lstm_workspace_bytes(feats.shape[0], max_steps, model.num_labels, True, model.SEQUENTIAL), dtype=torch.uint8,
+                         device=feats.device)          # per-forward workspace, kept on the autograd ctx (see _Res8Function)
+        ctx.model, ctx.shape, ctx.lengths, ctx.max_steps, ctx.ws = model, tuple(feats.shape), lengths, max_steps, ws
+        ctx.flat_ptr, ctx.flat_version = model._flat.data_ptr(), model._flat._version
+        return model._run(feats, lengths, max_steps, train=True, ws=ws)
 
     @staticmethod
     def backward(ctx, dlogits):
         m = ctx.model
+        _check_unchanged(ctx, m._flat)
         c = get_context(m._flat.device, ctx.shape[2])
         grads = torch.empty_like(m._flat)
-        c.lstm_bwd(ctx.shape, ctx.lengths, ctx.max_steps, None, m._flat, grads, None, m._ws, dlogits=dlogits.contiguous(),
+        c.lstm_bwd(ctx.shape, ctx.lengths, ctx.max_steps, None, m._flat, grads, None, ctx.ws, dlogits=dlogits.contiguous(),
                    sequential=dlogits.dim() == 3)
+        ctx.ws = None
         out, off = [], 0
         for p in m._param_list():
             out.append(grads[off:off + p.numel()].view(p.shape))
@@ -232,6 +255,7 @@ class _LstmFunction(torch.autograd.Function):
 
 class _LstmBase(RegisteredModel):
     HIDDEN = 128
+    SEQUENTIAL = False
 
     def __init__(self, num_labels: int, config=None):
         super().__init__(num_labels)
@@ -268,9 +292,9 @@ class _LstmBase(RegisteredModel):
 class SimpleLstm(_LstmBase, name="lstm"):
     """dnn(h_n) -> [B, L]; the reference never carries state for this model (its streaming_state setter is a no-op)."""
 
-    def _run(self, feats, lengths, max_steps, train):
+    def _run(self, feats, lengths, max_steps, train, ws=None):
         ctx = get_context(feats.device, feats.shape[2])
-        ws = self._workspace(ctx, feats.shape[0], max_steps, train, False)
+        ws = self._workspace(ctx, feats.shape[0], max_steps, train, False) if ws is None else ws
         return ctx.lstm_fwd(feats, lengths, max_steps, self._flat, ws, sequential=False, train=train)
 
     def forward(self, x, lengths):
@@ -282,6 +306,8 @@ class SimpleLstm(_LstmBase, name="lstm"):
 
 class SequentialLstm(_LstmBase, name="seq-lstm"):
     """dnn(h_t) for every frame -> [T', B, L]; carries (h, c) between calls when streaming (rnn.py:60-71)."""
+
+    SEQUENTIAL = True
 
     def __init__(self, num_labels: int, config=None):
         super().__init__(num_labels, config)
@@ -295,10 +321,10 @@ class SequentialLstm(_LstmBase, name="seq-lstm"):
     def streaming_state(self, x: Any):
         self.hc = x
 
-    def _run(self, feats, lengths, max_steps, train):
+    def _run(self, feats, lengths, max_steps, train, ws=None):
         ctx = get_context(feats.device, feats.shape[2])
         b = feats.shape[0]
-        ws = self._workspace(ctx, b, max_steps, train, True)
+        ws = self._workspace(ctx, b, max_steps, train, True) if ws is None else ws
         state_in = None
         if self.is_streaming and self.hc is not None:
             state_in = torch.stack([self.hc[0].reshape(b, self.HIDDEN), self.hc[1].reshape(b, self.HIDDEN)]).contiguous().float()
@@ -314,3 +340,58 @@ class SequentialLstm(_LstmBase, name="seq-lstm"):
         if self.training and torch.is_grad_enabled():
             return _LstmFunction.apply(self, feats, lengths, max_steps, *self._param_list())
         return self._run(feats, lengths, max_steps, train=False)
+
+
+# =====================================================================================================================
+# ConvertedStaticModel (howl/model/base.py:40-62): a static model applied over sliding windows of the time axis
+# =====================================================================================================================
+class ConvertedStaticModel(RegisteredModel, name="converted"):
+    """Runs ``model`` on windows of ``frame_window_size`` frames every ``frame_stride_size`` frames and stacks the outputs
+    ``[n_windows, B, L]``.  Window arithmetic follows the reference literally, INCLUDING its first window, which is the tail
+    ``x[..., frame_window_size:]`` rather than the head (base.py:55) -- flagged, kept.  In eval mode all equally sized windows go
+    through the model as ONE batch (n_windows x B utterances per launch instead of n_windows launches)."""
+
+    def __init__(self, model: RegisteredModel, frame_window_size: int, frame_stride_size: int):
+        super().__init__(model.num_labels)
+        self.model, self.frame_window_size, self.frame_stride_size = model, frame_window_size, frame_stride_size
+
+    def compute_length(self, length: int):
+        return None if length is None else max(1, (length - self.frame_window_size) // self.frame_stride_size)
+
+    def _window_list(self, x):
+        w, s, total = self.frame_window_size, self.frame_stride_size, x.size(3)
+        out, idx, cur = [x[:, :, :, w:]], s, None
+        while True:
+            cur = x[:, :, :, idx:idx + w]
+            if cur.size(3) != w:
+                break
+            out.append(cur)
+            idx += s
+        return out
+
+    def forward(self, x, lengths):
+        wins = self._window_list(x)
+        if self.training or len(wins) < 3:
+            return torch.stack([self.model(w, lengths) for w in wins])
+        head = self.model(wins[0], lengths)                          # the odd-sized first window
+        b = x.size(0)
+        rep = None if lengths is None else lengths.repeat(len(wins) - 1)
+        rest = self.model(torch.cat([w.contiguous() for w in wins[1:]], 0), rep)
+        return torch.cat([head.unsqueeze(0), rest.view(len(wins) - 1, b, -1)], 0)
+
+
+def _not_accelerated(name: str, where: str):
+    class _Stub(RegisteredModel, name=name):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"howl_b200: model '{name}' ({where}) is not on the accelerated hot path (SURVEY.md §2/§8a, "
+                                      "DESIGN.md §1); inside a reference checkout plugin.install() keeps the reference's torch module")
+    _Stub.__name__ = f"NotAccelerated_{name.replace('-', '_')}"
+    return _Stub
+
+
+# registry names of the reference (SURVEY App. B.1) without a CUDA path here: constructible only through the reference itself
+for _n, _w in (("small-cnn", "howl/model/cnn.py:40-74"), ("seq-cnn", "howl/model/cnn.py:77-104"), ("gru", "howl/model/rnn.py:94-130")):
+    _not_accelerated(_n, _w)
+
+# name -> class of every model with a CUDA forward/backward in this package (what plugin.install() re-points)
+ACCELERATED = {"res8": Res8, "lstm": SimpleLstm, "seq-lstm": SequentialLstm}

@@ -268,6 +268,11 @@ class Context:
                         logits, ws):
         b, t = pcm.shape
         num_labels = self.lstm_labels_from_params(params)
+        _check(pcm, torch.float32, self.device, "pcm")
+        _check(labels, torch.int64, self.device, "labels")
+        _check(lengths, torch.int64, self.device, "lengths")
+        for name, t_ in (("fb", fb), ("params", params), ("grads", grads), ("m", m), ("v", v), ("loss", loss), ("logits", logits)):
+            _check(t_, torch.float32, self.device, name)
         self._rc(self.lib.howl_b200_lstm_train_step(
             self.handle, self._stream(), _ptr(pcm), _ptr(labels), _ptr(lengths), b, t, _ptr(fb), float(zmuv[0]),
             float(zmuv[1]), num_labels, max_steps, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), step, lr, weight_decay,
@@ -287,6 +292,12 @@ class Context:
                                 v, step, lr, weight_decay, loss, scores, ws):
         b, t = pcm.shape
         num_labels = self.lstm_labels_from_params(params)
+        _check(pcm, torch.float32, self.device, "pcm")
+        for name, t_ in (("targets", targets), ("target_lengths", target_lengths), ("lengths", lengths)):
+            _check(t_, torch.int64, self.device, name)
+        for name, t_ in (("fb", fb), ("params", params), ("state", state), ("grads", grads), ("m", m), ("v", v), ("loss", loss),
+                         ("scores", scores)):
+            _check(t_, torch.float32, self.device, name)
         self._rc(self.lib.howl_b200_seq_lstm_ctc_train_step(
             self.handle, self._stream(), _ptr(pcm), _ptr(targets), _ptr(target_lengths), targets.shape[1], blank, _ptr(lengths),
             b, t, _ptr(fb), float(zmuv[0]), float(zmuv[1]), num_labels, max_steps, _ptr(params), _ptr(state), _ptr(grads),
@@ -314,6 +325,16 @@ class Context:
             _check(t_, torch.float32, self.device, name)
         if pcm.dim() != 2 or labels.numel() != pcm.shape[0]:
             raise HowlB200Error("res8_train_step: pcm must be [B,T] and labels [B]")
+        if rects is not None:
+            _check(rects, torch.int32, self.device, "rects")
+            if tuple(rects.shape) != (pcm.shape[0], 4):
+                raise HowlB200Error("res8_train_step: rects must be [B,4]")
+        _check(nbt, torch.int64, self.device, "nbt")
+        _check(loss, torch.float32, self.device, "loss")
+        _check(logits, torch.float32, self.device, "logits")
+        _check(ws, torch.uint8, self.device, "ws")
+        if logits.numel() < pcm.shape[0] * self._labels_from_params(params):
+            raise HowlB200Error("res8_train_step: logits buffer smaller than [B, num_labels]")
         b, t = pcm.shape
         num_labels = self._labels_from_params(params)
         self._rc(self.lib.howl_b200_res8_train_step(

@@ -58,25 +58,45 @@ def _load(cls):
 
 class HowlSettings:
     def __init__(self):
+        self._delegate = None
         self.reset()
 
     def reset(self):
         self._audio = self._audio_transform = self._inference_engine = None
 
+    def bind(self, external) -> None:
+        """Delegate every group to another settings object with the same attributes -- ``plugin.install()`` binds the reference's
+        ``howl.settings.SETTINGS`` so that ``Workspace.load_settings()`` (hubconf.py:54, demo.py:27) and direct assignments such as
+        ``SETTINGS.inference_engine.inference_sequence = [0, 1, 2]`` reach the CUDA-backed classes.  ``bind(None)`` undoes it."""
+        self._delegate = external
+
+    def __getattr__(self, name):
+        # groups this mirror does not model (training, dataset, cache, ...) exist only on a bound reference object
+        d = self.__dict__.get("_delegate")
+        if d is not None and not name.startswith("_"):
+            return getattr(d, name)
+        raise AttributeError(name)
+
     @property
     def audio(self) -> AudioSettings:
+        if self._delegate is not None:
+            return self._delegate.audio
         if self._audio is None:
             self._audio = _load(AudioSettings)
         return self._audio
 
     @property
     def audio_transform(self) -> AudioTransformSettings:
+        if self._delegate is not None:
+            return self._delegate.audio_transform
         if self._audio_transform is None:
             self._audio_transform = _load(AudioTransformSettings)
         return self._audio_transform
 
     @property
     def inference_engine(self) -> InferenceEngineSettings:
+        if self._delegate is not None:
+            return self._delegate.inference_engine
         if self._inference_engine is None:
             self._inference_engine = _load(InferenceEngineSettings)
         return self._inference_engine

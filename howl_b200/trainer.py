@@ -122,21 +122,40 @@ class Res8TrainStep(_HostPipeline):
         self._init_host_pipeline()
 
     # ------------------------------------------------------------------ device-resident step
-    def step(self, pcm: torch.Tensor, labels: torch.Tensor, rects: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """One train step on device tensors; returns the (device) loss tensor of this step."""
+    def _ensure_capacity(self, b: int, t: int):
+        """Workspace / logits follow the batch actually passed: a larger or longer batch than the one the step was built for grows
+        them (the last, smaller batch of an epoch just uses a prefix)."""
+        if t != self.samples or b > self.batch:
+            self.batch, self.samples = max(b, self.batch), t
+            self.frames = self.ctx.num_frames(t)
+            self.ws = None
+            self.ws = torch.empty(self.ctx.train_step_workspace_bytes(self.batch, t, self.num_labels), dtype=torch.uint8, device=self.device)
+            self.logits = torch.zeros(self.batch, self.num_labels, device=self.device)
+
+    def step(self, pcm: torch.Tensor, labels: torch.Tensor, rects: Optional[torch.Tensor] = None,
+             fb: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One train step on device tensors; returns the (device) loss tensor of this step.  `rects` [B,4] int32 (device): this
+        step's SpecAugment rectangles; `fb` [257, M]: this step's mel filterbank (the VTLP matrix drawn for the step), default the
+        standard bank."""
+        if pcm.dim() != 2 or labels.shape[0] != pcm.shape[0]:
+            raise ValueError("Res8TrainStep.step: pcm must be [B, T] and labels [B]")
+        b, t = pcm.shape
+        self._ensure_capacity(b, t)
         self.step_count += 1
         c = self.ctx
+        fb = self.fb if fb is None else fb
         if self.world == 1:
-            c.res8_train_step(pcm, labels, self.fb, self.zmuv, self.params, self.bn_running, self.nbt, self.grads, self.m,
+            c.res8_train_step(pcm, labels, fb, self.zmuv, self.params, self.bn_running, self.nbt, self.grads, self.m,
                               self.v, self.step_count, self.lr, self.weight_decay, self.loss, self.logits, self.ws, rects)
         else:
             from .parallel import allreduce_flat_grads
 
-            feats = self.ws[: self.batch * self.frames * c.n_mels * 4].view(torch.float32).view(self.batch, self.frames, c.n_mels)
-            ws = self.ws[self.feat_bytes:]
-            c.frontend(pcm, self.fb, "time_major", zmuv=self.zmuv, rects=rects, out=feats)
+            nfeat = b * self.frames * c.n_mels * 4
+            feats = self.ws[:nfeat].view(torch.float32).view(b, self.frames, c.n_mels)
+            ws = self.ws[(nfeat + 255) // 256 * 256:]
+            c.frontend(pcm, fb, "time_major", zmuv=self.zmuv, rects=rects, out=feats)
             c.res8_fwd(feats, self.params, self.bn_running, self.nbt, True, ws, logits=self.logits)
-            c.res8_bwd(feats, labels, self.params, self.grads, self.loss, ws, loss_scale_batch=self.batch * self.world)
+            c.res8_bwd(feats, labels, self.params, self.grads, self.loss, ws, loss_scale_batch=b * self.world)
             allreduce_flat_grads(self.grads)     # one NCCL all-reduce(SUM) of the flat gradient over NVLink
             c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
         return self.loss
@@ -272,6 +291,7 @@ class Trainer:
         self.logger = logger or logging.getLogger(self.__class__.__name__)
         self.device = device
         self.step_obj = None
+        self._aug = None
         self.epoch = 0
         if training_cfg.model_config.architecture != "res8":
             raise NotImplementedError(f"Trainer: fused training step exists for res8, not {training_cfg.model_config.architecture!r}")
@@ -283,23 +303,41 @@ class Trainer:
                                           lr=cfg.learning_rate, weight_decay=cfg.weight_decay, zmuv=zmuv, seed=self.context_cfg.seed)
         return self.step_obj
 
-    def train_epoch(self, batches, zmuv=(0.0, 1.0)) -> float:
+    def train_epoch(self, batches, zmuv=(0.0, 1.0), augment: bool = True) -> float:
         """One pass over ``batches`` (iterable of (pcm [B,T] float32, labels [B] int64), host or device tensors); returns the mean
-        loss.  The learning rate decays by ``lr_decay`` after the epoch (``train.py:306-307``)."""
+        loss.  As in the reference loop (``training/run/train.py:280-307``) every step draws, from the global ``random`` and in the
+        reference's order, (1) the ``audio_transform.train()`` coin: with p = 0.75 a VTLP-warped filterbank (alpha ~ U[0.9, 1.1)) for
+        the whole batch (``transform.py:93,441``), (2) the two ``SpecAugmentTransform().train()`` coins and, when they fall, one
+        frequency / time rectangle per clip (``transform.py:310-326``); both are applied inside the fused frontend kernel.
+        ``augment=False`` trains on the plain features (the parity-comparable recipe).  The learning rate decays by ``lr_decay``
+        after the epoch (``train.py:306-307``)."""
+        from .transform import SpecAugmentTransform, StandardAudioTransform, vtlp_filterbank
+
+        if augment and self._aug is None:
+            self._aug = (StandardAudioTransform().train(), SpecAugmentTransform().train())
         total, n = 0.0, 0
         for pcm, labels in batches:
             step = self._ensure_step(pcm, zmuv)
-            loss = step.step(pcm.to(step.device, torch.float32), labels.to(step.device, torch.int64))
+            fb = rects = None
+            if augment:
+                std, spec = self._aug
+                if std.rand.random() < std.augment_params[0].prob:          # AugmentModule.forward's coin (transform.py:93)
+                    import random as _random
+
+                    alpha = _random.random() * 0.2 + 0.9                      # VtlpMelScale.forward (transform.py:441)
+                    fb = vtlp_filterbank(alpha, std.num_mels, std.sample_rate, std.num_fft // 2 + 1).to(step.device)
+                rects = spec.draw_rects(pcm.shape[0], std.num_mels, step.ctx.num_frames(pcm.shape[1])).to(step.device)
+            loss = step.step(pcm.to(step.device, torch.float32), labels.to(step.device, torch.int64), rects=rects, fb=fb)
             total, n = total + float(loss.item()), n + 1
         if self.step_obj is not None:
             self.step_obj.lr *= self.training_cfg.lr_decay
         self.epoch += 1
         return total / max(n, 1)
 
-    def train(self, make_batches, zmuv=(0.0, 1.0)):
+    def train(self, make_batches, zmuv=(0.0, 1.0), augment: bool = True):
         """``num_epochs`` epochs; ``make_batches(epoch)`` returns that epoch's batch iterable.  Returns the per-epoch mean losses."""
         losses = []
         for epoch in range(self.training_cfg.num_epochs):
-            losses.append(self.train_epoch(make_batches(epoch), zmuv))
+            losses.append(self.train_epoch(make_batches(epoch), zmuv, augment))
             self.logger.info("epoch %d: mean loss %.5f, lr %.6f", epoch, losses[-1], self.step_obj.lr if self.step_obj else float("nan"))
         return losses

@@ -190,22 +190,25 @@ class ZmuvTransform(nn.Module):
         self.register_buffer("mean2", torch.zeros(1))
 
     def update(self, data: torch.Tensor, mask=None):
+        """Running sums (operator.py:126-135).  The two reductions run in `sum_sumsq_kernel`; the scalar bookkeeping stays on the
+        device (no `.item()`): fitting ZMUV over 2001 clips (train.py:235-237) queues work without a host round trip per clip."""
         with torch.no_grad():
-            if mask is not None:
-                data = data * mask
-                n = float(mask.sum().item())
-            else:
-                n = float(data.numel())
             if data.device.type != "cuda":
                 raise RuntimeError("howl_b200.ZmuvTransform needs CUDA tensors (no CPU fallback)")
-            ctx = get_context(data.device, SETTINGS.audio_transform.num_mels)
-            sums = torch.zeros(2, dtype=torch.float64, device=data.device)
+            dev = data.device
+            if mask is not None:
+                data = data * mask
+                n = mask.sum().double()
+            else:
+                n = float(data.numel())
+            ctx = get_context(dev, SETTINGS.audio_transform.num_mels)
+            sums = torch.zeros(2, dtype=torch.float64, device=dev)
             ctx.sum_sumsq(data.contiguous().float(), sums)
-            s = sums.cpu()
-            total = float(self.total.item())
-            self.mean = ((s[0] + self.mean.double().cpu() * total) / (total + n)).float().to(self.mean.device)
-            self.mean2 = ((s[1] + self.mean2.double().cpu() * total) / (total + n)).float().to(self.mean2.device)
-            self.total += n
+            home = self.mean.device
+            total = self.total.to(dev).double()
+            self.mean = ((sums[0] + self.mean.to(dev).double() * total) / (total + n)).float().to(home)
+            self.mean2 = ((sums[1] + self.mean2.to(dev).double() * total) / (total + n)).float().to(home)
+            self.total = (total + n).float().to(home)
 
     def initialize(self, iterable: Iterable[torch.Tensor]):
         for ex in iterable:
@@ -216,7 +219,15 @@ class ZmuvTransform(nn.Module):
         return (self.mean2 - self.mean ** 2).sqrt()
 
     def constants(self) -> Tuple[float, float]:
-        return float(self.mean.item()), float(self.std.item())
+        """(mean, std) as host floats for the kernel arguments, read back ONCE per change of the buffers (update / load_state_dict /
+        .to()), not per forward call."""
+        key = (id(self.mean), self.mean._version, id(self.mean2), self.mean2._version)
+        cached = getattr(self, "_const_cache", None)
+        if cached is None or cached[0] != key:
+            pair = torch.stack([self.mean.reshape(()), self.std.reshape(())]).cpu()
+            cached = (key, (float(pair[0]), float(pair[1])))
+            self._const_cache = cached
+        return cached[1]
 
     def forward(self, x: torch.Tensor):
         if x.device.type != "cuda":

@@ -126,7 +126,7 @@ def test_res8_module_trains_like_the_reference_loop(golden):
         model.load_state_dict({k: torch.from_numpy(g[f"step{step}.sd.{k}"]) for k in sd})
 
 
-@pytest.mark.parametrize("batched", [False, True])
+@pytest.mark.parametrize("batched", ["infer", "infer_batched", "ingest_frame"])
 def test_frame_inference_engine_known_answers(golden, batched):
     """the shipped hey-fire-fox res8 + zmuv through FrameInferenceEngine(500, 63)."""
     from howl_b200.inference import FrameInferenceEngine, SimpleContext
@@ -146,7 +146,18 @@ def test_frame_inference_engine_known_answers(golden, batched):
     for name in ("hey_fire_fox", "hello_world"):
         engine = FrameInferenceEngine(500, 63, model, zmuv, ctx)
         audio = torch.from_numpy(g[f"trace_{name}_pcm"]).to(DEV)
-        detected = engine.infer_batched(audio) if batched else engine.infer(audio)
+        if batched == "ingest_frame":      # the live-streaming path: one window at a time, as howl_client.py:94-105 drives it
+            from howl_b200.inference import stride
+
+            detected = False
+            for window in stride(audio, 500, 63, 16000):
+                engine.ingest_frame(window, engine.curr_time)
+                engine.curr_time += 63
+                if engine.sequence_present(engine.curr_time):
+                    detected = True
+                    break
+        else:
+            detected = getattr(engine, batched)(audio)
         assert detected == meta[name]["detected"]
         assert [int(l) for _, l in engine.label_history] == meta[name]["labels"]
 
@@ -168,3 +179,101 @@ def test_device_batchifier_matches_reference_batches():
         assert np.array_equal(labels.cpu().numpy(), g[f"t{trial}.labels"])
         assert np.array_equal(lengths.cpu().numpy(), g[f"t{trial}.lengths"])
     ctx.close()
+
+
+def test_autograd_two_forwards_before_backward():
+    """The drop-in nn.Module under ordinary PyTorch usage: a second training forward (and an eval pass) between a forward and
+    its backward must not disturb that backward -- each forward carries its own activation workspace on the autograd ctx."""
+    from howl_b200.model import RegisteredModel
+
+    torch.manual_seed(0)
+    L = 4
+    model = RegisteredModel.find_registered_class("res8")(L).to(DEV).train()
+    xa = torch.randn(6, 3, 40, 41, device=DEV)
+    xb = torch.randn(9, 3, 40, 81, device=DEV)       # larger batch, longer clip: would have reallocated a shared workspace
+    ya, yb = torch.randint(0, L, (6,), device=DEV), torch.randint(0, L, (9,), device=DEV)
+
+    def grad_of(x, y):
+        model.zero_grad()
+        torch.nn.functional.cross_entropy(model(x, None), y).backward()
+        return torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+
+    ga, gb = grad_of(xa, ya), grad_of(xb, yb)
+    model.zero_grad()
+    la = torch.nn.functional.cross_entropy(model(xa, None), ya)
+    lb = torch.nn.functional.cross_entropy(model(xb, None), yb)
+    with torch.no_grad():
+        model.eval()
+        model(xb, None)
+        model.train()
+    la.backward()
+    got_a = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+    model.zero_grad()
+    lb.backward()
+    got_b = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+    assert torch.allclose(got_a, ga, rtol=1e-4, atol=1e-6 * ga.abs().max().item())
+    assert torch.allclose(got_b, gb, rtol=1e-4, atol=1e-6 * gb.abs().max().item())
+    # parameters changed between forward and backward -> refuse instead of differentiating against the wrong weights
+    loss = torch.nn.functional.cross_entropy(model(xa, None), ya)
+    with torch.no_grad():
+        model.conv1.weight.add_(1e-3)
+    with pytest.raises(RuntimeError, match="modified"):
+        loss.backward()
+
+
+def test_converted_static_model_batches_windows():
+    from howl_b200.model import ConvertedStaticModel, RegisteredModel
+
+    torch.manual_seed(1)
+    inner = RegisteredModel.find_registered_class("res8")(4).to(DEV).eval()
+    conv = ConvertedStaticModel(inner, 41, 10).eval()
+    assert "converted" in RegisteredModel.registered_names() and conv.compute_length(81) == 4
+    x = torch.randn(3, 3, 40, 101, device=DEV)
+    with torch.no_grad():
+        got = conv(x, None)
+        # the reference loop (base.py:52-62), window by window
+        wins, idx = [x[:, :, :, 41:]], 10
+        while x[:, :, :, idx:idx + 41].size(3) == 41:
+            wins.append(x[:, :, :, idx:idx + 41])
+            idx += 10
+        want = torch.stack([inner(w.contiguous(), None) for w in wins])
+    assert got.shape == want.shape == (len(wins), 3, 4)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    for name in ("small-cnn", "seq-cnn", "gru"):
+        with pytest.raises(NotImplementedError):
+            RegisteredModel.find_registered_class(name)(4)
+
+
+def test_trainer_epoch_applies_the_reference_augmentations(monkeypatch):
+    """Trainer.train_epoch = the loop of training/run/train.py:280-307: per step the VTLP coin (+ alpha) and the two SpecAugment
+    coins (+ per-clip rectangles) come from the global `random` in the reference's order; batches may shrink or grow."""
+    from howl_b200.config import TrainingConfig
+    from howl_b200.trainer import Trainer
+    from howl_b200.transform import SpecAugmentTransform
+
+    cfg = TrainingConfig(**{"num_epochs": 1, "learning_rate": 0.01, "lr_decay": 0.5, "weight_decay": 1e-5,
+                            "context_config": {"vocab": ["hey", "fire", "fox"], "token_type": "word", "seed": 3},
+                            "model_config": {"architecture": "res8"}})
+    tr = Trainer(cfg, device="cuda:0")
+    sizes = [(8, 8000), (5, 8000), (12, 8000)]          # smaller last batch, then a larger one: workspace follows
+    batches = [O.synthetic_batch(b, t, 4, seed=i) for i, (b, t) in enumerate(sizes)]
+    random.seed(11)
+    loss = tr.train_epoch(batches, zmuv=(-1.8, 3.9))
+    after = random.random()
+    assert np.isfinite(loss) and tr.step_obj.step_count == 3 and abs(tr.step_obj.lr - 0.005) < 1e-12
+    # replay the draws the reference loop makes for the same batches
+    random.seed(11)
+    spec = SpecAugmentTransform().train()
+    for b, t in sizes:
+        if random.random() < 0.75:
+            random.random()
+        spec.draw_rects(b, 40, 1 + t // 200)
+    assert random.random() == after
+    # augment=False consumes no draws
+    random.seed(11)
+    tr.train_epoch(batches[:1], zmuv=(-1.8, 3.9), augment=False)
+    random.seed(11)
+    first = random.random()
+    random.seed(11)
+    tr.train_epoch(batches[:1], zmuv=(-1.8, 3.9), augment=False)
+    assert random.random() == first

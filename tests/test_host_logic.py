@@ -246,7 +246,16 @@ names = {n: RegisteredModel.find_registered_class(n).__module__ for n in ("res8"
 assert set(names.values()) == {"howl_b200.model"}, names
 assert "mobilenet" in RegisteredModel.registered_names() and "las" in RegisteredModel.registered_names()   # others untouched
 assert t.StandardAudioTransform.__module__ == t.SpecAugmentTransform.__module__ == op.ZmuvTransform.__module__ == "howl_b200.transform"
-assert inf.FrameInferenceEngine.__module__ == "howl_b200.inference"
+assert inf.FrameInferenceEngine.__module__ == "howl.model.inference" and hasattr(inf.FrameInferenceEngine, "infer_batched")   # reference engines stay
+# settings: the substituted classes read the REFERENCE's settings object (Workspace.load_settings / direct assignment reach them)
+from howl.settings import SETTINGS as REF
+from howl_b200.settings import SETTINGS as OURS
+REF.inference_engine.inference_sequence = [0, 1, 2, 1]
+REF._audio_transform = None; os.environ["NUM_MELS"] = "64"
+assert OURS.inference_engine.inference_sequence == [0, 1, 2, 1] and OURS.audio_transform.num_mels == 64 == REF.audio_transform.num_mels
+import howl_b200.inference as I, types
+eng = I.InferenceEngine(types.SimpleNamespace(streaming_state=None), None, I.SimpleContext.for_vocab(["hey", "fire", "fox"]))
+assert eng.sequence == [0, 1, 2, 1] and eng.std.num_mels == 64
 print("ok")
 ''' % (ROOT, ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
