@@ -38,8 +38,14 @@ struct R8Ws {
   float* g;
   float* dc;
   float* gu[2];
-  __nv_bfloat16* dcT;              // conv-output gradient, rows = channels (weight-gradient operand of the tensor-core engine)
-  __nv_bfloat16* uop[R8_LAYERS];   // a0, u1..u5 in operand format (tensor-core engine; null when H is unsupported)
+  // ---- tensor-core engine (null when H is unsupported): everything the convolutions read is in operand format
+  __nv_bfloat16* dcT;              // conv-output gradient, rows = channels (weight-gradient operand)
+  __nv_bfloat16* dc2;              // second conv-output-gradient buffer (the fused data gradient reads one and writes the other)
+  __nv_bfloat16* uop[R8_LAYERS + 1];   // a0, u1..u6
+  uint16_t* mask_bits[3];          // ReLU decisions of the residual layers 2, 4, 6: [B][3 channel groups][R]
+  float* pooled_raw;               // [B,45] spatial sums of u6 (accumulated by the forward epilogue of layer 6)
+  float* dones;                    // [6][45*9] raw ones columns of the weight gradients
+  float* bn_coef;                  // [3][48] BatchNorm-backward coefficients of the layer being differentiated
   size_t bytes;
 };
 
@@ -72,9 +78,14 @@ static R8Ws r8_carve(void* base, int64_t B, int H, int L) {
   }
   w.gu[0] = (float*)take(n);
   w.gu[1] = (float*)take(n);
-  w.dcT = r8tc_supported(H) ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
-  for (int i = 0; i < R8_LAYERS; ++i)
-    w.uop[i] = r8tc_supported(H) ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
+  const bool tc = r8tc_supported(H);
+  w.dcT = tc ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
+  w.dc2 = tc ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
+  for (int i = 0; i <= R8_LAYERS; ++i) w.uop[i] = tc ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
+  for (int i = 0; i < 3; ++i) w.mask_bits[i] = tc ? (uint16_t*)take((size_t)B * 3 * r8tc_dcop_rows(H) * sizeof(uint16_t)) : nullptr;
+  w.pooled_raw = (float*)take(sizeof(float) * B * R8_C);
+  w.dones = (float*)take(sizeof(float) * R8_LAYERS * R8_C * 9);
+  w.bn_coef = (float*)take(sizeof(float) * 3 * 48);
   w.bytes = off;
   return w;
 }
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
     for (int r = 0; r < 5; ++r)
 #pragma unroll
       for (int c = 0; c < 6; ++c) patch[r][c] = s_x[(3 * h + r) * C0_STRIDE + 4 * w + c];
-    float* dst = a0 + (b * R8_C) * (int64_t)HW + pp;
+    float* dst = a0 ? a0 + (b * R8_C) * (int64_t)HW + pp : nullptr;
     float ov[8];
 #pragma unroll 1
     for (int oc = 0; oc < 48; ++oc) {
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
           sum += fmaxf(pre, 0.f);
         }
       const float o = __fdiv_rn(sum, 12.f);
-      dst[(int64_t)oc * HW] = o;
+      if (dst) dst[(int64_t)oc * HW] = o;
       ov[oc & 7] = o;
       if ((oc & 7) == 7 && op) {
         uint4 hi, lo;
@@ -527,7 +538,8 @@ __global__ void bn_eval_prepare_kernel(const float* __restrict__ running, float*
 }
 
 // bn6 -> spatial mean -> Linear(45 -> L); one CTA (128 threads) per utterance
-__global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__ u6, const float* __restrict__ mean_rstd,
+__global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__ u6, const float* __restrict__ pooled_raw,
+                                                       const float* __restrict__ mean_rstd,
                                                        const float* __restrict__ wout, const float* __restrict__ bout,
                                                        float* __restrict__ pooled, float* __restrict__ logits,
                                                        float* __restrict__ logits_ws, int HW, int L) {
@@ -535,10 +547,14 @@ __global__ void __launch_bounds__(128) head_fwd_kernel(const float* __restrict__
   const int64_t b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c = warp; c < R8_C; c += 4) {
-    const float* src = u6 + (b * R8_C + c) * (int64_t)HW;
     float s = 0.f;
-    for (int i = lane; i < HW; i += 32) s += src[i];
-    s = warp_sum(s);
+    if (pooled_raw) {
+      s = pooled_raw[b * R8_C + c];
+    } else {
+      const float* src = u6 + (b * R8_C + c) * (int64_t)HW;
+      for (int i = lane; i < HW; i += 32) s += src[i];
+      s = warp_sum(s);
+    }
     if (lane == 0) {
       const float v = (s / (float)HW - mean_rstd[c]) * mean_rstd[R8_C + c];
       s_pool[c] = v;
@@ -800,12 +816,13 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   const float* wout = wl + (size_t)R8_LAYERS * R8_KW;
   const float* bout = wout + (size_t)L * R8_C;
 
+  const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(H);
   {
     const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + R8_C * 9);
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const bool op = ctx->conv_engine >= 1 && r8tc_supported(H);
-    conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, ws.a0, op ? reinterpret_cast<uint4*>(ws.uop[0]) : nullptr,
-                                                          r8tc_dcop_rows(H), frames, H);
+    // tensor-core engine: a0 exists in operand format only
+    conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, use_tc ? nullptr : ws.a0,
+                                                          use_tc ? reinterpret_cast<uint4*>(ws.uop[0]) : nullptr, r8tc_dcop_rows(H), frames, H);
     HOWL_LAUNCHED(ctx, "conv0_pool");
   }
   if (train) {
@@ -814,47 +831,58 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     bn_eval_prepare_kernel<<<R8_LAYERS, 64, 0, st>>>(bn_running, ws.mean_rstd);
     HOWL_LAUNCHED(ctx, "bn_eval_prepare");
   }
+  if (use_tc) HOWL_CUDA(ctx, cudaMemsetAsync(ws.pooled_raw, 0, sizeof(float) * B * R8_C, st));
   const size_t csm = conv_smem_bytes(H);
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
   const int grid = r8_grid(ctx, B);
   const double count = (double)B * HW;
-  const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(H);
   for (int i = 1; i <= R8_LAYERS; ++i) {
-    ConvParams p;
-    memset(&p, 0, sizeof(p));
-    p.in = (i == 1) ? ws.a0 : ws.u[i - 2];
-    if (i > 1) {
-      p.in_mean = ws.mean_rstd + (i - 2) * 2 * R8_C;
-      p.in_rstd = p.in_mean + R8_C;
-    }
-    p.w = wl + (size_t)(i - 1) * R8_KW;
-    p.res = (i % 2 == 0) ? ((i == 2) ? ws.a0 : ws.u[i - 3]) : nullptr;
-    p.out = ws.u[i - 1];
-    p.B = B;
-    p.H = H;
+    const float* in_mean = (i > 1) ? ws.mean_rstd + (i - 2) * 2 * R8_C : nullptr;
+    const float* w_i = wl + (size_t)(i - 1) * R8_KW;
+    double* stats = train ? ws.stats_fwd + (i - 1) * 2 * R8_C : nullptr;
     if (use_tc) {
-      // operand-format activations; BatchNorm of layer i-1 folded into this layer's weights (res8_tc.cu)
+      // operand-format activations only; BatchNorm of layer i-1 folded into this layer's weights (res8_tc.cu)
       __nv_bfloat16* wblk = ws.wprep + ((size_t)((i - 1) * 2 + 0) * 2) * R8TC_WBLOCK;
-      if (train) p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
-      rc = r8tc_fold(ctx, st, p.w, i > 1 ? p.in_mean : nullptr, wblk);
+      rc = r8tc_fold(ctx, st, w_i, in_mean, wblk);
       if (rc) return rc;
-      rc = r8tc_conv(ctx, st, p, ws.uop[i - 1], i < R8_LAYERS ? ws.uop[i] : nullptr, wblk, true, train ? 1 : 0);
+      TcConvCall c;
+      memset(&c, 0, sizeof(c));
+      c.mode = train ? 1 : 0;
+      c.B = B; c.H = H;
+      c.in_op = ws.uop[i - 1];
+      c.w = wblk;
+      c.out_op = ws.uop[i];
+      c.res_op = (i % 2 == 0) ? ws.uop[i - 2] : nullptr;
+      c.mask_out = (train && i % 2 == 0) ? ws.mask_bits[i / 2 - 1] : nullptr;
+      c.pooled_raw = (i == R8_LAYERS) ? ws.pooled_raw : nullptr;
+      c.stats = stats;
+      rc = r8tc_conv(ctx, st, c);
       if (rc) return rc;
     } else {
-      if (train) p.stats = ws.stats_fwd + (i - 1) * 2 * R8_C;
+      ConvParams p;
+      memset(&p, 0, sizeof(p));
+      p.in = (i == 1) ? ws.a0 : ws.u[i - 2];
+      p.in_mean = in_mean;
+      p.in_rstd = in_mean ? in_mean + R8_C : nullptr;
+      p.w = w_i;
+      p.res = (i % 2 == 0) ? ((i == 2) ? ws.a0 : ws.u[i - 3]) : nullptr;
+      p.out = ws.u[i - 1];
+      p.B = B;
+      p.H = H;
+      p.stats = stats;
       if (train) conv3x3_kernel<true, 1><<<grid, CV_THREADS, csm, st>>>(p);
       else conv3x3_kernel<true, 0><<<grid, CV_THREADS, csm, st>>>(p);
       HOWL_LAUNCHED(ctx, "conv3x3_fwd");
     }
     if (train) {
-      bn_finalize_kernel<<<1, 64, 0, st>>>(p.stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C, bn_running + (i - 1) * 2 * R8_C,
+      bn_finalize_kernel<<<1, 64, 0, st>>>(stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C, bn_running + (i - 1) * 2 * R8_C,
                                            num_batches_tracked ? num_batches_tracked + (i - 1) : nullptr);
       HOWL_LAUNCHED(ctx, "bn_finalize");
     }
   }
-  head_fwd_kernel<<<(unsigned)B, 128, 0, st>>>(ws.u[5], ws.mean_rstd + 5 * 2 * R8_C, wout, bout, ws.pooled, logits,
-                                               ws.logits, HW, L);
+  head_fwd_kernel<<<(unsigned)B, 128, 0, st>>>(ws.u[5], use_tc ? ws.pooled_raw : nullptr, ws.mean_rstd + 5 * 2 * R8_C, wout, bout,
+                                               ws.pooled, logits, ws.logits, HW, L);
   HOWL_LAUNCHED(ctx, "head_fwd");
   return HOWL_OK;
 }
@@ -897,12 +925,68 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
                                            B, L);
   HOWL_LAUNCHED(ctx, "head_wgrad");
 
+  const double count = (double)B * HW;
+  if (use_tc) {
+    // ---- tensor-core engine.  Per layer i = 6..1:  weight gradient (also yields the BatchNorm-backward statistics of layer i-1,
+    // bn_bwd_coef_kernel)  ->  data gradient whose epilogue applies BatchNorm backward + residual fan-in + ReLU mask of layer i-1 and
+    // writes the next conv-output gradient directly in both operand formats.  No planar gradient tensor, no separate apply pass.
+    HOWL_CUDA(ctx, cudaMemsetAsync(ws.dones, 0, sizeof(float) * R8_LAYERS * R8_C * 9, st));
+    __nv_bfloat16* dc[2] = {reinterpret_cast<__nv_bfloat16*>(ws.dc), ws.dc2};
+    int cur = 0;
+    {
+      ApplyOpParams ao;
+      memset(&ao, 0, sizeof(ao));
+      ao.g_bcast = ws.dh;
+      ao.u_op = ws.uop[R8_LAYERS];
+      ao.mask_bits = ws.mask_bits[2];
+      ao.mean_rstd = ws.mean_rstd + 5 * 2 * R8_C;
+      ao.stats = ws.stats_bwd + 5 * 2 * R8_C;
+      ao.gu_out = ws.gu[(R8_LAYERS / 2) & 1];
+      ao.dc_op = dc[cur];
+      ao.dc_opT = ws.dcT;
+      ao.B = B; ao.H = H; ao.count = count;
+      rc = r8tc_apply_head(ctx, st, ao);
+      if (rc) return rc;
+    }
+    for (int i = R8_LAYERS; i >= 1; --i) {
+      const int j = i - 1;                                  // the layer whose output feeds conv_i
+      const float* x_mean = (i > 1) ? ws.mean_rstd + (j - 1) * 2 * R8_C : nullptr;
+      float* dw = g_wl + (size_t)(i - 1) * R8_KW;
+      float* dones = ws.dones + (size_t)(i - 1) * R8_C * 9;
+      rc = r8tc_wgrad(ctx, st, ws.dcT, ws.uop[j], x_mean, x_mean ? x_mean + R8_C : nullptr, dw, dones, B, H);
+      if (rc) return rc;
+      TcConvCall c;
+      memset(&c, 0, sizeof(c));
+      c.B = B; c.H = H;
+      c.in_op = dc[cur];
+      c.w = ws.wprep + ((size_t)((i - 1) * 2 + 1) * 2) * R8TC_WBLOCK;
+      if (i > 1) {
+        rc = r8tc_bn_bwd_coef(ctx, st, wl + (size_t)(i - 1) * R8_KW, dw, dones, x_mean, count, ws.bn_coef);
+        if (rc) return rc;
+        c.mode = 3;
+        c.u_op = ws.uop[j];
+        c.bn_coef = ws.bn_coef;
+        if (j % 2 == 0) {
+          c.gu_in = ws.gu[((j + 2) / 2) & 1];
+          c.gu_out = ws.gu[(j / 2) & 1];
+          c.mask_in = ws.mask_bits[j / 2 - 1];
+        }
+        c.dc_out = dc[cur ^ 1];
+        c.dc_outT = ws.dcT;
+      } else {
+        c.mode = 2;
+        c.out_planar = ws.g;                                // dL/d(a0) through conv1; conv0_bwd adds the residual path
+      }
+      rc = r8tc_conv(ctx, st, c);
+      if (rc) return rc;
+      cur ^= 1;
+    }
+  } else {
   const size_t csm = conv_smem_bytes(H), wsm = wgrad_smem_bytes(H);
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
   HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
   const int grid = r8_grid(ctx, B);
-  const double count = (double)B * HW;
   const int64_t n2 = (int64_t)B * R8_C * HW / 2;
   int64_t ablocks = howl_ceil_div(n2, 256);
   if (ablocks > (int64_t)ctx->sm_count * 16) ablocks = (int64_t)ctx->sm_count * 16;
@@ -924,24 +1008,12 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     a.n2 = n2;
     a.HW = HW;
     a.count = count;
-    if (use_tc) {
-      ApplyOpParams ao;
-      ao.g = a.g; ao.g_bcast = a.g_bcast; ao.u = a.u; ao.mean_rstd = a.mean_rstd; ao.stats = a.stats;
-      ao.gu_in = a.gu_in; ao.mask_prev = a.mask_prev; ao.gu_out = a.gu_out;
-      ao.dc_op = reinterpret_cast<__nv_bfloat16*>(ws.dc);
-      ao.dc_opT = ws.dcT;
-      ao.B = B; ao.H = H; ao.count = count;
-      rc = r8tc_apply(ctx, st, ao);
-      if (rc) return rc;
-    } else {
-      bn_bwd_apply_kernel<<<(unsigned)ablocks, 256, 0, st>>>(a);
-      HOWL_LAUNCHED(ctx, "bn_bwd_apply");
-    }
+    bn_bwd_apply_kernel<<<(unsigned)ablocks, 256, 0, st>>>(a);
+    HOWL_LAUNCHED(ctx, "bn_bwd_apply");
 
     WgradParams wg;
     memset(&wg, 0, sizeof(wg));
     wg.dc = ws.dc;
-    wg.dc_op = reinterpret_cast<const __nv_bfloat16*>(ws.dc);
     wg.x = (i == 1) ? ws.a0 : ws.u[i - 2];
     if (i > 1) {
       wg.x_mean = ws.mean_rstd + (i - 2) * 2 * R8_C;
@@ -950,13 +1022,8 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     wg.dw = g_wl + (size_t)(i - 1) * R8_KW;
     wg.B = B;
     wg.H = H;
-    if (use_tc) {
-      rc = r8tc_wgrad(ctx, st, ws.dcT, ws.uop[i - 1], wg.x_mean, wg.x_rstd, wg.dw, B, H);
-      if (rc) return rc;
-    } else {
-      conv3x3_wgrad_kernel<<<grid, WG_THREADS, wsm, st>>>(wg);
-      HOWL_LAUNCHED(ctx, "conv3x3_wgrad");
-    }
+    conv3x3_wgrad_kernel<<<grid, WG_THREADS, wsm, st>>>(wg);
+    HOWL_LAUNCHED(ctx, "conv3x3_wgrad");
 
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -971,16 +1038,10 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
       p.aux_mean = ws.mean_rstd + (i - 2) * 2 * R8_C;
       p.aux_rstd = p.aux_mean + R8_C;
     }
-    if (use_tc) {
-      const __nv_bfloat16* wblk = ws.wprep + ((size_t)((i - 1) * 2 + 1) * 2) * R8TC_WBLOCK;
-      rc = r8tc_conv(ctx, st, p, reinterpret_cast<const __nv_bfloat16*>(ws.dc), nullptr, wblk, false,
-                     i > 1 ? 2 : 0);
-      if (rc) return rc;
-    } else {
-      if (i > 1) conv3x3_kernel<false, 2><<<grid, CV_THREADS, csm, st>>>(p);
-      else conv3x3_kernel<false, 0><<<grid, CV_THREADS, csm, st>>>(p);
-      HOWL_LAUNCHED(ctx, "conv3x3_dgrad");
-    }
+    if (i > 1) conv3x3_kernel<false, 2><<<grid, CV_THREADS, csm, st>>>(p);
+    else conv3x3_kernel<false, 0><<<grid, CV_THREADS, csm, st>>>(p);
+    HOWL_LAUNCHED(ctx, "conv3x3_dgrad");
+  }
   }
   {
     const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + R8_C * (HW + 1) + R8_C * 9);
@@ -1065,7 +1126,13 @@ extern "C" int howl_b200_res8_debug_masks(howl_ctx_t* ctx, void* stream, const f
     HOWL_LAUNCHED(ctx, "debug_mask0");
   }
   if (masks16) {
+    const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(H);
     for (int i = 1; i <= R8_LAYERS; ++i) {
+      if (use_tc) {   // odd layers: u > 0 from the operand-format activations; residual layers: the bits the forward stored
+        rc = r8tc_debug_mask(ctx, st, ws.uop[i], (i % 2 == 0) ? ws.mask_bits[i / 2 - 1] : nullptr, masks16 + (size_t)(i - 1) * n, B, H);
+        if (rc) return rc;
+        continue;
+      }
       const float* prev = (i % 2 == 0) ? ((i == 2) ? ws.a0 : ws.u[i - 3]) : nullptr;
       debug_mask_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ws.u[i - 1], prev, masks16 + (size_t)(i - 1) * n, n);
       HOWL_LAUNCHED(ctx, "debug_mask");

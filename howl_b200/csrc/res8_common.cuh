@@ -54,29 +54,55 @@ bool r8tc_supported(int H);
 size_t r8tc_dcop_bytes(int H);          // bytes per utterance
 int r8tc_dcop_rows(int H);              // R
 
+// head of the backward (layer 6: upstream gradient = broadcast dh / HW), tensor-core engine
 struct ApplyOpParams {
-  const float* g;          // dgrad output [B,45,HW], or null when g_bcast is used
-  const float* g_bcast;    // [B,45]: g = g_bcast / HW (layer 6)
-  const float* u;
-  const float* mean_rstd;  // [2][45] of this layer
+  const float* g_bcast;    // [B,45]: g = g_bcast / HW
+  const __nv_bfloat16* u_op;   // u_6 in operand format
+  const uint16_t* mask_bits;   // ReLU decisions of conv_6 stored by the forward: [B][3 channel groups][R]
+  const float* mean_rstd;  // [2][45] of layer 6
   const double* stats;     // [2][45] sum(g), sum(g xhat)
-  const float* gu_in;
-  const float* mask_prev;
-  float* gu_out;
+  float* gu_out;           // planar G_6 (residual-path gradient of layer 4)
   __nv_bfloat16* dc_op;
   __nv_bfloat16* dc_opT;   // the same gradient with rows = channels (weight-gradient A operand), r8tc_dcop_bytes per utterance
   int64_t B;
   int H;
   double count;
 };
-int r8tc_apply(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p);
+int r8tc_apply_head(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p);
+
+// one launch of the stream kernel (res8_tc.cu).  mode 0: forward (eval), 1: forward + BatchNorm statistics, 2: plain data gradient
+// (planar fp32 out), 3: data gradient + BatchNorm backward / ReLU mask of the producer layer fused into the epilogue.
+struct TcConvCall {
+  int mode;
+  int64_t B;
+  int H;
+  const __nv_bfloat16* in_op;    // A operand: activations (forward) or conv-output gradient (data gradient), operand format
+  const __nv_bfloat16* w;        // weight operand block of this layer and direction
+  // forward
+  __nv_bfloat16* out_op;         // output in operand format (or null)
+  const __nv_bfloat16* res_op;   // residual added after the ReLU (or null)
+  uint16_t* mask_out;            // ReLU decisions [B][3][R] (or null)
+  float* pooled_raw;             // [B][45] spatial sums of the output, accumulated (layer 6; or null)
+  double* stats;                 // mode 1: [2][45] sum, sum of squares
+  float* out_planar;             // planar fp32 copy of the output (mode 2: the data gradient; forward: optional)
+  // mode 3
+  const __nv_bfloat16* u_op;
+  const float* bn_coef;          // [3][48] from r8tc_bn_bwd_coef
+  const float* gu_in;
+  float* gu_out;
+  const uint16_t* mask_in;
+  __nv_bfloat16* dc_out;
+  __nv_bfloat16* dc_outT;
+};
+int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const TcConvCall& c);
+// BatchNorm-backward coefficients of layer j from the weight gradient of layer j + 1 (see bn_bwd_coef_kernel)
+int r8tc_bn_bwd_coef(howl_ctx_t* ctx, cudaStream_t st, const float* w, const float* dw, const float* dones, const float* mean_rstd,
+                     double count, float* coef);
+int r8tc_debug_mask(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* u_op, const uint16_t* bits, uint8_t* mask, int64_t B, int H);
 // data-gradient weight operands of all six layers (direction 1 blocks of wprep)
 int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __nv_bfloat16* wprep);
 // forward weight operand of one layer with BatchNorm(mean_rstd, or identity when null) folded in (the border-dependent bias
 // rides on the ones channel)
 int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* blk);
-// forward (fwd, stats 0 / 1) or data gradient (!fwd, stats 0 / 2) of one layer; p.in is unused
-int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* in_op, __nv_bfloat16* out_op,
-              const __nv_bfloat16* w, bool fwd, int stats);
 int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_opT, const __nv_bfloat16* x_op, const float* x_mean,
-               const float* x_rstd, float* dw, int64_t B, int H);
+               const float* x_rstd, float* dw, float* dones, int64_t B, int H);

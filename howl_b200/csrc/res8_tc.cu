@@ -38,7 +38,7 @@ __host__ __device__ static inline int r8tc_dcop_rows_dev(int H) { return ((H + 2
 int r8tc_dcop_rows(int H) { return r8tc_dcop_rows_dev(H); }
 size_t r8tc_dcop_bytes(int H) { return (size_t)12 * r8tc_dcop_rows(H) * 16; }
 
-static size_t tc_stream_smem(int R) { return (size_t)TC_WBYTES + (size_t)12 * (2 * R + 2 * TC_PAD) * 16 + (48 * 2 + TS_EPI_WARPS * 2 * 16) * 4; }
+static size_t tc_stream_smem(int R) { return (size_t)TC_WBYTES + (size_t)12 * (2 * R + 2 * TC_PAD) * 16 + (48 * 3 + TS_EPI_WARPS * 2 * 16) * 4; }
 static size_t tc_wgrad_smem(int R) { return (size_t)6 * (12 * R * 16 / 4) + 2 * (size_t)12 * (R + 2 * TC_PAD) * 16; }   // TW_DSLOTS quarters + 2 X
 bool r8tc_supported(int H) {
   const int R = r8tc_dcop_rows(H);
@@ -118,18 +118,61 @@ int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const floa
 // stream kernel: forward (FWD) and data gradient of the 45->45 3x3 convolution
 // =============================================================================================
 struct TcStreamArgs {
-  ConvParams p;                  // out (planar fp32), res (FWD), stats, aux / aux_mean / aux_rstd (data gradient), B, H
+  ConvParams p;                  // out (planar fp32 or null), stats, B, H
   const __nv_bfloat16* in_op;    // [B][2][6][R][8]
-  __nv_bfloat16* out_op;         // FWD: the output in operand format as well, or null
+  __nv_bfloat16* out_op;         // forward: the output in operand format, or null
   const __nv_bfloat16* w;        // [9][6][96][8]
+  // forward extras
+  const __nv_bfloat16* res_op;   // residual (operand format) added after the ReLU, or null
+  uint16_t* mask_out;            // [B][3 channel groups][R] ReLU decisions (bit jj = channel 16 * grp + jj), or null
+  float* pooled_raw;             // [B][45] per-utterance spatial sums of the output (layer 6 -> head), or null
+  // data gradient with the BatchNorm backward of the producer layer j fused into the epilogue (MODE 3):
+  //   G = rstd * (g - m1 - xhat * m2) [+ gu_in];  gu_out = G;  dC = relu'(conv_j) ? G : 0  ->  dc_out (rows = pixels), dc_outT (rows = channels)
+  const __nv_bfloat16* u_op;     // u_j in operand format (xhat and, for odd j, the ReLU decision u > 0)
+  const float* bn_coef;          // [3][48]: rstd, A = -rstd m1 + mean rstd^2 m2, Bc = -rstd^2 m2   (G = rstd g + A + Bc u)
+  const float* gu_in;            // planar [B,45,H,10] residual-path gradient flowing into u_j, or null
+  float* gu_out;                 // planar G (even j), or null
+  const uint16_t* mask_in;       // ReLU decisions of conv_j stored by the forward (even j), or null (odd j: u > 0)
+  __nv_bfloat16* dc_out;
+  __nv_bfloat16* dc_outT;
   int R;
   unsigned long long* prof;      // tuning aid: per-CTA cycle counters of the pipeline waits, or null
 };
 
-// STATS: 0 none, 1 forward BatchNorm statistics (sum, sum of squares), 2 BatchNorm-backward (sum g, sum g * xhat(aux))
+// 8 channels of one raster row: operand-format (hi, lo) pair -> fp32
+__device__ __forceinline__ void tc_unpack8(const uint4& hi, const uint4& lo, float* v) {
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
+    v[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
+  }
+}
+
+// 8 x 8 transpose among the 8 lanes of a raster-row group: in  d[j] = channel j of this lane's row,
+// out d[j] = row j of the group for channel `sub` (= lane & 7)
+__device__ __forceinline__ void tc_transpose8(float* d, int sub) {
+#pragma unroll
+  for (int s = 1; s < 8; s <<= 1) {
+    const bool up = (sub & s) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if ((j & s) == 0) {
+        const float send = up ? d[j] : d[j + s];
+        const float got = __shfl_xor_sync(0xffffffffu, send, s);
+        if (up) d[j] = got; else d[j + s] = got;
+      }
+    }
+  }
+}
+
+// MODE 0: forward (eval), 1: forward + BatchNorm statistics (train), 2: plain data gradient (planar fp32 out; layer 1),
+//      3: data gradient + fused BatchNorm backward / ReLU mask of the producer layer (operand-format dC out)
 // SINGLE: fast mode, bf16 x bf16 only (the two low-order MMAs per product are skipped; conv_engine = 2)
-template <bool FWD, int STATS, bool SINGLE>
+template <int MODE, bool SINGLE>
 __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const TcStreamArgs a) {
+  constexpr bool FWD = MODE <= 1;
+  constexpr int STATS = MODE == 1 ? 1 : 0;
   extern __shared__ __align__(128) unsigned char smem[];
   const ConvParams& p = a.p;
   const int H = p.H, HW = H * R8_W, R = a.R, RS = 2 * R + 2 * TC_PAD, T = 2 * R / 128;
@@ -138,9 +181,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
   uint4* w_s = reinterpret_cast<uint4*>(smem);                              // [9][6][96] x 16 B
   uint4* a_s = reinterpret_cast<uint4*>(smem + TC_WBYTES);                  // [hi 6 | lo 6][RS] x 16 B, ring row r at TC_PAD + r
   float* s_f = reinterpret_cast<float*>(smem + TC_WBYTES + (size_t)12 * RS * 16);
-  float* s_amean = s_f;           // [48]
-  float* s_arstd = s_f + 48;      // [48]
-  float* s_red = s_f + 96;        // [12 warps][2][16]
+  float* s_coef = s_f;            // [3][48] BatchNorm-backward coefficients (MODE 3)
+  float* s_red = s_f + 144;       // [12 warps][2][16]
   __shared__ __align__(8) uint64_t bar_w, bar_in[2], bar_tile[5], bar_tfree[5];
   __shared__ long long s_tload[2];
   __shared__ uint32_t s_tmem;
@@ -160,11 +202,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
       tc::fence_barrier_init();
     }
   }
-  if (tid < 48) {
-    const bool c_ok = tid < R8_C;
-    s_amean[tid] = (STATS == 2 && c_ok) ? p.aux_mean[tid] : 0.f;
-    s_arstd[tid] = (STATS == 2 && c_ok) ? p.aux_rstd[tid] : 0.f;
-  }
+  if (tid < 144) s_coef[tid] = (MODE == 3) ? a.bn_coef[tid] : 0.f;
   // ring := 0 (a CTA with an odd utterance count multiplies a never-loaded slot into discarded rows); the zero pad rows in
   // front of and behind the ring stand for the neighbouring utterances' halo rows
   for (int i = tid; i < 12 * RS; i += TS_THREADS) a_s[i] = make_uint4(0, 0, 0, 0);
@@ -184,7 +222,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
     if (tc::elect_one()) {
       const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.in_op);
       const size_t utt_bytes = (size_t)12 * R * 16;
-      const float* side = FWD ? p.res : (STATS == 2 ? p.aux : nullptr);
+      const __nv_bfloat16* side_op = FWD ? a.res_op : (MODE == 3 ? a.u_op : nullptr);
+      const float* side = (MODE == 3) ? a.gu_in : nullptr;
       auto load = [&](int64_t k) {            // utterance k of this CTA -> ring slot k & 1, one copy per 8-channel group
         const int s = (int)(k & 1);
         const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
@@ -193,7 +232,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
         tc::mbar_expect_tx(&bar_in[s], (uint32_t)utt_bytes);
         for (int g = 0; g < 12; ++g)
           tc::tma_bulk_g2s(a_s + (size_t)g * RS + TC_PAD + s * R, src + (size_t)g * R * 16, (uint32_t)(R * 16), &bar_in[s]);
-        // the planes the epilogue of this utterance will read (residual / BatchNorm-backward input): pull them into L2 now
+        // what the epilogue of this utterance will read (residual / BatchNorm-backward input): pull it into L2 now
+        if (side_op) tc::l2_prefetch_bulk(reinterpret_cast<const unsigned char*>(side_op) + (size_t)b * utt_bytes, (uint32_t)utt_bytes);
         if (side) {
           const uintptr_t lo = reinterpret_cast<uintptr_t>(side + b * (int64_t)R8_C * HW);
           const uintptr_t lo16 = lo & ~(uintptr_t)15, hi16 = (lo + (uintptr_t)R8_C * HW * 4 + 15) & ~(uintptr_t)15;
@@ -286,7 +326,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
     float st1[16], st2[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) st1[c] = st2[c] = 0.f;
-    const float* side = FWD ? p.res : (STATS == 2 ? p.aux : nullptr);
     unsigned long long ep_wait = 0;
     const long long ep_begin = clock64();
     for (int64_t cyc = 0; cyc < n_cycles; ++cyc) {
@@ -297,20 +336,36 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
         const int r = 128 * j + 32 * (warp & 3) + lane;
         const int slot = r >= R ? 1 : 0, q = r - slot * R;
         const int64_t kk = 2 * cyc + slot;
-        const bool live = kk < n_local;
+        const bool live = kk < n_local;                       // warp uniform: R is a multiple of 64
         const int64_t b = blockIdx.x + kk * (int64_t)gridDim.x;
         const int y = q / TC_PITCH - 1, x = q % TC_PITCH - 1;
         const bool valid = live && (y >= 0) && (y < H) && (x >= 0) && (x < R8_W);
         // 32-bit element offset of (b, first channel of the quad, y, x); the host checks B * 45 * HW < 2^31
         const uint32_t off0 = valid ? (uint32_t)(b * R8_C + 16 * grp) * (uint32_t)HW + (uint32_t)(y * R8_W + x) : 0u;
         const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(96 * j + 16 * grp);
-        float pre[16];
+        const size_t op_row = (size_t)b * 12 * R + q;         // 16-byte units; chunk c of part p at (p * 6 + c) * R
+        // ---- everything the tile's epilogue reads from HBM is requested before the accumulator wait
+        float pre[16], gin[16];
+        uint32_t bits = 0;
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) pre[jj] = 0.f;
-        if (side != nullptr && valid) {
+        for (int jj = 0; jj < 16; ++jj) pre[jj] = gin[jj] = 0.f;
+        const __nv_bfloat16* side_op = FWD ? a.res_op : (MODE == 3 ? a.u_op : nullptr);
+        if (side_op != nullptr && valid) {
+          const uint4* so = reinterpret_cast<const uint4*>(side_op) + op_row;
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj)
-            if (jj < 13 || full) pre[jj] = __ldg(side + off0 + (uint32_t)jj * (uint32_t)HW);
+          for (int cb = 0; cb < 2; ++cb) {
+            const int ch = 2 * grp + cb;
+            const uint4 hi = __ldg(so + (size_t)ch * R), lo = __ldg(so + (size_t)(6 + ch) * R);
+            tc_unpack8(hi, lo, pre + 8 * cb);
+          }
+        }
+        if (MODE == 3 && valid) {
+          if (a.gu_in) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj)
+              if (jj < 13 || full) gin[jj] = __ldg(a.gu_in + off0 + (uint32_t)jj * (uint32_t)HW);
+          }
+          if (a.mask_in) bits = a.mask_in[((size_t)b * 3 + grp) * R + q];
         }
         const long long te0 = (a.prof && warp == 0) ? clock64() : 0;
         tc::mbar_wait(&bar_tile[j], par);
@@ -323,35 +378,86 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
         float ov[16];
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) ov[jj] = 0.f;
-        if (valid) {
+        if (FWD) {
+          uint32_t mbits = 0;
+          if (valid) {
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            if (jj < 13 || full) {
-              float o = __uint_as_float(v[jj]) + (SINGLE ? 0.f : __uint_as_float(v2[jj]));
-              if (FWD) o = fmaxf(o, 0.f) + pre[jj];
-              p.out[off0 + (uint32_t)jj * (uint32_t)HW] = o;
-              if (STATS == 1) {
-                st1[jj] += o;
-                st2[jj] = fmaf(o, o, st2[jj]);
-              } else if (STATS == 2) {
-                st1[jj] += o;
-                st2[jj] = fmaf(o, pre[jj], st2[jj]);     // sum g * u; centred and scaled once at the end
+            for (int jj = 0; jj < 16; ++jj) {
+              if (jj < 13 || full) {
+                const float acc = __uint_as_float(v[jj]) + (SINGLE ? 0.f : __uint_as_float(v2[jj]));
+                if (acc > 0.f) mbits |= 1u << jj;
+                const float o = fmaxf(acc, 0.f) + pre[jj];
+                if (p.out) p.out[off0 + (uint32_t)jj * (uint32_t)HW] = o;
+                if (STATS == 1) {
+                  st1[jj] += o;
+                  st2[jj] = fmaf(o, o, st2[jj]);
+                }
+                ov[jj] = o;
+              } else if (jj == 13) {
+                ov[jj] = 1.f;                 // channel 45: the "ones" channel (BatchNorm fold of the consumer and of its weight gradient)
               }
-              ov[jj] = o;
-            } else if (FWD && jj == 13) {
-              ov[jj] = 1.f;                 // channel 45: the "ones" channel (BatchNorm fold of the consumer and of its weight gradient)
             }
           }
-        }
-        if (FWD && a.out_op && live) {
-          uint4* o_op = reinterpret_cast<uint4*>(a.out_op) + (size_t)b * 12 * R + q;
+          if (live) {
+            if (a.out_op) {
+              uint4* o_op = reinterpret_cast<uint4*>(a.out_op) + op_row;
 #pragma unroll
-          for (int cb = 0; cb < 2; ++cb) {
-            uint4 hi, lo;
-            tc::split8(ov + 8 * cb, hi, lo);
-            const int ch = 2 * grp + cb;
-            o_op[(size_t)ch * R] = hi;
-            o_op[(size_t)(6 + ch) * R] = lo;
+              for (int cb = 0; cb < 2; ++cb) {
+                uint4 hi, lo;
+                tc::split8(ov + 8 * cb, hi, lo);
+                const int ch = 2 * grp + cb;
+                o_op[(size_t)ch * R] = hi;
+                o_op[(size_t)(6 + ch) * R] = lo;
+              }
+            }
+            if (a.mask_out) a.mask_out[((size_t)b * 3 + grp) * R + q] = (uint16_t)mbits;
+            if (a.pooled_raw) {              // per-utterance spatial sums for the head (a warp's 32 rows belong to one utterance)
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                if (jj < 13 || full) {
+                  const float sum = warp_sum(ov[jj]);
+                  if (lane == 0) atomicAdd(a.pooled_raw + b * R8_C + 16 * grp + jj, sum);
+                }
+              }
+            }
+          }
+        } else if (MODE == 2) {
+          if (valid) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj)
+              if (jj < 13 || full) p.out[off0 + (uint32_t)jj * (uint32_t)HW] = __uint_as_float(v[jj]) + (SINGLE ? 0.f : __uint_as_float(v2[jj]));
+          }
+        } else {
+          // MODE 3: BatchNorm backward of the producer layer + residual fan-in + ReLU mask, straight from the accumulator
+          if (valid) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              if (jj < 13 || full) {
+                const int c = 16 * grp + jj;
+                const float g = __uint_as_float(v[jj]) + (SINGLE ? 0.f : __uint_as_float(v2[jj]));
+                const float u = pre[jj];
+                const float G = fmaf(s_coef[c], g, fmaf(s_coef[96 + c], u, s_coef[48 + c])) + gin[jj];
+                if (a.gu_out) a.gu_out[off0 + (uint32_t)jj * (uint32_t)HW] = G;
+                const bool on = a.mask_in ? ((bits >> jj) & 1u) != 0 : (u > 0.f);
+                ov[jj] = on ? G : 0.f;
+              }
+            }
+          }
+          if (live) {                        // halo rows are written too (zeros): no memset of the gradient operands
+            uint4* o_op = reinterpret_cast<uint4*>(a.dc_out) + op_row;
+            uint4* o_T = reinterpret_cast<uint4*>(a.dc_outT) + ((size_t)b * (R / 8) + (q >> 3)) * 96 + (lane & 7);
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb) {
+              uint4 hi, lo;
+              const int ch = 2 * grp + cb;
+              tc::split8(ov + 8 * cb, hi, lo);
+              o_op[(size_t)ch * R] = hi;
+              o_op[(size_t)(6 + ch) * R] = lo;
+              tc_transpose8(ov + 8 * cb, lane & 7);          // lane & 7 now holds channel 8 * ch + (lane & 7) at the group's 8 rows
+              tc::split8(ov + 8 * cb, hi, lo);
+              o_T[ch * 8] = hi;
+              o_T[48 + ch * 8] = lo;
+            }
           }
         }
         tc::fence_before_sync();
@@ -378,46 +484,50 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
   __syncthreads();
   if (STATS && tid < 2 * R8_C) {
     const int which = tid / R8_C, c = tid - which * R8_C, grp = c / 16, jj = c - 16 * grp;
-    double s = 0.0, s1 = 0.0;
-    for (int w = 4 * grp; w < 4 * grp + 4; ++w) {
-      s += (double)s_red[(w * 2 + which) * 16 + jj];
-      s1 += (double)s_red[(w * 2 + 0) * 16 + jj];
-    }
-    if (STATS == 2 && which == 1) s = (double)s_arstd[c] * (s - (double)s_amean[c] * s1);   // sum g * xhat
+    double s = 0.0;
+    for (int w = 4 * grp; w < 4 * grp + 4; ++w) s += (double)s_red[(w * 2 + which) * 16 + jj];
     atomicAdd(&p.stats[tid], s);
   }
   if (warp == TS_EPI_WARPS) tc::tmem_dealloc<512>(tmem);
 }
 
-// mode: forward = stats 0 / 1 with fwd = true; data gradient = stats 0 / 2 with fwd = false
-int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const ConvParams& p, const __nv_bfloat16* in_op, __nv_bfloat16* out_op,
-              const __nv_bfloat16* w, bool fwd, int stats) {
+int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const TcConvCall& c) {
   TcStreamArgs a;
-  a.p = p;
-  a.in_op = in_op; a.out_op = out_op; a.w = w;
-  HOWL_REQUIRE(ctx, p.B * (int64_t)R8_C * p.H * R8_W < ((int64_t)1 << 31), HOWL_E_UNSUPPORTED,
-               "tensor-core conv: batch of %lld utterances exceeds the 32-bit element offsets", (long long)p.B);
-  a.R = r8tc_dcop_rows(p.H);
+  memset(&a, 0, sizeof(a));
+  a.p.B = c.B; a.p.H = c.H; a.p.out = c.out_planar; a.p.stats = c.stats;
+  a.in_op = c.in_op; a.out_op = c.out_op; a.w = c.w;
+  a.res_op = c.res_op; a.mask_out = c.mask_out; a.pooled_raw = c.pooled_raw;
+  a.u_op = c.u_op; a.bn_coef = c.bn_coef; a.gu_in = c.gu_in; a.gu_out = c.gu_out; a.mask_in = c.mask_in;
+  a.dc_out = c.dc_out; a.dc_outT = c.dc_outT;
+  HOWL_REQUIRE(ctx, c.B * (int64_t)R8_C * c.H * R8_W < ((int64_t)1 << 31), HOWL_E_UNSUPPORTED,
+               "tensor-core conv: batch of %lld utterances exceeds the 32-bit element offsets", (long long)c.B);
+  HOWL_REQUIRE(ctx, c.in_op && c.w, HOWL_E_INVALID, "tensor-core conv: null operand");
+  HOWL_REQUIRE(ctx, c.mode != 1 || c.stats, HOWL_E_INVALID, "tensor-core conv: statistics buffer missing");
+  HOWL_REQUIRE(ctx, c.mode != 2 || c.out_planar, HOWL_E_INVALID, "tensor-core conv: output missing");
+  HOWL_REQUIRE(ctx, c.mode != 3 || (c.u_op && c.bn_coef && c.dc_out && c.dc_outT && c.dc_out != c.in_op), HOWL_E_INVALID,
+               "tensor-core conv: fused BatchNorm-backward arguments missing");
+  a.R = r8tc_dcop_rows(c.H);
+  const bool fwd = c.mode <= 1;
   a.prof = (ctx->tc_prof && ctx->tc_prof_kind == (fwd ? 1 : 2)) ? ctx->tc_prof : nullptr;
-  HOWL_REQUIRE(ctx, r8tc_supported(p.H), HOWL_E_UNSUPPORTED, "tensor-core conv: H=%d does not fit", p.H);
+  HOWL_REQUIRE(ctx, r8tc_supported(c.H), HOWL_E_UNSUPPORTED, "tensor-core conv: H=%d does not fit", c.H);
   const size_t smem = tc_stream_smem(a.R);
-  const int grid = (int)(p.B < ctx->sm_count ? p.B : ctx->sm_count);
+  const int grid = (int)(c.B < ctx->sm_count ? c.B : ctx->sm_count);
   const bool single = ctx->conv_engine == 2;
-#define TS_LAUNCH1(FWD_, STATS_, SINGLE_)                                                                                \
+#define TS_LAUNCH1(MODE_, SINGLE_)                                                                                       \
   do {                                                                                                                   \
-    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_stream_tc_kernel<FWD_, STATS_, SINGLE_>,                                 \
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(conv3x3_stream_tc_kernel<MODE_, SINGLE_>,                                        \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
-    conv3x3_stream_tc_kernel<FWD_, STATS_, SINGLE_><<<grid, TS_THREADS, smem, st>>>(a);                                  \
+    conv3x3_stream_tc_kernel<MODE_, SINGLE_><<<grid, TS_THREADS, smem, st>>>(a);                                         \
   } while (0)
-#define TS_LAUNCH(FWD_, STATS_)                  \
-  do {                                           \
-    if (single) TS_LAUNCH1(FWD_, STATS_, true);  \
-    else TS_LAUNCH1(FWD_, STATS_, false);        \
+#define TS_LAUNCH(MODE_)                  \
+  do {                                    \
+    if (single) TS_LAUNCH1(MODE_, true);  \
+    else TS_LAUNCH1(MODE_, false);        \
   } while (0)
-  if (fwd && stats == 1) TS_LAUNCH(true, 1);
-  else if (fwd && stats == 0) TS_LAUNCH(true, 0);
-  else if (!fwd && stats == 2) TS_LAUNCH(false, 2);
-  else if (!fwd && stats == 0) TS_LAUNCH(false, 0);
+  if (c.mode == 0) TS_LAUNCH(0);
+  else if (c.mode == 1) TS_LAUNCH(1);
+  else if (c.mode == 2) TS_LAUNCH(2);
+  else if (c.mode == 3) TS_LAUNCH(3);
   else HOWL_REQUIRE(ctx, false, HOWL_E_INVALID, "tensor-core conv: unsupported mode");
 #undef TS_LAUNCH
 #undef TS_LAUNCH1
@@ -445,6 +555,7 @@ struct TcWgradArgs {
   const float* x_mean;   // or null (layer 1: X = a0, no normalisation)
   const float* x_rstd;
   float* dw;
+  float* dones;          // [45][9]: sum_q dC[q][o] * 1[q + shift inside the image] -- the raw ones column (BatchNorm-backward statistics), or null
   int64_t B;
   int R;
 };
@@ -572,6 +683,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
       tc::tmem_ld16(taddr + 32, v + 32);
       if (ok) {
         const float ones = v[R8_C];
+        if (a.dones) atomicAdd(&a.dones[o * 9 + tap], ones);
 #pragma unroll
         for (int c = 0; c < R8_C; ++c) {
           const float mu = a.x_mean ? __ldg(a.x_mean + c) : 0.f, rs = a.x_rstd ? __ldg(a.x_rstd + c) : 1.f;
@@ -586,9 +698,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
 }
 
 int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_opT, const __nv_bfloat16* x_op, const float* x_mean,
-               const float* x_rstd, float* dw, int64_t B, int H) {
+               const float* x_rstd, float* dw, float* dones, int64_t B, int H) {
   TcWgradArgs a;
-  a.dc_opT = dc_opT; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.B = B;
+  a.dc_opT = dc_opT; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.dones = dones; a.B = B;
   a.R = r8tc_dcop_rows(H);
   HOWL_REQUIRE(ctx, r8tc_supported(H), HOWL_E_UNSUPPORTED, "tensor-core wgrad: H=%d does not fit", H);
   const size_t smem = tc_wgrad_smem(a.R);
@@ -604,18 +716,69 @@ int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_opT, co
   return HOWL_OK;
 }
 
-// BatchNorm backward + residual fan-in + ReLU mask (same arithmetic as bn_bwd_apply_kernel in res8.cu).  One thread = 8 channels
-// of one RASTER position (halo positions compute zeros), so a warp covers four aligned groups of 8 raster rows.  Emits the
-// conv-output gradient twice, both as (hi, lo) bf16:
-//   dc_op  [hi, lo][6 chunks][R rows][8 channels]       rows = pixels : A operand of the data gradient (K = channels)
-//   dc_opT [R / 8 row groups][hi 48 | lo 48 channels][8 rows]  rows = channels: K-major A operand of the weight gradient, which copies
-//          it to tensor memory (K = pixels); produced by an 8 x 8 transpose among the 8 lanes of a row group.
-// grid.y = channel chunk.
-template <bool EVEN, bool GU_IN, bool BCAST>
-__global__ void __launch_bounds__(256) bn_bwd_apply_op_kernel(const ApplyOpParams p) {
+// =============================================================================================
+// BatchNorm-backward statistics of layer j = i - 1 WITHOUT a pass over the gradient tensor: with g = dL/d(xn_j) the data gradient of
+// conv_i,   sum_q g[q][c]        = sum_{o,tap} W_i[o][c][tap] * D1[o][tap]          D1 = the weight gradient's raw ones column
+//           sum_q g[q][c] xhat_j = sum_{o,tap} W_i[o][c][tap] * dW_i[o][c][tap]     dW_i = the (BatchNorm-folded) weight gradient
+// (substitute g = sum_{o,tap} W_i dC_i[q - s] and exchange the sums).  So the weight-gradient kernel of layer i, which runs before
+// the data gradient, already holds both statistics, and the data-gradient epilogue can apply the BatchNorm backward on the fly.
+// Output: the coefficients of  G = rstd g + A + Bc u   (= rstd (g - m1 - xhat m2)),  [3][48].   grid = 48 channels.
+// =============================================================================================
+__global__ void __launch_bounds__(128) bn_bwd_coef_kernel(const float* __restrict__ w, const float* __restrict__ dw,
+                                                          const float* __restrict__ dones, const float* __restrict__ mean_rstd,
+                                                          double count, float* __restrict__ coef) {
+  const int c = blockIdx.x, tid = threadIdx.x;
+  __shared__ double sh[2][4];
+  double s1 = 0.0, s2 = 0.0;
+  if (c < R8_C) {
+    for (int i = tid; i < R8_C * 9; i += 128) {
+      const int o = i / 9, tap = i - o * 9;
+      const double wv = (double)w[(o * R8_C + c) * 9 + tap];
+      s1 += wv * (double)dones[i];
+      s2 += wv * (double)dw[(o * R8_C + c) * 9 + tap];
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((tid & 31) == 0) {
+    sh[0][tid >> 5] = s1;
+    sh[1][tid >> 5] = s2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float rs = 0.f, A = 0.f, Bc = 0.f;
+    if (c < R8_C) {
+      const double m1 = (sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]) / count, m2 = (sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3]) / count;
+      const double mu = mean_rstd[c], r = mean_rstd[R8_C + c];
+      rs = (float)r;
+      A = (float)(-r * m1 + mu * r * r * m2);
+      Bc = (float)(-r * r * m2);
+    }
+    coef[c] = rs;
+    coef[48 + c] = A;
+    coef[96 + c] = Bc;
+  }
+}
+
+int r8tc_bn_bwd_coef(howl_ctx_t* ctx, cudaStream_t st, const float* w, const float* dw, const float* dones, const float* mean_rstd,
+                     double count, float* coef) {
+  bn_bwd_coef_kernel<<<48, 128, 0, st>>>(w, dw, dones, mean_rstd, count, coef);
+  HOWL_LAUNCHED(ctx, "bn_bwd_coef");
+  return HOWL_OK;
+}
+
+// =============================================================================================
+// Head of the backward: BatchNorm backward + ReLU mask of layer 6, whose upstream gradient is the broadcast dh / HW (spatial mean).
+// One thread = 8 channels of one RASTER position (halo positions compute zeros, so no memset).  Emits the conv-output gradient as
+// both gradient operands, (hi, lo) bf16:
+//   dc_op  [hi, lo][6 chunks][R rows][8 channels]               rows = pixels : A operand of the data gradient (K = channels)
+//   dc_opT [R / 8 row groups][hi 48 | lo 48 channels][8 rows]   rows = channels: K-major A operand of the weight gradient
+// and G itself (planar) as the residual-path gradient of layer 4.   grid.y = channel chunk.
+// =============================================================================================
+__global__ void __launch_bounds__(256) bn_bwd_head_op_kernel(const ApplyOpParams p) {
   const int HW = p.H * R8_W, R = r8tc_dcop_rows_dev(p.H), chunk = blockIdx.y;
   float mu[8], rs[8], m1[8], m2[8], live[8];
-  int coff[8];
+  int coff[8], cidx[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
@@ -626,9 +789,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_op_kernel(const ApplyOpParam
     m1[j] = (float)(p.stats[cc] / p.count);
     m2[j] = (float)(p.stats[R8_C + cc] / p.count);
     coff[j] = cc * HW;
+    cidx[j] = cc;
   }
   const float inv_hw = 1.f / (float)HW;
   const int64_t items = p.B * R;                     // multiple of 64: whole warps, aligned 8-lane row groups
+  const uint4* uop = reinterpret_cast<const uint4*>(p.u_op);
   uint4* out = reinterpret_cast<uint4*>(p.dc_op);
   uint4* outT = reinterpret_cast<uint4*>(p.dc_opT);
   const int lane = threadIdx.x & 31, sub = lane & 7;
@@ -640,43 +805,25 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_op_kernel(const ApplyOpParam
     float d[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) d[j] = 0.f;
+    const int64_t base = b * 12 * (int64_t)R + (int64_t)chunk * R + q;
     if (valid) {
       const int64_t ub = b * (int64_t)R8_C * HW + y * R8_W + x;
-      float g[8], u[8], gi[8], pv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {       // every load of the item is issued before any is consumed
-        const int64_t idx = ub + coff[j];
-        u[j] = p.u[idx];
-        g[j] = BCAST ? __ldg(p.g_bcast + b * R8_C + (coff[j] / HW)) * inv_hw : p.g[idx];
-        gi[j] = GU_IN ? p.gu_in[idx] : 0.f;
-        pv[j] = EVEN ? p.mask_prev[idx] : 0.f;
-      }
+      float u[8];
+      tc_unpack8(__ldg(uop + base), __ldg(uop + base + 6 * (int64_t)R), u);
+      const uint32_t bits = (uint32_t)p.mask_bits[(b * 3 + (chunk >> 1)) * R + q] >> (8 * (chunk & 1));
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float G = rs[j] * (g[j] - m1[j] - (u[j] - mu[j]) * rs[j] * m2[j]) + gi[j];
-        if (EVEN && live[j] != 0.f) p.gu_out[ub + coff[j]] = G;
-        d[j] = (u[j] > pv[j]) ? G * live[j] : 0.f;
+        const float g = __ldg(p.g_bcast + b * R8_C + cidx[j]) * inv_hw;
+        const float G = rs[j] * (g - m1[j] - (u[j] - mu[j]) * rs[j] * m2[j]);
+        if (live[j] != 0.f) p.gu_out[ub + coff[j]] = G;
+        d[j] = ((bits >> j) & 1u) ? G * live[j] : 0.f;
       }
     }
     uint4 hi, lo;
     tc::split8(d, hi, lo);
-    const int64_t base = b * 12 * (int64_t)R + (int64_t)chunk * R + q;
     out[base] = hi;                                   // halo rows are written too (zeros): no memset of dc_op needed
     out[base + 6 * (int64_t)R] = lo;
-    // 8 x 8 transpose inside the row group: afterwards lane `sub` holds channel chunk * 8 + sub at the group's 8 rows
-#pragma unroll
-    for (int s = 1; s < 8; s <<= 1) {
-      const bool up = (sub & s) != 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if ((j & s) == 0) {
-          // lanes with bit s clear keep d[j] and receive the partner's d[j] into d[j + s]; lanes with it set do the mirror image
-          const float send = up ? d[j] : d[j + s];
-          const float got = __shfl_xor_sync(0xffffffffu, send, s);
-          if (up) d[j] = got; else d[j + s] = got;
-        }
-      }
-    }
+    tc_transpose8(d, sub);                            // afterwards lane `sub` holds channel chunk * 8 + sub at the group's 8 rows
     tc::split8(d, hi, lo);
     const int64_t baseT = (b * (int64_t)(R / 8) + (q >> 3)) * 96 + chunk * 8 + sub;
     outT[baseT] = hi;
@@ -684,25 +831,41 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_op_kernel(const ApplyOpParam
   }
 }
 
-int r8tc_apply(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p) {
+int r8tc_apply_head(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p) {
   const int64_t items = p.B * r8tc_dcop_rows(p.H);
   int64_t bx = howl_ceil_div(items, 256);
   const int64_t cap = (int64_t)ctx->sm_count * 4;
   if (bx > cap) bx = cap;
   const dim3 grid((unsigned)bx, 6, 1);
-  const bool even = p.gu_out != nullptr;
-  HOWL_REQUIRE(ctx, even == (p.mask_prev != nullptr) && (!p.gu_in || even) && ((p.g != nullptr) != (p.g_bcast != nullptr)),
-               HOWL_E_INVALID, "apply: inconsistent arguments");
-  if (p.g_bcast) {
-    HOWL_REQUIRE(ctx, even && !p.gu_in, HOWL_E_INVALID, "apply: broadcast gradient is the last (even) layer");
-    bn_bwd_apply_op_kernel<true, false, true><<<grid, 256, 0, st>>>(p);
-  } else if (even && p.gu_in) {
-    bn_bwd_apply_op_kernel<true, true, false><<<grid, 256, 0, st>>>(p);
-  } else if (even) {
-    bn_bwd_apply_op_kernel<true, false, false><<<grid, 256, 0, st>>>(p);
-  } else {
-    bn_bwd_apply_op_kernel<false, false, false><<<grid, 256, 0, st>>>(p);
+  HOWL_REQUIRE(ctx, p.g_bcast && p.u_op && p.mask_bits && p.gu_out && p.dc_op && p.dc_opT, HOWL_E_INVALID, "apply_head: null argument");
+  bn_bwd_head_op_kernel<<<grid, 256, 0, st>>>(p);
+  HOWL_LAUNCHED(ctx, "bn_bwd_head_op");
+  return HOWL_OK;
+}
+
+// test hook: ReLU decisions of the tensor-core engine as bytes [B,45,H,10]: the stored bits (even layers), or u > 0 (odd layers)
+__global__ void tc_debug_mask_kernel(const __nv_bfloat16* __restrict__ u_op, const uint16_t* __restrict__ bits, uint8_t* __restrict__ mask,
+                                     int64_t B, int H) {
+  const int HW = H * R8_W, R = r8tc_dcop_rows_dev(H);
+  const int64_t n = B * R8_C * HW;
+  const uint4* uop = reinterpret_cast<const uint4*>(u_op);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW), c = (int)((i / HW) % R8_C);
+    const int64_t b = i / ((int64_t)HW * R8_C);
+    const int q = (pix / R8_W + 1) * TC_PITCH + (pix % R8_W + 1);
+    if (bits) {
+      mask[i] = (bits[(b * 3 + c / 16) * R + q] >> (c % 16)) & 1;
+    } else {
+      float u[8];
+      const int64_t base = b * 12 * (int64_t)R + (int64_t)(c / 8) * R + q;
+      tc_unpack8(uop[base], uop[base + 6 * (int64_t)R], u);
+      mask[i] = u[c % 8] > 0.f ? 1 : 0;
+    }
   }
-  HOWL_LAUNCHED(ctx, "bn_bwd_apply_op");
+}
+
+int r8tc_debug_mask(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* u_op, const uint16_t* bits, uint8_t* mask, int64_t B, int H) {
+  tc_debug_mask_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(u_op, bits, mask, B, H);
+  HOWL_LAUNCHED(ctx, "debug_mask");
   return HOWL_OK;
 }

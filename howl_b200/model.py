@@ -108,9 +108,12 @@ def _flatten_into(owner, params, attr: str, device):
 
 
 def _check_unchanged(ctx, flat):
-    if flat.data_ptr() != ctx.flat_ptr or flat._version != ctx.flat_version:
-        raise RuntimeError("howl_b200: the model's parameters were modified (or moved) between forward and backward; "
+    """Backward differentiates against the flat parameter buffer: refuse if it moved, and let autograd's saved-tensor version
+    check refuse if a parameter was modified in place since the forward (as torch does for its own modules)."""
+    if flat.data_ptr() != ctx.flat_ptr:
+        raise RuntimeError("howl_b200: the model's parameters were modified (moved) between forward and backward; "
                            "gradients would be computed against the wrong weights")
+    _ = ctx.saved_tensors
 
 
 class _Res8Function(torch.autograd.Function):
@@ -125,7 +128,8 @@ class _Res8Function(torch.autograd.Function):
                          device=feats.device)
         logits = model._run_forward(feats, train=True, ws=ws)
         ctx.model, ctx.feats, ctx.ws = model, feats, ws
-        ctx.flat_ptr, ctx.flat_version = model._flat.data_ptr(), model._flat._version
+        ctx.flat_ptr = model._flat.data_ptr()
+        ctx.save_for_backward(*params)
         return logits
 
     @staticmethod
@@ -234,7 +238,8 @@ class _LstmFunction(torch.autograd.Function):
         ws = torch.empty(c.lstm_workspace_bytes(feats.shape[0], max_steps, model.num_labels, True, model.SEQUENTIAL), dtype=torch.uint8,
                          device=feats.device)          # per-forward workspace, kept on the autograd ctx (see _Res8Function)
         ctx.model, ctx.shape, ctx.lengths, ctx.max_steps, ctx.ws = model, tuple(feats.shape), lengths, max_steps, ws
-        ctx.flat_ptr, ctx.flat_version = model._flat.data_ptr(), model._flat._version
+        ctx.flat_ptr = model._flat.data_ptr()
+        ctx.save_for_backward(*params)
         return model._run(feats, lengths, max_steps, train=True, ws=ws)
 
     @staticmethod
