@@ -6,6 +6,7 @@
 #include "../../include/howl_b200_debug.h"
 
 char g_howl_create_error[512] = "";
+int howl_fe_alloc_scratch(howl_ctx_t* ctx);   // frontend.cu
 
 extern "C" int howl_b200_abi_version(void) { return HOWL_B200_ABI_VERSION; }
 
@@ -46,21 +47,35 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
   ctx->tc_prof_kind = 0;
   // tables in double, rounded once
   float win[HOWL_NFFT];
-  float2 tw256[256], tw512[HOWL_NFREQ];
+  static float2 tw_lane[32 * 8], tw_stage[32 * 4], w512_lane[32 * 8];
   const double two_pi = 6.283185307179586476925286766559;
+  auto br5 = [](int x) { return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4); };
   for (int n = 0; n < HOWL_NFFT; ++n) win[n] = (float)(0.5 - 0.5 * cos(two_pi * n / HOWL_NFFT));
-  for (int k = 0; k < 256; ++k) tw256[k] = make_float2((float)cos(two_pi * k / 256), (float)(-sin(two_pi * k / 256)));
-  for (int k = 0; k < HOWL_NFREQ; ++k)
-    tw512[k] = make_float2((float)cos(two_pi * k / 512), (float)(-sin(two_pi * k / 512)));
+  for (int L = 0; L < 32; ++L) {
+    for (int m2 = 0; m2 < 8; ++m2) {
+      tw_lane[L * 8 + m2] = make_float2((float)cos(two_pi * L * m2 / 256), (float)(-sin(two_pi * L * m2 / 256)));
+      const int m = m2 + 8 * br5(L);
+      w512_lane[L * 8 + m2] = make_float2((float)cos(two_pi * m / 512), (float)(-sin(two_pi * m / 512)));
+    }
+    for (int s = 0; s < 4; ++s) {
+      const int h = 16 >> s;                       // radix-2 DIF stage of span h: the upper lane multiplies by W_(2h)^(L mod h)
+      const bool upper = (L & h) != 0;
+      const double ang = two_pi * (L % h) / (2 * h);
+      tw_stage[L * 4 + s] = upper ? make_float2((float)cos(ang), (float)(-sin(ang))) : make_float2(1.f, 0.f);
+    }
+  }
 #define CK(x)                                                                          \
   if ((e = (x)) != cudaSuccess) CREATE_FAIL(HOWL_E_CUDA, "%s: %s", #x, cudaGetErrorString(e))
   CK(cudaMalloc(&ctx->d_window, sizeof(win)));
-  CK(cudaMalloc(&ctx->d_tw256, sizeof(tw256)));
-  CK(cudaMalloc(&ctx->d_tw512, sizeof(tw512)));
+  CK(cudaMalloc(&ctx->d_tw_lane, sizeof(tw_lane)));
+  CK(cudaMalloc(&ctx->d_tw_stage, sizeof(tw_stage)));
+  CK(cudaMalloc(&ctx->d_w512_lane, sizeof(w512_lane)));
   CK(cudaMemcpy(ctx->d_window, win, sizeof(win), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_tw256, tw256, sizeof(tw256), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(ctx->d_tw512, tw512, sizeof(tw512), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_tw_lane, tw_lane, sizeof(tw_lane), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_tw_stage, tw_stage, sizeof(tw_stage), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_w512_lane, w512_lane, sizeof(w512_lane), cudaMemcpyHostToDevice));
 #undef CK
+  if (howl_fe_alloc_scratch(ctx) != HOWL_OK) CREATE_FAIL(HOWL_E_CUDA, "create: cudaMalloc of the filterbank scratch failed");
   *out_ctx = ctx;
   return HOWL_OK;
 }
@@ -70,6 +85,10 @@ extern "C" int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t v
   if (strcmp(name, "conv_engine") == 0) {
     HOWL_REQUIRE(ctx, value >= 0 && value <= 2, HOWL_E_INVALID, "set_option: conv_engine must be 0 (fp32), 1 (tcgen05, split bf16) or 2 (tcgen05, single bf16)");
     ctx->conv_engine = (int)value;
+    return HOWL_OK;
+  }
+  if (strcmp(name, "fb_unchanged") == 0) {   // one-shot: the next frontend call's filterbank equals the previous call's
+    ctx->fb_same_next = value != 0;
     return HOWL_OK;
   }
   HOWL_SET_ERR(ctx, "set_option: unknown option '%s'", name);
@@ -110,13 +129,11 @@ extern "C" void howl_b200_destroy(howl_ctx_t* ctx) {
   if (ctx->prof_ev[0])
     for (int i = 0; i <= HOWL_PROF_CAP; ++i) cudaEventDestroy(ctx->prof_ev[i]);
   cudaFree(ctx->d_window);
-  cudaFree(ctx->d_tw256);
-  cudaFree(ctx->d_tw512);
-  cudaFree(ctx->fb_lo);
-  cudaFree(ctx->fb_hi);
-  cudaFree(ctx->fb_off);
-  cudaFree(ctx->fbc);
-  cudaFree(ctx->mel_plan);
+  cudaFree(ctx->d_tw_lane);
+  cudaFree(ctx->d_tw_stage);
+  cudaFree(ctx->d_w512_lane);
+  cudaFree(ctx->fe_bank);
+  cudaFree(ctx->fe_ent);
   free(ctx);
 }
 

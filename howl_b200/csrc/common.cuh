@@ -18,14 +18,14 @@ struct howl_ctx {
   howl_frontend_cfg fe;
   // device tables (built in double on the host, rounded once to f32)
   float* d_window;   // [512]  periodic Hann
-  float2* d_tw256;   // [256]  exp(-2*pi*i*k/256)
-  float2* d_tw512;   // [257]  exp(-2*pi*i*k/512)
-  // compact filterbank scratch (rebuilt by every frontend call; stream ordered)
-  int* fb_lo;
-  int* fb_hi;
-  int* fb_off;
-  float* fbc;
-  int* mel_plan;     // FePlan (frontend.cu)
+  float2* d_tw_lane;    // [32][8]  W256^(L * m2): twiddles between the in-register and the cross-lane part of the warp FFT
+  float2* d_tw_stage;   // [32][4]  cross-lane stage twiddles of lane L (spans 16, 8, 4, 2; 1 in the lower lane of a pair)
+  float2* d_w512_lane;  // [32][8]  W512^(m2 + 8 * br5(L)): real-FFT post-processing twiddles of the bins lane L ends up with
+  // block-entry filterbank (frontend.cu: FeBank + entries), rebuilt when the bank changes; stream ordered
+  void* fe_bank;
+  float* fe_ent;
+  int fb_plan_valid; // the compact bank / plan on the device belong to the filterbank of the previous frontend call
+  int fb_same_next;  // one-shot promise of the caller (set_option "fb_unchanged"): the next call's fb equals the previous call's
   int64_t launches;
   int conv_engine;
   unsigned long long* tc_prof;   // tuning aid (howl_b200_debug_stream_profile): device buffer [sm_count][16] or null

@@ -14,24 +14,36 @@
 #include "common.cuh"
 
 #define FE_TILE 27          // frames per CTA (81 = 3 tiles for 1 s clips, 41 = 27 + 14 for 0.5 s)
-#define FE_WARPS 8
+#define FE_WARPS 9          // one frame per warp at a time: 27 = 3 x 9
 #define FE_THREADS (FE_WARPS * 32)
-#define FE_FBC_CAP 1024     // compact filterbank entries kept in shared memory (standard 40-mel bank: 493, VTLP worst ~750)
-#define FE_MAXU 128         // work units of the mel contraction: a filter span, or half of a span longer than 16 bins
-#define FE_LANE_UNITS 8     // units one lane may own
+#define FE_ENT_SMEM 256     // mel entries kept in shared memory (standard 40-mel bank: ~100, 80 mels: ~170); the rest is read from global
 #define FE_LOG_EPS 1e-7f
+
+// Sparse mel contraction, organised by BIN BLOCKS: the FFT below leaves lane L of a warp with the power of the 8 consecutive bins
+// [8 * br5(L), 8 * br5(L) + 8) in registers, so the filterbank is cut into "entries" (block, filter m, the 8 weights fb[8 blk + i][m])
+// for every (block, filter) pair with a non-zero weight.  A lane walks the entries of its block -- 8 FMAs and one shared-memory
+// atomic add per entry -- and bin 256 (Nyquist) has its own (filter, weight) list.  Built on the device from any dense [257, M] bank
+// (VTLP-warped ones included), rebuilt only when the bank changes.
+struct FeEntry {
+  int m;
+  float w[8];
+};
+struct FeBank {
+  int ent_off[33];          // entries of block blk: [ent_off[blk], ent_off[blk + 1])
+  int ny_count;             // filters with a non-zero Nyquist weight
+  int ny_m[HOWL_MAX_MELS];
+  float ny_w[HOWL_MAX_MELS];
+};
+#define FE_ENT_WORDS 9
 
 struct FeParams {
   const float* pcm;
-  const float* fb;        // dense [257, M] (global) -- only used beyond FE_FBC_CAP
-  const float* fbc;       // compact non-zero spans
-  const int* fb_lo;       // [M]
-  const int* fb_hi;       // [M]
-  const int* fb_off;      // [M + 1]
-  const int* mel_plan;    // balanced work plan built by fb_compact_kernel (layout: FePlan)
+  const FeBank* bank;
+  const float* ent;       // [n_entries][9] words: m (as int bits), w[8]
   const float* window;
-  const float2* tw256;
-  const float2* tw512;
+  const float2* tw_lane;  // [32][8]: W256^(L * m2), m2 = 0..7
+  const float2* tw_stage; // [32][4]: the cross-lane stage twiddles of lane L (spans 16, 8, 4, 2)
+  const float2* w512_lane;// [32][8]: W512^(m2 + 8 * br5(L))
   const int32_t* rects;
   float* out;
   int64_t B, T;
@@ -41,115 +53,61 @@ struct FeParams {
   int use_tma;
 };
 
-// Balanced plan of the sparse mel contraction.  A unit = bins [lo, hi) of one filter (spans longer than 16 bins are cut
-// in two); units are dealt to the 32 lanes longest-first onto the least loaded lane, so a frame costs ~nnz/32 + a few
-// iterations per lane instead of the longest span plus the tail round.
-struct FePlan {
-  int n_units;
-  int u_lo[FE_MAXU], u_hi[FE_MAXU], u_off[FE_MAXU];     // bin range and offset of the unit's first weight in fbc
-  int mel_unit[HOWL_MAX_MELS][2];                       // units of every filter (-1 = none)
-  int lane_n[32];
-  int lane_unit[32][FE_LANE_UNITS];
-};
-
 // ---------------------------------------------------------------------------------------------
-// compact filterbank: [lo, hi) non-zero span per column + prefix offsets.  One block, M threads.
+// filterbank -> block entries.  One CTA; thread t scans the (block, filter) pairs t, t + 1024, ...
 // ---------------------------------------------------------------------------------------------
-__global__ void fb_compact_kernel(const float* __restrict__ fb, int M, int* __restrict__ lo, int* __restrict__ hi,
-                                  int* __restrict__ off, float* __restrict__ fbc, FePlan* __restrict__ plan) {
-  extern __shared__ float s_fb[];              // the whole [257][M] bank, staged once with coalesced loads
-  __shared__ int s_len[HOWL_MAX_MELS];
-  __shared__ int s_lo2[HOWL_MAX_MELS];
-  for (int i = threadIdx.x; i < HOWL_NFREQ * M; i += blockDim.x) s_fb[i] = fb[i];
+__global__ void __launch_bounds__(1024) fb_compact_kernel(const float* __restrict__ fb, int M, FeBank* __restrict__ bank,
+                                                          float* __restrict__ ent) {
+  __shared__ int s_cnt[33];
+  __shared__ int s_off[34];
+  const int tid = threadIdx.x;
+  if (tid < 33) s_cnt[tid] = 0;
   __syncthreads();
-  __shared__ int s_off[HOWL_MAX_MELS + 1];
-  const int m = threadIdx.x;
-  int l = 0, h = 0;
-  if (m < M) {
-    l = HOWL_NFREQ;
-    for (int j = 0; j < HOWL_NFREQ; ++j) {
-      if (s_fb[j * M + m] != 0.f) {
-        if (j < l) l = j;
-        h = j + 1;
-      }
-    }
-    if (h == 0) l = 0;
-    lo[m] = l;
-    hi[m] = h;
-    s_len[m] = h - l;
-    s_lo2[m] = l;
+  const int pairs = 32 * M;
+  // pass 1: count the non-empty pairs of every block
+  for (int pidx = tid; pidx < pairs; pidx += blockDim.x) {
+    const int blk = pidx / M, m = pidx - blk * M;
+    bool nz = false;
+    for (int i = 0; i < 8; ++i) nz |= fb[(8 * blk + i) * M + m] != 0.f;
+    if (nz) atomicAdd(&s_cnt[blk], 1);
   }
   __syncthreads();
-  if (m == 0) {
+  if (tid == 0) {
     int acc = 0;
-    for (int i = 0; i < M; ++i) {
-      s_off[i] = acc;
-      acc += s_len[i];
+    for (int blk = 0; blk < 32; ++blk) {
+      s_off[blk] = acc;
+      acc += s_cnt[blk];
     }
-    s_off[M] = acc;
-  }
-  __syncthreads();
-  if (m < M) {
-    off[m] = s_off[m];
-    for (int j = l; j < h; ++j) fbc[s_off[m] + (j - l)] = s_fb[j * M + m];
-  }
-  if (m == 0) off[M] = s_off[M];
-  __syncthreads();
-  __shared__ FePlan s_plan;      // planned in shared memory (no global-latency chain), copied out by all
-  __shared__ short s_order[FE_MAXU];
-  __shared__ short s_cnt[HOWL_NFREQ + 2];
-  if (m == 0) {   // tiny serial planner (<= 128 units, 32 lanes)
-    FePlan* plan = &s_plan;
+    s_off[32] = acc;
+    for (int blk = 0; blk <= 32; ++blk) bank->ent_off[blk] = s_off[blk];
     int n = 0;
-    for (int i = 0; i < M; ++i) {
-      const int l = s_lo2[i], h = s_lo2[i] + s_len[i], len = s_len[i];
-      plan->mel_unit[i][0] = plan->mel_unit[i][1] = -1;
-      if (len <= 0) continue;
-      const int cut = (len > 16 && n + 2 <= FE_MAXU) ? l + len / 2 : h;
-      plan->u_lo[n] = l; plan->u_hi[n] = cut; plan->u_off[n] = s_off[i];
-      plan->mel_unit[i][0] = n++;
-      if (cut < h) {
-        plan->u_lo[n] = cut; plan->u_hi[n] = h; plan->u_off[n] = s_off[i] + (cut - l);
-        plan->mel_unit[i][1] = n++;
+    for (int m = 0; m < M; ++m) {
+      const float w = fb[256 * M + m];
+      if (w != 0.f) {
+        bank->ny_m[n] = m;
+        bank->ny_w[n] = w;
+        ++n;
       }
     }
-    plan->n_units = n;
-    // longest-first order by a counting sort on the span length (<= 257)
-    for (int i = 0; i < HOWL_NFREQ + 2; ++i) s_cnt[i] = 0;
-    for (int i = 0; i < n; ++i) s_cnt[plan->u_hi[i] - plan->u_lo[i]]++;
-    {
-      int pos = 0;
-      for (int len = HOWL_NFREQ + 1; len >= 0; --len) {
-        const int c = s_cnt[len];
-        s_cnt[len] = (short)pos;
-        pos += c;
-      }
-    }
-    for (int i = 0; i < n; ++i) s_order[s_cnt[plan->u_hi[i] - plan->u_lo[i]]++] = (short)i;
+    bank->ny_count = n;
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    // greedy onto the least loaded lane (ties: lowest lane; lanes holding FE_LANE_UNITS units are closed): warp 0, lane i
-    // keeps the load of plan lane i in a register, one warp-min per unit
-    const int lane = threadIdx.x, n = s_plan.n_units;
-    int my_load = 0, my_n = 0;
-    for (int it = 0; it < n; ++it) {
-      const int best = s_order[it];
-      const int blen = s_plan.u_hi[best] - s_plan.u_lo[best];
-      const unsigned key = (my_n < FE_LANE_UNITS) ? (unsigned)my_load * 32u + (unsigned)lane : 0xFFFFFFFFu;
-      const unsigned sel = __reduce_min_sync(0xffffffffu, key) & 31u;
-      if ((unsigned)lane == sel) {
-        s_plan.lane_unit[lane][my_n++] = best;
-        my_load += blen + 2;
+  // pass 2: one thread per block writes its entries in filter order (deterministic layout)
+  if (tid < 32) {
+    const int blk = tid;
+    int e = s_off[blk];
+    for (int m = 0; m < M; ++m) {
+      float w[8];
+      bool nz = false;
+      for (int i = 0; i < 8; ++i) {
+        w[i] = fb[(8 * blk + i) * M + m];
+        nz |= w[i] != 0.f;
       }
+      if (!nz) continue;
+      ent[e * FE_ENT_WORDS] = __int_as_float(m);
+      for (int i = 0; i < 8; ++i) ent[e * FE_ENT_WORDS + 1 + i] = w[i];
+      ++e;
     }
-    s_plan.lane_n[lane] = my_n;
-  }
-  __syncthreads();
-  {
-    const int* src = reinterpret_cast<const int*>(&s_plan);
-    int* dst = reinterpret_cast<int*>(plan);
-    for (int i = threadIdx.x; i < (int)(sizeof(FePlan) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
   }
 }
 
@@ -187,52 +145,64 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 
-// one radix-4 Stockham pass over 256 complex points held in the warp's scratch (2 butterflies per lane)
-template <int NS>
-__device__ __forceinline__ void fft256_pass(const float2* __restrict__ in, float2* __restrict__ out, int lane,
-                                            const float2* __restrict__ tw) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int j = lane + 32 * h;
-    const int k = j & (NS - 1);
-    float2 v0 = in[j], v1 = in[j + 64], v2 = in[j + 128], v3 = in[j + 192];
-    if (NS > 1) {
-      const int m = k * (64 / NS);
-      v1 = cmul(v1, tw[m]);
-      v2 = cmul(v2, tw[2 * m]);
-      v3 = cmul(v3, tw[3 * m]);
-    }
-    const float2 t0 = make_float2(v0.x + v2.x, v0.y + v2.y);
-    const float2 t1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-    const float2 t2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-    const float2 t3 = make_float2(v1.y - v3.y, -(v1.x - v3.x));  // (v1 - v3) * (-i)
-    const int j0 = ((j - k) << 2) + k;
-    out[j0] = make_float2(t0.x + t2.x, t0.y + t2.y);
-    out[j0 + NS] = make_float2(t1.x + t3.x, t1.y + t3.y);
-    out[j0 + 2 * NS] = make_float2(t0.x - t2.x, t0.y - t2.y);
-    out[j0 + 3 * NS] = make_float2(t1.x - t3.x, t1.y - t3.y);
+// 256-point complex FFT of one frame held by a warp: lane L enters with z[L + 32 k] in v[k] and leaves with X[m2 + 8 * br5(L)]
+// in v[m2] (br5 = 5-bit reversal).  N = 8 x 32:  X[m2 + 8 m1] = sum_n1 W256^(n1 m2) W32^(n1 m1) [ sum_n2 z[n1 + 32 n2] W8^(n2 m2) ]
+//   (1) the bracket: an 8-point DFT over the lane's own registers;
+//   (2) the twiddles W256^(L m2) (per-lane constants tw[m2]);
+//   (3) for every register a 32-point DFT ACROSS the lanes: five radix-2 decimation-in-frequency stages whose butterflies exchange
+//       partners with __shfl_xor (span 16, 8, 4, 2, 1); the upper lane of a pair keeps (x_lo - x_hi) * W, the lower x_lo + x_hi.
+__device__ __forceinline__ void fft256_warp(float2* v, const float2* tw, const float2* st, int lane) {
+  const float c8 = 0.70710678118654752440f;
+  {
+    // ---- (1) 8-point DIF in registers; outputs renamed to natural order
+    float2 u0 = cadd(v[0], v[4]), u1 = cadd(v[1], v[5]), u2 = cadd(v[2], v[6]), u3 = cadd(v[3], v[7]);
+    float2 d0 = csub(v[0], v[4]), d1 = csub(v[1], v[5]), d2 = csub(v[2], v[6]), d3 = csub(v[3], v[7]);
+    d1 = make_float2(c8 * (d1.x + d1.y), c8 * (d1.y - d1.x));        // * W8^1 = (c, -c)
+    d2 = cmul_mi(d2);                                                // * W8^2 = -i
+    d3 = make_float2(c8 * (d3.y - d3.x), -c8 * (d3.x + d3.y));       // * W8^3 = (-c, -c)
+    const float2 uu0 = cadd(u0, u2), uu1 = cadd(u1, u3), uv0 = csub(u0, u2), uv1 = cmul_mi(csub(u1, u3));
+    const float2 vu0 = cadd(d0, d2), vu1 = cadd(d1, d3), vv0 = csub(d0, d2), vv1 = cmul_mi(csub(d1, d3));
+    v[0] = cadd(uu0, uu1); v[4] = csub(uu0, uu1);
+    v[2] = cadd(uv0, uv1); v[6] = csub(uv0, uv1);
+    v[1] = cadd(vu0, vu1); v[5] = csub(vu0, vu1);
+    v[3] = cadd(vv0, vv1); v[7] = csub(vv0, vv1);
   }
-  __syncwarp();
+  // ---- (2)
+#pragma unroll
+  for (int m2 = 1; m2 < 8; ++m2) v[m2] = cmul(v[m2], tw[m2]);
+  // ---- (3)
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int h = 16 >> s;
+    const bool upper = (lane & h) != 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float ox = __shfl_xor_sync(0xffffffffu, v[r].x, h), oy = __shfl_xor_sync(0xffffffffu, v[r].y, h);
+      float2 t = upper ? make_float2(ox - v[r].x, oy - v[r].y) : make_float2(v[r].x + ox, v[r].y + oy);
+      if (s < 3) t = cmul(t, st[s]);              // st[s] = 1 in the lower lane
+      else if (s == 3 && upper && (lane & 1)) t = cmul_mi(t);      // W4^1 = -i
+      v[r] = t;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FeParams p) {
+__global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // carve-up (all offsets multiples of 16 bytes)
   const int span_cap = (FE_TILE - 1) * p.hop + HOWL_NFFT + 8;
   float* s_pcm = reinterpret_cast<float*>(smem_raw);
   float* s_win = s_pcm + ((span_cap + 3) & ~3);
-  float2* s_tw256 = reinterpret_cast<float2*>(s_win + HOWL_NFFT);
-  float2* s_tw512 = s_tw256 + 256;
-  float* s_fbc = reinterpret_cast<float*>(s_tw512 + 258);
-  float2* s_scratch = reinterpret_cast<float2*>(s_fbc + FE_FBC_CAP);        // [FE_WARPS][2][256]
-  float* s_res = reinterpret_cast<float*>(s_scratch + FE_WARPS * 512);      // [FE_TILE][M]
-  int* s_lo = reinterpret_cast<int*>(s_res + FE_TILE * p.M);
-  int* s_hi = s_lo + HOWL_MAX_MELS;
-  int* s_off = s_hi + HOWL_MAX_MELS;
-  float* s_upart = reinterpret_cast<float*>(s_off + HOWL_MAX_MELS + 4);     // [FE_WARPS][FE_MAXU] unit partial sums
+  float2* s_w512 = reinterpret_cast<float2*>(s_win + HOWL_NFFT);            // [32 lanes][8]
+  float* s_ent = reinterpret_cast<float*>(s_w512 + 256);                    // [FE_ENT_SMEM][9]
+  float* s_mel = s_ent + FE_ENT_SMEM * FE_ENT_WORDS;                        // [FE_WARPS][M]
+  float* s_res = s_mel + FE_WARPS * ((p.M + 3) & ~3);                       // [FE_TILE][M]
   __shared__ __align__(8) uint64_t s_bar;
-  const FePlan* plan = reinterpret_cast<const FePlan*>(p.mel_plan);
+  __shared__ int s_off[33];
+  __shared__ int s_ny;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = blockIdx.y;
@@ -261,23 +231,25 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FeParams p) 
   }
   // tables (overlaps the bulk copy)
   for (int i = tid; i < HOWL_NFFT; i += FE_THREADS) s_win[i] = __ldg(p.window + i);
-  for (int i = tid; i < 256; i += FE_THREADS) s_tw256[i] = __ldg(p.tw256 + i);
-  for (int i = tid; i < HOWL_NFREQ; i += FE_THREADS) s_tw512[i] = __ldg(p.tw512 + i);
-  for (int i = tid; i < p.M; i += FE_THREADS) {
-    s_lo[i] = __ldg(p.fb_lo + i);
-    s_hi[i] = __ldg(p.fb_hi + i);
-  }
-  for (int i = tid; i <= p.M; i += FE_THREADS) s_off[i] = __ldg(p.fb_off + i);
+  for (int i = tid; i < 256; i += FE_THREADS) s_w512[i] = __ldg(p.w512_lane + i);
+  if (tid < 33) s_off[tid] = p.bank->ent_off[tid];
+  if (tid == 33) s_ny = p.bank->ny_count;
   {
-    const int total = min(__ldg(p.fb_off + p.M), FE_FBC_CAP);
-    for (int i = tid; i < total; i += FE_THREADS) s_fbc[i] = __ldg(p.fbc + i);
+    const int total = min(p.bank->ent_off[32], FE_ENT_SMEM) * FE_ENT_WORDS;
+    for (int i = tid; i < total; i += FE_THREADS) s_ent[i] = __ldg(p.ent + i);
   }
+  const int Mp = (p.M + 3) & ~3;
+  for (int i = tid; i < FE_WARPS * Mp; i += FE_THREADS) s_mel[i] = 0.f;
+  // per-lane FFT constants
+  float2 tw[8], st[3];
+#pragma unroll
+  for (int m2 = 0; m2 < 8; ++m2) tw[m2] = __ldg(p.tw_lane + lane * 8 + m2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) st[i] = __ldg(p.tw_stage + lane * 4 + i);
+  const int blk = (int)(__brev((unsigned)lane) >> 27);               // this lane's bin block = br5(lane)
+  const int src0 = (int)(__brev((unsigned)((32 - blk) & 31)) >> 27); // lane holding X[256 - 8 * blk] in register 0
   __syncthreads();
   if (p.use_tma) mbar_wait(&s_bar, 0);
-
-  float2* bufA = s_scratch + warp * 512;
-  float2* bufB = bufA + 256;
-  float* pw = reinterpret_cast<float*>(bufB);  // power spectrum [257] re-uses bufB after the FFT
 
   int rf0 = 0, rfl = 0, rt0 = 0, rtl = 0;
   const bool masked = (p.rects != nullptr) && !(p.flags & HOWL_FE_STACKED);
@@ -288,6 +260,8 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FeParams p) 
     rtl = p.rects[b * 4 + 3];
   }
   const bool do_zmuv = (p.flags & HOWL_FE_ZMUV) && !(p.flags & HOWL_FE_STACKED);
+  float* mel = s_mel + warp * Mp;
+  const int e_begin = s_off[blk], e_end = s_off[blk + 1];
 
   for (int fi = warp; fi < nfr; fi += FE_WARPS) {
     const int f = f0 + fi;
@@ -295,81 +269,64 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(const FeParams p) 
     const bool interior = (start >= 0) && (start + HOWL_NFFT <= T);   // no reflection: plain 64-bit vector loads
     const float2* fr2 = reinterpret_cast<const float2*>(s_pcm + (interior ? (int)(start - lo) : 0));
     const float2* win2 = reinterpret_cast<const float2*>(s_win);
-    // ---- pass 0 (NS = 1, no twiddles) straight from the staged PCM: z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1]
+    // ---- z[n] = x[2n] w[2n] + i x[2n+1] w[2n+1],  n = lane + 32 k
+    float2 v[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = lane + 32 * h;
-      float2 v[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int n = j + 64 * r;
-        if (interior) {
-          const float2 x = fr2[n], w = win2[n];
-          v[r] = make_float2(x.x * w.x, x.y * w.y);
-        } else {
-          int64_t sa = start + 2 * n, sb = sa + 1;
-          if (sa < 0) sa = -sa;
-          if (sb < 0) sb = -sb;
-          if (sa >= T) sa = 2 * (T - 1) - sa;
-          if (sb >= T) sb = 2 * (T - 1) - sb;
-          v[r] = make_float2(s_pcm[sa - lo] * s_win[2 * n], s_pcm[sb - lo] * s_win[2 * n + 1]);
-        }
-      }
-      const float2 t0 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
-      const float2 t1 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-      const float2 t2 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
-      const float2 t3 = make_float2(v[1].y - v[3].y, -(v[1].x - v[3].x));
-      const int j0 = j << 2;
-      bufB[j0] = make_float2(t0.x + t2.x, t0.y + t2.y);
-      bufB[j0 + 1] = make_float2(t1.x + t3.x, t1.y + t3.y);
-      bufB[j0 + 2] = make_float2(t0.x - t2.x, t0.y - t2.y);
-      bufB[j0 + 3] = make_float2(t1.x - t3.x, t1.y - t3.y);
-    }
-    __syncwarp();
-    fft256_pass<4>(bufB, bufA, lane, s_tw256);
-    fft256_pass<16>(bufA, bufB, lane, s_tw256);
-    fft256_pass<64>(bufB, bufA, lane, s_tw256);  // Z in bufA, natural order
-    // ---- real-FFT post-processing + power: X[k] = E[k] + W512^k O[k], k = 0..256
-#pragma unroll
-    for (int h = 0; h < 9; ++h) {
-      const int k = lane + 32 * h;
-      if (k <= 256) {
-        const float2 zk = bufA[k & 255];
-        float2 zc = bufA[(256 - k) & 255];
-        zc.y = -zc.y;
-        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-        const float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
-        const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);  // d / (2i)
-        const float2 wo = cmul(s_tw512[k], o);
-        const float xr = e.x + wo.x, xi = e.y + wo.y;
-        pw[k] = xr * xr + xi * xi;
+    for (int k = 0; k < 8; ++k) {
+      const int n = lane + 32 * k;
+      const float2 w = win2[n];
+      if (interior) {
+        const float2 x = fr2[n];
+        v[k] = make_float2(x.x * w.x, x.y * w.y);
+      } else {
+        int64_t sa = start + 2 * n, sb = sa + 1;
+        if (sa < 0) sa = -sa;
+        if (sb < 0) sb = -sb;
+        if (sa >= T) sa = 2 * (T - 1) - sa;
+        if (sb >= T) sb = 2 * (T - 1) - sb;
+        v[k] = make_float2(s_pcm[sa - lo] * w.x, s_pcm[sb - lo] * w.y);
       }
     }
-    __syncwarp();
-    // ---- sparse mel contraction (balanced units) + log + zmuv + mask
-    float* up = s_upart + warp * FE_MAXU;
-    {
-      const int nu = plan->lane_n[lane];
-      for (int q = 0; q < nu; ++q) {
-        const int u = plan->lane_unit[lane][q];
-        const int jl = plan->u_lo[u], jh = plan->u_hi[u], off = plan->u_off[u];
-        float acc = 0.f;
-        for (int j = jl; j < jh; ++j) {
-          const int e = off + (j - jl);
-          const float w = (e < FE_FBC_CAP) ? s_fbc[e] : __ldg(p.fbc + e);
-          acc = fmaf(pw[j], w, acc);
-        }
-        up[u] = acc;
+    fft256_warp(v, tw, st, lane);
+    // ---- real-FFT post-processing + power: X[m] = E + W512^m O with E = (Z[m] + conj Z[256-m]) / 2, O = (Z[m] - conj Z[256-m]) / 2i;
+    //      Z[256 - m] for m = m2 + 8 blk sits in register 8 - m2 of lane 31 - L (m2 > 0) or register 0 of lane src0 (m2 = 0)
+    float pw[8];
+    float nyq = 0.f;
+#pragma unroll
+    for (int m2 = 0; m2 < 8; ++m2) {
+      const int r = (8 - m2) & 7;
+      const int from = m2 == 0 ? src0 : (31 - lane);
+      float2 zc = make_float2(__shfl_sync(0xffffffffu, v[r].x, from), -__shfl_sync(0xffffffffu, v[r].y, from));
+      const float2 zk = v[m2];
+      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+      const float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
+      const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);  // d / (2i)
+      const float2 wo = cmul(s_w512[lane * 8 + m2], o);
+      const float xr = e.x + wo.x, xi = e.y + wo.y;
+      pw[m2] = xr * xr + xi * xi;
+      if (m2 == 0) {                     // bin 256 from Z[0] (lane 0 only uses it): X[256] = Re Z[0] - Im Z[0]
+        const float t = zk.x - zk.y;
+        nyq = t * t;
       }
+    }
+    // ---- sparse mel contraction: this lane's block entries, partial sums combined in shared memory
+    for (int eidx = e_begin; eidx < e_end; ++eidx) {
+      const float* ep = (eidx < FE_ENT_SMEM) ? s_ent + eidx * FE_ENT_WORDS : p.ent + (size_t)eidx * FE_ENT_WORDS;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(pw[i], ep[1 + i], acc);
+      atomicAdd(mel + __float_as_int(ep[0]), acc);
+    }
+    if (lane == 0) {
+      for (int i = 0; i < s_ny; ++i) atomicAdd(mel + p.bank->ny_m[i], nyq * p.bank->ny_w[i]);
     }
     __syncwarp();
     for (int m = lane; m < p.M; m += 32) {
-      const int u0 = plan->mel_unit[m][0], u1 = plan->mel_unit[m][1];
-      float acc = (u0 >= 0 ? up[u0] : 0.f) + (u1 >= 0 ? up[u1] : 0.f);
-      float v = logf(acc + FE_LOG_EPS);
-      if (do_zmuv) v = __fdiv_rn(v - p.zmean, p.zstd);
-      if (masked && ((m >= rf0 && m < rf0 + rfl) || (f >= rt0 && f < rt0 + rtl))) v = 0.f;
-      s_res[fi * p.M + m] = v;
+      float val = logf(mel[m] + FE_LOG_EPS);
+      mel[m] = 0.f;
+      if (do_zmuv) val = __fdiv_rn(val - p.zmean, p.zstd);
+      if (masked && ((m >= rf0 && m < rf0 + rfl) || (f >= rt0 && f < rt0 + rtl))) val = 0.f;
+      s_res[fi * p.M + m] = val;
     }
     __syncwarp();
   }
@@ -482,14 +439,10 @@ __global__ void sum_sumsq_kernel(const float* __restrict__ x, int64_t n, double*
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int fe_scratch(howl_ctx_t* ctx) {
-  if (!ctx->fb_lo) {
-    HOWL_CUDA(ctx, cudaMalloc(&ctx->fb_lo, sizeof(int) * HOWL_MAX_MELS));
-    HOWL_CUDA(ctx, cudaMalloc(&ctx->fb_hi, sizeof(int) * HOWL_MAX_MELS));
-    HOWL_CUDA(ctx, cudaMalloc(&ctx->fb_off, sizeof(int) * (HOWL_MAX_MELS + 1)));
-    HOWL_CUDA(ctx, cudaMalloc(&ctx->fbc, sizeof(float) * HOWL_NFREQ * HOWL_MAX_MELS));
-    HOWL_CUDA(ctx, cudaMalloc(&ctx->mel_plan, sizeof(FePlan)));
-  }
+// scratch of the block-entry filterbank, allocated once by howl_b200_create (no allocation on the call path)
+int howl_fe_alloc_scratch(howl_ctx_t* ctx) {
+  if (cudaMalloc(&ctx->fe_bank, sizeof(FeBank)) != cudaSuccess) return HOWL_E_CUDA;
+  if (cudaMalloc(&ctx->fe_ent, sizeof(float) * FE_ENT_WORDS * 32 * HOWL_MAX_MELS) != cudaSuccess) return HOWL_E_CUDA;
   return HOWL_OK;
 }
 
@@ -498,12 +451,10 @@ size_t howl_fe_smem_bytes(int hop, int M) {
   size_t b = 0;
   b += sizeof(float) * ((span_cap + 3) & ~3);
   b += sizeof(float) * HOWL_NFFT;
-  b += sizeof(float2) * (256 + 258);
-  b += sizeof(float) * FE_FBC_CAP;
-  b += sizeof(float2) * FE_WARPS * 512;
+  b += sizeof(float2) * 256;
+  b += sizeof(float) * FE_ENT_SMEM * FE_ENT_WORDS;
+  b += sizeof(float) * FE_WARPS * ((M + 3) & ~3);
   b += sizeof(float) * FE_TILE * M;
-  b += sizeof(int) * (3 * HOWL_MAX_MELS + 4);
-  b += sizeof(float) * FE_WARPS * FE_MAXU;
   return howl_align_up(b, 16);
 }
 
@@ -525,17 +476,18 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
   const int64_t F64 = 1 + T / hop;
   HOWL_REQUIRE(ctx, F64 <= 0x7fffffff / HOWL_MAX_MELS, HOWL_E_UNSUPPORTED, "frontend_fwd: clip too long");
   const int F = (int)F64;
-  int rc = fe_scratch(ctx);
-  if (rc) return rc;
-  const size_t fbsm = sizeof(float) * HOWL_NFREQ * M;
-  HOWL_CUDA(ctx, cudaFuncSetAttribute(fb_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fbsm));
-  fb_compact_kernel<<<1, 512, fbsm, st>>>(fb, M, ctx->fb_lo, ctx->fb_hi, ctx->fb_off, ctx->fbc,
-                                                 reinterpret_cast<FePlan*>(ctx->mel_plan));
-  HOWL_LAUNCHED(ctx, "fb_compact");
+  // the compact bank + balanced plan are rebuilt unless the caller promised (one-shot option "fb_unchanged") that this call's
+  // filterbank is the previous call's -- the standard bank is constant between VTLP draws
+  if (!(ctx->fb_plan_valid && ctx->fb_same_next)) {
+    fb_compact_kernel<<<1, 1024, 0, st>>>(fb, M, reinterpret_cast<FeBank*>(ctx->fe_bank), ctx->fe_ent);
+    HOWL_LAUNCHED(ctx, "fb_compact");
+    ctx->fb_plan_valid = 1;
+  }
+  ctx->fb_same_next = 0;
 
   FeParams p;
-  p.pcm = pcm; p.fb = fb; p.fbc = ctx->fbc; p.fb_lo = ctx->fb_lo; p.fb_hi = ctx->fb_hi; p.fb_off = ctx->fb_off; p.mel_plan = ctx->mel_plan;
-  p.window = ctx->d_window; p.tw256 = ctx->d_tw256; p.tw512 = ctx->d_tw512;
+  p.pcm = pcm; p.bank = reinterpret_cast<const FeBank*>(ctx->fe_bank); p.ent = ctx->fe_ent;
+  p.window = ctx->d_window; p.tw_lane = ctx->d_tw_lane; p.tw_stage = ctx->d_tw_stage; p.w512_lane = ctx->d_w512_lane;
   p.rects = rects; p.out = out; p.B = B; p.T = T; p.F = F; p.M = M; p.hop = hop;
   p.zmean = zmuv_mean; p.zstd = zmuv_std; p.flags = flags;
   p.use_tma = ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((hop & 3) == 0);

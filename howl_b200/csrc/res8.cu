@@ -33,6 +33,7 @@ struct R8Ws {
   float* dh;           // [B,45]
   float* dlogits;      // [B,L]
   float* logits;       // [B,L]  copy of the forward's logits for the backward
+  uint16_t* bits0;     // [B,45,H,10] the 12 ReLU decisions of every conv0 pooling window
   float* a0;
   float* u[R8_LAYERS];
   float* g;
@@ -69,6 +70,7 @@ static R8Ws r8_carve(void* base, int64_t B, int H, int L) {
   w.dlogits = (float*)take(sizeof(float) * B * L);
   w.logits = (float*)take(sizeof(float) * B * L);
   const size_t n = sizeof(float) * (size_t)B * R8_C * H * R8_W;
+  w.bits0 = (uint16_t*)take(n / 2);
   w.a0 = (float*)take(n);
   for (int i = 0; i < R8_LAYERS; ++i) w.u[i] = (float*)take(n);
   w.g = (float*)take(n);
@@ -112,7 +114,8 @@ __device__ __forceinline__ void c0_stage_tile(float* s_x, const float* __restric
 
 __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __restrict__ feats,
                                                                  const float* __restrict__ w0, float* __restrict__ a0,
-                                                                 uint4* __restrict__ a0_op, int Rx, int F, int H) {
+                                                                 uint4* __restrict__ a0_op, uint16_t* __restrict__ bits0, int Rx, int F,
+                                                                 int H) {
   extern __shared__ __align__(16) float smem[];
   const int rows = 3 * H + 2;
   float* s_x = smem;
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
 #pragma unroll
       for (int k = 0; k < 9; ++k) wk[k] = s_w[oc * 9 + k];
       float sum = 0.f;
+      uint32_t mb = 0;
 #pragma unroll
       for (int py = 0; py < 3; ++py)
 #pragma unroll
@@ -167,8 +171,10 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) pre = fmaf(wk[ky * 3 + kx], patch[py + ky][px + kx], pre);
+          if (pre > 0.f) mb |= 1u << (py * 4 + px);
           sum += fmaxf(pre, 0.f);
         }
+      if (bits0) bits0[(b * R8_C + oc) * (int64_t)HW + pp] = (uint16_t)mb;   // ReLU decisions of the pooling window, for conv0_bwd
       const float o = __fdiv_rn(sum, 12.f);
       if (dst) dst[(int64_t)oc * HW] = o;
       ov[oc & 7] = o;
@@ -183,47 +189,98 @@ __global__ void __launch_bounds__(C0_THREADS) conv0_pool_kernel(const float* __r
   }
 }
 
-// backward of conv0: dW0[oc][k] = sum_{b,pos} relu'(pre[oc,pos]) * G[oc, pos/pool] / 12 * x[pos + k]; pre is recomputed
-// with the same FMA order as the forward.  Persistent CTAs; thread = (pixel group pg, output channel oc): the nine
-// tap accumulators of its channel stay in registers across all pixels and utterances (no per-channel reductions in the
-// loop), the 5x6 input patch of a pooled pixel is a shared-memory broadcast, G = ga (+ gb) is staged per utterance.
-#define C0B_GROUPS 6
+// backward of conv0: dW0[oc][k] = sum_{b,pp} G[oc,pp] / 12 * sum_{t in 3x4 window} relu'(pre[oc,pp,t]) * x[pos(pp,t) + k].  The ReLU
+// decisions are the 12 bits per (oc, pooled pixel) that conv0_pool stored, so nothing is recomputed: per (oc, pp) the inner sum
+// S[k] costs 108 multiply-adds with the 0/1 mask and the fold into the accumulators 9 more.  Persistent CTAs, one per SM.  The three
+// per-utterance inputs (G planes, bits, features) are contiguous in HBM and arrive by TMA bulk copies into a two-deep ring, one
+// utterance ahead of the arithmetic (the kernel used to spend most of its time in the staging loop's load latency); thread =
+// (pixel group pg, output channel oc): the nine tap accumulators of its channel stay in registers across all pixels and utterances,
+// the 5x6 input patch of a pooled pixel is a shared-memory broadcast.
+#define C0B_GROUPS 12
 #define C0B_THREADS (C0B_GROUPS * 48)
-__global__ void __launch_bounds__(C0B_THREADS, 3) conv0_bwd_kernel(const float* __restrict__ feats,
-                                                                 const float* __restrict__ w0,
-                                                                 const float* __restrict__ ga,
-                                                                 const float* __restrict__ gb, float* __restrict__ dw0,
-                                                                 int64_t B, int F, int H) {
-  extern __shared__ __align__(16) float smem[];
+struct C0bLayout {
+  uint32_t g_bytes, m_bytes, f_bytes;     // ring slot sizes (16-byte multiples, with slack for the alignment offset)
+  uint32_t off_g, off_m, off_f, off_x, off_acc, total;
+};
+__host__ __device__ static inline C0bLayout c0b_layout(int F, int H, int slots) {
+  C0bLayout L;
+  const uint32_t HW = (uint32_t)H * R8_W;
+  L.g_bytes = (R8_C * HW * 4 + 16 + 15) & ~15u;
+  L.m_bytes = (R8_C * HW * 2 + 16 + 15) & ~15u;
+  L.f_bytes = ((uint32_t)F * R8_MELS * 4 + 15) & ~15u;
+  L.off_g = 0;
+  L.off_m = L.off_g + slots * L.g_bytes;
+  L.off_f = L.off_m + slots * L.m_bytes;
+  L.off_x = L.off_f + slots * L.f_bytes;
+  L.off_acc = L.off_x + (uint32_t)(3 * H + 2) * C0_STRIDE * 4;
+  L.total = L.off_acc + R8_C * 9 * 4;
+  return L;
+}
+
+__global__ void __launch_bounds__(C0B_THREADS, 1) conv0_bwd_kernel(const float* __restrict__ feats,
+                                                                 const uint16_t* __restrict__ bits0,
+                                                                 const float* __restrict__ g0, float* __restrict__ dw0,
+                                                                 int64_t B, int F, int H, int slots) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[2];
+  const C0bLayout L = c0b_layout(F, H, slots);
   const int rows = 3 * H + 2, HW = H * R8_W;
-  float* s_x = smem;                          // [(3H+2)][44]  feature tile with halo
-  float* s_g = s_x + rows * C0_STRIDE;        // [45][HW + 1]  G / 12 for this utterance (padded row: bank spread)
-  float* s_acc = s_g + R8_C * (HW + 1);       // [45][9]
+  float* s_x = reinterpret_cast<float*>(smem_raw + L.off_x);       // [(3H+2)][44]  feature tile with a zero halo
+  float* s_acc = reinterpret_cast<float*>(smem_raw + L.off_acc);   // [45][9]
   const int tid = threadIdx.x;
   const int pg = tid / 48, oc = tid - pg * 48;
   const bool active = oc < R8_C;
-  float wk[9], acc[9];
+  float acc[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    wk[k] = active ? __ldg(w0 + oc * 9 + k) : 0.f;
-    acc[k] = 0.f;
-  }
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
   for (int i = tid; i < R8_C * 9; i += C0B_THREADS) s_acc[i] = 0.f;
-  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-    __syncthreads();
-    c0_stage_tile(s_x, feats + b * (int64_t)F * R8_MELS, F, rows, tid, C0B_THREADS);
-    for (int i = tid; i < R8_C * HW; i += C0B_THREADS) {
-      const int64_t idx = b * (int64_t)R8_C * HW + i;
-      float gv = ga[idx];
-      if (gb) gv += gb[idx];
-      const int c = i / HW;
-      s_g[c * (HW + 1) + (i - c * HW)] = __fdiv_rn(gv, 12.f);
+  for (int i = tid; i < rows * C0_STRIDE; i += C0B_THREADS) s_x[i] = 0.f;      // halo stays zero for good
+  if (tid == 0) {
+    tc::mbar_init(&bar_full[0], 1);
+    tc::mbar_init(&bar_full[1], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t n_local = (B - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  // 16-byte aligned supersets of the utterance's G planes / bits (their per-utterance sizes are not multiples of 16 bytes)
+  auto issue = [&](int64_t k) {
+    const int s = (int)(k % slots);
+    const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
+    const uintptr_t ga = reinterpret_cast<uintptr_t>(g0 + b * (int64_t)R8_C * HW), ga0 = ga & ~(uintptr_t)15;
+    const uintptr_t ma = reinterpret_cast<uintptr_t>(bits0 + b * (int64_t)R8_C * HW), ma0 = ma & ~(uintptr_t)15;
+    const uint32_t gb = (uint32_t)(((ga + (uintptr_t)R8_C * HW * 4 + 15) & ~(uintptr_t)15) - ga0);
+    const uint32_t mb = (uint32_t)(((ma + (uintptr_t)R8_C * HW * 2 + 15) & ~(uintptr_t)15) - ma0);
+    tc::mbar_expect_tx(&bar_full[s], gb + mb + L.f_bytes);
+    tc::tma_bulk_g2s(smem_raw + L.off_g + s * L.g_bytes, reinterpret_cast<const void*>(ga0), gb, &bar_full[s]);
+    tc::tma_bulk_g2s(smem_raw + L.off_m + s * L.m_bytes, reinterpret_cast<const void*>(ma0), mb, &bar_full[s]);
+    tc::tma_bulk_g2s(smem_raw + L.off_f + s * L.f_bytes, feats + b * (int64_t)F * R8_MELS, L.f_bytes, &bar_full[s]);
+  };
+  if (tid == 0 && n_local > 0) issue(0);
+  for (int64_t k = 0; k < n_local; ++k) {
+    const int s = (int)(k % slots);
+    const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
+    // two slots: the other one was released by the barrier that ended iteration k - 1, so the next utterance loads during this one
+    if (slots == 2 && tid == 0 && k + 1 < n_local) issue(k + 1);
+    tc::mbar_wait(&bar_full[s], (uint32_t)((k / slots) & 1));
+    const float* s_f = reinterpret_cast<const float*>(smem_raw + L.off_f + s * L.f_bytes);
+    const float* s_g = reinterpret_cast<const float*>(smem_raw + L.off_g + s * L.g_bytes +
+                                                      (reinterpret_cast<uintptr_t>(g0 + b * (int64_t)R8_C * HW) & 15));
+    const uint16_t* s_m = reinterpret_cast<const uint16_t*>(smem_raw + L.off_m + s * L.m_bytes +
+                                                            (reinterpret_cast<uintptr_t>(bits0 + b * (int64_t)R8_C * HW) & 15));
+    // padded tile s_x[(y + 1) * 44 + (x + 1)] from the raw [F][40] features (rows beyond 3H + 1 are not needed)
+    const int nvalid = min(F, rows - 1);
+    for (int i = tid; i < nvalid * (R8_MELS / 4); i += C0B_THREADS) {
+      const int y = i / (R8_MELS / 4), x4 = i - y * (R8_MELS / 4);
+      const float4 v = reinterpret_cast<const float4*>(s_f + (size_t)y * R8_MELS)[x4];
+      float* d = s_x + (y + 1) * C0_STRIDE + x4 * 4 + 1;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
     __syncthreads();
     if (active) {
       for (int pp = pg; pp < HW; pp += C0B_GROUPS) {
         const int h = pp / R8_W, w = pp - h * R8_W;
-        const float gv = s_g[oc * (HW + 1) + pp];
+        const float gv = s_g[oc * HW + pp];
+        const uint32_t mb = s_m[oc * HW + pp];
         float patch[5][6];
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
@@ -233,28 +290,29 @@ __global__ void __launch_bounds__(C0B_THREADS, 3) conv0_bwd_kernel(const float* 
           patch[r][0] = a.x; patch[r][1] = a.y; patch[r][2] = a.z; patch[r][3] = a.w;
           patch[r][4] = c2.x; patch[r][5] = c2.y;
         }
+        float S[9];
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) S[kk] = 0.f;
 #pragma unroll
         for (int py = 0; py < 3; ++py)
 #pragma unroll
           for (int px = 0; px < 4; ++px) {
-            float pre = 0.f;
+            const float m = ((mb >> (py * 4 + px)) & 1u) ? 1.f : 0.f;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx) pre = fmaf(wk[ky * 3 + kx], patch[py + ky][px + kx], pre);
-            const float gm = pre > 0.f ? gv : 0.f;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(gm, patch[py + ky][px + kx], acc[ky * 3 + kx]);
+              for (int kx = 0; kx < 3; ++kx) S[ky * 3 + kx] = fmaf(m, patch[py + ky][px + kx], S[ky * 3 + kx]);
           }
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) acc[kk] = fmaf(gv, S[kk], acc[kk]);
       }
     }
+    __syncthreads();       // slot s and the tile are free again
+    if (slots == 1 && tid == 0 && k + 1 < n_local) issue(k + 1);      // long clips: one slot, no overlap
   }
-  __syncthreads();
   if (active) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) atomicAdd(&s_acc[oc * 9 + k], acc[k]);
+    for (int k = 0; k < 9; ++k) atomicAdd(&s_acc[oc * 9 + k], acc[k] * (1.f / 12.f));    // the average pooling's 1 / 12
   }
   __syncthreads();
   for (int i = tid; i < R8_C * 9; i += C0B_THREADS) atomicAdd(&dw0[i], s_acc[i]);
@@ -822,7 +880,8 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     // tensor-core engine: a0 exists in operand format only
     conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, use_tc ? nullptr : ws.a0,
-                                                          use_tc ? reinterpret_cast<uint4*>(ws.uop[0]) : nullptr, r8tc_dcop_rows(H), frames, H);
+                                                          use_tc ? reinterpret_cast<uint4*>(ws.uop[0]) : nullptr,
+                                                          train ? ws.bits0 : nullptr, r8tc_dcop_rows(H), frames, H);
     HOWL_LAUNCHED(ctx, "conv0_pool");
   }
   if (train) {
@@ -896,7 +955,6 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int H = frames / 3, HW = H * R8_W, L = num_labels;
-  const float* w0 = params;
   const float* wl = params + R8_C * 9;
   const float* wout = wl + (size_t)R8_LAYERS * R8_KW;
   float* g_w0 = grads;
@@ -975,7 +1033,8 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
         c.dc_outT = ws.dcT;
       } else {
         c.mode = 2;
-        c.out_planar = ws.g;                                // dL/d(a0) through conv1; conv0_bwd adds the residual path
+        c.out_planar = ws.g;                                // dL/d(a0) = conv1 path + residual path (G_2, added in the epilogue)
+        c.gu_in = ws.gu[1];
       }
       rc = r8tc_conv(ctx, st, c);
       if (rc) return rc;
@@ -1038,17 +1097,21 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
       p.aux_mean = ws.mean_rstd + (i - 2) * 2 * R8_C;
       p.aux_rstd = p.aux_mean + R8_C;
     }
+    if (i == 1) p.res = ws.gu[1];      // dL/d(a0) = conv1 path + residual path (G_2), summed here for conv0_bwd
     if (i > 1) conv3x3_kernel<false, 2><<<grid, CV_THREADS, csm, st>>>(p);
     else conv3x3_kernel<false, 0><<<grid, CV_THREADS, csm, st>>>(p);
     HOWL_LAUNCHED(ctx, "conv3x3_dgrad");
   }
   }
   {
-    const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + R8_C * (HW + 1) + R8_C * 9);
+    // G_0 = dL/d(a0): ws.g already holds the sum of the conv1 path and the residual path (the layer-1 data gradient adds gu)
+    const int slots = c0b_layout(frames, H, 2).total <= 227 * 1024 ? 2 : 1;
+    const size_t sm = c0b_layout(frames, H, slots).total;
+    HOWL_REQUIRE(ctx, sm <= 227 * 1024, HOWL_E_UNSUPPORTED, "res8: %d frames exceeds the shared-memory ring of conv0_bwd", frames);
+    HOWL_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(feats) & 15) == 0, HOWL_E_INVALID, "res8_bwd: feats must be 16-byte aligned");
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    const int per_sm = sm <= 72 * 1024 ? 3 : (sm <= 110 * 1024 ? 2 : 1);
-    const int g0 = (int)(B < (int64_t)per_sm * ctx->sm_count ? B : (int64_t)per_sm * ctx->sm_count);
-    conv0_bwd_kernel<<<g0, C0B_THREADS, sm, st>>>(feats, w0, ws.g, ws.gu[1], g_w0, B, frames, H);
+    const int g0 = (int)(B < ctx->sm_count ? B : ctx->sm_count);
+    conv0_bwd_kernel<<<g0, C0B_THREADS, sm, st>>>(feats, ws.bits0, ws.g, g_w0, B, frames, H, slots);
     HOWL_LAUNCHED(ctx, "conv0_bwd");
   }
   return HOWL_OK;
@@ -1078,30 +1141,15 @@ extern "C" int howl_b200_res8_bwd_dlogits(howl_ctx_t* ctx, void* stream, const f
 // =============================================================================================
 // test hook (include/howl_b200_debug.h): the ReLU decisions of the backward, for the mask-forced gradient oracle
 // =============================================================================================
-// conv0: the same FMA order as conv0_pool_kernel / conv0_bwd_kernel (ky outer, kx inner, from 0)
-__global__ void debug_mask0_kernel(const float* __restrict__ feats, const float* __restrict__ w0, uint8_t* __restrict__ mask0,
-                                   int64_t B, int F, int H) {
-  const int rows = 3 * H;
-  const int64_t n = B * rows * R8_MELS;
+// conv0: the bits conv0_pool stored (bit py * 4 + px of pooled pixel (h, w) <-> pre-pool pixel (3h + py, 4w + px))
+__global__ void debug_mask0_kernel(const uint16_t* __restrict__ bits0, uint8_t* __restrict__ mask0, int64_t B, int H) {
+  const int rows = 3 * H, HW = H * R8_W;
+  const int64_t n = B * R8_C * rows * R8_MELS;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % R8_MELS), y = (int)((i / R8_MELS) % rows);
-    const int64_t b = i / ((int64_t)R8_MELS * rows);
-    float patch[3][3];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int yy = y + ky - 1, xx = x + kx - 1;
-        patch[ky][kx] = (yy >= 0 && yy < F && xx >= 0 && xx < R8_MELS) ? feats[(b * F + yy) * R8_MELS + xx] : 0.f;
-      }
-    for (int oc = 0; oc < R8_C; ++oc) {
-      float pre = 0.f;
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) pre = fmaf(__ldg(w0 + oc * 9 + ky * 3 + kx), patch[ky][kx], pre);
-      mask0[((b * R8_C + oc) * rows + y) * R8_MELS + x] = pre > 0.f ? 1 : 0;
-    }
+    const int64_t plane = i / ((int64_t)R8_MELS * rows);      // b * 45 + oc
+    const uint32_t mb = bits0[plane * HW + (y / 3) * R8_W + x / 4];
+    mask0[i] = (mb >> ((y % 3) * 4 + (x % 4))) & 1u;
   }
 }
 
@@ -1122,7 +1170,7 @@ extern "C" int howl_b200_res8_debug_masks(howl_ctx_t* ctx, void* stream, const f
   const int H = frames / 3;
   const int64_t n = B * R8_C * H * R8_W;
   if (mask0) {
-    debug_mask0_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(feats, params, mask0, B, frames, H);
+    debug_mask0_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ws.bits0, mask0, B, H);
     HOWL_LAUNCHED(ctx, "debug_mask0");
   }
   if (masks16) {

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
       const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.in_op);
       const size_t utt_bytes = (size_t)12 * R * 16;
       const __nv_bfloat16* side_op = FWD ? a.res_op : (MODE == 3 ? a.u_op : nullptr);
-      const float* side = (MODE == 3) ? a.gu_in : nullptr;
+      const float* side = (MODE >= 2) ? a.gu_in : nullptr;
       auto load = [&](int64_t k) {            // utterance k of this CTA -> ring slot k & 1, one copy per 8-channel group
         const int s = (int)(k & 1);
         const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
@@ -328,6 +328,24 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
     for (int c = 0; c < 16; ++c) st1[c] = st2[c] = 0.f;
     unsigned long long ep_wait = 0;
     const long long ep_begin = clock64();
+    // layer 6: per-utterance spatial sums for the head.  A warp's 32-row block visits the rows of one utterance in consecutive
+    // tiles, so one running set per thread is flushed (warp reduction + one atomic per channel) when the utterance changes.
+    float pl[16];
+    int64_t pl_b = -1;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) pl[c] = 0.f;
+    auto pool_flush = [&]() {
+      if (pl_b >= 0) {
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          if (jj < 13 || full) {
+            const float sum = warp_sum(pl[jj]);
+            if (lane == 0) atomicAdd(a.pooled_raw + pl_b * R8_C + 16 * grp + jj, sum);
+          }
+          pl[jj] = 0.f;
+        }
+      }
+    };
     for (int64_t cyc = 0; cyc < n_cycles; ++cyc) {
       const uint32_t par = (uint32_t)(cyc & 1);
       const bool has1 = 2 * cyc + 1 < n_local;
@@ -345,126 +363,115 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
         const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(96 * j + 16 * grp);
         const size_t op_row = (size_t)b * 12 * R + q;         // 16-byte units; chunk c of part p at (p * 6 + c) * R
         // ---- everything the tile's epilogue reads from HBM is requested before the accumulator wait
-        float pre[16], gin[16];
+        uint4 sh[2], sl[2];                 // residual (forward) / u_j (fused BatchNorm backward): raw operand-format vectors
+        float gin[16];
         uint32_t bits = 0;
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) pre[jj] = gin[jj] = 0.f;
+        for (int cb = 0; cb < 2; ++cb) sh[cb] = sl[cb] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) gin[jj] = 0.f;
         const __nv_bfloat16* side_op = FWD ? a.res_op : (MODE == 3 ? a.u_op : nullptr);
         if (side_op != nullptr && valid) {
           const uint4* so = reinterpret_cast<const uint4*>(side_op) + op_row;
 #pragma unroll
           for (int cb = 0; cb < 2; ++cb) {
             const int ch = 2 * grp + cb;
-            const uint4 hi = __ldg(so + (size_t)ch * R), lo = __ldg(so + (size_t)(6 + ch) * R);
-            tc_unpack8(hi, lo, pre + 8 * cb);
+            sh[cb] = __ldg(so + (size_t)ch * R);
+            sl[cb] = __ldg(so + (size_t)(6 + ch) * R);
           }
         }
-        if (MODE == 3 && valid) {
+        if (MODE >= 2 && valid) {
           if (a.gu_in) {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj)
               if (jj < 13 || full) gin[jj] = __ldg(a.gu_in + off0 + (uint32_t)jj * (uint32_t)HW);
           }
-          if (a.mask_in) bits = a.mask_in[((size_t)b * 3 + grp) * R + q];
+          if (MODE == 3 && a.mask_in) bits = a.mask_in[((size_t)b * 3 + grp) * R + q];
         }
         const long long te0 = (a.prof && warp == 0) ? clock64() : 0;
         tc::mbar_wait(&bar_tile[j], par);
         if (a.prof && warp == 0) ep_wait += (unsigned long long)(clock64() - te0);
         tc::fence_after_sync();
-        uint32_t v[16], v2[16];
-        tc::tmem_ld16_nowait(taddr, v);            // hi x hi + lo x hi
-        tc::tmem_ld16_nowait(taddr + 48, v2);      // hi x lo
-        tc::tmem_ld_wait();
-        float ov[16];
+        uint32_t mbits = 0;
+        // two halves of 8 channels: keeps the live register set small (accumulator columns, side values, outputs of one half)
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) ov[jj] = 0.f;
-        if (FWD) {
-          uint32_t mbits = 0;
-          if (valid) {
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t v[8], v2[8];
+          tc::tmem_ld8_nowait(taddr + 8 * cb, v);             // hi x hi + lo x hi
+          if (!SINGLE) tc::tmem_ld8_nowait(taddr + 48 + 8 * cb, v2);   // hi x lo
+          float pre[8], ov[8];
+          tc_unpack8(sh[cb], sl[cb], pre);
+          tc::tmem_ld_wait();
+          const int ch = 2 * grp + cb;
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              if (jj < 13 || full) {
-                const float acc = __uint_as_float(v[jj]) + (SINGLE ? 0.f : __uint_as_float(v2[jj]));
+          for (int j8 = 0; j8 < 8; ++j8) {
+            const int jj = 8 * cb + j8;
+            const bool chan = (jj < 13 || full);             // a real channel (0..44)
+            float o = 0.f;
+            if (valid && chan) {
+              const float acc = __uint_as_float(v[j8]) + (SINGLE ? 0.f : __uint_as_float(v2[j8]));
+              if (FWD) {
                 if (acc > 0.f) mbits |= 1u << jj;
-                const float o = fmaxf(acc, 0.f) + pre[jj];
+                o = fmaxf(acc, 0.f) + pre[j8];
                 if (p.out) p.out[off0 + (uint32_t)jj * (uint32_t)HW] = o;
                 if (STATS == 1) {
                   st1[jj] += o;
                   st2[jj] = fmaf(o, o, st2[jj]);
                 }
-                ov[jj] = o;
-              } else if (jj == 13) {
-                ov[jj] = 1.f;                 // channel 45: the "ones" channel (BatchNorm fold of the consumer and of its weight gradient)
+              } else if (MODE == 2) {
+                p.out[off0 + (uint32_t)jj * (uint32_t)HW] = acc + gin[jj];
+              } else {
+                // BatchNorm backward of the producer layer + residual fan-in + ReLU mask, straight from the accumulator
+                const int c = 16 * grp + jj;
+                const float u = pre[j8];
+                const float G = fmaf(s_coef[c], acc, fmaf(s_coef[96 + c], u, s_coef[48 + c])) + gin[jj];
+                if (a.gu_out) a.gu_out[off0 + (uint32_t)jj * (uint32_t)HW] = G;
+                const bool on = a.mask_in ? ((bits >> jj) & 1u) != 0 : (u > 0.f);
+                o = on ? G : 0.f;
               }
+            } else if (FWD && valid && jj == 13) {
+              o = 1.f;                      // channel 45: the "ones" channel (BatchNorm fold of the consumer and of its weight gradient)
             }
+            ov[j8] = o;
           }
-          if (live) {
-            if (a.out_op) {
-              uint4* o_op = reinterpret_cast<uint4*>(a.out_op) + op_row;
-#pragma unroll
-              for (int cb = 0; cb < 2; ++cb) {
-                uint4 hi, lo;
-                tc::split8(ov + 8 * cb, hi, lo);
-                const int ch = 2 * grp + cb;
+          if (live && MODE != 2) {            // halo rows are written too (zeros): no memset of the operand tensors
+            uint4 hi, lo;
+            if (FWD) {
+              if (a.out_op) {
+                uint4* o_op = reinterpret_cast<uint4*>(a.out_op) + op_row;
+                tc::split8(ov, hi, lo);
                 o_op[(size_t)ch * R] = hi;
                 o_op[(size_t)(6 + ch) * R] = lo;
               }
-            }
-            if (a.mask_out) a.mask_out[((size_t)b * 3 + grp) * R + q] = (uint16_t)mbits;
-            if (a.pooled_raw) {              // per-utterance spatial sums for the head (a warp's 32 rows belong to one utterance)
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
-                if (jj < 13 || full) {
-                  const float sum = warp_sum(ov[jj]);
-                  if (lane == 0) atomicAdd(a.pooled_raw + b * R8_C + 16 * grp + jj, sum);
+              if (a.pooled_raw) {
+                if (cb == 0 && b != pl_b) {      // warp uniform: a 32-row block never straddles two utterances
+                  pool_flush();
+                  pl_b = b;
                 }
+#pragma unroll
+                for (int j8 = 0; j8 < 8; ++j8)
+                  if (full || 8 * cb + j8 != 13) pl[8 * cb + j8] += ov[j8];      // (the ones channel of the last quad is not a channel)
               }
-            }
-          }
-        } else if (MODE == 2) {
-          if (valid) {
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj)
-              if (jj < 13 || full) p.out[off0 + (uint32_t)jj * (uint32_t)HW] = __uint_as_float(v[jj]) + (SINGLE ? 0.f : __uint_as_float(v2[jj]));
-          }
-        } else {
-          // MODE 3: BatchNorm backward of the producer layer + residual fan-in + ReLU mask, straight from the accumulator
-          if (valid) {
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              if (jj < 13 || full) {
-                const int c = 16 * grp + jj;
-                const float g = __uint_as_float(v[jj]) + (SINGLE ? 0.f : __uint_as_float(v2[jj]));
-                const float u = pre[jj];
-                const float G = fmaf(s_coef[c], g, fmaf(s_coef[96 + c], u, s_coef[48 + c])) + gin[jj];
-                if (a.gu_out) a.gu_out[off0 + (uint32_t)jj * (uint32_t)HW] = G;
-                const bool on = a.mask_in ? ((bits >> jj) & 1u) != 0 : (u > 0.f);
-                ov[jj] = on ? G : 0.f;
-              }
-            }
-          }
-          if (live) {                        // halo rows are written too (zeros): no memset of the gradient operands
-            uint4* o_op = reinterpret_cast<uint4*>(a.dc_out) + op_row;
-            uint4* o_T = reinterpret_cast<uint4*>(a.dc_outT) + ((size_t)b * (R / 8) + (q >> 3)) * 96 + (lane & 7);
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-              uint4 hi, lo;
-              const int ch = 2 * grp + cb;
-              tc::split8(ov + 8 * cb, hi, lo);
+            } else {
+              uint4* o_op = reinterpret_cast<uint4*>(a.dc_out) + op_row;
+              uint4* o_T = reinterpret_cast<uint4*>(a.dc_outT) + ((size_t)b * (R / 8) + (q >> 3)) * 96 + (lane & 7);
+              tc::split8(ov, hi, lo);
               o_op[(size_t)ch * R] = hi;
               o_op[(size_t)(6 + ch) * R] = lo;
-              tc_transpose8(ov + 8 * cb, lane & 7);          // lane & 7 now holds channel 8 * ch + (lane & 7) at the group's 8 rows
-              tc::split8(ov + 8 * cb, hi, lo);
+              tc_transpose8(ov, lane & 7);                 // lane & 7 now holds channel 8 * ch + (lane & 7) at the group's 8 rows
+              tc::split8(ov, hi, lo);
               o_T[ch * 8] = hi;
               o_T[48 + ch * 8] = lo;
             }
           }
         }
+        if (FWD && live && a.mask_out) a.mask_out[((size_t)b * 3 + grp) * R + q] = (uint16_t)mbits;
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bar_tfree[j]);
       }
     }
+    if (FWD && a.pooled_raw) pool_flush();
     if (a.prof && tid == 0) {
       a.prof[blockIdx.x * 16 + 8] = ep_wait;
       a.prof[blockIdx.x * 16 + 9] = (unsigned long long)(clock64() - ep_begin);

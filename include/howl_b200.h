@@ -61,6 +61,8 @@ int64_t howl_b200_launch_count(const howl_ctx_t* ctx);
 /* Options: "conv_engine" = 1 (default, PARITY mode) 45->45 convolutions on tcgen05 tensor cores with bf16x3-split operands
  * and fp32 accumulation (logits within 1e-5 of fp32); 0 = exact-fp32 FFMA kernels; 2 = FAST mode, the same kernels with the
  * low-order bf16 terms skipped (single bf16 x bf16 products, ~3e-3 relative: outside the 1e-4 parity bar, never the default). */
+/* "fb_unchanged" = 1: one-shot promise that the NEXT frontend / train-step call passes the same filterbank contents as the previous
+ * one on this context, so the compact bank + work plan built from it are reused instead of rebuilt (cleared by that call). */
 int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value);
 /* ---- per-launch device timing (CUDA events on the launching stream; used by bench.py's roofline) --------- */
 /* After profile_begin every kernel launch of this context is bracketed by an event on `stream`. */

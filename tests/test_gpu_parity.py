@@ -118,6 +118,24 @@ def test_frontend_ragged_shapes_vs_oracle(ctx, shape):
     np.testing.assert_allclose(out, want, rtol=RTOL, atol=ATOL)
 
 
+def test_frontend_filterbank_plan_cache(ctx):
+    """The compact bank / work plan are reused only when the very same, unmodified filterbank tensor comes again (steady-state
+    training between VTLP draws); an in-place change or another tensor rebuilds them."""
+    pcm, _ = O.synthetic_batch(3, 8000, 4, seed=5)
+    pcm_d = pcm.to(DEV)
+    fb = O.mel_filterbank(40).to(DEV)
+    want = O.log_mel_f32(pcm, fb.cpu()).numpy()
+    n0 = ctx.launch_count
+    for _ in range(3):
+        np.testing.assert_allclose(ctx.frontend(pcm_d, fb, "mels").cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+    assert ctx.launch_count - n0 <= 4          # 3 frontend launches + at most one plan build
+    warped = O.vtlp_filterbank(1.07, 40)
+    fb.copy_(warped.to(DEV))                   # same tensor object, new contents
+    np.testing.assert_allclose(ctx.frontend(pcm_d, fb, "mels").cpu().numpy(), O.log_mel_f32(pcm, warped).numpy(), rtol=RTOL, atol=ATOL)
+    other = O.mel_filterbank(40).to(DEV)       # another tensor
+    np.testing.assert_allclose(ctx.frontend(pcm_d, other, "mels").cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+
+
 def test_frontend_rejects_short_clip(ctx):
     import howl_b200
 
