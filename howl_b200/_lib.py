@@ -40,6 +40,9 @@ SIGNATURES: Dict[str, tuple] = {
     "howl_b200_selftest_umma": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32]),
     "howl_b200_debug_stream_profile": (C.c_int, [_vp, _vp, _i32]),
     "howl_b200_debug_umma_bench": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "howl_b200_debug_mbn_workspace_bytes": (_i64, [_i64, C.c_int, C.c_int]),
+    "howl_b200_debug_mbn_gemm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz]),
+    "howl_b200_debug_mbn_wgrad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz]),
     "howl_b200_res8_debug_masks": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
     "howl_b200_profile_begin": (C.c_int, [_vp, _vp]),
     "howl_b200_profile_end": (C.c_int, [_vp, _vp, _sz, _vp, _i32]),
@@ -67,6 +70,15 @@ SIGNATURES: Dict[str, tuple] = {
                                                     _i32, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _sz]),
     "howl_b200_lstm_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _i32, _i32, _vp, _vp, _vp,
                                             _vp, _i64, _f32, _f32, _vp, _vp, _vp, _sz]),
+    "howl_b200_mobilenet_param_count": (_i64, [_i32]),
+    "howl_b200_mobilenet_bn_channels": (_i64, []),
+    "howl_b200_mobilenet_bn_layers": (_i64, []),
+    "howl_b200_mobilenet_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
+    "howl_b200_mobilenet_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, _f32, C.c_uint64, _vp, _vp, _sz]),
+    "howl_b200_mobilenet_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i64, _vp, _vp, _f32, C.c_uint64, _vp, _vp, _sz]),
+    "howl_b200_mobilenet_bwd_dlogits": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _f32, C.c_uint64, _vp, _sz]),
+    "howl_b200_mobilenet_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                 _i64, _f32, _f32, _f32, C.c_uint64, _vp, _vp, _vp, _sz]),
     "howl_b200_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32]),
     "howl_b200_res8_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _vp, _i32, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _sz]),

@@ -266,6 +266,56 @@ class SeqLstmCtcTrainStep(LstmTrainStep):
         return self.loss
 
 
+class MobileNetTrainStep(_HostPipeline):
+    """Fused train step of the `mobilenet` model (BASELINE.json configs[2]): frontend -> MobileNetV2 (bf16 tensor-core GEMMs, fp32
+    master weights / BatchNorm statistics) -> CE -> backward -> [allreduce] -> AdamW."""
+
+    def __init__(self, device, num_labels: int, batch: int, samples: int, n_mels: int = 40, lr: float = 0.01, weight_decay: float = 1e-5,
+                 zmuv: Tuple[float, float] = (0.0, 1.0), seed: int = 0, world_size: int = 1, dropout_p: float = 0.2):
+        from . import mobilenet as mb
+
+        self.mb = mb
+        self.ctx = Context(device, n_mels=n_mels)
+        dev = self.ctx.device
+        self.device, self.num_labels, self.batch, self.samples = dev, num_labels, batch, samples
+        self.lr, self.weight_decay, self.zmuv, self.world, self.dropout_p, self.seed = lr, weight_decay, zmuv, world_size, dropout_p, seed
+        self.params = mb.init_flat(num_labels, seed).to(dev)
+        n = self.params.numel()
+        assert n == int(self.ctx.lib.howl_b200_mobilenet_param_count(num_labels))
+        self.grads, self.m, self.v = (torch.zeros(n, device=dev) for _ in range(3))
+        nc = mb.bn_channels(self.ctx)
+        self.bn_running = torch.cat([torch.zeros(1, nc), torch.ones(1, nc)]).contiguous().to(dev)       # [2][channels]: means, variances
+        self.nbt = torch.zeros(mb.bn_layers(self.ctx), dtype=torch.int64, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        self.logits = torch.zeros(batch, num_labels, device=dev)
+        self.fb = mel_filterbank(n_mels).to(dev)
+        self.frames = self.ctx.num_frames(samples)
+        self.feat_bytes = (batch * self.frames * n_mels * 4 + 255) // 256 * 256
+        self.ws = torch.empty(self.feat_bytes + mb.workspace_bytes(self.ctx, batch, self.frames, num_labels), dtype=torch.uint8, device=dev)
+        self.step_count = 0
+        self._init_host_pipeline()
+
+    def step(self, pcm: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        self.step_count += 1
+        c, mb = self.ctx, self.mb
+        seed = self.seed * 1000003 + self.step_count
+        if self.world == 1:
+            mb.train_step(c, pcm, labels, self.fb, self.zmuv, self.params, self.bn_running, self.nbt, self.grads, self.m, self.v,
+                          self.step_count, self.lr, self.weight_decay, self.dropout_p, seed, self.loss, self.logits, self.ws)
+        else:
+            from .parallel import allreduce_flat_grads
+
+            b = pcm.shape[0]
+            feats = self.ws[: b * self.frames * c.n_mels * 4].view(torch.float32).view(b, c.n_mels, self.frames)
+            ws = self.ws[self.feat_bytes:]
+            c.frontend(pcm, self.fb, "mels", zmuv=self.zmuv, out=feats)
+            mb.forward(c, feats, self.params, self.bn_running, self.nbt, True, ws, self.dropout_p, seed, logits=self.logits)
+            mb.backward(c, feats, labels, self.params, self.grads, self.loss, ws, self.dropout_p, seed, loss_scale_batch=b * self.world)
+            allreduce_flat_grads(self.grads)
+            c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
+        return self.loss
+
+
 class Trainer:
     """``howl.trainer.Trainer`` (``howl/trainer.py:11-31``): constructible from a ``TrainingConfig`` exactly like the reference's
     (which is a stub without a training loop); ``train`` is the addition the reference leaves open -- the epoch loop of
@@ -326,7 +376,7 @@ class Trainer:
 
                     alpha = _random.random() * 0.2 + 0.9                      # VtlpMelScale.forward (transform.py:441)
                     fb = vtlp_filterbank(alpha, std.num_mels, std.sample_rate, std.num_fft // 2 + 1).to(step.device)
-                rects = spec.draw_rects(pcm.shape[0], std.num_mels, step.ctx.num_frames(pcm.shape[1])).to(step.device)
+                rects = spec.draw_rects(pcm.shape[0], std.num_mels, 1 + pcm.shape[1] // std.hop_length).to(step.device)
             loss = step.step(pcm.to(step.device, torch.float32), labels.to(step.device, torch.int64), rects=rects, fb=fb)
             total, n = total + float(loss.item()), n + 1
         if self.step_obj is not None:

@@ -193,6 +193,38 @@ int howl_b200_lstm_train_step(howl_ctx_t* ctx, void* stream, const float* pcm, c
                               float* exp_avg, float* exp_avg_sq, int64_t step, float lr, float weight_decay, float* loss,
                               float* logits, void* workspace, size_t workspace_bytes);
 
+/* ---- K6: MobileNetClassifier (MobileNetV2) ------------------------------------------------------- */
+/* Replaces MobileNetClassifier.forward (howl/model/cnn.py:15-29: Conv2d(1,3,3,pad=(1,3)) + BatchNorm2d(3) + ReLU + MaxPool2d((1,2)), then
+ * torchvision's MobileNetV2 features + Dropout(0.2) + Linear) and its autograd backward.  bf16 activations / gradients, fp32 master
+ * weights, fp32 BatchNorm statistics, fp32 accumulation (BASELINE.json configs[2]).
+ * Flat parameter layout = the trainable tensors in state_dict order (conv weight [, conv bias], BatchNorm weight, BatchNorm bias per
+ * convolution; classifier weight [L,1280], bias [L]); 2,262,338 floats at 30 labels.  BatchNorm running statistics:
+ * bn_running [2][bn_channels] (all means, then all variances, layers concatenated in state_dict order), num_batches_tracked [bn_layers]. */
+int64_t howl_b200_mobilenet_param_count(int32_t num_labels);
+int64_t howl_b200_mobilenet_bn_channels(void);
+int64_t howl_b200_mobilenet_bn_layers(void);
+int64_t howl_b200_mobilenet_workspace_bytes(int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels);
+/* feats: [B, n_mels, frames] f32 log-mel (HOWL_FE_MELS_ONLY layout = x[:, :1] of the stacked features, cnn.py:27).  train != 0: batch
+ * statistics + running-stat update, activations kept in `workspace` for the backward; dropout_p / seed drive the classifier's dropout
+ * mask (a counter-based hash of (seed, utterance, channel); eval: identity).  Writes logits [B, L]. */
+int howl_b200_mobilenet_fwd(howl_ctx_t* ctx, void* stream, const float* feats, int64_t B, int32_t frames, int32_t n_mels,
+                            int32_t num_labels, const float* params, float* bn_running, int64_t* num_batches_tracked, int train,
+                            float dropout_p, uint64_t seed, float* logits, void* workspace, size_t workspace_bytes);
+/* CrossEntropyLoss(mean) + backward (training/run/train.py:293,299-301 with --model mobilenet) for the forward kept in `workspace`;
+ * dropout_p / seed as given to the forward.  grads (flat layout) is OVERWRITTEN. */
+int howl_b200_mobilenet_bwd(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* labels, int64_t B, int32_t frames,
+                            int32_t n_mels, int32_t num_labels, int64_t loss_scale_batch, const float* params, float* grads,
+                            float dropout_p, uint64_t seed, float* loss, void* workspace, size_t workspace_bytes);
+int howl_b200_mobilenet_bwd_dlogits(howl_ctx_t* ctx, void* stream, const float* feats, const float* dlogits, int64_t B, int32_t frames,
+                                    int32_t n_mels, int32_t num_labels, const float* params, float* grads, float dropout_p,
+                                    uint64_t seed, void* workspace, size_t workspace_bytes);
+/* frontend -> MobileNetV2 -> CE -> backward -> AdamW in one call (single device). */
+int howl_b200_mobilenet_train_step(howl_ctx_t* ctx, void* stream, const float* pcm, const int64_t* labels, int64_t B, int64_t T,
+                                   const float* fb, float zmuv_mean, float zmuv_std, int32_t num_labels, float* params,
+                                   float* bn_running, int64_t* num_batches_tracked, float* grads, float* exp_avg, float* exp_avg_sq,
+                                   int64_t step, float lr, float weight_decay, float dropout_p, uint64_t seed, float* loss,
+                                   float* logits, void* workspace, size_t workspace_bytes);
+
 /* ---- K4: fused AdamW over a flat buffer ------------------------------------------------------- */
 /* torch.optim.AdamW.step (training/run/train.py:256,302): decoupled weight decay, bias correction,
  * eps outside the sqrt; `step` is 1-based. */

@@ -36,6 +36,14 @@ int howl_b200_res8_debug_masks(howl_ctx_t* ctx, void* stream, const float* feats
                                int32_t frames, int32_t n_mels, int32_t num_labels, const void* workspace,
                                size_t workspace_bytes, uint8_t* mask0, uint8_t* masks16);
 
+/* Test hooks for the tensor-core GEMMs of the MobileNetV2 path on plain fp32 row-major matrices (converted to the bf16 tile-major
+ * operand format inside):  C[M,N] = A[M,K] * W[N,K]^T (+ add[M,N]);   dW[N,K] = dC[M,N]^T * A[M,K]. */
+int64_t howl_b200_debug_mbn_workspace_bytes(int64_t M, int K, int N);
+int howl_b200_debug_mbn_gemm(howl_ctx_t* ctx, void* stream, const float* A, const float* W, const float* add, float* C, int64_t M,
+                             int32_t K, int32_t N, void* workspace, size_t workspace_bytes);
+int howl_b200_debug_mbn_wgrad(howl_ctx_t* ctx, void* stream, const float* dC, const float* A, float* dW, int64_t M, int32_t N,
+                              int32_t K, void* workspace, size_t workspace_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -532,29 +532,57 @@ def mobilenet_plan():
     return plan
 
 
-def mobilenet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], train: bool = False) -> torch.Tensor:
+def _ste_bf16(t: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 (nearest even) and back, straight-through for autograd."""
+    return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+
+
+def mobilenet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], train: bool = False, bf16: bool = False) -> torch.Tensor:
     """x: [B, C>=1, 40, F] stacked features (only the log-mel channel is used, cnn.py:27); returns logits [B, L].
-    Dropout of the classifier is the identity (eval) -- the training-mode restatement is deterministic up to dropout."""
+    Dropout of the classifier is the identity (eval) -- the training-mode restatement is deterministic up to dropout.
+
+    ``bf16=True`` restates the SAME graph with the storage precision BASELINE.json configs[2] asks for ("bf16 activations / weights with
+    fp32 master weights and fp32 BatchNorm statistics"): every tensor that is stored between layers -- the stem's pooled activations,
+    every convolution's raw output, the depthwise outputs after BatchNorm + ReLU6, the block outputs -- and the GEMM convolutions'
+    weights are rounded to bf16; all arithmetic (accumulation, BatchNorm statistics from the rounded outputs, normalisation) stays fp32.
+    With batch-statistics BatchNorm a randomly initialised MobileNetV2 amplifies that rounding to ~20 % of the logits (it is 0.7-1.3 %
+    with the shipped GSC checkpoint; tests/test_oracle_golden.py), so the GPU path is held against THIS restatement."""
     import torch.nn.functional as F
 
+    r = _ste_bf16 if bf16 else (lambda t: t)
     relu6 = lambda t: torch.clamp(t, 0.0, 6.0)
     x = x[:, :1]
     x = F.conv2d(x, sd["downsample.0.weight"], sd["downsample.0.bias"], padding=(1, 3))
-    x = F.max_pool2d(torch.relu(_bn(x, sd, "downsample.1", train)), (1, 2))
+    x = r(F.max_pool2d(torch.relu(_bn(x, sd, "downsample.1", train)), (1, 2)))
     f = "model.features."
-    x = relu6(_bn(F.conv2d(x, sd[f + "0.0.weight"], None, stride=2, padding=1), sd, f + "0.1", train))
+    x = relu6(_bn(r(F.conv2d(x, r(sd[f + "0.0.weight"]), None, stride=2, padding=1)), sd, f + "0.1", train))
     for idx, inp, oup, stride, t in mobilenet_plan():
         p, h, j = f"{f}{idx}.conv.", x, 0
         if t != 1:      # pointwise expansion
-            h = relu6(_bn(F.conv2d(h, sd[f"{p}0.0.weight"]), sd, f"{p}0.1", train))
+            h = relu6(_bn(r(F.conv2d(h, r(sd[f"{p}0.0.weight"]))), sd, f"{p}0.1", train))
             j = 1
         hidden = h.shape[1]
-        h = relu6(_bn(F.conv2d(h, sd[f"{p}{j}.0.weight"], None, stride=stride, padding=1, groups=hidden), sd, f"{p}{j}.1", train))   # depthwise
-        h = _bn(F.conv2d(h, sd[f"{p}{j + 1}.weight"]), sd, f"{p}{j + 2}", train)                                                  # linear projection
-        x = x + h if (stride == 1 and inp == oup) else h
-    x = relu6(_bn(F.conv2d(x, sd[f + "18.0.weight"]), sd, f + "18.1", train))
+        h = r(relu6(_bn(r(F.conv2d(h, sd[f"{p}{j}.0.weight"], None, stride=stride, padding=1, groups=hidden)), sd, f"{p}{j}.1", train)))   # depthwise
+        h = _bn(r(F.conv2d(h, r(sd[f"{p}{j + 1}.weight"]))), sd, f"{p}{j + 2}", train)                                                  # linear projection
+        x = r(x + h if (stride == 1 and inp == oup) else h)
+    x = relu6(_bn(r(F.conv2d(x, r(sd[f + "18.0.weight"]))), sd, f + "18.1", train))
     x = x.mean((2, 3))                                                  # adaptive_avg_pool2d(1) + flatten
     return x @ sd["model.classifier.1.weight"].t() + sd["model.classifier.1.bias"]
+
+
+def mobilenet_param_names(sd: Dict[str, torch.Tensor]) -> List[str]:
+    """Trainable tensors of a MobileNetClassifier state dict, in state_dict order (= the flat layout of include/howl_b200.h)."""
+    return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))]
+
+
+def mobilenet_grads(x: torch.Tensor, labels: torch.Tensor, sd: Dict[str, torch.Tensor], dtype=torch.float32, bf16: bool = False):
+    """CrossEntropyLoss(mean) + autograd through ``mobilenet_forward`` in train mode (batch statistics, dropout off):
+    -> (loss, logits, {name: grad}).  ``bf16``: the bf16-storage restatement of the forward (gradients themselves stay fp32)."""
+    leaves = {k: (v.to(dtype).requires_grad_(True) if k in set(mobilenet_param_names(sd)) else v) for k, v in sd.items()}
+    logits = mobilenet_forward(x.to(dtype), leaves, train=True, bf16=bf16)
+    loss = F.cross_entropy(logits, labels)
+    loss.backward()
+    return loss.detach(), logits.detach(), {k: leaves[k].grad.detach() for k in mobilenet_param_names(sd)}
 
 
 # =====================================================================================================

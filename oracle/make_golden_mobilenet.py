@@ -64,6 +64,46 @@ def main():
                         digest=np.frombuffer(state_dict_digest(sd).encode(), dtype=np.uint8))
     print("mobilenet fixture:", feats.shape, logits_eval[0, :4], state_dict_digest(sd)[:16])
 
+    # ---- the checkpoint itself, for the GPU box (where /root/reference does not exist).  A randomly initialised MobileNetV2 with
+    # batch-statistics BatchNorm is chaotic (perturbations grow exponentially with depth), so bf16 parity can only be judged on trained
+    # weights.  The GEMM convolutions' weights are stored as bf16 bit patterns (what the tensor-core path feeds the MMAs anyway), the
+    # rest as fp32: 4.6 MB.  The logits below come from the REFERENCE module loaded with exactly these (dequantised) weights, on a
+    # larger seeded batch, in eval and in train (batch statistics, dropout off) mode, plus the reference's own autograd gradients.
+    q = {}
+    sd_q = {}
+    for k, v in sd.items():
+        if v.dim() == 4 and (v.shape[2] == 1 or k == "model.features.0.0.weight") and v.shape[1] > 1:
+            bits = v.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+            q[k + "::bf16"] = bits
+            sd_q[k] = v.to(torch.bfloat16).to(torch.float32)
+        else:
+            q[k] = v.numpy()
+            sd_q[k] = v.clone()
+    model.load_state_dict(sd_q)
+    g2 = torch.Generator().manual_seed(321)
+    pcm2 = (torch.randn(24, 16000, generator=g2) * 0.1).clamp_(-1, 1)
+    labels2 = torch.randint(0, 30, (24,), generator=g2)
+    with torch.no_grad():
+        feats2 = zmuv(std(pcm2))
+        model.eval()
+        q["logits_eval"] = model(feats2, None).numpy()
+    model.train()
+    model.model.classifier[0].p = 0.0
+    model.zero_grad()
+    out = model(feats2, None)
+    loss = torch.nn.functional.cross_entropy(out, labels2)
+    loss.backward()
+    q["logits_train"], q["loss_train"] = out.detach().numpy(), np.float32(loss.item())
+    # (the 9 MB of reference gradients are not shipped: tests/test_oracle_golden.py checks, where the reference is mounted, that the
+    # oracle's autograd reproduces them; the GPU box compares against the oracle)
+    gnorm = {k: float(p_.grad.norm()) for k, p_ in model.named_parameters()}
+    q["grad_norms"] = np.array([gnorm[k] for k, _ in model.named_parameters()], dtype=np.float32)
+    q["grad_sample"] = torch.cat([p_.grad.reshape(-1)[:16] for _, p_ in model.named_parameters()]).numpy()
+    q["pcm"], q["labels"] = pcm2.numpy(), labels2.numpy()
+    q["zmuv_mean"], q["zmuv_mean2"] = zmuv.mean.numpy(), zmuv.mean2.numpy()
+    np.savez_compressed(os.path.join(OUT, "mobilenet_ckpt.npz"), **q)
+    print("mobilenet checkpoint fixture:", os.path.getsize(os.path.join(OUT, "mobilenet_ckpt.npz")) / 1e6, "MB, train loss", loss.item())
+
 
 if __name__ == "__main__":
     main()

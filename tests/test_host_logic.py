@@ -209,8 +209,10 @@ def test_trainer_epoch_loop_decays_lr(monkeypatch):
             self.device, self.lr = torch.device("cpu"), lr
             calls.append(("init", num_labels, batch, samples, lr, weight_decay, zmuv, seed))
 
-        def step(self, pcm, labels):
+        def step(self, pcm, labels, rects=None, fb=None):
             assert pcm.dtype == torch.float32 and labels.dtype == torch.int64
+            assert rects is not None and rects.dtype == torch.int32 and tuple(rects.shape) == (pcm.shape[0], 4)     # SpecAugment draws
+            assert fb is None or tuple(fb.shape) == (257, 80)                                                     # VTLP bank (NUM_MELS default)
             calls.append(("step", self.lr))
             return torch.tensor(2.0)
 

@@ -299,3 +299,28 @@ def test_gru_restatement_matches_reference(golden):
         np.testing.assert_allclose(O.gru_forward(feats, sd, lengths).numpy(), g["logits_eval_ragged"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(O.gru_forward(feats, sd, lengths, train=True).numpy(), g["logits_train_ragged"], rtol=1e-4, atol=1e-5)
     assert lengths.tolist() == [78, 68, 43, 23]       # the restatement must not modify its argument (the reference does: `lengths += 4`)
+
+
+def test_mobilenet_checkpoint_fixture_pins_oracle_forward_and_gradients(golden):
+    """tests/golden/mobilenet_ckpt.npz (the shipped GSC checkpoint + the REFERENCE module's logits / loss / gradient norms for it): the oracle's
+    fp32 restatement reproduces them, and its bf16-storage restatement stays within the bf16 bar the GPU path is held to."""
+    g = golden("mobilenet_ckpt")
+    sd = {}
+    for k, v in g.items():
+        if k.endswith("::bf16"):
+            sd[k[:-6]] = torch.from_numpy(v.view(np.int16).copy()).view(torch.bfloat16).to(torch.float32)
+        elif k.startswith(("downsample.", "model.")):
+            sd[k] = torch.from_numpy(v)
+    pcm, labels = torch.from_numpy(g["pcm"]), torch.from_numpy(g["labels"])
+    x = O.hot_path_features(pcm, O.mel_filterbank(40), torch.from_numpy(g["zmuv_mean"]), torch.from_numpy(g["zmuv_mean2"]))
+    with torch.no_grad():
+        np.testing.assert_allclose(O.mobilenet_forward(x, sd, train=False).numpy(), g["logits_eval"], rtol=1e-3, atol=1e-3)
+        bf = O.mobilenet_forward(x, sd, train=True, bf16=True)
+    loss, logits, grads = O.mobilenet_grads(x, labels, sd)
+    np.testing.assert_allclose(logits.numpy(), g["logits_train"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(loss.item(), float(g["loss_train"]), rtol=1e-4)
+    names = O.mobilenet_param_names(sd)
+    np.testing.assert_allclose([float(grads[k].norm()) for k in names], g["grad_norms"], rtol=1e-2, atol=1e-4 * float(g["grad_norms"].max()))
+    np.testing.assert_allclose(torch.cat([grads[k].reshape(-1)[:16] for k in names]).numpy(), g["grad_sample"], rtol=2e-2, atol=1e-4 * float(g["grad_norms"].max()))
+    want = torch.from_numpy(g["logits_train"])
+    assert ((bf - want).norm() / want.norm()).item() < 2e-2 and torch.equal(bf.argmax(1), want.argmax(1))
