@@ -54,6 +54,7 @@ SIGNATURES: Dict[str, tuple] = {
     "howl_b200_spec_mask": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "howl_b200_to_time_major": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "howl_b200_batch_gather": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "howl_b200_batch_gather_aug": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
     "howl_b200_res8_param_count": (_i64, [_i32]),
     "howl_b200_res8_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, C.c_int]),
     "howl_b200_res8_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, _vp, _vp, _sz]),

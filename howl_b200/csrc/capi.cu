@@ -87,6 +87,10 @@ extern "C" int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t v
     ctx->conv_engine = (int)value;
     return HOWL_OK;
   }
+  if (strcmp(name, "pcm_i16") == 0) {
+    ctx->pcm_i16 = value != 0;
+    return HOWL_OK;
+  }
   if (strcmp(name, "fb_unchanged") == 0) {   // one-shot: the next frontend call's filterbank equals the previous call's
     ctx->fb_same_next = value != 0;
     return HOWL_OK;

@@ -25,6 +25,7 @@ struct howl_ctx {
   void* fe_bank;
   float* fe_ent;
   int fb_plan_valid; // the compact bank / plan on the device belong to the filterbank of the previous frontend call
+  int pcm_i16;       // option "pcm_i16": every PCM pointer handed to this context is int16 (the on-disk format), scaled by 1 / 32768 in K1
   int fb_same_next;  // one-shot promise of the caller (set_option "fb_unchanged"): the next call's fb equals the previous call's
   int64_t launches;
   int conv_engine;

@@ -110,3 +110,93 @@ extern "C" int howl_b200_batch_gather(howl_ctx_t* ctx, void* stream, const float
   HOWL_LAUNCHED(ctx, "batch_gather");
   return HOWL_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-side waveform augmentation fused into the batch gather.  The reference augments whole clips on the host
+// before batching (training/run/train.py:202-221: DatasetMixer -> TimeshiftTransform -> NoiseTransform -> batchifier,
+// howl/data/transform/transform.py:120-231); here the host only replays the draws and row r of the batch is produced in ONE pass:
+//   x[j]   = clips[starts[r] + j]                                   (the time shift is a start offset / a shorter count)
+//   x[j]   = x[j] * (1 - alpha) + bg[bg_starts[r] + j] * alpha       (DatasetMixer; two roundings and an add, as torch computes it)
+//   x[j]   = clamp(x[j] + clamp(N(0, sigma)), -1, 1)                 (NoiseTransform "white")
+//   x[j]   = clamp(x[j] + (Bern(p/2) - Bern(p/2)), -1, 1)            (NoiseTransform "salt_pepper")
+// with the noise drawn in the kernel from Philox4x32-10 keyed by (seed; row, sample) -- the same distributions as torch's host
+// generator, not the same stream.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+struct GatherAugArgs {
+  const float* clips;
+  const int64_t* starts;
+  const int64_t* counts;
+  const int64_t* dst_off;
+  const float* bg;            // concatenated background clips, or null
+  const int64_t* bg_starts;   // [B], < 0: no mixing for the row
+  const double* alpha;        // [B] (double: the reference forms 1 - alpha in double before torch rounds both weights to fp32)
+  const float* sigma;         // [B] white-noise strength, 0: off
+  const float* sp_prob;       // [B] salt-and-pepper probability, 0: off
+  unsigned long long seed;
+  int64_t max_length;
+  float* out;
+};
+
+__global__ void __launch_bounds__(256) batch_gather_aug_kernel(const GatherAugArgs a) {
+  const int64_t r = blockIdx.y;
+  const int64_t n = a.counts[r], d0 = a.dst_off[r];
+  const float* src = a.clips + a.starts[r];
+  const int64_t bgs = (a.bg && a.bg_starts) ? a.bg_starts[r] : -1;
+  const double al64 = a.alpha ? a.alpha[r] : 0.0;
+  const float al = (float)al64, one_m = (float)(1.0 - al64);      // python computes 1 - alpha in double, torch rounds both weights to fp32
+  const float sg = a.sigma ? a.sigma[r] : 0.f, sp = a.sp_prob ? a.sp_prob[r] : 0.f;
+  float* dst = a.out + r * a.max_length;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.max_length; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i - d0;
+    float x = 0.f;
+    if (j >= 0 && j < n) {
+      x = __ldg(src + j);
+      if (bgs >= 0) x = __fadd_rn(__fmul_rn(x, one_m), __fmul_rn(__ldg(a.bg + bgs + j), al));
+      if (sg > 0.f || sp > 0.f) {
+        const uint4 rnd = philox4x32_10(make_uint4((uint32_t)j, (uint32_t)(j >> 32), (uint32_t)r, 0u),
+                                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        if (sg > 0.f) {
+          const float u1 = ((float)(rnd.x >> 8) + 0.5f) * (1.f / 16777216.f), u2 = ((float)(rnd.y >> 8) + 0.5f) * (1.f / 16777216.f);
+          const float nz = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2) * sg;
+          x = fminf(fmaxf(x + fminf(fmaxf(nz, -1.f), 1.f), -1.f), 1.f);
+        }
+        if (sp > 0.f) {
+          const float half = 0.5f * sp;
+          const float m = (((float)(rnd.z >> 8) * (1.f / 16777216.f)) < half ? 1.f : 0.f) - (((float)(rnd.w >> 8) * (1.f / 16777216.f)) < half ? 1.f : 0.f);
+          x = fminf(fmaxf(x + m, -1.f), 1.f);
+        }
+      }
+    }
+    dst[i] = x;
+  }
+}
+
+extern "C" int howl_b200_batch_gather_aug(howl_ctx_t* ctx, void* stream, const float* clips, const int64_t* starts, const int64_t* counts,
+                                          const int64_t* dst_off, int64_t B, int64_t max_length, const float* bg, const int64_t* bg_starts,
+                                          const double* alpha, const float* sigma, const float* sp_prob, uint64_t seed, float* out) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, clips && starts && counts && dst_off && out, HOWL_E_INVALID, "batch_gather_aug: null pointer");
+  HOWL_REQUIRE(ctx, B >= 0 && B <= 65535 && max_length >= 0, HOWL_E_INVALID, "batch_gather_aug: bad shape");
+  HOWL_REQUIRE(ctx, (bg != nullptr) == (bg_starts != nullptr) && (!bg || alpha), HOWL_E_INVALID, "batch_gather_aug: bg, bg_starts and alpha go together");
+  if (B == 0 || max_length == 0) return HOWL_OK;
+  GatherAugArgs a;
+  a.clips = clips; a.starts = starts; a.counts = counts; a.dst_off = dst_off; a.bg = bg; a.bg_starts = bg_starts; a.alpha = alpha;
+  a.sigma = sigma; a.sp_prob = sp_prob; a.seed = seed; a.max_length = max_length; a.out = out;
+  int64_t bx = howl_ceil_div(max_length, 256 * 4);
+  if (bx > 64) bx = 64;
+  batch_gather_aug_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(a);
+  HOWL_LAUNCHED(ctx, "batch_gather_aug");
+  return HOWL_OK;
+}

@@ -51,6 +51,7 @@ struct FeParams {
   float zmean, zstd;
   uint32_t flags;
   int use_tma;
+  int pcm_i16;            // pcm points to int16 samples
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -219,7 +220,20 @@ __global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams 
   const int span = (int)(hi - lo);
   const float* src = p.pcm + b * T + lo;
 
-  if (p.use_tma) {
+  if (p.pcm_i16) {
+    // int16 PCM: x / 32768 (exact in fp32) while staging; 4 samples per 64-bit load where the span start is 8-byte aligned
+    const short* s16 = reinterpret_cast<const short*>(p.pcm) + b * T + lo;
+    if ((reinterpret_cast<uintptr_t>(s16) & 7) == 0) {
+      const int n4 = span >> 2;
+      for (int i = tid; i < n4; i += FE_THREADS) {
+        const short4 q = __ldg(reinterpret_cast<const short4*>(s16) + i);
+        reinterpret_cast<float4*>(s_pcm)[i] = make_float4(q.x * (1.f / 32768.f), q.y * (1.f / 32768.f), q.z * (1.f / 32768.f), q.w * (1.f / 32768.f));
+      }
+      for (int i = (n4 << 2) + tid; i < span; i += FE_THREADS) s_pcm[i] = s16[i] * (1.f / 32768.f);
+    } else {
+      for (int i = tid; i < span; i += FE_THREADS) s_pcm[i] = s16[i] * (1.f / 32768.f);
+    }
+  } else if (p.use_tma) {
     if (tid == 0) mbar_init(&s_bar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -490,7 +504,8 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
   p.window = ctx->d_window; p.tw_lane = ctx->d_tw_lane; p.tw_stage = ctx->d_tw_stage; p.w512_lane = ctx->d_w512_lane;
   p.rects = rects; p.out = out; p.B = B; p.T = T; p.F = F; p.M = M; p.hop = hop;
   p.zmean = zmuv_mean; p.zstd = zmuv_std; p.flags = flags;
-  p.use_tma = ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((hop & 3) == 0);
+  p.pcm_i16 = ((flags & HOWL_FE_PCM_I16) || ctx->pcm_i16) ? 1 : 0;
+  p.use_tma = !p.pcm_i16 && ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((hop & 3) == 0);
   const size_t smem = howl_fe_smem_bytes(hop, M);
   HOWL_CUDA(ctx, cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)howl_ceil_div(F, FE_TILE), (unsigned)1, 1);
@@ -498,7 +513,7 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
   for (int64_t b0 = 0; b0 < B; b0 += 65535) {
     const int64_t nb = (B - b0 < 65535) ? (B - b0) : 65535;
     FeParams q = p;
-    q.pcm = pcm + b0 * T;
+    q.pcm = p.pcm_i16 ? reinterpret_cast<const float*>(reinterpret_cast<const short*>(pcm) + b0 * T) : pcm + b0 * T;
     q.rects = rects ? rects + b0 * 4 : nullptr;
     const int64_t per = (flags & HOWL_FE_STACKED) ? 3LL * M * F : (int64_t)M * F;
     q.out = out + b0 * per;

@@ -151,7 +151,7 @@ def backward(ctx: Context, feats, labels, params, grads, loss, ws, dropout_p: fl
 
 def train_step(ctx: Context, pcm, labels, fb, zmuv, params, bn_running, nbt, grads, m, v, step, lr, weight_decay, dropout_p, seed, loss,
                logits, ws):
-    _check(pcm, torch.float32, ctx.device, "pcm")
+    ctx._note_pcm(pcm)
     _check(labels, torch.int64, ctx.device, "labels")
     for name, t_ in (("fb", fb), ("params", params), ("bn_running", bn_running), ("grads", grads), ("m", m), ("v", v), ("loss", loss),
                      ("logits", logits)):

@@ -104,6 +104,15 @@ class Context:
         labels = names.raw.split(b"\0")[:n]
         return [(labels[i].decode(), float(ms[i])) for i in range(n)]
 
+    def _note_pcm(self, pcm: torch.Tensor, name: str = "pcm"):
+        """PCM may be float32 or int16 (the wav files' own format: K1 converts with x / 32768); tells the library which."""
+        if pcm.dtype not in (torch.float32, torch.int16) or pcm.device != self.device or not pcm.is_contiguous():
+            raise HowlB200Error(f"{name}: need a contiguous float32 or int16 tensor on {self.device}, got {pcm.dtype} {pcm.device}")
+        i16 = pcm.dtype == torch.int16
+        if i16 != getattr(self, "_pcm_i16", False):
+            self.set_option("pcm_i16", int(i16))
+            self._pcm_i16 = i16
+
     def _note_fb(self, fb: torch.Tensor):
         """Tell the library when this call's filterbank is the very tensor (same object, unmodified) of the previous call, so that
         the compact bank / work plan on the device are reused.  The tensor is kept referenced: its storage cannot be recycled for
@@ -126,7 +135,7 @@ class Context:
     def frontend(self, pcm: torch.Tensor, fb: torch.Tensor, layout: str = "stacked", zmuv=None,
                  rects: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """layout: 'stacked' [B,3,M,F] | 'mels' [B,M,F] | 'time_major' [B,F,M]; zmuv = (mean, std) or None."""
-        _check(pcm, torch.float32, self.device, "pcm")
+        self._note_pcm(pcm)
         _check(fb, torch.float32, self.device, "fb")
         if pcm.dim() != 2 or tuple(fb.shape) != (self.n_fft // 2 + 1, self.n_mels):
             raise HowlB200Error(f"frontend: pcm must be [B,T] and fb [{self.n_fft // 2 + 1},{self.n_mels}]")
@@ -181,6 +190,24 @@ class Context:
         out = torch.empty(starts.numel(), max_length, dtype=torch.float32, device=self.device)
         self._rc(self.lib.howl_b200_batch_gather(self.handle, self._stream(), _ptr(clips), _ptr(starts), _ptr(counts),
                                                  _ptr(dst_off), starts.numel(), max_length, _ptr(out)), "batch_gather")
+        return out
+
+    def batch_gather_aug(self, clips, starts, counts, dst_off, max_length: int, bg=None, bg_starts=None, alpha=None, sigma=None,
+                         sp_prob=None, seed: int = 0) -> torch.Tensor:
+        """batch_gather with the waveform augmentations applied in the same pass; per-row parameter tensors on the
+        device (float64 alpha, float32 sigma / sp_prob, int64 bg_starts), any of them None."""
+        _check(clips, torch.float32, self.device, "clips")
+        for name, t in (("starts", starts), ("counts", counts), ("dst_off", dst_off)) + ((("bg_starts", bg_starts),) if bg_starts is not None else ()):
+            _check(t, torch.int64, self.device, name)
+        for name, t in (("bg", bg), ("sigma", sigma), ("sp_prob", sp_prob)):
+            if t is not None:
+                _check(t, torch.float32, self.device, name)
+        if alpha is not None:
+            _check(alpha, torch.float64, self.device, "alpha")
+        out = torch.empty(starts.numel(), max_length, dtype=torch.float32, device=self.device)
+        self._rc(self.lib.howl_b200_batch_gather_aug(self.handle, self._stream(), _ptr(clips), _ptr(starts), _ptr(counts), _ptr(dst_off),
+                                                     starts.numel(), max_length, _ptr(bg), _ptr(bg_starts), _ptr(alpha), _ptr(sigma),
+                                                     _ptr(sp_prob), int(seed), _ptr(out)), "batch_gather_aug")
         return out
 
     # ------------------------------------------------------------------ res8
@@ -279,7 +306,7 @@ class Context:
                         logits, ws):
         b, t = pcm.shape
         num_labels = self.lstm_labels_from_params(params)
-        _check(pcm, torch.float32, self.device, "pcm")
+        self._note_pcm(pcm)
         _check(labels, torch.int64, self.device, "labels")
         _check(lengths, torch.int64, self.device, "lengths")
         for name, t_ in (("fb", fb), ("params", params), ("grads", grads), ("m", m), ("v", v), ("loss", loss), ("logits", logits)):
@@ -304,7 +331,7 @@ class Context:
                                 v, step, lr, weight_decay, loss, scores, ws):
         b, t = pcm.shape
         num_labels = self.lstm_labels_from_params(params)
-        _check(pcm, torch.float32, self.device, "pcm")
+        self._note_pcm(pcm)
         for name, t_ in (("targets", targets), ("target_lengths", target_lengths), ("lengths", lengths)):
             _check(t_, torch.int64, self.device, name)
         for name, t_ in (("fb", fb), ("params", params), ("state", state), ("grads", grads), ("m", m), ("v", v), ("loss", loss),
@@ -332,7 +359,7 @@ class Context:
 
     def res8_train_step(self, pcm, labels, fb, zmuv, params, bn_running, nbt, grads, m, v, step, lr, weight_decay,
                         loss, logits, ws, rects=None):
-        _check(pcm, torch.float32, self.device, "pcm")
+        self._note_pcm(pcm)
         _check(labels, torch.int64, self.device, "labels")
         for name, t_ in (("fb", fb), ("params", params), ("bn_running", bn_running), ("grads", grads), ("m", m), ("v", v)):
             _check(t_, torch.float32, self.device, name)

@@ -125,7 +125,7 @@ class StandardAudioTransform(AugmentModule):
         if audio.device.type != "cuda":
             raise RuntimeError("howl_b200.StandardAudioTransform needs CUDA tensors (no CPU fallback)")
         ctx = get_context(audio.device, self.num_mels)
-        audio = audio.contiguous().float()
+        audio = audio.contiguous() if audio.dtype == torch.int16 else audio.contiguous().float()   # int16 PCM goes to the kernel as is
         if audio.dim() == 1:
             audio = audio.unsqueeze(0)
         return ctx.frontend(audio, fb.to(audio.device), "mels" if mels_only else "stacked")

@@ -36,7 +36,9 @@ enum {
   HOWL_FE_TIME_MAJOR = 0x1, /* out = [B, F, M] log-mel only: the [B,1,F,M] tensor Res8.forward builds at cnn.py:128-129 */
   HOWL_FE_MELS_ONLY = 0x2,  /* out = [B, M, F]   (StandardAudioTransform(..., mels_only=True), transform.py:276-277) */
   HOWL_FE_STACKED = 0x4,    /* out = [B, 3, M, F] log-mel, delta, delta-delta (transform.py:278-280) */
-  HOWL_FE_ZMUV = 0x10       /* apply (x - mean) / std afterwards (ZmuvTransform.forward, operator.py:145-146) */
+  HOWL_FE_ZMUV = 0x10,      /* apply (x - mean) / std afterwards (ZmuvTransform.forward, operator.py:145-146) */
+  HOWL_FE_PCM_I16 = 0x40    /* `pcm` points to int16 samples (the wav files' own format); K1 converts with x / 32768 exactly as the
+                               reference's loader does (howl/utils/audio_utils.py / soundfile), halving the bytes shipped and read */
 };
 
 typedef struct howl_ctx howl_ctx_t;
@@ -61,7 +63,9 @@ int64_t howl_b200_launch_count(const howl_ctx_t* ctx);
 /* Options: "conv_engine" = 1 (default, PARITY mode) 45->45 convolutions on tcgen05 tensor cores with bf16x3-split operands
  * and fp32 accumulation (logits within 1e-5 of fp32); 0 = exact-fp32 FFMA kernels; 2 = FAST mode, the same kernels with the
  * low-order bf16 terms skipped (single bf16 x bf16 products, ~3e-3 relative: outside the 1e-4 parity bar, never the default). */
-/* "fb_unchanged" = 1: one-shot promise that the NEXT frontend / train-step call passes the same filterbank contents as the previous
+/* "pcm_i16" = 1 (persistent): every `pcm` argument of this context -- frontend_fwd and the fused train steps -- is int16 (see
+ * HOWL_FE_PCM_I16).
+ * "fb_unchanged" = 1: one-shot promise that the NEXT frontend / train-step call passes the same filterbank contents as the previous
  * one on this context, so the compact bank + work plan built from it are reused instead of rebuilt (cleared by that call). */
 int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value);
 /* ---- per-launch device timing (CUDA events on the launching stream; used by bench.py's roofline) --------- */
@@ -109,6 +113,15 @@ int howl_b200_to_time_major(howl_ctx_t* ctx, void* stream, const float* x, int64
  * `clips` starting at absolute offset starts[r], at column dst_off[r].  All index arrays [B] i64 on the device. */
 int howl_b200_batch_gather(howl_ctx_t* ctx, void* stream, const float* clips, const int64_t* starts, const int64_t* counts,
                            const int64_t* dst_off, int64_t B, int64_t max_length, float* out);
+
+/* The same gather with the reference's waveform augmentations (howl/data/transform/transform.py:120-231: TimeshiftTransform,
+ * NoiseTransform, DatasetMixer) applied in the same pass, for draws replayed on the host: the time shift is folded into starts / counts;
+ * row r is mixed with bg[bg_starts[r] + j] as x * (1 - alpha[r]) + bg * alpha[r] (alpha f64 [B]; bg_starts[r] < 0: not mixed), then white noise of
+ * strength sigma[r] and salt-and-pepper noise of probability sp_prob[r] are added with the reference's clamps (0: off); the noise itself
+ * comes from an in-kernel Philox4x32-10 keyed by (seed, row, sample).  bg / bg_starts / alpha / sigma / sp_prob may be NULL. */
+int howl_b200_batch_gather_aug(howl_ctx_t* ctx, void* stream, const float* clips, const int64_t* starts, const int64_t* counts,
+                               const int64_t* dst_off, int64_t B, int64_t max_length, const float* bg, const int64_t* bg_starts,
+                               const double* alpha, const float* sigma, const float* sp_prob, uint64_t seed, float* out);
 
 /* ---- res8 ----------------------------------------------------------------------------------- */
 /* Flat parameter layout (state_dict order):

@@ -277,3 +277,44 @@ def test_trainer_epoch_applies_the_reference_augmentations(monkeypatch):
     random.seed(11)
     tr.train_epoch(batches[:1], zmuv=(-1.8, 3.9), augment=False)
     assert random.random() == first
+
+
+def test_device_wave_augmentation_matches_reference_chain_and_noise_statistics():
+    """SURVEY §8f row 3 on the device: (1) mixer + time shift + batchifier fused into one gather kernel reproduce the reference chain's
+    batches bit for bit (tests/golden/augment.npz); (2) the in-kernel Philox noise has the distributions NoiseTransform draws from
+    (N(0, sigma) clamped; +-1 impulses with probability p / 2 each) and respects the final clamp to [-1, 1]."""
+    import howl_b200
+    from howl_b200.batchifier import DeviceFrameBatchifier, DeviceWaveAugmenter
+    from test_host_logic import _batchifier_inputs
+
+    g, clips = _batchifier_inputs()
+    a = dict(np.load(os.path.join(GOLDEN, "augment.npz")))
+    ctx = howl_b200.Context(DEV, n_mels=40)
+    dev_clips, dev_bg = torch.from_numpy(g["clips"]).to(DEV), torch.from_numpy(a["bg"]).to(DEV)
+    for trial in range(8):
+        random.seed(500 + trial)
+        aug = DeviceWaveAugmenter(DeviceFrameBatchifier(3, positive_sample_prob=[0.5, 0.9, 0.1][trial % 3]), a["bg_lengths"].tolist(), noise=False)
+        audio, labels, lengths = aug(ctx, dev_clips, clips * 2, dev_bg)
+        assert np.array_equal(audio.cpu().numpy(), a[f"t{trial}.audio"])
+        assert np.array_equal(labels.cpu().numpy(), a[f"t{trial}.labels"]) and np.array_equal(lengths.cpu().numpy(), a[f"t{trial}.lengths"])
+    # ---- noise statistics on a constant signal
+    B, T = 8, 200000
+    base = torch.full((B * T,), 0.25, device=DEV)
+    starts = torch.arange(B, device=DEV) * T
+    counts, dst = torch.full((B,), T, dtype=torch.int64, device=DEV), torch.zeros(B, dtype=torch.int64, device=DEV)
+    sigma = torch.tensor([0.0, 0.001, 0.01, 0.1, 0.0, 0.0, 0.5, 0.05], device=DEV)
+    sp = torch.tensor([0.0, 0.0, 0.0, 0.0, 0.01, 0.2, 0.0, 0.1], device=DEV)
+    out = ctx.batch_gather_aug(base, starts, counts, dst, T, sigma=sigma, sp_prob=sp, seed=7).cpu()
+    other = ctx.batch_gather_aug(base, starts, counts, dst, T, sigma=sigma, sp_prob=sp, seed=8).cpu()
+    assert torch.equal(out[0], torch.full((T,), 0.25)) and not torch.equal(out[1], other[1]) and out.abs().max() <= 1.0
+    for r in (1, 2, 3):
+        d = out[r] - 0.25
+        assert abs(d.mean().item()) < 4 * sigma[r].item() / T ** 0.5 and abs(d.std().item() / sigma[r].item() - 1) < 0.02
+    for r in (4, 5):
+        d = out[r] - 0.25
+        up, down = (d > 0.5).float().mean().item(), (d < -0.5).float().mean().item()
+        p = sp[r].item() / 2
+        assert abs(up - p * (1 - p)) < 5 * (p / T) ** 0.5 and abs(down - p * (1 - p)) < 5 * (p / T) ** 0.5
+        assert out[r].max() <= 1.0 and out[r].min() >= -0.75 - 1e-6            # 0.25 + 1 clamps to 1, 0.25 - 1 = -0.75
+    assert (out[6] == 1.0).any() and (out[6] == -1.0).any()                    # large white noise is clamped at both ends
+    ctx.close()

@@ -136,6 +136,21 @@ def test_frontend_filterbank_plan_cache(ctx):
     np.testing.assert_allclose(ctx.frontend(pcm_d, other, "mels").cpu().numpy(), want, rtol=RTOL, atol=ATOL)
 
 
+def test_frontend_int16_pcm(ctx):
+    """int16 PCM at the boundary (the wav files' own format, half the bytes): K1's x / 32768 is the loader's conversion, so the features
+    equal those of the float path on the converted samples bit for bit, for aligned and unaligned clip lengths."""
+    fb = O.mel_filterbank(40).to(DEV)
+    for T in (16000, 8000, 12345, 4567):
+        g = torch.Generator().manual_seed(T)
+        i16 = torch.randint(-20000, 20000, (5, T), generator=g, dtype=torch.int16)
+        f32 = i16.to(torch.float32) / 32768.0
+        a = ctx.frontend(i16.to(DEV), fb, "time_major", zmuv=(-1.7, 3.9))
+        b = ctx.frontend(f32.to(DEV), fb, "time_major", zmuv=(-1.7, 3.9))
+        assert torch.equal(a, b)
+        np.testing.assert_allclose(ctx.frontend(i16.to(DEV), fb, "stacked").cpu().numpy(), O.standard_audio_transform_f32(f32, fb.cpu()).numpy(),
+                                   rtol=RTOL, atol=ATOL)
+
+
 def test_frontend_rejects_short_clip(ctx):
     import howl_b200
 

@@ -163,6 +163,32 @@ def test_frame_batchifier_plan_is_bit_exact_with_reference():
         assert np.array_equal(out, g[f"t{trial}.audio"])
 
 
+def test_wave_augmenter_replays_the_reference_chain():
+    """DatasetMixer -> TimeshiftTransform -> batchifier of the reference on a seeded global `random`
+    (tests/golden/augment.npz) against the host plan of DeviceWaveAugmenter, with the fused gather emulated in numpy (two fp32
+    roundings and an add for the mix, as torch computes it): bit exact, and the random stream ends at the same position."""
+    import random
+
+    from howl_b200.batchifier import DeviceFrameBatchifier, DeviceWaveAugmenter
+
+    g, clips = _batchifier_inputs()
+    a = dict(np.load(os.path.join(GOLDEN, "augment.npz")))
+    for trial in range(8):
+        random.seed(500 + trial)
+        aug = DeviceWaveAugmenter(DeviceFrameBatchifier(3, positive_sample_prob=[0.5, 0.9, 0.1][trial % 3]), a["bg_lengths"].tolist(), noise=False)
+        starts, counts, dst, labels, max_length, bg_starts, alpha, sigma, sp = aug.plan(clips * 2)
+        assert random.random() == float(a[f"t{trial}.next_draw"])
+        out = np.zeros((len(starts), max_length), np.float32)
+        for r in range(len(starts)):
+            x = g["clips"][starts[r]:starts[r] + counts[r]]
+            if bg_starts[r] >= 0:
+                x = x * np.float32(1.0 - alpha[r]) + a["bg"][bg_starts[r]:bg_starts[r] + counts[r]] * np.float32(alpha[r])
+            out[r, dst[r]:dst[r] + counts[r]] = x
+        assert np.array_equal(labels, a[f"t{trial}.labels"]) and np.array_equal(counts, a[f"t{trial}.lengths"])
+        assert np.array_equal(out, a[f"t{trial}.audio"]), trial
+        assert not sigma.any() and not sp.any()
+
+
 def test_honkling_export_matches_reference_script():
     """§8f row 4: byte-identical to training/run/export_honkling.py on the shipped hey-fire-fox checkpoint (golden: SHA-256)."""
     import hashlib
