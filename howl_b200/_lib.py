@@ -43,6 +43,8 @@ SIGNATURES: Dict[str, tuple] = {
     "howl_b200_debug_mbn_workspace_bytes": (_i64, [_i64, C.c_int, C.c_int]),
     "howl_b200_debug_mbn_gemm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz]),
     "howl_b200_debug_mbn_wgrad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _sz]),
+    "howl_b200_mobilenet_debug_mask_bytes": (_i64, [_i64, _i32, _i32]),
+    "howl_b200_mobilenet_debug_masks": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _sz, _vp]),
     "howl_b200_res8_debug_masks": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
     "howl_b200_profile_begin": (C.c_int, [_vp, _vp]),
     "howl_b200_profile_end": (C.c_int, [_vp, _vp, _sz, _vp, _i32]),

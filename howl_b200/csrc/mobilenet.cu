@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "mbn_common.cuh"
+#include "../../include/howl_b200_debug.h"
 
 #define MB_EPS 1e-5
 #define MB_MOM 0.1
@@ -1201,4 +1202,71 @@ extern "C" int howl_b200_mobilenet_train_step(howl_ctx_t* ctx, void* stream, con
   if (rc) return rc;
   const int64_t np = howl_b200_mobilenet_param_count(num_labels);
   return howl_b200_adamw(ctx, stream, params, grads, exp_avg, exp_avg_sq, np, step, lr, 0.9f, 0.999f, 1e-8f, weight_decay);
+}
+
+// ---------------------------------------------------------------------------------------------
+// test hook (include/howl_b200_debug.h): the activation decisions the backward takes, for the mask-forced gradient oracle
+// ---------------------------------------------------------------------------------------------
+__global__ void mbn_debug_mask_kernel(const uint4* __restrict__ raw, const float* __restrict__ bn, int c, int cp, int64_t rows, uint8_t* __restrict__ out) {
+  const int64_t n = rows * c;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / c;
+    const int ch = (int)(i - row * c);
+    const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(raw + mbn_vec(row, ch >> 3, cp / 8));
+    const float y = fmaf(__bfloat162float(v[ch & 7]), bn[ch], bn[cp + ch]);
+    out[i] = (y > 0.f && y < 6.f) ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) mbn_debug_stem_mask_kernel(const MbStemArgs a, uint8_t* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int64_t b = blockIdx.x;
+  const int pitch = mb_stem_stage(a, b, smem);
+  for (int i = threadIdx.x; i < 3 * a.H * a.Wc; i += blockDim.x) {
+    const int c = i / (a.H * a.Wc), rem = i - c * a.H * a.Wc, y = rem / a.Wc, x = rem - y * a.Wc;
+    uint8_t m = 0;
+    if ((x >> 1) < a.Wp) {
+      const float sc = a.bn[c], sh = a.bn[16 + c];
+      const float n = fmaf(mb_stem_conv(smem, pitch, a.w + c * 9, a.bias[c], y, x), sc, sh);
+      const float other = fmaf(mb_stem_conv(smem, pitch, a.w + c * 9, a.bias[c], y, x ^ 1), sc, sh);
+      const float r = fmaxf(n, 0.f), ro = fmaxf(other, 0.f);
+      const bool win = (x & 1) ? (r > ro) : (r >= ro);
+      m = (win && n > 0.f) ? 1 : 0;
+    }
+    out[b * 3 * a.H * a.Wc + i] = m;
+  }
+}
+
+extern "C" int64_t howl_b200_mobilenet_debug_mask_bytes(int64_t B, int32_t frames, int32_t n_mels) {
+  const MbNet net = mb_build(n_mels, frames, 1);
+  int64_t n = B * 3 * n_mels * (frames + 4);
+  for (size_t i = 1; i < net.convs.size(); ++i)
+    if (net.convs[i].act) n += B * net.convs[i].hout * net.convs[i].wout * net.convs[i].cout;
+  return n;
+}
+
+extern "C" int howl_b200_mobilenet_debug_masks(howl_ctx_t* ctx, void* stream, const float* feats, const float* params, int64_t B, int32_t frames,
+                                               int32_t n_mels, int32_t num_labels, const void* workspace, size_t workspace_bytes, uint8_t* out) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, feats && params && out, HOWL_E_INVALID, "mobilenet_debug_masks: null pointer");
+  MbNet net;
+  MbWs ws;
+  int rc = mb_check(ctx, B, frames, n_mels, num_labels, workspace, workspace_bytes, &net, &ws);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  MbStemArgs a = mb_stem_args(net, ws, feats, params, B);
+  const size_t sm = sizeof(float) * ((size_t)(a.H + 2) * (a.W + 8) + 3 * (size_t)a.H * a.Wp);
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_debug_stem_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  mbn_debug_stem_mask_kernel<<<(unsigned)B, 256, sm, st>>>(a, out);
+  HOWL_LAUNCHED(ctx, "mbn_debug_stem_mask");
+  uint8_t* p = out + B * 3 * a.H * a.Wc;
+  for (size_t i = 1; i < net.convs.size(); ++i) {
+    const MbConv& c = net.convs[i];
+    if (!c.act) continue;
+    const int64_t rows = B * c.hout * c.wout;
+    mbn_debug_mask_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(reinterpret_cast<const uint4*>(ws.raw[i]), ws.bn[i], c.cout, mbn_pad16(c.cout), rows, p);
+    HOWL_LAUNCHED(ctx, "mbn_debug_mask");
+    p += rows * c.cout;
+  }
+  return HOWL_OK;
 }

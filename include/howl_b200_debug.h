@@ -44,6 +44,14 @@ int howl_b200_debug_mbn_gemm(howl_ctx_t* ctx, void* stream, const float* A, cons
 int howl_b200_debug_mbn_wgrad(howl_ctx_t* ctx, void* stream, const float* dC, const float* A, float* dW, int64_t M, int32_t N,
                               int32_t K, void* workspace, size_t workspace_bytes);
 
+/* Test hook for the mask-forced gradient oracle of the MobileNetV2 path: the activation decisions the backward of the forward kept in
+ * `workspace` takes, as bytes (1 = gradient passes), concatenated:
+ *   stem      [B, 3, n_mels, frames + 4]   conv output that wins its (1,2) max-pooling pair AND is positive (ReLU)
+ *   per conv with ReLU6, in network order: [B * hout * wout, cout] (NHWC)   0 < BatchNorm output < 6 */
+int64_t howl_b200_mobilenet_debug_mask_bytes(int64_t B, int32_t frames, int32_t n_mels);
+int howl_b200_mobilenet_debug_masks(howl_ctx_t* ctx, void* stream, const float* feats, const float* params, int64_t B, int32_t frames,
+                                    int32_t n_mels, int32_t num_labels, const void* workspace, size_t workspace_bytes, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -537,7 +537,7 @@ def _ste_bf16(t: torch.Tensor) -> torch.Tensor:
     return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
 
 
-def mobilenet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], train: bool = False, bf16: bool = False) -> torch.Tensor:
+def mobilenet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], train: bool = False, bf16: bool = False, masks=None) -> torch.Tensor:
     """x: [B, C>=1, 40, F] stacked features (only the log-mel channel is used, cnn.py:27); returns logits [B, L].
     Dropout of the classifier is the identity (eval) -- the training-mode restatement is deterministic up to dropout.
 
@@ -551,9 +551,25 @@ def mobilenet_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], train: bool 
 
     r = _ste_bf16 if bf16 else (lambda t: t)
     relu6 = lambda t: torch.clamp(t, 0.0, 6.0)
+    if masks is not None:
+        # mask-forced activations (as res8_forward_masked): the forward VALUES are the exact ones, the DERIVATIVES are the given 0/1
+        # decisions -- ``masks`` = [stem route [B,3,H,W+4], then one [B,C,H,W] mask per ReLU6 in network order].  With the decisions the
+        # implementation under test took, this graph's gradient is the one it must produce, free of activation-boundary flips.
+        it = iter(masks[1:])
+
+        def relu6(t):   # noqa: F811
+            m = next(it).to(t.dtype)
+            return t * m + (torch.clamp(t, 0.0, 6.0) - t * m).detach()
     x = x[:, :1]
     x = F.conv2d(x, sd["downsample.0.weight"], sd["downsample.0.bias"], padding=(1, 3))
-    x = r(F.max_pool2d(torch.relu(_bn(x, sd, "downsample.1", train)), (1, 2)))
+    n0 = _bn(x, sd, "downsample.1", train)
+    pooled = F.max_pool2d(torch.relu(n0), (1, 2))
+    if masks is not None:
+        routed = n0 * masks[0].to(n0.dtype)
+        wp = routed.shape[-1] // 2
+        routed = routed[..., :2 * wp].reshape(*routed.shape[:-1], wp, 2).sum(-1)
+        pooled = routed + (pooled - routed).detach()
+    x = r(pooled)
     f = "model.features."
     x = relu6(_bn(r(F.conv2d(x, r(sd[f + "0.0.weight"]), None, stride=2, padding=1)), sd, f + "0.1", train))
     for idx, inp, oup, stride, t in mobilenet_plan():
@@ -575,14 +591,15 @@ def mobilenet_param_names(sd: Dict[str, torch.Tensor]) -> List[str]:
     return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))]
 
 
-def mobilenet_grads(x: torch.Tensor, labels: torch.Tensor, sd: Dict[str, torch.Tensor], dtype=torch.float32, bf16: bool = False):
+def mobilenet_grads(x: torch.Tensor, labels: torch.Tensor, sd: Dict[str, torch.Tensor], dtype=torch.float32, bf16: bool = False, masks=None):
     """CrossEntropyLoss(mean) + autograd through ``mobilenet_forward`` in train mode (batch statistics, dropout off):
     -> (loss, logits, {name: grad}).  ``bf16``: the bf16-storage restatement of the forward (gradients themselves stay fp32)."""
-    leaves = {k: (v.to(dtype).requires_grad_(True) if k in set(mobilenet_param_names(sd)) else v) for k, v in sd.items()}
-    logits = mobilenet_forward(x.to(dtype), leaves, train=True, bf16=bf16)
+    trainable = set(mobilenet_param_names(sd))
+    leaves = {k: (v.detach().clone().to(dtype).requires_grad_(True) if k in trainable else v) for k, v in sd.items()}
+    logits = mobilenet_forward(x.to(dtype), leaves, train=True, bf16=bf16, masks=masks)
     loss = F.cross_entropy(logits, labels)
     loss.backward()
-    return loss.detach(), logits.detach(), {k: leaves[k].grad.detach() for k in mobilenet_param_names(sd)}
+    return loss.detach(), logits.detach(), {k: leaves[k].grad.detach().clone() for k in mobilenet_param_names(sd)}
 
 
 # =====================================================================================================

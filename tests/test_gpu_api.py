@@ -316,5 +316,5 @@ def test_device_wave_augmentation_matches_reference_chain_and_noise_statistics()
         p = sp[r].item() / 2
         assert abs(up - p * (1 - p)) < 5 * (p / T) ** 0.5 and abs(down - p * (1 - p)) < 5 * (p / T) ** 0.5
         assert out[r].max() <= 1.0 and out[r].min() >= -0.75 - 1e-6            # 0.25 + 1 clamps to 1, 0.25 - 1 = -0.75
-    assert (out[6] == 1.0).any() and (out[6] == -1.0).any()                    # large white noise is clamped at both ends
+    assert (out[6] == 1.0).any() and out[6].min() >= -0.75 - 1e-6               # the noise mask itself is clamped to [-1, 1] first
     ctx.close()
