@@ -89,7 +89,8 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--global-batch", type=int, default=32768, help="--scaling strong: the fixed global batch (configs[4])")
     ap.add_argument("--cpu-sample", type=int, default=256, help="utterances per CPU-baseline step")
-    ap.add_argument("--pcm16", action="store_true", help="e2e leg ships int16 PCM (the loader's on-disk format) instead of fp32")
+    ap.add_argument("--pcm32", action="store_true", help="e2e leg ships float32 PCM instead of int16 (the wav files' own sample format, "
+                                                        "which the C ABI accepts directly: K1 converts with x / 32768 like the reference's loader)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-library-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -99,6 +100,7 @@ def parse():
     a.seconds = spec["seconds"] if a.seconds is None else a.seconds
     a.samples = int(round(a.seconds * SR))
     a.labels = spec["labels"]
+    a.pcm16 = not a.pcm32
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.scaling == "strong":
         if a.global_batch % world:
@@ -174,20 +176,38 @@ def oracle_step_factory(model, batch, samples, labels, device="cpu"):
     fb = O.mel_filterbank(N_MELS).to(dev)
     zm, zm2 = torch.tensor([ZMEAN], device=dev), torch.tensor([ZMEAN ** 2 + ZSTD ** 2], device=dev)
     state = {"step": 0, "hc": None}
-    if model == "res8":
+    if model == "mobilenet":
+        from howl_b200 import mobilenet as mb   # host-side shapes / initialiser only (no CUDA)
+
+        flat, sd, off = mb.init_flat(labels, 0), {}, 0
+        for name, shape in mb.param_shapes(labels):
+            n = int(torch.tensor(shape).prod())
+            sd[name] = flat[off:off + n].view(shape).clone().to(dev)
+            off += n
+        for _, _, bnn, shape, _ in mb.layer_plan(labels):
+            sd[bnn + ".running_mean"], sd[bnn + ".running_var"] = torch.zeros(shape[0], device=dev), torch.ones(shape[0], device=dev)
+        params = {k: sd[k] for k in O.mobilenet_param_names(sd)}
+    elif model == "res8":
         params = {k: v.to(dev) for k, v in O.res8_init(labels, seed=0).items()}
         bn = {k: v.to(dev) for k, v in O.res8_bn_init().items()}
     else:
         params = {k: v.to(dev) for k, v in O.lstm_init(labels, seed=0).items()}
         steps = (samples - N_FFT) // HOP + 1
-        lengths = torch.full((batch,), steps, dtype=torch.int64)
+        lengths = torch.full((batch,), steps, dtype=torch.int64, device=dev)
     m = {k: torch.zeros_like(p) for k, p in params.items()}
     v = {k: torch.zeros_like(p) for k, p in params.items()}
 
     def step():
         state["step"] += 1
         feats = O.hot_path_features(inputs[0], fb, zm, zm2)
-        if model == "res8":
+        if model == "mobilenet":
+            with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=state.get("autocast", False)):
+                loss, _, grads = O.mobilenet_grads(feats, inputs[1], sd)
+            with torch.no_grad():
+                O.adamw_step(params, grads, m, v, state["step"], LR, WD)
+                for k in params:
+                    sd[k] = params[k]
+        elif model == "res8":
             loss, _, _ = O.res8_train_step(feats, inputs[1], params, bn, m, v, state["step"], LR, WD)
         elif model == "lstm":
             loss, _, _ = O.lstm_train_step(feats, inputs[1], lengths, params, m, v, state["step"], LR, WD)
@@ -197,6 +217,7 @@ def oracle_step_factory(model, batch, samples, labels, device="cpu"):
             state["hc"] = tuple(t.detach() for t in hc)
         return loss
 
+    step.state = state
     return step
 
 
@@ -238,6 +259,7 @@ def run_gpu_library(model, batch, samples, labels, dev, steps=5, warmup=2):
             torch.backends.cudnn.allow_tf32 = tf32
             torch.backends.cuda.matmul.allow_tf32 = tf32
             step = oracle_step_factory(model, batch, samples, labels, device=str(dev))
+            step.state["autocast"] = bool(tf32 and model == "mobilenet")        # mobilenet: the "on" leg is torch's bf16 autocast
             for _ in range(warmup):
                 step()
             torch.cuda.synchronize(dev)
@@ -254,7 +276,8 @@ def run_gpu_library(model, batch, samples, labels, dev, steps=5, warmup=2):
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     out["what"] = (f"oracle graph of the same train step on cuda:0 through stock torch {torch.__version__} (cuFFT / cuDNN / cuBLAS, eager "
-                   f"autograd), batch {batch}, {steps} steps after {warmup} warm-up; PCM resident on the device")
+                   f"autograd), batch {batch}, {steps} steps after {warmup} warm-up; PCM resident on the device"
+                   + ("; tf32_on = TF32 convolutions + torch.autocast(bfloat16)" if model == "mobilenet" else ""))
     return out
 
 
@@ -267,9 +290,6 @@ def workload_text(a, world):
 def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
-    if a.model == "mobilenet":
-        print(json.dumps({"impl": "reference", "unavailable": "no CPU oracle train step for mobilenet (forward oracle only)"}), flush=True)
         return
     steps, warmup = max(1, a.steps), max(0, a.warmup)
     sample = min(a.cpu_sample, a.batch)
@@ -313,7 +333,7 @@ def family_of(name):
         return "conv3x3"
     if name.startswith(("lstm_", "ctc")):
         return "lstm"
-    if name.startswith("mbn_gemm"):
+    if name.startswith(("mbn_gemm", "mbn_wgrad")):
         return "mbn_gemm"
     return name
 
@@ -441,7 +461,7 @@ def main_ours(a):
         else:
             key = "lstm" if a.model in ("lstm", "seq-lstm") else "mbn_gemm"
             cf = fam.get(key, {"ms": ms_step, "launches": 1, "kernels": []})
-            ach = B * alg["flop"] / (cf["ms"] / 1e3) / 1e12
+            ach = B * alg.get("gemm_flop", alg["flop"]) / (cf["ms"] / 1e3) / 1e12
             roofline = {"bound": "tensor", "kernel": f"{key} family ({cf['launches']} launches/step)", "achieved": ach, "peak": tensor_peak,
                         "unit": "TFLOP/s", "frac": ach / tensor_peak, "traffic": None, "family_ms_per_step": cf["ms"],
                         "peak_source": peaks["source"] + ", dense bf16 cuBLAS sustained"}
@@ -455,14 +475,14 @@ def main_ours(a):
             roofline["frontend"] = {"bound": "hbm", "ms": fe["ms"], "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"],
                                     "frac": gbs / peaks["hbm_gbs"], "traffic": traffic.get("frontend")}
         cpu = None
-        if not a.no_cpu_baseline and world == 1 and a.model != "mobilenet":
+        if not a.no_cpu_baseline and world == 1:
             sample = min(a.cpu_sample, B)
             v, ms, cores = run_cpu(a.model, sample, a.samples, a.labels, 10, 2)
             cpu = {"value": v, "unit": "utterances/s", "cores": cores, "kind": "port",
                    "sample": f"10 steps x {sample} utterances of the same workload after 2 warm-up (oracle port, torch CPU), "
                              f"{cores} intra-op threads of {os.cpu_count()} host cores"}
         gpu_lib = None
-        if not a.no_gpu_library_baseline and world == 1 and a.model != "mobilenet":
+        if not a.no_gpu_library_baseline and world == 1:
             del step_obj
             torch.cuda.empty_cache()
             try:

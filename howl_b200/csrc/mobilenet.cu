@@ -258,29 +258,33 @@ struct MbDwArgs {
   int c, cp, hin, win, hout, wout, stride;
 };
 
-__global__ void __launch_bounds__(256) mbn_dw_fwd_kernel(const MbDwArgs a) {
+__global__ void __launch_bounds__(256, 3) mbn_dw_fwd_kernel(const MbDwArgs a) {
   const int chunk = blockIdx.y, c8 = a.cp / 8;
-  float sc[8], sh[8], w[8][9];
+  __shared__ __align__(16) float s_w[9][8];       // this chunk's taps: read as warp-wide broadcasts (keeps 72 registers free -> 3 CTAs / SM)
+  if (threadIdx.x < 72) {
+    const int k = threadIdx.x >> 3, c = chunk * 8 + (threadIdx.x & 7);
+    s_w[k][threadIdx.x & 7] = c < a.c ? a.w[c * 9 + k] : 0.f;
+  }
+  float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = chunk * 8 + j;
     sc[j] = a.bn_in[c];
     sh[j] = a.bn_in[a.cp + c];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) w[j][k] = c < a.c ? a.w[c * 9 + k] : 0.f;
   }
-  const int64_t rows = a.B * a.hout * a.wout, rows_pad = mbn_tiles(rows) * MBN_TILE;
+  __syncthreads();
+  const int rows = (int)(a.B * a.hout * a.wout), rows_pad = (int)(mbn_tiles(rows) * MBN_TILE);     // the host checks rows_pad < 2^31
   const int hw_o = a.hout * a.wout, hw_i = a.hin * a.win;
   float part[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) part[i] = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows_pad; r += (int64_t)gridDim.x * blockDim.x) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows_pad; r += gridDim.x * blockDim.x) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (r < rows) {
-      const int64_t b = r / hw_o;
-      const int p = (int)(r - b * hw_o), yo = p / a.wout, xo = p - yo * a.wout;
+      const int b = r / hw_o;
+      const int p = r - b * hw_o, yo = p / a.wout, xo = p - yo * a.wout;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int yi = yo * a.stride - 1 + ky;
@@ -291,10 +295,12 @@ __global__ void __launch_bounds__(256) mbn_dw_fwd_kernel(const MbDwArgs a) {
           if (xi < 0 || xi >= a.win) continue;
           float v[8];
           mb_unpack(__ldg(a.in + mbn_vec(b * hw_i + yi * a.win + xi, chunk, c8)), v);
+          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][0]), w1 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][4]);
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float x = fminf(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f), 6.f);
-            acc[j] = fmaf(x, w[j][ky * 3 + kx], acc[j]);
+            acc[j] = fmaf(x, w[j], acc[j]);
           }
         }
       }
@@ -333,22 +339,23 @@ struct MbDwBwdArgs {
   int c, cp, hin, win, hout, wout, stride;
 };
 
-__global__ void __launch_bounds__(256) mbn_dw_bwd_data_kernel(const MbDwBwdArgs a) {
+__global__ void __launch_bounds__(256, 3) mbn_dw_bwd_data_kernel(const MbDwBwdArgs a) {
   const int chunk = blockIdx.y, c8 = a.cp / 8;
-  float w[8][9];
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-#pragma unroll
-    for (int k = 0; k < 9; ++k) w[j][k] = (chunk * 8 + j) < a.c ? a.w[(chunk * 8 + j) * 9 + k] : 0.f;
-  const int64_t rows = a.B * a.hin * a.win, rows_pad = mbn_tiles(rows) * MBN_TILE;
+  __shared__ __align__(16) float s_w[9][8];
+  if (threadIdx.x < 72) {
+    const int k = threadIdx.x >> 3, c = chunk * 8 + (threadIdx.x & 7);
+    s_w[k][threadIdx.x & 7] = c < a.c ? a.w[c * 9 + k] : 0.f;
+  }
+  __syncthreads();
+  const int rows = (int)(a.B * a.hin * a.win), rows_pad = (int)(mbn_tiles(rows) * MBN_TILE);
   const int hw_o = a.hout * a.wout, hw_i = a.hin * a.win;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows_pad; r += (int64_t)gridDim.x * blockDim.x) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows_pad; r += gridDim.x * blockDim.x) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     if (r < rows) {
-      const int64_t b = r / hw_i;
-      const int p = (int)(r - b * hw_i), yi = p / a.win, xi = p - yi * a.win;
+      const int b = r / hw_i;
+      const int p = r - b * hw_i, yi = p / a.win, xi = p - yi * a.win;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int ty = yi + 1 - ky;
@@ -363,8 +370,10 @@ __global__ void __launch_bounds__(256) mbn_dw_bwd_data_kernel(const MbDwBwdArgs 
           if (xo >= a.wout) continue;
           float v[8];
           mb_unpack(__ldg(a.dout + mbn_vec(b * hw_o + yo * a.wout + xo, chunk, c8)), v);
+          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][0]), w1 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][4]);
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], w[j][ky * 3 + kx], acc[j]);
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], w[j], acc[j]);
         }
       }
     }
@@ -392,11 +401,11 @@ __global__ void __launch_bounds__(256) mbn_dw_bwd_weight_kernel(const MbDwWgArgs
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[j][k] = 0.f;
   }
-  const int64_t rows = a.B * a.hout * a.wout;
+  const int rows = (int)(a.B * a.hout * a.wout);
   const int hw_o = a.hout * a.wout, hw_i = a.hin * a.win;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = r / hw_o;
-    const int p = (int)(r - b * hw_o), yo = p / a.wout, xo = p - yo * a.wout;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const int b = r / hw_o;
+    const int p = r - b * hw_o, yo = p / a.wout, xo = p - yo * a.wout;
     float g[8];
     mb_unpack(__ldg(a.dout + mbn_vec(r, chunk, c8)), g);
 #pragma unroll
@@ -916,6 +925,8 @@ static int mb_check(howl_ctx_t* ctx, int64_t B, int frames, int n_mels, int L, c
   *net = mb_build(n_mels, frames, L);
   *out = mb_carve(*net, const_cast<void*>(ws), B, L);
   HOWL_REQUIRE(ctx, out->bytes <= ws_bytes, HOWL_E_WORKSPACE, "mobilenet: workspace %zu < required %zu", ws_bytes, out->bytes);
+  HOWL_REQUIRE(ctx, B * (int64_t)n_mels * ((frames + 4) / 2) < ((int64_t)1 << 30), HOWL_E_UNSUPPORTED,
+               "mobilenet: batch of %lld clips exceeds the 32-bit row indices of the stencil kernels", (long long)B);
   const size_t stem_smem = sizeof(float) * ((size_t)(n_mels + 2) * (frames + 8) + 3 * (size_t)n_mels * ((frames + 4) / 2));
   HOWL_REQUIRE(ctx, stem_smem <= 200 * 1024, HOWL_E_UNSUPPORTED, "mobilenet: clip of %d frames exceeds the stem's shared-memory tile", frames);
   return HOWL_OK;
