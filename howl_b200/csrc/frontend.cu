@@ -16,13 +16,15 @@
 #define FE_TILE 27          // frames per CTA (81 = 3 tiles for 1 s clips, 41 = 27 + 14 for 0.5 s)
 #define FE_WARPS 9          // one frame per warp at a time: 27 = 3 x 9
 #define FE_THREADS (FE_WARPS * 32)
+#define FE_PART 272         // floats of per-warp scratch: FE_ENT_SMEM partial sums, or the 257 power bins in the dense fallback
 #define FE_ENT_SMEM 256     // mel entries kept in shared memory (standard 40-mel bank: ~100, 80 mels: ~170); the rest is read from global
 #define FE_LOG_EPS 1e-7f
 
 // Sparse mel contraction, organised by BIN BLOCKS: the FFT below leaves lane L of a warp with the power of the 8 consecutive bins
 // [8 * br5(L), 8 * br5(L) + 8) in registers, so the filterbank is cut into "entries" (block, filter m, the 8 weights fb[8 blk + i][m])
 // for every (block, filter) pair with a non-zero weight.  A lane walks the entries of its block -- 8 FMAs and one shared-memory
-// atomic add per entry -- and bin 256 (Nyquist) has its own (filter, weight) list.  Built on the device from any dense [257, M] bank
+// store of the partial sum per entry; afterwards lane m gathers the partial sums of filter m's entries (no shared-memory atomics: fp32
+// atomicAdd on shared memory is a compare-and-swap spin loop) -- and bin 256 (Nyquist) has its own (filter, weight) list.  Built on the device from any dense [257, M] bank
 // (VTLP-warped ones included), rebuilt only when the bank changes.
 struct FeEntry {
   int m;
@@ -33,11 +35,15 @@ struct FeBank {
   int ny_count;             // filters with a non-zero Nyquist weight
   int ny_m[HOWL_MAX_MELS];
   float ny_w[HOWL_MAX_MELS];
+  float ny_dense[HOWL_MAX_MELS];      // Nyquist weight of every filter (0 if none)
+  int filt_off[HOWL_MAX_MELS + 1];    // entries of filter m (one per block it overlaps): filt_idx[filt_off[m] .. filt_off[m + 1])
+  int filt_idx[32 * HOWL_MAX_MELS];
 };
 #define FE_ENT_WORDS 9
 
 struct FeParams {
   const float* pcm;
+  const float* fb;        // dense [257, M] bank (only read by the fallback for banks with more than FE_ENT_SMEM entries)
   const FeBank* bank;
   const float* ent;       // [n_entries][9] words: m (as int bits), w[8]
   const float* window;
@@ -59,28 +65,41 @@ struct FeParams {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) fb_compact_kernel(const float* __restrict__ fb, int M, FeBank* __restrict__ bank,
                                                           float* __restrict__ ent) {
-  __shared__ int s_cnt[33];
-  __shared__ int s_off[34];
+  __shared__ unsigned char s_nz[32][HOWL_MAX_MELS];     // (block, filter) has a non-zero weight
+  __shared__ short s_ent[32][HOWL_MAX_MELS];            // its entry index
+  __shared__ int s_off[33];
+  __shared__ int s_fcnt[HOWL_MAX_MELS + 1];
   const int tid = threadIdx.x;
-  if (tid < 33) s_cnt[tid] = 0;
-  __syncthreads();
-  const int pairs = 32 * M;
-  // pass 1: count the non-empty pairs of every block
-  for (int pidx = tid; pidx < pairs; pidx += blockDim.x) {
+  for (int pidx = tid; pidx < 32 * M; pidx += blockDim.x) {
     const int blk = pidx / M, m = pidx - blk * M;
     bool nz = false;
     for (int i = 0; i < 8; ++i) nz |= fb[(8 * blk + i) * M + m] != 0.f;
-    if (nz) atomicAdd(&s_cnt[blk], 1);
+    s_nz[blk][m] = nz ? 1 : 0;
+  }
+  __syncthreads();
+  if (tid < 32) {            // rank of every non-empty pair inside its block (entries of a block are in filter order)
+    int n = 0;
+    for (int m = 0; m < M; ++m) {
+      s_ent[tid][m] = (short)n;
+      n += s_nz[tid][m];
+    }
+    s_off[tid + 1] = n;      // count for now
+  }
+  if (tid >= 64 && tid < 64 + M) {
+    const int m = tid - 64;
+    int n = 0;
+    for (int blk = 0; blk < 32; ++blk) n += s_nz[blk][m];
+    s_fcnt[m + 1] = n;
+    bank->ny_dense[m] = fb[256 * M + m];
   }
   __syncthreads();
   if (tid == 0) {
-    int acc = 0;
-    for (int blk = 0; blk < 32; ++blk) {
-      s_off[blk] = acc;
-      acc += s_cnt[blk];
-    }
-    s_off[32] = acc;
+    s_off[0] = 0;
+    for (int blk = 0; blk < 32; ++blk) s_off[blk + 1] += s_off[blk];
     for (int blk = 0; blk <= 32; ++blk) bank->ent_off[blk] = s_off[blk];
+    s_fcnt[0] = 0;
+    for (int m = 0; m < M; ++m) s_fcnt[m + 1] += s_fcnt[m];
+    for (int m = 0; m <= M; ++m) bank->filt_off[m] = s_fcnt[m];
     int n = 0;
     for (int m = 0; m < M; ++m) {
       const float w = fb[256 * M + m];
@@ -93,22 +112,18 @@ __global__ void __launch_bounds__(1024) fb_compact_kernel(const float* __restric
     bank->ny_count = n;
   }
   __syncthreads();
-  // pass 2: one thread per block writes its entries in filter order (deterministic layout)
-  if (tid < 32) {
-    const int blk = tid;
-    int e = s_off[blk];
-    for (int m = 0; m < M; ++m) {
-      float w[8];
-      bool nz = false;
-      for (int i = 0; i < 8; ++i) {
-        w[i] = fb[(8 * blk + i) * M + m];
-        nz |= w[i] != 0.f;
-      }
-      if (!nz) continue;
-      ent[e * FE_ENT_WORDS] = __int_as_float(m);
-      for (int i = 0; i < 8; ++i) ent[e * FE_ENT_WORDS + 1 + i] = w[i];
-      ++e;
-    }
+  // entries: thread per (block, filter) pair writes its 9 words; per-filter lists: thread per filter
+  for (int pidx = tid; pidx < 32 * M; pidx += blockDim.x) {
+    const int blk = pidx / M, m = pidx - blk * M;
+    if (!s_nz[blk][m]) continue;
+    const int e = s_off[blk] + s_ent[blk][m];
+    ent[e * FE_ENT_WORDS] = __int_as_float(m);
+    for (int i = 0; i < 8; ++i) ent[e * FE_ENT_WORDS + 1 + i] = fb[(8 * blk + i) * M + m];
+  }
+  if (tid < M) {
+    int n = s_fcnt[tid];
+    for (int blk = 0; blk < 32; ++blk)
+      if (s_nz[blk][tid]) bank->filt_idx[n++] = s_off[blk] + s_ent[blk][tid];
   }
 }
 
@@ -197,13 +212,15 @@ __global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams 
   const int span_cap = (FE_TILE - 1) * p.hop + HOWL_NFFT + 8;
   float* s_pcm = reinterpret_cast<float*>(smem_raw);
   float* s_win = s_pcm + ((span_cap + 3) & ~3);
-  float2* s_w512 = reinterpret_cast<float2*>(s_win + HOWL_NFFT);            // [32 lanes][8]
+  float2* s_w512 = reinterpret_cast<float2*>(s_win + HOWL_NFFT);            // [8][32 lanes]
   float* s_ent = reinterpret_cast<float*>(s_w512 + 256);                    // [FE_ENT_SMEM][9]
-  float* s_mel = s_ent + FE_ENT_SMEM * FE_ENT_WORDS;                        // [FE_WARPS][M]
-  float* s_res = s_mel + FE_WARPS * ((p.M + 3) & ~3);                       // [FE_TILE][M]
+  float* s_part = s_ent + FE_ENT_SMEM * FE_ENT_WORDS;                       // [FE_WARPS][FE_ENT_SMEM] partial sums of the entries
+  float* s_res = s_part + FE_WARPS * FE_PART;                               // [FE_TILE][M]
+  int* s_fidx = reinterpret_cast<int*>(s_res + FE_TILE * p.M);              // [FE_ENT_SMEM] entry ids grouped by filter
+  int* s_foff = s_fidx + FE_ENT_SMEM;                                       // [M + 1]
+  float* s_nyw = reinterpret_cast<float*>(s_foff + HOWL_MAX_MELS + 1);      // [M] Nyquist weights
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_off[33];
-  __shared__ int s_ny;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = blockIdx.y;
@@ -245,15 +262,17 @@ __global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams 
   }
   // tables (overlaps the bulk copy)
   for (int i = tid; i < HOWL_NFFT; i += FE_THREADS) s_win[i] = __ldg(p.window + i);
-  for (int i = tid; i < 256; i += FE_THREADS) s_w512[i] = __ldg(p.w512_lane + i);
+  for (int i = tid; i < 256; i += FE_THREADS) s_w512[(i & 7) * 32 + (i >> 3)] = __ldg(p.w512_lane + i);   // [m2][lane]: conflict-free reads
   if (tid < 33) s_off[tid] = p.bank->ent_off[tid];
-  if (tid == 33) s_ny = p.bank->ny_count;
   {
     const int total = min(p.bank->ent_off[32], FE_ENT_SMEM) * FE_ENT_WORDS;
     for (int i = tid; i < total; i += FE_THREADS) s_ent[i] = __ldg(p.ent + i);
   }
-  const int Mp = (p.M + 3) & ~3;
-  for (int i = tid; i < FE_WARPS * Mp; i += FE_THREADS) s_mel[i] = 0.f;
+  const int n_ent = p.bank->ent_off[32];
+  const bool small_bank = n_ent <= FE_ENT_SMEM;        // the usual case: every entry and list fits in shared memory
+  for (int i = tid; i < min(n_ent, FE_ENT_SMEM); i += FE_THREADS) s_fidx[i] = p.bank->filt_idx[i];
+  for (int i = tid; i <= p.M; i += FE_THREADS) s_foff[i] = p.bank->filt_off[i];
+  for (int i = tid; i < p.M; i += FE_THREADS) s_nyw[i] = p.bank->ny_dense[i];
   // per-lane FFT constants
   float2 tw[8], st[3];
 #pragma unroll
@@ -274,7 +293,7 @@ __global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams 
     rtl = p.rects[b * 4 + 3];
   }
   const bool do_zmuv = (p.flags & HOWL_FE_ZMUV) && !(p.flags & HOWL_FE_STACKED);
-  float* mel = s_mel + warp * Mp;
+  float* part = s_part + warp * FE_PART;
   const int e_begin = s_off[blk], e_end = s_off[blk + 1];
 
   for (int fi = warp; fi < nfr; fi += FE_WARPS) {
@@ -315,7 +334,7 @@ __global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams 
       const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
       const float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
       const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);  // d / (2i)
-      const float2 wo = cmul(s_w512[lane * 8 + m2], o);
+      const float2 wo = cmul(s_w512[m2 * 32 + lane], o);
       const float xr = e.x + wo.x, xi = e.y + wo.y;
       pw[m2] = xr * xr + xi * xi;
       if (m2 == 0) {                     // bin 256 from Z[0] (lane 0 only uses it): X[256] = Re Z[0] - Im Z[0]
@@ -323,21 +342,34 @@ __global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams 
         nyq = t * t;
       }
     }
-    // ---- sparse mel contraction: this lane's block entries, partial sums combined in shared memory
-    for (int eidx = e_begin; eidx < e_end; ++eidx) {
-      const float* ep = (eidx < FE_ENT_SMEM) ? s_ent + eidx * FE_ENT_WORDS : p.ent + (size_t)eidx * FE_ENT_WORDS;
-      float acc = 0.f;
+    // ---- sparse mel contraction: this lane's block entries -> one partial sum each; then lane m gathers filter m's entries
+    const float nyq0 = __shfl_sync(0xffffffffu, nyq, 0);
+    if (small_bank) {
+      for (int eidx = e_begin; eidx < e_end; ++eidx) {
+        const float* ep = s_ent + eidx * FE_ENT_WORDS;
+        float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc = fmaf(pw[i], ep[1 + i], acc);
-      atomicAdd(mel + __float_as_int(ep[0]), acc);
-    }
-    if (lane == 0) {
-      for (int i = 0; i < s_ny; ++i) atomicAdd(mel + p.bank->ny_m[i], nyq * p.bank->ny_w[i]);
+        for (int i = 0; i < 8; ++i) acc = fmaf(pw[i], ep[1 + i], acc);
+        part[eidx] = acc;
+      }
+    } else {
+      // banks with more than FE_ENT_SMEM (block, filter) pairs (e.g. 128 mels): the power bins go through shared memory and every
+      // filter walks its dense column
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part[8 * blk + i] = pw[i];
+      if (lane == 0) part[256] = nyq;
     }
     __syncwarp();
     for (int m = lane; m < p.M; m += 32) {
-      float val = logf(mel[m] + FE_LOG_EPS);
-      mel[m] = 0.f;
+      float acc;
+      if (small_bank) {
+        acc = nyq0 * s_nyw[m];
+        for (int k = s_foff[m]; k < s_foff[m + 1]; ++k) acc += part[s_fidx[k]];
+      } else {
+        acc = 0.f;
+        for (int j = 0; j < HOWL_NFREQ; ++j) acc = fmaf(part[j], __ldg(p.fb + (size_t)j * p.M + m), acc);
+      }
+      float val = logf(acc + FE_LOG_EPS);
       if (do_zmuv) val = __fdiv_rn(val - p.zmean, p.zstd);
       if (masked && ((m >= rf0 && m < rf0 + rfl) || (f >= rt0 && f < rt0 + rtl))) val = 0.f;
       s_res[fi * p.M + m] = val;
@@ -467,8 +499,9 @@ size_t howl_fe_smem_bytes(int hop, int M) {
   b += sizeof(float) * HOWL_NFFT;
   b += sizeof(float2) * 256;
   b += sizeof(float) * FE_ENT_SMEM * FE_ENT_WORDS;
-  b += sizeof(float) * FE_WARPS * ((M + 3) & ~3);
+  b += sizeof(float) * FE_WARPS * FE_PART;
   b += sizeof(float) * FE_TILE * M;
+  b += sizeof(int) * (FE_ENT_SMEM + HOWL_MAX_MELS + 1) + sizeof(float) * HOWL_MAX_MELS;
   return howl_align_up(b, 16);
 }
 
@@ -500,7 +533,7 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
   ctx->fb_same_next = 0;
 
   FeParams p;
-  p.pcm = pcm; p.bank = reinterpret_cast<const FeBank*>(ctx->fe_bank); p.ent = ctx->fe_ent;
+  p.pcm = pcm; p.fb = fb; p.bank = reinterpret_cast<const FeBank*>(ctx->fe_bank); p.ent = ctx->fe_ent;
   p.window = ctx->d_window; p.tw_lane = ctx->d_tw_lane; p.tw_stage = ctx->d_tw_stage; p.w512_lane = ctx->d_w512_lane;
   p.rects = rects; p.out = out; p.B = B; p.T = T; p.F = F; p.M = M; p.hop = hop;
   p.zmean = zmuv_mean; p.zstd = zmuv_std; p.flags = flags;

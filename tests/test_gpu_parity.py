@@ -168,6 +168,18 @@ def test_frontend_80_mels(golden):
     np.testing.assert_allclose(out, O.standard_audio_transform_f32(pcm, fb).numpy(), rtol=RTOL, atol=ATOL)
 
 
+def test_frontend_128_mels_dense_bank_fallback():
+    """A bank with more (bin block, filter) pairs than the shared-memory entry table holds takes the dense fallback of K1."""
+    import howl_b200
+
+    c = howl_b200.Context("cuda:0", n_mels=128)
+    pcm, _ = O.synthetic_batch(2, 8000, 4, seed=9)
+    fb = O.mel_filterbank(128)
+    out = c.frontend(pcm.to(DEV), fb.to(DEV), "stacked").cpu().numpy()
+    np.testing.assert_allclose(out, O.standard_audio_transform_f32(pcm, fb).numpy(), rtol=RTOL, atol=ATOL)
+    c.close()
+
+
 def test_sum_sumsq(ctx):
     x = torch.randn(1_000_003, device=DEV)
     sums = torch.zeros(2, dtype=torch.float64, device=DEV)
