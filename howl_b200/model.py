@@ -328,3 +328,7 @@ ACCELERATED = {"res8": Res8, "lstm": SimpleLstm, "seq-lstm": SequentialLstm}
 from .mobilenet import MobileNetClassifier  # noqa: E402  (own module; shares registry.py with this one)
 
 ACCELERATED["mobilenet"] = MobileNetClassifier
+
+from .las import LASClassifier  # noqa: E402  (forward only)
+
+ACCELERATED["las"] = LASClassifier

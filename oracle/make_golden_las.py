@@ -46,7 +46,8 @@ def main():
         ragged = model(feats, lengths.clone())     # LASEncoder mutates nothing, SimpleGru would (`lengths += 4`): clone anyway
     np.savez_compressed(os.path.join(OUT, "las.npz"), pcm=pcm.numpy(), feats=feats.numpy(), lengths=lengths.numpy(),
                         logits_full=full.numpy(), logits_ragged=ragged.numpy(), zmuv_mean=zmuv.mean.numpy(), zmuv_mean2=zmuv.mean2.numpy(),
-                        digest=np.frombuffer(state_dict_digest(sd).encode(), dtype=np.uint8))
+                        digest=np.frombuffer(state_dict_digest(sd).encode(), dtype=np.uint8),
+                        **{"sd." + k: v.numpy() for k, v in sd.items()})      # the checkpoint itself (1.9 MB): the GPU box has no /root/reference
     print("las fixture:", feats.shape, lengths.tolist(), full[0, :3], ragged[4, :3])
 
 
