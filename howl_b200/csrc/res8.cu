@@ -40,7 +40,6 @@ struct R8Ws {
   float* dc;
   float* gu[2];
   // ---- tensor-core engine (null when H is unsupported): everything the convolutions read is in operand format
-  __nv_bfloat16* dcT;              // conv-output gradient, rows = channels (weight-gradient operand)
   __nv_bfloat16* dc2;              // second conv-output-gradient buffer (the fused data gradient reads one and writes the other)
   __nv_bfloat16* uop[R8_LAYERS + 1];   // a0, u1..u6
   uint16_t* mask_bits[3];          // ReLU decisions of the residual layers 2, 4, 6: [B][3 channel groups][R]
@@ -81,7 +80,6 @@ static R8Ws r8_carve(void* base, int64_t B, int H, int L) {
   w.gu[0] = (float*)take(n);
   w.gu[1] = (float*)take(n);
   const bool tc = r8tc_supported(H);
-  w.dcT = tc ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
   w.dc2 = tc ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
   for (int i = 0; i <= R8_LAYERS; ++i) w.uop[i] = tc ? (__nv_bfloat16*)take((size_t)B * r8tc_dcop_bytes(H)) : nullptr;
   for (int i = 0; i < 3; ++i) w.mask_bits[i] = tc ? (uint16_t*)take((size_t)B * 3 * r8tc_dcop_rows(H) * sizeof(uint16_t)) : nullptr;
@@ -1001,7 +999,6 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
       ao.stats = ws.stats_bwd + 5 * 2 * R8_C;
       ao.gu_out = ws.gu[(R8_LAYERS / 2) & 1];
       ao.dc_op = dc[cur];
-      ao.dc_opT = ws.dcT;
       ao.B = B; ao.H = H; ao.count = count;
       rc = r8tc_apply_head(ctx, st, ao);
       if (rc) return rc;
@@ -1011,7 +1008,7 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
       const float* x_mean = (i > 1) ? ws.mean_rstd + (j - 1) * 2 * R8_C : nullptr;
       float* dw = g_wl + (size_t)(i - 1) * R8_KW;
       float* dones = ws.dones + (size_t)(i - 1) * R8_C * 9;
-      rc = r8tc_wgrad(ctx, st, ws.dcT, ws.uop[j], x_mean, x_mean ? x_mean + R8_C : nullptr, dw, dones, B, H);
+      rc = r8tc_wgrad(ctx, st, dc[cur], ws.uop[j], x_mean, x_mean ? x_mean + R8_C : nullptr, dw, dones, B, H);
       if (rc) return rc;
       TcConvCall c;
       memset(&c, 0, sizeof(c));
@@ -1030,7 +1027,6 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
           c.mask_in = ws.mask_bits[j / 2 - 1];
         }
         c.dc_out = dc[cur ^ 1];
-        c.dc_outT = ws.dcT;
       } else {
         c.mode = 2;
         c.out_planar = ws.g;                                // dL/d(a0) = conv1 path + residual path (G_2, added in the epilogue)

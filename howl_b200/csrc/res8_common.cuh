@@ -62,8 +62,7 @@ struct ApplyOpParams {
   const float* mean_rstd;  // [2][45] of layer 6
   const double* stats;     // [2][45] sum(g), sum(g xhat)
   float* gu_out;           // planar G_6 (residual-path gradient of layer 4)
-  __nv_bfloat16* dc_op;
-  __nv_bfloat16* dc_opT;   // the same gradient with rows = channels (weight-gradient A operand), r8tc_dcop_bytes per utterance
+  __nv_bfloat16* dc_op;    // conv-output gradient of layer 6 in operand format
   int64_t B;
   int H;
   double count;
@@ -92,7 +91,6 @@ struct TcConvCall {
   float* gu_out;
   const uint16_t* mask_in;
   __nv_bfloat16* dc_out;
-  __nv_bfloat16* dc_outT;
 };
 int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const TcConvCall& c);
 // BatchNorm-backward coefficients of layer j from the weight gradient of layer j + 1 (see bn_bwd_coef_kernel)
@@ -104,5 +102,5 @@ int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __
 // forward weight operand of one layer with BatchNorm(mean_rstd, or identity when null) folded in (the border-dependent bias
 // rides on the ones channel)
 int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* blk);
-int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_opT, const __nv_bfloat16* x_op, const float* x_mean,
+int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, const __nv_bfloat16* x_op, const float* x_mean,
                const float* x_rstd, float* dw, float* dones, int64_t B, int H);

@@ -39,7 +39,8 @@ int r8tc_dcop_rows(int H) { return r8tc_dcop_rows_dev(H); }
 size_t r8tc_dcop_bytes(int H) { return (size_t)12 * r8tc_dcop_rows(H) * 16; }
 
 static size_t tc_stream_smem(int R) { return (size_t)TC_WBYTES + (size_t)12 * (2 * R + 2 * TC_PAD) * 16 + (48 * 3 + TS_EPI_WARPS * 2 * 16) * 4; }
-static size_t tc_wgrad_smem(int R) { return (size_t)6 * (12 * R * 16 / 4) + 2 * (size_t)12 * (R + 2 * TC_PAD) * 16; }   // TW_DSLOTS quarters + 2 X
+// 3 transposed quarter slots (8-channel groups 144 B apart) + 3 raw quarter slots (planes padded by 16 B) + 2 X buffers + 1 KB overrun pad
+static size_t tc_wgrad_smem(int R) { return (size_t)3 * ((R / 32) * 12 * 144) + (size_t)3 * 12 * ((R / 4) * 16 + 16) + 2 * (size_t)12 * (R + 2 * TC_PAD) * 16 + 1024; }
 bool r8tc_supported(int H) {
   const int R = r8tc_dcop_rows(H);
   return H >= 1 && 2 * R / 128 * 96 <= 512 && tc_stream_smem(R) <= TC_SMEM_LIMIT && tc_wgrad_smem(R) <= TC_SMEM_LIMIT;
@@ -127,14 +128,13 @@ struct TcStreamArgs {
   uint16_t* mask_out;            // [B][3 channel groups][R] ReLU decisions (bit jj = channel 16 * grp + jj), or null
   float* pooled_raw;             // [B][45] per-utterance spatial sums of the output (layer 6 -> head), or null
   // data gradient with the BatchNorm backward of the producer layer j fused into the epilogue (MODE 3):
-  //   G = rstd * (g - m1 - xhat * m2) [+ gu_in];  gu_out = G;  dC = relu'(conv_j) ? G : 0  ->  dc_out (rows = pixels), dc_outT (rows = channels)
+  //   G = rstd * (g - m1 - xhat * m2) [+ gu_in];  gu_out = G;  dC = relu'(conv_j) ? G : 0  ->  dc_out (operand format, rows = pixels)
   const __nv_bfloat16* u_op;     // u_j in operand format (xhat and, for odd j, the ReLU decision u > 0)
   const float* bn_coef;          // [3][48]: rstd, A = -rstd m1 + mean rstd^2 m2, Bc = -rstd^2 m2   (G = rstd g + A + Bc u)
   const float* gu_in;            // planar [B,45,H,10] residual-path gradient flowing into u_j, or null
   float* gu_out;                 // planar G (even j), or null
   const uint16_t* mask_in;       // ReLU decisions of conv_j stored by the forward (even j), or null (odd j: u > 0)
   __nv_bfloat16* dc_out;
-  __nv_bfloat16* dc_outT;
   int R;
   unsigned long long* prof;      // tuning aid: per-CTA cycle counters of the pipeline waits, or null
 };
@@ -454,14 +454,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
               }
             } else {
               uint4* o_op = reinterpret_cast<uint4*>(a.dc_out) + op_row;
-              uint4* o_T = reinterpret_cast<uint4*>(a.dc_outT) + ((size_t)b * (R / 8) + (q >> 3)) * 96 + (lane & 7);
               tc::split8(ov, hi, lo);
               o_op[(size_t)ch * R] = hi;
               o_op[(size_t)(6 + ch) * R] = lo;
-              tc_transpose8(ov, lane & 7);                 // lane & 7 now holds channel 8 * ch + (lane & 7) at the group's 8 rows
-              tc::split8(ov, hi, lo);
-              o_T[ch * 8] = hi;
-              o_T[48 + ch * 8] = lo;
             }
           }
         }
@@ -505,13 +500,13 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const TcConvCall& c) {
   a.in_op = c.in_op; a.out_op = c.out_op; a.w = c.w;
   a.res_op = c.res_op; a.mask_out = c.mask_out; a.pooled_raw = c.pooled_raw;
   a.u_op = c.u_op; a.bn_coef = c.bn_coef; a.gu_in = c.gu_in; a.gu_out = c.gu_out; a.mask_in = c.mask_in;
-  a.dc_out = c.dc_out; a.dc_outT = c.dc_outT;
+  a.dc_out = c.dc_out;
   HOWL_REQUIRE(ctx, c.B * (int64_t)R8_C * c.H * R8_W < ((int64_t)1 << 31), HOWL_E_UNSUPPORTED,
                "tensor-core conv: batch of %lld utterances exceeds the 32-bit element offsets", (long long)c.B);
   HOWL_REQUIRE(ctx, c.in_op && c.w, HOWL_E_INVALID, "tensor-core conv: null operand");
   HOWL_REQUIRE(ctx, c.mode != 1 || c.stats, HOWL_E_INVALID, "tensor-core conv: statistics buffer missing");
   HOWL_REQUIRE(ctx, c.mode != 2 || c.out_planar, HOWL_E_INVALID, "tensor-core conv: output missing");
-  HOWL_REQUIRE(ctx, c.mode != 3 || (c.u_op && c.bn_coef && c.dc_out && c.dc_outT && c.dc_out != c.in_op), HOWL_E_INVALID,
+  HOWL_REQUIRE(ctx, c.mode != 3 || (c.u_op && c.bn_coef && c.dc_out && c.dc_out != c.in_op), HOWL_E_INVALID,
                "tensor-core conv: fused BatchNorm-backward arguments missing");
   a.R = r8tc_dcop_rows(c.H);
   const bool fwd = c.mode <= 1;
@@ -557,7 +552,7 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const TcConvCall& c) {
 //     dW[o][c] = rstd[c] * ( sum_q dC[q][o] X[q+s][c]  -  mean[c] * sum_q dC[q][o] 1[q+s] )
 // =============================================================================================
 struct TcWgradArgs {
-  const __nv_bfloat16* dc_opT;
+  const __nv_bfloat16* dc_op;   // conv-output gradient in operand format (rows = raster positions); transposed in shared memory here
   const __nv_bfloat16* x_op;
   const float* x_mean;   // or null (layer 1: X = a0, no normalisation)
   const float* x_rstd;
@@ -567,27 +562,40 @@ struct TcWgradArgs {
   int R;
 };
 #define TW_ASLOTS 8          // ring of A tiles in tensor memory behind the 9 x 48 accumulator columns
-#define TW_DSLOTS 6          // shared-memory ring of dC quarter-utterances
+#define TW_DSLOTS 3          // shared-memory ring of TRANSPOSED dC quarter-utterances (A tiles for tcgen05.cp)
+#define TW_RSLOTS 3          // raw (as in HBM) dC quarter-utterances, landed by TMA and transposed by the worker warps
+#define TW_GSTRIDE 144       // bytes between the 8-channel groups of a transposed tile (128 + 16: the transposers' stores spread over all banks)
+#define TW_TWARPS 4          // worker warps doing the transposes
 
 template <bool SINGLE>   // SINGLE: fast mode, the X_lo MMA is skipped
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const TcWgradArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.R, Rx = R + 2 * TC_PAD, Rq = R / 4;            // a quarter utterance = Rq raster rows = Rq / 16 K steps
   const uint32_t x_bytes = (uint32_t)(12 * Rx * 16), u_bytes = (uint32_t)(12 * R * 16), q_bytes = u_bytes / 4;
-  unsigned char* d_ring = smem;                                  // TW_DSLOTS x [Rq / 8 row groups][96 channels][8 rows] bf16; the
-                                                                 // 128-row copy of a slot's last group runs 512 B past it (don't-care lanes)
-  unsigned char* x_buf = smem + (size_t)TW_DSLOTS * q_bytes;     // 2 x [hi 6 | lo 6][Rx] x 16 B, raster row q at row q + 12
-  __shared__ __align__(8) uint64_t bar_x[2], bar_d[TW_DSLOTS], bar_free[TW_DSLOTS];
+  const uint32_t t_lbo = 12u * TW_GSTRIDE, t_bytes = (uint32_t)(Rq / 8) * t_lbo;      // transposed quarter: [Rq / 8 row groups][12 channel groups x 144 B]
+  const uint32_t r_plane = (uint32_t)Rq * 16u + 16u, r_bytes = 12u * r_plane;          // raw quarter: 12 planes of Rq rows, 16 B of padding each
+  unsigned char* x_buf = smem;                                   // 2 x [hi 6 | lo 6][Rx] x 16 B, raster row q at row q + 12
+  unsigned char* r_ring = x_buf + 2 * (size_t)x_bytes;           // TW_RSLOTS raw quarters, as in HBM
+  unsigned char* d_ring = r_ring + (size_t)TW_RSLOTS * r_bytes;  // TW_DSLOTS transposed quarters; the 128-lane copy of a tile reads 4 channel groups
+                                                                 // (576 B) past the 12 real ones: don't-care lanes, inside the 1 KB pad at the end
+  __shared__ __align__(8) uint64_t bar_x[2], bar_d[TW_DSLOTS], bar_free[TW_DSLOTS], bar_raw[TW_RSLOTS], bar_rawfree[TW_RSLOTS], bar_xfree[2];
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (warp == 8) {
     tc::tmem_alloc<512>(&s_tmem);
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) tc::mbar_init(&bar_x[i], 1);
+      for (int i = 0; i < 2; ++i) {
+        tc::mbar_init(&bar_x[i], 1);
+        tc::mbar_init(&bar_xfree[i], 1);
+      }
       for (int i = 0; i < TW_DSLOTS; ++i) {
-        tc::mbar_init(&bar_d[i], 1);
+        tc::mbar_init(&bar_d[i], TW_TWARPS);
         tc::mbar_init(&bar_free[i], 1);
+      }
+      for (int i = 0; i < TW_RSLOTS; ++i) {
+        tc::mbar_init(&bar_raw[i], 1);
+        tc::mbar_init(&bar_rawfree[i], TW_TWARPS);
       }
       tc::fence_barrier_init();
     }
@@ -602,41 +610,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   const int64_t n_quarters = 4 * n_local;
 
   if (warp == 9) {
-    // ================= TMA loader: dC quarters through a ring of TW_DSLOTS, X double buffered per utterance =================
+    // ================= TMA loader 1: raw dC quarters (12 row slices of the operand format) through TW_RSLOTS slots =================
+    if (tc::elect_one() && n_local > 0) {
+      const unsigned char* dsrc = reinterpret_cast<const unsigned char*>(a.dc_op);
+      const uint32_t slice = (uint32_t)Rq * 16u;
+      for (int64_t g = 0; g < n_quarters; ++g) {
+        const int rs = (int)(g % TW_RSLOTS);
+        if (g >= TW_RSLOTS) tc::mbar_wait(&bar_rawfree[rs], (uint32_t)(((g / TW_RSLOTS) - 1) & 1));
+        const int64_t b = blockIdx.x + (g >> 2) * (int64_t)gridDim.x;
+        tc::mbar_expect_tx(&bar_raw[rs], q_bytes);
+        for (uint32_t pc = 0; pc < 12; ++pc)
+          tc::tma_bulk_g2s(r_ring + (size_t)rs * r_bytes + (size_t)pc * r_plane, dsrc + (size_t)b * u_bytes + ((size_t)pc * R + (size_t)(g & 3) * Rq) * 16, slice,
+                           &bar_raw[rs]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 7) {
+    // ================= TMA loader 2: X, double buffered per utterance; a buffer is refilled once the MMAs of its utterance retired =================
     if (tc::elect_one() && n_local > 0) {
       const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(a.x_op);
-      const unsigned char* dsrc = reinterpret_cast<const unsigned char*>(a.dc_opT);
-      auto load_x = [&](int64_t k) {
+      for (int64_t k = 0; k < n_local; ++k) {
+        if (k >= 2) tc::mbar_wait(&bar_xfree[k & 1], (uint32_t)(((k >> 1) - 1) & 1));
         const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
         tc::mbar_expect_tx(&bar_x[k & 1], u_bytes);
         for (uint32_t g = 0; g < 12; ++g)
           tc::tma_bulk_g2s(x_buf + (size_t)(k & 1) * x_bytes + ((size_t)g * Rx + TC_PAD) * 16,
                            xsrc + (size_t)b * u_bytes + (size_t)g * R * 16, (uint32_t)(R * 16), &bar_x[k & 1]);
-      };
-      auto load_q = [&](int64_t g) {            // quarter g & 3 of utterance g / 4: contiguous in the transposed format
-        const int64_t b = blockIdx.x + (g >> 2) * (int64_t)gridDim.x;
-        const int slot = (int)(g % TW_DSLOTS);
-        tc::mbar_expect_tx(&bar_d[slot], q_bytes);
-        tc::tma_bulk_g2s(d_ring + (size_t)slot * q_bytes, dsrc + (size_t)b * u_bytes + (size_t)(g & 3) * q_bytes, q_bytes, &bar_d[slot]);
-      };
-      load_x(0);
-      for (int64_t g = 0; g < TW_DSLOTS && g < n_quarters; ++g) load_q(g);
-      if (n_local > 1) load_x(1);
-      for (int64_t g = 0; g < n_quarters; ++g) {
-        const bool more_d = g + TW_DSLOTS < n_quarters, more_x = (g & 3) == 3 && (g >> 2) + 2 < n_local;
-        if (!more_d && !more_x) continue;
-        tc::mbar_wait(&bar_free[g % TW_DSLOTS], (uint32_t)((g / TW_DSLOTS) & 1));   // MMAs of quarter g have retired
-        if (more_d) load_q(g + TW_DSLOTS);
-        if (more_x) load_x((g >> 2) + 2);       // the utterance's last quarter also releases its X buffer
       }
     }
     __syncwarp();
+  } else if (warp < TW_TWARPS) {
+    // ================= transposers: raw quarter [plane][row][8 channels] -> A-tile layout [row group][hi 48 | lo 48 channels][8 rows] =================
+    // (an 8 x 8 bf16 transpose per (plane, row group) in registers: byte permutes pair the rows, the 32-bit words are then renamed)
+    const int nblk = 12 * (Rq / 8);
+    for (int64_t g = 0; g < n_quarters; ++g) {
+      const int rs = (int)(g % TW_RSLOTS), slot = (int)(g % TW_DSLOTS);
+      tc::mbar_wait(&bar_raw[rs], (uint32_t)((g / TW_RSLOTS) & 1));
+      if (g >= TW_DSLOTS) tc::mbar_wait(&bar_free[slot], (uint32_t)(((g / TW_DSLOTS) - 1) & 1));      // MMAs that read the slot's previous tile retired
+      tc::fence_after_sync();
+      const unsigned char* raw = r_ring + (size_t)rs * r_bytes;
+      unsigned char* dst = d_ring + (size_t)slot * t_bytes;
+      for (int blk = tid; blk < nblk; blk += 32 * TW_TWARPS) {
+        const int rg = blk / 12, pc = blk - rg * 12;     // plane fastest: neighbouring lanes are 1296 B (loads) / 144 B (stores) apart -> no bank conflicts
+        uint4 r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = *reinterpret_cast<const uint4*>(raw + (size_t)pc * r_plane + (size_t)(rg * 8 + i) * 16);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(r);       // w[4 * row + k] = channels (2k, 2k + 1) of the row
+        uint4 o[8];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);                  // ow[4 * channel + i] = rows (2i, 2i + 1) of the channel
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t lo = w[4 * (2 * i) + k], hi = w[4 * (2 * i + 1) + k];
+            ow[4 * (2 * k) + i] = __byte_perm(lo, hi, 0x5410);
+            ow[4 * (2 * k + 1) + i] = __byte_perm(lo, hi, 0x7632);
+          }
+        uint4* d = reinterpret_cast<uint4*>(dst + (size_t)rg * t_lbo + (size_t)pc * TW_GSTRIDE);   // plane pc = part * 6 + chunk -> channel group pc
+#pragma unroll
+        for (int c = 0; c < 8; ++c) d[c] = o[c];
+      }
+      tc::fence_proxy_async();       // the tiles are read by tcgen05.cp (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(&bar_d[slot]);
+        tc::mbar_arrive(&bar_rawfree[rs]);
+      }
+    }
   } else if (warp == 8) {
     // ================= MMA issuer =================
     if (tc::elect_one() && n_local > 0) {
       const uint32_t idesc = tc::instr_desc_bf16(128, TC_N, 0, 1);   // A K-major from tensor memory, B MN-major (K = raster rows)
       const uint32_t d_s = tc::smem_u32(d_ring), x_s = tc::smem_u32(x_buf);
-      const uint32_t cp_hi = tc::desc_hi(128u);                       // channel rows dense; the two 8-row K groups 1536 B apart
+      const uint32_t cp_hi = tc::desc_hi((uint32_t)TW_GSTRIDE);        // 8-channel groups 144 B apart; the two 8-row K groups of a tile t_lbo apart
       const uint32_t b_hi = tc::desc_hi((uint32_t)Rx * 16u);
       const uint32_t a_tmem0 = tmem + 9u * TC_N;
       uint32_t step = 0;
@@ -645,7 +691,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
         const int qi = (int)(g & 3), slot = (int)(g % TW_DSLOTS);
         const uint32_t xh_s = x_s + (uint32_t)(k & 1) * x_bytes;
         const uint32_t bh_lo = tc::desc_lo(xh_s, 128u), bl_lo = tc::desc_lo(xh_s + (uint32_t)(6 * Rx * 16), 128u);
-        const uint32_t cp_lo = tc::desc_lo(d_s + (uint32_t)slot * q_bytes, 96u * 16u);
+        const uint32_t cp_lo = tc::desc_lo(d_s + (uint32_t)slot * t_bytes, t_lbo);
         if (qi == 0) tc::mbar_wait(&bar_x[k & 1], (uint32_t)((k >> 1) & 1));
         tc::mbar_wait(&bar_d[slot], (uint32_t)((g / TW_DSLOTS) & 1));
         tc::fence_after_sync();
@@ -656,7 +702,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
         for (int kq = 0; kq < Rq; kq += 16, ++step) {
           const uint32_t a_t = a_tmem0 + 8u * (step % TW_ASLOTS);
           if (kq + 16 < Rq)
-            tc::tmem_cp_128x256b(a_tmem0 + 8u * ((step + 1) % TW_ASLOTS), tc::desc_make(cp_lo + (uint32_t)((kq + 16) >> 3) * 96u, cp_hi));
+            tc::tmem_cp_128x256b(a_tmem0 + 8u * ((step + 1) % TW_ASLOTS), tc::desc_make(cp_lo + (uint32_t)((kq + 16) >> 3) * (t_lbo >> 4), cp_hi));
           const uint32_t acc = step ? 1u : 0u;
           const int k0 = qi * Rq + kq;
 #pragma unroll
@@ -669,6 +715,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
           }
         }
         tc::umma_commit(&bar_free[slot]);
+        if (qi == 3) tc::umma_commit(&bar_xfree[k & 1]);      // the utterance's X buffer may be refilled
       }
       tc::mbar_wait(&bar_free[(n_quarters - 1) % TW_DSLOTS], (uint32_t)(((n_quarters - 1) / TW_DSLOTS) & 1));
     }
@@ -704,10 +751,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
   if (warp == 8) tc::tmem_dealloc<512>(tmem);
 }
 
-int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_opT, const __nv_bfloat16* x_op, const float* x_mean,
+int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, const __nv_bfloat16* x_op, const float* x_mean,
                const float* x_rstd, float* dw, float* dones, int64_t B, int H) {
   TcWgradArgs a;
-  a.dc_opT = dc_opT; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.dones = dones; a.B = B;
+  a.dc_op = dc_op; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.dones = dones; a.B = B;
   a.R = r8tc_dcop_rows(H);
   HOWL_REQUIRE(ctx, r8tc_supported(H), HOWL_E_UNSUPPORTED, "tensor-core wgrad: H=%d does not fit", H);
   const size_t smem = tc_wgrad_smem(a.R);
@@ -802,8 +849,6 @@ __global__ void __launch_bounds__(256) bn_bwd_head_op_kernel(const ApplyOpParams
   const int64_t items = p.B * R;                     // multiple of 64: whole warps, aligned 8-lane row groups
   const uint4* uop = reinterpret_cast<const uint4*>(p.u_op);
   uint4* out = reinterpret_cast<uint4*>(p.dc_op);
-  uint4* outT = reinterpret_cast<uint4*>(p.dc_opT);
-  const int lane = threadIdx.x & 31, sub = lane & 7;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = it / R;
     const int q = (int)(it - b * R);
@@ -830,11 +875,6 @@ __global__ void __launch_bounds__(256) bn_bwd_head_op_kernel(const ApplyOpParams
     tc::split8(d, hi, lo);
     out[base] = hi;                                   // halo rows are written too (zeros): no memset of dc_op needed
     out[base + 6 * (int64_t)R] = lo;
-    tc_transpose8(d, sub);                            // afterwards lane `sub` holds channel chunk * 8 + sub at the group's 8 rows
-    tc::split8(d, hi, lo);
-    const int64_t baseT = (b * (int64_t)(R / 8) + (q >> 3)) * 96 + chunk * 8 + sub;
-    outT[baseT] = hi;
-    outT[baseT + 48] = lo;
   }
 }
 
@@ -844,7 +884,7 @@ int r8tc_apply_head(howl_ctx_t* ctx, cudaStream_t st, const ApplyOpParams& p) {
   const int64_t cap = (int64_t)ctx->sm_count * 4;
   if (bx > cap) bx = cap;
   const dim3 grid((unsigned)bx, 6, 1);
-  HOWL_REQUIRE(ctx, p.g_bcast && p.u_op && p.mask_bits && p.gu_out && p.dc_op && p.dc_opT, HOWL_E_INVALID, "apply_head: null argument");
+  HOWL_REQUIRE(ctx, p.g_bcast && p.u_op && p.mask_bits && p.gu_out && p.dc_op, HOWL_E_INVALID, "apply_head: null argument");
   bn_bwd_head_op_kernel<<<grid, 256, 0, st>>>(p);
   HOWL_LAUNCHED(ctx, "bn_bwd_head_op");
   return HOWL_OK;
