@@ -873,13 +873,14 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   const float* bout = wout + (size_t)L * R8_C;
 
   const bool use_tc = ctx->conv_engine >= 1 && r8tc_supported(H);
-  {
+  if (use_tc) {
+    // tensor-core engine: conv0 + ReLU + pool as split-bf16 GEMMs over im2col tiles built in shared memory; a0 in operand format only
+    rc = r8tc_conv0(ctx, st, feats, w0, ws.uop[0], train ? ws.bits0 : nullptr, B, frames, H);
+    if (rc) return rc;
+  } else {
     const size_t sm = sizeof(float) * ((3 * H + 2) * C0_STRIDE + R8_C * 9);
     HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    // tensor-core engine: a0 exists in operand format only
-    conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, use_tc ? nullptr : ws.a0,
-                                                          use_tc ? reinterpret_cast<uint4*>(ws.uop[0]) : nullptr,
-                                                          train ? ws.bits0 : nullptr, r8tc_dcop_rows(H), frames, H);
+    conv0_pool_kernel<<<(unsigned)B, C0_THREADS, sm, st>>>(feats, w0, ws.a0, nullptr, train ? ws.bits0 : nullptr, r8tc_dcop_rows(H), frames, H);
     HOWL_LAUNCHED(ctx, "conv0_pool");
   }
   if (train) {

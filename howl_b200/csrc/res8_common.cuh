@@ -97,6 +97,9 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const TcConvCall& c);
 int r8tc_bn_bwd_coef(howl_ctx_t* ctx, cudaStream_t st, const float* w, const float* dw, const float* dones, const float* mean_rstd,
                      double count, float* coef);
 int r8tc_debug_mask(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* u_op, const uint16_t* bits, uint8_t* mask, int64_t B, int H);
+// conv0 + ReLU + AvgPool(3,4) on the tensor cores: features -> a0 in operand format (+ the ReLU bits of every pooling window, or null)
+int r8tc_conv0(howl_ctx_t* ctx, cudaStream_t st, const float* feats, const float* w0, __nv_bfloat16* a0_op, uint16_t* bits0, int64_t B, int F,
+               int H);
 // data-gradient weight operands of all six layers (direction 1 blocks of wprep)
 int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __nv_bfloat16* wprep);
 // forward weight operand of one layer with BatchNorm(mean_rstd, or identity when null) folded in (the border-dependent bias

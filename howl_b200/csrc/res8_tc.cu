@@ -771,6 +771,215 @@ int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, con
 }
 
 // =============================================================================================
+// conv0 (1 -> 45, 3x3, pad 1) + ReLU + AvgPool(3, 4) on the tensor cores.
+// One output pixel of the pooled map averages 12 pre-pool pixels, each a 9-tap dot product: as a GEMM per sub-position t = (ty, tx) of the
+// pooling window,  D_t[pp][oc] = sum_k A_t[pp][k] W[oc][k],  rows = 128 pooled pixels of the flattened (utterance, pixel) stream, K = 9 taps
+// padded to 16, N = 48; fp32 via the same bf16 split as the 45 -> 45 layers (hi*hi + lo*hi + hi*lo).  The A tiles (an im2col of the 5 x 6
+// feature patch of every pooled pixel) are BUILT in shared memory by the worker warps from the fp32 features -- 13 KB per utterance in HBM
+// instead of a 583 KB pre-pool tensor -- the epilogue applies the ReLU, adds the 12 sub-positions, keeps their ReLU decisions as the 12 bits
+// conv0_bwd needs, and writes a0 straight in operand format.  Two CTAs per SM (256 TMEM columns each = four sub-positions per pass) overlap
+// one CTA's tile building / epilogue with the other's MMAs.
+// =============================================================================================
+#define C0T_THREADS 288          // warps 0-7 build + epilogue, warp 8 issues the MMAs
+#define C0T_A_BYTES (12 * 2 * 2 * 128 * 16)      // [12 sub-positions][hi, lo][2 chunks of 8 taps][128 rows][8 x bf16]
+#define C0T_W_BYTES (2 * 2 * 48 * 16)            // [hi, lo][2 chunks][48 rows][8 x bf16]
+
+struct Conv0TcArgs {
+  const float* feats;      // [B, F, 40]
+  const float* w0;         // [45][9]
+  uint4* a0_op;            // [B][12][R][8 bf16]
+  uint16_t* bits0;         // [B][45][HW] or null
+  int64_t B;
+  int F, H, R;
+};
+
+__global__ void __launch_bounds__(C0T_THREADS, 2) conv0_tc_kernel(const Conv0TcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* a_s = smem;
+  unsigned char* w_s = smem + C0T_A_BYTES;
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int HW = a.H * R8_W;
+  const int64_t P = a.B * HW, tiles = (P + 127) / 128;
+  if (warp == 8) {
+    tc::tmem_alloc<256>(&s_tmem);
+    if (lane == 0) {
+      tc::mbar_init(&bar_acc, 1);
+      tc::fence_barrier_init();
+    }
+  }
+  // weight operand: W[oc][k] (k < 9), hi / lo
+  for (int i = tid; i < 2 * 48; i += C0T_THREADS) {
+    const int chunk = i / 48, n = i - chunk * 48;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = chunk * 8 + j;
+      v[j] = (n < R8_C && k < 9) ? a.w0[n * 9 + k] : 0.f;
+    }
+    uint4 hi, lo;
+    tc::split8(v, hi, lo);
+    reinterpret_cast<uint4*>(w_s)[chunk * 48 + n] = hi;
+    reinterpret_cast<uint4*>(w_s)[2 * 48 + chunk * 48 + n] = lo;
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  const int row = tid & 127, half = (tid >> 7) & 1;      // builders: two threads per row, six sub-positions each; epilogue: 24 channels each
+  uint32_t n_acc = 0;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t gp = tile * 128 + row;
+    const bool valid = gp < P;
+    const int64_t b = valid ? gp / HW : 0;
+    const int pp = valid ? (int)(gp - b * HW) : 0, h = pp / R8_W, w = pp - h * R8_W;
+    if (warp < 8) {
+      // ---- build the A tiles of this thread's six sub-positions from the 5 x 6 feature patch (rows 3h-1.., columns 4w-1..; zero outside)
+      float patch[5][6];
+      const float* f = a.feats + b * (int64_t)a.F * R8_MELS;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        const int y = 3 * h + r - 1;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const int x = 4 * w + c - 1;
+          patch[r][c] = (valid && y >= 0 && y < a.F && x >= 0 && x < R8_MELS) ? __ldg(f + (int64_t)y * R8_MELS + x) : 0.f;
+        }
+      }
+      uint4* A = reinterpret_cast<uint4*>(a_s);
+#pragma unroll
+      for (int t = 0; t < 12; ++t) {
+        if (t / 6 != half) continue;           // warp uniform; keeps every patch index a compile-time constant (registers, not local memory)
+        const int ty = t >> 2, tx = t & 3;
+        float v0[8], v1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v0[k] = patch[ty + k / 3][tx + k % 3];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v1[k] = 0.f;
+        v1[0] = patch[ty + 2][tx + 2];
+        uint4 hi, lo;
+        tc::split8(v0, hi, lo);
+        A[((t * 2 + 0) * 2 + 0) * 128 + row] = hi;
+        A[((t * 2 + 1) * 2 + 0) * 128 + row] = lo;
+        tc::split8(v1, hi, lo);
+        A[((t * 2 + 0) * 2 + 1) * 128 + row] = hi;
+        A[((t * 2 + 1) * 2 + 1) * 128 + row] = lo;
+      }
+      tc::fence_proxy_async();
+    }
+    float sum[24];
+    uint32_t bits[12];           // ReLU decisions: channel pair (2i, 2i + 1) in the low / high 16 bits
+#pragma unroll
+    for (int j = 0; j < 24; ++j) sum[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) bits[j] = 0u;
+    for (int pass = 0; pass < 3; ++pass) {
+      tc::fence_before_sync();
+      __syncthreads();           // pass 0: the tiles are built; later passes: the previous pass's accumulators are drained
+      tc::fence_after_sync();
+      if (warp == 8) {
+        if (tc::elect_one()) {
+          const uint32_t idesc = tc::instr_desc_bf16(128, 48, 0, 0), hi128 = tc::desc_hi(128u);
+          const uint32_t sa = tc::smem_u32(a_s), sw = tc::smem_u32(w_s);
+          const uint64_t wh = tc::desc_make(tc::desc_lo(sw, 48u * 16u), hi128), wl = tc::desc_make(tc::desc_lo(sw + 2u * 48u * 16u, 48u * 16u), hi128);
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            const int t = pass * 4 + tt;
+            const uint64_t ah = tc::desc_make(tc::desc_lo(sa + (uint32_t)(t * 2 + 0) * 4096u, 2048u), hi128);
+            const uint64_t al = tc::desc_make(tc::desc_lo(sa + (uint32_t)(t * 2 + 1) * 4096u, 2048u), hi128);
+            const uint32_t d = tmem + (uint32_t)(tt * 48);
+            tc::umma_bf16(d, ah, wh, idesc, 0u);
+            tc::umma_bf16(d, al, wh, idesc, 1u);
+            tc::umma_bf16(d, ah, wl, idesc, 1u);
+          }
+          tc::umma_commit(&bar_acc);
+        }
+        __syncwarp();
+      } else {
+        tc::mbar_wait(&bar_acc, n_acc & 1);
+        tc::fence_after_sync();
+        const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(24 * half);
+#pragma unroll
+        for (int tp = 0; tp < 2; ++tp) {            // two sub-positions per wait: 48 accumulator values in flight
+          uint32_t v[48];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            tc::tmem_ld8_nowait(taddr + (2 * tp + u) * 48, v + 24 * u);
+            tc::tmem_ld8_nowait(taddr + (2 * tp + u) * 48 + 8, v + 24 * u + 8);
+            tc::tmem_ld8_nowait(taddr + (2 * tp + u) * 48 + 16, v + 24 * u + 16);
+          }
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int t = pass * 4 + 2 * tp + u;
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+              const float x = __uint_as_float(v[24 * u + j]);
+              if (x > 0.f) {
+                sum[j] += x;
+                bits[j >> 1] |= 1u << (t + 16 * (j & 1));
+              }
+            }
+          }
+        }
+      }
+      ++n_acc;
+    }
+    if (warp < 8 && valid) {
+      const int q = (h + 1) * TC_PITCH + (w + 1);
+      uint4* op = a.a0_op + (size_t)b * 12 * a.R + q;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int oc = 24 * half + 8 * c + j;
+          o[j] = oc < R8_C ? __fdiv_rn(sum[8 * c + j], 12.f) : (oc == R8_C ? 1.f : 0.f);      // channel 45: the ones channel
+          if (a.bits0 && oc < R8_C) a.bits0[(b * R8_C + oc) * (int64_t)HW + pp] = (uint16_t)(bits[(8 * c + j) >> 1] >> (16 * (j & 1)));
+        }
+        uint4 hi, lo;
+        tc::split8(o, hi, lo);
+        const int chunk = 3 * half + c;
+        op[(size_t)chunk * a.R] = hi;
+        op[(size_t)(6 + chunk) * a.R] = lo;
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc<256>(tmem);
+}
+
+// halo rows of the operand-format a0 (raster rows outside the image) := 0
+__global__ void conv0_halo_kernel(uint4* __restrict__ a0_op, int64_t B, int H, int R) {
+  const int64_t n = B * R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / R;
+    const int q = (int)(i - b * R), y = q / TC_PITCH - 1, x = q % TC_PITCH - 1;
+    if (y >= 0 && y < H && x >= 0 && x < R8_W) continue;
+#pragma unroll
+    for (int g = 0; g < 12; ++g) a0_op[(size_t)b * 12 * R + (size_t)g * R + q] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+int r8tc_conv0(howl_ctx_t* ctx, cudaStream_t st, const float* feats, const float* w0, __nv_bfloat16* a0_op, uint16_t* bits0, int64_t B, int F,
+               int H) {
+  Conv0TcArgs a;
+  a.feats = feats; a.w0 = w0; a.a0_op = reinterpret_cast<uint4*>(a0_op); a.bits0 = bits0; a.B = B; a.F = F; a.H = H; a.R = r8tc_dcop_rows(H);
+  conv0_halo_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a.a0_op, B, H, a.R);
+  HOWL_LAUNCHED(ctx, "conv0_halo");
+  const size_t smem = C0T_A_BYTES + C0T_W_BYTES;
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = (B * H * R8_W + 127) / 128;
+  const int grid = (int)(tiles < 2 * ctx->sm_count ? tiles : 2 * ctx->sm_count);
+  conv0_tc_kernel<<<grid, C0T_THREADS, smem, st>>>(a);
+  HOWL_LAUNCHED(ctx, "conv0_tc");
+  return HOWL_OK;
+}
+
+// =============================================================================================
 // BatchNorm-backward statistics of layer j = i - 1 WITHOUT a pass over the gradient tensor: with g = dL/d(xn_j) the data gradient of
 // conv_i,   sum_q g[q][c]        = sum_{o,tap} W_i[o][c][tap] * D1[o][tap]          D1 = the weight gradient's raw ones column
 //           sum_q g[q][c] xhat_j = sum_{o,tap} W_i[o][c][tap] * dW_i[o][c][tap]     dW_i = the (BatchNorm-folded) weight gradient
