@@ -2,7 +2,7 @@
 """bench.py -- train-step throughput of the howl hot path on N x B200 (utterances / s), with roofline and baselines.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--model res8|lstm|seq-lstm|mobilenet] [--batch B] [--seconds S] [--scaling weak|strong] [--global-batch G]
+                    [--model res8|lstm|seq-lstm|mobilenet|las] [--batch B] [--seconds S] [--scaling weak|strong] [--global-batch G]
 
 A "step" is one pass of the hot path over one batch of synthetic 16 kHz clips (training/run/train.py:287-302 of the reference):
 frontend (STFT -> mel -> log -> ZMUV) -> model forward -> loss -> backward -> [allreduce] -> AdamW.
@@ -48,6 +48,7 @@ MODELS = {
     "lstm": {"seconds": 0.5, "batch": 2048, "labels": 5, "dtype": "f32"},
     "seq-lstm": {"seconds": 0.5, "batch": 2048, "labels": 5, "blank": 4, "dtype": "f32"},
     "mobilenet": {"seconds": 1.0, "batch": 8192, "labels": 12, "dtype": "bf16"},
+    "las": {"seconds": 1.0, "batch": 2048, "labels": 12, "dtype": "f32"},     # not a BASELINE config: SURVEY §8 row a12, for completeness
 }
 
 
@@ -74,6 +75,13 @@ def algorithmic(model, samples, labels, batch):
     if model == "mobilenet":
         from howl_b200.mobilenet import algorithmic_flops   # exists once the a10 row is built
         return algorithmic_flops(samples, labels, batch)
+    if model == "las":
+        h1, w1 = N_MELS + 2, F + 2
+        h2, w2 = h1 + 2, w1 // 2 + 2
+        T, inp = w2 // 2, 8 * h2
+        mac = 8 * 27 * h1 * w1 + 8 * 72 * h2 * w2 + T * 2 * 384 * (inp + 96) + 2 * T * 192 * 192 + 192 * 256 + 256 * labels
+        nparam = 8 * 27 + 8 * 72 + 32 + 2 * (384 * (inp + 96) + 768) + 192 + 2 * 192 * 193 + 256 * 193 + 257 * labels
+        return {"flop": 3 * 2.0 * mac, "bytes": samples * 4 + 8 + 4 * labels + 24.0 * nparam / batch}
     raise ValueError(model)
 
 
@@ -187,6 +195,16 @@ def oracle_step_factory(model, batch, samples, labels, device="cpu"):
         for _, _, bnn, shape, _ in mb.layer_plan(labels):
             sd[bnn + ".running_mean"], sd[bnn + ".running_var"] = torch.zeros(shape[0], device=dev), torch.ones(shape[0], device=dev)
         params = {k: sd[k] for k in O.mobilenet_param_names(sd)}
+    elif model == "las":
+        from howl_b200 import las   # host-side shapes only (no CUDA)
+
+        g = torch.Generator().manual_seed(0)
+        sd = {n: ((torch.rand(sh, generator=g) * 2 - 1) / (max(int(torch.tensor(sh[1:]).prod()), 1) ** 0.5 if len(sh) > 1 else 10.0)).to(dev)
+              for n, sh in las.param_shapes(labels, N_MELS)}
+        for idx in ("1", "5"):
+            sd[f"encoder.conv_encoder.{idx}.weight"] = torch.ones(8, device=dev)
+        params = dict(sd)
+        las_len = torch.full((batch,), (samples - N_FFT) // HOP + 1, dtype=torch.int64)
     elif model == "res8":
         params = {k: v.to(dev) for k, v in O.res8_init(labels, seed=0).items()}
         bn = {k: v.to(dev) for k, v in O.res8_bn_init().items()}
@@ -207,6 +225,10 @@ def oracle_step_factory(model, batch, samples, labels, device="cpu"):
                 O.adamw_step(params, grads, m, v, state["step"], LR, WD)
                 for k in params:
                     sd[k] = params[k]
+        elif model == "las":
+            loss, _, grads = O.las_grads(feats, inputs[1], params, las_len, dtype=torch.float32)
+            with torch.no_grad():
+                O.adamw_step(params, grads, m, v, state["step"], LR, WD)
         elif model == "res8":
             loss, _, _ = O.res8_train_step(feats, inputs[1], params, bn, m, v, state["step"], LR, WD)
         elif model == "lstm":
@@ -283,7 +305,8 @@ def run_gpu_library(model, batch, samples, labels, dev, steps=5, warmup=2):
 
 def workload_text(a, world):
     per = {"res8": "fused STFT->mel->conv train step", "lstm": "frontend + LSTM(40->128) + MLP train step (frame objective)",
-           "seq-lstm": "frontend + streaming seq-lstm + CTC train step", "mobilenet": "frontend + MobileNetV2 train step"}[a.model]
+           "seq-lstm": "frontend + streaming seq-lstm + CTC train step", "mobilenet": "frontend + MobileNetV2 train step",
+           "las": "frontend + LASClassifier (convs, BiLSTM(352->96), attention, MLP) train step"}[a.model]
     return (f"{a.model} NUM_MELS={N_MELS} batch={a.batch}/GPU {per}, synthetic GSC-shaped {a.seconds:g} s clips, L={a.labels}")
 
 
@@ -325,6 +348,8 @@ def make_step(a, dev, world):
         return T.SeqLstmCtcTrainStep(dev, blank=MODELS[a.model]["blank"], lr=1e-4, **kw)
     if a.model == "mobilenet":
         return T.MobileNetTrainStep(dev, lr=LR, **kw)
+    if a.model == "las":
+        return T.LasTrainStep(dev, lr=LR, **kw)
     raise ValueError(a.model)
 
 
@@ -335,6 +360,8 @@ def family_of(name):
         return "lstm"
     if name.startswith(("mbn_gemm", "mbn_wgrad")):
         return "mbn_gemm"
+    if name.startswith(("las_lstm", "las_gemm")):
+        return "las_lstm"
     return name
 
 
@@ -459,7 +486,7 @@ def main_ours(a):
                         "peak_source": peaks["source"] + ", dense bf16 cuBLAS sustained",
                         "note": "fp32-equivalent flops; the issued bf16 MMA flops are 3x (hi*hi + hi*lo + lo*hi)"}
         else:
-            key = "lstm" if a.model in ("lstm", "seq-lstm") else "mbn_gemm"
+            key = {"lstm": "lstm", "seq-lstm": "lstm", "las": "las_lstm"}.get(a.model, "mbn_gemm")
             cf = fam.get(key, {"ms": ms_step, "launches": 1, "kernels": []})
             ach = B * alg.get("gemm_flop", alg["flop"]) / (cf["ms"] / 1e3) / 1e12
             roofline = {"bound": "tensor", "kernel": f"{key} family ({cf['launches']} launches/step)", "achieved": ach, "peak": tensor_peak,

@@ -83,9 +83,11 @@ SIGNATURES: Dict[str, tuple] = {
     "howl_b200_mobilenet_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                                  _i64, _f32, _f32, _f32, C.c_uint64, _vp, _vp, _vp, _sz]),
     "howl_b200_las_param_count": (_i64, [_i32, _i32]),
-    "howl_b200_las_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "howl_b200_las_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, C.c_int]),
     "howl_b200_las_lengths": (C.c_int, [_vp, _i64, _vp]),
-    "howl_b200_las_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, _vp, _vp, _sz]),
+    "howl_b200_las_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, C.c_int, C.c_float, C.c_uint64, _vp, _vp, _sz]),
+    "howl_b200_las_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i64, _vp, _vp, C.c_float, _vp, _vp, _sz]),
+    "howl_b200_las_bwd_dlogits": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, C.c_float, _vp, _sz]),
     "howl_b200_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32]),
     "howl_b200_res8_train_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _vp, _i32, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _sz]),

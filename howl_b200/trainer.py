@@ -316,6 +316,72 @@ class MobileNetTrainStep(_HostPipeline):
         return self.loss
 
 
+class LasTrainStep(_HostPipeline):
+    """Train step of the `las` model: frontend (stacked log-mel / delta / delta-delta, ZMUV) -> LASClassifier forward
+    (batch statistics) -> CE -> backward -> [allreduce] -> AdamW, exact fp32, every stage a C-ABI call on one stream."""
+
+    def __init__(self, device, num_labels: int, batch: int, samples: int, n_mels: int = 40, lr: float = 0.01, weight_decay: float = 1e-5,
+                 zmuv: Tuple[float, float] = (0.0, 1.0), seed: int = 0, world_size: int = 1, dropout_p: float = 0.1):
+        from . import las
+
+        self.las = las
+        self.ctx = Context(device, n_mels=n_mels)
+        dev = self.ctx.device
+        self.device, self.num_labels, self.batch, self.samples = dev, num_labels, batch, samples
+        self.lr, self.weight_decay, self.zmuv, self.world, self.dropout_p, self.seed = lr, weight_decay, zmuv, world_size, dropout_p, seed
+        g = torch.Generator().manual_seed(seed)
+        init = []
+        for name, shape in las.param_shapes(num_labels, n_mels):
+            if ".conv_encoder." in name:
+                init.append(torch.ones(shape) if name.endswith("weight") else torch.zeros(shape))
+            elif name == "attn.context_vec":
+                init.append(torch.rand(shape, generator=g) * 0.5 - 0.25)
+            else:
+                fan = 96 if "lstm_encoder" in name else {"encoder.conv1": 27, "encoder.conv2": 72, "attn.v_proj": 192, "attn.k_proj": 192,
+                                                        "fc.0": 192, "fc.3": 256}[name.rsplit(".", 1)[0]]
+                init.append((torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan))
+        self.params = torch.cat([t.reshape(-1) for t in init]).to(dev)
+        n = self.params.numel()
+        assert n == int(self.ctx.lib.howl_b200_las_param_count(num_labels, n_mels))
+        self.grads, self.m, self.v = (torch.zeros(n, device=dev) for _ in range(3))
+        self.bn_running = torch.stack([torch.stack([torch.zeros(8), torch.ones(8)])] * 2).contiguous().to(dev)
+        self.nbt = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        self.fb = mel_filterbank(n_mels).to(dev)
+        self.frames = self.ctx.num_frames(samples)
+        self.feats = torch.empty(batch, 3, n_mels, self.frames, device=dev)
+        self.ws = torch.empty(las.workspace_bytes(self.ctx, batch, self.frames, n_mels, num_labels, True), dtype=torch.uint8, device=dev)
+        # train.py:290-291 hands the model `audio_transform.compute_lengths(batch.lengths)` = floor((samples - 512) / 200) + 1 frames
+        full = torch.full((batch,), (samples - self.ctx.n_fft) // self.ctx.hop + 1, dtype=torch.int64)
+        self.full_lengths = las.encoder_lengths(self.ctx, full, batch, self.frames)
+        self.logits = None
+        self.step_count = 0
+        self._init_host_pipeline()
+
+    def step(self, pcm: torch.Tensor, labels: torch.Tensor, lengths=None) -> torch.Tensor:
+        """pcm [B, T] f32 / int16, labels [B] i64 on the device; lengths [B] i64 = samples per clip (None: full clips)."""
+        self.step_count += 1
+        c, las = self.ctx, self.las
+        b = pcm.shape[0]
+        seed = self.seed * 1000003 + self.step_count
+        feats = self.feats[:b]
+        c.frontend(pcm, self.fb, "stacked", zmuv=self.zmuv, out=feats)
+        if lengths is None:
+            enc = self.full_lengths[:b]
+        else:
+            frames = torch.div(lengths.cpu().long() - c.n_fft, c.hop, rounding_mode="floor") + 1
+            enc = las.encoder_lengths(c, frames, b, self.frames)
+        self.logits = las.forward(c, feats, None, self.params, self.bn_running, self.nbt, True, self.ws, self.num_labels, self.dropout_p, seed, enc)
+        las.backward(c, feats, enc, self.params, self.grads, self.ws, self.num_labels, labels=labels, loss=self.loss, dropout_p=self.dropout_p,
+                     loss_scale_batch=b * self.world)
+        if self.world > 1:
+            from .parallel import allreduce_flat_grads
+
+            allreduce_flat_grads(self.grads)
+        c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
+        return self.loss
+
+
 class Trainer:
     """``howl.trainer.Trainer`` (``howl/trainer.py:11-31``): constructible from a ``TrainingConfig`` exactly like the reference's
     (which is a stub without a training loop); ``train`` is the addition the reference leaves open -- the epoch loop of

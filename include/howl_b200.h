@@ -238,20 +238,31 @@ int howl_b200_mobilenet_train_step(howl_ctx_t* ctx, void* stream, const float* p
                                    int64_t step, float lr, float weight_decay, float dropout_p, uint64_t seed, float* loss,
                                    float* logits, void* workspace, size_t workspace_bytes);
 
-/* ---- K7: LASClassifier, forward only --------------------------------------------------------------- */
+/* ---- K7: LASClassifier -------------------------------------------------------------------------------- */
 /* LASClassifier.forward (howl/model/rnn.py:206-215) = LASEncoder (two Conv2d(.., 8, 3, padding=2) + BatchNorm2d + ReLU + MaxPool2d((1,2)) over
  * the three stacked feature channels, bidirectional LSTM(8 * (n_mels + 4) -> 96) over each clip's own length) + FixedAttentionModule (4 heads)
- * + Linear(192, 256) + ReLU + Linear(256, L); exact fp32.  Inference and the batch-statistics forward of train mode; no backward.
+ * + Linear(192, 256) + ReLU + Dropout + Linear(256, L), and its autograd backward; exact fp32.
  * Flat parameter layout = `parameters()` order of the reference module (477,862 floats at 30 labels / 40 mels); bn_running [2 layers][2][8]
- * (mean, var), num_batches_tracked [2].  enc_lengths [B] i64 (device) = howl_b200_las_lengths of the clips' frame counts. */
+ * (mean, var), num_batches_tracked [2].  enc_lengths [B] i64 (device) = howl_b200_las_lengths of the clips' frame counts.
+ * train != 0 in workspace_bytes adds the activations the backward needs. */
 int64_t howl_b200_las_param_count(int32_t num_labels, int32_t n_mels);
-int64_t howl_b200_las_workspace_bytes(int64_t B, int32_t frames, int32_t n_mels);
+int64_t howl_b200_las_workspace_bytes(int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels, int train);
 /* LASEncoder.forward's length arithmetic (rnn.py:163-168; float floors at every step as the reference), host arrays. */
 int howl_b200_las_lengths(const int64_t* lengths, int64_t n, int64_t* out);
-/* feats [B, 3, n_mels, frames] f32 (HOWL_FE_STACKED layout, normalised). */
+/* feats [B, 3, n_mels, frames] f32 (HOWL_FE_STACKED layout, normalised).  train != 0: batch statistics + running-stat update, activations
+ * kept in `workspace` (sized with train = 1) for the backward; dropout_p / seed drive the fc dropout mask (a counter-based hash of
+ * (seed, utterance, unit); eval: identity). */
 int howl_b200_las_fwd(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* enc_lengths, int64_t B, int32_t frames,
                       int32_t n_mels, int32_t num_labels, const float* params, float* bn_running, int64_t* num_batches_tracked, int train,
-                      float* logits, void* workspace, size_t workspace_bytes);
+                      float dropout_p, uint64_t seed, float* logits, void* workspace, size_t workspace_bytes);
+/* CrossEntropyLoss(mean) + backward (training/run/train.py:293,299-301 with --model las) of the train-mode forward kept in `workspace`;
+ * dropout_p as given to that forward.  grads (flat layout) is OVERWRITTEN; loss may be NULL. */
+int howl_b200_las_bwd(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* enc_lengths, const int64_t* labels, int64_t B,
+                      int32_t frames, int32_t n_mels, int32_t num_labels, int64_t loss_scale_batch, const float* params, float* grads,
+                      float dropout_p, float* loss, void* workspace, size_t workspace_bytes);
+int howl_b200_las_bwd_dlogits(howl_ctx_t* ctx, void* stream, const float* feats, const int64_t* enc_lengths, const float* dlogits,
+                              int64_t B, int32_t frames, int32_t n_mels, int32_t num_labels, const float* params, float* grads,
+                              float dropout_p, void* workspace, size_t workspace_bytes);
 
 /* ---- K4: fused AdamW over a flat buffer ------------------------------------------------------- */
 /* torch.optim.AdamW.step (training/run/train.py:256,302): decoupled weight decay, bias correction,

@@ -638,9 +638,9 @@ def las_lengths(lengths: torch.Tensor, use_maxpool: bool = True) -> torch.Tensor
 
 
 def las_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], lengths: Optional[torch.Tensor] = None, train: bool = False,
-                num_heads: int = 4) -> torch.Tensor:
+                num_heads: int = 4, hid_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: [B, 3, 40, F] stacked features, lengths: frames per clip, sorted descending (pack_padded_sequence, rnn.py:169).
-    Dropout is the identity.  Returns logits [B, L]."""
+    Dropout (rnn.py:202) is the identity unless `hid_mask` [B, 256] (keep / (1 - p) factors) is given.  Returns logits [B, L]."""
     if lengths is None:
         lengths = torch.full((x.shape[0],), x.shape[-1], dtype=torch.long)
     e = "encoder."
@@ -650,13 +650,13 @@ def las_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], lengths: Optional[
     h = F.max_pool2d(torch.relu(_bn(h, sd, e + "conv_encoder.5", train)), (1, 2))
     h = h.permute(3, 0, 1, 2).contiguous()
     h = h.view(-1, h.size(1), h.size(2) * h.size(3))                       # [F', B, 8 * 44]
-    ll = las_lengths(lengths)
+    ll = las_lengths(lengths).to(x.device)
     p = e + "lstm_encoder."
     fwd, _ = _lstm_direction(h, sd[p + "weight_ih_l0"], sd[p + "weight_hh_l0"], sd[p + "bias_ih_l0"], sd[p + "bias_hh_l0"], ll, False)
     bwd, _ = _lstm_direction(h, sd[p + "weight_ih_l0_reverse"], sd[p + "weight_hh_l0_reverse"], sd[p + "bias_ih_l0_reverse"],
                              sd[p + "bias_hh_l0_reverse"], ll, True)
     rnn_seq = torch.cat([fwd, bwd], 2)                                      # [Tmax, B, 192] = pad_packed_sequence output
-    mask = (torch.arange(rnn_seq.shape[0])[:, None] < ll[None, :]).to(rnn_seq.dtype)
+    mask = (torch.arange(rnn_seq.shape[0], device=rnn_seq.device)[:, None] < ll.to(rnn_seq.device)[None, :]).to(rnn_seq.dtype)
     # FixedAttentionModule.forward (rnn.py:181-191)
     values = F.linear(rnn_seq, sd["attn.v_proj.weight"], sd["attn.v_proj.bias"])
     keys = F.linear(rnn_seq, sd["attn.k_proj.weight"], sd["attn.k_proj.bias"])
@@ -668,7 +668,22 @@ def las_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], lengths: Optional[
     scores = torch.softmax(logits, 0)
     context = torch.einsum("ijk,ijkl->jkl", scores, k4).reshape(b, -1)
     hid = torch.relu(F.linear(context, sd["fc.0.weight"], sd["fc.0.bias"]))
+    if hid_mask is not None:
+        hid = hid * hid_mask
     return F.linear(hid, sd["fc.3.weight"], sd["fc.3.bias"])
+
+
+def las_grads(x: torch.Tensor, labels: torch.Tensor, sd: Dict[str, torch.Tensor], lengths: Optional[torch.Tensor] = None,
+              dtype=torch.float64, hid_mask: Optional[torch.Tensor] = None):
+    """Train-mode (batch statistics) forward + CrossEntropyLoss(mean) + autograd backward (train.py:293,299-301) of `las_forward`.
+    Returns (loss, logits, {name: grad}) for the trainable tensors of `sd`."""
+    names = [k for k in sd if "running_" not in k and "num_batches" not in k]
+    leaves = {k: (v.detach().clone().to(dtype).requires_grad_(True) if k in names else v.detach().clone().to(dtype)) for k, v in sd.items()
+              if v.is_floating_point()}
+    logits = las_forward(x.to(dtype), leaves, lengths, train=True, hid_mask=None if hid_mask is None else hid_mask.to(dtype))
+    loss = F.cross_entropy(logits, labels)
+    loss.backward()
+    return float(loss.detach()), logits.detach(), {k: leaves[k].grad for k in names}
 
 
 # =====================================================================================================
