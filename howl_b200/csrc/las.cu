@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(256) las_head_kernel(const float* __restrict__
   float* s_sc = s_h + (size_t)T * LA_D;    // [T][4] attention logits -> scores
   float* s_ctx = s_sc + T * LA_HEADS;      // [192]
   float* s_hid = s_ctx + LA_D;             // [256]
+  float* s_hbar = s_hid + LA_DNN;          // [4][192]
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x, len = (int)(lengths[b] < (int64_t)T ? lengths[b] : (int64_t)T);
   for (int i = tid; i < T * LA_D; i += 256) s_h[i] = hseq[((int64_t)(i / LA_D) * B + b) * LA_D + (i % LA_D)];
@@ -396,14 +397,17 @@ __global__ void __launch_bounds__(256) las_head_kernel(const float* __restrict__
   if (sc_save)
     for (int i = tid; i < T * LA_HEADS; i += 256) sc_save[b * T * LA_HEADS + i] = s_sc[i];
   // context[h * 48 + l] = sum_t scores[t][h] * keys[t][h * 48 + l] = k_proj( sum_t scores[t][h] h_t )[row] (+ bias: the scores sum to 1)
+  for (int i = tid; i < LA_HEADS * LA_D; i += 256) {
+    const int h = i / LA_D, k = i - h * LA_D;
+    float hb = 0.f;
+    for (int t = 0; t < T; ++t) hb = fmaf(s_sc[t * LA_HEADS + h], s_h[t * LA_D + k], hb);
+    s_hbar[i] = hb;
+  }
+  __syncthreads();
   for (int row = tid; row < LA_D; row += 256) {
-    const int h = row / (LA_D / LA_HEADS);
+    const float* hb = s_hbar + (row / (LA_D / LA_HEADS)) * LA_D;
     float acc = q.kb[row];
-    for (int k = 0; k < LA_D; ++k) {
-      float hb = 0.f;
-      for (int t = 0; t < T; ++t) hb = fmaf(s_sc[t * LA_HEADS + h], s_h[t * LA_D + k], hb);
-      acc = fmaf(__ldg(q.kw + row * LA_D + k), hb, acc);
-    }
+    for (int k = 0; k < LA_D; ++k) acc = fmaf(__ldg(q.kw + row * LA_D + k), hb[k], acc);
     s_ctx[row] = acc;
     if (ctx_save) ctx_save[b * LA_D + row] = acc;
   }
@@ -784,50 +788,61 @@ __global__ void __launch_bounds__(256) las_conv_dgrad_kernel(const float* __rest
   }
 }
 
-// conv weight / bias gradients: block = 8 * CIN * 9 threads, thread = (o, c, ky, kx); LW_ROWS output rows (b, yo) per iteration staged in
-// shared memory (input rows with two zero columns on each side, so the taps need no bounds test)
+// conv weight / bias gradients: block = LW_ROWS x (8 * CIN * 3) threads, thread = (staged row, o, c, ky) with the three kx taps in
+// registers over a sliding input window (2 shared-memory loads per 3 FMAs); LW_ROWS output rows (b, yo) are staged per iteration, input
+// rows with two zero columns on each side so the taps need no bounds test
 #define LW_ROWS 4
 template <int CIN>
-__global__ void __launch_bounds__(LA_C * CIN * 9) las_conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dout, int64_t B,
-                                                                         int hi, int wi, float* __restrict__ dw, float* __restrict__ dbias) {
+__global__ void __launch_bounds__(LW_ROWS * LA_C * CIN * 3) las_conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dout,
+                                                                                   int64_t B, int hi, int wi, float* __restrict__ dw,
+                                                                                   float* __restrict__ dbias) {
   extern __shared__ __align__(16) float smem[];
   const int ho = hi + 2, wo = wi + 2, wpad = wi + 4;
   float* s_d = smem;                               // [LW_ROWS][8][wo]
   float* s_in = s_d + LW_ROWS * LA_C * wo;         // [LW_ROWS][CIN][3][wi + 4]
-  const int tid = threadIdx.x, nth = LA_C * CIN * 9;
-  const int o = tid / (CIN * 9), c = (tid / 9) % CIN, ky = (tid / 3) % 3, kx = tid % 3;
+  constexpr int ROLES = LA_C * CIN * 3;
+  const int tid = threadIdx.x, nth = LW_ROWS * ROLES;
+  const int r = tid / ROLES, role = tid % ROLES;
+  const int o = role / (CIN * 3), c = (role / 3) % CIN, ky = role % 3;
   const int64_t rows = B * ho;
-  float acc = 0.f, accb = 0.f;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accb = 0.f;
   for (int64_t row0 = (int64_t)blockIdx.x * LW_ROWS; row0 < rows; row0 += (int64_t)gridDim.x * LW_ROWS) {
     __syncthreads();
     for (int i = tid; i < LW_ROWS * LA_C * wo; i += nth) {
-      const int r = i / (LA_C * wo), j = i - r * (LA_C * wo);
-      const int64_t row = row0 + r;
+      const int rr = i / (LA_C * wo), j = i - rr * (LA_C * wo);
+      const int64_t row = row0 + rr;
       const int yo = (int)(row % ho);
       const int64_t b = row / ho;
       s_d[i] = row < rows ? dout[((b * LA_C + j / wo) * ho + yo) * (int64_t)wo + j % wo] : 0.f;
     }
     for (int i = tid; i < LW_ROWS * CIN * 3 * wpad; i += nth) {
-      const int r = i / (CIN * 3 * wpad), j = i - r * (CIN * 3 * wpad);
-      const int64_t row = row0 + r;
+      const int rr = i / (CIN * 3 * wpad), j = i - rr * (CIN * 3 * wpad);
+      const int64_t row = row0 + rr;
       const int yo = (int)(row % ho);
       const int64_t b = row / ho;
-      const int xx = j % wpad - 2, rr = (j / wpad) % 3, cc = j / (3 * wpad);
-      const int yy = yo + rr - 2;
+      const int xx = j % wpad - 2, kr = (j / wpad) % 3, cc = j / (3 * wpad);
+      const int yy = yo + kr - 2;
       s_in[i] = (row < rows && xx >= 0 && xx < wi && yy >= 0 && yy < hi) ? in[((b * CIN + cc) * hi + yy) * (int64_t)wi + xx] : 0.f;
     }
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < LW_ROWS; ++r) {
-      const float* dr = s_d + (r * LA_C + o) * wo;
-      const float* ir = s_in + ((r * CIN + c) * 3 + ky) * wpad + kx;          // input column xo + kx - 2 -> padded index xo + kx
-      for (int xo = 0; xo < wo; ++xo) acc = fmaf(dr[xo], ir[xo], acc);
-      if (tid % (CIN * 9) == 0)
-        for (int xo = 0; xo < wo; ++xo) accb += dr[xo];
+    const float* dr = s_d + (r * LA_C + o) * wo;
+    const float* ir = s_in + ((r * CIN + c) * 3 + ky) * wpad;        // input column xo + kx - 2 -> padded index xo + kx
+    float w0 = ir[0], w1 = ir[1];
+    for (int xo = 0; xo < wo; ++xo) {
+      const float dv = dr[xo], w2 = ir[xo + 2];
+      acc0 = fmaf(dv, w0, acc0);
+      acc1 = fmaf(dv, w1, acc1);
+      acc2 = fmaf(dv, w2, acc2);
+      w0 = w1;
+      w1 = w2;
+      if (role % (CIN * 3) == 0) accb += dv;
     }
   }
-  atomicAdd(dw + tid, acc);
-  if (tid % (CIN * 9) == 0) atomicAdd(dbias + o, accb);
+  float* out = dw + ((o * CIN + c) * 3 + ky) * 3;
+  atomicAdd(out, acc0);
+  atomicAdd(out + 1, acc1);
+  atomicAdd(out + 2, acc2);
+  if (role % (CIN * 3) == 0) atomicAdd(dbias + o, accb);
 }
 
 // =============================================================================================
@@ -852,7 +867,7 @@ extern "C" int howl_b200_las_lengths(const int64_t* lengths, int64_t n, int64_t*
   return HOWL_OK;
 }
 
-static size_t las_head_smem(const LasDims& d) { return sizeof(float) * ((size_t)d.w2p * LA_D + d.w2p * LA_HEADS + LA_D + LA_DNN); }
+static size_t las_head_smem(const LasDims& d) { return sizeof(float) * ((size_t)d.w2p * LA_D + d.w2p * LA_HEADS + LA_D + LA_DNN + LA_HEADS * LA_D); }
 static size_t las_head_bwd_smem(const LasDims& d, int L) {
   return sizeof(float) * ((size_t)d.w2p * LA_D + 2 * d.w2p * LA_HEADS + LA_DNN + LA_D + 2 * LA_HEADS * LA_D + L);
 }
@@ -1005,7 +1020,7 @@ static int las_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const
   {
     const size_t smem = sizeof(float) * LW_ROWS * ((size_t)LA_C * d.w2 + LA_C * 3 * (d.w1p + 4));
     HOWL_CUDA(ctx, cudaFuncSetAttribute(las_conv_wgrad_kernel<LA_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    las_conv_wgrad_kernel<LA_C><<<ctx->sm_count * 3, LA_C * LA_C * 9, smem, st>>>(ws.pool1, ws.draw2, B, d.h1, d.w1p, G(q.c2w), G(q.c2b));
+    las_conv_wgrad_kernel<LA_C><<<ctx->sm_count * 2, LW_ROWS * LA_C * LA_C * 3, smem, st>>>(ws.pool1, ws.draw2, B, d.h1, d.w1p, G(q.c2w), G(q.c2b));
     HOWL_LAUNCHED(ctx, "las_conv_wgrad");
   }
   las_conv_dgrad_kernel<<<blocks, 256, 0, st>>>(ws.draw2, q.c2w, ws.dpool1, B, d.h1, d.w1p);
@@ -1019,7 +1034,7 @@ static int las_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const
   {
     const size_t smem = sizeof(float) * LW_ROWS * ((size_t)LA_C * d.w1 + 3 * 3 * (d.F + 4));
     HOWL_CUDA(ctx, cudaFuncSetAttribute(las_conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    las_conv_wgrad_kernel<3><<<ctx->sm_count * 8, LA_C * 3 * 9, smem, st>>>(feats, ws.draw1, B, d.M, d.F, G(q.c1w), G(q.c1b));
+    las_conv_wgrad_kernel<3><<<ctx->sm_count * 6, LW_ROWS * LA_C * 3 * 3, smem, st>>>(feats, ws.draw1, B, d.M, d.F, G(q.c1w), G(q.c1b));
     HOWL_LAUNCHED(ctx, "las_conv_wgrad");
   }
   return HOWL_OK;
