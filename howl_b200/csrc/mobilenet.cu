@@ -246,8 +246,39 @@ __global__ void __launch_bounds__(256) mbn_apply_kernel(const uint4* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// depthwise 3x3 (pad 1, stride s): in = relu6(bn_in(raw_in)) applied while loading; raw output + its statistics
+// depthwise 3x3 (pad 1, stride s).  All three kernels work on IMAGE TILES: a CTA owns one 8-channel chunk and walks groups of `ni`
+// consecutive utterances; the tensor the stencil reads (the activated input, or the output gradient) is staged ONCE per group in shared
+// memory as fp32 with a one-pixel zero border (two float4 planes -> conflict-free 128-bit reads), so BatchNorm + ReLU6 of the producer
+// is applied once per element instead of once per tap, the taps need no bounds tests, and the nine reads per output hit shared memory.
+// Pixel indices are decoded with multiply-high divisions by host-precomputed reciprocals.
 // ---------------------------------------------------------------------------------------------
+#define DW_PX 1024          // padded pixels of one staged tile (2 planes x 16 B x 1024 = 32 KB)
+
+struct MbFastDiv { unsigned m, d; };
+static MbFastDiv mb_fastdiv(int d) {
+  MbFastDiv f;
+  f.d = (unsigned)d;
+  f.m = d > 1 ? (unsigned)((1ull << 32) / (unsigned)d + 1) : 0u;      // exact for x < 2^32 / d
+  return f;
+}
+__device__ __forceinline__ int mb_div(int x, const MbFastDiv f) { return f.d == 1 ? x : (int)__umulhi((unsigned)x, f.m); }
+
+struct MbDwGeom {
+  int ni, ph, pw;                  // utterances per group, padded tile height / width
+  MbFastDiv fd_tile, fd_pw;        // / (ph * pw), / pw: staged pixel -> (image, row, column)
+  MbFastDiv fd_hw, fd_w;           // / (h * w), / w of the tensor the compute loop walks
+};
+// staged tensor hs x ws (padded by one pixel), walked tensor hwalk x wwalk
+static MbDwGeom mb_dw_geom(int64_t B, int hs, int ws, int hwalk, int wwalk) {
+  MbDwGeom g;
+  g.ph = hs + 2; g.pw = ws + 2;
+  g.ni = (int)std::max<int64_t>(1, std::min<int64_t>(B, DW_PX / (g.ph * g.pw)));
+  g.fd_tile = mb_fastdiv(g.ph * g.pw); g.fd_pw = mb_fastdiv(g.pw);
+  g.fd_hw = mb_fastdiv(hwalk * wwalk); g.fd_w = mb_fastdiv(wwalk);
+  return g;
+}
+static bool mb_dw_fits(int hs, int ws) { return (hs + 2) * (ws + 2) <= DW_PX; }
+
 struct MbDwArgs {
   const uint4* in;       // raw producer output, TMO [B * hin * win][cp]
   const float* bn_in;    // producer's [5][cp]
@@ -256,62 +287,106 @@ struct MbDwArgs {
   double* stats;         // [2][cp] of the output (bf16-rounded), or null
   int64_t B;
   int c, cp, hin, win, hout, wout, stride;
+  MbDwGeom g;
 };
 
-__global__ void __launch_bounds__(256, 3) mbn_dw_fwd_kernel(const MbDwArgs a) {
+// A tile holds at most DW_PX = 4 x blockDim pixels.  mb_dw_load issues this thread's (up to four) global loads of the padded tile of the
+// group starting at utterance b0 (zero outside the h x w image; bit e of the result = pixel e is inside); mb_dw_store converts them to
+// the fp32 planes, applying the producer's BatchNorm + ReLU6 when s_bn is given.  The kernels issue the loads of the NEXT group before
+// they compute the current one, so the DRAM latency overlaps the stencil arithmetic.
+__device__ __forceinline__ unsigned mb_dw_load(uint4 (&raw)[4], const uint4* __restrict__ in, const MbDwGeom& g, int b0, int nb, int h, int w, int chunk,
+                                               int c8) {
+  const int tile = g.ph * g.pw, hw = h * w;
+  unsigned inside = 0u;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = threadIdx.x + e * 256;
+    const int img = mb_div(i, g.fd_tile), q = i - img * tile;
+    const int py = mb_div(q, g.fd_pw), px = q - py * g.pw;
+    raw[e] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < nb * tile && py >= 1 && py <= h && px >= 1 && px <= w) {
+      raw[e] = __ldg(in + mbn_vec((int64_t)(b0 + img) * hw + (py - 1) * w + (px - 1), chunk, c8));
+      inside |= 1u << e;
+    }
+  }
+  return inside;
+}
+__device__ __forceinline__ void mb_dw_store(float4* s_lo, float4* s_hi, const uint4 (&raw)[4], unsigned inside, int count, const float* s_bn) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = threadIdx.x + e * 256;
+    if (i >= count) break;
+    float v[8];
+    mb_unpack(raw[e], v);
+    if (s_bn && (inside >> e & 1u)) {
+      const float4 sc0 = *reinterpret_cast<const float4*>(s_bn), sc1 = *reinterpret_cast<const float4*>(s_bn + 4);
+      const float4 sh0 = *reinterpret_cast<const float4*>(s_bn + 8), sh1 = *reinterpret_cast<const float4*>(s_bn + 12);
+      const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w}, sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fminf(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f), 6.f);
+    }
+    s_lo[i] = make_float4(v[0], v[1], v[2], v[3]);
+    s_hi[i] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) mbn_dw_fwd_kernel(const MbDwArgs a) {
   const int chunk = blockIdx.y, c8 = a.cp / 8;
-  __shared__ __align__(16) float s_w[9][8];       // this chunk's taps: read as warp-wide broadcasts (keeps 72 registers free -> 3 CTAs / SM)
+  __shared__ float4 s_lo[DW_PX], s_hi[DW_PX];
+  __shared__ __align__(16) float s_w[9][8];       // this chunk's taps: read as warp-wide broadcasts
   if (threadIdx.x < 72) {
     const int k = threadIdx.x >> 3, c = chunk * 8 + (threadIdx.x & 7);
     s_w[k][threadIdx.x & 7] = c < a.c ? a.w[c * 9 + k] : 0.f;
   }
-  float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = chunk * 8 + j;
-    sc[j] = a.bn_in[c];
-    sh[j] = a.bn_in[a.cp + c];
+  __shared__ __align__(16) float s_bn[16];        // producer's scale[8], shift[8]
+  if (threadIdx.x >= 96 && threadIdx.x < 112) {
+    const int j = threadIdx.x - 96;
+    s_bn[j] = a.bn_in[(j >> 3) * a.cp + chunk * 8 + (j & 7)];
   }
-  __syncthreads();
-  const int rows = (int)(a.B * a.hout * a.wout), rows_pad = (int)(mbn_tiles(rows) * MBN_TILE);     // the host checks rows_pad < 2^31
-  const int hw_o = a.hout * a.wout, hw_i = a.hin * a.win;
+  const int hw_o = a.hout * a.wout, tile = a.g.ph * a.g.pw;
+  const int groups = (int)((a.B + a.g.ni - 1) / a.g.ni);
   float part[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) part[i] = 0.f;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows_pad; r += gridDim.x * blockDim.x) {
-    float acc[8];
+  uint4 raw[4];
+  unsigned inside = 0u;
+  if ((int)blockIdx.x < groups)
+    inside = mb_dw_load(raw, a.in, a.g, blockIdx.x * a.g.ni, (int)min((int64_t)a.g.ni, a.B - (int64_t)blockIdx.x * a.g.ni), a.hin, a.win, chunk, c8);
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int b0 = grp * a.g.ni, nb = (int)min((int64_t)a.g.ni, a.B - b0);
+    __syncthreads();
+    mb_dw_store(s_lo, s_hi, raw, inside, nb * tile, s_bn);
+    __syncthreads();
+    const int nxt = grp + gridDim.x;
+    if (nxt < groups) inside = mb_dw_load(raw, a.in, a.g, nxt * a.g.ni, (int)min((int64_t)a.g.ni, a.B - (int64_t)nxt * a.g.ni), a.hin, a.win, chunk, c8);
+    for (int o = threadIdx.x; o < nb * hw_o; o += blockDim.x) {
+      const int img = mb_div(o, a.g.fd_hw), p = o - img * hw_o;
+      const int yo = mb_div(p, a.g.fd_w), xo = p - yo * a.wout;
+      const int base = img * tile + yo * a.stride * a.g.pw + xo * a.stride;
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (r < rows) {
-      const int b = r / hw_o;
-      const int p = r - b * hw_o, yo = p / a.wout, xo = p - yo * a.wout;
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yi = yo * a.stride - 1 + ky;
-        if (yi < 0 || yi >= a.hin) continue;
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int xi = xo * a.stride - 1 + kx;
-          if (xi < 0 || xi >= a.win) continue;
-          float v[8];
-          mb_unpack(__ldg(a.in + mbn_vec(b * hw_i + yi * a.win + xi, chunk, c8)), v);
+          const float4 lo = s_lo[base + ky * a.g.pw + kx], hi = s_hi[base + ky * a.g.pw + kx];
           const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][0]), w1 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][4]);
-          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float x = fminf(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f), 6.f);
-            acc[j] = fmaf(x, w[j], acc[j]);
-          }
+          acc[0] = fmaf(lo.x, w0.x, acc[0]); acc[1] = fmaf(lo.y, w0.y, acc[1]); acc[2] = fmaf(lo.z, w0.z, acc[2]); acc[3] = fmaf(lo.w, w0.w, acc[3]);
+          acc[4] = fmaf(hi.x, w1.x, acc[4]); acc[5] = fmaf(hi.y, w1.y, acc[5]); acc[6] = fmaf(hi.z, w1.z, acc[6]); acc[7] = fmaf(hi.w, w1.w, acc[7]);
         }
-      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[j] = mb_bf16_round(acc[j]);
         part[j] += acc[j];
         part[8 + j] = fmaf(acc[j], acc[j], part[8 + j]);
       }
+      a.out[mbn_vec((int64_t)b0 * hw_o + o, chunk, c8)] = mb_pack(acc);
     }
-    a.out[mbn_vec(r, chunk, c8)] = mb_pack(acc);
+  }
+  if (blockIdx.x == 0) {        // pad rows of the last tile
+    const int64_t rows = a.B * hw_o, rows_pad = mbn_tiles(rows) * MBN_TILE;
+    for (int64_t r = rows + threadIdx.x; r < rows_pad; r += blockDim.x) a.out[mbn_vec(r, chunk, c8)] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (a.stats) {
     __shared__ float s_part[8][16];
@@ -330,54 +405,67 @@ __global__ void __launch_bounds__(256, 3) mbn_dw_fwd_kernel(const MbDwArgs a) {
   }
 }
 
-// data gradient of the depthwise convolution: d(in_act)[b, yi, xi, c] = sum_{ky,kx} dOut[b, yo, xo, c] w[c][ky][kx], yo * s - 1 + ky = yi
+// data gradient of the depthwise convolution: d(in_act)[b, yi, xi, c] = sum_{ky,kx} dOut[b, yo, xo, c] w[c][ky][kx], yo * s - 1 + ky = yi.
+// The output gradient is the staged tensor (border = the rows / columns yo = -1, hout that some taps address).
 struct MbDwBwdArgs {
   const uint4* dout;     // gradient at the raw depthwise output, TMO [B * hout * wout][cp]
   const float* w;
   uint4* din;            // gradient w.r.t. the depthwise input (post-activation), TMO [B * hin * win][cp]
   int64_t B;
   int c, cp, hin, win, hout, wout, stride;
+  MbDwGeom g;
 };
 
-__global__ void __launch_bounds__(256, 3) mbn_dw_bwd_data_kernel(const MbDwBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) mbn_dw_bwd_data_kernel(const MbDwBwdArgs a) {
   const int chunk = blockIdx.y, c8 = a.cp / 8;
+  __shared__ float4 s_lo[DW_PX], s_hi[DW_PX];
   __shared__ __align__(16) float s_w[9][8];
   if (threadIdx.x < 72) {
     const int k = threadIdx.x >> 3, c = chunk * 8 + (threadIdx.x & 7);
     s_w[k][threadIdx.x & 7] = c < a.c ? a.w[c * 9 + k] : 0.f;
   }
-  __syncthreads();
-  const int rows = (int)(a.B * a.hin * a.win), rows_pad = (int)(mbn_tiles(rows) * MBN_TILE);
-  const int hw_o = a.hout * a.wout, hw_i = a.hin * a.win;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows_pad; r += gridDim.x * blockDim.x) {
-    float acc[8];
+  const int hw_i = a.hin * a.win, tile = a.g.ph * a.g.pw;
+  const int groups = (int)((a.B + a.g.ni - 1) / a.g.ni);
+  uint4 raw[4];
+  unsigned inside = 0u;
+  if ((int)blockIdx.x < groups)
+    inside = mb_dw_load(raw, a.dout, a.g, blockIdx.x * a.g.ni, (int)min((int64_t)a.g.ni, a.B - (int64_t)blockIdx.x * a.g.ni), a.hout, a.wout, chunk, c8);
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int b0 = grp * a.g.ni, nb = (int)min((int64_t)a.g.ni, a.B - b0);
+    __syncthreads();
+    mb_dw_store(s_lo, s_hi, raw, inside, nb * tile, nullptr);
+    __syncthreads();
+    const int nxt = grp + gridDim.x;
+    if (nxt < groups) inside = mb_dw_load(raw, a.dout, a.g, nxt * a.g.ni, (int)min((int64_t)a.g.ni, a.B - (int64_t)nxt * a.g.ni), a.hout, a.wout, chunk, c8);
+    for (int o = threadIdx.x; o < nb * hw_i; o += blockDim.x) {
+      const int img = mb_div(o, a.g.fd_hw), p = o - img * hw_i;
+      const int yi = mb_div(p, a.g.fd_w), xi = p - yi * a.win;
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (r < rows) {
-      const int b = r / hw_i;
-      const int p = r - b * hw_i, yi = p / a.win, xi = p - yi * a.win;
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        const int ty = yi + 1 - ky;
-        if (ty < 0 || ty % a.stride) continue;
-        const int yo = ty / a.stride;
-        if (yo >= a.hout) continue;
+        const int ty = yi + 1 - ky;                   // = yo * stride
+        if (a.stride == 2 && (ty & 1)) continue;
+        const int yo = a.stride == 2 ? ty >> 1 : ty;  // -1 .. hout: inside the padded tile
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int tx = xi + 1 - kx;
-          if (tx < 0 || tx % a.stride) continue;
-          const int xo = tx / a.stride;
-          if (xo >= a.wout) continue;
-          float v[8];
-          mb_unpack(__ldg(a.dout + mbn_vec(b * hw_o + yo * a.wout + xo, chunk, c8)), v);
+          if (a.stride == 2 && (tx & 1)) continue;
+          const int xo = a.stride == 2 ? tx >> 1 : tx;
+          const int idx = img * tile + (yo + 1) * a.g.pw + (xo + 1);
+          const float4 lo = s_lo[idx], hi = s_hi[idx];
           const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][0]), w1 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][4]);
-          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], w[j], acc[j]);
+          acc[0] = fmaf(lo.x, w0.x, acc[0]); acc[1] = fmaf(lo.y, w0.y, acc[1]); acc[2] = fmaf(lo.z, w0.z, acc[2]); acc[3] = fmaf(lo.w, w0.w, acc[3]);
+          acc[4] = fmaf(hi.x, w1.x, acc[4]); acc[5] = fmaf(hi.y, w1.y, acc[5]); acc[6] = fmaf(hi.z, w1.z, acc[6]); acc[7] = fmaf(hi.w, w1.w, acc[7]);
         }
       }
+      a.din[mbn_vec((int64_t)b0 * hw_i + o, chunk, c8)] = mb_pack(acc);
     }
-    a.din[mbn_vec(r, chunk, c8)] = mb_pack(acc);
+  }
+  if (blockIdx.x == 0) {
+    const int64_t rows = a.B * hw_i, rows_pad = mbn_tiles(rows) * MBN_TILE;
+    for (int64_t r = rows + threadIdx.x; r < rows_pad; r += blockDim.x) a.din[mbn_vec(r, chunk, c8)] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -389,41 +477,58 @@ struct MbDwWgArgs {
   float* dw;             // [c][9] fp32, accumulated
   int64_t B;
   int c, cp, hin, win, hout, wout, stride;
+  MbDwGeom g;
 };
 
-__global__ void __launch_bounds__(256) mbn_dw_bwd_weight_kernel(const MbDwWgArgs a) {
+__global__ void __launch_bounds__(256, 2) mbn_dw_bwd_weight_kernel(const MbDwWgArgs a) {
   const int chunk = blockIdx.y, c8 = a.cp / 8;
-  float sc[8], sh[8], acc[8][9];
+  __shared__ float4 s_lo[DW_PX], s_hi[DW_PX];
+  __shared__ __align__(16) float s_bn[16];
+  if (threadIdx.x < 16) s_bn[threadIdx.x] = a.bn_in[(threadIdx.x >> 3) * a.cp + chunk * 8 + (threadIdx.x & 7)];
+  float acc[8][9];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = a.bn_in[chunk * 8 + j];
-    sh[j] = a.bn_in[a.cp + chunk * 8 + j];
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[j][k] = 0.f;
-  }
-  const int rows = (int)(a.B * a.hout * a.wout);
-  const int hw_o = a.hout * a.wout, hw_i = a.hin * a.win;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
-    const int b = r / hw_o;
-    const int p = r - b * hw_o, yo = p / a.wout, xo = p - yo * a.wout;
-    float g[8];
-    mb_unpack(__ldg(a.dout + mbn_vec(r, chunk, c8)), g);
+  const int hw_o = a.hout * a.wout, tile = a.g.ph * a.g.pw;
+  const int groups = (int)((a.B + a.g.ni - 1) / a.g.ni);
+  uint4 raw[4];
+  unsigned inside = 0u;
+  if ((int)blockIdx.x < groups)
+    inside = mb_dw_load(raw, a.in, a.g, blockIdx.x * a.g.ni, (int)min((int64_t)a.g.ni, a.B - (int64_t)blockIdx.x * a.g.ni), a.hin, a.win, chunk, c8);
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int b0 = grp * a.g.ni, nb = (int)min((int64_t)a.g.ni, a.B - b0);
+    uint4 gq[4];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yi = yo * a.stride - 1 + ky;
-      if (yi < 0 || yi >= a.hin) continue;
+    for (int e = 0; e < 4; ++e) {
+      const int o = threadIdx.x + e * 256;
+      gq[e] = make_uint4(0u, 0u, 0u, 0u);
+      if (o < nb * hw_o) gq[e] = __ldg(a.dout + mbn_vec((int64_t)b0 * hw_o + o, chunk, c8));
+    }
+    __syncthreads();
+    mb_dw_store(s_lo, s_hi, raw, inside, nb * tile, s_bn);
+    __syncthreads();
+    const int nxt = grp + gridDim.x;
+    if (nxt < groups) inside = mb_dw_load(raw, a.in, a.g, nxt * a.g.ni, (int)min((int64_t)a.g.ni, a.B - (int64_t)nxt * a.g.ni), a.hin, a.win, chunk, c8);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xi = xo * a.stride - 1 + kx;
-        if (xi < 0 || xi >= a.win) continue;
-        float v[8];
-        mb_unpack(__ldg(a.in + mbn_vec(b * hw_i + yi * a.win + xi, chunk, c8)), v);
+    for (int e = 0; e < 4; ++e) {
+      const int o = threadIdx.x + e * 256;
+      if (o >= nb * hw_o) break;
+      const int img = mb_div(o, a.g.fd_hw), p = o - img * hw_o;
+      const int yo = mb_div(p, a.g.fd_w), xo = p - yo * a.wout;
+      const int base = img * tile + yo * a.stride * a.g.pw + xo * a.stride;
+      float g[8];
+      mb_unpack(gq[e], g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float x = fminf(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f), 6.f);
-          acc[j][ky * 3 + kx] = fmaf(g[j], x, acc[j][ky * 3 + kx]);
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 lo = s_lo[base + ky * a.g.pw + kx], hi = s_hi[base + ky * a.g.pw + kx];
+          const int k = ky * 3 + kx;
+          acc[0][k] = fmaf(g[0], lo.x, acc[0][k]); acc[1][k] = fmaf(g[1], lo.y, acc[1][k]); acc[2][k] = fmaf(g[2], lo.z, acc[2][k]);
+          acc[3][k] = fmaf(g[3], lo.w, acc[3][k]); acc[4][k] = fmaf(g[4], hi.x, acc[4][k]); acc[5][k] = fmaf(g[5], hi.y, acc[5][k]);
+          acc[6][k] = fmaf(g[6], hi.z, acc[6][k]); acc[7][k] = fmaf(g[7], hi.w, acc[7][k]);
         }
-      }
     }
   }
   __shared__ float s_acc[72];
@@ -441,6 +546,226 @@ __global__ void __launch_bounds__(256) mbn_dw_bwd_weight_kernel(const MbDwWgArgs
     const int c = chunk * 8 + threadIdx.x / 9;
     if (c < a.c) atomicAdd(a.dw + c * 9 + threadIdx.x % 9, s_acc[threadIdx.x]);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise 3x3 on SMALL images (<= 3 x 3 pixels: the last ten depthwise layers at 1 s clips).  thread = (utterance, 8-channel chunk):
+// the whole image lives in registers, every load is issued up front, taps are resolved at compile time -- no shared-memory tile, no
+// barriers, no index arithmetic per pixel.  grid = (ceil(B / 128), chunks), block = 128.
+// ---------------------------------------------------------------------------------------------
+#define DWS_THREADS 128
+template <int HIN, int WIN, int S>
+struct MbSmall {
+  static constexpr int HOUT = (HIN - 1) / S + 1, WOUT = (WIN - 1) / S + 1, NIN = HIN * WIN, NOUT = HOUT * WOUT;
+};
+
+template <int HIN, int WIN, int S>
+__global__ void __launch_bounds__(DWS_THREADS) mbn_dw_small_fwd_kernel(const MbDwArgs a) {
+  using G = MbSmall<HIN, WIN, S>;
+  const int chunk = blockIdx.y, c8 = a.cp / 8;
+  __shared__ __align__(16) float s_w[9][8];
+  __shared__ float s_part[DWS_THREADS / 32][16];
+  if (threadIdx.x < 72) {
+    const int k = threadIdx.x >> 3, c = chunk * 8 + (threadIdx.x & 7);
+    s_w[k][threadIdx.x & 7] = c < a.c ? a.w[c * 9 + k] : 0.f;
+  }
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = a.bn_in[chunk * 8 + j];
+    sh[j] = a.bn_in[a.cp + chunk * 8 + j];
+  }
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * DWS_THREADS + threadIdx.x;
+  float part[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) part[i] = 0.f;
+  if (b < a.B) {
+    uint4 raw[G::NIN];
+#pragma unroll
+    for (int p = 0; p < G::NIN; ++p) raw[p] = __ldg(a.in + mbn_vec(b * G::NIN + p, chunk, c8));
+    float x[G::NIN][8];
+#pragma unroll
+    for (int p = 0; p < G::NIN; ++p) {
+      mb_unpack(raw[p], x[p]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[p][j] = fminf(fmaxf(fmaf(x[p][j], sc[j], sh[j]), 0.f), 6.f);
+    }
+#pragma unroll
+    for (int yo = 0; yo < G::HOUT; ++yo)
+#pragma unroll
+      for (int xo = 0; xo < G::WOUT; ++xo) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int yi = yo * S - 1 + ky, xi = xo * S - 1 + kx;
+            if (yi < 0 || yi >= HIN || xi < 0 || xi >= WIN) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(x[yi * WIN + xi][j], s_w[ky * 3 + kx][j], acc[j]);
+          }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = mb_bf16_round(acc[j]);
+          part[j] += acc[j];
+          part[8 + j] = fmaf(acc[j], acc[j], part[8 + j]);
+        }
+        a.out[mbn_vec(b * G::NOUT + yo * G::WOUT + xo, chunk, c8)] = mb_pack(acc);
+      }
+  }
+  if (blockIdx.x == 0) {
+    const int64_t rows = a.B * G::NOUT, rows_pad = mbn_tiles(rows) * MBN_TILE;
+    for (int64_t r = rows + threadIdx.x; r < rows_pad; r += blockDim.x) a.out[mbn_vec(r, chunk, c8)] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (a.stats) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float t = warp_sum(part[i]);
+      if (lane == 0) s_part[warp][i] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      double t = 0.0;
+      for (int wv = 0; wv < DWS_THREADS / 32; ++wv) t += (double)s_part[wv][threadIdx.x];
+      atomicAdd(a.stats + (size_t)(threadIdx.x >> 3) * a.cp + chunk * 8 + (threadIdx.x & 7), t);
+    }
+  }
+}
+
+template <int HIN, int WIN, int S>
+__global__ void __launch_bounds__(DWS_THREADS) mbn_dw_small_bwd_data_kernel(const MbDwBwdArgs a) {
+  using G = MbSmall<HIN, WIN, S>;
+  const int chunk = blockIdx.y, c8 = a.cp / 8;
+  __shared__ __align__(16) float s_w[9][8];
+  if (threadIdx.x < 72) {
+    const int k = threadIdx.x >> 3, c = chunk * 8 + (threadIdx.x & 7);
+    s_w[k][threadIdx.x & 7] = c < a.c ? a.w[c * 9 + k] : 0.f;
+  }
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * DWS_THREADS + threadIdx.x;
+  if (b < a.B) {
+    uint4 raw[G::NOUT];
+#pragma unroll
+    for (int p = 0; p < G::NOUT; ++p) raw[p] = __ldg(a.dout + mbn_vec(b * G::NOUT + p, chunk, c8));
+    float g[G::NOUT][8];
+#pragma unroll
+    for (int p = 0; p < G::NOUT; ++p) mb_unpack(raw[p], g[p]);
+#pragma unroll
+    for (int yi = 0; yi < HIN; ++yi)
+#pragma unroll
+      for (int xi = 0; xi < WIN; ++xi) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int ty = yi + 1 - ky, tx = xi + 1 - kx;
+            if (ty < 0 || tx < 0 || ty % S || tx % S) continue;
+            const int yo = ty / S, xo = tx / S;
+            if (yo >= G::HOUT || xo >= G::WOUT) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(g[yo * G::WOUT + xo][j], s_w[ky * 3 + kx][j], acc[j]);
+          }
+        a.din[mbn_vec(b * G::NIN + yi * WIN + xi, chunk, c8)] = mb_pack(acc);
+      }
+  }
+  if (blockIdx.x == 0) {
+    const int64_t rows = a.B * G::NIN, rows_pad = mbn_tiles(rows) * MBN_TILE;
+    for (int64_t r = rows + threadIdx.x; r < rows_pad; r += blockDim.x) a.din[mbn_vec(r, chunk, c8)] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+template <int HIN, int WIN, int S>
+__global__ void __launch_bounds__(DWS_THREADS) mbn_dw_small_bwd_weight_kernel(const MbDwWgArgs a) {
+  using G = MbSmall<HIN, WIN, S>;
+  const int chunk = blockIdx.y, c8 = a.cp / 8;
+  __shared__ float s_acc[72];
+  if (threadIdx.x < 72) s_acc[threadIdx.x] = 0.f;
+  float sc[8], sh[8], acc[8][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = a.bn_in[chunk * 8 + j];
+    sh[j] = a.bn_in[a.cp + chunk * 8 + j];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[j][k] = 0.f;
+  }
+  __syncthreads();
+  for (int64_t b = (int64_t)blockIdx.x * DWS_THREADS + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * DWS_THREADS) {
+    uint4 rin[G::NIN], rg[G::NOUT];
+#pragma unroll
+    for (int p = 0; p < G::NIN; ++p) rin[p] = __ldg(a.in + mbn_vec(b * G::NIN + p, chunk, c8));
+#pragma unroll
+    for (int p = 0; p < G::NOUT; ++p) rg[p] = __ldg(a.dout + mbn_vec(b * G::NOUT + p, chunk, c8));
+    float x[G::NIN][8];
+#pragma unroll
+    for (int p = 0; p < G::NIN; ++p) {
+      mb_unpack(rin[p], x[p]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[p][j] = fminf(fmaxf(fmaf(x[p][j], sc[j], sh[j]), 0.f), 6.f);
+    }
+#pragma unroll
+    for (int yo = 0; yo < G::HOUT; ++yo)
+#pragma unroll
+      for (int xo = 0; xo < G::WOUT; ++xo) {
+        float g[8];
+        mb_unpack(rg[yo * G::WOUT + xo], g);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int yi = yo * S - 1 + ky, xi = xo * S - 1 + kx;
+            if (yi < 0 || yi >= HIN || xi < 0 || xi >= WIN) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j][ky * 3 + kx] = fmaf(g[j], x[yi * WIN + xi][j], acc[j][ky * 3 + kx]);
+          }
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float t = warp_sum(acc[j][k]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[j * 9 + k], t);
+    }
+  __syncthreads();
+  if (threadIdx.x < 72) {
+    const int c = chunk * 8 + threadIdx.x / 9;
+    if (c < a.c) atomicAdd(a.dw + c * 9 + threadIdx.x % 9, s_acc[threadIdx.x]);
+  }
+}
+
+// shape dispatch of the small-image kernels; false = not a small shape (the tiled kernels take it)
+static bool mb_dw_small_fwd(cudaStream_t st, const MbDwArgs& d, int c8) {
+  const dim3 grid((unsigned)howl_ceil_div(d.B, DWS_THREADS), c8);
+  if (d.hin == 3 && d.win == 3 && d.stride == 1) mbn_dw_small_fwd_kernel<3, 3, 1><<<grid, DWS_THREADS, 0, st>>>(d);
+  else if (d.hin == 3 && d.win == 3 && d.stride == 2) mbn_dw_small_fwd_kernel<3, 3, 2><<<grid, DWS_THREADS, 0, st>>>(d);
+  else if (d.hin == 2 && d.win == 2 && d.stride == 1) mbn_dw_small_fwd_kernel<2, 2, 1><<<grid, DWS_THREADS, 0, st>>>(d);
+  else return false;
+  return true;
+}
+static bool mb_dw_small_bwd_data(cudaStream_t st, const MbDwBwdArgs& d, int c8) {
+  const dim3 grid((unsigned)howl_ceil_div(d.B, DWS_THREADS), c8);
+  if (d.hin == 3 && d.win == 3 && d.stride == 1) mbn_dw_small_bwd_data_kernel<3, 3, 1><<<grid, DWS_THREADS, 0, st>>>(d);
+  else if (d.hin == 3 && d.win == 3 && d.stride == 2) mbn_dw_small_bwd_data_kernel<3, 3, 2><<<grid, DWS_THREADS, 0, st>>>(d);
+  else if (d.hin == 2 && d.win == 2 && d.stride == 1) mbn_dw_small_bwd_data_kernel<2, 2, 1><<<grid, DWS_THREADS, 0, st>>>(d);
+  else return false;
+  return true;
+}
+static bool mb_dw_small_bwd_weight(cudaStream_t st, const MbDwWgArgs& d, int c8, int sm_count) {
+  // each CTA ends with 72 atomics per chunk: cap the grid so that a thread accumulates several utterances
+  const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(howl_ceil_div(d.B, DWS_THREADS), std::max<int64_t>(1, (int64_t)sm_count * 12 / c8)));
+  const dim3 grid((unsigned)gx, c8);
+  if (d.hin == 3 && d.win == 3 && d.stride == 1) mbn_dw_small_bwd_weight_kernel<3, 3, 1><<<grid, DWS_THREADS, 0, st>>>(d);
+  else if (d.hin == 3 && d.win == 3 && d.stride == 2) mbn_dw_small_bwd_weight_kernel<3, 3, 2><<<grid, DWS_THREADS, 0, st>>>(d);
+  else if (d.hin == 2 && d.win == 2 && d.stride == 1) mbn_dw_small_bwd_weight_kernel<2, 2, 1><<<grid, DWS_THREADS, 0, st>>>(d);
+  else return false;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -896,6 +1221,13 @@ static MbWs mb_carve(const MbNet& net, void* base, int64_t B, int L) {
   return w;
 }
 
+// grid.x of the depthwise kernels: groups of `ni` utterances, capped at ~6 CTAs per SM over all chunks
+static unsigned mb_dw_blocks(howl_ctx_t* ctx, int64_t B, int ni, int chunks) {
+  const int64_t groups = howl_ceil_div(B, ni);
+  const int64_t cap = std::max<int64_t>(1, (int64_t)ctx->sm_count * 6 / chunks);
+  return (unsigned)std::max<int64_t>(1, std::min(groups, cap));
+}
+
 static unsigned mb_rowblocks(howl_ctx_t* ctx, int64_t rows, int chunks) {
   int64_t bx = howl_ceil_div(rows, 256);
   const int64_t cap = std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / chunks);
@@ -1013,7 +1345,9 @@ extern "C" int howl_b200_mobilenet_fwd(howl_ctx_t* ctx, void* stream, const floa
       d.in = reinterpret_cast<const uint4*>(ws.raw[i - 1]); d.bn_in = ws.bn[i - 1]; d.w = params + c.w_off;
       d.out = reinterpret_cast<uint4*>(ws.raw[i]); d.stats = train ? ws.stats[i] : nullptr;
       d.B = B; d.c = c.cout; d.cp = cp; d.hin = c.hin; d.win = c.win; d.hout = c.hout; d.wout = c.wout; d.stride = c.stride;
-      mbn_dw_fwd_kernel<<<dim3(mb_rowblocks(ctx, rows_pad, c8), c8), 256, 0, st>>>(d);
+      HOWL_REQUIRE(ctx, mb_dw_fits(c.hin, c.win), HOWL_E_UNSUPPORTED, "mobilenet: a %d x %d depthwise input exceeds the shared-memory image tile", c.hin, c.win);
+      d.g = mb_dw_geom(B, c.hin, c.win, c.hout, c.wout);
+      if (!mb_dw_small_fwd(st, d, c8)) mbn_dw_fwd_kernel<<<dim3(mb_dw_blocks(ctx, B, d.g.ni, c8), c8), 256, 0, st>>>(d);
       HOWL_LAUNCHED(ctx, "mbn_dw_fwd");
     } else {
       if (c.kind == 2 && c.block >= 0 && net.convs[i - 1].block != c.block) block_in = x;   // first conv of a block: its input is the skip
@@ -1116,12 +1450,15 @@ static int mb_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
       wg.dout = reinterpret_cast<const uint4*>(gr); wg.in = reinterpret_cast<const uint4*>(ws.raw[i - 1]); wg.bn_in = ws.bn[i - 1];
       wg.dw = grads + c.w_off; wg.B = B; wg.c = c.cout; wg.cp = cp; wg.hin = c.hin; wg.win = c.win; wg.hout = c.hout; wg.wout = c.wout;
       wg.stride = c.stride;
-      mbn_dw_bwd_weight_kernel<<<dim3(mb_rowblocks(ctx, rows, c8), c8), 256, 0, st>>>(wg);
+      wg.g = mb_dw_geom(B, c.hin, c.win, c.hout, c.wout);
+      if (!mb_dw_small_bwd_weight(st, wg, c8, ctx->sm_count))
+        mbn_dw_bwd_weight_kernel<<<dim3(mb_dw_blocks(ctx, B, wg.g.ni, c8), c8), 256, 0, st>>>(wg);
       HOWL_LAUNCHED(ctx, "mbn_dw_bwd_weight");
       MbDwBwdArgs d;
       d.dout = reinterpret_cast<const uint4*>(gr); d.w = params + c.w_off; d.din = reinterpret_cast<uint4*>(dst);
       d.B = B; d.c = c.cout; d.cp = cp; d.hin = c.hin; d.win = c.win; d.hout = c.hout; d.wout = c.wout; d.stride = c.stride;
-      mbn_dw_bwd_data_kernel<<<dim3(mb_rowblocks(ctx, rows_in_pad, c8), c8), 256, 0, st>>>(d);
+      d.g = mb_dw_geom(B, c.hout, c.wout, c.hin, c.win);
+      if (!mb_dw_small_bwd_data(st, d, c8)) mbn_dw_bwd_data_kernel<<<dim3(mb_dw_blocks(ctx, B, d.g.ni, c8), c8), 256, 0, st>>>(d);
       HOWL_LAUNCHED(ctx, "mbn_dw_bwd_data");
     } else {
       // GEMM convolution: dW[cout][k] += gr^T * input;  d(input) = gr * W (+ the skip gradient at a block's first convolution)
