@@ -1116,16 +1116,19 @@ __global__ void mbn_ce_kernel(const float* __restrict__ logits, const int64_t* _
 __global__ void __launch_bounds__(256) mbn_cls_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ pooled, int64_t B, int L,
                                                             float* __restrict__ dwc, float* __restrict__ dbc, const double* __restrict__ loss_acc,
                                                             float* __restrict__ loss) {
+  // grid = (L, 1280 / 256, batch slices): partial sums over a slice of the batch, accumulated into the (zeroed) gradient
   const int l = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x;
-  double acc = 0.0, accb = 0.0;
-  for (int64_t b = 0; b < B; ++b) {
+  const int64_t per = (B + gridDim.z - 1) / gridDim.z;
+  const int64_t lo = (int64_t)blockIdx.z * per, hi = lo + per < B ? lo + per : B;
+  float acc = 0.f, accb = 0.f;
+  for (int64_t b = lo; b < hi; ++b) {
     const float d = dlogits[b * L + l];
-    acc += (double)d * pooled[b * MB_LAST + c];
+    acc = fmaf(d, pooled[b * MB_LAST + c], acc);
     accb += d;
   }
-  dwc[(size_t)l * MB_LAST + c] = (float)acc;
-  if (c == 0) dbc[l] = (float)accb;
-  if (l == 0 && c == 0 && loss) *loss = (float)(*loss_acc);
+  atomicAdd(dwc + (size_t)l * MB_LAST + c, acc);
+  if (c == 0) atomicAdd(dbc + l, accb);
+  if (l == 0 && c == 0 && blockIdx.z == 0 && loss) *loss = (float)(*loss_acc);
 }
 
 // gradient at the last activation: dY[b, p, c] = keep * dPooled[b][c] / ((1 - p) hw), dPooled = dlogits . Wc      (TMO bf16)
@@ -1408,7 +1411,7 @@ static int mb_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   mbn_ce_kernel<<<(unsigned)howl_ceil_div(B, 128), 128, 0, st>>>(ws.logits, labels, dlogits_in, ws.dlogits, ws.loss_acc, B, L,
                                                                  1.f / (float)loss_scale_batch);
   HOWL_LAUNCHED(ctx, "mbn_ce");
-  mbn_cls_wgrad_kernel<<<dim3(L, MB_LAST / 256), 256, 0, st>>>(ws.dlogits, ws.pooled, B, L, grads + net.cls_w, grads + net.cls_b, ws.loss_acc, loss);
+  mbn_cls_wgrad_kernel<<<dim3(L, MB_LAST / 256, (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, B / 64))), 256, 0, st>>>(ws.dlogits, ws.pooled, B, L, grads + net.cls_w, grads + net.cls_b, ws.loss_acc, loss);
   HOWL_LAUNCHED(ctx, "mbn_cls_wgrad");
   const MbConv& last = net.convs[n - 1];
   // Three gradient buffers rotate: `gy` = dL/d(activation after conv i's BatchNorm), `gr` = dL/d(raw output of conv i), and the
