@@ -245,3 +245,21 @@ def test_las_module_trains_like_oracle():
         np.testing.assert_allclose(got[n].detach().cpu().numpy(), ref[n].detach().float().numpy(), rtol=0, atol=atol)
     bn = model.state_dict()["encoder.conv_encoder.1.num_batches_tracked"]
     assert int(bn) == 3
+
+
+def test_las_full_batch_permutation():
+    """Bench size (B = 2048 x 1 s, ragged lengths): permuting the batch permutes the logits and leaves loss and every parameter gradient
+    unchanged (exact fp32 arithmetic; only the order of the batch sums differs)."""
+    from howl_b200 import las
+
+    L, B = 12, 2048
+    ctx, sd, feats, x, labels, lengths = _seeded(B, 16000, L, seed=5)
+    del x
+    lg1, loss1, g1 = _run_gpu(ctx, sd, feats, labels, lengths, L)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+    lg2, loss2, g2 = _run_gpu(ctx, sd, feats[perm.to(DEV)].contiguous(), labels[perm], lengths[perm], L)
+    np.testing.assert_allclose(lg2.numpy(), lg1[perm].numpy(), rtol=1e-4, atol=1e-4)
+    assert abs(loss1 - loss2) <= 1e-5 * abs(loss1)
+    for k in g1:
+        scale = float(g1[k].abs().max())
+        assert float((g1[k] - g2[k]).abs().max()) <= 2e-3 * scale + 1e-7, k
