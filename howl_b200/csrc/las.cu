@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "mbn_common.cuh"
 
 #define LA_C 8              // latent channels
 #define LA_H 96             // LSTM hidden size
@@ -99,6 +100,8 @@ struct LasWs {
   float* draw1;     // [B, 8, h1, w1]
   double* bstats;   // [2 layers][2][8]  sum dy, sum dy * xhat
   double* loss_acc; // [2]
+  __nv_bfloat16 *px_hi, *px_lo;   // (hi, lo) bf16 operands of the LSTM weight-gradient products: [w2p * B][384] ...
+  __nv_bfloat16 *py_hi, *py_lo;   // ... and [w2p * B][8 * h2]
   size_t bytes;
 };
 static LasWs las_carve(void* base, int64_t B, const LasDims& d, int train = 0, int L = 0) {
@@ -143,7 +146,12 @@ static LasWs las_carve(void* base, int64_t B, const LasDims& d, int train = 0, i
     w.draw1 = (float*)take(sizeof(float) * B * LA_C * d.h1 * d.w1);
     w.bstats = (double*)take(sizeof(double) * 2 * 2 * LA_C);
     w.loss_acc = (double*)take(sizeof(double) * 2);
+    w.px_hi = (__nv_bfloat16*)take(mbn_tmo_bytes((int64_t)TB, LA_G));
+    w.px_lo = (__nv_bfloat16*)take(mbn_tmo_bytes((int64_t)TB, LA_G));
+    w.py_hi = (__nv_bfloat16*)take(mbn_tmo_bytes((int64_t)TB, d.in));
+    w.py_lo = (__nv_bfloat16*)take(mbn_tmo_bytes((int64_t)TB, d.in));
   } else {
+    w.px_hi = w.px_lo = w.py_hi = w.py_lo = nullptr;
     w.gates = w.cseq = w.scores = w.ctxs = w.hidd = w.logits = w.dlogits = w.dctx = w.hbar = w.dhid = w.du = w.dsum = w.red = nullptr;
     w.dhseq = w.dgates = w.dx = w.draw2 = w.dpool1 = w.draw1 = nullptr;
     w.bstats = w.loss_acc = nullptr;
@@ -1001,13 +1009,22 @@ static int las_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const
     const float* dg = ws.dgates + dir * LA_G;        // [TB][2 * 384], this direction's columns
     // dx += da W_ih
     if ((rc = las_gemm(ctx, st, dg, 2 * LA_G, 1, q.wih[dir], in, 1, ws.dx, in, TB, in, LA_G, dir == 1))) return rc;
-    // dW_ih = da^T x
-    if ((rc = las_gemm(ctx, st, dg, 1, 2 * LA_G, ws.x, in, 1, G(q.wih[dir]), in, LA_G, in, TB, true))) return rc;
-    // dW_hh = da^T h_prev: the previous step of the forward direction is t - 1, of the reverse direction t + 1 (rows shifted by B)
-    if (T > 1) {
-      const float* da = dir ? dg : dg + (size_t)B * 2 * LA_G;
-      const float* hp = dir ? ws.hseq + (size_t)B * LA_D + LA_H : ws.hseq;
-      if ((rc = las_gemm(ctx, st, da, 1, 2 * LA_G, hp, LA_D, 1, G(q.whh[dir]), LA_H, LA_G, LA_H, TB - B, true))) return rc;
+    // dW_ih = da^T x and dW_hh = da^T h_prev.  The previous step of the forward direction is t - 1, of the reverse direction t + 1
+    // (rows shifted by B).  Large batches: tensor cores, (hi, lo) bf16 operands, three products each, fp32 accumulate.
+    const float* da = dir ? dg : dg + (size_t)B * 2 * LA_G;
+    const float* hp = dir ? ws.hseq + (size_t)B * LA_D + LA_H : ws.hseq;
+    if (TB >= 1024) {
+      if ((rc = mbn_pack_split(ctx, st, dg, 2 * LA_G, TB, LA_G, ws.px_hi, ws.px_lo))) return rc;
+      if ((rc = mbn_pack_split(ctx, st, ws.x, in, TB, in, ws.py_hi, ws.py_lo))) return rc;
+      if ((rc = mbn_atb3_packed(ctx, st, ws.px_hi, ws.px_lo, ws.py_hi, ws.py_lo, G(q.wih[dir]), TB, LA_G, in, in))) return rc;
+      if (T > 1) {
+        if ((rc = mbn_pack_split(ctx, st, da, 2 * LA_G, TB - B, LA_G, ws.px_hi, ws.px_lo))) return rc;
+        if ((rc = mbn_pack_split(ctx, st, hp, LA_D, TB - B, LA_H, ws.py_hi, ws.py_lo))) return rc;
+        if ((rc = mbn_atb3_packed(ctx, st, ws.px_hi, ws.px_lo, ws.py_hi, ws.py_lo, G(q.whh[dir]), TB - B, LA_G, LA_H, LA_H))) return rc;
+      }
+    } else {
+      if ((rc = las_gemm(ctx, st, dg, 1, 2 * LA_G, ws.x, in, 1, G(q.wih[dir]), in, LA_G, in, TB, true))) return rc;
+      if (T > 1 && (rc = las_gemm(ctx, st, da, 1, 2 * LA_G, hp, LA_D, 1, G(q.whh[dir]), LA_H, LA_G, LA_H, TB - B, true))) return rc;
     }
     if ((rc = las_colsum(ctx, st, dg, TB, LA_G, 2 * LA_G, G(q.bih[dir]), G(q.bhh[dir])))) return rc;
   }

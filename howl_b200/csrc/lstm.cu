@@ -12,6 +12,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "mbn_common.cuh"
 
 #define LS_H 128
 #define LS_G 512            // 4 * hidden, rows ordered (i, f, g, o) as in torch.nn.LSTM
@@ -40,6 +41,9 @@ struct LstmWs {
   float* dh;        // [R][128]  gradient at h_n (R = B) or at every h_t (R = T*B, sequential)
   float* alpha;     // [B][T][CTC_SMAX]  CTC forward variables (sequential + train)
   double* loss_acc;
+  // (hi, lo) bf16 operands of the weight-gradient products on the tensor cores (mbn_atb3_packed)
+  __nv_bfloat16 *px_hi, *px_lo;   // X side: up to [T * B][512]
+  __nv_bfloat16 *py_hi, *py_lo;   // Y side: up to [T * B][256]
   size_t bytes;
 };
 
@@ -74,6 +78,11 @@ static LstmWs lstm_carve(void* base, int64_t B, int T, int M, int L, int train, 
     w.gates = (float*)take(sizeof(float) * (size_t)T * B * LS_G);
     w.cs = (float*)take(sizeof(float) * (size_t)T * B * LS_H);
     w.xh = (float*)take(sizeof(float) * (size_t)T * B * K);
+    const int64_t R = (int64_t)T * B;
+    w.px_hi = (__nv_bfloat16*)take(mbn_tmo_bytes(R, LS_G));
+    w.px_lo = (__nv_bfloat16*)take(mbn_tmo_bytes(R, LS_G));
+    w.py_hi = (__nv_bfloat16*)take(mbn_tmo_bytes(R, LS_MLP));
+    w.py_lo = (__nv_bfloat16*)take(mbn_tmo_bytes(R, LS_MLP));
   }
   w.bytes = off;
   return w;
@@ -630,6 +639,17 @@ static int lstm_atb(howl_ctx_t* ctx, cudaStream_t st, const float* A, int lda, c
   return HOWL_OK;
 }
 
+// out[m][n] += sum_r A[r][m] Bm[r][n] on the tensor cores: both sides split into (hi, lo) bf16 operands, three products, fp32 accumulate.
+// reuse_x: the X side (A) is already packed in ws.px_* (the gate gradients feed two products)
+static int lstm_atb_tc(howl_ctx_t* ctx, cudaStream_t st, const LstmWs& ws, const float* A, int lda, const float* Bm, int ldb, float* out, int ldo,
+                       int Mo, int No, int64_t R, bool reuse_x) {
+  int rc;
+  if (R < 1024) return lstm_atb(ctx, st, A, lda, Bm, ldb, out, ldo, Mo, No, R);      // a handful of row tiles: the FFMA kernel, exact fp32
+  if (!reuse_x && (rc = mbn_pack_split(ctx, st, A, lda, R, Mo, ws.px_hi, ws.px_lo))) return rc;
+  if ((rc = mbn_pack_split(ctx, st, Bm, ldb, R, No, ws.py_hi, ws.py_lo))) return rc;
+  return mbn_atb3_packed(ctx, st, ws.px_hi, ws.px_lo, ws.py_hi, ws.py_lo, out, R, Mo, No, ldo);
+}
+
 static int lstm_colsum(howl_ctx_t* ctx, cudaStream_t st, const float* A, int lda, int Mo, int64_t R, float* out, float* out2) {
   const int gx = (Mo + 255) / 256;
   int64_t splits = (int64_t)ctx->sm_count * 2 / gx;
@@ -737,9 +757,10 @@ static int lstm_bwd_impl(howl_ctx_t* ctx, void* stream, const int64_t* lengths, 
     HOWL_LAUNCHED(ctx, "lstm_loss");
   }
   // head parameter gradients
+  // (L output rows fill a sliver of a 128-row MMA tile: the FFMA kernel reads z1 once and is faster here)
   if ((rc = lstm_atb(ctx, st, ws.dlogits, L, ws.z1, LS_MLP, g_w2, LS_MLP, L, LS_MLP, rows))) return rc;
   if ((rc = lstm_colsum(ctx, st, ws.dlogits, L, L, rows, g_b2, nullptr))) return rc;
-  if ((rc = lstm_atb(ctx, st, ws.dz1, LS_MLP, sequential ? ws.hseq : ws.hfin, LS_H, g_w1, LS_H, LS_MLP, LS_H, rows))) return rc;
+  if ((rc = lstm_atb_tc(ctx, st, ws, ws.dz1, LS_MLP, sequential ? ws.hseq : ws.hfin, LS_H, g_w1, LS_H, LS_MLP, LS_H, rows, false))) return rc;
   if ((rc = lstm_colsum(ctx, st, ws.dz1, LS_MLP, LS_MLP, rows, g_b1, nullptr))) return rc;
   // BPTT
   LstmBwdArgs a;
@@ -751,8 +772,8 @@ static int lstm_bwd_impl(howl_ctx_t* ctx, void* stream, const int64_t* lengths, 
   HOWL_LAUNCHED(ctx, "lstm_bwd");
   // weight gradients over all (t, b) rows: [W_ih | W_hh] from xh = [x_t | h_{t-1}]
   const int64_t R = (int64_t)T * B;
-  if ((rc = lstm_atb(ctx, st, ws.gates, LS_G, ws.xh, K, g_w_ih, M, LS_G, M, R))) return rc;
-  if ((rc = lstm_atb(ctx, st, ws.gates, LS_G, ws.xh + M, K, g_w_hh, LS_H, LS_G, LS_H, R))) return rc;
+  if ((rc = lstm_atb_tc(ctx, st, ws, ws.gates, LS_G, ws.xh, K, g_w_ih, M, LS_G, M, R, false))) return rc;
+  if ((rc = lstm_atb_tc(ctx, st, ws, ws.gates, LS_G, ws.xh + M, K, g_w_hh, LS_H, LS_G, LS_H, R, true))) return rc;
   if ((rc = lstm_colsum(ctx, st, ws.gates, LS_G, LS_G, R, g_b_ih, g_b_hh))) return rc;
   return HOWL_OK;
 }

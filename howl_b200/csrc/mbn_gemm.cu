@@ -9,6 +9,8 @@
 //  * mbn_gemm_wgrad_kernel: dW = dC^T * A, the reduction runs over the ROWS, so both operands are read MN-major straight from the
 //    same tiles (K = 16 rows per MMA); the [128 x Kt] accumulator stays in TMEM across all row tiles of a CTA and is added to the
 //    fp32 gradient with atomics once.
+#include <algorithm>
+
 #include "mbn_common.cuh"
 #include "tc_common.cuh"
 #include "../../include/howl_b200_debug.h"
@@ -199,8 +201,9 @@ int mbn_gemm_nt(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* A, const 
 // weight gradient: dW[n][k] += sum_rows dC[row][n] * A[row][k]
 // =============================================================================================
 struct MwArgs {
-  const __nv_bfloat16* dC;
-  const __nv_bfloat16* A;
+  const __nv_bfloat16* dC[3];   // `products` operand pairs accumulated into the same tile (1: plain bf16; 3: the hi/lo split of an fp32 product)
+  const __nv_bfloat16* A[3];
+  int products;
   float* dW;
   int64_t m_tiles;
   int n8, k8;          // chunks of dC / A
@@ -246,16 +249,17 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mbn_gemm_wgrad_kernel(const MwA
   if (warp == 5) {
     if (tc::elect_one()) {
       uint32_t it = 0;
-      for (int64_t t = t0; t < t1; ++t, ++it) {
-        const int s = it % MW_STAGES;
-        if (it >= MW_STAGES) tc::mbar_wait(&bar_empty[s], ((it / MW_STAGES) - 1) & 1);
-        unsigned char* dst = smem + (size_t)s * stage_bytes;
-        tc::mbar_expect_tx(&bar_full[s], (uint32_t)nch * 2048u + a_bytes);
-        tc::tma_bulk_g2s(dst, reinterpret_cast<const unsigned char*>(a.dC) + ((size_t)t * a.n8 + (size_t)ntile * 16) * 2048, (uint32_t)nch * 2048u,
-                         &bar_full[s]);
-        tc::tma_bulk_g2s(dst + d_bytes, reinterpret_cast<const unsigned char*>(a.A) + ((size_t)t * a.k8 + (size_t)ktile * kch) * 2048, a_bytes,
-                         &bar_full[s]);
-      }
+      for (int p = 0; p < a.products; ++p)
+        for (int64_t t = t0; t < t1; ++t, ++it) {
+          const int s = it % MW_STAGES;
+          if (it >= MW_STAGES) tc::mbar_wait(&bar_empty[s], ((it / MW_STAGES) - 1) & 1);
+          unsigned char* dst = smem + (size_t)s * stage_bytes;
+          tc::mbar_expect_tx(&bar_full[s], (uint32_t)nch * 2048u + a_bytes);
+          tc::tma_bulk_g2s(dst, reinterpret_cast<const unsigned char*>(a.dC[p]) + ((size_t)t * a.n8 + (size_t)ntile * 16) * 2048,
+                           (uint32_t)nch * 2048u, &bar_full[s]);
+          tc::tma_bulk_g2s(dst + d_bytes, reinterpret_cast<const unsigned char*>(a.A[p]) + ((size_t)t * a.k8 + (size_t)ktile * kch) * 2048, a_bytes,
+                           &bar_full[s]);
+        }
     }
     __syncwarp();
   } else if (warp == 4) {
@@ -263,7 +267,8 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mbn_gemm_wgrad_kernel(const MwA
       const uint32_t idesc = tc::instr_desc_bf16(128, a.kt, 1, 1);       // both operands MN-major: K = rows of the tile
       const uint32_t hi = tc::desc_hi(2048u);                            // stride between 8-channel groups
       uint32_t it = 0;
-      for (int64_t t = t0; t < t1; ++t, ++it) {
+      const int64_t n_it = (t1 - t0) * a.products;
+      for (int64_t tt = 0; tt < n_it; ++tt, ++it) {
         const int s = it % MW_STAGES;
         tc::mbar_wait(&bar_full[s], (it / MW_STAGES) & 1);
         tc::fence_after_sync();
@@ -301,10 +306,23 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mbn_gemm_wgrad_kernel(const MwA
   if (warp == 4) tc::tmem_dealloc<256>(tmem);
 }
 
+static int mbn_gemm_wgrad_n(howl_ctx_t* ctx, cudaStream_t st, int products, const __nv_bfloat16* const* dCs, const __nv_bfloat16* const* As, float* dW,
+                            int64_t M, int N, int K, int n_valid, int k_valid, int ld);
 int mbn_gemm_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dC, const __nv_bfloat16* A, float* dW, int64_t M, int N,
                    int K, int n_valid, int k_valid, int ld) {
+  return mbn_gemm_wgrad_n(ctx, st, 1, &dC, &A, dW, M, N, K, n_valid, k_valid, ld);
+}
+static int mbn_gemm_wgrad_n(howl_ctx_t* ctx, cudaStream_t st, int products, const __nv_bfloat16* const* dCs, const __nv_bfloat16* const* As, float* dW,
+                            int64_t M, int N, int K, int n_valid, int k_valid, int ld) {
   MwArgs a;
-  a.dC = dC; a.A = A; a.dW = dW; a.m_tiles = mbn_tiles(M);
+  const __nv_bfloat16* dC = dCs[0];
+  const __nv_bfloat16* A = As[0];
+  for (int p = 0; p < 3; ++p) {
+    a.dC[p] = dCs[p < products ? p : 0];
+    a.A[p] = As[p < products ? p : 0];
+  }
+  a.products = products;
+  a.dW = dW; a.m_tiles = mbn_tiles(M);
   const int np = mbn_pad16(N), kp = mbn_pad16(K);
   a.n8 = np / 8; a.k8 = kp / 8;
   a.kt = mbn_ntile(kp); a.k_tiles = kp / a.kt;
@@ -321,6 +339,61 @@ int mbn_gemm_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dC, co
   mbn_gemm_wgrad_kernel<<<pairs * slices, MW_THREADS, smem, st>>>(a);
   HOWL_LAUNCHED(ctx, "mbn_wgrad");
   return HOWL_OK;
+}
+
+// =============================================================================================
+// fp32 A^T B as three bf16 products (LSTM / LAS weight gradients): split-pack + three weight-gradient GEMMs
+// =============================================================================================
+// thread = one 16-byte vector of the TMO output (row fastest inside a 128-row tile): stores are contiguous, loads are 32-byte row pieces
+__global__ void __launch_bounds__(256) mbn_pack_split_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int c, int c8,
+                                                             uint4* __restrict__ hi, uint4* __restrict__ lo) {
+  const int64_t n = mbn_tiles(rows) * MBN_TILE * c8;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(v % MBN_TILE), chunk = (int)((v / MBN_TILE) % c8);
+    const int64_t row = (v / MBN_TILE / c8) * MBN_TILE + r;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (row < rows) {
+      const float* src = x + row * ld + chunk * 8;
+      if (chunk * 8 + 8 <= c && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (chunk * 8 + j < c) f[j] = src[j];
+      }
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
+      h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    hi[v] = make_uint4(h[0], h[1], h[2], h[3]);
+    lo[v] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+int mbn_pack_split(howl_ctx_t* ctx, cudaStream_t st, const float* x, int64_t ld, int64_t rows, int c, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  HOWL_REQUIRE(ctx, x && hi && lo && rows > 0 && c > 0, HOWL_E_INVALID, "mbn_pack_split: bad argument");
+  const int c8 = mbn_pad16(c) / 8;
+  const int64_t n = mbn_tiles(rows) * MBN_TILE * c8;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  mbn_pack_split_kernel<<<blocks, 256, 0, st>>>(x, ld, rows, c, c8, reinterpret_cast<uint4*>(hi), reinterpret_cast<uint4*>(lo));
+  HOWL_LAUNCHED(ctx, "mbn_pack_split");
+  return HOWL_OK;
+}
+
+int mbn_atb3_packed(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo, const __nv_bfloat16* yhi,
+                    const __nv_bfloat16* ylo, float* dW, int64_t rows, int N, int K, int ld) {
+  // one launch: the three operand pairs stream through the same accumulator tile, one epilogue
+  const __nv_bfloat16* xs[3] = {xhi, xhi, xlo};
+  const __nv_bfloat16* ys[3] = {yhi, ylo, yhi};
+  return mbn_gemm_wgrad_n(ctx, st, 3, xs, ys, dW, rows, N, K, N, K, ld);
 }
 
 // =============================================================================================

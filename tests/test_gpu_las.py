@@ -143,7 +143,7 @@ def _compare(got, want, bar=2e-3):
     return worst
 
 
-@pytest.mark.parametrize("B,T", [(1, 16000), (6, 8000), (19, 16000), (40, 12345)])
+@pytest.mark.parametrize("B,T", [(1, 16000), (6, 8000), (19, 16000), (40, 12345), (72, 16000)])     # 72 x 21 steps >= 1024 rows: tensor-core weight gradients
 def test_las_gradients_vs_oracle(B, T):
     L = 12
     ctx, sd, feats, x, labels, lengths = _seeded(B, T, L, seed=100 + B)
