@@ -44,6 +44,10 @@ struct LstmWs {
   // (hi, lo) bf16 operands of the weight-gradient products on the tensor cores (mbn_atb3_packed)
   __nv_bfloat16 *px_hi, *px_lo;   // X side: up to [T * B][512]
   __nv_bfloat16 *py_hi, *py_lo;   // Y side: up to [T * B][256]
+  // head products X W^T on the tensor cores (mbn_gemm_nt3_f32): X3 = [hi | hi | lo] of h or dz1, W3 operands of dnn.0.weight
+  __nv_bfloat16* p3;              // [rows][3 * 256]
+  __nv_bfloat16* wop_w1;          // dnn.0.weight [256][128]   -> z1 = h W1^T
+  __nv_bfloat16* wop_w1t;         // its transpose [128][256]  -> dh = dz1 W1
   size_t bytes;
 };
 
@@ -83,6 +87,9 @@ static LstmWs lstm_carve(void* base, int64_t B, int T, int M, int L, int train, 
     w.px_lo = (__nv_bfloat16*)take(mbn_tmo_bytes(R, LS_G));
     w.py_hi = (__nv_bfloat16*)take(mbn_tmo_bytes(R, LS_MLP));
     w.py_lo = (__nv_bfloat16*)take(mbn_tmo_bytes(R, LS_MLP));
+    w.p3 = (__nv_bfloat16*)take(mbn_tmo_bytes(rows, 3 * LS_MLP));
+    w.wop_w1 = (__nv_bfloat16*)take(mbn_weight_operand3_bytes(LS_MLP, LS_H));
+    w.wop_w1t = (__nv_bfloat16*)take(mbn_weight_operand3_bytes(LS_H, LS_MLP));
   }
   w.bytes = off;
   return w;
@@ -293,6 +300,65 @@ __global__ void __launch_bounds__(256) lstm_head_fwd_kernel(const float* __restr
     for (int n = 0; n < LS_MLP; ++n) s = fmaf(__ldg(w2 + l * LS_MLP + n), s_z[r * LS_MLP + n], s);
     out[(r0 + r) * L + l] = s;
     if (out2) out2[(r0 + r) * L + l] = s;
+  }
+}
+
+// ---- large row counts (training on every frame): the two 128 <-> 256 products run on the tensor cores (mbn_gemm_nt3_f32) and these
+// two kernels do the L-wide rest.  One warp per row.
+#define LH_TC_ROWS 4096          // below this the 16-row FFMA kernels are used
+__global__ void __launch_bounds__(256) lstm_scores_kernel(const float* __restrict__ z1, int64_t rows, const float* __restrict__ w2,
+                                                          const float* __restrict__ b2, float* __restrict__ out, float* __restrict__ out2, int L) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float z[LS_MLP / 32];
+#pragma unroll
+  for (int i = 0; i < LS_MLP / 32; ++i) z[i] = z1[r * LS_MLP + i * 32 + lane];
+  for (int l = 0; l < L; ++l) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LS_MLP / 32; ++i) s = fmaf(__ldg(w2 + l * LS_MLP + i * 32 + lane), z[i], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      s += b2[l];
+      out[r * L + l] = s;
+      if (out2) out2[r * L + l] = s;
+    }
+  }
+}
+
+// CE (or given dlogits) -> dlogits, loss;  dz1[r][n] = relu'(z1) * sum_l dlogits[r][l] W2[l][n]
+__global__ void __launch_bounds__(256) lstm_dz1_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                       const float* __restrict__ dlogits_in, const float* __restrict__ z1,
+                                                       const float* __restrict__ w2, float* __restrict__ dlogits, float* __restrict__ dz1,
+                                                       double* __restrict__ loss_acc, int64_t rows, int L, float inv_batch) {
+  __shared__ float s_dl[8][96];
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * 8 + wv;
+  if (r < rows && lane == 0) {
+    if (labels) {
+      const float* z = logits + r * L;
+      float mx = z[0];
+      for (int l = 1; l < L; ++l) mx = fmaxf(mx, z[l]);
+      float se = 0.f;
+      for (int l = 0; l < L; ++l) se += expf(z[l] - mx);
+      const float lse = mx + logf(se);
+      const int64_t y = labels[r];
+      for (int l = 0; l < L; ++l) s_dl[wv][l] = (expf(z[l] - lse) - (l == y ? 1.f : 0.f)) * inv_batch;
+      if (y >= 0 && y < L) atomicAdd(loss_acc, (double)(lse - z[y]) * (double)inv_batch);
+    } else {
+      for (int l = 0; l < L; ++l) s_dl[wv][l] = dlogits_in[r * L + l];
+    }
+    for (int l = 0; l < L; ++l) dlogits[r * L + l] = s_dl[wv][l];
+  }
+  __syncwarp();
+  if (r >= rows) return;
+#pragma unroll
+  for (int i = 0; i < LS_MLP / 32; ++i) {
+    const int n = i * 32 + lane;
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s = fmaf(s_dl[wv][l], __ldg(w2 + l * LS_MLP + n), s);
+    dz1[r * LS_MLP + n] = z1[r * LS_MLP + n] > 0.f ? s : 0.f;
   }
 }
 
@@ -706,6 +772,16 @@ extern "C" int howl_b200_lstm_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     HOWL_CUDA(ctx, cudaMemcpyAsync(state_out + B * LS_H, ws.cfin, sizeof(float) * B * LS_H, cudaMemcpyDeviceToDevice, st));
   }
   const int64_t rows = sequential ? (int64_t)T * B : B;
+  if (train && rows >= LH_TC_ROWS) {
+    // z1 = relu(h W1^T + b1) on the tensor cores, then the L-wide scores
+    int rc;
+    if ((rc = mbn_weight_operand3(ctx, st, v.w1, LS_MLP, LS_H, LS_H, 0, ws.wop_w1))) return rc;
+    if ((rc = mbn_pack3(ctx, st, sequential ? ws.hseq : ws.hfin, LS_H, rows, LS_H, ws.p3))) return rc;
+    if ((rc = mbn_gemm_nt3_f32(ctx, st, ws.p3, ws.wop_w1, ws.z1, LS_MLP, rows, LS_H, LS_MLP, v.b1, 1))) return rc;
+    lstm_scores_kernel<<<(unsigned)howl_ceil_div(rows, 8), 256, 0, st>>>(ws.z1, rows, v.w2, v.b2, out, ws.logits, L);
+    HOWL_LAUNCHED(ctx, "lstm_scores");
+    return HOWL_OK;
+  }
   lstm_head_fwd_kernel<<<(unsigned)howl_ceil_div(rows, 16), 256, 0, st>>>(sequential ? ws.hseq : ws.hfin, rows, ws.w1t, v.b1,
                                                                           v.w2, v.b2, train ? ws.z1 : nullptr, out,
                                                                           (sequential && !train) ? nullptr : ws.logits, L);
@@ -748,10 +824,20 @@ static int lstm_bwd_impl(howl_ctx_t* ctx, void* stream, const int64_t* lengths, 
     HOWL_LAUNCHED(ctx, "ctc");
     dlogits_in = ws.dlogits;
   }
-  lstm_head_bwd_kernel<<<(unsigned)howl_ceil_div(rows, 16), 256, 0, st>>>(ws.logits, labels, dlogits_in, ws.z1, v.w1, v.w2,
-                                                                          ws.dlogits, ws.dz1, ws.dh, ws.loss_acc, rows, L,
-                                                                          inv_batch);
-  HOWL_LAUNCHED(ctx, "lstm_head_bwd");
+  if (rows >= LH_TC_ROWS) {
+    // dlogits, dz1 (L-wide), then dh = dz1 W1 on the tensor cores
+    lstm_dz1_kernel<<<(unsigned)howl_ceil_div(rows, 8), 256, 0, st>>>(ws.logits, labels, dlogits_in, ws.z1, v.w2, ws.dlogits, ws.dz1, ws.loss_acc,
+                                                                      rows, L, inv_batch);
+    HOWL_LAUNCHED(ctx, "lstm_dz1");
+    if ((rc = mbn_weight_operand3(ctx, st, v.w1, LS_H, LS_MLP, LS_H, 1, ws.wop_w1t))) return rc;
+    if ((rc = mbn_pack3(ctx, st, ws.dz1, LS_MLP, rows, LS_MLP, ws.p3))) return rc;
+    if ((rc = mbn_gemm_nt3_f32(ctx, st, ws.p3, ws.wop_w1t, ws.dh, LS_H, rows, LS_MLP, LS_H, nullptr, 0))) return rc;
+  } else {
+    lstm_head_bwd_kernel<<<(unsigned)howl_ceil_div(rows, 16), 256, 0, st>>>(ws.logits, labels, dlogits_in, ws.z1, v.w1, v.w2,
+                                                                            ws.dlogits, ws.dz1, ws.dh, ws.loss_acc, rows, L,
+                                                                            inv_batch);
+    HOWL_LAUNCHED(ctx, "lstm_head_bwd");
+  }
   if (loss) {
     lstm_loss_kernel<<<1, 1, 0, st>>>(ws.loss_acc, loss);
     HOWL_LAUNCHED(ctx, "lstm_loss");

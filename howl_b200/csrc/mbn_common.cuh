@@ -43,3 +43,13 @@ int mbn_pack_split(howl_ctx_t* ctx, cudaStream_t st, const float* x, int64_t ld,
 // dW[n][k] (fp32, row stride ld) += sum_r X[r][n] Y[r][k] = Xhi^T Yhi + Xhi^T Ylo + Xlo^T Yhi  (|error| ~ 2^-16 per product, fp32 accumulate)
 int mbn_atb3_packed(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo, const __nv_bfloat16* yhi,
                     const __nv_bfloat16* ylo, float* dW, int64_t rows, int N, int K, int ld);
+
+// ---- fp32 C = X W^T on the tensor cores (bf16 x 3 split folded into K), used by the LSTM heads --------------------------------
+// X3 = [X_hi | X_hi | X_lo] in TMO with 3 * pad16(c) channels (mbn_tmo_bytes(rows, 3 * pad16(c)) bytes)
+int mbn_pack3(howl_ctx_t* ctx, cudaStream_t st, const float* x, int64_t ld, int64_t rows, int c, __nv_bfloat16* out);
+// W3 = [W_hi | W_lo | W_hi] operand of an fp32 [n][k] matrix (row stride ld; transpose != 0: stored [k][n])
+size_t mbn_weight_operand3_bytes(int n, int k);
+int mbn_weight_operand3(howl_ctx_t* ctx, cudaStream_t st, const float* w, int n, int k, int ld, int transpose, __nv_bfloat16* out);
+// C[row * ldc + n] = sum_k X[row][k] W[n][k] (+ bias[n]) (ReLU), fp32 row-major output
+int mbn_gemm_nt3_f32(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* x3, const __nv_bfloat16* wop3, float* C, int64_t ldc, int64_t M, int K,
+                     int N, const float* bias, int relu);

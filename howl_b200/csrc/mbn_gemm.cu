@@ -57,6 +57,11 @@ struct MgArgs {
   __nv_bfloat16* C;
   int64_t M, m_tiles;
   int k8, n8, nt, n_tiles;
+  // fp32 row-major output (C32 != null): C32[row * ldc + n] = acc (+ bias[n]) (ReLU), n < n_valid
+  float* C32;
+  int64_t ldc;
+  const float* bias;
+  int n_valid, relu;
 };
 
 __global__ void __launch_bounds__(MG_THREADS, 1) mbn_gemm_nt_kernel(const MgArgs a) {
@@ -154,6 +159,26 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mbn_gemm_nt_kernel(const MgArgs
       for (int c = 0; c < nt / 8; ++c) {
         float v[8];
         tc::tmem_ld8(taddr + 8 * c, v);
+        if (a.C32) {
+          if (valid) {
+            const int n0 = ntile * nt + c * 8;
+            float* dst = a.C32 + (mt * MBN_TILE + r) * a.ldc + n0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (a.bias && n0 + j < a.n_valid) v[j] += __ldg(a.bias + n0 + j);
+              if (a.relu) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (n0 + 8 <= a.n_valid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+              reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (n0 + j < a.n_valid) dst[j] = v[j];
+            }
+          }
+          continue;
+        }
         if (add && valid) {
           const uint4 av = __ldg(add + (size_t)c * MBN_TILE);
           const uint32_t w[4] = {av.x, av.y, av.z, av.w};
@@ -185,6 +210,7 @@ int mbn_gemm_nt(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* A, const 
                 __nv_bfloat16* C, int64_t M, int K, int N) {
   MgArgs a;
   a.A = A; a.W = wop; a.add = add; a.C = C; a.M = M; a.m_tiles = mbn_tiles(M);
+  a.C32 = nullptr; a.ldc = 0; a.bias = nullptr; a.n_valid = N; a.relu = 0;
   const int kp = mbn_pad16(K), np = mbn_pad16(N);
   a.k8 = kp / 8; a.n8 = np / 8; a.nt = mbn_ntile(np); a.n_tiles = np / a.nt;
   HOWL_REQUIRE(ctx, A && wop && C && M > 0, HOWL_E_INVALID, "mbn_gemm: bad argument");
@@ -338,6 +364,99 @@ static int mbn_gemm_wgrad_n(howl_ctx_t* ctx, cudaStream_t st, int products, cons
   HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mbn_gemm_wgrad_kernel<<<pairs * slices, MW_THREADS, smem, st>>>(a);
   HOWL_LAUNCHED(ctx, "mbn_wgrad");
+  return HOWL_OK;
+}
+
+// =============================================================================================
+// fp32 C = X W^T on the tensor cores: the three bf16 products of the (hi, lo) split as ONE GEMM over a three times longer K,
+//   X3 = [X_hi | X_hi | X_lo]  (TMO, mbn_pack3),   W3 = [W_hi | W_lo | W_hi]  (operand, mbn_weight_operand3),   fp32 accumulation in TMEM,
+// with an fp32 row-major epilogue (+ bias, ReLU).  Used by the LSTM heads.
+// =============================================================================================
+__global__ void __launch_bounds__(256) mbn_pack3_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int c, int c8,
+                                                        uint4* __restrict__ out) {
+  const int64_t n = mbn_tiles(rows) * MBN_TILE * c8;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(v % MBN_TILE), chunk = (int)((v / MBN_TILE) % c8);
+    const int64_t tile = v / MBN_TILE / c8, row = tile * MBN_TILE + r;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    if (row < rows) {
+      const float* src = x + row * ld + chunk * 8;
+      if (chunk * 8 + 8 <= c && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (chunk * 8 + j < c) f[j] = src[j];
+      }
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(f[2 * j + 1] - __bfloat162float(h1));
+      h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    // the output tensor has 3 * c8 chunks per tile: [hi | hi | lo]
+    uint4* dst = out + (tile * 3 * c8 + chunk) * MBN_TILE + r;
+    const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]);
+    dst[0] = hv;
+    dst[(size_t)c8 * MBN_TILE] = hv;
+    dst[(size_t)2 * c8 * MBN_TILE] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+int mbn_pack3(howl_ctx_t* ctx, cudaStream_t st, const float* x, int64_t ld, int64_t rows, int c, __nv_bfloat16* out) {
+  HOWL_REQUIRE(ctx, x && out && rows > 0 && c > 0, HOWL_E_INVALID, "mbn_pack3: bad argument");
+  const int c8 = mbn_pad16(c) / 8;
+  const int64_t n = mbn_tiles(rows) * MBN_TILE * c8;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  mbn_pack3_kernel<<<blocks, 256, 0, st>>>(x, ld, rows, c, c8, reinterpret_cast<uint4*>(out));
+  HOWL_LAUNCHED(ctx, "mbn_pack3");
+  return HOWL_OK;
+}
+
+// operand of W3 = [W_hi | W_lo | W_hi] for an fp32 [n][k] matrix (transpose != 0: stored [k][n]); K3 = 3 * pad16(k)
+__global__ void mbn_weight_operand3_kernel(const float* __restrict__ w, int n, int k, int ld, int transpose, int np, int kp, int nt,
+                                           __nv_bfloat16* __restrict__ out) {
+  const int k3 = 3 * kp, total = np * k3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i & 7, row = (i >> 3) % nt, chunk = ((i >> 3) / nt) % (k3 / 8), tile = (i >> 3) / (nt * (k3 / 8));
+    const int nn = tile * nt + row, kk3 = chunk * 8 + j, part = kk3 / kp, kk = kk3 - part * kp;
+    float v = 0.f;
+    if (nn < n && kk < k) v = transpose ? w[(size_t)kk * ld + nn] : w[(size_t)nn * ld + kk];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = part == 1 ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+  }
+}
+
+size_t mbn_weight_operand3_bytes(int n, int k) { return (size_t)mbn_pad16(n) * 3 * mbn_pad16(k) * 2; }
+
+int mbn_weight_operand3(howl_ctx_t* ctx, cudaStream_t st, const float* w, int n, int k, int ld, int transpose, __nv_bfloat16* out) {
+  const int np = mbn_pad16(n), kp = mbn_pad16(k), nt = mbn_ntile(np);
+  const int total = np * 3 * kp;
+  mbn_weight_operand3_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, n, k, ld, transpose, np, kp, nt, out);
+  HOWL_LAUNCHED(ctx, "mbn_weight_operand3");
+  return HOWL_OK;
+}
+
+int mbn_gemm_nt3_f32(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* x3, const __nv_bfloat16* wop3, float* C, int64_t ldc, int64_t M, int K,
+                     int N, const float* bias, int relu) {
+  MgArgs a;
+  a.A = x3; a.W = wop3; a.add = nullptr; a.C = nullptr; a.M = M; a.m_tiles = mbn_tiles(M);
+  a.C32 = C; a.ldc = ldc; a.bias = bias; a.n_valid = N; a.relu = relu;
+  const int kp3 = 3 * mbn_pad16(K), np = mbn_pad16(N);
+  a.k8 = kp3 / 8; a.n8 = np / 8; a.nt = mbn_ntile(np); a.n_tiles = np / a.nt;
+  HOWL_REQUIRE(ctx, x3 && wop3 && C && M > 0, HOWL_E_INVALID, "mbn_gemm_nt3_f32: bad argument");
+  const size_t smem = (size_t)MG_STAGES * (MG_KSTAGE * 2048 + (size_t)MG_KSTAGE * a.nt * 16);
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t items = a.m_tiles * a.n_tiles;
+  const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
+  mbn_gemm_nt_kernel<<<grid, MG_THREADS, smem, st>>>(a);
+  HOWL_LAUNCHED(ctx, "mbn_gemm");
   return HOWL_OK;
 }
 
