@@ -102,6 +102,9 @@ struct LasWs {
   double* loss_acc; // [2]
   __nv_bfloat16 *px_hi, *px_lo;   // (hi, lo) bf16 operands of the LSTM weight-gradient products: [w2p * B][384] ...
   __nv_bfloat16 *py_hi, *py_lo;   // ... and [w2p * B][8 * h2]
+  __nv_bfloat16* p3;              // [w2p * B][3 * 384]: [hi | hi | lo] of one direction's gate gradients (dx = da W_ih on the tensor cores)
+  __nv_bfloat16* wop3;            // W_ih^T operand [8 * h2][3 * 384] / W_ih operand [384][3 * 8 * h2]
+  float* xproj;                   // [w2p * B][2][384]: input projections of all steps (forward, large batches)
   size_t bytes;
 };
 static LasWs las_carve(void* base, int64_t B, const LasDims& d, int train = 0, int L = 0) {
@@ -150,8 +153,12 @@ static LasWs las_carve(void* base, int64_t B, const LasDims& d, int train = 0, i
     w.px_lo = (__nv_bfloat16*)take(mbn_tmo_bytes((int64_t)TB, LA_G));
     w.py_hi = (__nv_bfloat16*)take(mbn_tmo_bytes((int64_t)TB, d.in));
     w.py_lo = (__nv_bfloat16*)take(mbn_tmo_bytes((int64_t)TB, d.in));
+    w.p3 = (__nv_bfloat16*)take(mbn_tmo_bytes((int64_t)TB, 3 * LA_G));
+    w.wop3 = (__nv_bfloat16*)take(mbn_weight_operand3_bytes(d.in, LA_G));
+    w.xproj = (float*)take(sizeof(float) * TB * 2 * LA_G);
   } else {
-    w.px_hi = w.px_lo = w.py_hi = w.py_lo = nullptr;
+    w.px_hi = w.px_lo = w.py_hi = w.py_lo = w.p3 = w.wop3 = nullptr;
+    w.xproj = nullptr;
     w.gates = w.cseq = w.scores = w.ctxs = w.hidd = w.logits = w.dlogits = w.dctx = w.hbar = w.dhid = w.du = w.dsum = w.red = nullptr;
     w.dhseq = w.dgates = w.dx = w.draw2 = w.dpool1 = w.draw1 = nullptr;
     w.bstats = w.loss_acc = nullptr;
@@ -275,7 +282,10 @@ __global__ void las_lstm_prep_kernel(LasParams q, int in, float* __restrict__ wt
 // one direction of the recurrence for LA_NB sequences: grid = (ceil(B / LA_NB), 2), block = 384 threads (thread j = gate row j)
 __global__ void __launch_bounds__(LA_G, 1) las_lstm_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengths, const float* __restrict__ wt,
                                                           const float* __restrict__ bsum, float* __restrict__ hseq, int64_t B, int T, int in,
-                                                          float* __restrict__ gsave, float* __restrict__ csave) {
+                                                          float* __restrict__ gsave, float* __restrict__ csave,
+                                                          const float* __restrict__ xproj) {
+  // xproj != null: [T, B, 2, 384] = W_ih x_t + b_ih + b_hh of every step, computed up front as one tensor-core GEMM per direction; the loop
+  // then only carries the 96-wide recurrent product
   extern __shared__ __align__(16) float smem[];
   const int K = in + LA_H, dir = blockIdx.y, j = threadIdx.x;
   float* s_xh = smem;                         // [K][LA_NB]
@@ -291,16 +301,22 @@ __global__ void __launch_bounds__(LA_G, 1) las_lstm_kernel(const float* __restri
   const float bias = bsum[dir * LA_G + j];
   for (int step = 0; step < T; ++step) {
     const int t = dir ? T - 1 - step : step;
-    // x_t of the 16 sequences -> s_xh[k][b]
-    for (int i = j; i < in * LA_NB; i += LA_G) {
-      const int bb = i / in, k = i - bb * in;
-      s_xh[(size_t)k * LA_NB + bb] = (b0 + bb < B) ? __ldg(x + ((int64_t)t * B + b0 + bb) * in + k) : 0.f;
-    }
-    __syncthreads();
     float acc[LA_NB];
+    if (xproj) {
 #pragma unroll
-    for (int bb = 0; bb < LA_NB; ++bb) acc[bb] = bias;
-    for (int k = 0; k < K; ++k) {
+      for (int bb = 0; bb < LA_NB; ++bb)
+        acc[bb] = (b0 + bb < B) ? __ldg(xproj + (((int64_t)t * B + b0 + bb) * 2 + dir) * LA_G + j) : 0.f;
+    } else {
+      // x_t of the 16 sequences -> s_xh[k][b]
+      for (int i = j; i < in * LA_NB; i += LA_G) {
+        const int bb = i / in, k = i - bb * in;
+        s_xh[(size_t)k * LA_NB + bb] = (b0 + bb < B) ? __ldg(x + ((int64_t)t * B + b0 + bb) * in + k) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int bb = 0; bb < LA_NB; ++bb) acc[bb] = bias;
+    }
+    for (int k = xproj ? in : 0; k < K; ++k) {
       const float wv = __ldg(w + (size_t)k * LA_G + j);
       const float4* xv = reinterpret_cast<const float4*>(s_xh + (size_t)k * LA_NB);
 #pragma unroll
@@ -916,8 +932,20 @@ extern "C" int howl_b200_las_fwd(howl_ctx_t* ctx, void* stream, const float* fea
   las_lstm_prep_kernel<<<blocks, 256, 0, st>>>(q, d.in, ws.wt, ws.bsum);
   HOWL_LAUNCHED(ctx, "las_lstm_prep");
   HOWL_CUDA(ctx, cudaFuncSetAttribute(las_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem));
+  const float* xproj = nullptr;
+  if (train && (int64_t)d.w2p * B >= 1024) {
+    // input projections of every step and both directions on the tensor cores: xproj[:, dir] = x W_ih[dir]^T + b_ih + b_hh
+    const int64_t TB = (int64_t)d.w2p * B;
+    int rc;
+    if ((rc = mbn_pack3(ctx, st, ws.x, d.in, TB, d.in, ws.p3))) return rc;
+    for (int dir = 0; dir < 2; ++dir) {
+      if ((rc = mbn_weight_operand3(ctx, st, q.wih[dir], LA_G, d.in, d.in, 0, ws.wop3))) return rc;
+      if ((rc = mbn_gemm_nt3_f32(ctx, st, ws.p3, ws.wop3, ws.xproj + dir * LA_G, 2 * LA_G, TB, d.in, LA_G, ws.bsum + dir * LA_G, 0))) return rc;
+    }
+    xproj = ws.xproj;
+  }
   las_lstm_kernel<<<dim3((unsigned)howl_ceil_div(B, LA_NB), 2), LA_G, lstm_smem, st>>>(ws.x, enc_lengths, ws.wt, ws.bsum, ws.hseq, B, d.w2p, d.in,
-                                                                                       ws.gates, ws.cseq);
+                                                                                       ws.gates, ws.cseq, xproj);
   HOWL_LAUNCHED(ctx, "las_lstm");
   las_attn_prep_kernel<<<(LA_HEADS * LA_D + LA_HEADS + 255) / 256, 256, 0, st>>>(q, ws.u);
   HOWL_LAUNCHED(ctx, "las_attn_prep");
@@ -1007,8 +1035,14 @@ static int las_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const
   HOWL_LAUNCHED(ctx, "las_lstm_bwd");
   for (int dir = 0; dir < 2; ++dir) {
     const float* dg = ws.dgates + dir * LA_G;        // [TB][2 * 384], this direction's columns
-    // dx += da W_ih
-    if ((rc = las_gemm(ctx, st, dg, 2 * LA_G, 1, q.wih[dir], in, 1, ws.dx, in, TB, in, LA_G, dir == 1))) return rc;
+    // dx (+)= da W_ih: large batches on the tensor cores (C[r][k] = sum_j da[r][j] W_ih[j][k]: the weight is stored [reduction][output])
+    if (TB >= 1024) {
+      if ((rc = mbn_weight_operand3(ctx, st, q.wih[dir], in, LA_G, in, 1, ws.wop3))) return rc;
+      if ((rc = mbn_pack3(ctx, st, dg, 2 * LA_G, TB, LA_G, ws.p3))) return rc;
+      if ((rc = mbn_gemm_nt3_f32(ctx, st, ws.p3, ws.wop3, ws.dx, in, TB, LA_G, in, nullptr, 0, dir == 1))) return rc;
+    } else if ((rc = las_gemm(ctx, st, dg, 2 * LA_G, 1, q.wih[dir], in, 1, ws.dx, in, TB, in, LA_G, dir == 1))) {
+      return rc;
+    }
     // dW_ih = da^T x and dW_hh = da^T h_prev.  The previous step of the forward direction is t - 1, of the reverse direction t + 1
     // (rows shifted by B).  Large batches: tensor cores, (hi, lo) bf16 operands, three products each, fp32 accumulate.
     const float* da = dir ? dg : dg + (size_t)B * 2 * LA_G;

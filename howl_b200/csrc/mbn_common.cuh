@@ -50,6 +50,6 @@ int mbn_pack3(howl_ctx_t* ctx, cudaStream_t st, const float* x, int64_t ld, int6
 // W3 = [W_hi | W_lo | W_hi] operand of an fp32 [n][k] matrix (row stride ld; transpose != 0: stored [k][n])
 size_t mbn_weight_operand3_bytes(int n, int k);
 int mbn_weight_operand3(howl_ctx_t* ctx, cudaStream_t st, const float* w, int n, int k, int ld, int transpose, __nv_bfloat16* out);
-// C[row * ldc + n] = sum_k X[row][k] W[n][k] (+ bias[n]) (ReLU), fp32 row-major output
+// C[row * ldc + n] (+)= sum_k X[row][k] W[n][k] (+ bias[n]) (ReLU), fp32 row-major output
 int mbn_gemm_nt3_f32(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* x3, const __nv_bfloat16* wop3, float* C, int64_t ldc, int64_t M, int K,
-                     int N, const float* bias, int relu);
+                     int N, const float* bias, int relu, int accumulate = 0);

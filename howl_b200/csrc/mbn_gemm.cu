@@ -61,7 +61,7 @@ struct MgArgs {
   float* C32;
   int64_t ldc;
   const float* bias;
-  int n_valid, relu;
+  int n_valid, relu, accumulate;     // accumulate: C32 += (the second direction of a bidirectional product)
 };
 
 __global__ void __launch_bounds__(MG_THREADS, 1) mbn_gemm_nt_kernel(const MgArgs a) {
@@ -168,6 +168,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mbn_gemm_nt_kernel(const MgArgs
               if (a.bias && n0 + j < a.n_valid) v[j] += __ldg(a.bias + n0 + j);
               if (a.relu) v[j] = fmaxf(v[j], 0.f);
             }
+            if (a.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (n0 + j < a.n_valid) v[j] += dst[j];
+            }
             if (n0 + 8 <= a.n_valid && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
               reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
               reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -210,7 +215,7 @@ int mbn_gemm_nt(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* A, const 
                 __nv_bfloat16* C, int64_t M, int K, int N) {
   MgArgs a;
   a.A = A; a.W = wop; a.add = add; a.C = C; a.M = M; a.m_tiles = mbn_tiles(M);
-  a.C32 = nullptr; a.ldc = 0; a.bias = nullptr; a.n_valid = N; a.relu = 0;
+  a.C32 = nullptr; a.ldc = 0; a.bias = nullptr; a.n_valid = N; a.relu = 0; a.accumulate = 0;
   const int kp = mbn_pad16(K), np = mbn_pad16(N);
   a.k8 = kp / 8; a.n8 = np / 8; a.nt = mbn_ntile(np); a.n_tiles = np / a.nt;
   HOWL_REQUIRE(ctx, A && wop && C && M > 0, HOWL_E_INVALID, "mbn_gemm: bad argument");
@@ -444,10 +449,10 @@ int mbn_weight_operand3(howl_ctx_t* ctx, cudaStream_t st, const float* w, int n,
 }
 
 int mbn_gemm_nt3_f32(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* x3, const __nv_bfloat16* wop3, float* C, int64_t ldc, int64_t M, int K,
-                     int N, const float* bias, int relu) {
+                     int N, const float* bias, int relu, int accumulate) {
   MgArgs a;
   a.A = x3; a.W = wop3; a.add = nullptr; a.C = nullptr; a.M = M; a.m_tiles = mbn_tiles(M);
-  a.C32 = C; a.ldc = ldc; a.bias = bias; a.n_valid = N; a.relu = relu;
+  a.C32 = C; a.ldc = ldc; a.bias = bias; a.n_valid = N; a.relu = relu; a.accumulate = accumulate;
   const int kp3 = 3 * mbn_pad16(K), np = mbn_pad16(N);
   a.k8 = kp3 / 8; a.n8 = np / 8; a.nt = mbn_ntile(np); a.n_tiles = np / a.nt;
   HOWL_REQUIRE(ctx, x3 && wop3 && C && M > 0, HOWL_E_INVALID, "mbn_gemm_nt3_f32: bad argument");
