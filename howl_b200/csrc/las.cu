@@ -832,21 +832,27 @@ __global__ void __launch_bounds__(LW_ROWS * LA_C * CIN * 3) las_conv_wgrad_kerne
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accb = 0.f;
   for (int64_t row0 = (int64_t)blockIdx.x * LW_ROWS; row0 < rows; row0 += (int64_t)gridDim.x * LW_ROWS) {
     __syncthreads();
-    for (int i = tid; i < LW_ROWS * LA_C * wo; i += nth) {
-      const int rr = i / (LA_C * wo), j = i - rr * (LA_C * wo);
+    // staging by row segments: a warp copies one contiguous run (a channel row of the gradient, or one padded input row) per turn, lanes
+    // along x -- no per-element index arithmetic
+    for (int seg = tid >> 5; seg < LW_ROWS * (LA_C + CIN * 3); seg += nth >> 5) {
+      const int rr = seg / (LA_C + CIN * 3), sidx = seg - rr * (LA_C + CIN * 3);
       const int64_t row = row0 + rr;
-      const int yo = (int)(row % ho);
-      const int64_t b = row / ho;
-      s_d[i] = row < rows ? dout[((b * LA_C + j / wo) * ho + yo) * (int64_t)wo + j % wo] : 0.f;
-    }
-    for (int i = tid; i < LW_ROWS * CIN * 3 * wpad; i += nth) {
-      const int rr = i / (CIN * 3 * wpad), j = i - rr * (CIN * 3 * wpad);
-      const int64_t row = row0 + rr;
-      const int yo = (int)(row % ho);
-      const int64_t b = row / ho;
-      const int xx = j % wpad - 2, kr = (j / wpad) % 3, cc = j / (3 * wpad);
-      const int yy = yo + kr - 2;
-      s_in[i] = (row < rows && xx >= 0 && xx < wi && yy >= 0 && yy < hi) ? in[((b * CIN + cc) * hi + yy) * (int64_t)wi + xx] : 0.f;
+      const bool ok = row < rows;
+      const int yo = ok ? (int)(row % ho) : 0;
+      const int64_t b = ok ? row / ho : 0;
+      const int lane = tid & 31;
+      if (sidx < LA_C) {
+        const float* src = dout + ((b * LA_C + sidx) * ho + yo) * (int64_t)wo;
+        float* dst = s_d + (rr * LA_C + sidx) * wo;
+        for (int x = lane; x < wo; x += 32) dst[x] = ok ? src[x] : 0.f;
+      } else {
+        const int cc = (sidx - LA_C) / 3, kr = (sidx - LA_C) - cc * 3;
+        const int yy = yo + kr - 2;
+        const bool valid = ok && yy >= 0 && yy < hi;
+        const float* src = in + ((b * CIN + cc) * hi + (valid ? yy : 0)) * (int64_t)wi;
+        float* dst = s_in + ((rr * CIN + cc) * 3 + kr) * wpad;
+        for (int x = lane; x < wpad; x += 32) dst[x] = (valid && x >= 2 && x < wi + 2) ? src[x - 2] : 0.f;
+      }
     }
     __syncthreads();
     const float* dr = s_d + (r * LA_C + o) * wo;
