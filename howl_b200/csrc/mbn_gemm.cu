@@ -64,6 +64,7 @@ struct MgArgs {
   int n_valid, relu, accumulate;     // accumulate: C32 += (the second direction of a bidirectional product)
 };
 
+template <bool F32>
 __global__ void __launch_bounds__(MG_THREADS, 1) mbn_gemm_nt_kernel(const MgArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_full[MG_STAGES], bar_empty[MG_STAGES], bar_acc[2], bar_accfree[2];
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) mbn_gemm_nt_kernel(const MgArgs
       for (int c = 0; c < nt / 8; ++c) {
         float v[8];
         tc::tmem_ld8(taddr + 8 * c, v);
-        if (a.C32) {
+        if (F32) {
           if (valid) {
             const int n0 = ntile * nt + c * 8;
             float* dst = a.C32 + (mt * MBN_TILE + r) * a.ldc + n0;
@@ -220,10 +221,10 @@ int mbn_gemm_nt(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* A, const 
   a.k8 = kp / 8; a.n8 = np / 8; a.nt = mbn_ntile(np); a.n_tiles = np / a.nt;
   HOWL_REQUIRE(ctx, A && wop && C && M > 0, HOWL_E_INVALID, "mbn_gemm: bad argument");
   const size_t smem = (size_t)MG_STAGES * (MG_KSTAGE * 2048 + (size_t)MG_KSTAGE * a.nt * 16);
-  HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t items = a.m_tiles * a.n_tiles;
   const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
-  mbn_gemm_nt_kernel<<<grid, MG_THREADS, smem, st>>>(a);
+  mbn_gemm_nt_kernel<false><<<grid, MG_THREADS, smem, st>>>(a);
   HOWL_LAUNCHED(ctx, "mbn_gemm");
   return HOWL_OK;
 }
@@ -246,6 +247,7 @@ struct MwArgs {
 #define MW_THREADS 192
 #define MW_STAGES 2
 
+template <int PRODUCTS>
 __global__ void __launch_bounds__(MW_THREADS, 1) mbn_gemm_wgrad_kernel(const MwArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_full[MW_STAGES], bar_empty[MW_STAGES], bar_done;
@@ -280,7 +282,8 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mbn_gemm_wgrad_kernel(const MwA
   if (warp == 5) {
     if (tc::elect_one()) {
       uint32_t it = 0;
-      for (int p = 0; p < a.products; ++p)
+#pragma unroll
+      for (int p = 0; p < PRODUCTS; ++p)
         for (int64_t t = t0; t < t1; ++t, ++it) {
           const int s = it % MW_STAGES;
           if (it >= MW_STAGES) tc::mbar_wait(&bar_empty[s], ((it / MW_STAGES) - 1) & 1);
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(MW_THREADS, 1) mbn_gemm_wgrad_kernel(const MwA
       const uint32_t idesc = tc::instr_desc_bf16(128, a.kt, 1, 1);       // both operands MN-major: K = rows of the tile
       const uint32_t hi = tc::desc_hi(2048u);                            // stride between 8-channel groups
       uint32_t it = 0;
-      const int64_t n_it = (t1 - t0) * a.products;
+      const int64_t n_it = (t1 - t0) * PRODUCTS;
       for (int64_t tt = 0; tt < n_it; ++tt, ++it) {
         const int s = it % MW_STAGES;
         tc::mbar_wait(&bar_full[s], (it / MW_STAGES) & 1);
@@ -366,9 +369,15 @@ static int mbn_gemm_wgrad_n(howl_ctx_t* ctx, cudaStream_t st, int products, cons
   if (slices < 1) slices = 1;
   a.slices = slices;
   const size_t smem = (size_t)MW_STAGES * (16 * 2048 + (size_t)(a.kt / 8) * 2048) + 2048;
-  HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mbn_gemm_wgrad_kernel<<<pairs * slices, MW_THREADS, smem, st>>>(a);
-  HOWL_LAUNCHED(ctx, "mbn_wgrad");
+  if (products == 3) {
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_gemm_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mbn_gemm_wgrad_kernel<3><<<pairs * slices, MW_THREADS, smem, st>>>(a);
+    HOWL_LAUNCHED(ctx, "mbn_wgrad3");
+  } else {
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_gemm_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mbn_gemm_wgrad_kernel<1><<<pairs * slices, MW_THREADS, smem, st>>>(a);
+    HOWL_LAUNCHED(ctx, "mbn_wgrad");
+  }
   return HOWL_OK;
 }
 
@@ -457,11 +466,11 @@ int mbn_gemm_nt3_f32(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* x3, 
   a.k8 = kp3 / 8; a.n8 = np / 8; a.nt = mbn_ntile(np); a.n_tiles = np / a.nt;
   HOWL_REQUIRE(ctx, x3 && wop3 && C && M > 0, HOWL_E_INVALID, "mbn_gemm_nt3_f32: bad argument");
   const size_t smem = (size_t)MG_STAGES * (MG_KSTAGE * 2048 + (size_t)MG_KSTAGE * a.nt * 16);
-  HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t items = a.m_tiles * a.n_tiles;
   const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
-  mbn_gemm_nt_kernel<<<grid, MG_THREADS, smem, st>>>(a);
-  HOWL_LAUNCHED(ctx, "mbn_gemm");
+  mbn_gemm_nt_kernel<true><<<grid, MG_THREADS, smem, st>>>(a);
+  HOWL_LAUNCHED(ctx, "mbn_gemm_f32");
   return HOWL_OK;
 }
 

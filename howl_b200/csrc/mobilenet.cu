@@ -784,20 +784,30 @@ __global__ void __launch_bounds__(256) mbn_bn_bwd_stats_kernel(const uint4* __re
     sc[j] = bn[c]; sh[j] = bn[cp + c]; mu[j] = bn[2 * cp + c]; rs[j] = bn[3 * cp + c];
     part[j] = part[8 + j] = 0.f;
   }
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
-    const size_t idx = mbn_vec(r, chunk, c8);
-    float g[8], x[8];
-    mb_unpack(dy[idx], g);
-    mb_unpack(raw[idx], x);
+  // two rows per thread and iteration: four 16-byte loads in flight before the first use (the kernel is register-limited to a few
+  // warps per SM, so the bytes in flight per thread are what feeds HBM)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += 2 * stride) {
+    const int64_t r2 = r + stride;
+    const bool two = r2 < rows;
+    const size_t idx = mbn_vec(r, chunk, c8), idx2 = mbn_vec(two ? r2 : r, chunk, c8);
+    const uint4 qg = dy[idx], qx = raw[idx], qg2 = dy[idx2], qx2 = raw[idx2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float dn = g[j];
-      if (act) {
-        const float n = fmaf(x[j], sc[j], sh[j]);
-        if (!(n > 0.f && n < 6.f)) dn = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      float g[8], x[8];
+      mb_unpack(h ? qg2 : qg, g);
+      mb_unpack(h ? qx2 : qx, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dn = g[j];
+        if (act) {
+          const float n = fmaf(x[j], sc[j], sh[j]);
+          if (!(n > 0.f && n < 6.f)) dn = 0.f;
+        }
+        part[j] += dn;
+        part[8 + j] = fmaf(dn, (x[j] - mu[j]) * rs[j], part[8 + j]);
       }
-      part[j] += dn;
-      part[8 + j] = fmaf(dn, (x[j] - mu[j]) * rs[j], part[8 + j]);
     }
   }
   __shared__ float s_part[8][16];
@@ -821,40 +831,53 @@ __global__ void __launch_bounds__(256) mbn_bn_bwd_apply_kernel(const uint4* __re
                                                                uint4* __restrict__ draw, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta) {
   const int chunk = blockIdx.y, c8 = cp / 8;
-  float sc[8], sh[8], mu[8], rs[8], k0[8], m1[8], m2[8];
+  // dRaw = k0 (dn - m1 - (x - mu) rs m2) = k0 dn + ka x + kb
+  float sc[8], sh[8], k0[8], ka[8], kb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = chunk * 8 + j;
-    sc[j] = bn[ch]; sh[j] = bn[cp + ch]; mu[j] = bn[2 * cp + ch]; rs[j] = bn[3 * cp + ch];
-    k0[j] = bn[4 * cp + ch] * rs[j];
-    m1[j] = (float)(stats[ch] / count);
-    m2[j] = (float)(stats[cp + ch] / count);
+    const float mu = bn[2 * cp + ch], rs = bn[3 * cp + ch];
+    sc[j] = bn[ch]; sh[j] = bn[cp + ch];
+    k0[j] = bn[4 * cp + ch] * rs;
+    const float m1 = (float)(stats[ch] / count), m2 = (float)(stats[cp + ch] / count);
+    ka[j] = -k0[j] * rs * m2;
+    kb[j] = -k0[j] * m1 - ka[j] * mu;
     if (blockIdx.x == 0 && threadIdx.x == 0 && ch < c) {     // parameter gradients of the affine transform
       dgamma[ch] = (float)stats[cp + ch];
       dbeta[ch] = (float)stats[ch];
     }
   }
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows_pad; r += (int64_t)gridDim.x * blockDim.x) {
-    const size_t idx = mbn_vec(r, chunk, c8);
-    float g[8];
-    if (r < rows) {
-      float x[8];
-      mb_unpack(dy[idx], g);
-      mb_unpack(raw[idx], x);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows_pad; r += 2 * stride) {
+    const int64_t r2 = r + stride;
+    const bool two = r2 < rows_pad;
+    const size_t idx = mbn_vec(r, chunk, c8), idx2 = mbn_vec(two ? r2 : r, chunk, c8);
+    uint4 qg = make_uint4(0u, 0u, 0u, 0u), qx = qg, qg2 = qg, qx2 = qg;
+    if (r < rows) { qg = dy[idx]; qx = raw[idx]; }
+    if (two && r2 < rows) { qg2 = dy[idx2]; qx2 = raw[idx2]; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float dn = g[j];
-        if (act) {
-          const float n = fmaf(x[j], sc[j], sh[j]);
-          if (!(n > 0.f && n < 6.f)) dn = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      float g[8];
+      if ((h ? r2 : r) < rows) {
+        float x[8];
+        mb_unpack(h ? qg2 : qg, g);
+        mb_unpack(h ? qx2 : qx, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dn = g[j];
+          if (act) {
+            const float n = fmaf(x[j], sc[j], sh[j]);
+            if (!(n > 0.f && n < 6.f)) dn = 0.f;
+          }
+          g[j] = fmaf(k0[j], dn, fmaf(ka[j], x[j], kb[j]));
         }
-        g[j] = k0[j] * (dn - m1[j] - (x[j] - mu[j]) * rs[j] * m2[j]);
-      }
-    } else {
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+      }
+      draw[h ? idx2 : idx] = mb_pack(g);
     }
-    draw[idx] = mb_pack(g);
   }
 }
 
