@@ -499,8 +499,14 @@ def main_ours(a):
         fe = next((g for g in groups if g["name"] == "frontend"), None)
         if fe:
             gbs = B * (a.samples * 4 + frames_of(a.samples) * N_MELS * 4) / (fe["ms"] / 1e3) / 1e9
+            # 1.0 MFLOP per 1 s utterance (FFT 0.93 + sparse mel 0.08), scaled with the frame count
+            fe_flop = B * 1.0e6 * frames_of(a.samples) / 81.0
             roofline["frontend"] = {"bound": "hbm", "ms": fe["ms"], "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"],
-                                    "frac": gbs / peaks["hbm_gbs"], "traffic": traffic.get("frontend")}
+                                    "frac": gbs / peaks["hbm_gbs"], "traffic": traffic.get("frontend"),
+                                    "fp32_tflops_algorithmic": fe_flop / (fe["ms"] / 1e3) / 1e12,
+                                    "fp32_frac": fe_flop / (fe["ms"] / 1e3) / 1e12 / FP32_PEAK_TFLOPS,
+                                    "note": "HBM is the roof SURVEY 8(d) names for K1; at 13-34 FLOP/B (twice that with int16 PCM) the kernel sits at "
+                                            "the FP32 ridge and is bound by instruction issue of the FFT (DESIGN.md section 4)"}
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             sample = min(a.cpu_sample, B)
