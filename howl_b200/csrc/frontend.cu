@@ -39,13 +39,13 @@ struct FeBank {
   int filt_off[HOWL_MAX_MELS + 1];    // entries of filter m (one per block it overlaps): filt_idx[filt_off[m] .. filt_off[m + 1])
   int filt_idx[32 * HOWL_MAX_MELS];
 };
-#define FE_ENT_WORDS 9
+#define FE_ENT_WORDS 8          // the 8 weights of a (block of 8 bins, filter) pair: two aligned 128-bit shared-memory reads
 
 struct FeParams {
   const float* pcm;
   const float* fb;        // dense [257, M] bank (only read by the fallback for banks with more than FE_ENT_SMEM entries)
   const FeBank* bank;
-  const float* ent;       // [n_entries][9] words: m (as int bits), w[8]
+  const float* ent;       // [n_entries][8]: the weights of bins 8 blk .. 8 blk + 7 for one (block, filter) pair
   const float* window;
   const float2* tw_lane;  // [32][8]: W256^(L * m2), m2 = 0..7
   const float2* tw_stage; // [32][4]: the cross-lane stage twiddles of lane L (spans 16, 8, 4, 2)
@@ -112,13 +112,12 @@ __global__ void __launch_bounds__(1024) fb_compact_kernel(const float* __restric
     bank->ny_count = n;
   }
   __syncthreads();
-  // entries: thread per (block, filter) pair writes its 9 words; per-filter lists: thread per filter
+  // entries: thread per (block, filter) pair writes its 8 weights; per-filter lists: thread per filter
   for (int pidx = tid; pidx < 32 * M; pidx += blockDim.x) {
     const int blk = pidx / M, m = pidx - blk * M;
     if (!s_nz[blk][m]) continue;
     const int e = s_off[blk] + s_ent[blk][m];
-    ent[e * FE_ENT_WORDS] = __int_as_float(m);
-    for (int i = 0; i < 8; ++i) ent[e * FE_ENT_WORDS + 1 + i] = fb[(8 * blk + i) * M + m];
+    for (int i = 0; i < 8; ++i) ent[e * FE_ENT_WORDS + i] = fb[(8 * blk + i) * M + m];
   }
   if (tid < M) {
     int n = s_fcnt[tid];
@@ -195,10 +194,11 @@ __device__ __forceinline__ void fft256_warp(float2* v, const float2* tw, const f
   for (int s = 0; s < 5; ++s) {
     const int h = 16 >> s;
     const bool upper = (lane & h) != 0;
+    const float sgn = upper ? -1.f : 1.f;          // partner + sgn * own: one FFMA per component, the same rounding as the add / subtract
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const float ox = __shfl_xor_sync(0xffffffffu, v[r].x, h), oy = __shfl_xor_sync(0xffffffffu, v[r].y, h);
-      float2 t = upper ? make_float2(ox - v[r].x, oy - v[r].y) : make_float2(v[r].x + ox, v[r].y + oy);
+      float2 t = make_float2(fmaf(sgn, v[r].x, ox), fmaf(sgn, v[r].y, oy));
       if (s < 3) t = cmul(t, st[s]);              // st[s] = 1 in the lower lane
       else if (s == 3 && upper && (lane & 1)) t = cmul_mi(t);      // W4^1 = -i
       v[r] = t;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams 
   float* s_pcm = reinterpret_cast<float*>(smem_raw);
   float* s_win = s_pcm + ((span_cap + 3) & ~3);
   float2* s_w512 = reinterpret_cast<float2*>(s_win + HOWL_NFFT);            // [8][32 lanes]
-  float* s_ent = reinterpret_cast<float*>(s_w512 + 256);                    // [FE_ENT_SMEM][9]
+  float* s_ent = reinterpret_cast<float*>(s_w512 + 256);                    // [FE_ENT_SMEM][8]
   float* s_part = s_ent + FE_ENT_SMEM * FE_ENT_WORDS;                       // [FE_WARPS][FE_ENT_SMEM] partial sums of the entries
   float* s_res = s_part + FE_WARPS * FE_PART;                               // [FE_TILE][M]
   int* s_fidx = reinterpret_cast<int*>(s_res + FE_TILE * p.M);              // [FE_ENT_SMEM] entry ids grouped by filter
@@ -346,10 +346,11 @@ __global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams 
     const float nyq0 = __shfl_sync(0xffffffffu, nyq, 0);
     if (small_bank) {
       for (int eidx = e_begin; eidx < e_end; ++eidx) {
-        const float* ep = s_ent + eidx * FE_ENT_WORDS;
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(pw[i], ep[1 + i], acc);
+        const float4 w0 = *reinterpret_cast<const float4*>(s_ent + eidx * FE_ENT_WORDS);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_ent + eidx * FE_ENT_WORDS + 4);
+        float acc = pw[0] * w0.x;
+        acc = fmaf(pw[1], w0.y, acc); acc = fmaf(pw[2], w0.z, acc); acc = fmaf(pw[3], w0.w, acc);
+        acc = fmaf(pw[4], w1.x, acc); acc = fmaf(pw[5], w1.y, acc); acc = fmaf(pw[6], w1.z, acc); acc = fmaf(pw[7], w1.w, acc);
         part[eidx] = acc;
       }
     } else {
