@@ -8,7 +8,10 @@
 // step and CTA, coalesced along j).  The cell update is done by the same 512 threads on (sequence, unit) pairs.  For
 // training the activated gates, cell states and the xh rows are kept in the workspace; the backward walks the steps in
 // reverse (dh through W_hh with a 4-way split of the 512-long reduction) and leaves the pre-activation gradients in
-// place of the gates, so that the weight gradients are two tall-skinny A^T B products (lstm_atb_kernel) over all (t, b).
+// place of the gates, so that the weight gradients are tall-skinny A^T B products over all (t, b) rows: on the tensor cores
+// (operands split into (hi, lo) bf16, three products through one TMEM accumulator, mbn_gemm.cu) for training-size batches, the
+// exact-fp32 lstm_atb_kernel for a few hundred rows.  The per-frame MLP head of seq-lstm (X W^T over all T * B rows) runs on
+// the tensor cores the same way (bf16 x 3 folded into K, fp32 epilogue); the recurrence itself is FP32 FFMA.
 #include <math.h>
 
 #include "common.cuh"

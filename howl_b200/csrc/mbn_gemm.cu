@@ -9,6 +9,9 @@
 //  * mbn_gemm_wgrad_kernel: dW = dC^T * A, the reduction runs over the ROWS, so both operands are read MN-major straight from the
 //    same tiles (K = 16 rows per MMA); the [128 x Kt] accumulator stays in TMEM across all row tiles of a CTA and is added to the
 //    fp32 gradient with atomics once.
+//  * fp32 products for the LSTM / LAS paths reuse both kernels with the operands split into (hi, lo) bf16: A^T B as three operand pairs
+//    streaming through one accumulator (mbn_atb3_packed), X W^T with the split folded into K ([hi|hi|lo] x [hi|lo|hi], mbn_gemm_nt3_f32)
+//    and an fp32 row-major epilogue (+ bias, ReLU, accumulate).
 #include <algorithm>
 
 #include "mbn_common.cuh"

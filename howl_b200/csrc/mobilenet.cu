@@ -5,8 +5,9 @@
 // Every tensor between layers is in the tile-major operand format of mbn_common.cuh, so
 //   * the 35 pointwise (1x1) convolutions and the 3x3 stride-2 entry convolution (as an im2col GEMM) -- >90 % of the flops -- and their
 //     data / weight gradients run on the tensor cores (mbn_gemm.cu, tcgen05 + TMEM, operands landed by TMA);
-//   * the depthwise 3x3 convolutions are bandwidth-bound stencils on 16-byte (8-channel) vectors with the producer's BatchNorm + ReLU6
-//     applied while loading, so the expanded tensors are stored once (raw) and never in normalised form;
+//   * the depthwise 3x3 convolutions are stencils on 16-byte (8-channel) vectors over image tiles staged in shared memory (register-
+//     resident images for the small late layers), with the producer's BatchNorm + ReLU6 applied while staging, so the expanded tensors
+//     are stored once (raw) and never in normalised form;
 //   * BatchNorm needs batch statistics before anything can be normalised: [conv -> statistics -> finalize -> consumer applies].
 // Layer order, parameter order and names follow the reference's state_dict (SURVEY App. B.2 / BASELINE.md: 2,262,338 parameters at
 // 30 labels).
