@@ -680,85 +680,65 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict
                                                           float* __restrict__ dbout, double* __restrict__ stats6,
                                                           const double* __restrict__ loss_acc, float* __restrict__ loss,
                                                           int64_t B, int L) {
-  __shared__ double sh[8][96];
+  // grid = (L + 2 roles, batch slices): every CTA reduces its slice of the batch and accumulates into the (zeroed) outputs
+  __shared__ double sh[8][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int blk = blockIdx.x;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;   // up to three columns per lane
-  if (blk < L) {
-    for (int64_t b = warp; b < B; b += 8) {
+  const int64_t per = (B + gridDim.y - 1) / gridDim.y;
+  const int64_t lo = (int64_t)blockIdx.y * per, hi = lo + per < B ? lo + per : B;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (blk < L) {                       // d output.weight[blk][lane], [lane + 32]
+    for (int64_t b = lo + warp; b < hi; b += 8) {
       const double d = dlogits[b * L + blk];
       a0 += d * pooled[b * R8_C + lane];
       if (lane + 32 < R8_C) a1 += d * pooled[b * R8_C + lane + 32];
     }
-  } else if (blk == L) {
-    for (int64_t b = warp; b < B; b += 8) {
+  } else if (blk == L) {               // d output.bias
+    for (int64_t b = lo + warp; b < hi; b += 8) {
       if (lane < L) a0 += dlogits[b * L + lane];
       if (lane + 32 < L) a1 += dlogits[b * L + lane + 32];
       if (lane + 64 < L) a2 += dlogits[b * L + lane + 64];
     }
-  } else {
-    for (int64_t b = warp; b < B; b += 8) {
+  } else {                             // BatchNorm-6 backward statistics: sum dh, sum dh * pooled per channel
+    for (int64_t b = lo + warp; b < hi; b += 8) {
       const float d0 = dh[b * R8_C + lane];
       a0 += d0;
-      a1 += (double)d0 * pooled[b * R8_C + lane];   // lanes 0..31
-    }
-    // channels 32..44 in a second sweep
-    double c0 = 0.0, c1 = 0.0;
-    if (lane + 32 < R8_C)
-      for (int64_t b = warp; b < B; b += 8) {
-        const float d0 = dh[b * R8_C + lane + 32];
-        c0 += d0;
-        c1 += (double)d0 * pooled[b * R8_C + lane + 32];
-      }
-    sh[warp][lane] = a0;
-    sh[warp][32 + lane] = a1;
-    __syncthreads();
-    double t0 = 0.0, t1 = 0.0;
-    if (warp == 0) {
-      for (int w = 0; w < 8; ++w) {
-        t0 += sh[w][lane];
-        t1 += sh[w][32 + lane];
-      }
-    }
-    __syncthreads();
-    sh[warp][lane] = c0;
-    sh[warp][32 + lane] = c1;
-    __syncthreads();
-    if (warp == 0) {
-      stats6[lane] = t0;
-      stats6[R8_C + lane] = t1;
+      a1 += (double)d0 * pooled[b * R8_C + lane];
       if (lane + 32 < R8_C) {
-        double u0 = 0.0, u1 = 0.0;
-        for (int w = 0; w < 8; ++w) {
-          u0 += sh[w][lane];
-          u1 += sh[w][32 + lane];
-        }
-        stats6[32 + lane] = u0;
-        stats6[R8_C + 32 + lane] = u1;
+        const float d1 = dh[b * R8_C + lane + 32];
+        a2 += d1;
+        a3 += (double)d1 * pooled[b * R8_C + lane + 32];
       }
-      if (lane == 0) *loss = (float)(*loss_acc);
     }
-    return;
   }
   sh[warp][lane] = a0;
   sh[warp][32 + lane] = a1;
   sh[warp][64 + lane] = a2;
+  sh[warp][96 + lane] = a3;
   __syncthreads();
-  if (warp == 0) {
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-    for (int w = 0; w < 8; ++w) {
-      t0 += sh[w][lane];
-      t1 += sh[w][32 + lane];
-      t2 += sh[w][64 + lane];
+  if (warp != 0) return;
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  for (int w = 0; w < 8; ++w) {
+    t0 += sh[w][lane];
+    t1 += sh[w][32 + lane];
+    t2 += sh[w][64 + lane];
+    t3 += sh[w][96 + lane];
+  }
+  if (blk < L) {
+    atomicAdd(dwout + blk * R8_C + lane, (float)t0);
+    if (lane + 32 < R8_C) atomicAdd(dwout + blk * R8_C + lane + 32, (float)t1);
+  } else if (blk == L) {
+    if (lane < L) atomicAdd(dbout + lane, (float)t0);
+    if (lane + 32 < L) atomicAdd(dbout + lane + 32, (float)t1);
+    if (lane + 64 < L) atomicAdd(dbout + lane + 64, (float)t2);
+  } else {
+    atomicAdd(stats6 + lane, t0);
+    atomicAdd(stats6 + R8_C + lane, t1);
+    if (lane + 32 < R8_C) {
+      atomicAdd(stats6 + 32 + lane, t2);
+      atomicAdd(stats6 + R8_C + 32 + lane, t3);
     }
-    if (blk < L) {
-      dwout[blk * R8_C + lane] = (float)t0;
-      if (lane + 32 < R8_C) dwout[blk * R8_C + lane + 32] = (float)t1;
-    } else {
-      if (lane < L) dbout[lane] = (float)t0;
-      if (lane + 32 < L) dbout[lane + 32] = (float)t1;
-      if (lane + 64 < L) dbout[lane + 64] = (float)t2;
-    }
+    if (lane == 0 && blockIdx.y == 0) *loss = (float)(*loss_acc);
   }
 }
 
@@ -977,7 +957,7 @@ static int r8_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
                                                                    ws.dh, ws.loss_acc, B, L,
                                                                    1.f / (float)loss_scale_batch);
   HOWL_LAUNCHED(ctx, "head_bwd");
-  head_wgrad_kernel<<<L + 2, 256, 0, st>>>(ws.dlogits, ws.pooled, ws.dh, g_wout, g_bout,
+  head_wgrad_kernel<<<dim3(L + 2, (unsigned)std::max<int64_t>(1, std::min<int64_t>(16, B / 128))), 256, 0, st>>>(ws.dlogits, ws.pooled, ws.dh, g_wout, g_bout,
                                            ws.stats_bwd + 5 * 2 * R8_C, ws.loss_acc, loss ? loss : (float*)ws.loss_acc + 2,
                                            B, L);
   HOWL_LAUNCHED(ctx, "head_wgrad");
