@@ -211,22 +211,29 @@ class LstmTrainStep(_HostPipeline):
         self.step_count = 0
         self._init_host_pipeline()
 
-    def step(self, pcm: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    def step(self, pcm: torch.Tensor, labels: torch.Tensor, rects: Optional[torch.Tensor] = None, fb: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """rects [B,4] int32 (SpecAugment rectangles) / fb [257,M] (a VTLP-warped bank for this step) select the stage-by-stage path
+        (the fused entry point takes the plain features); a smaller last batch uses a prefix of the buffers."""
         self.step_count += 1
         c = self.ctx
-        if self.world == 1:
-            c.lstm_train_step(pcm, labels, self.lengths, self.steps, self.fb, self.zmuv, self.params, self.grads, self.m, self.v,
-                              self.step_count, self.lr, self.weight_decay, self.loss, self.logits, self.ws)
+        b = pcm.shape[0]
+        if b > self.batch:
+            raise ValueError(f"batch of {b} exceeds the step's capacity {self.batch}")
+        lengths, logits = self.lengths[:b], self.logits[:b]
+        if self.world == 1 and rects is None and fb is None:
+            c.lstm_train_step(pcm, labels, lengths, self.steps, self.fb, self.zmuv, self.params, self.grads, self.m, self.v,
+                              self.step_count, self.lr, self.weight_decay, self.loss, logits, self.ws)
         else:
-            from .parallel import allreduce_flat_grads
-
-            feats = self.ws[: self.batch * self.frames * c.n_mels * 4].view(torch.float32).view(self.batch, self.frames, c.n_mels)
+            feats = self.ws[: b * self.frames * c.n_mels * 4].view(torch.float32).view(b, self.frames, c.n_mels)
             ws = self.ws[self.feat_bytes:]
-            c.frontend(pcm, self.fb, "time_major", zmuv=self.zmuv, out=feats)
-            c.lstm_fwd(feats, self.lengths, self.steps, self.params, ws, train=True, out=self.logits)
-            c.lstm_bwd(tuple(feats.shape), self.lengths, self.steps, labels, self.params, self.grads, self.loss, ws,
-                       loss_scale_batch=self.batch * self.world)
-            allreduce_flat_grads(self.grads)
+            c.frontend(pcm, self.fb if fb is None else fb, "time_major", zmuv=self.zmuv, rects=rects, out=feats)
+            c.lstm_fwd(feats, lengths, self.steps, self.params, ws, train=True, out=logits)
+            c.lstm_bwd(tuple(feats.shape), lengths, self.steps, labels, self.params, self.grads, self.loss, ws,
+                       loss_scale_batch=b * self.world)
+            if self.world > 1:
+                from .parallel import allreduce_flat_grads
+
+                allreduce_flat_grads(self.grads)
             c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
         return self.loss
 
@@ -295,23 +302,28 @@ class MobileNetTrainStep(_HostPipeline):
         self.step_count = 0
         self._init_host_pipeline()
 
-    def step(self, pcm: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    def step(self, pcm: torch.Tensor, labels: torch.Tensor, rects: Optional[torch.Tensor] = None, fb: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """rects / fb as in LstmTrainStep.step."""
         self.step_count += 1
         c, mb = self.ctx, self.mb
         seed = self.seed * 1000003 + self.step_count
-        if self.world == 1:
+        b = pcm.shape[0]
+        if b > self.batch:
+            raise ValueError(f"batch of {b} exceeds the step's capacity {self.batch}")
+        logits = self.logits[:b]
+        if self.world == 1 and rects is None and fb is None:
             mb.train_step(c, pcm, labels, self.fb, self.zmuv, self.params, self.bn_running, self.nbt, self.grads, self.m, self.v,
-                          self.step_count, self.lr, self.weight_decay, self.dropout_p, seed, self.loss, self.logits, self.ws)
+                          self.step_count, self.lr, self.weight_decay, self.dropout_p, seed, self.loss, logits, self.ws)
         else:
-            from .parallel import allreduce_flat_grads
-
-            b = pcm.shape[0]
             feats = self.ws[: b * self.frames * c.n_mels * 4].view(torch.float32).view(b, c.n_mels, self.frames)
             ws = self.ws[self.feat_bytes:]
-            c.frontend(pcm, self.fb, "mels", zmuv=self.zmuv, out=feats)
-            mb.forward(c, feats, self.params, self.bn_running, self.nbt, True, ws, self.dropout_p, seed, logits=self.logits)
+            c.frontend(pcm, self.fb if fb is None else fb, "mels", zmuv=self.zmuv, rects=rects, out=feats)
+            mb.forward(c, feats, self.params, self.bn_running, self.nbt, True, ws, self.dropout_p, seed, logits=logits)
             mb.backward(c, feats, labels, self.params, self.grads, self.loss, ws, self.dropout_p, seed, loss_scale_batch=b * self.world)
-            allreduce_flat_grads(self.grads)
+            if self.world > 1:
+                from .parallel import allreduce_flat_grads
+
+                allreduce_flat_grads(self.grads)
             c.adamw(self.params, self.grads, self.m, self.v, self.step_count, self.lr, self.weight_decay)
         return self.loss
 
@@ -358,14 +370,21 @@ class LasTrainStep(_HostPipeline):
         self.step_count = 0
         self._init_host_pipeline()
 
-    def step(self, pcm: torch.Tensor, labels: torch.Tensor, lengths=None) -> torch.Tensor:
-        """pcm [B, T] f32 / int16, labels [B] i64 on the device; lengths [B] i64 = samples per clip (None: full clips)."""
+    def step(self, pcm: torch.Tensor, labels: torch.Tensor, lengths=None, rects: Optional[torch.Tensor] = None,
+             fb: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pcm [B, T] f32 / int16, labels [B] i64 on the device; lengths [B] i64 = samples per clip (None: full clips); rects / fb as in
+        LstmTrainStep.step.  The stacked layout applies the SpecAugment mask after the delta channels, as the reference does
+        (spectrogram_augmentations run on the transform's output, train.py:289-290)."""
         self.step_count += 1
         c, las = self.ctx, self.las
         b = pcm.shape[0]
+        if b > self.batch:
+            raise ValueError(f"batch of {b} exceeds the step's capacity {self.batch}")
         seed = self.seed * 1000003 + self.step_count
         feats = self.feats[:b]
-        c.frontend(pcm, self.fb, "stacked", zmuv=self.zmuv, out=feats)
+        c.frontend(pcm, self.fb if fb is None else fb, "stacked", zmuv=self.zmuv, out=feats)
+        if rects is not None:
+            c.spec_mask(feats, rects)
         if lengths is None:
             enc = self.full_lengths[:b]
         else:
@@ -409,14 +428,28 @@ class Trainer:
         self.step_obj = None
         self._aug = None
         self.epoch = 0
-        if training_cfg.model_config.architecture != "res8":
-            raise NotImplementedError(f"Trainer: fused training step exists for res8, not {training_cfg.model_config.architecture!r}")
+        if training_cfg.model_config.architecture not in self.STEPS:
+            raise NotImplementedError(f"Trainer: a CUDA training step exists for {sorted(self.STEPS)}, not "
+                                      f"{training_cfg.model_config.architecture!r}")
+
+    # frame-objective steps by registry name (the CTC objective of seq-lstm needs targets: SeqLstmCtcTrainStep, driven directly)
+    STEPS = {"res8": "Res8TrainStep", "mobilenet": "MobileNetTrainStep", "lstm": "LstmTrainStep", "las": "LasTrainStep"}
 
     def _ensure_step(self, pcm: torch.Tensor, zmuv):
-        if self.step_obj is None:
+        """The step object is built for the first batch; res8 grows its buffers with the batch, the other models are sized for the
+        largest batch seen at construction (pass the largest batch first, or construct the step yourself)."""
+        if self.step_obj is None or (not isinstance(self.step_obj, Res8TrainStep) and pcm.shape[0] > self.step_obj.batch):
             cfg = self.training_cfg
-            self.step_obj = Res8TrainStep(self.device, num_labels=self.context.num_labels, batch=pcm.shape[0], samples=pcm.shape[1],
-                                          lr=cfg.learning_rate, weight_decay=cfg.weight_decay, zmuv=zmuv, seed=self.context_cfg.seed)
+            cls = globals()[self.STEPS[cfg.model_config.architecture]]
+            old = self.step_obj
+            self.step_obj = cls(self.device, num_labels=self.context.num_labels, batch=pcm.shape[0], samples=pcm.shape[1],
+                                lr=cfg.learning_rate if old is None else old.lr, weight_decay=cfg.weight_decay, zmuv=zmuv,
+                                seed=self.context_cfg.seed)
+            if old is not None:       # a larger batch arrived: keep the trained state
+                for name in ("params", "m", "v", "bn_running", "nbt"):
+                    if hasattr(old, name):
+                        getattr(self.step_obj, name).copy_(getattr(old, name))
+                self.step_obj.step_count = old.step_count
         return self.step_obj
 
     def train_epoch(self, batches, zmuv=(0.0, 1.0), augment: bool = True) -> float:

@@ -318,3 +318,28 @@ def test_device_wave_augmentation_matches_reference_chain_and_noise_statistics()
         assert out[r].max() <= 1.0 and out[r].min() >= -0.75 - 1e-6            # 0.25 + 1 clamps to 1, 0.25 - 1 = -0.75
     assert (out[6] == 1.0).any() and out[6].min() >= -0.75 - 1e-6               # the noise mask itself is clamped to [-1, 1] first
     ctx.close()
+
+
+@pytest.mark.parametrize("arch", ["lstm", "mobilenet", "las"])
+def test_trainer_runs_every_accelerated_architecture(arch):
+    """Trainer.train_epoch drives the CUDA step of every accelerated frame-objective model with the reference's augmentation draws
+    (VTLP bank for the step, SpecAugment rectangles); a smaller batch uses a prefix, a larger one rebuilds the step and keeps the state."""
+    from howl_b200.config import TrainingConfig
+    from howl_b200.trainer import Trainer
+
+    cfg = TrainingConfig(**{"num_epochs": 1, "learning_rate": 0.002, "lr_decay": 0.5, "weight_decay": 1e-5,
+                            "context_config": {"vocab": ["hey", "fire", "fox"], "token_type": "word", "seed": 3},
+                            "model_config": {"architecture": arch}})
+    tr = Trainer(cfg, device="cuda:0")
+    sizes = [(12, 16000), (8, 16000), (16, 16000)]
+    batches = [O.synthetic_batch(b, t, 4, seed=i) for i, (b, t) in enumerate(sizes)]
+    random.seed(5)
+    loss = tr.train_epoch(batches[:2], zmuv=(-1.8, 3.9))
+    assert np.isfinite(loss) and tr.step_obj.step_count == 2 and tr.step_obj.batch == 12
+    before = tr.step_obj.params.clone()
+    loss2 = tr.train_epoch(batches[2:], zmuv=(-1.8, 3.9), augment=False)
+    assert np.isfinite(loss2) and tr.step_obj.step_count == 3 and tr.step_obj.batch == 16
+    delta = (tr.step_obj.params - before).abs().max().item()
+    assert 0 < delta < 0.05                       # the rebuilt step continued from the trained parameters (one AdamW step away)
+    with pytest.raises(NotImplementedError):
+        Trainer(TrainingConfig(**{"context_config": {"vocab": ["a"], "token_type": "word"}, "model_config": {"architecture": "gru"}}))
