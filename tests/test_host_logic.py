@@ -343,3 +343,18 @@ def test_operand_format_row_group_transpose():
                     new[lane][j + s] = got
         d = new
     assert (d == np.arange(64).reshape(8, 8).T).all()
+
+
+def test_flat_parameter_layouts_have_the_reference_sizes():
+    """Host-side shape tables behind the flat parameter buffers (no CUDA): totals of BASELINE.md / SURVEY App. B.2 at 30 labels, and the
+    Trainer's table of CUDA training steps names classes that exist."""
+    import math
+
+    from howl_b200 import las, mobilenet, trainer
+
+    assert sum(math.prod(s) for _, s in las.param_shapes(30)) == 477862
+    assert sum(math.prod(s) for _, s in mobilenet.param_shapes(30)) == 2262338
+    names = [n for n, _ in las.param_shapes(12)]
+    assert names[:4] == ["encoder.conv1.weight", "encoder.conv1.bias", "encoder.conv2.weight", "encoder.conv2.bias"] and names[-1] == "fc.3.bias"
+    for arch, cls in trainer.Trainer.STEPS.items():
+        assert hasattr(trainer, cls), (arch, cls)
