@@ -415,16 +415,30 @@ struct MbDwBwdArgs {
   int64_t B;
   int c, cp, hin, win, hout, wout, stride;
   MbDwGeom g;
+  // BatchNorm-backward statistics of the PRODUCER convolution, fused (tiled kernel only): din is exactly the gradient at the producer's
+  // activated output, so S1 = sum dn and S2 = sum dn * xhat are accumulated here and the separate pass over (din, raw) is skipped
+  const uint4* raw_prev; // producer's raw output, or null
+  const float* bn_prev;  // producer's [5][cp]
+  double* bstats;        // [2][cp], zeroed by the host
+  int act_prev;
 };
 
 __global__ void __launch_bounds__(256, 2) mbn_dw_bwd_data_kernel(const MbDwBwdArgs a) {
   const int chunk = blockIdx.y, c8 = a.cp / 8;
   __shared__ float4 s_lo[DW_PX], s_hi[DW_PX];
   __shared__ __align__(16) float s_w[9][8];
+  __shared__ __align__(16) float s_bn[32];        // producer's scale, shift, mean, rstd of this chunk
   if (threadIdx.x < 72) {
     const int k = threadIdx.x >> 3, c = chunk * 8 + (threadIdx.x & 7);
     s_w[k][threadIdx.x & 7] = c < a.c ? a.w[c * 9 + k] : 0.f;
   }
+  if (a.bstats && threadIdx.x >= 96 && threadIdx.x < 128) {
+    const int j = threadIdx.x - 96;
+    s_bn[j] = a.bn_prev[(j >> 3) * a.cp + chunk * 8 + (j & 7)];
+  }
+  float part[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) part[i] = 0.f;
   const int hw_i = a.hin * a.win, tile = a.g.ph * a.g.pw;
   const int groups = (int)((a.B + a.g.ni - 1) / a.g.ni);
   uint4 raw[4];
@@ -441,6 +455,9 @@ __global__ void __launch_bounds__(256, 2) mbn_dw_bwd_data_kernel(const MbDwBwdAr
     for (int o = threadIdx.x; o < nb * hw_i; o += blockDim.x) {
       const int img = mb_div(o, a.g.fd_hw), p = o - img * hw_i;
       const int yi = mb_div(p, a.g.fd_w), xi = p - yi * a.win;
+      const size_t oidx = mbn_vec((int64_t)b0 * hw_i + o, chunk, c8);
+      uint4 xq = make_uint4(0u, 0u, 0u, 0u);
+      if (a.bstats) xq = __ldg(a.raw_prev + oidx);
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -461,12 +478,43 @@ __global__ void __launch_bounds__(256, 2) mbn_dw_bwd_data_kernel(const MbDwBwdAr
           acc[4] = fmaf(hi.x, w1.x, acc[4]); acc[5] = fmaf(hi.y, w1.y, acc[5]); acc[6] = fmaf(hi.z, w1.z, acc[6]); acc[7] = fmaf(hi.w, w1.w, acc[7]);
         }
       }
-      a.din[mbn_vec((int64_t)b0 * hw_i + o, chunk, c8)] = mb_pack(acc);
+      const uint4 packed = mb_pack(acc);
+      a.din[oidx] = packed;
+      if (a.bstats) {
+        float g[8], x[8];
+        mb_unpack(packed, g);                     // the statistics see the gradient as stored (bf16), like the separate pass did
+        mb_unpack(xq, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dn = g[j];
+          if (a.act_prev) {
+            const float n = fmaf(x[j], s_bn[j], s_bn[8 + j]);
+            if (!(n > 0.f && n < 6.f)) dn = 0.f;
+          }
+          part[j] += dn;
+          part[8 + j] = fmaf(dn, (x[j] - s_bn[16 + j]) * s_bn[24 + j], part[8 + j]);
+        }
+      }
     }
   }
   if (blockIdx.x == 0) {
     const int64_t rows = a.B * hw_i, rows_pad = mbn_tiles(rows) * MBN_TILE;
     for (int64_t r = rows + threadIdx.x; r < rows_pad; r += blockDim.x) a.din[mbn_vec(r, chunk, c8)] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (a.bstats) {
+    __shared__ float s_part[8][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float t = warp_sum(part[i]);
+      if (lane == 0) s_part[warp][i] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      double t = 0.0;
+      for (int wv = 0; wv < 8; ++wv) t += (double)s_part[wv][threadIdx.x];
+      atomicAdd(a.bstats + (size_t)(threadIdx.x >> 3) * a.cp + chunk * 8 + (threadIdx.x & 7), t);
+    }
   }
 }
 
@@ -1451,6 +1499,7 @@ static int mb_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   mbn_head_bwd_kernel<<<(unsigned)B, 256, 0, st>>>(ws.dlogits, params + net.cls_w, L, last.hout * last.wout, dropout_p, seed,
                                                   reinterpret_cast<uint4*>(gy), B);
   HOWL_LAUNCHED(ctx, "mbn_head_bwd");
+  bool stats_ready = false;       // the depthwise data gradient of conv i + 1 already left conv i's BatchNorm-backward statistics in ws.bstats
   for (size_t i = n - 1; i >= 1; --i) {
     const MbConv& c = net.convs[i];
     const int64_t rows = B * c.hout * c.wout, rows_pad = mbn_tiles(rows) * MBN_TILE;
@@ -1460,10 +1509,13 @@ static int mb_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     // ---- BatchNorm (+ ReLU6) backward of conv i: gy -> gr (+ dgamma, dbeta)
     __nv_bfloat16* gr = pick(gy, held, nullptr);
     HOWL_REQUIRE(ctx, gr != nullptr, HOWL_E_INVALID, "mobilenet_bwd: gradient buffer rotation");
-    HOWL_CUDA(ctx, cudaMemsetAsync(ws.bstats, 0, sizeof(double) * 2 * MB_MAXC, st));
-    mbn_bn_bwd_stats_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(gy), reinterpret_cast<const uint4*>(ws.raw[i]), ws.bn[i], cp, c.act,
-                                                  rows, ws.bstats);
-    HOWL_LAUNCHED(ctx, "mbn_bn_bwd_stats");
+    if (!stats_ready) {
+      HOWL_CUDA(ctx, cudaMemsetAsync(ws.bstats, 0, sizeof(double) * 2 * MB_MAXC, st));
+      mbn_bn_bwd_stats_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(gy), reinterpret_cast<const uint4*>(ws.raw[i]), ws.bn[i], cp,
+                                                    c.act, rows, ws.bstats);
+      HOWL_LAUNCHED(ctx, "mbn_bn_bwd_stats");
+    }
+    stats_ready = false;
     mbn_bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(gy), reinterpret_cast<const uint4*>(ws.raw[i]), ws.bn[i], c.cout, cp,
                                                   c.act, rows, rows_pad, ws.bstats, (double)rows, reinterpret_cast<uint4*>(gr),
                                                   grads + c.g_off, grads + c.b_off);
@@ -1485,7 +1537,16 @@ static int mb_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
       d.dout = reinterpret_cast<const uint4*>(gr); d.w = params + c.w_off; d.din = reinterpret_cast<uint4*>(dst);
       d.B = B; d.c = c.cout; d.cp = cp; d.hin = c.hin; d.win = c.win; d.hout = c.hout; d.wout = c.wout; d.stride = c.stride;
       d.g = mb_dw_geom(B, c.hout, c.wout, c.hin, c.win);
-      if (!mb_dw_small_bwd_data(st, d, c8)) mbn_dw_bwd_data_kernel<<<dim3(mb_dw_blocks(ctx, B, d.g.ni, c8), c8), 256, 0, st>>>(d);
+      d.raw_prev = nullptr; d.bn_prev = nullptr; d.bstats = nullptr; d.act_prev = 0;
+      if (!mb_dw_small_bwd_data(st, d, c8)) {
+        if (i >= 2) {       // the producer is a GEMM convolution with its own BatchNorm: fuse its backward statistics (same channel count)
+          HOWL_CUDA(ctx, cudaMemsetAsync(ws.bstats, 0, sizeof(double) * 2 * MB_MAXC, st));      // free again: conv i's apply pass has run
+          d.raw_prev = reinterpret_cast<const uint4*>(ws.raw[i - 1]); d.bn_prev = ws.bn[i - 1]; d.bstats = ws.bstats;
+          d.act_prev = net.convs[i - 1].act;
+          stats_ready = true;
+        }
+        mbn_dw_bwd_data_kernel<<<dim3(mb_dw_blocks(ctx, B, d.g.ni, c8), c8), 256, 0, st>>>(d);
+      }
       HOWL_LAUNCHED(ctx, "mbn_dw_bwd_data");
     } else {
       // GEMM convolution: dW[cout][k] += gr^T * input;  d(input) = gr * W (+ the skip gradient at a block's first convolution)
