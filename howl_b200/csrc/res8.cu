@@ -882,7 +882,17 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     if (use_tc) {
       // operand-format activations only; BatchNorm of layer i-1 folded into this layer's weights (res8_tc.cu)
       __nv_bfloat16* wblk = ws.wprep + ((size_t)((i - 1) * 2 + 0) * 2) * R8TC_WBLOCK;
-      rc = r8tc_fold(ctx, st, w_i, in_mean, wblk);
+      // train: the BatchNorm finalisation of layer i - 1 (mean / rstd, running statistics) happens inside this fold
+      TcFoldBn fb;
+      memset(&fb, 0, sizeof(fb));
+      if (train && i > 1) {
+        fb.stats = ws.stats_fwd + (i - 2) * 2 * R8_C;
+        fb.count = count;
+        fb.mean_rstd_out = ws.mean_rstd + (i - 2) * 2 * R8_C;
+        fb.running = bn_running + (i - 2) * 2 * R8_C;
+        fb.nbt = num_batches_tracked ? num_batches_tracked + (i - 2) : nullptr;
+      }
+      rc = r8tc_fold(ctx, st, w_i, in_mean, wblk, fb.stats ? &fb : nullptr);
       if (rc) return rc;
       TcConvCall c;
       memset(&c, 0, sizeof(c));
@@ -913,7 +923,7 @@ extern "C" int howl_b200_res8_fwd(howl_ctx_t* ctx, void* stream, const float* fe
       else conv3x3_kernel<true, 0><<<grid, CV_THREADS, csm, st>>>(p);
       HOWL_LAUNCHED(ctx, "conv3x3_fwd");
     }
-    if (train) {
+    if (train && !(use_tc && i < R8_LAYERS)) {      // (tensor-core engine: layers 1..5 are finalised by the next layer's fold)
       bn_finalize_kernel<<<1, 64, 0, st>>>(stats, count, ws.mean_rstd + (i - 1) * 2 * R8_C, bn_running + (i - 1) * 2 * R8_C,
                                            num_batches_tracked ? num_batches_tracked + (i - 1) : nullptr);
       HOWL_LAUNCHED(ctx, "bn_finalize");

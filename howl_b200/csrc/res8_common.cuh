@@ -104,6 +104,15 @@ int r8tc_conv0(howl_ctx_t* ctx, cudaStream_t st, const float* feats, const float
 int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __nv_bfloat16* wprep);
 // forward weight operand of one layer with BatchNorm(mean_rstd, or identity when null) folded in (the border-dependent bias
 // rides on the ones channel)
-int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* blk);
+// BatchNorm finalisation of the producer layer done inside the fold (train mode): batch statistics -> mean / rstd (also written to
+// mean_rstd_out for the backward), running statistics and num_batches_tracked updated once.  stats == null: mean_rstd is read as is.
+struct TcFoldBn {
+  const double* stats;      // [2][45] sum, sum of squares of the producer's output
+  double count;
+  float* mean_rstd_out;     // [2][45]
+  float* running;           // [2][45] running mean / var, or null
+  int64_t* nbt;             // or null
+};
+int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* blk, const TcFoldBn* bn = nullptr);
 int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, const __nv_bfloat16* x_op, const float* x_mean,
                const float* x_rstd, float* dw, float* dones, int64_t B, int H);

@@ -84,17 +84,40 @@ int r8tc_weight_prep(howl_ctx_t* ctx, cudaStream_t st, const float* w_layers, __
 //   W'[o][45][tap] = - sum_c W[o][c][tap] rstd[c] mean[c].
 // So the operand halo stays zero and the kernel needs no bias, no border cases and no halo rewrite.
 // grid = 9 taps; mean_rstd == null -> identity (layer 1 reads the un-normalised a0)
-__global__ void tc_fold_kernel(const float* __restrict__ w, const float* __restrict__ mean_rstd, __nv_bfloat16* __restrict__ blk) {
+__global__ void tc_fold_kernel(const float* __restrict__ w, const float* __restrict__ mean_rstd, __nv_bfloat16* __restrict__ blk, const TcFoldBn bn) {
   __shared__ float s_mu[48], s_rs[48], s_bias[48];
   const int tid = threadIdx.x, tap = blockIdx.x;
   if (tid < 48) {
-    s_mu[tid] = (tid < R8_C && mean_rstd) ? mean_rstd[tid] : 0.f;
-    s_rs[tid] = (tid < R8_C) ? (mean_rstd ? mean_rstd[R8_C + tid] : 1.f) : 0.f;
+    float mu = 0.f, rs = tid < R8_C ? 1.f : 0.f;
+    if (tid < R8_C && bn.stats) {
+      // the producer's batch statistics are final (its kernel has completed): every CTA derives mean / rstd, CTA 0 publishes them
+      const double mean = bn.stats[tid] / bn.count;
+      double var = bn.stats[R8_C + tid] / bn.count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mu = (float)mean;
+      rs = (float)(1.0 / sqrt(var + R8_BN_EPS));
+      if (tap == 0) {
+        bn.mean_rstd_out[tid] = mu;
+        bn.mean_rstd_out[R8_C + tid] = rs;
+        if (bn.running) {
+          const double unbiased = bn.count > 1.0 ? var * bn.count / (bn.count - 1.0) : var;
+          bn.running[tid] = (float)((1.0 - R8_BN_MOM) * bn.running[tid] + R8_BN_MOM * mean);
+          bn.running[R8_C + tid] = (float)((1.0 - R8_BN_MOM) * bn.running[R8_C + tid] + R8_BN_MOM * unbiased);
+        }
+        if (tid == 0 && bn.nbt) *bn.nbt += 1;
+      }
+    } else if (tid < R8_C && mean_rstd) {
+      mu = mean_rstd[tid];
+      rs = mean_rstd[R8_C + tid];
+    }
+    s_mu[tid] = mu;
+    s_rs[tid] = rs;
   }
+  const bool folded = bn.stats || mean_rstd;
   __syncthreads();
   if (tid < 48) {
     double b = 0.0;
-    if (tid < R8_C && mean_rstd)
+    if (tid < R8_C && folded)
       for (int c = 0; c < R8_C; ++c) b -= (double)w[(tid * R8_C + c) * 9 + tap] * (double)s_rs[c] * (double)s_mu[c];
     s_bias[tid] = (float)b;
   }
@@ -109,8 +132,10 @@ __global__ void tc_fold_kernel(const float* __restrict__ w, const float* __restr
   }
 }
 
-int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* blk) {
-  tc_fold_kernel<<<9, 256, 0, st>>>(w_layer, mean_rstd, blk);
+int r8tc_fold(howl_ctx_t* ctx, cudaStream_t st, const float* w_layer, const float* mean_rstd, __nv_bfloat16* blk, const TcFoldBn* bn) {
+  TcFoldBn none;
+  memset(&none, 0, sizeof(none));
+  tc_fold_kernel<<<9, 256, 0, st>>>(w_layer, mean_rstd, blk, bn ? *bn : none);
   HOWL_LAUNCHED(ctx, "tc_fold");
   return HOWL_OK;
 }
@@ -944,6 +969,10 @@ __global__ void __launch_bounds__(C0T_THREADS, 2) conv0_tc_kernel(const Conv0TcA
         const int chunk = 3 * half + c;
         op[(size_t)chunk * a.R] = hi;
         op[(size_t)(6 + chunk) * a.R] = lo;
+        if (w == 0) {           // the shared halo column left of the image row (raster row q - 1)
+          op[(size_t)chunk * a.R - 1] = make_uint4(0, 0, 0, 0);
+          op[(size_t)(6 + chunk) * a.R - 1] = make_uint4(0, 0, 0, 0);
+        }
       }
     }
   }
@@ -953,14 +982,16 @@ __global__ void __launch_bounds__(C0T_THREADS, 2) conv0_tc_kernel(const Conv0TcA
 }
 
 // halo rows of the operand-format a0 (raster rows outside the image) := 0
+// zero the raster rows of a0_op the convolution kernel does not write (it writes the image rows and their shared halo column): the top
+// halo row and everything from the bottom halo row to R -- two contiguous runs per plane; thread = one (utterance, plane, row)
 __global__ void conv0_halo_kernel(uint4* __restrict__ a0_op, int64_t B, int H, int R) {
-  const int64_t n = B * R;
+  const int bottom = (H + 1) * TC_PITCH, nh = TC_PITCH + (R - bottom);
+  const int64_t n = B * 12 * nh;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / R;
-    const int q = (int)(i - b * R), y = q / TC_PITCH - 1, x = q % TC_PITCH - 1;
-    if (y >= 0 && y < H && x >= 0 && x < R8_W) continue;
-#pragma unroll
-    for (int g = 0; g < 12; ++g) a0_op[(size_t)b * 12 * R + (size_t)g * R + q] = make_uint4(0, 0, 0, 0);
+    const int k = (int)(i % nh);
+    const int64_t plane = i / nh;           // b * 12 + g
+    const int q = k < TC_PITCH ? k : bottom + (k - TC_PITCH);
+    a0_op[(size_t)plane * R + q] = make_uint4(0, 0, 0, 0);
   }
 }
 
