@@ -114,11 +114,14 @@ __global__ void tc_fold_kernel(const float* __restrict__ w, const float* __restr
     s_rs[tid] = rs;
   }
   const bool folded = bn.stats || mean_rstd;
+  // this tap's 45 x 45 weights: one round of independent (strided) global loads into shared memory, read twice from there
+  __shared__ float s_w[R8_C * R8_C];
+  for (int i = tid; i < R8_C * R8_C; i += blockDim.x) s_w[i] = w[(size_t)i * 9 + tap];
   __syncthreads();
   if (tid < 48) {
     double b = 0.0;
     if (tid < R8_C && folded)
-      for (int c = 0; c < R8_C; ++c) b -= (double)w[(tid * R8_C + c) * 9 + tap] * (double)s_rs[c] * (double)s_mu[c];
+      for (int c = 0; c < R8_C; ++c) b -= (double)s_w[tid * R8_C + c] * (double)s_rs[c] * (double)s_mu[c];
     s_bias[tid] = (float)b;
   }
   __syncthreads();
@@ -126,7 +129,7 @@ __global__ void tc_fold_kernel(const float* __restrict__ w, const float* __restr
     const int j = r & 7, n = (r >> 3) % TC_N, chunk = (r >> 3) / TC_N;
     const int c = chunk * 8 + j;
     float v = 0.f;
-    if (n < R8_C && c < R8_C) v = w[(n * R8_C + c) * 9 + tap] * s_rs[c];
+    if (n < R8_C && c < R8_C) v = s_w[n * R8_C + c] * s_rs[c];
     else if (n < R8_C && c == R8_C) v = s_bias[n];
     tc_store_w(blk, tap, chunk, n, j, v);
   }
