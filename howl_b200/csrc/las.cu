@@ -1054,7 +1054,7 @@ static int las_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const
     const float* da = dir ? dg : dg + (size_t)B * 2 * LA_G;
     const float* hp = dir ? ws.hseq + (size_t)B * LA_D + LA_H : ws.hseq;
     if (TB >= 1024) {
-      if ((rc = mbn_pack_split(ctx, st, dg, 2 * LA_G, TB, LA_G, ws.px_hi, ws.px_lo))) return rc;
+      if ((rc = mbn_pack_split(ctx, st, dg, 2 * LA_G, TB, LA_G, ws.px_hi, ws.px_lo, G(q.bih[dir]), G(q.bhh[dir])))) return rc;      // + bias gradients
       if ((rc = mbn_pack_split(ctx, st, ws.x, in, TB, in, ws.py_hi, ws.py_lo))) return rc;
       if ((rc = mbn_atb3_packed(ctx, st, ws.px_hi, ws.px_lo, ws.py_hi, ws.py_lo, G(q.wih[dir]), TB, LA_G, in, in))) return rc;
       if (T > 1) {
@@ -1066,7 +1066,7 @@ static int las_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const
       if ((rc = las_gemm(ctx, st, dg, 1, 2 * LA_G, ws.x, in, 1, G(q.wih[dir]), in, LA_G, in, TB, true))) return rc;
       if (T > 1 && (rc = las_gemm(ctx, st, da, 1, 2 * LA_G, hp, LA_D, 1, G(q.whh[dir]), LA_H, LA_G, LA_H, TB - B, true))) return rc;
     }
-    if ((rc = las_colsum(ctx, st, dg, TB, LA_G, 2 * LA_G, G(q.bih[dir]), G(q.bhh[dir])))) return rc;
+    if (TB < 1024 && (rc = las_colsum(ctx, st, dg, TB, LA_G, 2 * LA_G, G(q.bih[dir]), G(q.bhh[dir])))) return rc;
   }
   // ---- BatchNorm 2 + ReLU + MaxPool, conv2
   las_bn_bwd_stats_kernel<<<dim3(ctx->sm_count, LA_C), 256, 0, st>>>(ws.raw2, ws.bn + 4 * LA_C, ws.dx, B, d.h2, d.w2, d.w2p, 1, ws.bstats + 2 * LA_C);

@@ -710,11 +710,16 @@ static int lstm_atb(howl_ctx_t* ctx, cudaStream_t st, const float* A, int lda, c
 
 // out[m][n] += sum_r A[r][m] Bm[r][n] on the tensor cores: both sides split into (hi, lo) bf16 operands, three products, fp32 accumulate.
 // reuse_x: the X side (A) is already packed in ws.px_* (the gate gradients feed two products)
+// colsum / colsum2: the column sums of A (bias gradients) are accumulated while A is packed -- or by lstm_colsum on the FFMA path
+static int lstm_colsum(howl_ctx_t* ctx, cudaStream_t st, const float* A, int lda, int Mo, int64_t R, float* out, float* out2);
 static int lstm_atb_tc(howl_ctx_t* ctx, cudaStream_t st, const LstmWs& ws, const float* A, int lda, const float* Bm, int ldb, float* out, int ldo,
-                       int Mo, int No, int64_t R, bool reuse_x) {
+                       int Mo, int No, int64_t R, bool reuse_x, float* colsum = nullptr, float* colsum2 = nullptr) {
   int rc;
-  if (R < 1024) return lstm_atb(ctx, st, A, lda, Bm, ldb, out, ldo, Mo, No, R);      // a handful of row tiles: the FFMA kernel, exact fp32
-  if (!reuse_x && (rc = mbn_pack_split(ctx, st, A, lda, R, Mo, ws.px_hi, ws.px_lo))) return rc;
+  if (R < 1024) {      // a handful of row tiles: the FFMA kernels, exact fp32
+    if (colsum && (rc = lstm_colsum(ctx, st, A, lda, Mo, R, colsum, colsum2))) return rc;
+    return lstm_atb(ctx, st, A, lda, Bm, ldb, out, ldo, Mo, No, R);
+  }
+  if (!reuse_x && (rc = mbn_pack_split(ctx, st, A, lda, R, Mo, ws.px_hi, ws.px_lo, colsum, colsum2))) return rc;
   if ((rc = mbn_pack_split(ctx, st, Bm, ldb, R, No, ws.py_hi, ws.py_lo))) return rc;
   return mbn_atb3_packed(ctx, st, ws.px_hi, ws.px_lo, ws.py_hi, ws.py_lo, out, R, Mo, No, ldo);
 }
@@ -849,8 +854,7 @@ static int lstm_bwd_impl(howl_ctx_t* ctx, void* stream, const int64_t* lengths, 
   // (L output rows fill a sliver of a 128-row MMA tile: the FFMA kernel reads z1 once and is faster here)
   if ((rc = lstm_atb(ctx, st, ws.dlogits, L, ws.z1, LS_MLP, g_w2, LS_MLP, L, LS_MLP, rows))) return rc;
   if ((rc = lstm_colsum(ctx, st, ws.dlogits, L, L, rows, g_b2, nullptr))) return rc;
-  if ((rc = lstm_atb_tc(ctx, st, ws, ws.dz1, LS_MLP, sequential ? ws.hseq : ws.hfin, LS_H, g_w1, LS_H, LS_MLP, LS_H, rows, false))) return rc;
-  if ((rc = lstm_colsum(ctx, st, ws.dz1, LS_MLP, LS_MLP, rows, g_b1, nullptr))) return rc;
+  if ((rc = lstm_atb_tc(ctx, st, ws, ws.dz1, LS_MLP, sequential ? ws.hseq : ws.hfin, LS_H, g_w1, LS_H, LS_MLP, LS_H, rows, false, g_b1))) return rc;
   // BPTT
   LstmBwdArgs a;
   a.lengths = lengths; a.w_hh = v.w_hh; a.c0 = ws.c0; a.gates = ws.gates; a.cs = ws.cs;
@@ -861,9 +865,8 @@ static int lstm_bwd_impl(howl_ctx_t* ctx, void* stream, const int64_t* lengths, 
   HOWL_LAUNCHED(ctx, "lstm_bwd");
   // weight gradients over all (t, b) rows: [W_ih | W_hh] from xh = [x_t | h_{t-1}]
   const int64_t R = (int64_t)T * B;
-  if ((rc = lstm_atb_tc(ctx, st, ws, ws.gates, LS_G, ws.xh, K, g_w_ih, M, LS_G, M, R, false))) return rc;
+  if ((rc = lstm_atb_tc(ctx, st, ws, ws.gates, LS_G, ws.xh, K, g_w_ih, M, LS_G, M, R, false, g_b_ih, g_b_hh))) return rc;
   if ((rc = lstm_atb_tc(ctx, st, ws, ws.gates, LS_G, ws.xh + M, K, g_w_hh, LS_H, LS_G, LS_H, R, true))) return rc;
-  if ((rc = lstm_colsum(ctx, st, ws.gates, LS_G, LS_G, R, g_b_ih, g_b_hh))) return rc;
   return HOWL_OK;
 }
 

@@ -38,8 +38,10 @@ int mbn_gemm_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dC, co
                    int K, int n_valid, int k_valid, int ld);
 
 // ---- fp32 A^T B on the tensor cores (bf16 x 3 split), used by the LSTM / LAS weight gradients -----------------------------------
-// hi = bf16(x), lo = bf16(x - hi) of the fp32 row-major matrix x [rows][ld] (columns 0 .. c-1), both in TMO (pad rows / channels zero)
-int mbn_pack_split(howl_ctx_t* ctx, cudaStream_t st, const float* x, int64_t ld, int64_t rows, int c, __nv_bfloat16* hi, __nv_bfloat16* lo);
+// hi = bf16(x), lo = bf16(x - hi) of the fp32 row-major matrix x [rows][ld] (columns 0 .. c-1), both in TMO (pad rows / channels zero);
+// colsum / colsum2 != null: += the column sums of x (the bias gradients come for free with the pass)
+int mbn_pack_split(howl_ctx_t* ctx, cudaStream_t st, const float* x, int64_t ld, int64_t rows, int c, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                   float* colsum = nullptr, float* colsum2 = nullptr);
 // dW[n][k] (fp32, row stride ld) += sum_r X[r][n] Y[r][k] = Xhi^T Yhi + Xhi^T Ylo + Xlo^T Yhi  (|error| ~ 2^-16 per product, fp32 accumulate)
 int mbn_atb3_packed(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* xhi, const __nv_bfloat16* xlo, const __nv_bfloat16* yhi,
                     const __nv_bfloat16* ylo, float* dW, int64_t rows, int N, int K, int ld);

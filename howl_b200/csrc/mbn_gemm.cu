@@ -480,13 +480,18 @@ int mbn_gemm_nt3_f32(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* x3, 
 // =============================================================================================
 // fp32 A^T B as three bf16 products (LSTM / LAS weight gradients): split-pack + three weight-gradient GEMMs
 // =============================================================================================
-// thread = one 16-byte vector of the TMO output (row fastest inside a 128-row tile): stores are contiguous, loads are 32-byte row pieces
+// thread = (row of a 128-row tile, 8-channel chunk = blockIdx.y), walking the tiles: stores are contiguous, loads are 32-byte row pieces.
+// colsum != null: the column sums of x (bias gradients) are accumulated on the way (+= into colsum and colsum2).
 __global__ void __launch_bounds__(256) mbn_pack_split_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int c, int c8,
-                                                             uint4* __restrict__ hi, uint4* __restrict__ lo) {
-  const int64_t n = mbn_tiles(rows) * MBN_TILE * c8;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(v % MBN_TILE), chunk = (int)((v / MBN_TILE) % c8);
-    const int64_t row = (v / MBN_TILE / c8) * MBN_TILE + r;
+                                                             uint4* __restrict__ hi, uint4* __restrict__ lo, float* __restrict__ colsum,
+                                                             float* __restrict__ colsum2) {
+  const int chunk = blockIdx.y, r = threadIdx.x & (MBN_TILE - 1);
+  const int64_t tiles = mbn_tiles(rows);
+  float cs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+  for (int64_t tile = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7); tile < tiles; tile += (int64_t)gridDim.x * 2) {
+    const int64_t row = tile * MBN_TILE + r;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = 0.f;
@@ -509,17 +514,38 @@ __global__ void __launch_bounds__(256) mbn_pack_split_kernel(const float* __rest
       h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
       l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
+    const size_t v = ((size_t)tile * c8 + chunk) * MBN_TILE + r;
     hi[v] = make_uint4(h[0], h[1], h[2], h[3]);
     lo[v] = make_uint4(l[0], l[1], l[2], l[3]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] += f[j];
+  }
+  if (colsum) {
+    __shared__ float s_cs[8][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = warp_sum(cs[j]);
+      if (lane == 0) s_cs[warp][j] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && chunk * 8 + threadIdx.x < c) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += s_cs[w][threadIdx.x];
+      atomicAdd(colsum + chunk * 8 + threadIdx.x, t);
+      if (colsum2) atomicAdd(colsum2 + chunk * 8 + threadIdx.x, t);
+    }
   }
 }
 
-int mbn_pack_split(howl_ctx_t* ctx, cudaStream_t st, const float* x, int64_t ld, int64_t rows, int c, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+int mbn_pack_split(howl_ctx_t* ctx, cudaStream_t st, const float* x, int64_t ld, int64_t rows, int c, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                   float* colsum, float* colsum2) {
   HOWL_REQUIRE(ctx, x && hi && lo && rows > 0 && c > 0, HOWL_E_INVALID, "mbn_pack_split: bad argument");
   const int c8 = mbn_pad16(c) / 8;
-  const int64_t n = mbn_tiles(rows) * MBN_TILE * c8;
-  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
-  mbn_pack_split_kernel<<<blocks, 256, 0, st>>>(x, ld, rows, c, c8, reinterpret_cast<uint4*>(hi), reinterpret_cast<uint4*>(lo));
+  const int64_t pairs = (mbn_tiles(rows) + 1) / 2;
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(pairs, std::max<int64_t>(1, (int64_t)ctx->sm_count * 16 / c8)));
+  mbn_pack_split_kernel<<<dim3(gx, c8), 256, 0, st>>>(x, ld, rows, c, c8, reinterpret_cast<uint4*>(hi), reinterpret_cast<uint4*>(lo), colsum,
+                                                      colsum2);
   HOWL_LAUNCHED(ctx, "mbn_pack_split");
   return HOWL_OK;
 }
