@@ -51,6 +51,7 @@ SIGNATURES: Dict[str, tuple] = {
     "howl_b200_num_frames": (_i64, [_i64, _i32]),
     "howl_b200_compute_lengths": (C.c_int, [_vp, _i64, _i32, _i32, _vp]),
     "howl_b200_frontend_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _f32, _f32, _vp, _u32, _vp]),
+    "howl_b200_deltas_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "howl_b200_sum_sumsq": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "howl_b200_zmuv_fwd": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _f32, _vp]),
     "howl_b200_spec_mask": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(FE_THREADS, 3) frontend_kernel(const FeParams 
 // d[t] = (-2x[t-2] - x[t-1] + x[t+1] + 2x[t+2]) / 10 with replicate padding, applied twice
 // (torchaudio ComputeDeltas); channel 0 holds raw log-mel on entry.
 // ---------------------------------------------------------------------------------------------
-__global__ void deltas_kernel(float* __restrict__ out, int64_t rows, int M, int F, float zmean, float zstd,
+__global__ void deltas_kernel(float* __restrict__ out, const float* __restrict__ src, int64_t rows, int M, int F, float zmean, float zstd,
                               int do_zmuv, const int32_t* __restrict__ rects) {
   extern __shared__ float s_rows[];  // [warps][2][F]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -419,7 +419,8 @@ __global__ void deltas_kernel(float* __restrict__ out, int64_t rows, int M, int 
     float* c0 = out + ((b * 3 + 0) * M + m) * (int64_t)F;
     float* c1 = out + ((b * 3 + 1) * M + m) * (int64_t)F;
     float* c2 = out + ((b * 3 + 2) * M + m) * (int64_t)F;
-    for (int t = lane; t < F; t += 32) xs[t] = c0[t];
+    const float* x0 = src ? src + row * (int64_t)F : c0;     // deltas_only: the log-mels come from the caller's tensor
+    for (int t = lane; t < F; t += 32) xs[t] = x0[t];
     __syncwarp();
     for (int t = lane; t < F; t += 32) {
       const float a = xs[max(t - 2, 0)], bb = xs[max(t - 1, 0)], c = xs[min(t + 1, F - 1)], d = xs[min(t + 2, F - 1)];
@@ -565,10 +566,30 @@ extern "C" int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float
     int64_t blocks = howl_ceil_div(rows, warps);
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    deltas_kernel<<<(unsigned)blocks, warps * 32, sm, st>>>(out, rows, M, F, zmuv_mean, zmuv_std,
+    deltas_kernel<<<(unsigned)blocks, warps * 32, sm, st>>>(out, nullptr, rows, M, F, zmuv_mean, zmuv_std,
                                                             (flags & HOWL_FE_ZMUV) ? 1 : 0, rects);
     HOWL_LAUNCHED(ctx, "deltas");
   }
+  return HOWL_OK;
+}
+
+// StandardAudioTransform._execute_op(deltas_only=True) (transform.py:272-280): the caller already holds log-mels x [B, M, F];
+// out [B, 3, M, F] = stack(x, deltas(x), deltas(deltas(x))).
+extern "C" int howl_b200_deltas_fwd(howl_ctx_t* ctx, void* stream, const float* x, int64_t B, int32_t M, int32_t F, float* out) {
+  if (!ctx) return HOWL_E_INVALID;
+  HOWL_REQUIRE(ctx, x && out && B >= 0 && M > 0 && F > 0, HOWL_E_INVALID, "deltas_fwd: bad argument");
+  HOWL_REQUIRE(ctx, x != out, HOWL_E_INVALID, "deltas_fwd: in place is not supported (the output is three times the input)");
+  if (B == 0) return HOWL_OK;
+  const int64_t rows = B * (int64_t)M;
+  const int warps = 8;
+  const size_t sm = sizeof(float) * warps * 2 * (size_t)F;
+  HOWL_REQUIRE(ctx, sm <= 200 * 1024, HOWL_E_UNSUPPORTED, "deltas_fwd: %d frames do not fit the delta kernel's row buffers", F);
+  HOWL_CUDA(ctx, cudaFuncSetAttribute(deltas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  int64_t blocks = howl_ceil_div(rows, warps);
+  const int64_t cap = (int64_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  deltas_kernel<<<(unsigned)blocks, warps * 32, sm, (cudaStream_t)stream>>>(out, x, rows, M, F, 0.f, 1.f, 0, nullptr);
+  HOWL_LAUNCHED(ctx, "deltas");
   return HOWL_OK;
 }
 

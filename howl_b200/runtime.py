@@ -157,6 +157,17 @@ class Context:
                                                  _ptr(rects), flag, _ptr(out)), "frontend_fwd")
         return out
 
+    def deltas(self, x: torch.Tensor) -> torch.Tensor:
+        """``_execute_op(deltas_only=True)`` (transform.py:272-280): log-mels x [..., M, F] -> [B, 3, M, F] (B = the leading axes folded)."""
+        _check(x, torch.float32, self.device, "x")
+        if x.dim() < 2:
+            raise HowlB200Error("deltas: x must be [..., M, F]")
+        m, f = x.shape[-2], x.shape[-1]
+        b = x.numel() // (m * f) if m * f else 0
+        out = torch.empty((b, 3, m, f), dtype=torch.float32, device=self.device)
+        self._rc(self.lib.howl_b200_deltas_fwd(self.handle, self._stream(), _ptr(x), b, m, f, _ptr(out)), "deltas_fwd")
+        return out
+
     def sum_sumsq(self, x: torch.Tensor, sums: torch.Tensor) -> None:
         _check(x, torch.float32, self.device, "x")
         _check(sums, torch.float64, self.device, "sums")

@@ -120,17 +120,22 @@ class StandardAudioTransform(AugmentModule):
 
     @torch.no_grad()
     def _execute(self, fb: torch.Tensor, audio: torch.Tensor, mels_only=False, deltas_only=False):
-        if deltas_only:
-            raise NotImplementedError("deltas_only is unused by the reference's callers and not built")
         if audio.device.type != "cuda":
             raise RuntimeError("howl_b200.StandardAudioTransform needs CUDA tensors (no CPU fallback)")
         ctx = get_context(audio.device, self.num_mels)
+        if deltas_only:     # transform.py:275: `audio` already holds log-mels [B, M, F]; only the delta / delta-delta stack is computed
+            if audio.dim() != 3:
+                raise ValueError("deltas_only expects log-mels of shape [B, M, F]")
+            log_mels = audio.contiguous().float()
+            return log_mels if mels_only else ctx.deltas(log_mels)
         audio = audio.contiguous() if audio.dtype == torch.int16 else audio.contiguous().float()   # int16 PCM goes to the kernel as is
         if audio.dim() == 1:
             audio = audio.unsqueeze(0)
         return ctx.frontend(audio, fb.to(audio.device), "mels" if mels_only else "stacked")
 
     def augment(self, param, examples: torch.Tensor, **kwargs):
+        if kwargs.get("deltas_only"):         # the VTLP op is never invoked (transform.py:275): no alpha draw
+            return self._execute(self.fb, examples, **kwargs)
         alpha = random.random() * 0.2 + 0.9  # VtlpMelScale.forward draws from the GLOBAL random (transform.py:441)
         fb = vtlp_filterbank(alpha, self.num_mels, self.sample_rate, self.num_fft // 2 + 1)
         return self._execute(fb, examples, **kwargs)

@@ -95,6 +95,10 @@ int howl_b200_compute_lengths(const int64_t* lengths, int64_t n, int32_t win, in
 int howl_b200_frontend_fwd(howl_ctx_t* ctx, void* stream, const float* pcm, int64_t B, int64_t T, const float* fb,
                            float zmuv_mean, float zmuv_std, const int32_t* rects, uint32_t flags, float* out);
 
+/* StandardAudioTransform._execute_op(..., deltas_only=True) (transform.py:272-280): x [B, M, F] already holds log-mels;
+ * out [B, 3, M, F] = stack(x, ComputeDeltas(x), ComputeDeltas(ComputeDeltas(x))) (win_length 5, replicate padding).  x != out. */
+int howl_b200_deltas_fwd(howl_ctx_t* ctx, void* stream, const float* x, int64_t B, int32_t M, int32_t F, float* out);
+
 /* Sum and sum of squares of n floats into sums[2] (f64, ACCUMULATED onto the existing contents).
  * Replaces the two reductions of ZmuvTransform.update (operator.py:126-135). */
 int howl_b200_sum_sumsq(howl_ctx_t* ctx, void* stream, const float* x, int64_t n, double* sums);

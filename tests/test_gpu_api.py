@@ -45,6 +45,23 @@ def test_standard_audio_transform_eval_and_train_draw_order(golden):
         np.testing.assert_allclose(std(pcm).cpu().numpy(), v["train_outs"][k], rtol=RTOL, atol=ATOL)
 
 
+def test_standard_audio_transform_deltas_only(golden):
+    """_execute_op(deltas_only=True) (transform.py:272-280): the reference's own log-mels in, its stacked [B,3,M,F] tensor out."""
+    from howl_b200.transform import StandardAudioTransform
+
+    g = golden("frontend")
+    std = StandardAudioTransform().to(DEV).eval()
+    for tag in ("t8000", "t16000", "t4567", "t1000"):
+        mels = torch.from_numpy(g[tag + "_mels_only"]).to(DEV)
+        out = std(mels, deltas_only=True)
+        assert out.shape == g[tag + "_out"].shape
+        assert torch.equal(out[:, 0], mels)
+        np.testing.assert_allclose(out.cpu().numpy(), g[tag + "_out"], rtol=1e-5, atol=1e-5)
+        assert torch.equal(std(mels, deltas_only=True, mels_only=True), mels)
+    with pytest.raises(ValueError):
+        std(torch.zeros(40, 41, device=DEV), deltas_only=True)
+
+
 def test_zmuv_transform_update_and_state_dict(golden):
     from howl_b200.transform import ZmuvTransform
 
