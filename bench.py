@@ -102,6 +102,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-library-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-module-path", action="store_true", help="skip the module-by-module (train.py loop body) leg")
     ap.add_argument("--breakdown", action="store_true", help="print per-kernel-group CUDA-event times to stderr")
     a = ap.parse_args()
     spec = MODELS[a.model]
@@ -303,6 +304,45 @@ def run_gpu_library(model, batch, samples, labels, dev, steps=5, warmup=2):
     return out
 
 
+def run_module_path(a, dev, pcm, labels, steps=10, warmup=3):
+    """The loop body of training/run/train.py:288-302 through the drop-in MODULES (what the reference's own train.py executes after
+    `plugin.install()`): StandardAudioTransform -> ZmuvTransform -> registry model (nn.Module, autograd Function) -> torch's
+    CrossEntropyLoss -> backward -> torch.optim.AdamW over model.parameters().  Same batch as the fused step; PCM resident in HBM."""
+    from howl_b200.model import RegisteredModel
+    from howl_b200.transform import StandardAudioTransform, ZmuvTransform
+
+    os.environ["NUM_MELS"] = str(N_MELS)
+    from howl_b200.settings import SETTINGS
+    SETTINGS.reset()
+    model = RegisteredModel.find_registered_class(a.model)(a.labels).to(dev).streaming()
+    std = StandardAudioTransform().to(dev).eval()
+    zmuv = ZmuvTransform().to(dev)
+    zmuv.mean = torch.tensor([ZMEAN], device=dev)
+    zmuv.mean2 = torch.tensor([ZMEAN ** 2 + ZSTD ** 2], device=dev)
+    opt = torch.optim.AdamW(model.parameters(), LR, weight_decay=WD)
+    crit = torch.nn.CrossEntropyLoss()
+    model.train()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize(dev)
+            ev0.record()
+        lengths = std.compute_lengths(torch.full((pcm.size(0),), pcm.size(1)))
+        scores = model(zmuv(std(pcm)), lengths)
+        loss = crit(scores, labels)
+        opt.zero_grad()
+        model.zero_grad()
+        loss.backward()
+        opt.step()
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1) / steps
+    return {"value": pcm.size(0) / (ms / 1e3), "unit": "utterances/s", "ms_per_step": ms, "last_loss": float(loss.item()),
+            "what": "train.py:288-302 loop body through the drop-in modules (StandardAudioTransform, ZmuvTransform, registry nn.Module under "
+                    f"autograd, torch CrossEntropyLoss + torch.optim.AdamW), batch {pcm.size(0)}, {steps} steps after {warmup} warm-up; the "
+                    "stacked [B,3,M,F] features and torch's optimizer are part of it -- the fused step (`value`) is the same math in one call"}
+
+
 def workload_text(a, world):
     per = {"res8": "fused STFT->mel->conv train step", "lstm": "frontend + LSTM(40->128) + MLP train step (frame objective)",
            "seq-lstm": "frontend + streaming seq-lstm + CTC train step", "mobilenet": "frontend + MobileNetV2 train step",
@@ -400,6 +440,8 @@ def main_ours(a):
     step_obj = make_step(a, dev, world)
     if os.environ.get("HOWL_CONV_ENGINE"):   # tuning experiments only
         step_obj.ctx.set_option("conv_engine", int(os.environ["HOWL_CONV_ENGINE"]))
+    if os.environ.get("HOWL_LSTM_ENGINE"):   # A/B of the recurrences: 0 = plain, 1 = software pipelined (default)
+        step_obj.ctx.set_option("lstm_engine", int(os.environ["HOWL_LSTM_ENGINE"]))
     ctx = step_obj.ctx
     warmup = max(a.warmup, 3)
 
@@ -514,6 +556,12 @@ def main_ours(a):
             cpu = {"value": v, "unit": "utterances/s", "cores": cores, "kind": "port",
                    "sample": f"10 steps x {sample} utterances of the same workload after 2 warm-up (oracle port, torch CPU), "
                              f"{cores} intra-op threads of {os.cpu_count()} host cores"}
+        modules = None
+        if a.model == "res8" and world == 1 and not a.no_module_path:
+            try:
+                modules = run_module_path(a, dev, devi[0][0], devi[0][1])
+            except Exception as exc:   # noqa: BLE001 -- a side leg must not take the measurement down
+                modules = {"error": repr(exc)[:300]}
         gpu_lib = None
         if not a.no_gpu_library_baseline and world == 1:
             del step_obj
@@ -532,7 +580,7 @@ def main_ours(a):
                        "l2_policy": f"inputs ({B * a.samples * 4 / 1e6:.0f} MB PCM + activations per step) exceed the 126 MB L2; "
                                     f"{nbuf} alternating batches"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "gpu_library_baseline": gpu_lib, "last_loss": last_loss_dev,
+            "gpu_library_baseline": gpu_lib, "drop_in_modules": modules, "last_loss": last_loss_dev,
             "groups_ms": {g["name"]: round(g["ms"], 4) for g in groups},
         }
         if a.breakdown:

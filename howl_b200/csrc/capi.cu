@@ -43,6 +43,7 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
   ctx->sm_count = prop.multiProcessorCount;
   ctx->fe = *cfg;
   ctx->conv_engine = 1;
+  ctx->lstm_engine = 1;
   ctx->tc_prof = nullptr;
   ctx->tc_prof_kind = 0;
   // tables in double, rounded once
@@ -85,6 +86,11 @@ extern "C" int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t v
   if (strcmp(name, "conv_engine") == 0) {
     HOWL_REQUIRE(ctx, value >= 0 && value <= 2, HOWL_E_INVALID, "set_option: conv_engine must be 0 (fp32), 1 (tcgen05, split bf16) or 2 (tcgen05, single bf16)");
     ctx->conv_engine = (int)value;
+    return HOWL_OK;
+  }
+  if (strcmp(name, "lstm_engine") == 0) {
+    HOWL_REQUIRE(ctx, value == 0 || value == 1, HOWL_E_INVALID, "set_option: lstm_engine must be 0 (plain) or 1 (software pipelined)");
+    ctx->lstm_engine = (int)value;
     return HOWL_OK;
   }
   if (strcmp(name, "pcm_i16") == 0) {

@@ -255,6 +255,147 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_fwd_kernel(const LstmFwdAr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// forward recurrence, software pipelined (default, option "lstm_engine" = 1).  Same mapping and the SAME summation order as
+// lstm_fwd_kernel above (bit-identical results); what changes is when the data moves:
+//   * the weights of the next 8 k are loaded from L2 while the current 8 are multiplied (register double buffer; the first
+//     batch never changes and stays resident), so the ~300-600 cycle L2 round trip no longer sits in front of every 4 k;
+//   * x_{t+1} is fetched from HBM during the product of step t and dropped into shared memory during the cell update
+//     (one __syncthreads less per step, no DRAM latency on the critical path);
+//   * the [k][sequence] tiles are padded to 20 floats per k (16-way -> 4-way bank conflicts of the transposing stores).
+// ---------------------------------------------------------------------------------------------
+#define LS_NBP 20           // padded sequence stride of the [k][16] shared-memory tiles (multiple of 4: 128-bit broadcast reads)
+#define LS_WB 8             // weights in flight per thread
+
+__device__ __forceinline__ void lstm_fma16(float (&acc)[LS_NB], const float w, const float* __restrict__ xrow) {
+  const float4* x4 = reinterpret_cast<const float4*>(xrow);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 x = x4[q];
+    acc[4 * q] = fmaf(w, x.x, acc[4 * q]);
+    acc[4 * q + 1] = fmaf(w, x.y, acc[4 * q + 1]);
+    acc[4 * q + 2] = fmaf(w, x.z, acc[4 * q + 2]);
+    acc[4 * q + 3] = fmaf(w, x.w, acc[4 * q + 3]);
+  }
+}
+
+// acc[b] += sum_{k < n} w[k * ldw] * xs[k * LS_NBP + b], k ascending.  wc[] holds the first LS_WB weights on entry AND on exit (the
+// prefetch of the last batch wraps around to batch 0, i.e. it is the next step's first batch): the double buffer lives across steps.
+__device__ __forceinline__ void lstm_dot_pipelined(float (&acc)[LS_NB], const float* __restrict__ w, const size_t ldw, const float* __restrict__ xs,
+                                                   const int n, float (&wc)[LS_WB]) {
+  const int nb = n / LS_WB;
+#pragma unroll 2
+  for (int kb = 0; kb < nb; ++kb) {
+    float wn[LS_WB];
+    const int kn = (kb + 1 < nb) ? (kb + 1) * LS_WB : 0;
+#pragma unroll
+    for (int i = 0; i < LS_WB; ++i) wn[i] = __ldg(w + (size_t)(kn + i) * ldw);
+#pragma unroll
+    for (int i = 0; i < LS_WB; ++i) lstm_fma16(acc, wc[i], xs + (kb * LS_WB + i) * LS_NBP);
+#pragma unroll
+    for (int i = 0; i < LS_WB; ++i) wc[i] = wn[i];
+  }
+  for (int k = nb * LS_WB; k < n; ++k) lstm_fma16(acc, __ldg(w + (size_t)k * ldw), xs + k * LS_NBP);
+}
+
+__global__ void __launch_bounds__(LS_THREADS, 1) lstm_fwd_pipe_kernel(const LstmFwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int M = a.M, K = M + LS_H;
+  float* s_xh = smem;                        // [K][20]
+  float* s_g = s_xh + K * LS_NBP;            // [16][512]
+  float* s_c = s_g + LS_NB * LS_G;           // [16][128]
+  __shared__ int s_len[LS_NB];
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * LS_NB;
+  if (tid < LS_NB) s_len[tid] = (b0 + tid < a.B) ? (int)a.lengths[b0 + tid] : 0;
+  for (int p = tid; p < LS_NB * LS_H; p += LS_THREADS) {
+    const int b = p / LS_H, u = p - b * LS_H;
+    const bool ok = b0 + b < a.B;
+    s_xh[(M + u) * LS_NBP + b] = ok ? a.h0[(b0 + b) * LS_H + u] : 0.f;
+    s_c[b * LS_H + u] = ok ? a.c0[(b0 + b) * LS_H + u] : 0.f;
+  }
+  // x of one step: element p = (sequence p / M, mel p % M), up to four per thread (M <= 128)
+  float xr[4];
+  auto load_x = [&](int t) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = tid + i * LS_THREADS;
+      const int b = p / M, k = p - b * M;
+      xr[i] = (p < LS_NB * M && b0 + b < a.B && t < a.F && t < a.T) ? __ldg(a.feats + ((b0 + b) * (int64_t)a.F + t) * M + k) : 0.f;
+    }
+  };
+  auto store_x = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = tid + i * LS_THREADS;
+      const int b = p / M, k = p - b * M;
+      if (p < LS_NB * M) s_xh[k * LS_NBP + b] = xr[i];
+    }
+  };
+  load_x(0);
+  store_x();
+  load_x(1);
+  const float bias = a.bsum[tid];
+  const float* wp = a.wt + tid;
+  float w0[LS_WB];
+#pragma unroll
+  for (int i = 0; i < LS_WB; ++i) w0[i] = __ldg(wp + (size_t)i * LS_G);      // K >= 132 > LS_WB
+  __syncthreads();
+  for (int t = 0; t < a.T; ++t) {
+    // gate row `tid` for the 16 sequences
+    float acc[LS_NB];
+#pragma unroll
+    for (int b = 0; b < LS_NB; ++b) acc[b] = bias;
+    lstm_dot_pipelined(acc, wp, LS_G, s_xh, K, w0);
+#pragma unroll
+    for (int b = 0; b < LS_NB; ++b) s_g[b * LS_G + tid] = acc[b];
+    // keep the inputs of this step for the weight gradients
+    if (a.xh) {
+      for (int p = tid; p < LS_NB * K; p += LS_THREADS) {
+        const int b = p / K, k = p - b * K;
+        if (b0 + b < a.B) a.xh[((size_t)t * a.B + b0 + b) * K + k] = s_xh[k * LS_NBP + b];
+      }
+    }
+    __syncthreads();
+    // cell update on (sequence, unit) pairs
+    for (int p = tid; p < LS_NB * LS_H; p += LS_THREADS) {
+      const int b = p / LS_H, u = p - b * LS_H;
+      const float gi = sigmoidf_acc(s_g[b * LS_G + u]);
+      const float gf = sigmoidf_acc(s_g[b * LS_G + LS_H + u]);
+      const float gg = tanhf(s_g[b * LS_G + 2 * LS_H + u]);
+      const float go = sigmoidf_acc(s_g[b * LS_G + 3 * LS_H + u]);
+      const bool live = t < s_len[b];
+      const float c_old = s_c[b * LS_H + u];
+      const float c_new = gf * c_old + gi * gg;
+      const float h_new = go * tanhf(c_new);
+      if (live) {
+        s_c[b * LS_H + u] = c_new;
+        s_xh[(M + u) * LS_NBP + b] = h_new;
+      }
+      if (b0 + b < a.B) {
+        const size_t row = (size_t)t * a.B + b0 + b;
+        if (a.gates) {
+          float* g = a.gates + row * LS_G;
+          g[u] = gi; g[LS_H + u] = gf; g[2 * LS_H + u] = gg; g[3 * LS_H + u] = go;
+          a.cs[row * LS_H + u] = live ? c_new : c_old;
+        }
+        if (a.hseq) a.hseq[row * LS_H + u] = live ? h_new : 0.f;
+      }
+    }
+    // x_{t+1} (in registers since the previous step) replaces x_t, whose last readers finished before the barrier above
+    store_x();
+    load_x(t + 2);
+    __syncthreads();
+  }
+  for (int p = tid; p < LS_NB * LS_H; p += LS_THREADS) {
+    const int b = p / LS_H, u = p - b * LS_H;
+    if (b0 + b < a.B) {
+      a.hfin[(b0 + b) * LS_H + u] = s_xh[(M + u) * LS_NBP + b];
+      a.cfin[(b0 + b) * LS_H + u] = s_c[b * LS_H + u];
+    }
+  }
+}
+
 // =============================================================================================
 // head: Linear(128 -> 256) + ReLU + Linear(256 -> L) on `rows` rows of h; 16 rows per CTA, 256 threads
 // =============================================================================================
@@ -512,6 +653,105 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_kernel(const LstmBwdAr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// backward recurrence, software pipelined (default, option "lstm_engine" = 1); same arithmetic and summation order as
+// lstm_bwd_kernel.  The saved gates / cell states of step t - 1 are fetched from HBM while step t multiplies (c_t of step t - 1
+// is c_prev of step t: carried in a register), the W_hh rows stream through the register double buffer of the forward, the
+// four partial sums of dh are added by the thread that consumes them (one barrier less per step), [j][sequence] tile padded to 20.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_pipe_kernel(const LstmBwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_da = smem;                          // [512][20]
+  float* s_dh = s_da + LS_G * LS_NBP;          // [16][128]
+  float* s_dc = s_dh + LS_NB * LS_H;           // [16][128]
+  float* s_part = s_dc + LS_NB * LS_H;         // [4][16][128]
+  __shared__ int s_len[LS_NB];
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * LS_NB;
+  if (tid < LS_NB) s_len[tid] = (b0 + tid < a.B) ? (int)a.lengths[b0 + tid] : 0;
+  for (int p = tid; p < LS_NB * LS_H; p += LS_THREADS) s_dh[p] = s_dc[p] = 0.f;
+  for (int p = tid; p < 4 * LS_NB * LS_H; p += LS_THREADS) s_part[p] = 0.f;
+  __syncthreads();
+  const int kk = tid & (LS_H - 1), part = tid >> 7;
+  // this thread's four (sequence, unit) pairs: sequence part + 4 i, unit kk
+  constexpr int NP = LS_NB * LS_H / LS_THREADS;
+  float r_g[NP][4], r_ct[NP], r_cp[NP], r_dseq[NP], r_dhead[NP];
+  int len[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int b = part + 4 * i;
+    len[i] = s_len[b];
+    r_dhead[i] = (b0 + b < a.B && a.dh_head) ? a.dh_head[(b0 + b) * LS_H + kk] : 0.f;
+    r_ct[i] = 0.f;
+  }
+  // saved tensors of step t (valid for every t < T and every sequence of the batch, live or not)
+  auto fetch = [&](int t, bool first) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int b = part + 4 * i;
+      const bool inb = b0 + b < a.B;
+      if (inb && t >= 0) {
+        const size_t row = (size_t)t * a.B + b0 + b;
+        const float* g = a.gates + row * LS_G;
+        r_g[i][0] = g[kk]; r_g[i][1] = g[LS_H + kk]; r_g[i][2] = g[2 * LS_H + kk]; r_g[i][3] = g[3 * LS_H + kk];
+        if (first) r_ct[i] = a.cs[row * LS_H + kk];
+        r_cp[i] = t > 0 ? a.cs[(row - a.B) * LS_H + kk] : a.c0[(b0 + b) * LS_H + kk];
+        r_dseq[i] = a.dh_seq ? a.dh_seq[row * LS_H + kk] : 0.f;
+      }
+    }
+  };
+  fetch(a.T - 1, true);
+  const float* wp = a.w_hh + (size_t)(part * LS_H) * LS_H + kk;
+  float w0[LS_WB];
+#pragma unroll
+  for (int i = 0; i < LS_WB; ++i) w0[i] = __ldg(wp + (size_t)i * LS_H);
+  for (int t = a.T - 1; t >= 0; --t) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const int b = part + 4 * i, p = b * LS_H + kk;
+      const bool inb = b0 + b < a.B;
+      const bool live = t < len[i];
+      // dh_{t} = pass-through part + the four partial products of step t + 1 (same order as the separate reduction pass had)
+      float dht = s_dh[p] + (s_part[p] + s_part[LS_NB * LS_H + p] + s_part[2 * LS_NB * LS_H + p] + s_part[3 * LS_NB * LS_H + p]);
+      if (inb && a.dh_head && t == len[i] - 1) dht += r_dhead[i];
+      if (inb && a.dh_seq && live) dht += r_dseq[i];
+      float dai = 0.f, daf = 0.f, dag = 0.f, dao = 0.f;
+      if (inb && live) {
+        float* g = a.gates + ((size_t)t * a.B + b0 + b) * LS_G;
+        const float gi = r_g[i][0], gf = r_g[i][1], gg = r_g[i][2], go = r_g[i][3];
+        const float c_t = r_ct[i], c_prev = r_cp[i];
+        const float tc = tanhf(c_t);
+        const float dtc = dht * go * (1.f - tc * tc) + s_dc[p];
+        dao = dht * tc * go * (1.f - go);
+        dai = dtc * gg * gi * (1.f - gi);
+        dag = dtc * gi * (1.f - gg * gg);
+        daf = dtc * c_prev * gf * (1.f - gf);
+        s_dc[p] = dtc * gf;
+        g[kk] = dai; g[LS_H + kk] = daf; g[2 * LS_H + kk] = dag; g[3 * LS_H + kk] = dao;
+      } else if (inb) {
+        float* g = a.gates + ((size_t)t * a.B + b0 + b) * LS_G;
+        g[kk] = 0.f; g[LS_H + kk] = 0.f; g[2 * LS_H + kk] = 0.f; g[3 * LS_H + kk] = 0.f;
+      }
+      s_da[kk * LS_NBP + b] = dai;
+      s_da[(LS_H + kk) * LS_NBP + b] = daf;
+      s_da[(2 * LS_H + kk) * LS_NBP + b] = dag;
+      s_da[(3 * LS_H + kk) * LS_NBP + b] = dao;
+      s_dh[p] = live ? 0.f : dht;      // dead steps pass the gradient straight through; live ones go through W_hh below
+      r_ct[i] = r_cp[i];               // c_{t-1}: the cell state of the next step to be visited
+    }
+    fetch(t - 1, false);               // in flight during the product below
+    __syncthreads();
+    // dh_prev[b][k] += sum_j W_hh[j][k] da[b][j]: thread (part, k) covers j in [128 part, 128 part + 128)
+    float acc[LS_NB];
+#pragma unroll
+    for (int b = 0; b < LS_NB; ++b) acc[b] = 0.f;
+    lstm_dot_pipelined(acc, wp, LS_H, s_da + (part * LS_H) * LS_NBP, LS_H, w0);
+#pragma unroll
+    for (int b = 0; b < LS_NB; ++b) s_part[(part * LS_NB + b) * LS_H + kk] = acc[b];
+    __syncthreads();
+  }
+}
 
 // =============================================================================================
 // CTC (nn.CTCLoss(blank), reduction 'mean', on log_softmax(scores); training/run/train.py:253,296-298).
@@ -771,9 +1011,15 @@ extern "C" int howl_b200_lstm_fwd(howl_ctx_t* ctx, void* stream, const float* fe
   a.gates = train ? ws.gates : nullptr; a.cs = ws.cs; a.xh = train ? ws.xh : nullptr;
   a.hfin = ws.hfin; a.cfin = ws.cfin; a.hseq = sequential ? ws.hseq : nullptr;
   a.B = B; a.F = frames; a.M = M; a.T = T;
-  const size_t smem = sizeof(float) * ((size_t)K * LS_NB + LS_NB * LS_G + LS_NB * LS_H);
-  HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lstm_fwd_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+  if (ctx->lstm_engine == 0) {
+    const size_t smem = sizeof(float) * ((size_t)K * LS_NB + LS_NB * LS_G + LS_NB * LS_H);
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_fwd_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+  } else {
+    const size_t smem = sizeof(float) * ((size_t)K * LS_NBP + LS_NB * LS_G + LS_NB * LS_H);
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_fwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_fwd_pipe_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+  }
   HOWL_LAUNCHED(ctx, "lstm_fwd");
   if (state_out) {
     HOWL_CUDA(ctx, cudaMemcpyAsync(state_out, ws.hfin, sizeof(float) * B * LS_H, cudaMemcpyDeviceToDevice, st));
@@ -859,9 +1105,15 @@ static int lstm_bwd_impl(howl_ctx_t* ctx, void* stream, const int64_t* lengths, 
   LstmBwdArgs a;
   a.lengths = lengths; a.w_hh = v.w_hh; a.c0 = ws.c0; a.gates = ws.gates; a.cs = ws.cs;
   a.dh_head = sequential ? nullptr : ws.dh; a.dh_seq = sequential ? ws.dh : nullptr; a.B = B; a.T = T;
-  const size_t smem = sizeof(float) * ((size_t)LS_G * LS_NB + 2 * LS_NB * LS_H + 4 * LS_NB * LS_H);
-  HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lstm_bwd_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+  if (ctx->lstm_engine == 0) {
+    const size_t smem = sizeof(float) * ((size_t)LS_G * LS_NB + 2 * LS_NB * LS_H + 4 * LS_NB * LS_H);
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_bwd_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+  } else {
+    const size_t smem = sizeof(float) * ((size_t)LS_G * LS_NBP + 2 * LS_NB * LS_H + 4 * LS_NB * LS_H);
+    HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_bwd_pipe_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+  }
   HOWL_LAUNCHED(ctx, "lstm_bwd");
   // weight gradients over all (t, b) rows: [W_ih | W_hh] from xh = [x_t | h_{t-1}]
   const int64_t R = (int64_t)T * B;

@@ -129,6 +129,48 @@ def test_lstm_fused_train_step_vs_oracle(B, T):
     ctx.close()
 
 
+@pytest.mark.parametrize("B,T,M", [(37, 8000, 40), (530, 8000, 40), (21, 4600, 80), (19, 8000, 44)])   # 44 mels: K = 172 = 21 * 8 + 4 (k tail)
+def test_lstm_pipelined_recurrences_match_the_plain_ones(B, T, M):
+    """Option "lstm_engine": the software-pipelined forward / backward recurrences (default) move data earlier but keep the mapping and
+    the summation order of the plain kernels.  The forward is deterministic end to end, so the logits must agree BIT FOR BIT; the
+    weight-gradient GEMMs and the loss accumulate with atomics (order varies run to run), so gradients are held to 1e-5 of the
+    tensor's scale -- on ragged lengths, for batches that are not a multiple of the 16-sequence CTA tile, with a k tail."""
+    import howl_b200
+
+    L = 7
+    pcm, labels = O.synthetic_batch(B, T, L, seed=B + 1)
+    fb = O.mel_filterbank(M)
+    full = int(O.compute_lengths([T])[0])
+    rng = np.random.default_rng(B)
+    lengths = torch.from_numpy(rng.integers(1, full + 1, size=B))
+    lengths[B // 2] = full
+    got = {}
+    for engine in (0, 1):
+        ctx = howl_b200.Context(DEV, n_mels=M)
+        ctx.set_option("lstm_engine", engine)
+        gen = torch.Generator().manual_seed(5)
+        flat = (torch.randn(ctx.lstm_param_count(L), generator=gen) * 0.08).to(DEV)
+        grads, m, v = torch.zeros_like(flat), torch.zeros_like(flat), torch.zeros_like(flat)
+        loss, logits = torch.zeros(1, device=DEV), torch.zeros(B, L, device=DEV)
+        ws = torch.empty(ctx.lstm_train_step_workspace_bytes(B, T, full, L), dtype=torch.uint8, device=DEV)
+        ctx.lstm_train_step(pcm.to(DEV), labels.to(DEV), lengths.to(DEV), full, fb.to(DEV), (-1.8, 3.9), flat, grads, m, v, 1,
+                            0.01, 1e-5, loss, logits, ws)
+        torch.cuda.synchronize()
+        got[engine] = (loss.clone(), logits.clone(), grads.clone())
+        ctx.close()
+    (l0, z0, g0), (l1, z1, g1) = got[0], got[1]
+    assert torch.isfinite(z1).all() and torch.isfinite(g1).all() and g1.abs().max() > 0
+    assert torch.equal(z0, z1), f"logits: max |diff| = {(z0 - z1).abs().max().item():.3e}"
+    np.testing.assert_allclose(l1.item(), l0.item(), rtol=1e-6)
+    # per parameter tensor of nn.LSTM(M -> 128) + Linear(128 -> 256) + Linear(256 -> L), flat in state_dict order
+    off = 0
+    for name, n in (("w_ih", 512 * M), ("w_hh", 512 * 128), ("b_ih", 512), ("b_hh", 512), ("w1", 256 * 128), ("b1", 256), ("w2", L * 256), ("b2", L)):
+        a, b = g0[off:off + n], g1[off:off + n]
+        assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item() + 1e-12, name
+        off += n
+    assert off == g0.numel()
+
+
 def test_seq_lstm_ctc_reference_steps_module_and_fused(golden):
     """The CTC branch of training/run/train.py:294-302 with the streaming seq-lstm, (a) through the nn.Module mirror with
     torch's log_softmax + nn.CTCLoss + AdamW, (b) through the fused C-ABI step with the library's own CTC kernel."""
