@@ -683,7 +683,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_pipe_kernel(const Lstm
     const int b = part + 4 * i;
     len[i] = s_len[b];
     r_dhead[i] = (b0 + b < a.B && a.dh_head) ? a.dh_head[(b0 + b) * LS_H + kk] : 0.f;
-    r_ct[i] = 0.f;
+    r_ct[i] = r_cp[i] = r_dseq[i] = 0.f;
+    r_g[i][0] = r_g[i][1] = r_g[i][2] = r_g[i][3] = 0.f;
   }
   // saved tensors of step t (valid for every t < T and every sequence of the batch, live or not)
   auto fetch = [&](int t, bool first) {
