@@ -43,7 +43,10 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
   ctx->sm_count = prop.multiProcessorCount;
   ctx->fe = *cfg;
   ctx->conv_engine = 1;
-  ctx->lstm_engine = 1;
+  ctx->lstm_engine = 2;
+  if (const char* e = getenv("HOWL_B200_LSTM_ENGINE")) {   // tuning aid: run unmodified callers on another recurrence engine (same results)
+    if (e[0] >= '0' && e[0] <= '2' && e[1] == 0) ctx->lstm_engine = e[0] - '0';
+  }
   ctx->tc_prof = nullptr;
   ctx->tc_prof_kind = 0;
   // tables in double, rounded once
@@ -89,7 +92,7 @@ extern "C" int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t v
     return HOWL_OK;
   }
   if (strcmp(name, "lstm_engine") == 0) {
-    HOWL_REQUIRE(ctx, value == 0 || value == 1, HOWL_E_INVALID, "set_option: lstm_engine must be 0 (plain) or 1 (software pipelined)");
+    HOWL_REQUIRE(ctx, value >= 0 && value <= 2, HOWL_E_INVALID, "set_option: lstm_engine must be 0 (plain), 1 (software pipelined) or 2 (pipelined, 2 x 8 register tile)");
     ctx->lstm_engine = (int)value;
     return HOWL_OK;
   }

@@ -298,6 +298,51 @@ __device__ __forceinline__ void lstm_dot_pipelined(float (&acc)[LS_NB], const fl
   for (int k = nb * LS_WB; k < n; ++k) lstm_fma16(acc, __ldg(w + (size_t)k * ldw), xs + k * LS_NBP);
 }
 
+// Register tile of 2 rows x 8 sequences (option "lstm_engine" = 2): the same 16 FFMA per k and thread, but they consume two 128-bit
+// shared-memory reads instead of four -- the product of the 1 x 16 tile is bound by the shared-memory pipe (every lane of a warp
+// receives the 16 sequences of a k), not by FFMA issue.  Lanes 0-15 / 16-31 of a warp hold the two sequence halves of the same 16
+// row pairs, so the weight loads of the two half-warps coalesce into one request.  Per output the k order is unchanged (bit-identical).
+__device__ __forceinline__ void lstm_fma2x8(float (&acc)[2][8], const float wa, const float wb, const float* __restrict__ xrow) {
+  const float4* x4 = reinterpret_cast<const float4*>(xrow);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float4 x = x4[q];
+    acc[0][4 * q] = fmaf(wa, x.x, acc[0][4 * q]);
+    acc[0][4 * q + 1] = fmaf(wa, x.y, acc[0][4 * q + 1]);
+    acc[0][4 * q + 2] = fmaf(wa, x.z, acc[0][4 * q + 2]);
+    acc[0][4 * q + 3] = fmaf(wa, x.w, acc[0][4 * q + 3]);
+    acc[1][4 * q] = fmaf(wb, x.x, acc[1][4 * q]);
+    acc[1][4 * q + 1] = fmaf(wb, x.y, acc[1][4 * q + 1]);
+    acc[1][4 * q + 2] = fmaf(wb, x.z, acc[1][4 * q + 2]);
+    acc[1][4 * q + 3] = fmaf(wb, x.w, acc[1][4 * q + 3]);
+  }
+}
+
+// acc[r][j] += sum_{k < n} w[k * ldw + r * row_b] * xs[k * LS_NBP + j]; wc as in lstm_dot_pipelined
+__device__ __forceinline__ void lstm_dot2x8_pipelined(float (&acc)[2][8], const float* __restrict__ w, const size_t ldw, const int row_b,
+                                                      const float* __restrict__ xs, const int n, float (&wc)[2][LS_WB]) {
+  const int nb = n / LS_WB;
+#pragma unroll 2
+  for (int kb = 0; kb < nb; ++kb) {
+    float wn[2][LS_WB];
+    const int kn = (kb + 1 < nb) ? (kb + 1) * LS_WB : 0;
+#pragma unroll
+    for (int i = 0; i < LS_WB; ++i) {
+      wn[0][i] = __ldg(w + (size_t)(kn + i) * ldw);
+      wn[1][i] = __ldg(w + (size_t)(kn + i) * ldw + row_b);
+    }
+#pragma unroll
+    for (int i = 0; i < LS_WB; ++i) lstm_fma2x8(acc, wc[0][i], wc[1][i], xs + (kb * LS_WB + i) * LS_NBP);
+#pragma unroll
+    for (int i = 0; i < LS_WB; ++i) {
+      wc[0][i] = wn[0][i];
+      wc[1][i] = wn[1][i];
+    }
+  }
+  for (int k = nb * LS_WB; k < n; ++k) lstm_fma2x8(acc, __ldg(w + (size_t)k * ldw), __ldg(w + (size_t)k * ldw + row_b), xs + k * LS_NBP);
+}
+
+template <int RT>   // RT = 1: thread = gate row x 16 sequences; RT = 2: thread = 2 gate rows x 8 sequences
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_fwd_pipe_kernel(const LstmFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int M = a.M, K = M + LS_H;
@@ -335,20 +380,40 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_fwd_pipe_kernel(const Lstm
   load_x(0);
   store_x();
   load_x(1);
-  const float bias = a.bsum[tid];
-  const float* wp = a.wt + tid;
-  float w0[LS_WB];
+  // RT = 1: gate row tid, sequences 0..15.  RT = 2: gate rows rA and rA + 256 (warp w: rows 16 w .. 16 w + 15), sequences sq0 .. sq0 + 7
+  const int rA = RT == 1 ? tid : (tid >> 5) * 16 + (tid & 15);
+  const int sq0 = RT == 1 ? 0 : 8 * ((tid >> 4) & 1);
+  const float bias = a.bsum[rA], bias_b = a.bsum[RT == 1 ? rA : rA + LS_G / 2];
+  const float* wp = a.wt + rA;
+  float w0[RT][LS_WB];
 #pragma unroll
-  for (int i = 0; i < LS_WB; ++i) w0[i] = __ldg(wp + (size_t)i * LS_G);      // K >= 132 > LS_WB
+  for (int i = 0; i < LS_WB; ++i) {                                          // K >= 132 > LS_WB
+    w0[0][i] = __ldg(wp + (size_t)i * LS_G);
+    if (RT == 2) w0[RT - 1][i] = __ldg(wp + (size_t)i * LS_G + LS_G / 2);
+  }
   __syncthreads();
   for (int t = 0; t < a.T; ++t) {
-    // gate row `tid` for the 16 sequences
-    float acc[LS_NB];
+    if constexpr (RT == 1) {
+      float acc[LS_NB];
 #pragma unroll
-    for (int b = 0; b < LS_NB; ++b) acc[b] = bias;
-    lstm_dot_pipelined(acc, wp, LS_G, s_xh, K, w0);
+      for (int b = 0; b < LS_NB; ++b) acc[b] = bias;
+      lstm_dot_pipelined(acc, wp, LS_G, s_xh, K, w0[0]);
 #pragma unroll
-    for (int b = 0; b < LS_NB; ++b) s_g[b * LS_G + tid] = acc[b];
+      for (int b = 0; b < LS_NB; ++b) s_g[b * LS_G + tid] = acc[b];
+    } else {
+      float acc[2][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] = bias;
+        acc[1][j] = bias_b;
+      }
+      lstm_dot2x8_pipelined(acc, wp, LS_G, LS_G / 2, s_xh + sq0, K, w0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s_g[(sq0 + j) * LS_G + rA] = acc[0][j];
+        s_g[(sq0 + j) * LS_G + rA + LS_G / 2] = acc[1][j];
+      }
+    }
     // keep the inputs of this step for the weight gradients
     if (a.xh) {
       for (int p = tid; p < LS_NB * K; p += LS_THREADS) {
@@ -660,6 +725,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_kernel(const LstmBwdAr
 // is c_prev of step t: carried in a register), the W_hh rows stream through the register double buffer of the forward, the
 // four partial sums of dh are added by the thread that consumes them (one barrier less per step), [j][sequence] tile padded to 20.
 // ---------------------------------------------------------------------------------------------
+template <int RT>   // register tile of the dh product: 1 = (part, k) x 16 sequences, 2 = (part, k and k + 64) x 8 sequences
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_pipe_kernel(const LstmBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* s_da = smem;                          // [512][20]
@@ -703,10 +769,16 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_pipe_kernel(const Lstm
     }
   };
   fetch(a.T - 1, true);
-  const float* wp = a.w_hh + (size_t)(part * LS_H) * LS_H + kk;
-  float w0[LS_WB];
+  // product mapping.  RT = 1: column kk, sequences 0..15.  RT = 2: columns kA and kA + 64 (the part's warp q: 16 q .. 16 q + 15), sequences sq0 .. sq0 + 7
+  const int kA = RT == 1 ? kk : ((tid >> 5) & 3) * 16 + (tid & 15);
+  const int sq0 = RT == 1 ? 0 : 8 * ((tid >> 4) & 1);
+  const float* wp = a.w_hh + (size_t)(part * LS_H) * LS_H + kA;
+  float w0[RT][LS_WB];
 #pragma unroll
-  for (int i = 0; i < LS_WB; ++i) w0[i] = __ldg(wp + (size_t)i * LS_H);
+  for (int i = 0; i < LS_WB; ++i) {
+    w0[0][i] = __ldg(wp + (size_t)i * LS_H);
+    if (RT == 2) w0[RT - 1][i] = __ldg(wp + (size_t)i * LS_H + LS_H / 2);
+  }
   for (int t = a.T - 1; t >= 0; --t) {
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -744,12 +816,24 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_pipe_kernel(const Lstm
     fetch(t - 1, false);               // in flight during the product below
     __syncthreads();
     // dh_prev[b][k] += sum_j W_hh[j][k] da[b][j]: thread (part, k) covers j in [128 part, 128 part + 128)
-    float acc[LS_NB];
+    if constexpr (RT == 1) {
+      float acc[LS_NB];
 #pragma unroll
-    for (int b = 0; b < LS_NB; ++b) acc[b] = 0.f;
-    lstm_dot_pipelined(acc, wp, LS_H, s_da + (part * LS_H) * LS_NBP, LS_H, w0);
+      for (int b = 0; b < LS_NB; ++b) acc[b] = 0.f;
+      lstm_dot_pipelined(acc, wp, LS_H, s_da + (part * LS_H) * LS_NBP, LS_H, w0[0]);
 #pragma unroll
-    for (int b = 0; b < LS_NB; ++b) s_part[(part * LS_NB + b) * LS_H + kk] = acc[b];
+      for (int b = 0; b < LS_NB; ++b) s_part[(part * LS_NB + b) * LS_H + kk] = acc[b];
+    } else {
+      float acc[2][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+      lstm_dot2x8_pipelined(acc, wp, LS_H, LS_H / 2, s_da + (part * LS_H) * LS_NBP + sq0, LS_H, w0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s_part[(part * LS_NB + sq0 + j) * LS_H + kA] = acc[0][j];
+        s_part[(part * LS_NB + sq0 + j) * LS_H + kA + LS_H / 2] = acc[1][j];
+      }
+    }
     __syncthreads();
   }
 }
@@ -1018,8 +1102,13 @@ extern "C" int howl_b200_lstm_fwd(howl_ctx_t* ctx, void* stream, const float* fe
     lstm_fwd_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
   } else {
     const size_t smem = sizeof(float) * ((size_t)K * LS_NBP + LS_NB * LS_G + LS_NB * LS_H);
-    HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_fwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_fwd_pipe_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+    if (ctx->lstm_engine == 2) {
+      HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_fwd_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lstm_fwd_pipe_kernel<2><<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+    } else {
+      HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_fwd_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lstm_fwd_pipe_kernel<1><<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+    }
   }
   HOWL_LAUNCHED(ctx, "lstm_fwd");
   if (state_out) {
@@ -1112,8 +1201,13 @@ static int lstm_bwd_impl(howl_ctx_t* ctx, void* stream, const int64_t* lengths, 
     lstm_bwd_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
   } else {
     const size_t smem = sizeof(float) * ((size_t)LS_G * LS_NBP + 2 * LS_NB * LS_H + 4 * LS_NB * LS_H);
-    HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_bwd_pipe_kernel<<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+    if (ctx->lstm_engine == 2) {
+      HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_bwd_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lstm_bwd_pipe_kernel<2><<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+    } else {
+      HOWL_CUDA(ctx, cudaFuncSetAttribute(lstm_bwd_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lstm_bwd_pipe_kernel<1><<<(unsigned)howl_ceil_div(B, LS_NB), LS_THREADS, smem, st>>>(a);
+    }
   }
   HOWL_LAUNCHED(ctx, "lstm_bwd");
   // weight gradients over all (t, b) rows: [W_ih | W_hh] from xh = [x_t | h_{t-1}]

@@ -131,8 +131,8 @@ def test_lstm_fused_train_step_vs_oracle(B, T):
 
 @pytest.mark.parametrize("B,T,M", [(37, 8000, 40), (530, 8000, 40), (21, 4600, 80), (19, 8000, 44)])   # 44 mels: K = 172 = 21 * 8 + 4 (k tail)
 def test_lstm_pipelined_recurrences_match_the_plain_ones(B, T, M):
-    """Option "lstm_engine": the software-pipelined forward / backward recurrences (default) move data earlier but keep the mapping and
-    the summation order of the plain kernels.  The forward is deterministic end to end, so the logits must agree BIT FOR BIT; the
+    """Option "lstm_engine": the software-pipelined forward / backward recurrences (1: same thread mapping; 2: 2 x 8 register tile) move
+    data earlier / re-tile the product but keep the summation order per output of the plain kernels (0).  The forward is deterministic end to end, so the logits must agree BIT FOR BIT; the
     weight-gradient GEMMs and the loss accumulate with atomics (order varies run to run), so gradients are held to 1e-5 of the
     tensor's scale -- on ragged lengths, for batches that are not a multiple of the 16-sequence CTA tile, with a k tail."""
     import howl_b200
@@ -145,7 +145,7 @@ def test_lstm_pipelined_recurrences_match_the_plain_ones(B, T, M):
     lengths = torch.from_numpy(rng.integers(1, full + 1, size=B))
     lengths[B // 2] = full
     got = {}
-    for engine in (0, 1):
+    for engine in (0, 1, 2):
         ctx = howl_b200.Context(DEV, n_mels=M)
         ctx.set_option("lstm_engine", engine)
         gen = torch.Generator().manual_seed(5)
@@ -158,17 +158,19 @@ def test_lstm_pipelined_recurrences_match_the_plain_ones(B, T, M):
         torch.cuda.synchronize()
         got[engine] = (loss.clone(), logits.clone(), grads.clone())
         ctx.close()
-    (l0, z0, g0), (l1, z1, g1) = got[0], got[1]
-    assert torch.isfinite(z1).all() and torch.isfinite(g1).all() and g1.abs().max() > 0
-    assert torch.equal(z0, z1), f"logits: max |diff| = {(z0 - z1).abs().max().item():.3e}"
-    np.testing.assert_allclose(l1.item(), l0.item(), rtol=1e-6)
-    # per parameter tensor of nn.LSTM(M -> 128) + Linear(128 -> 256) + Linear(256 -> L), flat in state_dict order
-    off = 0
-    for name, n in (("w_ih", 512 * M), ("w_hh", 512 * 128), ("b_ih", 512), ("b_hh", 512), ("w1", 256 * 128), ("b1", 256), ("w2", L * 256), ("b2", L)):
-        a, b = g0[off:off + n], g1[off:off + n]
-        assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item() + 1e-12, name
-        off += n
-    assert off == g0.numel()
+    l0, z0, g0 = got[0]
+    for engine in (1, 2):
+        l1, z1, g1 = got[engine]
+        assert torch.isfinite(z1).all() and torch.isfinite(g1).all() and g1.abs().max() > 0
+        assert torch.equal(z0, z1), f"engine {engine} logits: max |diff| = {(z0 - z1).abs().max().item():.3e}"
+        np.testing.assert_allclose(l1.item(), l0.item(), rtol=1e-6)
+        # per parameter tensor of nn.LSTM(M -> 128) + Linear(128 -> 256) + Linear(256 -> L), flat in state_dict order
+        off = 0
+        for name, n in (("w_ih", 512 * M), ("w_hh", 512 * 128), ("b_ih", 512), ("b_hh", 512), ("w1", 256 * 128), ("b1", 256), ("w2", L * 256), ("b2", L)):
+            a, b = g0[off:off + n], g1[off:off + n]
+            assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item() + 1e-12, (engine, name)
+            off += n
+        assert off == g0.numel()
 
 
 def test_seq_lstm_ctc_reference_steps_module_and_fused(golden):

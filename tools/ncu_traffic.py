@@ -5,7 +5,7 @@ import csv, json, sys, collections
 
 LABELS = [("conv3x3_stream_tc_kernel<0", "conv3x3_fwd_tc"), ("conv3x3_stream_tc_kernel<1", "conv3x3_fwd_tc"), ("conv3x3_stream_tc_kernel<2", "conv3x3_dgrad_tc"),
           ("conv3x3_stream_tc_kernel<3", "conv3x3_dgrad_tc"), ("conv3x3_wgrad_tc_kernel", "conv3x3_wgrad_tc"), ("frontend_kernel", "frontend"),
-          ("conv0_pool_kernel", "conv0_pool"), ("conv0_tc_kernel", "conv0_tc"), ("conv0_halo_kernel", "conv0_halo"), ("lstm_fwd_kernel", "lstm_fwd"),
+          ("conv0_pool_kernel", "conv0_pool"), ("conv0_tc_kernel", "conv0_tc"), ("conv0_halo_kernel", "conv0_halo"), ("lstm_fwd_kernel", "lstm_fwd"), ("lstm_fwd_pipe_kernel", "lstm_fwd"), ("lstm_bwd_pipe_kernel", "lstm_bwd"),
           ("lstm_bwd_kernel", "lstm_bwd"), ("lstm_atb_kernel", "lstm_atb"), ("ctc_kernel", "ctc"), ("conv0_bwd_kernel", "conv0_bwd"), ("bn_bwd_head_op_kernel", "bn_bwd_head_op")]
 WANT = {"dram__bytes_read.sum": "rd", "dram__bytes_write.sum": "wr", "gpu__time_duration.sum": "ns", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pct", "sm__inst_executed_pipe_tensor.sum": "tensor_inst",

@@ -1,4 +1,4 @@
-# One gpurun call: LSTM engine A/B (tests + bench), the new module-path leg of the res8 bench, then the rest of the GPU suite.
+# gpurun call 1: LSTM engine A/B (tests + bench) and the tests touching this session's other changes (deltas entry point, frontend.cu).
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
@@ -17,14 +17,5 @@ for e in (0, 1):
         print("${m}", e, "FAILED", exc)
 PY
 done
-timeout 300 python bench.py $B > gpurun_out/bench_res8.json 2> gpurun_out/bench_res8.err
-python - <<PY
-import json
-try:
-    d = json.load(open("gpurun_out/bench_res8.json"))
-    print("res8", round(d["ms_per_step"], 4), "ms", round(d["value"]), "utt/s e2e", round(d["e2e"]["value"]), "modules", d.get("drop_in_modules"))
-except Exception as exc:
-    print("res8 FAILED", exc)
-PY
 timeout 300 python -m pytest tests/test_gpu_api.py -q 2>&1 | tail -15 > gpurun_out/t_api.txt; tail -4 gpurun_out/t_api.txt
-timeout ${REST_TIMEOUT:-420} python -m pytest tests -m gpu -v --ignore=tests/test_gpu_lstm.py --ignore=tests/test_gpu_api.py --durations=15 > gpurun_out/t_rest.txt 2>&1; tail -25 gpurun_out/t_rest.txt | cut -c1-200
+timeout 200 python -m pytest tests/test_gpu_parity.py -q -k frontend 2>&1 | tail -8 > gpurun_out/t_fe.txt; tail -3 gpurun_out/t_fe.txt
