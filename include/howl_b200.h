@@ -66,7 +66,9 @@ int64_t howl_b200_launch_count(const howl_ctx_t* ctx);
 /* "pcm_i16" = 1 (persistent): every `pcm` argument of this context -- frontend_fwd and the fused train steps -- is int16 (see
  * HOWL_FE_PCM_I16).
  * "fb_unchanged" = 1: one-shot promise that the NEXT frontend / train-step call passes the same filterbank contents as the previous
- * one on this context, so the compact bank + work plan built from it are reused instead of rebuilt (cleared by that call). */
+ * one on this context, so the compact bank + work plan built from it are reused instead of rebuilt (cleared by that call).
+ * "lstm_engine" = 2 (default) software-pipelined lstm / seq-lstm recurrences with a 2 x 8 register tile; 1 = pipelined, 1 x 16 tile;
+ * 0 = the plain kernels.  All three keep the summation order per output: identical results, different speed. */
 int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t value);
 /* ---- per-launch device timing (CUDA events on the launching stream; used by bench.py's roofline) --------- */
 /* After profile_begin every kernel launch of this context is bracketed by an event on `stream`. */
