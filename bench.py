@@ -440,8 +440,6 @@ def main_ours(a):
     step_obj = make_step(a, dev, world)
     if os.environ.get("HOWL_CONV_ENGINE"):   # tuning experiments only
         step_obj.ctx.set_option("conv_engine", int(os.environ["HOWL_CONV_ENGINE"]))
-    if os.environ.get("HOWL_TC_L2_PREFETCH"):   # A/B: L2 prefetch ahead of the TMA rings of the tensor-core convolutions (default on)
-        step_obj.ctx.set_option("tc_l2_prefetch", int(os.environ["HOWL_TC_L2_PREFETCH"]))
     if os.environ.get("HOWL_LSTM_ENGINE"):   # A/B of the recurrences: 0 = plain, 1 = software pipelined, 2 = pipelined + 2 x 8 register tile (default)
         step_obj.ctx.set_option("lstm_engine", int(os.environ["HOWL_LSTM_ENGINE"]))
     ctx = step_obj.ctx

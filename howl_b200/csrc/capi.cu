@@ -43,7 +43,6 @@ extern "C" int howl_b200_create(int device, const howl_frontend_cfg* cfg, howl_c
   ctx->sm_count = prop.multiProcessorCount;
   ctx->fe = *cfg;
   ctx->conv_engine = 1;
-  ctx->tc_l2_prefetch = 1;
   ctx->lstm_engine = 2;
   if (const char* e = getenv("HOWL_B200_LSTM_ENGINE")) {   // tuning aid: run unmodified callers on another recurrence engine (same results)
     if (e[0] >= '0' && e[0] <= '2' && e[1] == 0) ctx->lstm_engine = e[0] - '0';
@@ -90,10 +89,6 @@ extern "C" int howl_b200_set_option(howl_ctx_t* ctx, const char* name, int64_t v
   if (strcmp(name, "conv_engine") == 0) {
     HOWL_REQUIRE(ctx, value >= 0 && value <= 2, HOWL_E_INVALID, "set_option: conv_engine must be 0 (fp32), 1 (tcgen05, split bf16) or 2 (tcgen05, single bf16)");
     ctx->conv_engine = (int)value;
-    return HOWL_OK;
-  }
-  if (strcmp(name, "tc_l2_prefetch") == 0) {
-    ctx->tc_l2_prefetch = value != 0;
     return HOWL_OK;
   }
   if (strcmp(name, "lstm_engine") == 0) {

@@ -29,7 +29,6 @@ struct howl_ctx {
   int fb_same_next;  // one-shot promise of the caller (set_option "fb_unchanged"): the next call's fb equals the previous call's
   int64_t launches;
   int conv_engine;
-  int tc_l2_prefetch;   // option "tc_l2_prefetch": the tensor-core convolutions pull the utterance after next into L2 ahead of their TMA rings
   int lstm_engine;   // option "lstm_engine": 0 = plain recurrences, 1 = software pipelined, 2 = pipelined with the 2 x 8 register tile (default); same results
   unsigned long long* tc_prof;   // tuning aid (howl_b200_debug_stream_profile): device buffer [sm_count][16] or null
   int tc_prof_kind;              // 1 = forward, 2 = data gradient

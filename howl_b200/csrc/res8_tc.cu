@@ -164,7 +164,6 @@ struct TcStreamArgs {
   const uint16_t* mask_in;       // ReLU decisions of conv_j stored by the forward (even j), or null (odd j: u > 0)
   __nv_bfloat16* dc_out;
   int R;
-  int l2_ahead;                  // option "tc_l2_prefetch": utterances pulled into L2 ahead of the shared-memory ring (0 = off)
   unsigned long long* prof;      // tuning aid: per-CTA cycle counters of the pipeline waits, or null
 };
 
@@ -261,9 +260,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv3x3_stream_tc_kernel(const 
         tc::mbar_expect_tx(&bar_in[s], (uint32_t)utt_bytes);
         for (int g = 0; g < 12; ++g)
           tc::tma_bulk_g2s(a_s + (size_t)g * RS + TC_PAD + s * R, src + (size_t)g * R * 16, (uint32_t)(R * 16), &bar_in[s]);
-        // the ring holds two utterances, i.e. a load is issued about one utterance of MMAs before its data is needed: have the
-        // utterance after next on its way from DRAM to L2 already, so that its ring refill is an L2 hit
-        if (a.l2_ahead && k + 2 < n_local) tc::l2_prefetch_bulk(src + 2 * (size_t)gridDim.x * utt_bytes, (uint32_t)utt_bytes);
         // what the epilogue of this utterance will read (residual / BatchNorm-backward input): pull it into L2 now
         if (side_op) tc::l2_prefetch_bulk(reinterpret_cast<const unsigned char*>(side_op) + (size_t)b * utt_bytes, (uint32_t)utt_bytes);
         if (side) {
@@ -541,7 +537,6 @@ int r8tc_conv(howl_ctx_t* ctx, cudaStream_t st, const TcConvCall& c) {
   HOWL_REQUIRE(ctx, c.mode != 3 || (c.u_op && c.bn_coef && c.dc_out && c.dc_out != c.in_op), HOWL_E_INVALID,
                "tensor-core conv: fused BatchNorm-backward arguments missing");
   a.R = r8tc_dcop_rows(c.H);
-  a.l2_ahead = ctx->tc_l2_prefetch;
   const bool fwd = c.mode <= 1;
   a.prof = (ctx->tc_prof && ctx->tc_prof_kind == (fwd ? 1 : 2)) ? ctx->tc_prof : nullptr;
   HOWL_REQUIRE(ctx, r8tc_supported(c.H), HOWL_E_UNSUPPORTED, "tensor-core conv: H=%d does not fit", c.H);
@@ -593,7 +588,6 @@ struct TcWgradArgs {
   float* dones;          // [45][9]: sum_q dC[q][o] * 1[q + shift inside the image] -- the raw ones column (BatchNorm-backward statistics), or null
   int64_t B;
   int R;
-  int l2_ahead;          // option "tc_l2_prefetch"
 };
 #define TW_ASLOTS 8          // ring of A tiles in tensor memory behind the 9 x 48 accumulator columns
 #define TW_DSLOTS 3          // shared-memory ring of TRANSPOSED dC quarter-utterances (A tiles for tcgen05.cp)
@@ -652,11 +646,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
         const int rs = (int)(g % TW_RSLOTS);
         if (g >= TW_RSLOTS) tc::mbar_wait(&bar_rawfree[rs], (uint32_t)(((g / TW_RSLOTS) - 1) & 1));
         const int64_t b = blockIdx.x + (g >> 2) * (int64_t)gridDim.x;
-        // the raw ring reaches less than an utterance ahead: keep the gradients of the next two utterances on their way to L2
-        if (a.l2_ahead && (g & 3) == 0) {
-          if (g == 0 && n_local > 1) tc::l2_prefetch_bulk(dsrc + (size_t)(b + gridDim.x) * u_bytes, u_bytes);
-          if ((g >> 2) + 2 < n_local) tc::l2_prefetch_bulk(dsrc + (size_t)(b + 2 * (int64_t)gridDim.x) * u_bytes, u_bytes);
-        }
         tc::mbar_expect_tx(&bar_raw[rs], q_bytes);
         for (uint32_t pc = 0; pc < 12; ++pc)
           tc::tma_bulk_g2s(r_ring + (size_t)rs * r_bytes + (size_t)pc * r_plane, dsrc + (size_t)b * u_bytes + ((size_t)pc * R + (size_t)(g & 3) * Rq) * 16, slice,
@@ -671,7 +660,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_wgrad_tc_kernel(const T
       for (int64_t k = 0; k < n_local; ++k) {
         if (k >= 2) tc::mbar_wait(&bar_xfree[k & 1], (uint32_t)(((k >> 1) - 1) & 1));
         const int64_t b = blockIdx.x + k * (int64_t)gridDim.x;
-        if (a.l2_ahead && k + 2 < n_local) tc::l2_prefetch_bulk(xsrc + (size_t)(b + 2 * (int64_t)gridDim.x) * u_bytes, u_bytes);
         tc::mbar_expect_tx(&bar_x[k & 1], u_bytes);
         for (uint32_t g = 0; g < 12; ++g)
           tc::tma_bulk_g2s(x_buf + (size_t)(k & 1) * x_bytes + ((size_t)g * Rx + TC_PAD) * 16,
@@ -796,7 +784,6 @@ int r8tc_wgrad(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* dc_op, con
   TcWgradArgs a;
   a.dc_op = dc_op; a.x_op = x_op; a.x_mean = x_mean; a.x_rstd = x_rstd; a.dw = dw; a.dones = dones; a.B = B;
   a.R = r8tc_dcop_rows(H);
-  a.l2_ahead = ctx->tc_l2_prefetch;
   HOWL_REQUIRE(ctx, r8tc_supported(H), HOWL_E_UNSUPPORTED, "tensor-core wgrad: H=%d does not fit", H);
   const size_t smem = tc_wgrad_smem(a.R);
   const int grid = (int)(B < ctx->sm_count ? B : ctx->sm_count);
