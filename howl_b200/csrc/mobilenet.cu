@@ -1040,11 +1040,19 @@ __global__ void __launch_bounds__(256) mbn_stem_im2col_kernel(const MbStemArgs a
 // backward of the stem.  pass 0: S1 = sum dn, S2 = sum dn * xhat;  pass 1: dRaw -> conv weight / bias gradients
 template <int PASS>
 __global__ void __launch_bounds__(256) mbn_stem_bwd_kernel(const MbStemArgs a, double count) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int64_t b = blockIdx.x;
   const int pitch = mb_stem_stage(a, b, smem);
   float* s_ds = smem + (a.H + 2) * (a.W + 8);           // [3][H][Wp] gradient w.r.t. the pooled activations (col2im, gathered)
   const int npix = a.ho * a.wo;
+  // the utterance's rows of the im2col gradient, staged once with coalesced 128-bit loads (consecutive threads = consecutive rows of a
+  // 128-row tile); the col2im gather below then reads single bf16 values out of shared memory instead of scattered 2-byte global loads
+  uint4* s_dcol = reinterpret_cast<uint4*>(smem + (((a.H + 2) * (a.W + 8) + 3 * a.H * a.Wp + 3) & ~3));      // [npix][4 chunks], 16-byte aligned
+  for (int i = threadIdx.x; i < npix * 4; i += blockDim.x) {
+    const int chunk = i / npix, pix = i - chunk * npix;
+    s_dcol[pix * 4 + chunk] = __ldg(a.dcol + mbn_vec(b * npix + pix, chunk, 4));
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < 3 * a.H * a.Wp; i += blockDim.x) {
     const int c = i / (a.H * a.Wp), rem = i - c * a.H * a.Wp, y = rem / a.Wp, x = rem - y * a.Wp;
     float g = 0.f;
@@ -1055,7 +1063,7 @@ __global__ void __launch_bounds__(256) mbn_stem_bwd_kernel(const MbStemArgs a, d
         const int tx = x + 1 - kx;
         if (tx < 0 || (tx & 1) || tx / 2 >= a.wo) continue;
         const int col = c * 9 + ky * 3 + kx;
-        const __nv_bfloat16* vec = reinterpret_cast<const __nv_bfloat16*>(a.dcol + mbn_vec(b * npix + (ty / 2) * a.wo + tx / 2, col >> 3, 4));
+        const __nv_bfloat16* vec = reinterpret_cast<const __nv_bfloat16*>(s_dcol + ((ty / 2) * a.wo + tx / 2) * 4 + (col >> 3));
         g += __bfloat162float(vec[col & 7]);
       }
     }
@@ -1570,7 +1578,8 @@ static int mb_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
     a.bstats = ws.bstats;
     a.dw = grads + net.convs[0].w_off;
     a.dbias = grads + net.convs[0].bias_off;
-    const size_t sm = sizeof(float) * ((size_t)(a.H + 2) * (a.W + 8) + 3 * (size_t)a.H * a.Wp);
+    const size_t sm = sizeof(float) * ((size_t)(a.H + 2) * (a.W + 8) + 3 * (size_t)a.H * a.Wp + 4) + 64 * (size_t)a.ho * a.wo;   // x tile, ds, dcol tile
+    HOWL_REQUIRE(ctx, sm <= 200 * 1024, HOWL_E_UNSUPPORTED, "mobilenet_bwd: %d frames do not fit the stem's shared-memory tiles", a.W);
     HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_stem_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     HOWL_CUDA(ctx, cudaFuncSetAttribute(mbn_stem_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     HOWL_CUDA(ctx, cudaMemsetAsync(ws.bstats, 0, sizeof(double) * 2 * MB_MAXC, st));
