@@ -30,6 +30,17 @@ int mbn_ntile(int np);
 //   out = [np / nt tiles][kp / 8][nt rows][8] bf16;  transpose != 0 takes the matrix as [k][n] (the data-gradient operand W^T)
 int mbn_weight_operand(howl_ctx_t* ctx, cudaStream_t st, const float* w, int n, int k, int ld, int transpose, __nv_bfloat16* out);
 size_t mbn_weight_operand_bytes(int n, int k);
+// several operands in one launch (kernel-argument table)
+#define MBN_WOP_BATCH 40
+struct MbnWopDesc {
+  const float* w;
+  __nv_bfloat16* out;
+  int n, k, ld, transpose, nt;   // nt is filled in by mbn_weight_operand_batch
+};
+struct MbnWopBatch {
+  MbnWopDesc d[MBN_WOP_BATCH];
+};
+int mbn_weight_operand_batch(howl_ctx_t* ctx, cudaStream_t st, const MbnWopDesc* descs, int count);
 // C[M x N] = A[M x K] * W[N x K]^T (+ Add):  A, C, Add in TMO (rows >= M are written as zero), fp32 accumulation in TMEM
 int mbn_gemm_nt(howl_ctx_t* ctx, cudaStream_t st, const __nv_bfloat16* A, const __nv_bfloat16* wop, const __nv_bfloat16* add,
                 __nv_bfloat16* C, int64_t M, int K, int N);

@@ -44,6 +44,36 @@ __global__ void mbn_weight_operand_kernel(const float* __restrict__ w, int n, in
   }
 }
 
+// The same conversion for up to MBN_WOP_BATCH matrices in ONE launch (grid.y = matrix): a MobileNetV2 step prepares 35 + 35 operands of a
+// few KB each, i.e. 70 launches that are pure launch latency when issued one by one.
+__global__ void mbn_weight_operand_batch_kernel(const MbnWopBatch batch) {
+  const MbnWopDesc d = batch.d[blockIdx.y];
+  const int np = mbn_pad16(d.n), kp = mbn_pad16(d.k), nt = d.nt;
+  const int total = np * kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i & 7, row = (i >> 3) % nt, chunk = ((i >> 3) / nt) % (kp / 8), tile = (i >> 3) / (nt * (kp / 8));
+    const int nn = tile * nt + row, kk = chunk * 8 + j;
+    float v = 0.f;
+    if (nn < d.n && kk < d.k) v = d.transpose ? d.w[(size_t)kk * d.ld + nn] : d.w[(size_t)nn * d.ld + kk];
+    d.out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+int mbn_weight_operand_batch(howl_ctx_t* ctx, cudaStream_t st, const MbnWopDesc* descs, int count) {
+  for (int first = 0; first < count; first += MBN_WOP_BATCH) {
+    MbnWopBatch batch;
+    const int m = count - first < MBN_WOP_BATCH ? count - first : MBN_WOP_BATCH;
+    for (int i = 0; i < m; ++i) {
+      batch.d[i] = descs[first + i];
+      HOWL_REQUIRE(ctx, batch.d[i].w && batch.d[i].out && batch.d[i].n > 0 && batch.d[i].k > 0, HOWL_E_INVALID, "mbn_weight_operand_batch: bad matrix %d", first + i);
+      batch.d[i].nt = mbn_ntile(mbn_pad16(batch.d[i].n));
+    }
+    mbn_weight_operand_batch_kernel<<<dim3(48, (unsigned)m), 256, 0, st>>>(batch);
+    HOWL_LAUNCHED(ctx, "mbn_weight_operand");
+  }
+  return HOWL_OK;
+}
+
 int mbn_weight_operand(howl_ctx_t* ctx, cudaStream_t st, const float* w, int n, int k, int ld, int transpose, __nv_bfloat16* out) {
   const int np = mbn_pad16(n), kp = mbn_pad16(k), nt = mbn_ntile(np);
   const int total = np * kp;

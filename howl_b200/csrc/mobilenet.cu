@@ -1386,14 +1386,14 @@ extern "C" int howl_b200_mobilenet_fwd(howl_ctx_t* ctx, void* stream, const floa
     for (size_t i = 0; i < n; ++i) HOWL_CUDA(ctx, cudaMemsetAsync(ws.stats[i], 0, sizeof(double) * 2 * mbn_pad16(net.convs[i].cout), st));
   }
   // ---- weight operands (bf16) from the fp32 master weights
-  for (size_t i = 1; i < n; ++i) {
-    const MbConv& c = net.convs[i];
-    if (c.kind == 1) {
-      rc = mbn_weight_operand(ctx, st, params + c.w_off, c.cout, 27, 27, 0, ws.wop[i]);
-    } else if (c.kind == 2) {
-      rc = mbn_weight_operand(ctx, st, params + c.w_off, c.cout, c.cin, c.cin, 0, ws.wop[i]);
+  {
+    std::vector<MbnWopDesc> descs;
+    for (size_t i = 1; i < n; ++i) {
+      const MbConv& c = net.convs[i];
+      if (c.kind == 1) descs.push_back(MbnWopDesc{params + c.w_off, ws.wop[i], c.cout, 27, 27, 0, 0});
+      else if (c.kind == 2) descs.push_back(MbnWopDesc{params + c.w_off, ws.wop[i], c.cout, c.cin, c.cin, 0, 0});
     }
-    if (rc) return rc;
+    if ((rc = mbn_weight_operand_batch(ctx, st, descs.data(), (int)descs.size()))) return rc;
   }
   // ---- stem (+ the entry convolution's im2col matrix)
   {
@@ -1481,11 +1481,14 @@ static int mb_bwd_impl(howl_ctx_t* ctx, void* stream, const float* feats, const 
   HOWL_CUDA(ctx, cudaMemsetAsync(grads, 0, sizeof(float) * net.n_params, st));
   HOWL_CUDA(ctx, cudaMemsetAsync(ws.loss_acc, 0, sizeof(double) * 2, st));
   // data-gradient weight operands (W^T) of the GEMM convolutions
-  for (size_t i = 1; i < n; ++i) {
-    const MbConv& c = net.convs[i];
-    if (c.kind == 1) rc = mbn_weight_operand(ctx, st, params + c.w_off, 27, c.cout, 27, 1, ws.wopT[i]);
-    else if (c.kind == 2) rc = mbn_weight_operand(ctx, st, params + c.w_off, c.cin, c.cout, c.cin, 1, ws.wopT[i]);
-    if (rc) return rc;
+  {
+    std::vector<MbnWopDesc> descs;
+    for (size_t i = 1; i < n; ++i) {
+      const MbConv& c = net.convs[i];
+      if (c.kind == 1) descs.push_back(MbnWopDesc{params + c.w_off, ws.wopT[i], 27, c.cout, 27, 1, 0});
+      else if (c.kind == 2) descs.push_back(MbnWopDesc{params + c.w_off, ws.wopT[i], c.cin, c.cout, c.cin, 1, 0});
+    }
+    if ((rc = mbn_weight_operand_batch(ctx, st, descs.data(), (int)descs.size()))) return rc;
   }
   // ---- head
   mbn_ce_kernel<<<(unsigned)howl_ceil_div(B, 128), 128, 0, st>>>(ws.logits, labels, dlogits_in, ws.dlogits, ws.loss_acc, B, L,
