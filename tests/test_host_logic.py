@@ -391,3 +391,42 @@ def test_flat_parameter_layouts_have_the_reference_sizes():
     assert names[:4] == ["encoder.conv1.weight", "encoder.conv1.bias", "encoder.conv2.weight", "encoder.conv2.bias"] and names[-1] == "fc.3.bias"
     for arch, cls in trainer.Trainer.STEPS.items():
         assert hasattr(trainer, cls), (arch, cls)
+
+
+def test_product_code_never_touches_the_oracle_or_the_reference_checkout():
+    """The oracle is test infrastructure: nothing under howl_b200/ (Python or CUDA) or include/ may import, link or name it, and nothing
+    there may read /root/reference at run time.  bench.py may use the oracle only in its CPU / stock-torch baseline legs."""
+    import re
+
+    offenders = []
+    for base in ("howl_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            if "__pycache__" in dirpath or os.sep + "lib" in dirpath:
+                continue
+            for name in files:
+                if not name.endswith((".py", ".cu", ".cuh", ".h")):
+                    continue
+                text = open(os.path.join(dirpath, name), encoding="utf-8").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|howl_oracle|/root/reference", text, re.M):
+                    offenders.append(os.path.join(dirpath, name))
+    assert not offenders, offenders
+    bench = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
+    uses = [m.start() for m in re.finditer(r"howl_oracle|from oracle", bench)]
+    assert uses, "bench.py's baseline legs are expected to use the oracle port"
+    first_product_fn = bench.index("def make_step(")
+    assert all(u < first_product_fn for u in uses), "the oracle may only appear in the baseline section of bench.py"
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, no CUDA needed."""
+    import subprocess
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "16"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "utterances/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["gpu_launches"] == 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
