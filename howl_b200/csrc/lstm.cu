@@ -2,10 +2,12 @@
 // time-major features, then Linear(128 -> 256) + ReLU + Linear(256 -> L); frame objective (CrossEntropy on dnn(h_n)) and
 // its full backward (BPTT), exact fp32.
 //
-// Recurrence: batch-parallel.  One CTA owns 16 sequences for all time steps; thread j owns gate row j (512 threads):
+// Recurrence: batch-parallel.  One CTA owns 16 sequences for all time steps (512 threads):
 //   gates[b][j] = sum_k Wt[k][j] * xh[b][k],  xh = [x_t (n_mels) | h_{t-1} (128)]
-// with xh in shared memory ([k][16], broadcast 128-bit reads) and the transposed weights streamed from L2 (344 KB per
-// step and CTA, coalesced along j).  The cell update is done by the same 512 threads on (sequence, unit) pairs.  For
+// with xh in shared memory ([k][sequence] tile, broadcast 128-bit reads) and the transposed weights streamed from L2 (344 KB per
+// step and CTA, coalesced along j).  Three engines with the same summation order per output (option "lstm_engine"): 0 = the plain
+// kernels (thread = gate row x 16 sequences); 1 = software pipelined (weights of the next 8 k in a register double buffer, x_{t+1} and
+// the backward's saved tensors fetched a step ahead); 2 (default) = pipelined with a 2 rows x 8 sequences register tile.  The cell update is done by the same 512 threads on (sequence, unit) pairs.  For
 // training the activated gates, cell states and the xh rows are kept in the workspace; the backward walks the steps in
 // reverse (dh through W_hh with a 4-way split of the 512-long reduction) and leaves the pre-activation gradients in
 // place of the gates, so that the weight gradients are tall-skinny A^T B products over all (t, b) rows: on the tensor cores
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_fwd_kernel(const LstmFwdAr
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward recurrence, software pipelined (default, option "lstm_engine" = 1).  Same mapping and the SAME summation order as
+// forward recurrence, software pipelined (option "lstm_engine" = 1, and = 2 with the register tile below).  Same mapping and the SAME summation order as
 // lstm_fwd_kernel above (bit-identical results); what changes is when the data moves:
 //   * the weights of the next 8 k are loaded from L2 while the current 8 are multiplied (register double buffer; the first
 //     batch never changes and stays resident), so the ~300-600 cycle L2 round trip no longer sits in front of every 4 k;
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_bwd_kernel(const LstmBwdAr
 
 
 // ---------------------------------------------------------------------------------------------
-// backward recurrence, software pipelined (default, option "lstm_engine" = 1); same arithmetic and summation order as
+// backward recurrence, software pipelined (option "lstm_engine" = 1 / 2); same arithmetic and summation order as
 // lstm_bwd_kernel.  The saved gates / cell states of step t - 1 are fetched from HBM while step t multiplies (c_t of step t - 1
 // is c_prev of step t: carried in a register), the W_hh rows stream through the register double buffer of the forward, the
 // four partial sums of dh are added by the thread that consumes them (one barrier less per step), [j][sequence] tile padded to 20.
